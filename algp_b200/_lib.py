@@ -1,0 +1,96 @@
+"""ctypes binding of libalgp_b200.so (include/algp_b200.h).
+
+There is NO CPU fallback: if the library is missing the import of any product
+module fails loudly, and every entry point raises on a non-zero status.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libalgp_b200.so")
+
+_p, _i64, _i32, _f64 = C.c_void_p, C.c_int64, C.c_int, C.c_double
+
+# name -> (restype, argtypes); mirrors include/algp_b200.h one to one
+SIGNATURES = {
+    "algp_version": (C.c_int, []),
+    "algp_strerror": (C.c_char_p, [C.c_int]),
+    "algp_last_cuda_error": (C.c_char_p, []),
+    "algp_kbuild": (C.c_int, [_p, _i64, _p, _i64, _i32, _p, _f64, _i32, _p, _f64, _i32,
+                              _p, _i64, _i64, _i64, _i32, _p, _p, _p]),
+    "algp_kbuild_col_tiles": (C.c_int, [_i64, _i32]),
+    "algp_rowsum": (C.c_int, [_p, _i64, _i32, _f64, _f64, _p, _p, _p]),
+    "algp_scatter_add": (C.c_int, [_p, _i64, _p, _i64, _f64, _p]),
+    "algp_potrf": (C.c_int, [_p, _i64, _i64, _p, _i64, _p, _p]),
+    "algp_trtri": (C.c_int, [_p, _i64, _i64, _p, _i64, _p, _i32, _p]),
+    "algp_trtri_work_doubles": (_i64, [_i64]),
+    "algp_gemv_lower": (C.c_int, [_p, _i64, _i64, _p, _p, _p]),
+    "algp_gemv_lower_t": (C.c_int, [_p, _i64, _i64, _p, _p, _p, _p]),
+    "algp_gemv_work_doubles": (_i64, [_i64]),
+    "algp_logdet_sumsq": (C.c_int, [_p, _i64, _i64, _p, _p, _p]),
+    "algp_trmm_rt": (C.c_int, [_p, _i64, _i64, _p, _i64, _i64, _p, _i64, _p, _p]),
+    "algp_gemm_nt": (C.c_int, [_p, _i64, _p, _i64, _p, _i64, _i64, _i64, _i64, _f64, _f64, _i32, _p]),
+    "algp_score_sets": (C.c_int, [_p, _i64, _i64, _p, _i32, _p, _f64, _i32, _f64, _p, _p, _p, _f64,
+                                  _i32, _i64, _f64, _p, _p]),
+    "algp_greedy_utilities": (C.c_int, [_p, _p, _p, _f64, _i64, _p, _p]),
+    "algp_argmax": (C.c_int, [_p, _i64, _i64, _p, _p, _p]),
+    "algp_argmax_work_bytes": (_i64, []),
+    "algp_append": (C.c_int, [_p, _i64, _i64, _p, _i64, _i32, _p, _f64, _i32, _f64, _p, _p, _p, _p, _f64,
+                              _i32, _p, _p]),
+    "algp_append_work_doubles": (_i64, [_i64]),
+}
+
+ERR_NOT_PD = 3
+
+
+class AlgpError(RuntimeError):
+    def __init__(self, fn, code, msg):
+        super().__init__("%s failed: %s (status %d)" % (fn, msg, code))
+        self.code = code
+
+
+def _load():
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            "algp_b200: %s is missing. Build it with `python -m algp_b200.build` (nvcc, sm_100a). "
+            "There is no CPU fallback." % LIB_PATH)
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)          # AttributeError if the header and the library diverge
+        fn.restype = res
+        fn.argtypes = args
+    return lib
+
+
+lib = _load()
+
+
+def check(name, code):
+    if code != 0:
+        msg = lib.algp_strerror(code).decode()
+        if code == 2:
+            msg += ": " + lib.algp_last_cuda_error().decode()
+        raise AlgpError(name, code, msg)
+
+
+def call(name, *args):
+    """Invoke a status-returning entry point and raise on failure."""
+    check(name, getattr(lib, name)(*args))
+
+
+def ptr(t):
+    """Device pointer of a torch tensor (or None)."""
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def host_f64(a):
+    """Host double array argument (hyper-parameters travel on the host)."""
+    a = np.ascontiguousarray(a, dtype=np.float64)
+    return a, a.ctypes.data_as(C.c_void_p)
+
+
+def stream():
+    import torch
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)

@@ -1,0 +1,231 @@
+"""Drop-in for the hot-path methods of the reference's ``Agent`` (agent.py):
+``update_model`` / ``get_sampled_dataset`` (agent.py:84-117), ``_post_update``
+(agent.py:89-90), ``predict`` (agent.py:289-293), ``greedy`` (agent.py:295-356)
+and ``best_path`` (agent.py:358-403).
+
+``HotPath`` holds those methods with the reference's signatures and returns;
+``patch(AgentClass)`` installs them on the reference's own ``Agent`` so that
+``run.py`` / ``agent.py`` run unchanged; ``Agent`` is a self-contained class
+(HotPath + the reference's sample bookkeeping) for use without the reference.
+
+The episode loops (run_ipp, run_greedy_ipp, run_naive, ...) are callers and
+stay in the reference.  The mutual-information criterion (agent.py:330-339)
+is off by default in the reference (run.py:218) and is not accelerated yet:
+it raises NotImplementedError.
+"""
+from copy import deepcopy
+
+import numpy as np
+import torch
+
+from . import engine
+from .models import GPR
+from .utils import predictive_distribution
+
+MAX_SET = 128      # slots per candidate the scoring kernel accepts (algp_score_sets)
+
+
+def _flags(data):
+    return np.array([len(v) > 0 for v in data], dtype=bool)
+
+
+class HotPath(object):
+    """Methods to mix into (or patch onto) an Agent that has ``env`` (``X``, ``test_X``,
+    ``num_samples``), ``gp``, ``static_data``, ``mobile_data``, ``static_std``, ``mobile_std``
+    and ``criterion``."""
+
+    # ---- model / dataset ------------------------------------------------------
+    def update_model(self):
+        indices, y, var = self.get_sampled_dataset()
+        x = self.env.X[indices]
+        self.gp.fit(x, y, var)
+
+    def get_sampled_dataset(self):
+        """agent.py:92-117: inverse-variance fusion of static and mobile readings per location."""
+        ss2, ms2 = self.static_std ** 2, self.mobile_std ** 2
+        all_y, all_var, indices = [], [], []
+        for i in range(self.env.num_samples):
+            has_m, has_s = len(self.mobile_data[i]) > 0, len(self.static_data[i]) > 0
+            if has_m and has_s:
+                yc, ys = np.mean(self.mobile_data[i]), np.mean(self.static_data[i])
+                yeq = (ms2 * ys + ss2 * yc) / (ms2 + ss2)
+                var = 1 / (1 / ss2 + 1 / ms2)
+            elif has_s:
+                yeq, var = np.mean(self.static_data[i]), ss2
+            elif has_m:
+                yeq, var = np.mean(self.mobile_data[i]), ms2
+            else:
+                continue
+            all_y.append(yeq)
+            all_var.append(var)
+            indices.append(i)
+        return indices, np.array(all_y), np.array(all_var)
+
+    def _post_update(self):
+        """agent.py:89-90.  The reference materialises cov_matrix = cov_mat(env.X, add_likelihood_var=True)
+        (n x n) on the host; here the device-side posterior state is what scoring uses, and the host
+        matrix is only built if somebody reads ``self.cov_matrix``."""
+        self._hot_state = None
+        self._hot_cov = None
+        self._hot_X = None
+
+    @property
+    def cov_matrix(self):
+        if getattr(self, "_hot_cov", None) is None:
+            self._hot_cov = self.gp.cov_mat(x1=self.env.X, add_likelihood_var=True)
+        return self._hot_cov
+
+    @cov_matrix.setter
+    def cov_matrix(self, value):
+        self._hot_cov = value
+
+    def predict(self, x=None, return_var=False, return_cov=False, return_mi=False):
+        x = self.env.test_X if x is None else x
+        train_ind, train_y, train_var = self.get_sampled_dataset()
+        train_x = self.env.X[train_ind]
+        return predictive_distribution(self.gp, train_x, train_y, x, train_var, return_var=return_var,
+                                       return_cov=return_cov, return_mi=return_mi)
+
+    # ---- scoring ----------------------------------------------------------------
+    def _device_X(self):
+        if getattr(self, "_hot_X", None) is None:
+            X = np.asarray(self.env.X, dtype=np.float64)
+            if X.ndim == 1:
+                X = X[:, None]
+            self._hot_X = engine.to_dev(X)
+        return self._hot_X
+
+    def _state_for(self, static_sampled, mobile_sampled, capacity):
+        """Posterior state whose base set carries exactly these flags; reused when the cached one
+        (e.g. left by greedy with its picks appended) already matches."""
+        pi = static_sampled / self.static_std ** 2 + mobile_sampled / self.mobile_std ** 2
+        hyper = self.gp.hyper()
+        st = getattr(self, "_hot_state", None)
+        if st is not None and st["hyper"] == hyper.key() and np.array_equal(st["pi"], pi) \
+                and st["state"].ldw - st["state"].ncols >= capacity:
+            return st["state"], pi
+        base = np.nonzero(pi > 0)[0]
+        state = engine.PosteriorState(hyper, self._device_X(), base, pi, is_static=static_sampled, capacity=capacity)
+        self._hot_state = dict(hyper=hyper.key(), pi=pi.copy(), state=state)
+        return state, pi
+
+    def _check_criterion(self):
+        if getattr(self, "criterion", "entropy") == 'mutual_information':
+            raise NotImplementedError("mutual_information scoring is not accelerated yet (SURVEY.md 8f #4)")
+
+    def greedy(self, num_samples):
+        """agent.py:295-356: greedily pick ``num_samples`` static locations by entropy gain."""
+        self._check_criterion()
+        static_sampled, mobile_sampled = _flags(self.static_data), _flags(self.mobile_data)
+        state, pi = self._state_for(static_sampled, mobile_sampled, capacity=num_samples + 16)
+        d = 1.0 / self.static_std ** 2
+        picks = state.greedy(num_samples, d)
+        # keep the cache key in step with the appended picks so best_path can reuse the state
+        pi = self._hot_state["pi"]
+        for j in picks:
+            pi[j] += d
+        return picks
+
+    def best_path(self, paths_mobile_indices, static_indices):
+        """agent.py:358-403: index of the path whose mobile samples maximise the joint entropy."""
+        if len(paths_mobile_indices) == 1:
+            return 0
+        self._check_criterion()
+        static_sampled, org_mobile = _flags(self.static_data), _flags(self.mobile_data)
+        static_sampled[static_indices] = True
+        state, pi = self._state_for(static_sampled, org_mobile, capacity=0)
+        dm = 1.0 / self.mobile_std ** 2
+        # slots: the NEW mobile locations of each path (the mobile flag is boolean: agent.py:377,
+        # so already-mobile locations and repeats add nothing)
+        rows = []
+        for p in paths_mobile_indices:
+            p = np.unique(np.asarray(p, dtype=np.int64).reshape(-1))
+            rows.append(p[~org_mobile[p]])
+        k = max(1, max(len(r) for r in rows))
+        if k > MAX_SET:
+            raise NotImplementedError("paths with more than %d new mobile locations are not supported yet" % MAX_SET)
+        idx = np.full((len(rows), k), -1, dtype=np.int32)
+        for c, r in enumerate(rows):
+            idx[c, :len(r)] = r
+        scores = state.score_sets(engine.to_dev(idx, dtype=torch.int32), None, delta_scalar=dm)
+        pair = state.argmax(scores)
+        return int(pair[1].item())
+
+
+def patch(agent_cls):
+    """Install the accelerated hot path on the reference's Agent class (agent.py:12)."""
+    for name in ("update_model", "get_sampled_dataset", "_post_update", "predict", "greedy", "best_path",
+                 "_device_X", "_state_for", "_check_criterion"):
+        setattr(agent_cls, name, HotPath.__dict__[name])
+    agent_cls.cov_matrix = HotPath.__dict__["cov_matrix"]
+    return agent_cls
+
+
+class Agent(HotPath):
+    """Self-contained agent: the reference's constructor and sample bookkeeping
+    (agent.py:13-82) around the accelerated hot path."""
+
+    def __init__(self, env, args, parent_agent=None, learn_likelihood_noise=True, mobile_std=None, static_std=None):
+        self.env = env
+        self.learn_likelihood_noise = learn_likelihood_noise
+        self._init_model(args)
+        self.static_std = args.static_std if static_std is None else static_std
+        self.mobile_std = 10 * self.static_std if mobile_std is None else mobile_std
+        self.num_samples_per_batch = args.num_samples_per_batch
+        self.update_every = args.update_every
+        self.criterion = 'entropy'
+        self._hot_state = self._hot_cov = self._hot_X = None
+        self.reset()
+        if parent_agent is None:
+            num_pretrain = int(args.fraction_pretrain * self.env.num_samples)
+            self._pre_train(num_samples=num_pretrain)
+        else:
+            self.load_model(parent_agent)
+            self.static_data = deepcopy(parent_agent.static_data)
+            self.mobile_data = deepcopy(parent_agent.mobile_data)
+            self.collected = deepcopy(parent_agent.collected)
+
+    def _init_model(self, args):
+        self.gp = GPR(latent=args.latent, lr=args.lr, max_iterations=args.max_iterations,
+                      kernel_params={'type': args.kernel}, learn_likelihood_noise=self.learn_likelihood_noise)
+
+    def load_model(self, parent_agent):
+        self.gp.reset(parent_agent.gp.train_x, parent_agent.gp.train_y, parent_agent.gp.train_var)
+        self.gp.model.load_state_dict(parent_agent.gp.model.state_dict())
+
+    def save_model(self, filename):
+        torch.save({'state_dict': self.gp.model.state_dict()}, filename)
+
+    def reset(self):
+        n = self.env.num_samples
+        self.pose = (0, 0)
+        self.heading = (1, 0)
+        self.path = np.copy(self.pose).reshape(-1, 2)
+        self.collected = {'ind': [], 'std': [], 'y': []}
+        self.static_locations = np.empty((0, 2))
+        self.static_data = [[] for _ in range(n)]
+        self.mobile_data = [[] for _ in range(n)]
+
+    def _pre_train(self, num_samples):
+        self.pilot_survey(num_samples, self.static_std)
+        self.update_model()
+
+    def pilot_survey(self, num_samples, std):
+        ind = np.random.permutation(self.env.num_samples)[:num_samples]
+        self._add_samples(ind, stds=[std] * num_samples)
+
+    def _add_samples(self, indices, stds):
+        ys = [None] * len(indices)
+        for i, idx in enumerate(indices):
+            if idx == -1:
+                continue
+            ys[i] = self.env.collect_samples(idx, stds[i])
+            (self.static_data if stds[i] == self.static_std else self.mobile_data)[idx].append(ys[i])
+        self.collected['ind'] += list(indices)
+        self.collected['std'] += list(stds)
+        self.collected['y'] += ys
+
+    def _setup_ipp(self, criterion, update=False):
+        assert criterion in ['entropy', 'mutual_information']      # agent.py:128
+        self.criterion = criterion
+        self._post_update()

@@ -1,0 +1,416 @@
+// K2: blocked right-looking Cholesky A = L L^T (fp64), the explicit blocked
+// inverse L^-1, and the O(N^2) solves built on it.
+//
+// Replaces np.linalg.inv(cov_aa) (reference utils.py:300, getrf+getri) and the
+// per-call np.linalg.slogdet (utils.py:193).  Everything is row-major with
+// N padded to a multiple of 128 (identity on the padded diagonal).
+//
+//   potrf : for each 128-wide panel j
+//             potf2inv   one CTA: factor the diagonal block and invert it
+//             panel      P <- P * inv(L_jj)^T            (DMMA GEMM, in place)
+//             syrk       A22 <- A22 - P P^T, lower tiles (DMMA GEMM)
+//   trtri : recursive doubling over block sizes b = 128, 256, ...:
+//             T = L21 * Linv11 ;  Linv21 = -Linv22 * T    (two batched DMMA GEMMs / level)
+//   solves: beta = L^-1 y, alpha = L^-T beta as triangular GEMVs over Linv (HBM bound),
+//           log det A = 2 sum log L_ii.
+#include "gemm.cuh"
+
+// ---------------------------------------------------------------------------
+// GEMM launcher
+// ---------------------------------------------------------------------------
+template <int ALAY, int BLAY>
+static int gemm_launch_t(const GemmArgs& a, int batch, cudaStream_t st) {
+  static bool configured = false;
+  if (!configured) {
+    ALGP_CUDA(cudaFuncSetAttribute(gemm_f64_kernel<ALAY, BLAY>, cudaFuncAttributeMaxDynamicSharedMemorySize, G_SMEM_BYTES));
+    configured = true;
+  }
+  int64_t tiles = (a.tmap == TM_LOWER) ? (int64_t)a.MT * (a.MT + 1) / 2 : (int64_t)a.MT * a.NT;
+  if (tiles <= 0 || batch <= 0) return ALGP_OK;
+  dim3 grid((unsigned)tiles, 1, (unsigned)batch);
+  gemm_f64_kernel<ALAY, BLAY><<<grid, 256, G_SMEM_BYTES, st>>>(a);
+  ALGP_LAUNCH_CHECK();
+  return ALGP_OK;
+}
+
+int gemm_f64_launch(const GemmArgs& a, int alay, int blay, int batch, cudaStream_t st) {
+  if (a.K % GK) return ALGP_ERR_INVALID;
+  if (alay == LAY_KMAJ && blay == LAY_KMAJ) return gemm_launch_t<LAY_KMAJ, LAY_KMAJ>(a, batch, st);
+  if (alay == LAY_KMAJ && blay == LAY_MNMAJ) return gemm_launch_t<LAY_KMAJ, LAY_MNMAJ>(a, batch, st);
+  if (alay == LAY_MNMAJ && blay == LAY_MNMAJ) return gemm_launch_t<LAY_MNMAJ, LAY_MNMAJ>(a, batch, st);
+  return gemm_launch_t<LAY_MNMAJ, LAY_KMAJ>(a, batch, st);
+}
+
+// ---------------------------------------------------------------------------
+// potf2inv: factor one 128x128 diagonal block and invert the factor, one CTA.
+//
+// 256 threads in a 16x16 grid; thread (ty,tx) owns the cyclic 8x8 patch
+// rows ty+16i, cols tx+16j in registers, so every thread stays busy as the
+// active window shrinks.  Phase 1 is an un-normalised elimination (LDL^T
+// style: no sqrt or divide on the column-to-column critical path, one
+// __syncthreads per column through a double-buffered column broadcast);
+// L = Ltilde D^1/2 is formed at the end.  Phase 2 applies the same
+// elimination to the identity to get Ltilde^-1, hence L^-1 = D^-1/2 Ltilde^-1.
+// ---------------------------------------------------------------------------
+#define P2_PITCH 129
+#define P2_SMEM_BYTES ((128 * P2_PITCH + 2 * 128 + 2 * 128 + 3 * 128) * 8)
+
+__global__ void __launch_bounds__(256, 1) potf2inv_kernel(double* __restrict__ A, int64_t ld, double* __restrict__ Linv,
+                                                          int64_t ldi, int j0, int* __restrict__ info) {
+  extern __shared__ __align__(16) double p2_smem[];
+  double* sL = p2_smem;                       // [128][129] unit-lower multipliers
+  double* colbuf = sL + 128 * P2_PITCH;       // [2][128]
+  double* rowbuf = colbuf + 256;              // [2][128]
+  double* pivbuf = rowbuf + 256;              // [128]
+  double* rcpbuf = pivbuf + 128;              // [128] 1/piv
+  double* rsbuf = rcpbuf + 128;               // [128] 1/sqrt(piv)
+
+  const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
+  double acc[8][8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[i][j] = A[(int64_t)(ty + 16 * i) * ld + tx + 16 * j];
+
+  // ---- phase 1: elimination ------------------------------------------------
+  for (int c = 0; c < 128; ++c) {
+    const int jc = c >> 4, txc = c & 15, ic = c >> 4;
+    double* cb = colbuf + (c & 1) * 128;
+    if (tx == txc) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        if (j == jc) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) cb[ty + 16 * i] = acc[i][j];
+        }
+    }
+    __syncthreads();
+    const double piv = cb[c];
+    const bool ok = piv > 0.0;
+    const double rcp = ok ? 1.0 / piv : 0.0;
+    if (tid == 0) {
+      pivbuf[c] = piv;
+      rcpbuf[c] = rcp;
+      rsbuf[c] = ok ? 1.0 / sqrt(piv) : 0.0;
+      if (!ok) atomicCAS(info, 0, j0 + c + 1);
+    }
+    double ri[8], cj[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) ri[i] = (i >= ic && ty + 16 * i > c) ? cb[ty + 16 * i] * rcp : 0.0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) cj[j] = (j >= jc && tx + 16 * j > c) ? cb[tx + 16 * j] : 0.0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+      if (i >= ic) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          if (j >= jc) acc[i][j] = fma(-ri[i], cj[j], acc[i][j]);
+      }
+  }
+  __syncthreads();
+
+  // ---- write L, stash multipliers -------------------------------------------
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int r = ty + 16 * i, c = tx + 16 * j;
+      double l;
+      if (r > c) {
+        l = acc[i][j] * rsbuf[c];
+        sL[r * P2_PITCH + c] = acc[i][j] * rcpbuf[c];
+      } else if (r == c) {
+        l = pivbuf[c] * rsbuf[c];
+      } else {
+        l = 0.0;
+      }
+      A[(int64_t)r * ld + c] = l;
+      acc[i][j] = (r == c) ? 1.0 : 0.0;       // becomes Y = Ltilde^-1
+    }
+  __syncthreads();
+
+  // ---- phase 2: Y <- Ltilde^-1 ----------------------------------------------
+  for (int c = 0; c < 127; ++c) {
+    const int ic = c >> 4, tyc = c & 15, jc = c >> 4;
+    double* rb = rowbuf + (c & 1) * 128;
+    if (ty == tyc) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        if (i == ic) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) rb[tx + 16 * j] = acc[i][j];
+        }
+    }
+    __syncthreads();
+    double ri[8], yj[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) ri[i] = (i >= ic && ty + 16 * i > c) ? sL[(ty + 16 * i) * P2_PITCH + c] : 0.0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) yj[j] = (j <= jc) ? rb[tx + 16 * j] : 0.0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+      if (i >= ic) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          if (j <= jc) acc[i][j] = fma(-ri[i], yj[j], acc[i][j]);
+      }
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int r = ty + 16 * i, c = tx + 16 * j;
+      Linv[(int64_t)r * ldi + c] = (r >= c) ? acc[i][j] * rsbuf[r] : 0.0;
+    }
+}
+
+static int potf2inv_launch(double* A, int64_t ld, double* Linv, int64_t ldi, int j0, int* info, cudaStream_t st) {
+  static bool configured = false;
+  if (!configured) {
+    ALGP_CUDA(cudaFuncSetAttribute(potf2inv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, P2_SMEM_BYTES));
+    configured = true;
+  }
+  potf2inv_kernel<<<1, 256, P2_SMEM_BYTES, st>>>(A, ld, Linv, ldi, j0, info);
+  ALGP_LAUNCH_CHECK();
+  return ALGP_OK;
+}
+
+// ---------------------------------------------------------------------------
+// potrf
+// ---------------------------------------------------------------------------
+extern "C" int algp_potrf(double* A, int64_t npad, int64_t ld, double* Linv, int64_t ldi, int* info_dev, void* stream) {
+  if (!A || !Linv || !info_dev || npad < 0 || npad % ALGP_BLK || ld < npad || ldi < npad || (ld & 1) || (ldi & 1))
+    return ALGP_ERR_INVALID;
+  cudaStream_t st = (cudaStream_t)stream;
+  ALGP_CUDA(cudaMemsetAsync(info_dev, 0, sizeof(int), st));
+  const int nb = (int)(npad / ALGP_BLK);
+  for (int j = 0; j < nb; ++j) {
+    double* Ajj = A + (int64_t)j * ALGP_BLK * (ld + 1);
+    double* Ljj_inv = Linv + (int64_t)j * ALGP_BLK * (ldi + 1);
+    int rc = potf2inv_launch(Ajj, ld, Ljj_inv, ldi, j * ALGP_BLK, info_dev, st);
+    if (rc) return rc;
+    const int rem = nb - 1 - j;
+    if (rem == 0) break;
+    double* panel = A + (int64_t)(j + 1) * ALGP_BLK * ld + (int64_t)j * ALGP_BLK;
+    {  // P <- P * inv(L_jj)^T   (in place: each CTA reads only the rows it writes)
+      GemmArgs g = gemm_args_default();
+      g.A = panel; g.lda = ld;
+      g.B = Ljj_inv; g.ldb = ldi;
+      g.C = panel; g.ldc = ld;
+      g.MT = rem; g.NT = 1; g.K = ALGP_BLK;
+      rc = gemm_f64_launch(g, LAY_KMAJ, LAY_KMAJ, 1, st);
+      if (rc) return rc;
+    }
+    {  // A22 <- A22 - P P^T on the lower tiles
+      GemmArgs g = gemm_args_default();
+      g.A = panel; g.lda = ld;
+      g.B = panel; g.ldb = ld;
+      g.C = A + (int64_t)(j + 1) * ALGP_BLK * (ld + 1); g.ldc = ld;
+      g.MT = rem; g.NT = rem; g.K = ALGP_BLK;
+      g.tmap = TM_LOWER; g.alpha = -1.0; g.beta = 1.0;
+      rc = gemm_f64_launch(g, LAY_KMAJ, LAY_KMAJ, 1, st);
+      if (rc) return rc;
+    }
+  }
+  return ALGP_OK;
+}
+
+// ---------------------------------------------------------------------------
+// trtri: complete Linv (diagonal 128-blocks already hold inv(L_jj)) by
+// recursive doubling.  work: >= npad*npad/4 doubles.
+// ---------------------------------------------------------------------------
+__global__ void zero_upper_blocks_kernel(double* __restrict__ M, int64_t ld, int nb) {
+  // zero the strictly-upper 128x128 blocks so Linv is a clean lower-triangular matrix
+  int bi = blockIdx.y, bj = blockIdx.x;
+  if (bj <= bi) return;
+  double* blk = M + (int64_t)bi * ALGP_BLK * ld + (int64_t)bj * ALGP_BLK;
+  for (int e = threadIdx.x; e < ALGP_BLK * ALGP_BLK / 2; e += blockDim.x) {
+    int r = e / (ALGP_BLK / 2), c2 = (e % (ALGP_BLK / 2)) * 2;
+    *reinterpret_cast<double2*>(blk + (int64_t)r * ld + c2) = make_double2(0.0, 0.0);
+  }
+}
+
+extern "C" int64_t algp_trtri_work_doubles(int64_t npad) {
+  int64_t need = 2;
+  for (int64_t b = ALGP_BLK; b < npad; b *= 2) {
+    int64_t pairs = (npad - b + 2 * b - 1) / (2 * b);
+    if (pairs * b * b > need) need = pairs * b * b;
+  }
+  return need;
+}
+
+extern "C" int algp_trtri(const double* L, int64_t npad, int64_t ld, double* Linv, int64_t ldi, double* work,
+                          int zero_upper, void* stream) {
+  if (!L || !Linv || npad < 0 || npad % ALGP_BLK || ld < npad || ldi < npad || (ld & 1) || (ldi & 1)) return ALGP_ERR_INVALID;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int nb = (int)(npad / ALGP_BLK);
+  if (nb > 1 && !work) return ALGP_ERR_INVALID;
+  if (zero_upper && nb > 1) {
+    zero_upper_blocks_kernel<<<dim3(nb, nb), 256, 0, st>>>(Linv, ldi, nb);
+    ALGP_LAUNCH_CHECK();
+  }
+  for (int64_t b = ALGP_BLK; b < npad; b *= 2) {
+    const int bt = (int)(b / ALGP_BLK);
+    const int pairs = (int)((npad - b + 2 * b - 1) / (2 * b));   // pairs whose second block is non-empty
+    if (pairs <= 0) break;
+    // T_p = L21_p * Linv11_p        (Linv11 lower: k >= n)
+    GemmArgs g = gemm_args_default();
+    g.A = L + b * ld; g.lda = ld; g.a_bs = 2 * b * (ld + 1);
+    g.B = Linv; g.ldb = ldi; g.b_bs = 2 * b * (ldi + 1);
+    g.C = work; g.ldc = b; g.c_bs = b * b;
+    g.MT = bt; g.NT = bt; g.K = (int)b;
+    g.kbeg_rule = KB_NT;
+    g.rows_left0 = npad - b; g.rows_left_bs = 2 * b;
+    int rc = gemm_f64_launch(g, LAY_KMAJ, LAY_MNMAJ, pairs, st);
+    if (rc) return rc;
+    // Linv21_p = -Linv22_p * T_p    (Linv22 lower: k <= m)
+    GemmArgs h = gemm_args_default();
+    h.A = Linv + b * (ldi + 1); h.lda = ldi; h.a_bs = 2 * b * (ldi + 1);
+    h.B = work; h.ldb = b; h.b_bs = b * b;
+    h.C = Linv + b * ldi; h.ldc = ldi; h.c_bs = 2 * b * (ldi + 1);
+    h.MT = bt; h.NT = bt; h.K = (int)b;
+    h.kend_rule = KE_MT1;
+    h.alpha = -1.0;
+    h.rows_left0 = npad - b; h.rows_left_bs = 2 * b;
+    rc = gemm_f64_launch(h, LAY_KMAJ, LAY_MNMAJ, pairs, st);
+    if (rc) return rc;
+  }
+  return ALGP_OK;
+}
+
+// ---------------------------------------------------------------------------
+// triangular GEMVs over a lower-triangular row-major matrix, log-det
+// ---------------------------------------------------------------------------
+// out[r] = sum_{k<=r} M[r][k] v[k] : one warp per row, coalesced along k
+__global__ void gemv_lower_n_kernel(const double* __restrict__ M, int64_t n, int64_t ld, const double* __restrict__ v,
+                                    double* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (r >= n) return;
+  const double* row = M + r * ld;
+  double s0 = 0.0, s1 = 0.0;
+  const int64_t kend = r + 1;
+  int64_t k = 2 * lane;
+  for (; k + 1 < kend; k += 64) {
+    double2 m = *reinterpret_cast<const double2*>(row + k);
+    s0 = fma(m.x, v[k], s0);
+    s1 = fma(m.y, v[k + 1], s1);
+  }
+  if (k < kend) s0 = fma(row[k], v[k], s0);
+  double s = warp_sum(s0 + s1);
+  if (lane == 0) out[r] = s;
+}
+
+// partial[chunk][c] = sum_{r in chunk, r>=c} M[r][c] v[r] : thread per column, rows streamed coalesced
+#define GT_CHUNK 256
+__global__ void gemv_lower_t_kernel(const double* __restrict__ M, int64_t n, int64_t ld, const double* __restrict__ v,
+                                    double* __restrict__ partial) {
+  const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t r0 = (int64_t)blockIdx.y * GT_CHUNK;
+  if (c >= n) return;
+  int64_t rb = r0 > c ? r0 : c;
+  int64_t re = r0 + GT_CHUNK < n ? r0 + GT_CHUNK : n;
+  double s0 = 0.0, s1 = 0.0;
+  int64_t r = rb;
+  for (; r + 1 < re; r += 2) {
+    s0 = fma(M[r * ld + c], v[r], s0);
+    s1 = fma(M[(r + 1) * ld + c], v[r + 1], s1);
+  }
+  if (r < re) s0 = fma(M[r * ld + c], v[r], s0);
+  partial[(int64_t)blockIdx.y * n + c] = s0 + s1;
+}
+
+__global__ void colsum_kernel(const double* __restrict__ partial, int64_t n, int chunks, double* __restrict__ out) {
+  const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= n) return;
+  double s = 0.0;
+  for (int k = 0; k < chunks; ++k) s += partial[(int64_t)k * n + c];
+  out[c] = s;
+}
+
+extern "C" int64_t algp_gemv_work_doubles(int64_t n) { return ((n + GT_CHUNK - 1) / GT_CHUNK) * n; }
+
+// beta = Linv y
+extern "C" int algp_gemv_lower(const double* M, int64_t n, int64_t ld, const double* v, double* out, void* stream) {
+  if (!M || !v || !out || n < 0 || ld < n || (ld & 1)) return ALGP_ERR_INVALID;
+  if (n == 0) return ALGP_OK;
+  gemv_lower_n_kernel<<<(unsigned)((n + 7) / 8), 256, 0, (cudaStream_t)stream>>>(M, n, ld, v, out);
+  ALGP_LAUNCH_CHECK();
+  return ALGP_OK;
+}
+
+// alpha = Linv^T beta ; work >= algp_gemv_work_doubles(n)
+extern "C" int algp_gemv_lower_t(const double* M, int64_t n, int64_t ld, const double* v, double* out, double* work,
+                                 void* stream) {
+  if (!M || !v || !out || !work || n < 0 || ld < n) return ALGP_ERR_INVALID;
+  if (n == 0) return ALGP_OK;
+  const int chunks = (int)((n + GT_CHUNK - 1) / GT_CHUNK);
+  cudaStream_t st = (cudaStream_t)stream;
+  gemv_lower_t_kernel<<<dim3((unsigned)((n + 127) / 128), chunks), 128, 0, st>>>(M, n, ld, v, work);
+  ALGP_LAUNCH_CHECK();
+  colsum_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(work, n, chunks, out);
+  ALGP_LAUNCH_CHECK();
+  return ALGP_OK;
+}
+
+// out[0] = 2 * sum_i log L_ii ; out[1] = sum_i v_i^2 (optional v): fixed-order single-CTA reduction
+__global__ void logdet_sumsq_kernel(const double* __restrict__ L, int64_t n, int64_t ld, const double* __restrict__ v,
+                                    double* __restrict__ out) {
+  __shared__ double s_ld[32], s_sq[32];
+  double a = 0.0, b = 0.0;
+  for (int64_t i = threadIdx.x; i < n; i += blockDim.x) {
+    a += log(L[i * (ld + 1)]);
+    if (v) b = fma(v[i], v[i], b);
+  }
+  a = warp_sum(a);
+  b = warp_sum(b);
+  if ((threadIdx.x & 31) == 0) { s_ld[threadIdx.x >> 5] = a; s_sq[threadIdx.x >> 5] = b; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double ta = 0.0, tb = 0.0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) { ta += s_ld[w]; tb += s_sq[w]; }
+    out[0] = 2.0 * ta;
+    out[1] = tb;
+  }
+}
+
+extern "C" int algp_logdet_sumsq(const double* L, int64_t n, int64_t ld, const double* v, double* out2, void* stream) {
+  if (!L || !out2 || n < 0) return ALGP_ERR_INVALID;
+  logdet_sumsq_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(L, n, ld, v, out2);
+  ALGP_LAUNCH_CHECK();
+  return ALGP_OK;
+}
+
+// ---------------------------------------------------------------------------
+// C-ABI views of the GEMM core used outside this file
+// ---------------------------------------------------------------------------
+// V = Ks * Linv^T restricted to the lower-triangular structure of Linv
+// (C[m][j] = sum_{k < (jt+1)*128} Ks[m][k] Linv[j][k]); optional store of V and
+// optional fused row partials  rn_partial[m][jt] = sum_{j in tile} V[m][j]^2.
+extern "C" int algp_trmm_rt(const double* Ks, int64_t mpad, int64_t ldk, const double* Linv, int64_t npad, int64_t ldi,
+                            double* V, int64_t ldv, double* rn_partial, void* stream) {
+  if (!Ks || !Linv || mpad % ALGP_BLK || npad % ALGP_BLK || ldk < npad || ldi < npad || (ldk & 1) || (ldi & 1)) return ALGP_ERR_INVALID;
+  if (!V && !rn_partial) return ALGP_ERR_INVALID;
+  if (V && (ldv < npad || (ldv & 1))) return ALGP_ERR_INVALID;
+  GemmArgs g = gemm_args_default();
+  g.A = Ks; g.lda = ldk;
+  g.B = Linv; g.ldb = ldi;
+  g.C = V; g.ldc = ldv; g.store_c = V ? 1 : 0;
+  g.MT = (int)(mpad / ALGP_BLK); g.NT = (int)(npad / ALGP_BLK); g.K = (int)npad;
+  g.kend_rule = KE_NT1;
+  g.rn_partial = rn_partial; g.rn_nt = g.NT;
+  return gemm_f64_launch(g, LAY_KMAJ, LAY_KMAJ, 1, (cudaStream_t)stream);
+}
+
+// C = beta*C + alpha * A * B^T, A [mpad x k], B [npad x k] row-major; lower_only: MT == NT, lower tiles only
+extern "C" int algp_gemm_nt(const double* A, int64_t lda, const double* B, int64_t ldb, double* C, int64_t ldc,
+                            int64_t mpad, int64_t npad, int64_t kpad, double alpha, double beta, int lower_only, void* stream) {
+  if (!A || !B || !C || mpad % ALGP_BLK || npad % ALGP_BLK || kpad % GK || (lda & 1) || (ldb & 1) || (ldc & 1)) return ALGP_ERR_INVALID;
+  if (lower_only && mpad != npad) return ALGP_ERR_INVALID;
+  GemmArgs g = gemm_args_default();
+  g.A = A; g.lda = lda; g.B = B; g.ldb = ldb; g.C = C; g.ldc = ldc;
+  g.MT = (int)(mpad / ALGP_BLK); g.NT = (int)(npad / ALGP_BLK); g.K = (int)kpad;
+  g.alpha = alpha; g.beta = beta;
+  g.tmap = lower_only ? TM_LOWER : TM_FULL;
+  return gemm_f64_launch(g, LAY_KMAJ, LAY_KMAJ, 1, (cudaStream_t)stream);
+}

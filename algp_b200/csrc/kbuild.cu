@@ -1,0 +1,236 @@
+// K1: fused kernel-matrix builder.
+//
+// Replaces GPR.cov_mat (reference models.py:161-181): s^2 k(x1,x2) for
+// ScaleKernel(RBF | Matern-1.5) with ARD lengthscales, the optional
+// diag(white_noise_var) and sigma_n^2 I adds fused in (the reference builds
+// them as two extra N x N temporaries, models.py:175-180), the zero /
+// identity padding the blocked factorisation wants, and optionally the
+// row-dot with a vector (mean = K(X*,X) alpha, utils.py:301) so that the
+// matrix is not re-read for the mean.
+//
+// Layout: out is row-major [n1_pad x ld].  A CTA owns a 64 x (128*VEC) tile;
+// each warp a 32-row x (32*VEC)-col strip; a lane keeps the (scaled)
+// coordinates of its VEC consecutive columns in registers, reads the row's
+// coordinates as a shared-memory broadcast, and stores 16 bytes per row, so a
+// warp writes 512 contiguous bytes per row.  HBM-store bound (8 B/element,
+// 4 B in float32 mode) unless the fp64 exp saturates the FP64 pipe first.
+#include "common.cuh"
+
+struct KbuildArgs {
+  KernelParams kp;
+  const double* x1;
+  const double* x2;
+  int64_t n1, n2;           // valid rows / cols
+  int64_t n1_pad, n2_pad;   // written extent (>= n1, n2)
+  const double* diag_add;   // [n1] or null: added where r == c
+  double diag_scalar;       // added where r == c (r < n1)
+  int pad_identity;         // 1: out[r][r] = 1 for r >= n1 (keeps padded factor SPD)
+  void* out;
+  int64_t ld;
+  const double* dot_vec;    // [n2] or null
+  double* dot_partial;      // [n1_pad x n_col_tiles]
+  int n_col_tiles;
+};
+
+template <typename T> struct Vec;
+template <> struct Vec<double> { static constexpr int N = 2; typedef double2 type; };
+template <> struct Vec<float> { static constexpr int N = 4; typedef float4 type; };
+
+template <typename T> __device__ __forceinline__ T kern_eval(T r2, int kind, T os);
+template <> __device__ __forceinline__ double kern_eval<double>(double r2, int kind, double os) { return kern_from_r2(r2, kind, os); }
+template <> __device__ __forceinline__ float kern_eval<float>(float r2, int kind, float os) { return kern_from_r2f(r2, kind, os); }
+
+#define KB_ROWS 64
+
+template <typename T, int D, bool DOT>
+__global__ void __launch_bounds__(256) kbuild_kernel(const KbuildArgs a) {
+  constexpr int VEC = Vec<T>::N;
+  constexpr int TILE_C = 128 * VEC;
+  __shared__ T sx1[KB_ROWS][ALGP_MAX_D];
+  __shared__ T sx2[D == 0 ? ALGP_MAX_D : 1][D == 0 ? TILE_C : 1];
+  __shared__ double sred[KB_ROWS][4];
+
+  const int d = (D == 0) ? a.kp.d : D;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int wr = warp >> 2, wc = warp & 3;
+  const int64_t row0 = (int64_t)blockIdx.y * KB_ROWS;
+  const int64_t col0 = (int64_t)blockIdx.x * TILE_C;
+  const int64_t c0 = col0 + (int64_t)wc * 32 * VEC + lane * VEC;
+
+  // stage the scaled row coordinates (rows past n1 read as 0; masked later)
+  for (int i = tid; i < KB_ROWS * d; i += 256) {
+    int r = i / d, j = i - r * d;
+    int64_t gr = row0 + r;
+    double v = (gr < a.n1) ? a.x1[gr * d + j] : 0.0;
+    sx1[r][j] = (T)((T)v * (T)a.kp.inv_ls[j]);
+  }
+  T x2r[D == 0 ? 1 : VEC][D == 0 ? 1 : D];
+  if (D == 0) {
+    for (int i = tid; i < TILE_C * d; i += 256) {
+      int c = i / d, j = i - c * d;
+      int64_t gc = col0 + c;
+      double v = (gc < a.n2) ? a.x2[gc * d + j] : 0.0;
+      sx2[j][c] = (T)((T)v * (T)a.kp.inv_ls[j]);
+    }
+  } else {
+#pragma unroll
+    for (int v = 0; v < VEC; ++v)
+#pragma unroll
+      for (int j = 0; j < (D == 0 ? 1 : D); ++j) {
+        int64_t gc = c0 + v;
+        double xv = (gc < a.n2) ? a.x2[gc * d + j] : 0.0;
+        x2r[v][j] = (T)((T)xv * (T)a.kp.inv_ls[j]);
+      }
+  }
+  T dv[VEC];
+  if (DOT) {
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) dv[v] = (c0 + v < a.n2) ? (T)a.dot_vec[c0 + v] : (T)0;
+  }
+  __syncthreads();
+
+  const T os = (T)a.kp.outputscale;
+  const int kind = a.kp.kind;
+  const int lc = wc * 32 * VEC + lane * VEC;   // column inside the tile
+  T* outp = (T*)a.out;
+
+  for (int rr = 0; rr < 32; ++rr) {
+    const int r = wr * 32 + rr;
+    const int64_t gr = row0 + r;
+    if (gr >= a.n1_pad) break;                 // warp-uniform
+    T val[VEC];
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) {
+      T r2 = (T)0;
+      if (D == 0) {
+        for (int j = 0; j < d; ++j) {
+          T df = sx1[r][j] - sx2[j][lc + v];
+          r2 += df * df;
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < (D == 0 ? 1 : D); ++j) {
+          T df = sx1[r][j] - x2r[v][j];
+          r2 += df * df;
+        }
+      }
+      T k = kern_eval<T>(r2, kind, os);
+      const int64_t gc = c0 + v;
+      const bool valid = (gr < a.n1) && (gc < a.n2);
+      if (!valid) k = (T)0;
+      if (gr == gc) {
+        if (gr < a.n1) {
+          double add = a.diag_scalar + (a.diag_add ? a.diag_add[gr] : 0.0);
+          k = (T)((double)k + add);
+        } else if (a.pad_identity) {
+          k = (T)1;
+        }
+      }
+      val[v] = k;
+    }
+    if (c0 < a.n2_pad) {
+      typename Vec<T>::type pk;
+#pragma unroll
+      for (int v = 0; v < VEC; ++v) ((T*)&pk)[v] = val[v];
+      *reinterpret_cast<typename Vec<T>::type*>(outp + gr * a.ld + c0) = pk;
+    }
+    if (DOT) {
+      double part = 0.0;
+#pragma unroll
+      for (int v = 0; v < VEC; ++v) part += (double)val[v] * (double)dv[v];
+      part = warp_sum(part);
+      if (lane == 0) sred[r][wc] = part;
+    }
+  }
+  if (DOT) {
+    __syncthreads();
+    if (tid < KB_ROWS) {
+      int64_t gr = row0 + tid;
+      if (gr < a.n1_pad)
+        a.dot_partial[gr * a.n_col_tiles + blockIdx.x] = (sred[tid][0] + sred[tid][1]) + (sred[tid][2] + sred[tid][3]);
+    }
+  }
+}
+
+// out[r] = bias + scale * sum_t partial[r][t]   (fixed order: deterministic)
+__global__ void rowsum_kernel(const double* __restrict__ partial, int64_t rows, int nt, double scale, double bias,
+                              const double* __restrict__ addvec, double* __restrict__ out) {
+  int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= rows) return;
+  double s = 0.0;
+  for (int t = 0; t < nt; ++t) s += partial[r * nt + t];
+  out[r] = bias + scale * s + (addvec ? addvec[r] : 0.0);
+}
+
+// Sigma[loc,B_k] gains sigma_n^2 where field location loc IS base point k
+// (agent.py:90 builds cov_matrix with add_likelihood_var=True, so the noise
+// sits on the n x n diagonal and travels with the (loc, base) gather).
+__global__ void scatter_add_kernel(double* __restrict__ M, int64_t ld, const int32_t* __restrict__ row_of_col, int64_t ncols,
+                                   double v) {
+  int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= ncols) return;
+  int32_t r = row_of_col[k];
+  if (r >= 0) M[(int64_t)r * ld + k] += v;
+}
+
+template <typename T, bool DOT>
+static int launch_kbuild(const KbuildArgs& a, cudaStream_t st) {
+  constexpr int TILE_C = 128 * Vec<T>::N;
+  dim3 grid((unsigned)((a.n2_pad + TILE_C - 1) / TILE_C), (unsigned)((a.n1_pad + KB_ROWS - 1) / KB_ROWS));
+  if (grid.y > 65535) return ALGP_ERR_INVALID;
+  switch (a.kp.d) {
+    case 2: kbuild_kernel<T, 2, DOT><<<grid, 256, 0, st>>>(a); break;
+    case 6: kbuild_kernel<T, 6, DOT><<<grid, 256, 0, st>>>(a); break;
+    default: kbuild_kernel<T, 0, DOT><<<grid, 256, 0, st>>>(a); break;
+  }
+  ALGP_LAUNCH_CHECK();
+  return ALGP_OK;
+}
+
+int make_kernel_params(KernelParams* kp, int d, const double* log_ls_host, double log_os, int kind);
+
+extern "C" int algp_kbuild_col_tiles(int64_t n2_pad, int out_dtype) {
+  int tile = 128 * (out_dtype == 0 ? 2 : 4);
+  return (int)((n2_pad + tile - 1) / tile);
+}
+
+extern "C" int algp_kbuild(const double* x1, int64_t n1, const double* x2, int64_t n2, int d,
+                           const double* log_ls_host, double log_os, int kind,
+                           const double* diag_add, double diag_scalar, int pad_identity,
+                           void* out, int64_t n1_pad, int64_t n2_pad, int64_t ld, int out_dtype,
+                           const double* dot_vec, double* dot_partial, void* stream) {
+  if (!x1 || !out || n1 < 0 || n2 < 0 || n1_pad < n1 || n2_pad < n2 || ld < n2_pad) return ALGP_ERR_INVALID;
+  if (out_dtype != 0 && out_dtype != 1) return ALGP_ERR_INVALID;
+  if ((dot_vec == nullptr) != (dot_partial == nullptr)) return ALGP_ERR_INVALID;
+  // 16-byte row stores: rows must start 16-byte aligned
+  int vec = out_dtype == 0 ? 2 : 4;
+  if (ld % vec || n2_pad % vec || ((uintptr_t)out & 15)) return ALGP_ERR_INVALID;
+  KbuildArgs a;
+  int rc = make_kernel_params(&a.kp, d, log_ls_host, log_os, kind);
+  if (rc) return rc;
+  a.x1 = x1; a.x2 = x2 ? x2 : x1; a.n1 = n1; a.n2 = n2; a.n1_pad = n1_pad; a.n2_pad = n2_pad;
+  a.diag_add = diag_add; a.diag_scalar = diag_scalar; a.pad_identity = pad_identity;
+  a.out = out; a.ld = ld; a.dot_vec = dot_vec; a.dot_partial = dot_partial;
+  a.n_col_tiles = algp_kbuild_col_tiles(n2_pad, out_dtype);
+  if (n1_pad == 0 || n2_pad == 0) return ALGP_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (out_dtype == 0) return dot_vec ? launch_kbuild<double, true>(a, st) : launch_kbuild<double, false>(a, st);
+  return dot_vec ? launch_kbuild<float, true>(a, st) : launch_kbuild<float, false>(a, st);
+}
+
+extern "C" int algp_rowsum(const double* partial, int64_t rows, int nt, double scale, double bias,
+                           const double* addvec, double* out, void* stream) {
+  if (!partial || !out || rows < 0 || nt < 0) return ALGP_ERR_INVALID;
+  if (rows == 0) return ALGP_OK;
+  rowsum_kernel<<<(unsigned)((rows + 255) / 256), 256, 0, (cudaStream_t)stream>>>(partial, rows, nt, scale, bias, addvec, out);
+  ALGP_LAUNCH_CHECK();
+  return ALGP_OK;
+}
+
+extern "C" int algp_scatter_add(double* M, int64_t ld, const int32_t* row_of_col, int64_t ncols, double v, void* stream) {
+  if (!M || !row_of_col || ncols < 0) return ALGP_ERR_INVALID;
+  if (ncols == 0) return ALGP_OK;
+  scatter_add_kernel<<<(unsigned)((ncols + 255) / 256), 256, 0, (cudaStream_t)stream>>>(M, ld, row_of_col, ncols, v);
+  ALGP_LAUNCH_CHECK();
+  return ALGP_OK;
+}

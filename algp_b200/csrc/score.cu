@@ -1,0 +1,462 @@
+// K3 / K5: information-gain scoring of candidate sample sets and paths.
+//
+// Replaces the per-candidate Python loops of Agent.greedy (reference
+// agent.py:313-347) and Agent.best_path (agent.py:373-400), each of which
+// fancy-indexes a fresh (|S|+k)^2 matrix and calls np.linalg.slogdet
+// (utils.py:193).  With the base set factored once (A_B = L L^T) and
+// Wt = Sigma_{:,B} L^-T resident in HBM (location-major: row `loc` holds the
+// N numbers L^-1 Sigma_{B,loc}), a candidate C only needs
+//     G = Wt_C Wt_C^T (k x k Gram over N),  P_CC = Sigma_CC - G,
+//     logdet(I + D P_CC D),  D = diag(sqrt(delta))
+// (SURVEY.md 9.3).  The Gram is one DMMA.8x8x4 per 4 values of N with the SAME
+// register as both operands, fed by 256-bit loads of whole 128-byte lines.
+//
+//   score_sets_k8      one warp per candidate, k <= 8; 8x8 elimination by shuffles
+//   score_sets_generic one CTA per candidate, k <= 128; Gram blocks per warp, elimination in smem
+//   greedy_utilities   k = 1 closed form over all n locations (agent.py:341)
+//   argmax             (max value, then min index) == np.argmax first-max (agent.py:349,402)
+//   append             posterior rank-1 downdate after an acquisition, as one new column of Wt
+#include "common.cuh"
+#include <math.h>
+
+#define ALGP_CONST 1.4189385332046727   // 0.5*log(2*pi*e), utils.py:10
+
+struct ScoreArgs {
+  KernelParams kp;
+  double noise;            // sigma_n^2 (on the diagonal of Sigma, agent.py:90)
+  const double* Wt;        // [n x ldw]
+  int64_t ldw;
+  int ncols16;             // number of valid Wt columns rounded up to 16 (tail columns are zero)
+  const double* X;         // [n x d] field coordinates
+  const double* pi0;       // [n] base precisions (0 = unsampled)
+  const int32_t* idx;      // [B x k]   (-1 = empty slot)
+  const double* delta;     // [B x k] or null
+  double delta_scalar;
+  int k;
+  int64_t B;
+  double H_base;
+  double* scores;          // [B]
+};
+
+__device__ __forceinline__ void ld256(const double* p, double& a, double& b, double& c, double& d) {
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(a), "=d"(b), "=d"(c), "=d"(d) : "l"(p));
+}
+__device__ __forceinline__ void ld256_l1(const double* p, double& a, double& b, double& c, double& d) {
+  asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(a), "=d"(b), "=d"(c), "=d"(d) : "l"(p));
+}
+
+// ---------------------------------------------------------------------------
+// k <= 8: one warp per candidate
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) score_sets_k8_kernel(const ScoreArgs a) {
+  const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  const int d = a.kp.d;
+
+  for (int64_t cand = warp0; cand < a.B; cand += nwarps) {
+    // slot g of this candidate (4 lanes per slot)
+    int my_idx = (g < a.k) ? a.idx[cand * a.k + g] : -1;
+    double my_delta = (g < a.k) ? (a.delta ? a.delta[cand * a.k + g] : a.delta_scalar) : 0.0;
+    bool active = (my_idx >= 0) && (my_delta > 0.0);
+    // duplicates inside a set are idempotent (agent.py:377): keep the first
+#pragma unroll
+    for (int s = 0; s < 7; ++s) {
+      int o_idx = __shfl_sync(0xffffffffu, my_idx, 4 * s);
+      int o_act = __shfl_sync(0xffffffffu, (int)active, 4 * s);
+      if (s < g && o_act && o_idx == my_idx) active = false;
+    }
+    const double* row = a.Wt + (int64_t)(active ? my_idx : 0) * a.ldw + 4 * t;
+
+    double c0[4], c1[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) c0[q] = c1[q] = 0.0;
+    int k0 = 0;
+    // empty / duplicate slots issue no loads; the MMA itself is warp-wide
+    for (; k0 + 32 <= a.ncols16; k0 += 32) {
+      double v[8];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) v[q] = 0.0;
+      if (active) {
+        ld256(row + k0, v[0], v[1], v[2], v[3]);
+        ld256(row + k0 + 16, v[4], v[5], v[6], v[7]);
+      }
+#pragma unroll
+      for (int q = 0; q < 8; ++q) dmma884(c0[q & 3], c1[q & 3], v[q], v[q]);
+    }
+    for (; k0 < a.ncols16; k0 += 16) {
+      double v[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) v[q] = 0.0;
+      if (active) ld256(row + k0, v[0], v[1], v[2], v[3]);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) dmma884(c0[q], c1[q], v[q], v[q]);
+    }
+    const double G0 = (c0[0] + c0[1]) + (c0[2] + c0[3]);   // G[g][2t]
+    const double G1 = (c1[0] + c1[1]) + (c1[2] + c1[3]);   // G[g][2t+1]
+
+    // Sigma_CC from coordinates: lane needs x of slot g (row) and slots 2t, 2t+1 (cols)
+    double r2a = 0.0, r2b = 0.0;
+    for (int j = 0; j < d; ++j) {
+      double xg = (my_idx >= 0) ? a.X[(int64_t)my_idx * d + j] * a.kp.inv_ls[j] : 0.0;
+      double xa = __shfl_sync(0xffffffffu, xg, 4 * (2 * t));
+      double xb = __shfl_sync(0xffffffffu, xg, 4 * (2 * t + 1));
+      r2a = fma(xg - xa, xg - xa, r2a);
+      r2b = fma(xg - xb, xg - xb, r2b);
+    }
+    const double sq = active ? sqrt(my_delta) : 0.0;
+    const double sqa = __shfl_sync(0xffffffffu, sq, 4 * (2 * t));
+    const double sqb = __shfl_sync(0xffffffffu, sq, 4 * (2 * t + 1));
+    double m0 = (kern_from_r2(r2a, a.kp.kind, a.kp.outputscale) + ((g == 2 * t) ? a.noise : 0.0) - G0) * sq * sqa;
+    double m1 = (kern_from_r2(r2b, a.kp.kind, a.kp.outputscale) + ((g == 2 * t + 1) ? a.noise : 0.0) - G1) * sq * sqb;
+    if (g == 2 * t) m0 += 1.0;
+    if (g == 2 * t + 1) m1 += 1.0;
+
+    // 8x8 un-normalised elimination; element (i,j) lives in lane 4i + (j>>1), register j&1
+    double logdet = 0.0;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      const double src = (c & 1) ? m1 : m0;
+      const double piv = __shfl_sync(0xffffffffu, src, 4 * c + (c >> 1));
+      const double lic = __shfl_sync(0xffffffffu, src, 4 * g + (c >> 1));
+      const double lj0 = __shfl_sync(0xffffffffu, src, 4 * (2 * t) + (c >> 1));
+      const double lj1 = __shfl_sync(0xffffffffu, src, 4 * (2 * t + 1) + (c >> 1));
+      const double f = lic / piv;
+      if (g > c) {
+        if (2 * t > c) m0 = fma(-f, lj0, m0);
+        if (2 * t + 1 > c) m1 = fma(-f, lj1, m1);
+      }
+      logdet += log(piv);
+    }
+
+    // size / precision bookkeeping
+    double term = 0.0, nnew = 0.0;
+    if (t == 0 && active) {
+      const double p0 = a.pi0[my_idx];
+      term = log(p0 + my_delta) - (p0 > 0.0 ? log(p0) : 0.0);
+      nnew = (p0 > 0.0) ? 0.0 : 1.0;
+    }
+#pragma unroll
+    for (int o = 4; o < 32; o <<= 1) {
+      term += __shfl_xor_sync(0xffffffffu, term, o);
+      nnew += __shfl_xor_sync(0xffffffffu, nnew, o);
+    }
+    if (lane == 0) a.scores[cand] = a.H_base + nnew * ALGP_CONST + 0.5 * (logdet - term);
+  }
+}
+
+// ---------------------------------------------------------------------------
+// k <= 128: one CTA per candidate
+// ---------------------------------------------------------------------------
+#define SG_MAXK 128
+__global__ void __launch_bounds__(256) score_sets_generic_kernel(const ScoreArgs a) {
+  extern __shared__ __align__(16) double sg_smem[];
+  const int k = a.k;
+  const int kp = (k + 7) >> 3, kk = kp * 8, pitch = kk + 1;
+  double* M = sg_smem;                       // [kk][kk+1]
+  double* sqd = M + kk * pitch;              // [kk] sqrt(delta) or 0
+  double* sx = sqd + kk;                     // [kk][d] scaled coordinates
+  int* sidx = (int*)(sx + kk * a.kp.d);      // [kk]
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, t = lane & 3;
+  const int d = a.kp.d;
+
+  for (int64_t cand = blockIdx.x; cand < a.B; cand += gridDim.x) {
+    __syncthreads();
+    for (int s = tid; s < kk; s += 256) {
+      int ix = (s < k) ? a.idx[cand * k + s] : -1;
+      double dl = (s < k) ? (a.delta ? a.delta[cand * k + s] : a.delta_scalar) : 0.0;
+      bool act = ix >= 0 && dl > 0.0;
+      for (int q = 0; q < s && act; ++q) {
+        int oix = a.idx[cand * k + q];
+        double odl = a.delta ? a.delta[cand * k + q] : a.delta_scalar;
+        if (oix == ix && odl > 0.0) act = false;
+      }
+      sidx[s] = act ? ix : -1;
+      sqd[s] = act ? sqrt(dl) : 0.0;
+      for (int j = 0; j < d; ++j) sx[s * d + j] = act ? a.X[(int64_t)ix * d + j] * a.kp.inv_ls[j] : 0.0;
+    }
+    __syncthreads();
+
+    const int npairs = kp * (kp + 1) / 2;
+    for (int pr = warp; pr < npairs; pr += 8) {
+      int bi = (int)((sqrtf(8.0f * pr + 1.0f) - 1.0f) * 0.5f);
+      while ((bi + 1) * (bi + 2) / 2 <= pr) ++bi;
+      while (bi * (bi + 1) / 2 > pr) --bi;
+      const int bj = pr - bi * (bi + 1) / 2;
+      const int ia = sidx[bi * 8 + g], ib = sidx[bj * 8 + g];
+      const double* ra = a.Wt + (int64_t)(ia >= 0 ? ia : 0) * a.ldw + 4 * t;
+      const double* rb = a.Wt + (int64_t)(ib >= 0 ? ib : 0) * a.ldw + 4 * t;
+      double c0[4], c1[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) c0[q] = c1[q] = 0.0;
+      for (int k0 = 0; k0 < a.ncols16; k0 += 16) {
+        double va[4], vb[4];
+        ld256_l1(ra + k0, va[0], va[1], va[2], va[3]);
+        ld256_l1(rb + k0, vb[0], vb[1], vb[2], vb[3]);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) dmma884(c0[q], c1[q], ia >= 0 ? va[q] : 0.0, ib >= 0 ? vb[q] : 0.0);
+      }
+      const double G0 = (c0[0] + c0[1]) + (c0[2] + c0[3]);
+      const double G1 = (c1[0] + c1[1]) + (c1[2] + c1[3]);
+      const int r = bi * 8 + g;
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int c = bj * 8 + 2 * t + e;
+        double r2 = 0.0;
+        for (int j = 0; j < d; ++j) {
+          double df = sx[r * d + j] - sx[c * d + j];
+          r2 = fma(df, df, r2);
+        }
+        double kv = kern_from_r2(r2, a.kp.kind, a.kp.outputscale) + ((r == c) ? a.noise : 0.0);
+        double m = (kv - (e ? G1 : G0)) * sqd[r] * sqd[c] + ((r == c) ? 1.0 : 0.0);
+        M[r * pitch + c] = m;
+      }
+    }
+    __syncthreads();
+
+    // un-normalised elimination on the lower triangle of M
+    double logdet = 0.0;
+    for (int c = 0; c < kk; ++c) {
+      const double piv = M[c * pitch + c];
+      const double inv = 1.0 / piv;
+      if (tid == 0) logdet += log(piv);
+      const int rem = kk - 1 - c;
+      for (int e = tid; e < rem * rem; e += 256) {
+        const int r = c + 1 + e / rem, cc = c + 1 + e % rem;
+        if (cc <= r) M[r * pitch + cc] = fma(-M[r * pitch + c] * inv, M[cc * pitch + c], M[r * pitch + cc]);
+      }
+      __syncthreads();
+    }
+    // bookkeeping
+    double term = 0.0, nnew = 0.0;
+    for (int s = tid; s < kk; s += 256)
+      if (sidx[s] >= 0) {
+        const double p0 = a.pi0[sidx[s]];
+        const double dl = sqd[s] * sqd[s];
+        term += log(p0 + dl) - (p0 > 0.0 ? log(p0) : 0.0);
+        nnew += (p0 > 0.0) ? 0.0 : 1.0;
+      }
+    // k <= 128 < 256 threads: a single pass of warp sums through shared memory
+    term = warp_sum(term);
+    nnew = warp_sum(nnew);
+    __shared__ double s_t[8], s_n[8];
+    if (lane == 0) { s_t[warp] = term; s_n[warp] = nnew; }
+    __syncthreads();
+    if (tid == 0) {
+      double tt = 0.0, nn = 0.0;
+      for (int w = 0; w < 8; ++w) { tt += s_t[w]; nn += s_n[w]; }
+      a.scores[cand] = a.H_base + nn * ALGP_CONST + 0.5 * (logdet - tt);
+    }
+  }
+}
+
+int make_kernel_params(KernelParams* kp, int d, const double* log_ls_host, double log_os, int kind);
+
+extern "C" int algp_score_sets(const double* Wt, int64_t ldw, int64_t ncols, const double* X, int d,
+                               const double* log_ls_host, double log_os, int kind, double noise,
+                               const double* pi0, const int32_t* idx, const double* delta, double delta_scalar,
+                               int k, int64_t B, double H_base, double* scores, void* stream) {
+  if (!Wt || !X || !pi0 || !idx || !scores || k < 1 || k > SG_MAXK || B < 0 || ncols < 0) return ALGP_ERR_INVALID;
+  if ((ldw & 3) || ((uintptr_t)Wt & 31)) return ALGP_ERR_INVALID;       // 256-bit row loads
+  ScoreArgs a;
+  int rc = make_kernel_params(&a.kp, d, log_ls_host, log_os, kind);
+  if (rc) return rc;
+  a.noise = noise; a.Wt = Wt; a.ldw = ldw;
+  a.ncols16 = (int)((ncols + 15) / 16 * 16);
+  if (a.ncols16 > ldw) return ALGP_ERR_INVALID;
+  a.X = X; a.pi0 = pi0; a.idx = idx; a.delta = delta; a.delta_scalar = delta_scalar;
+  a.k = k; a.B = B; a.H_base = H_base; a.scores = scores;
+  if (B == 0) return ALGP_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  if (k <= 8) {
+    // persistent: 8 CTAs of 8 warps per SM, warps stride over the candidates
+    int64_t want = (B + 7) / 8;
+    int grid = (int)(want < (int64_t)sms * 8 ? want : (int64_t)sms * 8);
+    score_sets_k8_kernel<<<grid, 256, 0, st>>>(a);
+  } else {
+    const int kp = (k + 7) / 8, kk = kp * 8;
+    size_t smem = ((size_t)kk * (kk + 1) + kk + (size_t)kk * d) * 8 + (size_t)kk * 4 + 16;
+    static size_t configured = 0;
+    if (smem > configured) {
+      ALGP_CUDA(cudaFuncSetAttribute(score_sets_generic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      configured = smem;
+    }
+    int grid = (int)(B < (int64_t)sms * 2 ? B : (int64_t)sms * 2);
+    score_sets_generic_kernel<<<grid, 256, smem, st>>>(a);
+  }
+  ALGP_LAUNCH_CHECK();
+  return ALGP_OK;
+}
+
+// ---------------------------------------------------------------------------
+// greedy (k = 1) utilities, argmax, rank-1 append
+// ---------------------------------------------------------------------------
+// entropy criterion, agent.py:341 with the restructuring of SURVEY.md 9.3:
+// ut_i = [pi_i == 0]*CONST + 0.5*(log1p(dS*P_ii) - log(pi_i + dS) + [pi_i > 0] log pi_i);  -inf where already static
+__global__ void greedy_utilities_kernel(const double* __restrict__ diagP, const double* __restrict__ pi,
+                                        const uint8_t* __restrict__ is_static, double d_static, int64_t n,
+                                        double* __restrict__ ut) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double u;
+  if (is_static[i]) {
+    u = -INFINITY;
+  } else {
+    const double p = pi[i];
+    u = (p > 0.0 ? 0.0 : ALGP_CONST) + 0.5 * (log1p(d_static * diagP[i]) - log(p + d_static) + (p > 0.0 ? log(p) : 0.0));
+  }
+  ut[i] = u;
+}
+
+struct ArgPair { double v; long long i; };
+
+__device__ __forceinline__ bool arg_better(double v, long long i, double bv, long long bi) {
+  return (v > bv) || (v == bv && i < bi);
+}
+
+__global__ void argmax_stage1_kernel(const double* __restrict__ x, int64_t n, int64_t idx_offset, ArgPair* __restrict__ part) {
+  __shared__ double sv[32];
+  __shared__ long long si[32];
+  double bv = -INFINITY;
+  long long bi = 0x7fffffffffffffffLL;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    double v = x[i];
+    if (arg_better(v, i + idx_offset, bv, bi)) { bv = v; bi = i + idx_offset; }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    double ov = __shfl_xor_sync(0xffffffffu, bv, o);
+    long long oi = __shfl_xor_sync(0xffffffffu, bi, o);
+    if (arg_better(ov, oi, bv, bi)) { bv = ov; bi = oi; }
+  }
+  if ((threadIdx.x & 31) == 0) { sv[threadIdx.x >> 5] = bv; si[threadIdx.x >> 5] = bi; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < (int)(blockDim.x >> 5); ++w)
+      if (arg_better(sv[w], si[w], bv, bi)) { bv = sv[w]; bi = si[w]; }
+    part[blockIdx.x].v = bv;
+    part[blockIdx.x].i = bi;
+  }
+}
+
+__global__ void argmax_stage2_kernel(const ArgPair* __restrict__ part, int np, ArgPair* __restrict__ out) {
+  double bv = -INFINITY;
+  long long bi = 0x7fffffffffffffffLL;
+  for (int p = threadIdx.x; p < np; p += 32)
+    if (arg_better(part[p].v, part[p].i, bv, bi)) { bv = part[p].v; bi = part[p].i; }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    double ov = __shfl_xor_sync(0xffffffffu, bv, o);
+    long long oi = __shfl_xor_sync(0xffffffffu, bi, o);
+    if (arg_better(ov, oi, bv, bi)) { bv = ov; bi = oi; }
+  }
+  if (threadIdx.x == 0) { out->v = bv; out->i = bi; }
+}
+
+#define ARGMAX_BLOCKS 148
+extern "C" int64_t algp_argmax_work_bytes(void) { return (int64_t)ARGMAX_BLOCKS * sizeof(ArgPair); }
+
+// out_pair: {double value; int64 index} on the device; index = position + idx_offset (global id of a shard)
+extern "C" int algp_argmax(const double* x, int64_t n, int64_t idx_offset, void* out_pair, void* work, void* stream) {
+  if (!x || !out_pair || !work || n <= 0) return ALGP_ERR_INVALID;
+  cudaStream_t st = (cudaStream_t)stream;
+  int blocks = (int)((n + 255) / 256 < ARGMAX_BLOCKS ? (n + 255) / 256 : ARGMAX_BLOCKS);
+  argmax_stage1_kernel<<<blocks, 256, 0, st>>>(x, n, idx_offset, (ArgPair*)work);
+  ALGP_LAUNCH_CHECK();
+  argmax_stage2_kernel<<<1, 32, 0, st>>>((const ArgPair*)work, blocks, (ArgPair*)out_pair);
+  ALGP_LAUNCH_CHECK();
+  return ALGP_OK;
+}
+
+extern "C" int algp_greedy_utilities(const double* diagP, const double* pi, const uint8_t* is_static, double d_static,
+                                     int64_t n, double* ut, void* stream) {
+  if (!diagP || !pi || !is_static || !ut || n < 0) return ALGP_ERR_INVALID;
+  if (n == 0) return ALGP_OK;
+  greedy_utilities_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(diagP, pi, is_static, d_static, n, ut);
+  ALGP_LAUNCH_CHECK();
+  return ALGP_OK;
+}
+
+// append: P <- P - P_:j P_j: / (P_jj + 1/delta) expressed as one new column of Wt:
+//   w_loc = (Sigma[loc,j] - Wt[loc,:ncols] . Wt[j,:ncols]) / sqrt(P_jj + 1/delta),  diagP[loc] -= w_loc^2
+struct AppendArgs {
+  KernelParams kp;
+  double noise;
+  double* Wt; int64_t ldw; int ncols;      // current number of columns; the new one is written at column ncols
+  const double* X; int64_t n;
+  double* diagP; double* pi; uint8_t* is_static;
+  const long long* j_dev;                  // chosen location (device scalar, e.g. the index of an ArgPair)
+  double delta; int mark_static;
+  double* scratch;                         // [2]: denom, (unused)
+};
+
+__global__ void append_prepare_kernel(const AppendArgs a) {
+  const long long j = *a.j_dev;
+  a.scratch[0] = sqrt(a.diagP[j] + 1.0 / a.delta);
+  a.pi[j] += a.delta;
+  if (a.mark_static) a.is_static[j] = 1;
+}
+
+__global__ void __launch_bounds__(256) append_column_kernel(const AppendArgs a) {
+  const int lane = threadIdx.x & 31;
+  const int64_t loc = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (loc >= a.n) return;
+  const long long j = *a.j_dev;
+  const double* rl = a.Wt + loc * a.ldw;
+  const double* rj = a.Wt + (int64_t)j * a.ldw;
+  double s0 = 0.0, s1 = 0.0;
+  int k = 2 * lane;
+  for (; k + 1 < a.ncols; k += 64) {
+    double2 x = *reinterpret_cast<const double2*>(rl + k);
+    double2 y = *reinterpret_cast<const double2*>(rj + k);
+    s0 = fma(x.x, y.x, s0);
+    s1 = fma(x.y, y.y, s1);
+  }
+  if (k < a.ncols) s0 = fma(rl[k], rj[k], s0);
+  const double dot = warp_sum(s0 + s1);
+  if (lane == 0) {
+    const int d = a.kp.d;
+    double r2 = 0.0;
+    for (int q = 0; q < d; ++q) {
+      double df = (a.X[loc * d + q] - a.X[(int64_t)j * d + q]) * a.kp.inv_ls[q];
+      r2 = fma(df, df, r2);
+    }
+    double sig = kern_from_r2(r2, a.kp.kind, a.kp.outputscale) + ((loc == j) ? a.noise : 0.0);
+    double w = (sig - dot) / a.scratch[0];
+    a.scratch[2 + loc] = w;                // staged: row j of Wt is still being read by other warps
+    a.diagP[loc] -= w * w;
+  }
+}
+
+__global__ void append_commit_kernel(double* __restrict__ Wt, int64_t ldw, int col, const double* __restrict__ w, int64_t n) {
+  const int64_t loc = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (loc < n) Wt[loc * ldw + col] = w[loc];
+}
+
+extern "C" int64_t algp_append_work_doubles(int64_t n) { return n + 2; }
+
+extern "C" int algp_append(double* Wt, int64_t ldw, int64_t ncols, const double* X, int64_t n, int d,
+                           const double* log_ls_host, double log_os, int kind, double noise,
+                           double* diagP, double* pi, uint8_t* is_static, const void* j_dev, double delta,
+                           int mark_static, double* work, void* stream) {
+  if (!Wt || !X || !diagP || !pi || !is_static || !j_dev || !work || ncols < 0 || ncols >= ldw || (ldw & 1) || !(delta > 0.0)) return ALGP_ERR_INVALID;
+  AppendArgs a;
+  int rc = make_kernel_params(&a.kp, d, log_ls_host, log_os, kind);
+  if (rc) return rc;
+  a.noise = noise; a.Wt = Wt; a.ldw = ldw; a.ncols = (int)ncols; a.X = X; a.n = n;
+  a.diagP = diagP; a.pi = pi; a.is_static = is_static; a.j_dev = (const long long*)j_dev;
+  a.delta = delta; a.mark_static = mark_static; a.scratch = work;
+  if (n == 0) return ALGP_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  append_prepare_kernel<<<1, 1, 0, st>>>(a);
+  ALGP_LAUNCH_CHECK();
+  append_column_kernel<<<(unsigned)((n + 7) / 8), 256, 0, st>>>(a);
+  ALGP_LAUNCH_CHECK();
+  append_commit_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(Wt, ldw, (int)ncols, work + 2, n);
+  ALGP_LAUNCH_CHECK();
+  return ALGP_OK;
+}

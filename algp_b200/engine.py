@@ -1,0 +1,319 @@
+"""Device-resident building blocks behind the reference-facing API.
+
+``GPFactor``       A = s^2 k(X,X) + diag(var) + sigma_n^2 I = L L^T with L^-1: everything
+                   ``predictive_distribution`` (reference utils.py:293-319) needs.
+``PosteriorState`` the factored base set plus Wt = Sigma_{:,B} L^-T and diag(P): everything
+                   ``Agent.greedy`` / ``Agent.best_path`` (agent.py:295-403) need.
+
+PyTorch owns the memory and the stream; all arithmetic is in libalgp_b200.so
+(hand-written sm_100a kernels, include/algp_b200.h).  No CPU fallback.
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import call, ptr, stream
+
+BLK = 128
+CONST = 0.5 * np.log(2 * np.pi * np.exp(1))        # utils.py:10
+KIND = {"rbf": 0, None: 0, "matern": 1}
+
+
+def pad_to(n, m=BLK):
+    return (int(n) + m - 1) // m * m
+
+
+def require_cuda():
+    if not torch.cuda.is_available():
+        raise RuntimeError("algp_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+    return torch.device("cuda", torch.cuda.current_device())
+
+
+class Hyper(object):
+    """theta as the reference stores it (logs; run.py:36-37, models.py:180)."""
+
+    def __init__(self, log_lengthscale, log_outputscale, log_noise, kind="rbf"):
+        self.log_ls = np.ascontiguousarray(np.asarray(log_lengthscale, dtype=np.float64).reshape(-1))
+        self.log_os = float(log_outputscale)
+        self.log_noise = float(log_noise)
+        if kind not in KIND:
+            raise NotImplementedError(kind)         # models.py:226-227
+        self.kind = KIND[kind]
+        self.kind_name = "rbf" if self.kind == 0 else "matern"
+
+    @property
+    def d(self):
+        return self.log_ls.shape[0]
+
+    @property
+    def outputscale(self):
+        return float(np.exp(self.log_os))
+
+    @property
+    def noise(self):
+        return float(np.exp(self.log_noise))
+
+    def key(self):
+        return (self.log_ls.tobytes(), self.log_os, self.log_noise, self.kind)
+
+
+def to_dev(a, dtype=torch.float64, device=None):
+    """Host array -> device tensor through pinned memory (or pass a device tensor through)."""
+    device = device or require_cuda()
+    if isinstance(a, torch.Tensor):
+        return a.to(device=device, dtype=dtype).contiguous()
+    a = np.ascontiguousarray(a)
+    t = torch.from_numpy(a)
+    if t.dtype != dtype:
+        t = t.to(dtype)
+    return t.pin_memory().to(device, non_blocking=True)
+
+
+def kbuild(hyper, x1, x2=None, n1_pad=None, n2_pad=None, diag_add=None, diag_scalar=0.0, pad_identity=False,
+           out=None, dtype=torch.float64, dot_vec=None):
+    """GPR.cov_mat on the device (models.py:161-181).  Returns (out, dot_partial|None)."""
+    n1, d = x1.shape
+    n2 = n1 if x2 is None else x2.shape[0]
+    if d != hyper.d:
+        raise ValueError("x has %d dims, hyper-parameters have %d" % (d, hyper.d))
+    n1_pad = n1 if n1_pad is None else n1_pad
+    vec = 2 if dtype == torch.float64 else 4
+    n2_pad = pad_to(n2, vec) if n2_pad is None else n2_pad
+    if out is None:
+        out = torch.empty((n1_pad, n2_pad), dtype=dtype, device=x1.device)
+    ld = out.stride(0)
+    partial = None
+    odt = 0 if dtype == torch.float64 else 1
+    if dot_vec is not None:
+        nt = _lib.lib.algp_kbuild_col_tiles(n2_pad, odt)
+        partial = torch.empty((n1_pad, nt), dtype=torch.float64, device=x1.device)
+    ls, ls_p = _lib.host_f64(hyper.log_ls)
+    call("algp_kbuild", ptr(x1), n1, ptr(x2), n2, d, ls_p, hyper.log_os, hyper.kind,
+         ptr(diag_add), float(diag_scalar), int(bool(pad_identity)),
+         ptr(out), n1_pad, n2_pad, ld, odt, ptr(dot_vec), ptr(partial), stream())
+    return out, partial
+
+
+def rowsum(partial, scale=1.0, bias=0.0, addvec=None, rows=None):
+    rows = partial.shape[0] if rows is None else rows
+    out = torch.empty(rows, dtype=torch.float64, device=partial.device)
+    call("algp_rowsum", ptr(partial), rows, partial.shape[1], float(scale), float(bias), ptr(addvec), ptr(out), stream())
+    return out
+
+
+class GPFactor(object):
+    """Cholesky factor and explicit inverse factor of the training covariance."""
+
+    def __init__(self, hyper, x, diag_add=None, diag_scalar=None, keep_linv=True):
+        self.hyper = hyper
+        self.x = x
+        self.N = x.shape[0]
+        self.Npad = max(BLK, pad_to(self.N))
+        dev = x.device
+        if diag_scalar is None:
+            diag_scalar = hyper.noise                       # add_likelihood_var=True, models.py:179-180
+        self.L, _ = kbuild(hyper, x, None, self.Npad, self.Npad, diag_add, diag_scalar, True)
+        self.Linv = torch.empty((self.Npad, self.Npad), dtype=torch.float64, device=dev)
+        self.info = torch.zeros(1, dtype=torch.int32, device=dev)
+        call("algp_potrf", ptr(self.L), self.Npad, self.Npad, ptr(self.Linv), self.Npad, ptr(self.info), stream())
+        nwork = _lib.lib.algp_trtri_work_doubles(self.Npad)
+        work = torch.empty(max(2, nwork), dtype=torch.float64, device=dev)
+        call("algp_trtri", ptr(self.L), self.Npad, self.Npad, ptr(self.Linv), self.Npad, ptr(work), 1, stream())
+        del work
+        self._ld2 = None
+
+    def check(self):
+        """Raise if the matrix was not positive definite (one 4-byte D2H; synchronises)."""
+        info = int(self.info.item())
+        if info != 0:
+            raise np.linalg.LinAlgError("Matrix is not positive definite (leading minor of order %d)" % info)
+
+    def logdet_quad(self, beta=None):
+        """tensor([log det A, |beta|^2]) on the device."""
+        out = torch.empty(2, dtype=torch.float64, device=self.L.device)
+        call("algp_logdet_sumsq", ptr(self.L), self.Npad, self.Npad, ptr(beta), ptr(out), stream())
+        return out
+
+    def solve(self, y0):
+        """alpha = A^-1 y0 (and beta = L^-1 y0) for a length-N device vector."""
+        dev = self.L.device
+        yp = torch.zeros(self.Npad, dtype=torch.float64, device=dev)
+        yp[:self.N] = y0
+        beta = torch.empty_like(yp)
+        alpha = torch.empty_like(yp)
+        call("algp_gemv_lower", ptr(self.Linv), self.Npad, self.Npad, ptr(yp), ptr(beta), stream())
+        work = torch.empty(_lib.lib.algp_gemv_work_doubles(self.Npad), dtype=torch.float64, device=dev)
+        call("algp_gemv_lower_t", ptr(self.Linv), self.Npad, self.Npad, ptr(beta), ptr(alpha), ptr(work), stream())
+        return alpha, beta
+
+    def cross(self, xs, alpha=None):
+        """Ks = s^2 k(xs, X) padded to [Mpad x Npad]; with alpha also the per-tile mean partials."""
+        M = xs.shape[0]
+        Mpad = max(BLK, pad_to(M))
+        return kbuild(self.hyper, xs, self.x, Mpad, self.Npad, dot_vec=alpha)
+
+    def whiten(self, Ks, want_V=True, want_norm=True, V_out=None):
+        """V = Ks L^-T (rows = test points) and/or its squared row norms."""
+        Mpad = Ks.shape[0]
+        dev = Ks.device
+        V = None
+        if want_V:
+            V = V_out if V_out is not None else torch.empty((Mpad, self.Npad), dtype=torch.float64, device=dev)
+        rn = torch.empty((Mpad, self.Npad // BLK), dtype=torch.float64, device=dev) if want_norm else None
+        call("algp_trmm_rt", ptr(Ks), Mpad, Ks.stride(0), ptr(self.Linv), self.Npad, self.Npad,
+             ptr(V), V.stride(0) if V is not None else 0, ptr(rn), stream())
+        return V, rn
+
+    def mean_var(self, xs, y0, ymean, test_var=None, want_var=True, max_rows=65536):
+        """Posterior mean (and latent variance) at xs: utils.py:300-308 without the inverse."""
+        alpha, _ = self.solve(y0)
+        M = xs.shape[0]
+        mu = torch.empty(M, dtype=torch.float64, device=xs.device)
+        var = torch.empty(M, dtype=torch.float64, device=xs.device) if want_var else None
+        for lo in range(0, M, max_rows):
+            hi = min(M, lo + max_rows)
+            Ks, part = self.cross(xs[lo:hi], alpha)
+            mu[lo:hi] = rowsum(part, 1.0, ymean, rows=hi - lo)
+            if want_var:
+                _, rn = self.whiten(Ks, want_V=False)
+                tv = None if test_var is None else test_var[lo:hi].contiguous()
+                var[lo:hi] = rowsum(rn, -1.0, self.hyper.outputscale, tv, rows=hi - lo)
+            del Ks
+        return mu, var
+
+
+def gemm_nt(A, B, C, alpha, beta, lower_only=False):
+    call("algp_gemm_nt", ptr(A), A.stride(0), ptr(B), B.stride(0), ptr(C), C.stride(0),
+         C.shape[0], C.shape[1], A.shape[1], float(alpha), float(beta), int(lower_only), stream())
+    return C
+
+
+def chol_logdet(Apad, n):
+    """log det of an SPD matrix held in a padded device buffer (destroys it): replaces slogdet (utils.py:193)."""
+    npad = Apad.shape[0]
+    dev = Apad.device
+    scratch = torch.empty((npad, npad), dtype=torch.float64, device=dev)
+    info = torch.zeros(1, dtype=torch.int32, device=dev)
+    call("algp_potrf", ptr(Apad), npad, Apad.stride(0), ptr(scratch), npad, ptr(info), stream())
+    out = torch.empty(2, dtype=torch.float64, device=dev)
+    call("algp_logdet_sumsq", ptr(Apad), npad, Apad.stride(0), None, ptr(out), stream())
+    res = out.cpu()
+    if int(info.item()) != 0:
+        raise np.linalg.LinAlgError("Matrix is not positive definite (leading minor of order %d)" % int(info.item()))
+    return float(res[0])
+
+
+class PosteriorState(object):
+    """Factored base set B (locations with precision pi0 > 0) of a field of n locations.
+
+    Holds Wt [n x ldw] (row loc = L^-1 Sigma_{B,loc}), diagP[n] = diag(Sigma - W^T W),
+    H_base = H(B), the running precisions pi and static flags.  ``capacity`` extra
+    columns are reserved for rank-1 appends (greedy commits)."""
+
+    def __init__(self, hyper, X, base_idx, pi0, is_static=None, capacity=0):
+        dev = X.device
+        self.hyper = hyper
+        self.X = X
+        self.n = X.shape[0]
+        self.n_pad = max(BLK, pad_to(self.n))
+        base_idx = np.asarray(base_idx, dtype=np.int64)
+        pi0 = np.asarray(pi0, dtype=np.float64)
+        self.N0 = len(base_idx)
+        self.pi = to_dev(pi0, device=dev)
+        st = np.zeros(self.n, dtype=np.uint8) if is_static is None else np.asarray(is_static, dtype=np.uint8)
+        self.is_static = to_dev(st, dtype=torch.uint8, device=dev)
+        prior = hyper.outputscale + hyper.noise           # diag of cov_matrix (agent.py:90)
+        if self.N0 == 0:
+            self.Npad = 0
+            self.ldw = pad_to(max(16, capacity), 16)
+            self.Wt = torch.zeros((self.n_pad, self.ldw), dtype=torch.float64, device=dev)
+            self.diagP = torch.full((self.n,), prior, dtype=torch.float64, device=dev)
+            self.H_base_dev = torch.zeros(1, dtype=torch.float64, device=dev)
+            self.factor = None
+        else:
+            bidx = to_dev(base_idx, dtype=torch.int64, device=dev)
+            xb = X.index_select(0, bidx).contiguous()
+            inv_pi = to_dev(1.0 / pi0[base_idx], device=dev)
+            self.factor = GPFactor(hyper, xb, diag_add=inv_pi, diag_scalar=hyper.noise)
+            self.Npad = self.factor.Npad
+            self.ldw = pad_to(self.Npad + capacity, 16)
+            Ks, _ = kbuild(hyper, X, xb, self.n_pad, self.Npad)
+            call("algp_scatter_add", ptr(Ks), Ks.stride(0), ptr(bidx.to(torch.int32)), self.N0, hyper.noise, stream())
+            self.Wt = torch.zeros((self.n_pad, self.ldw), dtype=torch.float64, device=dev)
+            _, rn = self.factor.whiten(Ks, want_V=True, want_norm=True, V_out=self.Wt)
+            del Ks
+            self.diagP = rowsum(rn, -1.0, prior, rows=self.n)
+            ldq = self.factor.logdet_quad()
+            self.H_base_dev = (0.5 * ldq[0:1] + self.N0 * CONST)
+        self.ncols = self.Npad                      # valid columns of Wt
+        self._H_base = None
+        self._argwork = torch.empty(_lib.lib.algp_argmax_work_bytes(), dtype=torch.uint8, device=dev)
+        self._appwork = torch.empty(_lib.lib.algp_append_work_doubles(self.n), dtype=torch.float64, device=dev)
+
+    @property
+    def H_base(self):
+        if self._H_base is None:
+            if self.factor is not None:
+                self.factor.check()
+            self._H_base = float(self.H_base_dev.item())
+        return self._H_base
+
+    def score_sets(self, idx, delta=None, delta_scalar=0.0, H_base=None, out=None):
+        """scores[c] = H(S1_c) for candidate sets idx [B,k] (int32 device tensor, -1 = empty)."""
+        B, k = idx.shape
+        if out is None:
+            out = torch.empty(B, dtype=torch.float64, device=idx.device)
+        ls, ls_p = _lib.host_f64(self.hyper.log_ls)
+        hb = self.H_base if H_base is None else H_base
+        call("algp_score_sets", ptr(self.Wt), self.ldw, self.ncols, ptr(self.X), self.hyper.d, ls_p,
+             self.hyper.log_os, self.hyper.kind, self.hyper.noise, ptr(self.pi), ptr(idx), ptr(delta),
+             float(delta_scalar), k, B, float(hb), ptr(out), stream())
+        return out
+
+    def argmax(self, x, idx_offset=0, out=None):
+        """Device {value, index} pair with np.argmax first-max semantics."""
+        if out is None:
+            out = torch.empty(2, dtype=torch.int64, device=x.device)     # 16 bytes: double + int64
+        call("algp_argmax", ptr(x), x.shape[0], int(idx_offset), ptr(out), ptr(self._argwork), stream())
+        return out
+
+    def greedy_utilities(self, d_static, out=None):
+        if out is None:
+            out = torch.empty(self.n, dtype=torch.float64, device=self.X.device)
+        call("algp_greedy_utilities", ptr(self.diagP), ptr(self.pi), ptr(self.is_static), float(d_static), self.n,
+             ptr(out), stream())
+        return out
+
+    def append(self, j_dev, delta, mark_static=True):
+        """Commit location *j_dev (device int64) with precision increment delta."""
+        if self.ncols >= self.ldw:
+            raise RuntimeError("PosteriorState capacity exhausted (%d columns)" % self.ldw)
+        ls, ls_p = _lib.host_f64(self.hyper.log_ls)
+        call("algp_append", ptr(self.Wt), self.ldw, self.ncols, ptr(self.X), self.n, self.hyper.d, ls_p,
+             self.hyper.log_os, self.hyper.kind, self.hyper.noise, ptr(self.diagP), ptr(self.pi), ptr(self.is_static),
+             C.c_void_p(j_dev.data_ptr()), float(delta), int(mark_static), ptr(self._appwork), stream())
+        self.ncols += 1
+
+    def greedy(self, num_samples, d_static, return_utilities=False):
+        """Agent.greedy's selection loop (agent.py:313-354) entirely on the device:
+        utilities -> argmax -> rank-1 append, one host read at the end."""
+        dev = self.X.device
+        pairs = torch.empty((num_samples, 2), dtype=torch.int64, device=dev)
+        uts = []
+        for s in range(num_samples):
+            ut = self.greedy_utilities(d_static)
+            self.argmax(ut, 0, out=pairs[s])
+            self.append(pairs[s, 1:2], d_static, mark_static=True)
+            # H(B + j) = H(B) + ut_j  (agent.py:315: cond = ent_v + sum(cumm_utilities))
+            self.H_base_dev += pairs[s, 0:1].view(torch.float64)
+            self._H_base = None
+            if return_utilities:
+                uts.append(ut)
+        picks = [int(v) for v in pairs[:, 1].cpu().tolist()]
+        if self.factor is not None:
+            self.factor.check()
+        if return_utilities:
+            return picks, torch.stack(uts).cpu().numpy()
+        return picks

@@ -1,0 +1,227 @@
+"""Drop-in for the reference's ``models.py`` GP wrapper (models.py:86-254).
+
+Same class names, constructor / method signatures, return conventions (host
+NumPy arrays) and error behaviour; the arithmetic runs in the sm_100a kernels
+of libalgp_b200.so through ``algp_b200.engine``.  gpytorch is not used: the
+model is ZeroMean + ScaleKernel(RBF | Matern nu=1.5, ARD) with the identity
+latent map, the only configuration the reference's CLI reaches
+(arguments.py:15-17).  Parameters are raw logs initialised at 0 with the
+reference-era names, so ``state_dict`` / ``load_state_dict`` / ``named_parameters``
+round-trip (agent.py:39-45, run.py:35-37).
+"""
+import numpy as np
+import torch
+import torch.nn as nn
+
+from . import engine
+from .utils import to_numpy
+
+
+class IdentityLatentFunction(nn.Module):
+    def __init__(self):
+        super().__init__()
+        self.embed_dim = None
+
+    def forward(self, x):
+        return x
+
+
+class _ARDKernel(nn.Module):
+    def __init__(self, ard_num_dims):
+        super().__init__()
+        self.log_lengthscale = nn.Parameter(torch.zeros(1, 1, ard_num_dims, dtype=torch.float64))
+
+
+class _ScaleKernel(nn.Module):
+    def __init__(self, base_kernel):
+        super().__init__()
+        self.base_kernel = base_kernel
+        self.log_outputscale = nn.Parameter(torch.zeros(1, dtype=torch.float64))
+
+
+class GaussianLikelihood(nn.Module):
+    def __init__(self):
+        super().__init__()
+        self.log_noise = nn.Parameter(torch.zeros(1, 1, dtype=torch.float64))
+
+
+class ExactGPModel(nn.Module):
+    """Parameter container with the reference's layout (models.py:206-254)."""
+
+    def __init__(self, train_x, train_y, likelihood, var=None, latent=None, kernel_params=None, latent_params=None):
+        super().__init__()
+        self.likelihood = likelihood
+        self._set_latent_function(latent, latent_params)
+        d = train_x.shape[-1] if train_x.ndim > 1 else 1
+        kernel = kernel_params['type'] if kernel_params is not None else 'rbf'
+        if kernel is None or kernel == 'rbf':
+            self.kernel_type = 'rbf'
+        elif kernel == 'matern':
+            self.kernel_type = 'matern'
+        else:
+            # 'spectral_mixture' is selectable in the reference (models.py:223-225) but never reached
+            # from its CLI; it is out of scope here
+            raise NotImplementedError
+        self.kernel_covar_module = _ScaleKernel(_ARDKernel(d))
+        self.train_inputs = (train_x,)
+        self.train_targets = train_y
+        self.train_var = var
+
+    def _set_latent_function(self, latent, latent_params):
+        if latent is None or latent == 'identity':
+            self.latent_func = IdentityLatentFunction()
+        else:
+            # linear / non_linear latents (models.py:240-247) are never selected by arguments.py:17
+            raise NotImplementedError
+
+    def set_train_data(self, inputs=None, targets=None, strict=True):
+        if inputs is not None:
+            self.train_inputs = (inputs,)
+        if targets is not None:
+            self.train_targets = targets
+
+    def hyper(self):
+        return engine.Hyper(self.kernel_covar_module.base_kernel.log_lengthscale.detach().cpu().numpy().reshape(-1),
+                            self.kernel_covar_module.log_outputscale.item(),
+                            self.likelihood.log_noise.item(), self.kernel_type)
+
+
+def _as_2d(x):
+    x = np.asarray(to_numpy(x), dtype=np.float64)
+    if x.ndim == 1:
+        x = x[:, None]
+    return np.ascontiguousarray(x)
+
+
+class GPR(object):
+    def __init__(self, latent=None, lr=.01, max_iterations=200, kernel_params=None, latent_params=None,
+                 learn_likelihood_noise=True):
+        self._train_x = None
+        self._train_y = None
+        self._train_y_mean = None
+        self._train_var = None
+        self.likelihood = None
+        self.model = None
+        self.optimizer = None
+        self.mll = None
+        self.lr = lr
+        self.latent = latent
+        self.kernel_params = kernel_params
+        self.latent_params = latent_params
+        self.max_iter = max_iterations
+        self.learn_likelihood_noise = learn_likelihood_noise     # accepted and ignored, as in models.py:101,119-120
+        self.dtype = np.float64      # np.float32 reproduces the reference's float32 kernel matrix (utils.py:19)
+        self._cache = {}
+
+    # -- data ---------------------------------------------------------------
+    @property
+    def train_x(self):
+        return np.array(self._train_x)
+
+    @property
+    def train_y(self):
+        return np.array(self._train_y)
+
+    @property
+    def train_var(self):
+        if self._train_var is None:
+            return None
+        return np.array(self._train_var)
+
+    def reset(self, x, y, var):
+        self.model = None
+        self.set_train_data(x, y, var)
+        self.likelihood = GaussianLikelihood()
+        self.model = ExactGPModel(self._train_x, self._zero_mean_train_y, self.likelihood, self._train_var,
+                                  self.latent, self.kernel_params, self.latent_params)
+        self.optimizer = torch.optim.Adam([{'params': self.model.parameters()}, ], lr=self.lr)
+        self.lr_scheduler = torch.optim.lr_scheduler.ReduceLROnPlateau(self.optimizer, mode='min', patience=50)
+        self._cache.clear()
+
+    def set_train_data(self, x, y, var=None):
+        self._train_x = _as_2d(x)
+        self._train_y = np.asarray(to_numpy(y), dtype=np.float64).reshape(-1)
+        self._train_y_mean = self._train_y.mean()
+        self._zero_mean_train_y = self._train_y - self._train_y_mean
+        if var is not None:
+            self._train_var = np.asarray(to_numpy(var), dtype=np.float64).reshape(-1)
+        if self.model is not None:
+            self.model.set_train_data(inputs=self._train_x, targets=self._zero_mean_train_y, strict=False)
+        self._cache.clear()
+
+    def hyper(self):
+        if self.model is None:
+            raise RuntimeError("GPR has no model yet: call fit() or reset() first")
+        return self.model.hyper()
+
+    # -- hyper-parameter learning ---------------------------------------------
+    def loss_and_grad(self):
+        """-(1/N) log marginal likelihood at the current theta and its gradient w.r.t. the raw
+        log-parameters (models.py:147-148), computed on the device."""
+        from .mll import mll_loss_and_grad
+        var = self._train_var if self._train_var is not None else np.zeros(len(self._train_y))
+        return mll_loss_and_grad(self.hyper(), self._train_x, self._zero_mean_train_y, var)
+
+    def fit(self, x, y, var=None, disp=False):
+        if var is None:
+            var = np.full(len(y), 1e-5)
+        self.reset(x, y, var)
+        params = dict(self.model.named_parameters())
+        p_ls = params['kernel_covar_module.base_kernel.log_lengthscale']
+        p_os = params['kernel_covar_module.log_outputscale']
+        p_nz = params['likelihood.log_noise']
+        initial_ll = final_ll = None
+        for i in range(self.max_iter):
+            self.optimizer.zero_grad()
+            loss, g = self.loss_and_grad()
+            d = p_ls.numel()
+            p_ls.grad = torch.tensor(g[:d], dtype=torch.float64).view_as(p_ls)
+            p_os.grad = torch.tensor(g[d:d + 1], dtype=torch.float64).view_as(p_os)
+            p_nz.grad = torch.tensor(g[d + 1:d + 2], dtype=torch.float64).view_as(p_nz)
+            self.optimizer.step()
+            self.lr_scheduler.step(loss)
+            if disp:
+                print(i, loss)
+            if i == 0:
+                initial_ll = -loss
+            if i == self.max_iter - 1:
+                final_ll = -loss
+        self._cache.clear()
+        if initial_ll is not None:
+            print('Initial LogLikelihood {:.3f} Final LogLikelihood {:.3f}'.format(initial_ll, final_ll))
+
+    # -- covariance / prediction ----------------------------------------------
+    def cov_mat(self, x1, x2=None, white_noise_var=None, add_likelihood_var=False):
+        """models.py:161-181: s^2 k(x1,x2) [+ diag(white_noise_var)] [+ sigma_n^2 I] as a host array."""
+        hyper = self.hyper()
+        dev = engine.require_cuda()
+        x1_ = _as_2d(x1)
+        x2_ = None if x2 is None else _as_2d(x2)
+        if x2_ is not None and x1_.shape == x2_.shape and np.array_equal(x1_, x2_):
+            x2_ = None                                   # torch.equal branch, models.py:169
+        n1 = x1_.shape[0]
+        n2 = n1 if x2_ is None else x2_.shape[0]
+        d1 = engine.to_dev(x1_, device=dev)
+        d2 = None if x2_ is None else engine.to_dev(x2_, device=dev)
+        wn = None if white_noise_var is None else engine.to_dev(np.asarray(white_noise_var, dtype=np.float64), device=dev)
+        tdtype = torch.float64 if self.dtype == np.float64 else torch.float32
+        out, _ = engine.kbuild(hyper, d1, d2, diag_add=wn, diag_scalar=hyper.noise if add_likelihood_var else 0.0,
+                               dtype=tdtype)
+        return out[:n1, :n2].cpu().numpy()
+
+    def predict(self, x, return_cov=False, return_std=False):
+        """models.py:183-197: likelihood(model(x)) + y-mean -- noise-inclusive;
+        ``return_std=True`` returns the VARIANCE diagonal, as the reference does (models.py:194)."""
+        from .utils import _posterior
+        hyper = self.hyper()
+        x_ = _as_2d(x)
+        mu, var, cov = _posterior(self, hyper, self._train_x, self._train_y, x_, self._train_var, None,
+                                  want_var=return_std, want_cov=(return_cov and not return_std))
+        if return_std:
+            return mu, var + hyper.noise
+        elif return_cov:
+            return mu, cov + hyper.noise * np.eye(len(cov))
+        return mu
+
+    def get_embeddings(self, x):
+        return _as_2d(x)

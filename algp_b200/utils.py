@@ -1,0 +1,173 @@
+"""Drop-in for the hot-path functions of the reference's ``utils.py``:
+``CONST``, ``to_torch``, ``to_numpy`` (utils.py:10-30), ``entropy_from_cov``
+(utils.py:188-194) and ``predictive_distribution`` (utils.py:293-319), plus a
+seeded ``generate_gaussian_data`` (utils.py:90-108) for the benchmarks.
+
+Same signatures and flag-dependent return tuples; inputs and outputs are host
+NumPy arrays; the arithmetic runs on the GPU in fp64 (Cholesky instead of the
+reference's explicit float32 inverse / LU slogdet).
+"""
+import hashlib
+
+import numpy as np
+import torch
+
+CONST = .5 * np.log(2 * np.pi * np.exp(1))
+
+
+def to_torch(arr):
+    # utils.py:13-20 forces float32; this build keeps float64 (the fp64 tier of the north star)
+    if arr is None:
+        return None
+    if arr.__class__.__module__ == 'torch':
+        return arr
+    if arr.__class__.__module__ == 'numpy':
+        return torch.from_numpy(np.asarray(arr, dtype=np.float64))
+    return arr
+
+
+def to_numpy(x):
+    if x is None:
+        return None
+    if x.__class__.__module__ == 'torch':
+        return x.detach().cpu().numpy()
+    if x.__class__.__module__ == 'numpy':
+        return x
+    return np.array(x)
+
+
+def generate_gaussian_data(num_rows, num_cols, k=5, min_var=10, max_var=100, algo='sum', seed=None):
+    """Mixture-of-Gaussians field of utils.py:90-108; ``seed`` (not in the reference, which never
+    seeds) selects numpy.random.default_rng(seed), None keeps the global RNG like the reference."""
+    x, y = np.meshgrid(np.arange(num_cols), np.arange(num_rows))
+    grid = np.vstack([y.flatten(), x.flatten()]).transpose()
+    rng = np.random if seed is None else np.random.default_rng(seed)
+    means_x = rng.uniform(0, num_rows, size=k)
+    means_y = rng.uniform(0, num_cols, size=k)
+    means = np.vstack([means_x, means_y]).transpose()
+    variances = rng.uniform(min_var, max_var, size=k)
+    y = np.zeros(num_rows * num_cols)
+    for i in range(k):
+        dist_sq = np.sum(np.square(grid - means[i].reshape(1, -1)), axis=1)
+        tmp = np.exp(-dist_sq / variances[i])
+        if algo == 'max':
+            y = np.maximum(y, tmp)
+        elif algo == 'sum':
+            y += tmp
+    return grid, y
+
+
+def entropy_from_cov(cov, constant=CONST):
+    """utils.py:188-194: k*CONST + 0.5*log det(cov), log det from a device Cholesky.
+    Raises numpy.linalg.LinAlgError if cov is not positive definite (the reference's LU slogdet
+    would return log|det| of an indefinite matrix; a covariance is never indefinite)."""
+    from . import engine
+    if constant is None:
+        constant = CONST
+    cov = np.asarray(to_numpy(cov), dtype=np.float64)
+    k = cov.shape[0]
+    if k == 0:
+        return 0.0
+    dev = engine.require_cuda()
+    kpad = max(engine.BLK, engine.pad_to(k))
+    A = torch.eye(kpad, dtype=torch.float64, device=dev)
+    A[:k, :k] = engine.to_dev(cov, device=dev)
+    return k * constant + 0.5 * engine.chol_logdet(A, k)
+
+
+def _digest(*arrays):
+    h = hashlib.blake2b(digest_size=16)
+    for a in arrays:
+        if a is None:
+            h.update(b"none")
+        else:
+            a = np.ascontiguousarray(a)
+            h.update(str(a.shape).encode())
+            h.update(a.tobytes())
+    return h.digest()
+
+
+def _factor_for(gp, hyper, train_x, train_var):
+    """Device factor of cov_aa (utils.py:296), cached on the GPR until its data or theta change."""
+    from . import engine
+    cache = getattr(gp, "_cache", None)
+    key = ("factor", _digest(train_x, train_var), hyper.key())
+    if cache is not None and cache.get("factor_key") == key:
+        return cache["factor"]
+    dev = engine.require_cuda()
+    x = engine.to_dev(train_x, device=dev)
+    wn = None if train_var is None else engine.to_dev(np.asarray(train_var, dtype=np.float64), device=dev)
+    f = engine.GPFactor(hyper, x, diag_add=wn, diag_scalar=hyper.noise)
+    if cache is not None:
+        cache.clear()
+        cache["factor_key"] = key
+        cache["factor"] = f
+    return f
+
+
+def _posterior(gp, hyper, train_x, train_y, test_x, train_var, test_var, want_var=False, want_cov=False,
+               want_kxx=False):
+    """mu, var, cov (and the padded device Kxx / cov buffers when want_kxx) of the latent posterior."""
+    from . import engine
+    train_x = np.asarray(to_numpy(train_x), dtype=np.float64)
+    if train_x.ndim == 1:
+        train_x = train_x[:, None]
+    test_x = np.asarray(to_numpy(test_x), dtype=np.float64)
+    if test_x.ndim == 1:
+        test_x = test_x[:, None]
+    train_y = np.asarray(to_numpy(train_y), dtype=np.float64).reshape(-1)
+    ymean = float(np.mean(train_y))                                   # utils.py:294
+    f = _factor_for(gp, hyper, train_x, train_var)
+    dev = f.L.device
+    xs = engine.to_dev(test_x, device=dev)
+    y0 = engine.to_dev(train_y - ymean, device=dev)
+    tv = None if test_var is None else engine.to_dev(np.asarray(test_var, dtype=np.float64), device=dev)
+    M = xs.shape[0]
+    if not want_cov:
+        mu, var = f.mean_var(xs, y0, ymean, tv, want_var=want_var)
+        mu_h = mu.cpu().numpy()
+        var_h = var.cpu().numpy() if want_var else None
+        f.check()
+        return mu_h, var_h, None
+    alpha, _ = f.solve(y0)
+    Ks, part = f.cross(xs, alpha)
+    mu = engine.rowsum(part, 1.0, ymean, rows=M)
+    V, _ = f.whiten(Ks, want_V=True, want_norm=False)
+    Mpad = Ks.shape[0]
+    Kxx, _ = engine.kbuild(hyper, xs, None, Mpad, Mpad, diag_add=tv, diag_scalar=0.0, pad_identity=True)   # utils.py:297
+    cov = Kxx.clone() if want_kxx else Kxx
+    engine.gemm_nt(V, V, cov, -1.0, 1.0)                               # utils.py:305
+    mu_h = mu.cpu().numpy()
+    f.check()
+    if want_kxx:
+        return mu_h, None, (Kxx, cov)
+    cov_h = cov[:M, :M].cpu().numpy()
+    return mu_h, (np.diag(cov_h).copy() if want_var else None), cov_h
+
+
+def predictive_distribution(gp, train_x, train_y, test_x, train_var=None, test_var=None, return_var=False,
+                            return_cov=False, return_mi=False):
+    """utils.py:293-319 with the reference's return convention:
+    mu | (mu, var) | (mu, cov) | (mu, mi) | (mu, cov, mi)."""
+    from . import engine
+    hyper = gp.hyper()
+    if not (return_var or return_cov or return_mi):
+        mu, _, _ = _posterior(gp, hyper, train_x, train_y, test_x, train_var, test_var)
+        return mu
+    if return_var and not (return_cov or return_mi):
+        mu, var, _ = _posterior(gp, hyper, train_x, train_y, test_x, train_var, test_var, want_var=True)
+        return mu, var
+    M = len(test_x)
+    mu, _, (Kxx, cov) = _posterior(gp, hyper, train_x, train_y, test_x, train_var, test_var, want_cov=True, want_kxx=True)
+    res = None
+    cov_h = None
+    if return_cov:
+        cov_h = cov[:M, :M].cpu().numpy()
+        res = (mu, cov_h)
+    if return_mi:
+        # entropy_from_cov(cov_xx) - entropy_from_cov(cov): the M*CONST terms cancel (utils.py:314)
+        mi = 0.5 * (engine.chol_logdet(Kxx, M) - engine.chol_logdet(cov, M))
+        res = (mu, mi)
+    if return_cov and return_mi:
+        res = (mu, cov_h, mi)
+    return res

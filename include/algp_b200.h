@@ -1,0 +1,110 @@
+/* algp_b200 -- C ABI of the B200-native GP inference / information-gain path.
+ *
+ * The reference (sumitsk/algp) is pure Python with no FFI of its own; its hot
+ * path is the NumPy / gpytorch call surface of models.py, utils.py and
+ * agent.py.  These entry points are what a binding for that surface needs;
+ * each cites the reference code it replaces.  INTEGRATION.md shows the ctypes
+ * stub a maintainer of the reference would add.
+ *
+ * Conventions
+ *  - All matrix pointers are DEVICE pointers (fp64 unless stated), row-major,
+ *    16-byte aligned, leading dimensions even.  Hyper-parameters arrive on the
+ *    HOST as the reference stores them: log-lengthscales, log-outputscale
+ *    (run.py:36-37) -- `kind` 0 = RBF, 1 = Matern nu=1.5 (models.py:216-222).
+ *  - Factor-side dimensions are padded to multiples of 128 (`*_pad`); the
+ *    padding of a covariance matrix is the identity (algp_kbuild does it).
+ *  - `stream` is a cudaStream_t; every call is asynchronous on it.
+ *  - Return value: 0 ok, 1 invalid argument, 2 CUDA error (see
+ *    algp_last_cuda_error), 3 not positive definite, 4 unsupported.  There is
+ *    no CPU fallback.
+ */
+#ifndef ALGP_B200_H
+#define ALGP_B200_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+int algp_version(void);
+const char* algp_strerror(int code);
+const char* algp_last_cuda_error(void);
+
+/* ---- K1: kernel matrix -------------------------------------------------- */
+/* GPR.cov_mat (models.py:161-181): out = s^2 k(x1,x2) [+ diag(diag_add)] [+ diag_scalar I],
+ * written over [n1_pad x n2_pad] (zeros outside [n1 x n2]; ones on the padded
+ * diagonal when pad_identity).  x2 == NULL means x2 = x1.  out_dtype 0 = fp64,
+ * 1 = fp32 (the reference's dtype, utils.py:19).  If dot_vec != NULL also
+ * writes dot_partial[r][t] = sum over column tile t of out[r][c]*dot_vec[c]
+ * (t < algp_kbuild_col_tiles) -- the mean of utils.py:301 without re-reading K. */
+int algp_kbuild(const double* x1, int64_t n1, const double* x2, int64_t n2, int d,
+                const double* log_ls_host, double log_os, int kind,
+                const double* diag_add, double diag_scalar, int pad_identity,
+                void* out, int64_t n1_pad, int64_t n2_pad, int64_t ld, int out_dtype,
+                const double* dot_vec, double* dot_partial, void* stream);
+int algp_kbuild_col_tiles(int64_t n2_pad, int out_dtype);
+/* out[r] = bias + scale * sum_t partial[r][t] (+ addvec[r]) */
+int algp_rowsum(const double* partial, int64_t rows, int nt, double scale, double bias,
+                const double* addvec, double* out, void* stream);
+/* M[row_of_col[k]][k] += v : the sigma_n^2 of cov_matrix (agent.py:90) under a (location, base) gather */
+int algp_scatter_add(double* M, int64_t ld, const int32_t* row_of_col, int64_t ncols, double v, void* stream);
+
+/* ---- K2: factor and solves ----------------------------------------------- */
+/* In-place blocked Cholesky of the lower triangle, A = L L^T; replaces
+ * np.linalg.inv(cov_aa) (utils.py:300) together with algp_trtri.  Also writes
+ * inv(L_jj) into the diagonal 128-blocks of Linv.  *info_dev = 0, or the
+ * 1-based column at which the matrix stopped being positive definite. */
+int algp_potrf(double* A, int64_t npad, int64_t ld, double* Linv, int64_t ldi, int* info_dev, void* stream);
+/* Completes Linv = L^-1 from its diagonal blocks (recursive doubling).
+ * work: algp_trtri_work_doubles(npad) doubles. */
+int algp_trtri(const double* L, int64_t npad, int64_t ld, double* Linv, int64_t ldi, double* work,
+               int zero_upper, void* stream);
+int64_t algp_trtri_work_doubles(int64_t npad);
+/* out = M v over the lower triangle (beta = L^-1 y) */
+int algp_gemv_lower(const double* M, int64_t n, int64_t ld, const double* v, double* out, void* stream);
+/* out = M^T v over the lower triangle (alpha = L^-T beta); work: algp_gemv_work_doubles(n) */
+int algp_gemv_lower_t(const double* M, int64_t n, int64_t ld, const double* v, double* out, double* work, void* stream);
+int64_t algp_gemv_work_doubles(int64_t n);
+/* out2[0] = log det A = 2 sum log L_ii (replaces slogdet, utils.py:193); out2[1] = |v|^2 if v */
+int algp_logdet_sumsq(const double* L, int64_t n, int64_t ld, const double* v, double* out2, void* stream);
+/* V = Ks L^-T using the triangular structure of Linv (cov_xa inv(cov_aa) cov_xa^T of
+ * utils.py:300-305 is V V^T).  V may be NULL; rn_partial[m][t] (t < npad/128), if not
+ * NULL, receives the row sums of V^2 per column tile: var = k** - sum_t rn_partial. */
+int algp_trmm_rt(const double* Ks, int64_t mpad, int64_t ldk, const double* Linv, int64_t npad, int64_t ldi,
+                 double* V, int64_t ldv, double* rn_partial, void* stream);
+/* C = beta C + alpha A B^T (A [mpad x kpad], B [npad x kpad]); lower_only: only tiles on/below the diagonal */
+int algp_gemm_nt(const double* A, int64_t lda, const double* B, int64_t ldb, double* C, int64_t ldc,
+                 int64_t mpad, int64_t npad, int64_t kpad, double alpha, double beta, int lower_only, void* stream);
+
+/* ---- K3 / K5: information-gain scoring ------------------------------------ */
+/* Entropy H(S1) of `B` candidate sets of `k` slots (k <= 128; idx -1 = empty
+ * slot, duplicates idempotent) against the factored base set: replaces the
+ * per-candidate slogdet loops of Agent.greedy / Agent.best_path
+ * (agent.py:317-347, 373-400).  Wt [n x ldw] = Sigma_{:,B} L^-T (first `ncols`
+ * columns valid, the rest zero up to a multiple of 16), X [n x d] the field
+ * coordinates, pi0[n] the base precisions, delta[B x k] (or delta_scalar) the
+ * precision each slot adds.  scores[c] = H_base + n_new*CONST +
+ * 0.5*(logdet(I + D P_CC D) - sum(log(pi0+delta) - [pi0>0] log pi0)). */
+int algp_score_sets(const double* Wt, int64_t ldw, int64_t ncols, const double* X, int d,
+                    const double* log_ls_host, double log_os, int kind, double noise,
+                    const double* pi0, const int32_t* idx, const double* delta, double delta_scalar,
+                    int k, int64_t B, double H_base, double* scores, void* stream);
+/* greedy utilities for every location (k = 1 closed form, agent.py:341) */
+int algp_greedy_utilities(const double* diagP, const double* pi, const uint8_t* is_static, double d_static,
+                          int64_t n, double* ut, void* stream);
+/* np.argmax semantics (first maximum, agent.py:349,402): out_pair = {double value; int64 index + idx_offset}.
+ * work: algp_argmax_work_bytes() bytes. */
+int algp_argmax(const double* x, int64_t n, int64_t idx_offset, void* out_pair, void* work, void* stream);
+int64_t algp_argmax_work_bytes(void);
+/* Commit an acquisition at location *j_dev with precision increment delta: appends column
+ * `ncols` to Wt, downdates diagP, raises pi[j] (and is_static[j] if mark_static).
+ * work: algp_append_work_doubles(n) doubles. */
+int algp_append(double* Wt, int64_t ldw, int64_t ncols, const double* X, int64_t n, int d,
+                const double* log_ls_host, double log_os, int kind, double noise,
+                double* diagP, double* pi, uint8_t* is_static, const void* j_dev, double delta,
+                int mark_static, double* work, void* stream);
+int64_t algp_append_work_doubles(int64_t n);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,207 @@
+"""Parity of the reference-facing API (GPR / predictive_distribution / entropy_from_cov /
+Agent.greedy / Agent.best_path) with the oracle and with golden vectors frozen from the
+reference's own code.  B200 only.
+
+Tolerances (north star): fp64 tier rel 1e-9 on mean / variance (variance relative to the prior
+scale s^2, SURVEY.md 7 "variance cancellation") and 1e-8 on log-dets / entropies; against the
+reference's float32 flow only the 1e-4 tier is meaningful (its own float32 inverse limits it
+to ~1e-3 of the prior scale on these conditionings)."""
+import os
+import types
+
+import numpy as np
+import pytest
+import torch
+
+import oracle as O
+import algp_b200
+from algp_b200 import engine
+from gpu_helpers import dev, field_problem, hyper_pair
+
+pytestmark = pytest.mark.gpu
+
+
+def make_gpr(kind, log_ls, log_os, log_noise, x, y, var):
+    gp = algp_b200.GPR(kernel_params={'type': kind})
+    gp.reset(x, y, var)
+    with torch.no_grad():
+        gp.model.kernel_covar_module.base_kernel.log_lengthscale.copy_(torch.tensor(log_ls).view(1, 1, -1))
+        gp.model.kernel_covar_module.log_outputscale.fill_(float(log_os))
+        gp.likelihood.log_noise.fill_(float(log_noise))
+    return gp
+
+
+def load(golden_dir, name):
+    return dict(np.load(os.path.join(golden_dir, name), allow_pickle=False))
+
+
+@pytest.mark.parametrize("kind", ["rbf", "matern"])
+def test_predictive_distribution_fp64_tier(kind):
+    X, y, tr, ytr, rng = field_problem(24, 20, 300, seed=2)
+    te = rng.choice(len(X), 150, replace=False)
+    var = np.where(rng.random(300) < 0.5, 0.01, 1.0 / (1 / 0.01 + 1 / 1.0))
+    tvar = np.full(150, 0.02)
+    th, hy = hyper_pair([2.5, 3.5], 1.3, 0.02, kind)
+    gp = make_gpr(kind, th.log_lengthscale, th.log_outputscale, th.log_noise, X[tr], ytr, var)
+    ogp = O.OracleGP(th, "fp64")
+    a = (X[tr], ytr, X[te], var)
+    s2 = np.exp(th.log_outputscale)
+
+    mu = algp_b200.predictive_distribution(gp, *a)
+    mu_o = O.predictive_distribution_chol(ogp, *a)
+    np.testing.assert_allclose(mu, mu_o, rtol=1e-9, atol=1e-9 * np.abs(mu_o).max())
+
+    mu2, var2 = algp_b200.predictive_distribution(gp, *a, return_var=True)
+    _, var_o = O.predictive_distribution_chol(ogp, *a, return_var=True)
+    np.testing.assert_allclose(mu2, mu_o, rtol=1e-9, atol=1e-9 * np.abs(mu_o).max())
+    np.testing.assert_allclose(var2, var_o, rtol=0, atol=1e-9 * s2)
+
+    mu3, cov3 = algp_b200.predictive_distribution(gp, *a, return_cov=True)
+    _, cov_o = O.predictive_distribution_chol(ogp, *a, return_cov=True)
+    np.testing.assert_allclose(cov3, cov_o, rtol=0, atol=1e-9 * s2)
+
+    mu4, mi4 = algp_b200.predictive_distribution(gp, *a, test_var=tvar, return_mi=True)
+    _, mi_o = O.predictive_distribution_chol(ogp, *a, test_var=tvar, return_mi=True)
+    assert mi4 == pytest.approx(mi_o, rel=1e-8)
+
+    mu5, cov5, mi5 = algp_b200.predictive_distribution(gp, *a, test_var=tvar, return_cov=True, return_mi=True)
+    assert mi5 == pytest.approx(mi_o, rel=1e-8)
+    assert cov5.shape == (150, 150)
+    # literal explicit-inverse formula in float64 agrees too
+    _, var_l = O.predictive_distribution(ogp, *a, return_var=True)
+    np.testing.assert_allclose(var2, var_l, rtol=0, atol=1e-8 * s2)
+
+
+@pytest.mark.parametrize("kind", ["rbf", "matern"])
+def test_against_reference_golden_gp(golden_dir, kind):
+    """Outputs of the reference's own utils.predictive_distribution / GPR.cov_mat (float32 flow)."""
+    g = load(golden_dir, "ref_gp_%s.npz" % kind)
+    gp = make_gpr(kind, g["log_ls"], g["log_os"], g["log_noise"], g["train_x"], g["train_y"], g["train_var"])
+    s2 = float(np.exp(g["log_os"]))
+    K = gp.cov_mat(g["train_x"], white_noise_var=g["train_var"], add_likelihood_var=True)
+    np.testing.assert_allclose(K, g["K_train_noise"], rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(gp.cov_mat(g["test_x"], g["train_x"]), g["K_test_train"], rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(gp.cov_mat(g["train_x"][:20], g["train_x"][:20].copy(), add_likelihood_var=True),
+                               g["K_same_x2"], rtol=1e-5, atol=1e-6)
+    gp.dtype = np.float32                         # the reference's own dtype
+    K32 = gp.cov_mat(g["train_x"], white_noise_var=g["train_var"], add_likelihood_var=True)
+    assert K32.dtype == np.float32
+    np.testing.assert_allclose(K32, g["K_train_noise"], rtol=2e-6, atol=2e-7)
+    gp.dtype = np.float64
+    a = (g["train_x"], g["train_y"], g["test_x"], g["train_var"])
+    mu, var = algp_b200.predictive_distribution(gp, *a, return_var=True)
+    np.testing.assert_allclose(mu, g["pd_mu"], rtol=0, atol=2e-3)
+    np.testing.assert_allclose(var, g["pd_var"], rtol=0, atol=2e-3 * s2)
+    _, cov = algp_b200.predictive_distribution(gp, *a, return_cov=True)
+    np.testing.assert_allclose(cov, g["pd_cov"], rtol=0, atol=2e-3 * s2)
+    _, mi = algp_b200.predictive_distribution(gp, *a, test_var=g["test_var"], return_mi=True)
+    assert mi == pytest.approx(float(g["pd_mi"]), rel=2e-3)
+    # entropy_from_cov on the reference's own matrices: same number as its LU slogdet
+    assert algp_b200.entropy_from_cov(g["K_train_noise"]) == pytest.approx(float(g["ent_K_train_noise"]), rel=1e-8)
+    assert algp_b200.entropy_from_cov(g["pd_cov_tv"]) == pytest.approx(float(g["ent_pd_cov_tv"]), rel=1e-8)
+    with pytest.raises(np.linalg.LinAlgError):
+        algp_b200.entropy_from_cov(-np.eye(5))
+    # GPR.predict (noise-inclusive; un-pinned stand-in semantics) at the reference-fitted theta
+    gp2 = make_gpr(kind, g["fit_log_ls"], g["fit_log_os"], g["fit_log_noise"], g["train_x"], g["train_y"], g["train_var"])
+    pm, pv = gp2.predict(g["test_x"], return_std=True)
+    np.testing.assert_allclose(pm, g["predict_mean"], rtol=0, atol=5e-3)
+    np.testing.assert_allclose(pv, g["predict_var"], rtol=0, atol=5e-3)
+
+
+def unflatten(counts, values):
+    out, p = [], 0
+    for c in counts:
+        out.append(list(values[p:p + c]))
+        p += c
+    return out
+
+
+class GoldenEnv(object):
+    def __init__(self, g):
+        self.X, self.test_X = g["X"], g["test_X"]
+        self.num_samples = len(self.X)
+
+
+def agent_from_golden(g, kind):
+    """The reference's Agent state (sample lists, theta) re-created on the accelerated Agent."""
+    ag = algp_b200.Agent.__new__(algp_b200.Agent)
+    ag.env = GoldenEnv(g)
+    ag.static_std, ag.mobile_std = float(g["static_std"]), float(g["mobile_std"])
+    ag.static_data = unflatten(g["static_counts"], g["static_values"])
+    ag.mobile_data = unflatten(g["mobile_counts"], g["mobile_values"])
+    ag.criterion = 'entropy'
+    ind, y, var = ag.get_sampled_dataset()
+    ag.gp = make_gpr(kind, g["log_ls"], g["log_os"], g["log_noise"], ag.env.X[ind], y, var)
+    ag._post_update()
+    return ag
+
+
+@pytest.mark.parametrize("kind", ["rbf", "matern"])
+def test_agent_matches_reference_golden(golden_dir, kind):
+    g = load(golden_dir, "ref_agent_%s_entropy.npz" % kind)
+    ag = agent_from_golden(g, kind)
+    ind, y, var = ag.get_sampled_dataset()
+    assert list(ind) == list(g["ds_indices"])
+    np.testing.assert_array_equal(y, g["ds_y"])
+    np.testing.assert_array_equal(var, g["ds_var"])
+    np.testing.assert_allclose(ag.cov_matrix, g["cov_matrix"], rtol=1e-5, atol=1e-6)
+    assert ag.greedy(3) == [int(v) for v in g["greedy"]]
+    paths = unflatten(g["path_lens"], g["path_flat"])
+    static_idx = [int(v) for v in g["static_indices"]]
+    assert ag.best_path(paths, static_idx) == int(g["best_path"])
+    assert ag.best_path(paths[:1], static_idx) == 0
+    mu, v = ag.predict(return_var=True)
+    np.testing.assert_allclose(mu, g["pred_mu"], rtol=0, atol=2e-3)
+    np.testing.assert_allclose(v, g["pred_var"], rtol=0, atol=2e-3)
+    # every path utility equals the literal reference entropy (oracle run on the float64 kernel matrix)
+    th = O.Theta(g["log_ls"], float(g["log_os"]), float(g["log_noise"]), kind)
+    cov = O.OracleGP(th, "fp64").cov_mat(g["X"], add_likelihood_var=True)
+    best, ut = O.best_path_literal(cov, g["static_sampled"], g["mobile_sampled"], ag.static_std, ag.mobile_std,
+                                   paths, static_idx, return_utilities=True)
+    assert best == int(g["best_path"])
+
+
+def test_agent_mutual_information_is_refused_not_faked(golden_dir):
+    g = load(golden_dir, "ref_agent_rbf_entropy.npz")
+    ag = agent_from_golden(g, "rbf")
+    ag.criterion = 'mutual_information'
+    with pytest.raises(NotImplementedError):
+        ag.greedy(1)
+
+
+def test_state_dict_roundtrip_and_unknown_kernel():
+    x = np.random.default_rng(0).uniform(0, 5, (20, 2))
+    gp = make_gpr("matern", np.log([1.5, 2.0]), 0.3, -2.0, x, x[:, 0], np.full(20, 0.01))
+    sd = gp.model.state_dict()
+    assert 'kernel_covar_module.log_outputscale' in sd and 'likelihood.log_noise' in sd      # run.py:36-37
+    gp2 = algp_b200.GPR(kernel_params={'type': 'matern'})
+    gp2.reset(gp.train_x, gp.train_y, gp.train_var)
+    gp2.model.load_state_dict(sd)                                                            # agent.py:39-41
+    assert gp2.hyper().key() == gp.hyper().key()
+    with pytest.raises(NotImplementedError):
+        algp_b200.GPR(kernel_params={'type': 'periodic'}).reset(x, x[:, 0], np.full(20, 0.01))
+
+
+# ------------------------------------------------------------------ full-size properties
+def test_fit_predict_n4096_properties():
+    """BASELINE config A: N=4096 training points, 64x64 grid, fp64.  The oracle takes seconds here,
+    so compare in full, then check size-independent properties."""
+    rng = np.random.default_rng(1)
+    grid, yf = O.gaussian_mixture_field(64, 64, seed=1)
+    x = rng.uniform(0, 64, size=(4096, 2))
+    y = np.zeros(4096)
+    for _ in range(3):
+        c = rng.uniform(0, 64, 2)
+        y += np.exp(-((x - c) ** 2).sum(1) / 60.0)
+    y = np.maximum(0, y + rng.normal(0, 0.1, 4096))
+    var = np.full(4096, 0.01)
+    th, hy = hyper_pair([4.0, 4.0], 1.0, 0.01, "rbf")
+    gp = make_gpr("rbf", th.log_lengthscale, th.log_outputscale, th.log_noise, x, y, var)
+    mu, v = algp_b200.predictive_distribution(gp, x, y, grid, var, return_var=True)
+    mu_o, v_o = O.predictive_distribution_chol(O.OracleGP(th, "fp64"), x, y, grid, var, return_var=True)
+    np.testing.assert_allclose(mu, mu_o, rtol=1e-9, atol=1e-9 * np.abs(mu_o).max())
+    np.testing.assert_allclose(v, v_o, rtol=0, atol=1e-9)
+    assert (v > 0).all() and (v < 1.0 + 1e-12).all()          # 0 < posterior var <= prior var s^2
+    # linearity of the mean in y (same factor, cached): mean(2y) - ybar-shift == 2*mean(y) - shift
+    mu2 = algp_b200.predictive_distribution(gp, x, 2 * y, grid, var)
+    np.testing.assert_allclose(mu2, 2 * mu, rtol=1e-9, atol=1e-9)

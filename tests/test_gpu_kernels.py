@@ -1,0 +1,226 @@
+"""Parity of each CUDA kernel (through the C ABI) with the CPU oracle.  B200 only."""
+import numpy as np
+import pytest
+import torch
+
+import oracle as O
+from algp_b200 import _lib, engine
+from gpu_helpers import dev, field_problem, hyper_pair
+
+pytestmark = pytest.mark.gpu
+
+
+# ---------------------------------------------------------------- K1 kbuild
+@pytest.mark.parametrize("kind", ["rbf", "matern"])
+@pytest.mark.parametrize("d", [2, 6, 3])
+def test_kbuild_fp64_matches_oracle(kind, d):
+    rng = np.random.default_rng(d)
+    x1 = rng.uniform(0, 20, size=(333, d))
+    x2 = rng.uniform(0, 20, size=(517, d))
+    th, hy = hyper_pair(np.linspace(2.0, 4.0, d), 1.3, 0.05, kind)
+    K, _ = engine.kbuild(hy, dev(x1), dev(x2))
+    ref = O.kernel_matrix(th, x1, x2, "fp64")
+    out = K.cpu().numpy()
+    assert out.shape == (333, 518)
+    # bit-level agreement is not expected (different libm exp); 1e-13 relative to s^2 is
+    np.testing.assert_allclose(out[:, :517], ref, rtol=1e-12, atol=1e-14)
+    assert (out[:, 517:] == 0).all()
+
+
+def test_kbuild_diag_padding_and_dot():
+    rng = np.random.default_rng(0)
+    x = rng.uniform(0, 15, size=(200, 2))
+    th, hy = hyper_pair([2.0, 3.0], 0.9, 0.02, "rbf")
+    var = rng.uniform(0.01, 0.5, 200)
+    vec = rng.normal(size=200)
+    vpad = np.zeros(256)
+    vpad[:200] = vec
+    K, part = engine.kbuild(hy, dev(x), None, 256, 256, diag_add=dev(var), diag_scalar=hy.noise, pad_identity=True,
+                            dot_vec=dev(vpad))
+    out = K.cpu().numpy()
+    ref = O.OracleGP(th, "fp64").cov_mat(x, white_noise_var=var, add_likelihood_var=True)
+    np.testing.assert_allclose(out[:200, :200], ref, rtol=1e-12, atol=1e-14)
+    assert (out[200:, :200] == 0).all() and (out[:200, 200:] == 0).all()
+    np.testing.assert_array_equal(out[200:, 200:], np.eye(56))
+    s = engine.rowsum(part, 1.0, 0.5).cpu().numpy()
+    np.testing.assert_allclose(s[:200], ref @ vec + 0.5, rtol=1e-11, atol=1e-12)
+
+
+@pytest.mark.parametrize("kind", ["rbf", "matern"])
+def test_kbuild_fp32_matches_ref32(kind):
+    rng = np.random.default_rng(1)
+    x1 = rng.uniform(0, 20, size=(300, 2))
+    th, hy = hyper_pair([2.5, 3.5], 1.3, 0.02, kind)
+    K, _ = engine.kbuild(hy, dev(x1), None, dtype=torch.float32)
+    ref = O.kernel_matrix(th, x1, None, "ref32")
+    np.testing.assert_allclose(K.cpu().numpy(), ref, rtol=1e-5, atol=1e-6)
+
+
+# ---------------------------------------------------------------- K2 potrf / trtri / solves
+def spd_problem(N, seed, kind="rbf"):
+    rng = np.random.default_rng(seed)
+    x = rng.uniform(0, 40, size=(N, 2))
+    th, hy = hyper_pair([3.0, 4.0], 1.0, 0.01, kind)
+    var = rng.uniform(0.01, 0.02, N)
+    A = O.OracleGP(th, "fp64").cov_mat(x, white_noise_var=var, add_likelihood_var=True)
+    return x, var, th, hy, A
+
+
+@pytest.mark.parametrize("N", [100, 128, 384, 645, 1000])
+def test_potrf_trtri_match_numpy(N):
+    x, var, th, hy, A = spd_problem(N, N)
+    f = engine.GPFactor(hy, dev(x), diag_add=dev(var))
+    f.check()
+    L = np.tril(f.L.cpu().numpy())[:N, :N]
+    Lref = np.linalg.cholesky(A)
+    scale = np.abs(Lref).max()
+    np.testing.assert_allclose(L, Lref, rtol=0, atol=1e-11 * scale)
+    Linv = f.Linv.cpu().numpy()
+    assert np.abs(np.triu(Linv, 1)).max() == 0.0
+    np.testing.assert_allclose(Linv[:N, :N] @ Lref, np.eye(N), rtol=0, atol=1e-9)
+    # padded part of both factors is the identity
+    np.testing.assert_array_equal(np.tril(f.L.cpu().numpy())[N:, N:], np.eye(f.Npad - N))
+    np.testing.assert_array_equal(Linv[N:, N:], np.eye(f.Npad - N))
+    ldq = f.logdet_quad().cpu().numpy()
+    assert ldq[0] == pytest.approx(np.linalg.slogdet(A)[1], rel=1e-11)
+
+
+def test_potrf_reports_not_positive_definite():
+    x, var, th, hy, A = spd_problem(200, 3)
+    bad = -np.ones(200)            # pushes the diagonal negative
+    f = engine.GPFactor(hy, dev(x), diag_add=dev(bad), diag_scalar=0.0)
+    with pytest.raises(np.linalg.LinAlgError):
+        f.check()
+    assert int(f.info.item()) >= 1
+
+
+@pytest.mark.parametrize("N", [200, 640])
+def test_solve_matches_numpy(N):
+    x, var, th, hy, A = spd_problem(N, N + 1)
+    rng = np.random.default_rng(5)
+    y = rng.normal(size=N)
+    f = engine.GPFactor(hy, dev(x), diag_add=dev(var))
+    alpha, beta = f.solve(dev(y))
+    ref = np.linalg.solve(A, y)
+    np.testing.assert_allclose(alpha.cpu().numpy()[:N], ref, rtol=1e-9, atol=1e-9 * np.abs(ref).max())
+    quad = f.logdet_quad(beta).cpu().numpy()[1]
+    assert quad == pytest.approx(y @ ref, rel=1e-10)
+
+
+def test_gemm_nt_matches_numpy():
+    rng = np.random.default_rng(2)
+    A = rng.normal(size=(256, 384))
+    B = rng.normal(size=(384, 384))
+    C = rng.normal(size=(256, 384))
+    Cd = dev(C)
+    engine.gemm_nt(dev(A), dev(B), Cd, -1.0, 1.0)
+    np.testing.assert_allclose(Cd.cpu().numpy(), C - A @ B.T, rtol=1e-12, atol=1e-11)
+    # lower-only SYRK form
+    S = rng.normal(size=(384, 128))
+    C2 = rng.normal(size=(384, 384))
+    C2d = dev(C2)
+    engine.gemm_nt(dev(S), dev(S), C2d, 1.0, 1.0, lower_only=True)
+    full = C2 + S @ S.T
+    got = C2d.cpu().numpy()
+    for bi in range(3):
+        for bj in range(3):
+            blk = (slice(bi * 128, bi * 128 + 128), slice(bj * 128, bj * 128 + 128))
+            np.testing.assert_allclose(got[blk], full[blk] if bj <= bi else C2[blk], rtol=1e-12, atol=1e-11)
+
+
+def test_whiten_rownorm_matches_numpy():
+    x, var, th, hy, A = spd_problem(300, 9)
+    rng = np.random.default_rng(4)
+    xs = rng.uniform(0, 40, size=(150, 2))
+    f = engine.GPFactor(hy, dev(x), diag_add=dev(var))
+    Ks, _ = f.cross(dev(xs))
+    V, rn = f.whiten(Ks)
+    Kref = O.kernel_matrix(th, xs, x, "fp64")
+    import scipy.linalg as sla
+    Vref = sla.solve_triangular(np.linalg.cholesky(A), Kref.T, lower=True).T
+    np.testing.assert_allclose(V.cpu().numpy()[:150, :300], Vref, rtol=0, atol=1e-10)
+    sq = engine.rowsum(rn).cpu().numpy()[:150]
+    np.testing.assert_allclose(sq, (Vref ** 2).sum(1), rtol=1e-10)
+
+
+# ---------------------------------------------------------------- K3 scoring
+def scoring_problem(kind, n_side=20, n_base=70, seed=3, d_extra=0):
+    X, y, tr, ytr, rng = field_problem(n_side, n_side + 3, n_base, seed, d_extra)
+    n = len(X)
+    d = X.shape[1]
+    th, hy = hyper_pair(np.linspace(2.0, 3.0, d), 1.1, 0.04, kind)
+    ss, ms = 0.1, 1.0
+    static = np.zeros(n, bool)
+    mobile = np.zeros(n, bool)
+    static[tr[: n_base // 2]] = True
+    mobile[tr[n_base // 3:]] = True
+    pi0 = O.precisions_from_flags(static, mobile, ss, ms)
+    cov = O.OracleGP(th, "fp64").cov_mat(X, add_likelihood_var=True)
+    return X, th, hy, static, mobile, pi0, cov, ss, ms, rng
+
+
+@pytest.mark.parametrize("kind", ["rbf", "matern"])
+@pytest.mark.parametrize("k", [1, 5, 8, 11, 40, 128])
+def test_score_sets_matches_oracle(kind, k):
+    X, th, hy, static, mobile, pi0, cov, ss, ms, rng = scoring_problem(kind, d_extra=(1 if k == 11 else 0))
+    n = len(X)
+    Bc = 300 if k <= 8 else 40
+    idx = np.full((Bc, k), -1, dtype=np.int32)
+    delta = np.zeros((Bc, k))
+    for c in range(Bc):
+        m = int(rng.integers(1, k + 1))
+        sel = rng.choice(n, m, replace=False)
+        idx[c, :m] = sel
+        delta[c, :m] = np.where(rng.random(m) < 0.3, 1 / ss ** 2, 1 / ms ** 2)
+        if m >= 3 and c % 4 == 0:
+            idx[c, m - 1] = idx[c, 0]           # duplicate -> idempotent
+        if m >= 2 and c % 5 == 0:
+            delta[c, 1] = 0.0                   # zero increment -> inactive slot
+    base = np.nonzero(pi0 > 0)[0]
+    state = engine.PosteriorState(hy, dev(X), base, pi0)
+    got = state.score_sets(dev(idx, torch.int32), dev(delta)).cpu().numpy()
+    ost = O.posterior_state(cov, pi0)
+    assert state.H_base == pytest.approx(ost["H"], rel=1e-11)
+    np.testing.assert_allclose(state.diagP.cpu().numpy(), np.diag(ost["P"]), rtol=0, atol=1e-10)
+    want = O.score_sets_restructured(ost["P"], pi0, idx, delta, ost["H"])
+    # log-det tier of the north star: rel 1e-8
+    np.testing.assert_allclose(got, want, rtol=1e-8, atol=1e-9)
+    assert int(np.argmax(got)) == int(np.argmax(want))
+
+
+def test_score_sets_empty_base_and_scalar_delta():
+    X, th, hy, static, mobile, pi0, cov, ss, ms, rng = scoring_problem("rbf")
+    n = len(X)
+    pi_none = np.zeros(n)
+    state = engine.PosteriorState(hy, dev(X), [], pi_none)
+    idx = np.stack([rng.choice(n, 6, replace=False) for _ in range(64)]).astype(np.int32)
+    got = state.score_sets(dev(idx, torch.int32), None, delta_scalar=1.0).cpu().numpy()
+    want = O.score_sets_restructured(cov, pi_none, idx, np.ones(idx.shape), 0.0)
+    np.testing.assert_allclose(got, want, rtol=1e-9, atol=1e-10)
+
+
+@pytest.mark.parametrize("kind", ["rbf", "matern"])
+def test_greedy_matches_literal_reference_loop(kind):
+    X, th, hy, static, mobile, pi0, cov, ss, ms, rng = scoring_problem(kind, n_side=12, n_base=40)
+    base = np.nonzero(pi0 > 0)[0]
+    state = engine.PosteriorState(hy, dev(X), base, pi0, is_static=static, capacity=8)
+    picks, uts = state.greedy(4, 1 / ss ** 2, return_utilities=True)
+    p_lit, u_lit = O.greedy_literal(cov, static, mobile, ss, ms, 4, return_utilities=True)
+    assert picks == [int(p) for p in p_lit]
+    fin = np.isfinite(u_lit)
+    assert (np.isfinite(uts) == fin).all()
+    np.testing.assert_allclose(uts[fin], u_lit[fin], rtol=0, atol=1e-9)
+    # scoring against the appended state == literal entropy of the grown set
+    st2 = static.copy()
+    st2[picks] = True
+    assert state.H_base == pytest.approx(O.set_entropy_literal(cov, st2, mobile, ss, ms), rel=1e-10)
+
+
+def test_argmax_first_max_semantics():
+    x = np.array([1.0, 5.0, -np.inf, 5.0, 2.0] * 1000)
+    state_work = torch.empty(_lib.lib.algp_argmax_work_bytes(), dtype=torch.uint8, device="cuda")
+    out = torch.empty(2, dtype=torch.int64, device="cuda")
+    xd = dev(x)
+    _lib.call("algp_argmax", _lib.ptr(xd), len(x), 7, _lib.ptr(out), _lib.ptr(state_work), _lib.stream())
+    assert int(out[1].item()) == 1 + 7
+    assert out[0:1].view(torch.float64).item() == 5.0
