@@ -29,6 +29,19 @@ def _flags(data):
     return np.array([len(v) > 0 for v in data], dtype=bool)
 
 
+def _pad_paths(paths, org_mobile):
+    """list-of-lists -> [P, k] int32 (-1 padded) holding each path's NEW mobile locations."""
+    rows = []
+    for p in paths:
+        p = np.unique(np.asarray(p, dtype=np.int64).reshape(-1))
+        rows.append(p[~org_mobile[p]])
+    k = max(1, max(len(r) for r in rows))
+    idx = np.full((len(rows), k), -1, dtype=np.int32)
+    for c, r in enumerate(rows):
+        idx[c, :len(r)] = r
+    return idx
+
+
 class HotPath(object):
     """Methods to mix into (or patch onto) an Agent that has ``env`` (``X``, ``test_X``,
     ``num_samples``), ``gp``, ``static_data``, ``mobile_data``, ``static_std``, ``mobile_std``
@@ -95,6 +108,18 @@ class HotPath(object):
             self._hot_X = engine.to_dev(X)
         return self._hot_X
 
+    def _sample_flags(self):
+        """Boolean static / mobile flags per location (agent.py:298,302), recomputed only when the
+        sample lists changed (every mutation in the reference goes through _add_samples / reset /
+        a deepcopy, all of which change this stamp)."""
+        col = getattr(self, "collected", None)
+        stamp = (id(self.static_data), id(self.mobile_data), -1 if col is None else len(col['ind']))
+        cached = getattr(self, "_hot_flags", None)
+        if cached is None or col is None or cached[0] != stamp:
+            cached = (stamp, _flags(self.static_data), _flags(self.mobile_data))
+            self._hot_flags = cached
+        return cached[1].copy(), cached[2].copy()
+
     def _state_for(self, static_sampled, mobile_sampled, capacity):
         """Posterior state whose base set carries exactly these flags; reused when the cached one
         (e.g. left by greedy with its picks appended) already matches."""
@@ -116,7 +141,7 @@ class HotPath(object):
     def greedy(self, num_samples):
         """agent.py:295-356: greedily pick ``num_samples`` static locations by entropy gain."""
         self._check_criterion()
-        static_sampled, mobile_sampled = _flags(self.static_data), _flags(self.mobile_data)
+        static_sampled, mobile_sampled = self._sample_flags()
         state, pi = self._state_for(static_sampled, mobile_sampled, capacity=num_samples + 16)
         d = 1.0 / self.static_std ** 2
         picks = state.greedy(num_samples, d)
@@ -131,31 +156,32 @@ class HotPath(object):
         if len(paths_mobile_indices) == 1:
             return 0
         self._check_criterion()
-        static_sampled, org_mobile = _flags(self.static_data), _flags(self.mobile_data)
+        static_sampled, org_mobile = self._sample_flags()
         static_sampled[static_indices] = True
         state, pi = self._state_for(static_sampled, org_mobile, capacity=0)
         dm = 1.0 / self.mobile_std ** 2
-        # slots: the NEW mobile locations of each path (the mobile flag is boolean: agent.py:377,
-        # so already-mobile locations and repeats add nothing)
-        rows = []
-        for p in paths_mobile_indices:
-            p = np.unique(np.asarray(p, dtype=np.int64).reshape(-1))
-            rows.append(p[~org_mobile[p]])
-        k = max(1, max(len(r) for r in rows))
-        if k > MAX_SET:
-            raise NotImplementedError("paths with more than %d new mobile locations are not supported yet" % MAX_SET)
-        idx = np.full((len(rows), k), -1, dtype=np.int32)
-        for c, r in enumerate(rows):
-            idx[c, :len(r)] = r
-        scores = state.score_sets(engine.to_dev(idx, dtype=torch.int32), None, delta_scalar=dm)
+        # The mobile flag is boolean (agent.py:377): already-mobile locations and repeats add nothing.
+        # A 2-D integer array [P, k] (-1 = empty slot) is taken as is -- the kernel skips already-mobile
+        # and duplicate slots itself; lists of lists are de-duplicated and padded on the host.
+        if isinstance(paths_mobile_indices, np.ndarray) and paths_mobile_indices.ndim == 2:
+            idx = paths_mobile_indices
+        else:
+            idx = _pad_paths(paths_mobile_indices, org_mobile)
+        if idx.shape[1] > MAX_SET:
+            raise NotImplementedError("paths with more than %d mobile locations are not supported yet" % MAX_SET)
+        if getattr(state, "_skip_src", None) is None or not np.array_equal(state._skip_src, org_mobile):
+            state._skip_src = org_mobile.copy()
+            state._skip = engine.to_dev(org_mobile.astype(np.uint8), dtype=torch.uint8)
+        scores = state.score_sets(engine.to_dev(idx, dtype=torch.int32), None, delta_scalar=dm, skip=state._skip)
         pair = state.argmax(scores)
+        self._last_path_scores = scores
         return int(pair[1].item())
 
 
 def patch(agent_cls):
     """Install the accelerated hot path on the reference's Agent class (agent.py:12)."""
     for name in ("update_model", "get_sampled_dataset", "_post_update", "predict", "greedy", "best_path",
-                 "_device_X", "_state_for", "_check_criterion"):
+                 "_device_X", "_state_for", "_check_criterion", "_sample_flags"):
         setattr(agent_cls, name, HotPath.__dict__[name])
     agent_cls.cov_matrix = HotPath.__dict__["cov_matrix"]
     return agent_cls

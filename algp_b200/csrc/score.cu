@@ -32,6 +32,7 @@ struct ScoreArgs {
   const int32_t* idx;      // [B x k]   (-1 = empty slot)
   const double* delta;     // [B x k] or null
   double delta_scalar;
+  const uint8_t* skip;     // [n] or null: slots at these locations add nothing (already-mobile, agent.py:377)
   int k;
   int64_t B;
   double H_base;
@@ -59,6 +60,7 @@ __global__ void __launch_bounds__(256) score_sets_k8_kernel(const ScoreArgs a) {
     int my_idx = (g < a.k) ? a.idx[cand * a.k + g] : -1;
     double my_delta = (g < a.k) ? (a.delta ? a.delta[cand * a.k + g] : a.delta_scalar) : 0.0;
     bool active = (my_idx >= 0) && (my_delta > 0.0);
+    if (active && a.skip && a.skip[my_idx]) active = false;
     // duplicates inside a set are idempotent (agent.py:377): keep the first
 #pragma unroll
     for (int s = 0; s < 7; ++s) {
@@ -167,6 +169,7 @@ __global__ void __launch_bounds__(256) score_sets_generic_kernel(const ScoreArgs
       int ix = (s < k) ? a.idx[cand * k + s] : -1;
       double dl = (s < k) ? (a.delta ? a.delta[cand * k + s] : a.delta_scalar) : 0.0;
       bool act = ix >= 0 && dl > 0.0;
+      if (act && a.skip && a.skip[ix]) act = false;
       for (int q = 0; q < s && act; ++q) {
         int oix = a.idx[cand * k + q];
         double odl = a.delta ? a.delta[cand * k + q] : a.delta_scalar;
@@ -256,7 +259,7 @@ int make_kernel_params(KernelParams* kp, int d, const double* log_ls_host, doubl
 extern "C" int algp_score_sets(const double* Wt, int64_t ldw, int64_t ncols, const double* X, int d,
                                const double* log_ls_host, double log_os, int kind, double noise,
                                const double* pi0, const int32_t* idx, const double* delta, double delta_scalar,
-                               int k, int64_t B, double H_base, double* scores, void* stream) {
+                               const uint8_t* skip, int k, int64_t B, double H_base, double* scores, void* stream) {
   if (!Wt || !X || !pi0 || !idx || !scores || k < 1 || k > SG_MAXK || B < 0 || ncols < 0) return ALGP_ERR_INVALID;
   if ((ldw & 3) || ((uintptr_t)Wt & 31)) return ALGP_ERR_INVALID;       // 256-bit row loads
   ScoreArgs a;
@@ -265,7 +268,7 @@ extern "C" int algp_score_sets(const double* Wt, int64_t ldw, int64_t ncols, con
   a.noise = noise; a.Wt = Wt; a.ldw = ldw;
   a.ncols16 = (int)((ncols + 15) / 16 * 16);
   if (a.ncols16 > ldw) return ALGP_ERR_INVALID;
-  a.X = X; a.pi0 = pi0; a.idx = idx; a.delta = delta; a.delta_scalar = delta_scalar;
+  a.X = X; a.pi0 = pi0; a.idx = idx; a.delta = delta; a.delta_scalar = delta_scalar; a.skip = skip;
   a.k = k; a.B = B; a.H_base = H_base; a.scores = scores;
   if (B == 0) return ALGP_OK;
   cudaStream_t st = (cudaStream_t)stream;

@@ -260,7 +260,7 @@ class PosteriorState(object):
             self._H_base = float(self.H_base_dev.item())
         return self._H_base
 
-    def score_sets(self, idx, delta=None, delta_scalar=0.0, H_base=None, out=None):
+    def score_sets(self, idx, delta=None, delta_scalar=0.0, H_base=None, out=None, skip=None):
         """scores[c] = H(S1_c) for candidate sets idx [B,k] (int32 device tensor, -1 = empty)."""
         B, k = idx.shape
         if out is None:
@@ -269,7 +269,7 @@ class PosteriorState(object):
         hb = self.H_base if H_base is None else H_base
         call("algp_score_sets", ptr(self.Wt), self.ldw, self.ncols, ptr(self.X), self.hyper.d, ls_p,
              self.hyper.log_os, self.hyper.kind, self.hyper.noise, ptr(self.pi), ptr(idx), ptr(delta),
-             float(delta_scalar), k, B, float(hb), ptr(out), stream())
+             float(delta_scalar), ptr(skip), k, B, float(hb), ptr(out), stream())
         return out
 
     def argmax(self, x, idx_offset=0, out=None):

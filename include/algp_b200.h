@@ -82,12 +82,13 @@ int algp_gemm_nt(const double* A, int64_t lda, const double* B, int64_t ldb, dou
  * (agent.py:317-347, 373-400).  Wt [n x ldw] = Sigma_{:,B} L^-T (first `ncols`
  * columns valid, the rest zero up to a multiple of 16), X [n x d] the field
  * coordinates, pi0[n] the base precisions, delta[B x k] (or delta_scalar) the
- * precision each slot adds.  scores[c] = H_base + n_new*CONST +
+ * precision each slot adds, skip[n] (or NULL) marks locations whose slots add
+ * nothing (already mobile-sampled: the flag is boolean, agent.py:377).  scores[c] = H_base + n_new*CONST +
  * 0.5*(logdet(I + D P_CC D) - sum(log(pi0+delta) - [pi0>0] log pi0)). */
 int algp_score_sets(const double* Wt, int64_t ldw, int64_t ncols, const double* X, int d,
                     const double* log_ls_host, double log_os, int kind, double noise,
                     const double* pi0, const int32_t* idx, const double* delta, double delta_scalar,
-                    int k, int64_t B, double H_base, double* scores, void* stream);
+                    const uint8_t* skip, int k, int64_t B, double H_base, double* scores, void* stream);
 /* greedy utilities for every location (k = 1 closed form, agent.py:341) */
 int algp_greedy_utilities(const double* diagP, const double* pi, const uint8_t* is_static, double d_static,
                           int64_t n, double* ut, void* stream);

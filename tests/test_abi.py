@@ -40,7 +40,7 @@ def test_invalid_arguments_are_rejected_without_a_gpu():
     # null pointers / unpadded sizes return ALGP_ERR_INVALID before any CUDA call
     assert _lib.lib.algp_potrf(None, 128, 128, None, 128, None, None) == 1
     assert _lib.lib.algp_trtri(None, 100, 100, None, 100, None, 0, None) == 1
-    assert _lib.lib.algp_score_sets(None, 0, 0, None, 2, None, 0.0, 0, 0.0, None, None, None, 0.0, 8, 1, 0.0, None, None) == 1
+    assert _lib.lib.algp_score_sets(None, 0, 0, None, 2, None, 0.0, 0, 0.0, None, None, None, 0.0, None, 8, 1, 0.0, None, None) == 1
 
 
 def test_product_never_imports_oracle():
