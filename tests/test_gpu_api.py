@@ -96,9 +96,13 @@ def test_against_reference_golden_gp(golden_dir, kind):
     np.testing.assert_allclose(cov, g["pd_cov"], rtol=0, atol=2e-3 * s2)
     _, mi = algp_b200.predictive_distribution(gp, *a, test_var=g["test_var"], return_mi=True)
     assert mi == pytest.approx(float(g["pd_mi"]), rel=2e-3)
-    # entropy_from_cov on the reference's own matrices: same number as its LU slogdet
-    assert algp_b200.entropy_from_cov(g["K_train_noise"]) == pytest.approx(float(g["ent_K_train_noise"]), rel=1e-8)
-    assert algp_b200.entropy_from_cov(g["pd_cov_tv"]) == pytest.approx(float(g["ent_pd_cov_tv"]), rel=1e-8)
+    # entropy_from_cov on the reference's own matrices.  The golden numbers come from the reference's
+    # float32 LU (np.linalg.slogdet of a float32 array, utils.py:193 via utils.py:314): 1e-4 tier.
+    assert algp_b200.entropy_from_cov(g["K_train_noise"]) == pytest.approx(float(g["ent_K_train_noise"]), rel=1e-5)
+    assert algp_b200.entropy_from_cov(g["pd_cov_tv"]) == pytest.approx(float(g["ent_pd_cov_tv"]), rel=1e-5)
+    # the same matrix in float64, against a float64 slogdet: log-det tier (1e-8)
+    K64 = g["K_train_noise"].astype(np.float64)
+    assert algp_b200.entropy_from_cov(K64) == pytest.approx(O.entropy_from_cov(K64), rel=1e-10)
     with pytest.raises(np.linalg.LinAlgError):
         algp_b200.entropy_from_cov(-np.eye(5))
     # GPR.predict (noise-inclusive; un-pinned stand-in semantics) at the reference-fitted theta
