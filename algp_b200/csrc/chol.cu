@@ -18,27 +18,41 @@
 // ---------------------------------------------------------------------------
 // GEMM launcher
 // ---------------------------------------------------------------------------
-template <int ALAY, int BLAY>
-static int gemm_launch_t(const GemmArgs& a, int batch, cudaStream_t st) {
+template <int ALAY, int BLAY, int TM, int TN>
+static int gemm_launch_t(GemmArgs a, int batch, cudaStream_t st) {
   static bool configured = false;
   if (!configured) {
-    ALGP_CUDA(cudaFuncSetAttribute(gemm_f64_kernel<ALAY, BLAY>, cudaFuncAttributeMaxDynamicSharedMemorySize, G_SMEM_BYTES));
+    ALGP_CUDA(cudaFuncSetAttribute(gemm_f64_kernel<ALAY, BLAY, TM, TN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   G_SMEM_BYTES(TM, TN)));
     configured = true;
   }
+  a.MT *= 128 / TM;                                  // callers count 128-tiles
+  a.NT *= 128 / TN;
   int64_t tiles = (a.tmap == TM_LOWER) ? (int64_t)a.MT * (a.MT + 1) / 2 : (int64_t)a.MT * a.NT;
   if (tiles <= 0 || batch <= 0) return ALGP_OK;
   dim3 grid((unsigned)tiles, 1, (unsigned)batch);
-  gemm_f64_kernel<ALAY, BLAY><<<grid, 256, G_SMEM_BYTES, st>>>(a);
+  gemm_f64_kernel<ALAY, BLAY, TM, TN><<<grid, 256, G_SMEM_BYTES(TM, TN), st>>>(a);
   ALGP_LAUNCH_CHECK();
   return ALGP_OK;
 }
 
+template <int ALAY, int BLAY>
+static int gemm_launch_l(const GemmArgs& a, int batch, cudaStream_t st) {
+  // Latency shapes when the 128-tile grid cannot fill the SMs.  Row-norm partials are per
+  // 128-column tile (keep 128x128); an in-place launch (NT == 1) may only shrink its row extent.
+  int64_t tiles = (a.tmap == TM_LOWER) ? (int64_t)a.MT * (a.MT + 1) / 2 : (int64_t)a.MT * a.NT;
+  const bool small = !a.rn_partial && tiles * batch < 120;
+  if (small && a.inplace_rows) return gemm_launch_t<ALAY, BLAY, 64, 128>(a, batch, st);
+  if (small) return gemm_launch_t<ALAY, BLAY, 64, 64>(a, batch, st);
+  return gemm_launch_t<ALAY, BLAY, 128, 128>(a, batch, st);
+}
+
 int gemm_f64_launch(const GemmArgs& a, int alay, int blay, int batch, cudaStream_t st) {
   if (a.K % GK) return ALGP_ERR_INVALID;
-  if (alay == LAY_KMAJ && blay == LAY_KMAJ) return gemm_launch_t<LAY_KMAJ, LAY_KMAJ>(a, batch, st);
-  if (alay == LAY_KMAJ && blay == LAY_MNMAJ) return gemm_launch_t<LAY_KMAJ, LAY_MNMAJ>(a, batch, st);
-  if (alay == LAY_MNMAJ && blay == LAY_MNMAJ) return gemm_launch_t<LAY_MNMAJ, LAY_MNMAJ>(a, batch, st);
-  return gemm_launch_t<LAY_MNMAJ, LAY_KMAJ>(a, batch, st);
+  if (alay == LAY_KMAJ && blay == LAY_KMAJ) return gemm_launch_l<LAY_KMAJ, LAY_KMAJ>(a, batch, st);
+  if (alay == LAY_KMAJ && blay == LAY_MNMAJ) return gemm_launch_l<LAY_KMAJ, LAY_MNMAJ>(a, batch, st);
+  if (alay == LAY_MNMAJ && blay == LAY_MNMAJ) return gemm_launch_l<LAY_MNMAJ, LAY_MNMAJ>(a, batch, st);
+  return gemm_launch_l<LAY_MNMAJ, LAY_KMAJ>(a, batch, st);
 }
 
 // ---------------------------------------------------------------------------
@@ -54,6 +68,68 @@ int gemm_f64_launch(const GemmArgs& a, int alay, int blay, int batch, cudaStream
 // ---------------------------------------------------------------------------
 #define P2_PITCH 129
 #define P2_SMEM_BYTES ((128 * P2_PITCH + 2 * 128 + 2 * 128 + 3 * 128) * 8)
+
+// Columns 16*IC .. 16*IC+15 of the elimination.  IC is a template parameter so that the register
+// patch is indexed statically and only the boundary block (i == IC or j == IC) needs a mask:
+// finished blocks (i < IC, j < IC) simply drop out of the unrolled loops.
+template <int IC>
+__device__ __forceinline__ void p2_eliminate_block(double (&acc)[8][8], double* colbuf, double* pivbuf, int ty, int tx,
+                                                   int tid, int j0, int* info) {
+#pragma unroll 1
+  for (int cc = 0; cc < 16; ++cc) {
+    const int c = IC * 16 + cc;
+    double* cb = colbuf + (c & 1) * 128;
+    if (tx == cc) {
+#pragma unroll
+      for (int i = IC; i < 8; ++i) cb[ty + 16 * i] = acc[i][IC];
+    }
+    __syncthreads();
+    const double piv = cb[c];
+    const bool ok = piv > 0.0;
+    const double rcp = ok ? 1.0 / piv : 0.0;
+    if (tid == 0) {
+      pivbuf[c] = piv;
+      if (!ok) atomicCAS(info, 0, j0 + c + 1);
+    }
+    double ri[8], cj[8];
+#pragma unroll
+    for (int i = IC; i < 8; ++i) ri[i] = cb[ty + 16 * i] * rcp;
+    if (ty <= cc) ri[IC] = 0.0;                 // rows at or above the pivot
+#pragma unroll
+    for (int j = IC; j < 8; ++j) cj[j] = cb[tx + 16 * j];
+    if (tx <= cc) cj[IC] = 0.0;                 // columns at or left of the pivot
+#pragma unroll
+    for (int i = IC; i < 8; ++i)
+#pragma unroll
+      for (int j = IC; j < 8; ++j) acc[i][j] = fma(-ri[i], cj[j], acc[i][j]);
+  }
+}
+
+// Same elimination applied to the identity: Y <- Ltilde^-1 (rows i >= IC, columns j <= IC are live).
+template <int IC>
+__device__ __forceinline__ void p2_invert_block(double (&acc)[8][8], const double* sL, double* rowbuf, int ty, int tx) {
+#pragma unroll 1
+  for (int cc = 0; cc < 16; ++cc) {
+    const int c = IC * 16 + cc;
+    if (c == 127) break;
+    double* rb = rowbuf + (c & 1) * 128;
+    if (ty == cc) {
+#pragma unroll
+      for (int j = 0; j <= IC; ++j) rb[tx + 16 * j] = acc[IC][j];
+    }
+    __syncthreads();
+    double ri[8], yj[8];
+#pragma unroll
+    for (int i = IC; i < 8; ++i) ri[i] = sL[(ty + 16 * i) * P2_PITCH + c];
+    if (ty <= cc) ri[IC] = 0.0;
+#pragma unroll
+    for (int j = 0; j <= IC; ++j) yj[j] = rb[tx + 16 * j];
+#pragma unroll
+    for (int i = IC; i < 8; ++i)
+#pragma unroll
+      for (int j = 0; j <= IC; ++j) acc[i][j] = fma(-ri[i], yj[j], acc[i][j]);
+  }
+}
 
 __global__ void __launch_bounds__(256, 1) potf2inv_kernel(double* __restrict__ A, int64_t ld, double* __restrict__ Linv,
                                                           int64_t ldi, int j0, int* __restrict__ info) {
@@ -73,39 +149,20 @@ __global__ void __launch_bounds__(256, 1) potf2inv_kernel(double* __restrict__ A
     for (int j = 0; j < 8; ++j) acc[i][j] = A[(int64_t)(ty + 16 * i) * ld + tx + 16 * j];
 
   // ---- phase 1: elimination ------------------------------------------------
-  for (int c = 0; c < 128; ++c) {
-    const int jc = c >> 4, txc = c & 15, ic = c >> 4;
-    double* cb = colbuf + (c & 1) * 128;
-    if (tx == txc) {
-#pragma unroll
-      for (int j = 0; j < 8; ++j)
-        if (j == jc) {
-#pragma unroll
-          for (int i = 0; i < 8; ++i) cb[ty + 16 * i] = acc[i][j];
-        }
-    }
-    __syncthreads();
-    const double piv = cb[c];
+  p2_eliminate_block<0>(acc, colbuf, pivbuf, ty, tx, tid, j0, info);
+  p2_eliminate_block<1>(acc, colbuf, pivbuf, ty, tx, tid, j0, info);
+  p2_eliminate_block<2>(acc, colbuf, pivbuf, ty, tx, tid, j0, info);
+  p2_eliminate_block<3>(acc, colbuf, pivbuf, ty, tx, tid, j0, info);
+  p2_eliminate_block<4>(acc, colbuf, pivbuf, ty, tx, tid, j0, info);
+  p2_eliminate_block<5>(acc, colbuf, pivbuf, ty, tx, tid, j0, info);
+  p2_eliminate_block<6>(acc, colbuf, pivbuf, ty, tx, tid, j0, info);
+  p2_eliminate_block<7>(acc, colbuf, pivbuf, ty, tx, tid, j0, info);
+  __syncthreads();
+  if (tid < 128) {
+    const double piv = pivbuf[tid];
     const bool ok = piv > 0.0;
-    const double rcp = ok ? 1.0 / piv : 0.0;
-    if (tid == 0) {
-      pivbuf[c] = piv;
-      rcpbuf[c] = rcp;
-      rsbuf[c] = ok ? 1.0 / sqrt(piv) : 0.0;
-      if (!ok) atomicCAS(info, 0, j0 + c + 1);
-    }
-    double ri[8], cj[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) ri[i] = (i >= ic && ty + 16 * i > c) ? cb[ty + 16 * i] * rcp : 0.0;
-#pragma unroll
-    for (int j = 0; j < 8; ++j) cj[j] = (j >= jc && tx + 16 * j > c) ? cb[tx + 16 * j] : 0.0;
-#pragma unroll
-    for (int i = 0; i < 8; ++i)
-      if (i >= ic) {
-#pragma unroll
-        for (int j = 0; j < 8; ++j)
-          if (j >= jc) acc[i][j] = fma(-ri[i], cj[j], acc[i][j]);
-      }
+    rcpbuf[tid] = ok ? 1.0 / piv : 0.0;
+    rsbuf[tid] = ok ? 1.0 / sqrt(piv) : 0.0;
   }
   __syncthreads();
 
@@ -130,31 +187,14 @@ __global__ void __launch_bounds__(256, 1) potf2inv_kernel(double* __restrict__ A
   __syncthreads();
 
   // ---- phase 2: Y <- Ltilde^-1 ----------------------------------------------
-  for (int c = 0; c < 127; ++c) {
-    const int ic = c >> 4, tyc = c & 15, jc = c >> 4;
-    double* rb = rowbuf + (c & 1) * 128;
-    if (ty == tyc) {
-#pragma unroll
-      for (int i = 0; i < 8; ++i)
-        if (i == ic) {
-#pragma unroll
-          for (int j = 0; j < 8; ++j) rb[tx + 16 * j] = acc[i][j];
-        }
-    }
-    __syncthreads();
-    double ri[8], yj[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) ri[i] = (i >= ic && ty + 16 * i > c) ? sL[(ty + 16 * i) * P2_PITCH + c] : 0.0;
-#pragma unroll
-    for (int j = 0; j < 8; ++j) yj[j] = (j <= jc) ? rb[tx + 16 * j] : 0.0;
-#pragma unroll
-    for (int i = 0; i < 8; ++i)
-      if (i >= ic) {
-#pragma unroll
-        for (int j = 0; j < 8; ++j)
-          if (j <= jc) acc[i][j] = fma(-ri[i], yj[j], acc[i][j]);
-      }
-  }
+  p2_invert_block<0>(acc, sL, rowbuf, ty, tx);
+  p2_invert_block<1>(acc, sL, rowbuf, ty, tx);
+  p2_invert_block<2>(acc, sL, rowbuf, ty, tx);
+  p2_invert_block<3>(acc, sL, rowbuf, ty, tx);
+  p2_invert_block<4>(acc, sL, rowbuf, ty, tx);
+  p2_invert_block<5>(acc, sL, rowbuf, ty, tx);
+  p2_invert_block<6>(acc, sL, rowbuf, ty, tx);
+  p2_invert_block<7>(acc, sL, rowbuf, ty, tx);
 #pragma unroll
   for (int i = 0; i < 8; ++i)
 #pragma unroll
@@ -176,41 +216,94 @@ static int potf2inv_launch(double* A, int64_t ld, double* Linv, int64_t ldi, int
 }
 
 // ---------------------------------------------------------------------------
-// potrf
+// potrf (right-looking, with look-ahead)
+//
+// The diagonal-block kernel runs on ONE SM; serialised with the trailing update it
+// would idle the other 147.  So each step first updates only block column j+1,
+// hands "factor block j+1 + solve panel j+1" to an auxiliary stream, and runs the
+// rest of step j's trailing update (block columns >= j+2, disjoint from the panel
+// being solved) on the caller's stream meanwhile.
 // ---------------------------------------------------------------------------
+struct PotrfAux {
+  cudaStream_t aux = nullptr;
+  cudaEvent_t col_ready = nullptr, panel_ready = nullptr;
+};
+static PotrfAux g_potrf_aux[64];
+
+static int potrf_aux_get(PotrfAux** out) {
+  int dev = 0;
+  ALGP_CUDA(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= 64) return ALGP_ERR_UNSUPPORTED;
+  PotrfAux& a = g_potrf_aux[dev];
+  if (!a.aux) {
+    ALGP_CUDA(cudaStreamCreateWithFlags(&a.aux, cudaStreamNonBlocking));
+    ALGP_CUDA(cudaEventCreateWithFlags(&a.col_ready, cudaEventDisableTiming));
+    ALGP_CUDA(cudaEventCreateWithFlags(&a.panel_ready, cudaEventDisableTiming));
+  }
+  *out = &a;
+  return ALGP_OK;
+}
+
+static int potrf_panel(double* A, int64_t ld, double* Linv, int64_t ldi, int j, int nb, cudaStream_t st) {
+  // P <- P * inv(L_jj)^T for the row blocks below the diagonal (in place: each CTA reads only the rows it writes)
+  const int rem = nb - 1 - j;
+  if (rem <= 0) return ALGP_OK;
+  double* panel = A + (int64_t)(j + 1) * ALGP_BLK * ld + (int64_t)j * ALGP_BLK;
+  GemmArgs g = gemm_args_default();
+  g.A = panel; g.lda = ld;
+  g.B = Linv + (int64_t)j * ALGP_BLK * (ldi + 1); g.ldb = ldi;
+  g.C = panel; g.ldc = ld;
+  g.MT = rem; g.NT = 1; g.K = ALGP_BLK;
+  g.inplace_rows = 1;
+  return gemm_f64_launch(g, LAY_KMAJ, LAY_KMAJ, 1, st);
+}
+
 extern "C" int algp_potrf(double* A, int64_t npad, int64_t ld, double* Linv, int64_t ldi, int* info_dev, void* stream) {
   if (!A || !Linv || !info_dev || npad < 0 || npad % ALGP_BLK || ld < npad || ldi < npad || (ld & 1) || (ldi & 1))
     return ALGP_ERR_INVALID;
   cudaStream_t st = (cudaStream_t)stream;
+  PotrfAux* ax = nullptr;
+  int rc = potrf_aux_get(&ax);
+  if (rc) return rc;
   ALGP_CUDA(cudaMemsetAsync(info_dev, 0, sizeof(int), st));
   const int nb = (int)(npad / ALGP_BLK);
-  for (int j = 0; j < nb; ++j) {
-    double* Ajj = A + (int64_t)j * ALGP_BLK * (ld + 1);
-    double* Ljj_inv = Linv + (int64_t)j * ALGP_BLK * (ldi + 1);
-    int rc = potf2inv_launch(Ajj, ld, Ljj_inv, ldi, j * ALGP_BLK, info_dev, st);
-    if (rc) return rc;
+  if (nb == 0) return ALGP_OK;
+  rc = potf2inv_launch(A, ld, Linv, ldi, 0, info_dev, st);
+  if (rc) return rc;
+  rc = potrf_panel(A, ld, Linv, ldi, 0, nb, st);
+  if (rc) return rc;
+  for (int j = 0; j + 1 < nb; ++j) {
     const int rem = nb - 1 - j;
-    if (rem == 0) break;
     double* panel = A + (int64_t)(j + 1) * ALGP_BLK * ld + (int64_t)j * ALGP_BLK;
-    {  // P <- P * inv(L_jj)^T   (in place: each CTA reads only the rows it writes)
-      GemmArgs g = gemm_args_default();
-      g.A = panel; g.lda = ld;
-      g.B = Ljj_inv; g.ldb = ldi;
-      g.C = panel; g.ldc = ld;
-      g.MT = rem; g.NT = 1; g.K = ALGP_BLK;
-      rc = gemm_f64_launch(g, LAY_KMAJ, LAY_KMAJ, 1, st);
-      if (rc) return rc;
-    }
-    {  // A22 <- A22 - P P^T on the lower tiles
+    {  // block column j+1 of the trailing update: A[i, j+1] -= P_i P_{j+1}^T, i >= j+1
       GemmArgs g = gemm_args_default();
       g.A = panel; g.lda = ld;
       g.B = panel; g.ldb = ld;
       g.C = A + (int64_t)(j + 1) * ALGP_BLK * (ld + 1); g.ldc = ld;
-      g.MT = rem; g.NT = rem; g.K = ALGP_BLK;
+      g.MT = rem; g.NT = 1; g.K = ALGP_BLK;
+      g.alpha = -1.0; g.beta = 1.0;
+      rc = gemm_f64_launch(g, LAY_KMAJ, LAY_KMAJ, 1, st);
+      if (rc) return rc;
+    }
+    ALGP_CUDA(cudaEventRecord(ax->col_ready, st));
+    ALGP_CUDA(cudaStreamWaitEvent(ax->aux, ax->col_ready, 0));
+    rc = potf2inv_launch(A + (int64_t)(j + 1) * ALGP_BLK * (ld + 1), ld, Linv + (int64_t)(j + 1) * ALGP_BLK * (ldi + 1), ldi,
+                         (j + 1) * ALGP_BLK, info_dev, ax->aux);
+    if (rc) return rc;
+    rc = potrf_panel(A, ld, Linv, ldi, j + 1, nb, ax->aux);
+    if (rc) return rc;
+    ALGP_CUDA(cudaEventRecord(ax->panel_ready, ax->aux));
+    if (rem > 1) {  // the rest of step j: lower tiles of the block columns >= j+2
+      GemmArgs g = gemm_args_default();
+      g.A = panel + (int64_t)ALGP_BLK * ld; g.lda = ld;
+      g.B = g.A; g.ldb = ld;
+      g.C = A + (int64_t)(j + 2) * ALGP_BLK * (ld + 1); g.ldc = ld;
+      g.MT = rem - 1; g.NT = rem - 1; g.K = ALGP_BLK;
       g.tmap = TM_LOWER; g.alpha = -1.0; g.beta = 1.0;
       rc = gemm_f64_launch(g, LAY_KMAJ, LAY_KMAJ, 1, st);
       if (rc) return rc;
     }
+    ALGP_CUDA(cudaStreamWaitEvent(st, ax->panel_ready, 0));
   }
   return ALGP_OK;
 }

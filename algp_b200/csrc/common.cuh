@@ -58,12 +58,41 @@ __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double
                : "d"(a), "d"(b));
 }
 
+// exp(x) for x <= 0, branch-free: k = rint(x log2 e), r = x - k ln2 (two-part Cody-Waite),
+// degree-13 Taylor polynomial on |r| <= 0.347 (truncation 4e-18), scaled by 2^k through the
+// exponent field.  ~18 fp64 ops against ~30 plus a special-case branch for exp(); error < 2 ulp.
+// Arguments below -708 (result < 3.4e-308) are clamped, so the result is never denormal.
+__device__ __forceinline__ double exp_nonpos(double x) {
+  x = fmax(x, -708.0);
+  const double magic = 6755399441055744.0;   // 1.5 * 2^52
+  double kf = fma(x, 1.4426950408889634, magic);
+  const int k = __double2loint(kf);
+  kf -= magic;
+  double r = fma(kf, -6.93147180369123816490e-01, x);
+  r = fma(kf, -1.90821492927058770002e-10, r);
+  double p = 1.6059043836821613e-10;          // 1/13!
+  p = fma(p, r, 2.08767569878681e-09);        // 1/12!
+  p = fma(p, r, 2.505210838544172e-08);       // 1/11!
+  p = fma(p, r, 2.755731922398589e-07);       // 1/10!
+  p = fma(p, r, 2.7557319223985893e-06);      // 1/9!
+  p = fma(p, r, 2.48015873015873e-05);        // 1/8!
+  p = fma(p, r, 1.984126984126984e-04);       // 1/7!
+  p = fma(p, r, 1.388888888888889e-03);       // 1/6!
+  p = fma(p, r, 8.333333333333333e-03);       // 1/5!
+  p = fma(p, r, 4.1666666666666664e-02);      // 1/4!
+  p = fma(p, r, 1.6666666666666666e-01);      // 1/3!
+  p = fma(p, r, 0.5);
+  p = fma(p, r, 1.0);
+  p = fma(p, r, 1.0);
+  return __hiloint2double(__double2hiint(p) + (k << 20), __double2loint(p));
+}
+
 // k(x,x') for already length-scaled squared distance r2
 __device__ __forceinline__ double kern_from_r2(double r2, int kind, double os) {
-  if (kind == 0) return os * exp(-0.5 * r2);
+  if (kind == 0) return os * exp_nonpos(-0.5 * r2);
   const double s3 = 1.7320508075688772;
   double r = sqrt(r2);
-  return os * (1.0 + s3 * r) * exp(-s3 * r);
+  return os * (1.0 + s3 * r) * exp_nonpos(-s3 * r);
 }
 __device__ __forceinline__ float kern_from_r2f(float r2, int kind, float os) {
   if (kind == 0) return os * expf(-0.5f * r2);

@@ -16,6 +16,8 @@
 // * All dimensions are multiples of 128 (the host pads with identity), so there
 //   is no edge predication; triangular structure is expressed as per-tile
 //   k-ranges and a lower-triangle tile map.
+// * Callers describe the problem in 128-tiles; the launcher switches to the 64x64 CTA
+//   tile (4x the CTAs, a quarter of the work each) when the grid would not fill the GPU.
 #pragma once
 #include "common.cuh"
 
@@ -24,8 +26,7 @@
 #define G_STAGES 4
 #define G_PITCH_K 20
 #define G_PITCH_MN 132
-#define G_OPER_DOUBLES (GT * G_PITCH_K)                 // 2560 >= 16*132 = 2112
-#define G_SMEM_BYTES (G_STAGES * 2 * G_OPER_DOUBLES * 8)  // 163840
+#define G_SMEM_BYTES(TM, TN) (G_STAGES * ((TM) + (TN)) * G_PITCH_K * 8)   // 163840 for 128x128, 81920 for 64x64
 
 enum { LAY_KMAJ = 0, LAY_MNMAJ = 1 };
 enum { TM_FULL = 0, TM_LOWER = 1 };
@@ -36,40 +37,50 @@ struct GemmArgs {
   const double* A; int64_t lda; int64_t a_bs;
   const double* B; int64_t ldb; int64_t b_bs;
   double* C; int64_t ldc; int64_t c_bs;
-  int MT, NT, K;
+  int MT, NT, K;                      // tile counts in units of the CTA tile edge chosen by the launcher
   int tmap, kbeg_rule, kend_rule;
   double alpha, beta;
   int64_t rows_left0, rows_left_bs;   // batch z has rows_left0 - z*rows_left_bs valid rows (ragged last batch)
   double* rn_partial; int rn_nt;      // optional: rn_partial[row*rn_nt + nt] = sum over the tile's 128 cols of value^2
   int store_c;
+  int inplace_rows;                   // C aliases A: a CTA must cover the full row extent it reads
 };
 
-template <int LAY>
+// TM x TN = CTA tile.  128x128 (8 warps x 64x32) is the throughput shape; 64x64 is the latency
+// shape for launches with too few 128-tiles to fill the 148 SMs; 64x128 is the latency shape for
+// the in-place panel solve, where a CTA must own whole rows (it overwrites its own A operand).
+template <int LAY, int TM>
 __device__ __forceinline__ void g_load_tile(double* s, const double* __restrict__ g, int64_t ld, int64_t mn0, int k0, int tid) {
   if (LAY == LAY_KMAJ) {
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
+    for (int i = 0; i < TM / 32; ++i) {          // TM rows x 8 granules of 16 B
       int q = tid + 256 * i;
       int r = q >> 3, gk = (q & 7) * 2;
       cp_async16(s + r * G_PITCH_K + gk, g + (mn0 + r) * ld + k0 + gk);
     }
   } else {
+    constexpr int GPR = TM / 2;                   // granules per k-row
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
+    for (int i = 0; i < TM / 32; ++i) {
       int q = tid + 256 * i;
-      int kk = q >> 6, gm = (q & 63) * 2;
-      cp_async16(s + kk * G_PITCH_MN + gm, g + (int64_t)(k0 + kk) * ld + mn0 + gm);
+      int kk = q / GPR, gm = (q % GPR) * 2;
+      cp_async16(s + kk * (TM + 4) + gm, g + (int64_t)(k0 + kk) * ld + mn0 + gm);
     }
   }
 }
 
-template <int LAY>
+template <int LAY, int TM>
 __device__ __forceinline__ double g_frag(const double* s, int row, int k) {
-  return (LAY == LAY_KMAJ) ? s[row * G_PITCH_K + k] : s[k * G_PITCH_MN + row];
+  return (LAY == LAY_KMAJ) ? s[row * G_PITCH_K + k] : s[k * (TM + 4) + row];
 }
 
-template <int ALAY, int BLAY>
-__global__ void __launch_bounds__(256, 1) gemm_f64_kernel(const GemmArgs p) {
+template <int ALAY, int BLAY, int TM, int TN>
+__global__ void __launch_bounds__(256, (TM == 128 && TN == 128) ? 1 : 2) gemm_f64_kernel(const GemmArgs p) {
+  constexpr int MI = TM / 16, NI = TN / 32;     // 8x8 accumulator blocks per warp (rows x cols)
+  constexpr int WM = TM / 2, WN = TN / 4;       // warp sub-tile
+  constexpr int OPER_A = TM * G_PITCH_K;        // doubles per operand per stage (>= 16*(TM+4))
+  constexpr int OPER_B = TN * G_PITCH_K;
+  constexpr int STAGE = OPER_A + OPER_B;
   extern __shared__ __align__(16) double g_smem[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int wm = warp >> 2, wn = warp & 3, g = lane >> 2, t = lane & 3;
@@ -87,31 +98,31 @@ __global__ void __launch_bounds__(256, 1) gemm_f64_kernel(const GemmArgs p) {
     mt = (int)(blockIdx.x % p.MT);
   }
   const int z = blockIdx.z;
-  if ((int64_t)mt * GT >= p.rows_left0 - (int64_t)z * p.rows_left_bs) return;
+  if ((int64_t)mt * TM >= p.rows_left0 - (int64_t)z * p.rows_left_bs) return;
 
   const double* __restrict__ A = p.A + (int64_t)z * p.a_bs;
   const double* __restrict__ B = p.B + (int64_t)z * p.b_bs;
   double* __restrict__ C = p.C ? p.C + (int64_t)z * p.c_bs : nullptr;
 
-  int kb = (p.kbeg_rule == KB_MT) ? mt * GT : (p.kbeg_rule == KB_NT) ? nt * GT : 0;
-  int ke = (p.kend_rule == KE_MT1) ? (mt + 1) * GT : (p.kend_rule == KE_NT1) ? (nt + 1) * GT : p.K;
+  int kb = (p.kbeg_rule == KB_MT) ? mt * TM : (p.kbeg_rule == KB_NT) ? nt * TN : 0;
+  int ke = (p.kend_rule == KE_MT1) ? (mt + 1) * TM : (p.kend_rule == KE_NT1) ? (nt + 1) * TN : p.K;
   if (ke > p.K) ke = p.K;
   const int KT = (ke > kb) ? (ke - kb) / GK : 0;
-  const int64_t m0 = (int64_t)mt * GT, n0 = (int64_t)nt * GT;
+  const int64_t m0 = (int64_t)mt * TM, n0 = (int64_t)nt * TN;
 
-  double acc[8][4][2];
+  double acc[MI][NI][2];
 #pragma unroll
-  for (int i = 0; i < 8; ++i)
+  for (int i = 0; i < MI; ++i)
 #pragma unroll
-    for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+    for (int j = 0; j < NI; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
 
   // ---- pipeline -----------------------------------------------------------
 #pragma unroll
   for (int s = 0; s < G_STAGES - 1; ++s) {
     if (s < KT) {
-      double* sa = g_smem + (size_t)s * 2 * G_OPER_DOUBLES;
-      g_load_tile<ALAY>(sa, A, p.lda, m0, kb + s * GK, tid);
-      g_load_tile<BLAY>(sa + G_OPER_DOUBLES, B, p.ldb, n0, kb + s * GK, tid);
+      double* sa = g_smem + (size_t)s * STAGE;
+      g_load_tile<ALAY, TM>(sa, A, p.lda, m0, kb + s * GK, tid);
+      g_load_tile<BLAY, TN>(sa + OPER_A, B, p.ldb, n0, kb + s * GK, tid);
     }
     cp_async_commit();
   }
@@ -121,38 +132,38 @@ __global__ void __launch_bounds__(256, 1) gemm_f64_kernel(const GemmArgs p) {
     {
       int nk = kt + G_STAGES - 1;
       if (nk < KT) {
-        double* sa = g_smem + (size_t)(nk % G_STAGES) * 2 * G_OPER_DOUBLES;
-        g_load_tile<ALAY>(sa, A, p.lda, m0, kb + nk * GK, tid);
-        g_load_tile<BLAY>(sa + G_OPER_DOUBLES, B, p.ldb, n0, kb + nk * GK, tid);
+        double* sa = g_smem + (size_t)(nk % G_STAGES) * STAGE;
+        g_load_tile<ALAY, TM>(sa, A, p.lda, m0, kb + nk * GK, tid);
+        g_load_tile<BLAY, TN>(sa + OPER_A, B, p.ldb, n0, kb + nk * GK, tid);
       }
       cp_async_commit();
     }
-    const double* sa = g_smem + (size_t)(kt % G_STAGES) * 2 * G_OPER_DOUBLES;
-    const double* sb = sa + G_OPER_DOUBLES;
+    const double* sa = g_smem + (size_t)(kt % G_STAGES) * STAGE;
+    const double* sb = sa + OPER_A;
 #pragma unroll
     for (int ks = 0; ks < GK / 4; ++ks) {
-      double af[8], bf[4];
+      double af[MI], bf[NI];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) af[i] = g_frag<ALAY>(sa, wm * 64 + i * 8 + g, ks * 4 + t);
+      for (int i = 0; i < MI; ++i) af[i] = g_frag<ALAY, TM>(sa, wm * WM + i * 8 + g, ks * 4 + t);
 #pragma unroll
-      for (int j = 0; j < 4; ++j) bf[j] = g_frag<BLAY>(sb, wn * 32 + j * 8 + g, ks * 4 + t);
+      for (int j = 0; j < NI; ++j) bf[j] = g_frag<BLAY, TN>(sb, wn * WN + j * 8 + g, ks * 4 + t);
 #pragma unroll
-      for (int i = 0; i < 8; ++i)
+      for (int i = 0; i < MI; ++i)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) dmma884(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+        for (int j = 0; j < NI; ++j) dmma884(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
     }
   }
   cp_async_wait<0>();
 
   // ---- epilogue -----------------------------------------------------------
-  double rs[8];
+  double rs[MI];
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
+  for (int i = 0; i < MI; ++i) {
     rs[i] = 0.0;
-    const int64_t r = m0 + wm * 64 + i * 8 + g;
+    const int64_t r = m0 + wm * WM + i * 8 + g;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int64_t c = n0 + wn * 32 + j * 8 + 2 * t;
+    for (int j = 0; j < NI; ++j) {
+      const int64_t c = n0 + wn * WN + j * 8 + 2 * t;
       double v0 = p.alpha * acc[i][j][0], v1 = p.alpha * acc[i][j][1];
       if (p.beta != 0.0) {
         double2 old = *reinterpret_cast<const double2*>(C + r * p.ldc + c);
@@ -165,17 +176,17 @@ __global__ void __launch_bounds__(256, 1) gemm_f64_kernel(const GemmArgs p) {
   }
   if (p.rn_partial) {
     __syncthreads();                       // pipeline smem is dead: reuse it
-    double* red = g_smem;                  // [4][128]
+    double* red = g_smem;                  // [4][TM]
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
+    for (int i = 0; i < MI; ++i) {
       double s = rs[i];
       s += __shfl_xor_sync(0xffffffffu, s, 1);
       s += __shfl_xor_sync(0xffffffffu, s, 2);
-      if (t == 0) red[wn * GT + wm * 64 + i * 8 + g] = s;
+      if (t == 0) red[wn * TM + wm * WM + i * 8 + g] = s;
     }
     __syncthreads();
-    if (tid < GT)
-      p.rn_partial[(m0 + tid) * p.rn_nt + nt] = (red[tid] + red[GT + tid]) + (red[2 * GT + tid] + red[3 * GT + tid]);
+    if (tid < TM)
+      p.rn_partial[(m0 + tid) * p.rn_nt + nt] = (red[tid] + red[TM + tid]) + (red[2 * TM + tid] + red[3 * TM + tid]);
   }
 }
 
@@ -193,5 +204,6 @@ static inline GemmArgs gemm_args_default() {
   a.rows_left0 = ((int64_t)1) << 60; a.rows_left_bs = 0;
   a.rn_partial = nullptr; a.rn_nt = 0;
   a.store_c = 1;
+  a.inplace_rows = 0;
   return a;
 }

@@ -36,18 +36,86 @@ template <typename T> struct Vec;
 template <> struct Vec<double> { static constexpr int N = 2; typedef double2 type; };
 template <> struct Vec<float> { static constexpr int N = 4; typedef float4 type; };
 
-template <typename T> __device__ __forceinline__ T kern_eval(T r2, int kind, T os);
-template <> __device__ __forceinline__ double kern_eval<double>(double r2, int kind, double os) { return kern_from_r2(r2, kind, os); }
-template <> __device__ __forceinline__ float kern_eval<float>(float r2, int kind, float os) { return kern_from_r2f(r2, kind, os); }
+template <typename T, int KIND> __device__ __forceinline__ T kern_eval(T r2, T os);
+template <> __device__ __forceinline__ double kern_eval<double, 0>(double r2, double os) { return os * exp_nonpos(-0.5 * r2); }
+template <> __device__ __forceinline__ double kern_eval<double, 1>(double r2, double os) {
+  const double s3 = 1.7320508075688772;
+  const double r = sqrt(r2);
+  return os * fma(s3, r, 1.0) * exp_nonpos(-s3 * r);
+}
+template <> __device__ __forceinline__ float kern_eval<float, 0>(float r2, float os) { return kern_from_r2f(r2, 0, os); }
+template <> __device__ __forceinline__ float kern_eval<float, 1>(float r2, float os) { return kern_from_r2f(r2, 1, os); }
 
 #define KB_ROWS 64
 
-template <typename T, int D, bool DOT>
+// FAST: the tile lies strictly inside [0,n1) x [0,n2) and carries no diagonal work, so the
+// row loop is distance -> kernel -> 16-byte store with no masking.
+template <typename T, int D, int KIND, bool DOT, bool FAST>
+__device__ __forceinline__ void kbuild_rows(const KbuildArgs& a, const T (*sx1)[ALGP_MAX_D], const T (*sx2)[128 * Vec<T>::N],
+                                            const T (*x2r)[D == 0 ? 1 : D], const T* dv, double (*sred)[4], int d, int wr,
+                                            int wc, int lane, int64_t row0, int64_t c0, int lc) {
+  constexpr int VEC = Vec<T>::N;
+  const T os = (T)a.kp.outputscale;
+  T* outp = (T*)a.out + (row0 + (int64_t)wr * 32) * a.ld + c0;
+  const bool col_ok = FAST || (c0 < a.n2_pad);
+#pragma unroll 2
+  for (int rr = 0; rr < 32; ++rr, outp += a.ld) {
+    const int r = wr * 32 + rr;
+    const int64_t gr = row0 + r;
+    if (!FAST && gr >= a.n1_pad) break;          // warp-uniform
+    T val[VEC];
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) {
+      T r2 = (T)0;
+      if (D == 0) {
+        for (int j = 0; j < d; ++j) {
+          T df = sx1[r][j] - sx2[j][lc + v];
+          r2 = fma(df, df, r2);
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < (D == 0 ? 1 : D); ++j) {
+          T df = sx1[r][j] - x2r[v][j];
+          r2 = fma(df, df, r2);
+        }
+      }
+      T k = kern_eval<T, KIND>(r2, os);
+      if (!FAST) {
+        const int64_t gc = c0 + v;
+        if (!((gr < a.n1) && (gc < a.n2))) k = (T)0;
+        if (gr == gc) {
+          if (gr < a.n1) {
+            double add = a.diag_scalar + (a.diag_add ? a.diag_add[gr] : 0.0);
+            k = (T)((double)k + add);
+          } else if (a.pad_identity) {
+            k = (T)1;
+          }
+        }
+      }
+      val[v] = k;
+    }
+    if (col_ok) {
+      typename Vec<T>::type pk;
+#pragma unroll
+      for (int v = 0; v < VEC; ++v) ((T*)&pk)[v] = val[v];
+      *reinterpret_cast<typename Vec<T>::type*>(outp) = pk;
+    }
+    if (DOT) {
+      double part = 0.0;
+#pragma unroll
+      for (int v = 0; v < VEC; ++v) part += (double)val[v] * (double)dv[v];
+      part = warp_sum(part);
+      if (lane == 0) sred[r][wc] = part;
+    }
+  }
+}
+
+template <typename T, int D, int KIND, bool DOT>
 __global__ void __launch_bounds__(256) kbuild_kernel(const KbuildArgs a) {
   constexpr int VEC = Vec<T>::N;
   constexpr int TILE_C = 128 * VEC;
-  __shared__ T sx1[KB_ROWS][ALGP_MAX_D];
-  __shared__ T sx2[D == 0 ? ALGP_MAX_D : 1][D == 0 ? TILE_C : 1];
+  __shared__ __align__(16) T sx1[KB_ROWS][ALGP_MAX_D];
+  __shared__ T sx2[D == 0 ? ALGP_MAX_D : 1][TILE_C];
   __shared__ double sred[KB_ROWS][4];
 
   const int d = (D == 0) ? a.kp.d : D;
@@ -64,7 +132,7 @@ __global__ void __launch_bounds__(256) kbuild_kernel(const KbuildArgs a) {
     double v = (gr < a.n1) ? a.x1[gr * d + j] : 0.0;
     sx1[r][j] = (T)((T)v * (T)a.kp.inv_ls[j]);
   }
-  T x2r[D == 0 ? 1 : VEC][D == 0 ? 1 : D];
+  T x2r[VEC][D == 0 ? 1 : D];
   if (D == 0) {
     for (int i = tid; i < TILE_C * d; i += 256) {
       int c = i / d, j = i - c * d;
@@ -83,65 +151,19 @@ __global__ void __launch_bounds__(256) kbuild_kernel(const KbuildArgs a) {
       }
   }
   T dv[VEC];
-  if (DOT) {
 #pragma unroll
-    for (int v = 0; v < VEC; ++v) dv[v] = (c0 + v < a.n2) ? (T)a.dot_vec[c0 + v] : (T)0;
-  }
+  for (int v = 0; v < VEC; ++v) dv[v] = (DOT && c0 + v < a.n2) ? (T)a.dot_vec[c0 + v] : (T)0;
   __syncthreads();
 
-  const T os = (T)a.kp.outputscale;
-  const int kind = a.kp.kind;
   const int lc = wc * 32 * VEC + lane * VEC;   // column inside the tile
-  T* outp = (T*)a.out;
+  const bool diag_work = (a.diag_add != nullptr) || (a.diag_scalar != 0.0) || (a.pad_identity != 0);
+  const bool touches_diag = (row0 < col0 + TILE_C) && (col0 < row0 + KB_ROWS);
+  const bool fast = (row0 + KB_ROWS <= a.n1) && (col0 + TILE_C <= a.n2) && !(diag_work && touches_diag);
+  if (fast)
+    kbuild_rows<T, D, KIND, DOT, true>(a, sx1, sx2, x2r, dv, sred, d, wr, wc, lane, row0, c0, lc);
+  else
+    kbuild_rows<T, D, KIND, DOT, false>(a, sx1, sx2, x2r, dv, sred, d, wr, wc, lane, row0, c0, lc);
 
-  for (int rr = 0; rr < 32; ++rr) {
-    const int r = wr * 32 + rr;
-    const int64_t gr = row0 + r;
-    if (gr >= a.n1_pad) break;                 // warp-uniform
-    T val[VEC];
-#pragma unroll
-    for (int v = 0; v < VEC; ++v) {
-      T r2 = (T)0;
-      if (D == 0) {
-        for (int j = 0; j < d; ++j) {
-          T df = sx1[r][j] - sx2[j][lc + v];
-          r2 += df * df;
-        }
-      } else {
-#pragma unroll
-        for (int j = 0; j < (D == 0 ? 1 : D); ++j) {
-          T df = sx1[r][j] - x2r[v][j];
-          r2 += df * df;
-        }
-      }
-      T k = kern_eval<T>(r2, kind, os);
-      const int64_t gc = c0 + v;
-      const bool valid = (gr < a.n1) && (gc < a.n2);
-      if (!valid) k = (T)0;
-      if (gr == gc) {
-        if (gr < a.n1) {
-          double add = a.diag_scalar + (a.diag_add ? a.diag_add[gr] : 0.0);
-          k = (T)((double)k + add);
-        } else if (a.pad_identity) {
-          k = (T)1;
-        }
-      }
-      val[v] = k;
-    }
-    if (c0 < a.n2_pad) {
-      typename Vec<T>::type pk;
-#pragma unroll
-      for (int v = 0; v < VEC; ++v) ((T*)&pk)[v] = val[v];
-      *reinterpret_cast<typename Vec<T>::type*>(outp + gr * a.ld + c0) = pk;
-    }
-    if (DOT) {
-      double part = 0.0;
-#pragma unroll
-      for (int v = 0; v < VEC; ++v) part += (double)val[v] * (double)dv[v];
-      part = warp_sum(part);
-      if (lane == 0) sred[r][wc] = part;
-    }
-  }
   if (DOT) {
     __syncthreads();
     if (tid < KB_ROWS) {
@@ -173,18 +195,23 @@ __global__ void scatter_add_kernel(double* __restrict__ M, int64_t ld, const int
   if (r >= 0) M[(int64_t)r * ld + k] += v;
 }
 
-template <typename T, bool DOT>
-static int launch_kbuild(const KbuildArgs& a, cudaStream_t st) {
+template <typename T, int KIND, bool DOT>
+static int launch_kbuild_k(const KbuildArgs& a, cudaStream_t st) {
   constexpr int TILE_C = 128 * Vec<T>::N;
   dim3 grid((unsigned)((a.n2_pad + TILE_C - 1) / TILE_C), (unsigned)((a.n1_pad + KB_ROWS - 1) / KB_ROWS));
   if (grid.y > 65535) return ALGP_ERR_INVALID;
   switch (a.kp.d) {
-    case 2: kbuild_kernel<T, 2, DOT><<<grid, 256, 0, st>>>(a); break;
-    case 6: kbuild_kernel<T, 6, DOT><<<grid, 256, 0, st>>>(a); break;
-    default: kbuild_kernel<T, 0, DOT><<<grid, 256, 0, st>>>(a); break;
+    case 2: kbuild_kernel<T, 2, KIND, DOT><<<grid, 256, 0, st>>>(a); break;
+    case 6: kbuild_kernel<T, 6, KIND, DOT><<<grid, 256, 0, st>>>(a); break;
+    default: kbuild_kernel<T, 0, KIND, DOT><<<grid, 256, 0, st>>>(a); break;
   }
   ALGP_LAUNCH_CHECK();
   return ALGP_OK;
+}
+
+template <typename T, bool DOT>
+static int launch_kbuild(const KbuildArgs& a, cudaStream_t st) {
+  return a.kp.kind == 0 ? launch_kbuild_k<T, 0, DOT>(a, st) : launch_kbuild_k<T, 1, DOT>(a, st);
 }
 
 int make_kernel_params(KernelParams* kp, int d, const double* log_ls_host, double log_os, int kind);

@@ -202,24 +202,29 @@ def fit_predict_bench(torch, engine, n_train, grid_side, reps, peak_hbm):
     names = ["kbuild_train", "potrf", "trtri", "solve", "kbuild_cross_mean", "variance_trmm"]
     times = {k: [] for k in names + ["total"]}
     M = xs.shape[0]
+    Npad = max(128, engine.pad_to(n_train))
+    Mpad = max(128, engine.pad_to(M))
+    dev = xd.device
+    # buffers live across repetitions: the timed region is kernels only (inputs resident in HBM)
+    A = torch.empty((Npad, Npad), dtype=torch.float64, device=dev)
+    Linv = torch.empty((Npad, Npad), dtype=torch.float64, device=dev)
+    Ks = torch.empty((Mpad, Npad), dtype=torch.float64, device=dev)
+    work = torch.empty(max(2, _lib.lib.algp_trtri_work_doubles(Npad)), dtype=torch.float64, device=dev)
+    info = torch.zeros(1, dtype=torch.int32, device=dev)
     for rep in range(reps + 1):
         marks = [ev() for _ in range(len(names) + 1)]
         marks[0].record()
-        Npad = max(128, engine.pad_to(n_train))
-        A, _ = engine.kbuild(hy, xd, None, Npad, Npad, var, hy.noise, True)
+        engine.kbuild(hy, xd, None, Npad, Npad, var, hy.noise, True, out=A)
         marks[1].record()
-        Linv = torch.empty((Npad, Npad), dtype=torch.float64, device=xd.device)
-        info = torch.zeros(1, dtype=torch.int32, device=xd.device)
         _lib.call("algp_potrf", _lib.ptr(A), Npad, Npad, _lib.ptr(Linv), Npad, _lib.ptr(info), _lib.stream())
         marks[2].record()
-        work = torch.empty(max(2, _lib.lib.algp_trtri_work_doubles(Npad)), dtype=torch.float64, device=xd.device)
         _lib.call("algp_trtri", _lib.ptr(A), Npad, Npad, _lib.ptr(Linv), Npad, _lib.ptr(work), 1, _lib.stream())
         marks[3].record()
         f = engine.GPFactor.__new__(engine.GPFactor)
         f.hyper, f.x, f.N, f.Npad, f.L, f.Linv, f.info = hy, xd, n_train, Npad, A, Linv, info
         alpha, beta = f.solve(y0)
         marks[4].record()
-        Ks, part = f.cross(xsd, alpha)
+        _, part = engine.kbuild(hy, xsd, xd, Mpad, Npad, out=Ks, dot_vec=alpha)
         mu = engine.rowsum(part, 1.0, float(y.mean()), rows=M)
         marks[5].record()
         _, rn = f.whiten(Ks, want_V=False)
@@ -233,7 +238,6 @@ def fit_predict_bench(torch, engine, n_train, grid_side, reps, peak_hbm):
         for i, k in enumerate(names):
             times[k].append(marks[i].elapsed_time(marks[i + 1]))
         times["total"].append(marks[0].elapsed_time(marks[-1]))
-        del A, Linv, work, Ks, part, rn
     med = {k: float(np.median(v)) for k, v in times.items()}
     N = float(max(128, engine.pad_to(n_train)))
     Mp = float(max(128, engine.pad_to(M)))
