@@ -18,11 +18,11 @@
 // ---------------------------------------------------------------------------
 // GEMM launcher
 // ---------------------------------------------------------------------------
-template <int ALAY, int BLAY, int TM, int TN>
+template <int ALAY, int BLAY, int TM, int TN, bool SUBC>
 static int gemm_launch_t(GemmArgs a, int batch, cudaStream_t st) {
   static bool configured = false;
   if (!configured) {
-    ALGP_CUDA(cudaFuncSetAttribute(gemm_f64_kernel<ALAY, BLAY, TM, TN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    ALGP_CUDA(cudaFuncSetAttribute(gemm_f64_kernel<ALAY, BLAY, TM, TN, SUBC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    G_SMEM_BYTES(TM, TN)));
     configured = true;
   }
@@ -31,7 +31,7 @@ static int gemm_launch_t(GemmArgs a, int batch, cudaStream_t st) {
   int64_t tiles = (a.tmap == TM_LOWER) ? (int64_t)a.MT * (a.MT + 1) / 2 : (int64_t)a.MT * a.NT;
   if (tiles <= 0 || batch <= 0) return ALGP_OK;
   dim3 grid((unsigned)tiles, 1, (unsigned)batch);
-  gemm_f64_kernel<ALAY, BLAY, TM, TN><<<grid, 256, G_SMEM_BYTES(TM, TN), st>>>(a);
+  gemm_f64_kernel<ALAY, BLAY, TM, TN, SUBC><<<grid, 256, G_SMEM_BYTES(TM, TN), st>>>(a);
   ALGP_LAUNCH_CHECK();
   return ALGP_OK;
 }
@@ -42,9 +42,14 @@ static int gemm_launch_l(const GemmArgs& a, int batch, cudaStream_t st) {
   // 128-column tile (keep 128x128); an in-place launch (NT == 1) may only shrink its row extent.
   int64_t tiles = (a.tmap == TM_LOWER) ? (int64_t)a.MT * (a.MT + 1) / 2 : (int64_t)a.MT * a.NT;
   const bool small = !a.rn_partial && tiles * batch < 120;
-  if (small && a.inplace_rows) return gemm_launch_t<ALAY, BLAY, 64, 128>(a, batch, st);
-  if (small) return gemm_launch_t<ALAY, BLAY, 64, 64>(a, batch, st);
-  return gemm_launch_t<ALAY, BLAY, 128, 128>(a, batch, st);
+  const bool subc = a.alpha == -1.0 && a.beta == 1.0 && a.store_c && !a.rn_partial && !a.inplace_rows && a.C;
+  if (subc) {
+    if (small) return gemm_launch_t<ALAY, BLAY, 64, 64, true>(a, batch, st);
+    return gemm_launch_t<ALAY, BLAY, 128, 128, true>(a, batch, st);
+  }
+  if (small && a.inplace_rows) return gemm_launch_t<ALAY, BLAY, 64, 128, false>(a, batch, st);
+  if (small) return gemm_launch_t<ALAY, BLAY, 64, 64, false>(a, batch, st);
+  return gemm_launch_t<ALAY, BLAY, 128, 128, false>(a, batch, st);
 }
 
 int gemm_f64_launch(const GemmArgs& a, int alay, int blay, int batch, cudaStream_t st) {

@@ -74,7 +74,10 @@ __device__ __forceinline__ double g_frag(const double* s, int row, int k) {
   return (LAY == LAY_KMAJ) ? s[row * G_PITCH_K + k] : s[k * (TM + 4) + row];
 }
 
-template <int ALAY, int BLAY, int TM, int TN>
+// SUBC: the update C <- C - A*B (alpha = -1, beta = 1: every Cholesky trailing update).  The
+// accumulators start as C, loaded while the cp.async prologue is in flight, and B fragments are
+// negated, so the epilogue is a plain store and no C read sits exposed after the last MMA.
+template <int ALAY, int BLAY, int TM, int TN, bool SUBC>
 __global__ void __launch_bounds__(256, (TM == 128 && TN == 128) ? 1 : 2) gemm_f64_kernel(const GemmArgs p) {
   constexpr int MI = TM / 16, NI = TN / 32;     // 8x8 accumulator blocks per warp (rows x cols)
   constexpr int WM = TM / 2, WN = TN / 4;       // warp sub-tile
@@ -93,8 +96,15 @@ __global__ void __launch_bounds__(256, (TM == 128 && TN == 128) ? 1 : 2) gemm_f6
     while ((mt + 1) * (mt + 2) / 2 <= L) ++mt;
     while (mt * (mt + 1) / 2 > L) --mt;
     nt = L - mt * (mt + 1) / 2;
+  } else if (p.kbeg_rule == KB_MT || p.kend_rule == KE_MT1) {
+    // k-extent depends on mt: issue the long tiles first (KE_MT1: large mt, KB_MT: small mt)
+    int q = (int)(blockIdx.x / p.NT);
+    mt = (p.kend_rule == KE_MT1) ? p.MT - 1 - q : q;
+    nt = (int)(blockIdx.x % p.NT);
   } else {
-    nt = p.NT - 1 - (int)(blockIdx.x / p.MT);     // long-k tiles (large nt under KE_NT1) first
+    // KE_NT1: large nt is long; KB_NT: small nt is long; uniform otherwise
+    int q = (int)(blockIdx.x / p.MT);
+    nt = (p.kbeg_rule == KB_NT) ? q : p.NT - 1 - q;
     mt = (int)(blockIdx.x % p.MT);
   }
   const int z = blockIdx.z;
@@ -110,13 +120,7 @@ __global__ void __launch_bounds__(256, (TM == 128 && TN == 128) ? 1 : 2) gemm_f6
   const int KT = (ke > kb) ? (ke - kb) / GK : 0;
   const int64_t m0 = (int64_t)mt * TM, n0 = (int64_t)nt * TN;
 
-  double acc[MI][NI][2];
-#pragma unroll
-  for (int i = 0; i < MI; ++i)
-#pragma unroll
-    for (int j = 0; j < NI; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
-
-  // ---- pipeline -----------------------------------------------------------
+  // ---- pipeline prologue --------------------------------------------------
 #pragma unroll
   for (int s = 0; s < G_STAGES - 1; ++s) {
     if (s < KT) {
@@ -126,6 +130,21 @@ __global__ void __launch_bounds__(256, (TM == 128 && TN == 128) ? 1 : 2) gemm_f6
     }
     cp_async_commit();
   }
+
+  double acc[MI][NI][2];
+#pragma unroll
+  for (int i = 0; i < MI; ++i)
+#pragma unroll
+    for (int j = 0; j < NI; ++j) {
+      if (SUBC) {
+        const double2 old = *reinterpret_cast<const double2*>(C + (m0 + wm * WM + i * 8 + g) * p.ldc + n0 + wn * WN + j * 8 + 2 * t);
+        acc[i][j][0] = old.x;
+        acc[i][j][1] = old.y;
+      } else {
+        acc[i][j][0] = acc[i][j][1] = 0.0;
+      }
+    }
+
   for (int kt = 0; kt < KT; ++kt) {
     cp_async_wait<G_STAGES - 2>();
     __syncthreads();
@@ -146,7 +165,10 @@ __global__ void __launch_bounds__(256, (TM == 128 && TN == 128) ? 1 : 2) gemm_f6
 #pragma unroll
       for (int i = 0; i < MI; ++i) af[i] = g_frag<ALAY, TM>(sa, wm * WM + i * 8 + g, ks * 4 + t);
 #pragma unroll
-      for (int j = 0; j < NI; ++j) bf[j] = g_frag<BLAY, TN>(sb, wn * WN + j * 8 + g, ks * 4 + t);
+      for (int j = 0; j < NI; ++j) {
+        const double b = g_frag<BLAY, TN>(sb, wn * WN + j * 8 + g, ks * 4 + t);
+        bf[j] = SUBC ? -b : b;
+      }
 #pragma unroll
       for (int i = 0; i < MI; ++i)
 #pragma unroll
@@ -164,8 +186,9 @@ __global__ void __launch_bounds__(256, (TM == 128 && TN == 128) ? 1 : 2) gemm_f6
 #pragma unroll
     for (int j = 0; j < NI; ++j) {
       const int64_t c = n0 + wn * WN + j * 8 + 2 * t;
-      double v0 = p.alpha * acc[i][j][0], v1 = p.alpha * acc[i][j][1];
-      if (p.beta != 0.0) {
+      double v0 = acc[i][j][0], v1 = acc[i][j][1];
+      if (!SUBC) { v0 *= p.alpha; v1 *= p.alpha; }
+      if (!SUBC && p.beta != 0.0) {
         double2 old = *reinterpret_cast<const double2*>(C + r * p.ldc + c);
         v0 += p.beta * old.x;
         v1 += p.beta * old.y;

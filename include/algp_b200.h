@@ -71,9 +71,22 @@ int algp_logdet_sumsq(const double* L, int64_t n, int64_t ld, const double* v, d
  * NULL, receives the row sums of V^2 per column tile: var = k** - sum_t rn_partial. */
 int algp_trmm_rt(const double* Ks, int64_t mpad, int64_t ldk, const double* Linv, int64_t npad, int64_t ldi,
                  double* V, int64_t ldv, double* rn_partial, void* stream);
-/* C = beta C + alpha A B^T (A [mpad x kpad], B [npad x kpad]); lower_only: only tiles on/below the diagonal */
+/* C = beta C + alpha A B^T (A [mpad x kpad], B [npad x kpad]).  lower_only: the lower triangle
+ * (diagonal included) is updated, strictly-upper 128-blocks are untouched, elements above the
+ * diagonal inside diagonal blocks are unspecified. */
 int algp_gemm_nt(const double* A, int64_t lda, const double* B, int64_t ldb, double* C, int64_t ldc,
                  int64_t mpad, int64_t npad, int64_t kpad, double alpha, double beta, int lower_only, void* stream);
+
+/* ---- K4: marginal-likelihood gradient (GPR.fit, models.py:145-158) ---------- */
+/* Ainv (lower triangle) = Linv^T Linv = A^-1 */
+int algp_potri_lower(const double* Linv, int64_t npad, int64_t ldi, double* Ainv, int64_t lda, void* stream);
+/* grad_out[d+2] = 0.5 tr((alpha alpha^T - A^-1) dA/dtheta), theta = (log lengthscale[d], log outputscale,
+ * log noise); K and dK/dtheta are rebuilt on the fly.  The gradient of the reference's loss -mll/N is
+ * -grad_out/N.  work: algp_mll_grad_work_doubles(n) doubles. */
+int algp_mll_grad(const double* x, int64_t n, int d, const double* log_ls_host, double log_os, int kind,
+                  double noise, const double* alpha, const double* Ainv, int64_t lda, double* work,
+                  double* grad_out, void* stream);
+int64_t algp_mll_grad_work_doubles(int64_t n);
 
 /* ---- K3 / K5: information-gain scoring ------------------------------------ */
 /* Entropy H(S1) of `B` candidate sets of `k` slots (k <= 128; idx -1 = empty

@@ -209,3 +209,40 @@ def test_fit_predict_n4096_properties():
     # linearity of the mean in y (same factor, cached): mean(2y) - ybar-shift == 2*mean(y) - shift
     mu2 = algp_b200.predictive_distribution(gp, x, 2 * y, grid, var)
     np.testing.assert_allclose(mu2, 2 * mu, rtol=1e-9, atol=1e-9)
+
+
+# ------------------------------------------------------------------ hyper-parameter learning
+@pytest.mark.parametrize("kind", ["rbf", "matern"])
+@pytest.mark.parametrize("n,d", [(40, 3), (300, 2), (200, 6)])
+def test_mll_loss_and_grad_match_oracle(kind, n, d):
+    from algp_b200.mll import mll_loss_and_grad
+    rng = np.random.default_rng(n + d)
+    x = rng.uniform(0, 10, size=(n, d))
+    y = np.sin(x[:, 0]) + 0.1 * rng.normal(size=n)
+    var = rng.uniform(0.005, 0.02, n)
+    th, hy = hyper_pair(np.linspace(1.5, 3.0, d), 0.8, 0.05, kind)
+    loss, g = mll_loss_and_grad(hy, x, y - y.mean(), var)
+    assert loss == pytest.approx(O.mll_loss(th, x, y, var), rel=1e-10)
+    g_o = O.mll_loss_grad(th, x, y, var)
+    np.testing.assert_allclose(g, g_o, rtol=1e-8, atol=1e-10)
+
+
+@pytest.mark.parametrize("kind", ["rbf", "matern"])
+def test_fit_follows_reference_adam_trajectory(golden_dir, kind, capsys):
+    """GPR.fit = 25 Adam steps on -mll/N from theta = 0 (models.py:137-159).  The reference ran the
+    same loop in float32 through the stand-in's autograd; float64 + analytic gradients stay close."""
+    g = load(golden_dir, "ref_gp_%s.npz" % kind)
+    gp = algp_b200.GPR(lr=0.1, max_iterations=25, kernel_params={'type': kind})
+    gp.fit(g["train_x"], g["train_y"], g["train_var"])
+    out = capsys.readouterr().out
+    assert "Initial LogLikelihood" in out and "Final LogLikelihood" in out
+    hy = gp.hyper()
+    np.testing.assert_allclose(hy.log_ls, g["fit_log_ls"], rtol=0, atol=0.05)
+    assert hy.log_os == pytest.approx(float(g["fit_log_os"]), abs=0.05)
+    assert hy.log_noise == pytest.approx(float(g["fit_log_noise"]), abs=0.05)
+    loss, _ = gp.loss_and_grad()
+    assert loss == pytest.approx(float(g["fit_loss_at_theta"]), abs=0.02)
+    # fit with var=None uses the reference's default 1e-5 (models.py:138-139) and must still factor
+    gp2 = algp_b200.GPR(lr=0.1, max_iterations=3, kernel_params={'type': kind})
+    gp2.fit(g["train_x"], g["train_y"])
+    assert np.allclose(gp2.train_var, 1e-5)

@@ -122,10 +122,20 @@ def test_gemm_nt_matches_numpy():
     engine.gemm_nt(dev(S), dev(S), C2d, 1.0, 1.0, lower_only=True)
     full = C2 + S @ S.T
     got = C2d.cpu().numpy()
+    # contract: the lower triangle (diagonal included) is updated; strictly-upper 128-blocks are
+    # untouched; elements above the diagonal inside diagonal blocks are unspecified
+    np.testing.assert_allclose(np.tril(got), np.tril(full), rtol=1e-12, atol=1e-11)
     for bi in range(3):
-        for bj in range(3):
+        for bj in range(bi + 1, 3):
             blk = (slice(bi * 128, bi * 128 + 128), slice(bj * 128, bj * 128 + 128))
-            np.testing.assert_allclose(got[blk], full[blk] if bj <= bi else C2[blk], rtol=1e-12, atol=1e-11)
+            np.testing.assert_array_equal(got[blk], C2[blk])
+    # a grid large enough for the 128x128 throughput shape (>= 120 tiles)
+    A3 = rng.normal(size=(1536, 256))
+    B3 = rng.normal(size=(1536, 256))
+    C3 = rng.normal(size=(1536, 1536))
+    C3d = dev(C3)
+    engine.gemm_nt(dev(A3), dev(B3), C3d, 0.5, -1.0)
+    np.testing.assert_allclose(C3d.cpu().numpy(), 0.5 * A3 @ B3.T - C3, rtol=1e-12, atol=1e-11)
 
 
 def test_whiten_rownorm_matches_numpy():
