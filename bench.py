@@ -70,29 +70,43 @@ def workload(seed_sets=2, n_cand=N_CAND):
 
 
 class ClockSampler(object):
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
-    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-         "clocks_event_reasons.sw_power_cap")
+    """SM clock and throttle reasons DURING the timed region (B200_PROFILING.md), polled through NVML
+    every few ms (the timed region is tens of ms; spawning nvidia-smi would see one sample)."""
 
     def __init__(self, index=0):
         self.rows = []
         self.stop = False
         self.index = index
+        self.max_mhz = None
         self.t = threading.Thread(target=self.run, daemon=True)
 
     def run(self):
-        while not self.stop:
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            h = nv.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
+            get_reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or \
+                nv.nvmlDeviceGetCurrentClocksThrottleReasons
+            bits = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "sw_thermal_slowdown": 0x20, "hw_thermal_slowdown": 0x40}
+            while not self.stop:
+                mhz = float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
+                r = int(get_reasons(h))
+                self.rows.append((mhz, [k for k, b in bits.items() if r & b]))
+                time.sleep(0.002)
+        except Exception as e:                      # NVML missing: fall back to one nvidia-smi sample
             try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=clocks.sm,clocks.max.sm",
                                       "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
-                self.rows.append([c.strip() for c in out.strip().split(",")])
+                a, b = [float(v) for v in out.strip().split(",")]
+                self.rows.append((a, []))
+                self.max_mhz = b
             except Exception:
-                pass
-            time.sleep(0.1)
+                self.rows.append((float("nan"), ["unavailable: %r" % (e,)]))
 
     def __enter__(self):
         self.t.start()
+        time.sleep(0.02)
         return self
 
     def __exit__(self, *a):
@@ -100,19 +114,10 @@ class ClockSampler(object):
         self.t.join(timeout=6)
 
     def summary(self):
-        sm, mx, reasons = [], 0.0, set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
-            try:
-                sm.append(float(r[0]))
-                mx = max(mx, float(r[1]))
-                for nme, v in zip(names, r[3:7]):
-                    if v.lower().startswith("active"):
-                        reasons.add(nme)
-            except Exception:
-                continue
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx or None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+        sm = [r[0] for r in self.rows if r[0] == r[0]]
+        reasons = sorted({x for r in self.rows for x in r[1]})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_min_mhz": float(min(sm)) if sm else None,
+                "sm_max_mhz": self.max_mhz, "reasons": reasons, "samples": len(sm)}
 
 
 # --------------------------------------------------------------------------------------
