@@ -246,3 +246,45 @@ def test_fit_follows_reference_adam_trajectory(golden_dir, kind, capsys):
     gp2 = algp_b200.GPR(lr=0.1, max_iterations=3, kernel_params={'type': kind})
     gp2.fit(g["train_x"], g["train_y"])
     assert np.allclose(gp2.train_var, 1e-5)
+
+
+# ------------------------------------------------------------------ episode (BASELINE configs[4])
+@pytest.mark.parametrize("kind", ["rbf", "matern"])
+def test_episode_matches_literal_reference_loops(kind):
+    """Greedy picks + best path + commits over several batches, against the oracle's literal
+    agent.py loops run on the same flags (small field so the CPU side takes seconds)."""
+    from algp_b200.episode import run_episode
+    X, y, tr, ytr, rng = field_problem(13, 12, 30, seed=4)
+    n = len(X)
+    th, hy = hyper_pair([2.0, 2.5], 1.0, 0.03, kind)
+    ss, ms = 0.1, 1.0
+    static = np.zeros(n, bool)
+    mobile = np.zeros(n, bool)
+    static[tr[:18]] = True
+    mobile[tr[12:]] = True                      # some locations carry both readings
+    pi0 = O.precisions_from_flags(static, mobile, ss, ms)
+    batches, per_batch = 3, 2
+    prng = np.random.default_rng(9)
+    all_paths = [np.stack([prng.choice(n, 7, replace=False) for _ in range(12)]).astype(np.int32) for _ in range(batches)]
+    for b in range(batches):
+        all_paths[b][0, 5] = all_paths[b][0, 1]          # a repeat inside a path
+        all_paths[b][3, 6] = -1                          # ragged path
+    res = run_episode(hy, dev(X), static, mobile, ss, ms, batches, per_batch,
+                      lambda b, picks: all_paths[b], return_scores=True)
+
+    cov = O.OracleGP(th, "fp64").cov_mat(X, add_likelihood_var=True)
+    st, mo = static.copy(), mobile.copy()
+    for b in range(batches):
+        picks = O.greedy_literal(cov, st, mo, ss, ms, per_batch)
+        assert res["picks"][b] == [int(p) for p in picks]
+        paths = [[int(v) for v in row if v >= 0] for row in all_paths[b]]
+        best, ut = O.best_path_literal(cov, st, mo, ss, ms, paths, picks, return_utilities=True)
+        assert res["best_paths"][b] == best
+        assert res["scores"][b] == pytest.approx(float(ut[best]), rel=1e-8)
+        st[picks] = True
+        mo[paths[best]] = True
+    # the device state now equals a fresh factorisation of the final flags
+    pi_fin = O.precisions_from_flags(st, mo, ss, ms)
+    ost = O.posterior_state(cov, pi_fin)
+    np.testing.assert_allclose(res["state"].diagP.cpu().numpy(), np.diag(ost["P"]), rtol=0, atol=1e-9)
+    np.testing.assert_allclose(res["state"].pi.cpu().numpy(), pi_fin, rtol=1e-12)
