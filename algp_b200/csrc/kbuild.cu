@@ -174,6 +174,105 @@ __global__ void __launch_bounds__(256) kbuild_kernel(const KbuildArgs a) {
   }
 }
 
+// ---------------------------------------------------------------------------
+// Symmetric build K(X,X): one CTA per lower 64x64 tile (I >= J) evaluates the tile once and
+// stores it twice -- directly at (I,J) and, through a shared-memory transpose, at (J,I) -- so
+// the fp64 work is halved while every global store stays a 256-byte row segment.  Thread
+// (ty,tx) of a 16x16 grid owns rows ty+16a, columns {2tx,2tx+1}+32b; all coordinates live in
+// registers.
+// ---------------------------------------------------------------------------
+#define KS_T 64
+template <int D, int KIND>
+__global__ void __launch_bounds__(256) kbuild_sym_kernel(const KbuildArgs a) {
+  __shared__ double sT[KS_T][KS_T + 1];
+  const int L = blockIdx.x;
+  int ti = (int)((sqrt(8.0 * (double)L + 1.0) - 1.0) * 0.5);
+  while ((ti + 1) * (ti + 2) / 2 <= L) ++ti;
+  while (ti * (ti + 1) / 2 > L) --ti;
+  const int tj = L - ti * (ti + 1) / 2;
+  const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
+  const int64_t r0 = (int64_t)ti * KS_T, c0 = (int64_t)tj * KS_T;
+  const int d = (D == 0) ? a.kp.d : D;
+  constexpr int DD = (D == 0) ? ALGP_MAX_D : D;
+
+  double xr[4][DD], xc[4][DD];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const int64_t gr = r0 + ty + 16 * q;
+    const int64_t gc = c0 + 2 * tx + (q & 1) + 32 * (q >> 1);
+#pragma unroll
+    for (int j = 0; j < DD; ++j) {
+      xr[q][j] = (j < d && gr < a.n1) ? a.x1[gr * d + j] * a.kp.inv_ls[j] : 0.0;
+      xc[q][j] = (j < d && gc < a.n1) ? a.x1[gc * d + j] * a.kp.inv_ls[j] : 0.0;
+    }
+  }
+  const double os = a.kp.outputscale;
+  const bool fast = (ti != tj) && (r0 + KS_T <= a.n1);      // off-diagonal and fully inside: no masks, no diagonal work
+  double* outp = (double*)a.out;
+#pragma unroll
+  for (int qa = 0; qa < 4; ++qa) {
+    const int r = ty + 16 * qa;
+    const int64_t gr = r0 + r;
+#pragma unroll
+    for (int b = 0; b < 2; ++b) {
+      double val[2];
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int qc = e + 2 * b;
+        double r2 = 0.0;
+#pragma unroll
+        for (int j = 0; j < DD; ++j) {
+          const double df = xr[qa][j] - xc[qc][j];
+          r2 = fma(df, df, r2);
+        }
+        double k = kern_eval<double, KIND>(r2, os);
+        if (!fast) {
+          const int64_t gc = c0 + 2 * tx + e + 32 * b;
+          if (!((gr < a.n1) && (gc < a.n1))) k = 0.0;
+          if (gr == gc) {
+            if (gr < a.n1) k += a.diag_scalar + (a.diag_add ? a.diag_add[gr] : 0.0);
+            else if (a.pad_identity) k = 1.0;
+          }
+        }
+        val[e] = k;
+      }
+      const int c = 2 * tx + 32 * b;
+      *reinterpret_cast<double2*>(outp + gr * a.ld + c0 + c) = make_double2(val[0], val[1]);
+      if (ti != tj) {
+        sT[c][r] = val[0];
+        sT[c + 1][r] = val[1];
+      }
+    }
+  }
+  if (ti == tj) return;                           // block-uniform
+  __syncthreads();
+#pragma unroll
+  for (int qa = 0; qa < 4; ++qa) {
+    const int r = ty + 16 * qa;                  // row of the mirrored tile = column of the original
+#pragma unroll
+    for (int b = 0; b < 2; ++b) {
+      const int c = 2 * tx + 32 * b;
+      *reinterpret_cast<double2*>(outp + (c0 + r) * a.ld + r0 + c) = make_double2(sT[r][c], sT[r][c + 1]);
+    }
+  }
+}
+
+template <int KIND>
+static int launch_kbuild_sym(const KbuildArgs& a, cudaStream_t st) {
+  const int64_t nt = a.n1_pad / KS_T;
+  const int64_t tiles = nt * (nt + 1) / 2;
+  if (tiles > 0x7fffffffLL) return ALGP_ERR_INVALID;
+  switch (a.kp.d) {
+    case 2: kbuild_sym_kernel<2, KIND><<<(unsigned)tiles, 256, 0, st>>>(a); break;
+    case 3: kbuild_sym_kernel<3, KIND><<<(unsigned)tiles, 256, 0, st>>>(a); break;
+    case 4: kbuild_sym_kernel<4, KIND><<<(unsigned)tiles, 256, 0, st>>>(a); break;
+    case 6: kbuild_sym_kernel<6, KIND><<<(unsigned)tiles, 256, 0, st>>>(a); break;
+    default: return ALGP_ERR_UNSUPPORTED;       // register-resident coordinates: small d only (caller falls back)
+  }
+  ALGP_LAUNCH_CHECK();
+  return ALGP_OK;
+}
+
 // out[r] = bias + scale * sum_t partial[r][t]   (fixed order: deterministic)
 __global__ void rowsum_kernel(const double* __restrict__ partial, int64_t rows, int nt, double scale, double bias,
                               const double* __restrict__ addvec, double* __restrict__ out) {
@@ -241,6 +340,10 @@ extern "C" int algp_kbuild(const double* x1, int64_t n1, const double* x2, int64
   a.n_col_tiles = algp_kbuild_col_tiles(n2_pad, out_dtype);
   if (n1_pad == 0 || n2_pad == 0) return ALGP_OK;
   cudaStream_t st = (cudaStream_t)stream;
+  // K(X,X) in fp64 on a square padded extent: lower tiles only, mirrored on the way out
+  if (!x2 && out_dtype == 0 && !dot_vec && n1_pad == n2_pad && n1_pad % KS_T == 0 && n1 == n2 &&
+      (d == 2 || d == 3 || d == 4 || d == 6))
+    return a.kp.kind == 0 ? launch_kbuild_sym<0>(a, st) : launch_kbuild_sym<1>(a, st);
   if (out_dtype == 0) return dot_vec ? launch_kbuild<double, true>(a, st) : launch_kbuild<double, false>(a, st);
   return dot_vec ? launch_kbuild<float, true>(a, st) : launch_kbuild<float, false>(a, st);
 }

@@ -48,12 +48,39 @@ __device__ __forceinline__ void ld256_l1(const double* p, double& a, double& b, 
 
 // ---------------------------------------------------------------------------
 // k <= 8: one warp per candidate
+//
+// The 8 rows of Wt a candidate needs are streamed through a per-warp cp.async ring in shared
+// memory: SC_STAGES stages of 32 doubles per row.  Lane (g,t) copies the 16-byte granules
+// {t, t+4, t+8, t+12} of row g's chunk and later reads back exactly those bytes, so the ring
+// needs no warp synchronisation at all -- cp.async.wait_group orders a lane's own copies.
+// The k-order inside a chunk is permuted by this assignment, which is harmless: A and B
+// operand of the DMMA are the same register, and the permutation depends on t only.
+// Row pitch 320 B makes the 16-byte reads of a quarter-warp hit 32 distinct banks.
 // ---------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) score_sets_k8_kernel(const ScoreArgs a) {
+#define SC_STAGES 4
+#define SC_CHUNK 32
+#define SC_PITCH 320
+#define SC_STAGE_BYTES (8 * SC_PITCH)
+#define SC_WARP_BYTES (SC_STAGES * SC_STAGE_BYTES)
+#define SC_THREADS 128
+
+// granule i of chunk c: doubles [c*32 + 8i + 2t, +2) of the row (row already points at 2t)
+__device__ __forceinline__ void sc_issue(unsigned char* my, const double* row, int c, bool active, int ncols16) {
+  unsigned char* dst = my + (c & (SC_STAGES - 1)) * SC_STAGE_BYTES;
+  const double* src = row + c * SC_CHUNK;
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+    if (active && c * SC_CHUNK + 8 * i < ncols16) cp_async16(dst + i * 64, src + 8 * i);
+}
+
+__global__ void __launch_bounds__(SC_THREADS) score_sets_k8_kernel(const ScoreArgs a) {
+  extern __shared__ __align__(16) unsigned char sc_smem[];
   const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  unsigned char* my = sc_smem + (threadIdx.x >> 5) * SC_WARP_BYTES + g * SC_PITCH + t * 16;
   const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
   const int d = a.kp.d;
+  const int nch = (a.ncols16 + SC_CHUNK - 1) / SC_CHUNK;
 
   for (int64_t cand = warp0; cand < a.B; cand += nwarps) {
     // slot g of this candidate (4 lanes per slot)
@@ -68,32 +95,37 @@ __global__ void __launch_bounds__(256) score_sets_k8_kernel(const ScoreArgs a) {
       int o_act = __shfl_sync(0xffffffffu, (int)active, 4 * s);
       if (s < g && o_act && o_idx == my_idx) active = false;
     }
-    const double* row = a.Wt + (int64_t)(active ? my_idx : 0) * a.ldw + 4 * t;
+    const double* row = a.Wt + (int64_t)(active ? my_idx : 0) * a.ldw + 2 * t;
 
+#pragma unroll
+    for (int s = 0; s < SC_STAGES - 1; ++s) {
+      if (s < nch) sc_issue(my, row, s, active, a.ncols16);
+      cp_async_commit();
+    }
     double c0[4], c1[4];
 #pragma unroll
     for (int q = 0; q < 4; ++q) c0[q] = c1[q] = 0.0;
-    int k0 = 0;
-    // empty / duplicate slots issue no loads; the MMA itself is warp-wide
-    for (; k0 + 32 <= a.ncols16; k0 += 32) {
-      double v[8];
+    for (int c = 0; c < nch; ++c) {
+      cp_async_wait<SC_STAGES - 2>();
+      const unsigned char* src = my + (c & (SC_STAGES - 1)) * SC_STAGE_BYTES;
+      double2 v[4];
 #pragma unroll
-      for (int q = 0; q < 8; ++q) v[q] = 0.0;
-      if (active) {
-        ld256(row + k0, v[0], v[1], v[2], v[3]);
-        ld256(row + k0 + 16, v[4], v[5], v[6], v[7]);
+      for (int i = 0; i < 4; ++i) {
+        v[i] = make_double2(0.0, 0.0);
+        if (active && c * SC_CHUNK + 8 * i < a.ncols16) v[i] = *reinterpret_cast<const double2*>(src + i * 64);
+      }
+      {
+        const int nx = c + SC_STAGES - 1;
+        if (nx < nch) sc_issue(my, row, nx, active, a.ncols16);
+        cp_async_commit();
       }
 #pragma unroll
-      for (int q = 0; q < 8; ++q) dmma884(c0[q & 3], c1[q & 3], v[q], v[q]);
+      for (int i = 0; i < 4; ++i) {
+        dmma884(c0[i], c1[i], v[i].x, v[i].x);
+        dmma884(c0[i], c1[i], v[i].y, v[i].y);
+      }
     }
-    for (; k0 < a.ncols16; k0 += 16) {
-      double v[4];
-#pragma unroll
-      for (int q = 0; q < 4; ++q) v[q] = 0.0;
-      if (active) ld256(row + k0, v[0], v[1], v[2], v[3]);
-#pragma unroll
-      for (int q = 0; q < 4; ++q) dmma884(c0[q], c1[q], v[q], v[q]);
-    }
+    cp_async_wait<0>();
     const double G0 = (c0[0] + c0[1]) + (c0[2] + c0[3]);   // G[g][2t]
     const double G1 = (c1[0] + c1[1]) + (c1[2] + c1[3]);   // G[g][2t+1]
 
@@ -276,10 +308,11 @@ extern "C" int algp_score_sets(const double* Wt, int64_t ldw, int64_t ncols, con
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   if (k <= 8) {
-    // persistent: 8 CTAs of 8 warps per SM, warps stride over the candidates
-    int64_t want = (B + 7) / 8;
-    int grid = (int)(want < (int64_t)sms * 8 ? want : (int64_t)sms * 8);
-    score_sets_k8_kernel<<<grid, 256, 0, st>>>(a);
+    // persistent: 5 CTAs of 4 warps per SM (40 KB of ring each), warps stride over the candidates
+    const int wpb = SC_THREADS / 32;
+    int64_t want = (B + wpb - 1) / wpb;
+    int grid = (int)(want < (int64_t)sms * 5 ? want : (int64_t)sms * 5);
+    score_sets_k8_kernel<<<grid, SC_THREADS, wpb * SC_WARP_BYTES, st>>>(a);
   } else {
     const int kp = (k + 7) / 8, kk = kp * 8;
     size_t smem = ((size_t)kk * (kk + 1) + kk + (size_t)kk * d) * 8 + (size_t)kk * 4 + 16;
