@@ -63,30 +63,36 @@ int gemm_f64_launch(const GemmArgs& a, int alay, int blay, int batch, cudaStream
 // ---------------------------------------------------------------------------
 // potf2inv: factor one 128x128 diagonal block and invert the factor, one CTA.
 //
-// 256 threads in a 16x16 grid; thread (ty,tx) owns the cyclic 8x8 patch
-// rows ty+16i, cols tx+16j in registers, so every thread stays busy as the
-// active window shrinks.  Phase 1 is an un-normalised elimination (LDL^T
-// style: no sqrt or divide on the column-to-column critical path, one
-// __syncthreads per column through a double-buffered column broadcast);
-// L = Ltilde D^1/2 is formed at the end.  Phase 2 applies the same
-// elimination to the identity to get Ltilde^-1, hence L^-1 = D^-1/2 Ltilde^-1.
+// 256 threads in a 16x16 grid; thread (ty,tx) owns the cyclic patch rows ty+16i,
+// cols tx+16j in registers, so every thread stays busy as the active window
+// shrinks.  The factorisation is an un-normalised elimination (LDL^T style: no
+// sqrt on the column-to-column critical path, one __syncthreads per column
+// through double-buffered broadcasts); L = Ltilde D^1/2 is formed at the end.
+// The same multipliers are applied, in the same loop, to the identity, which
+// yields Y = Ltilde^-1 and hence L^-1 = D^-1/2 Y.
 // ---------------------------------------------------------------------------
-#define P2_PITCH 129
-#define P2_SMEM_BYTES ((128 * P2_PITCH + 2 * 128 + 2 * 128 + 3 * 128) * 8)
+#define P2_SMEM_BYTES ((2 * 128 + 2 * 128 + 2 * 128) * 8)
 
-// Columns 16*IC .. 16*IC+15 of the elimination.  IC is a template parameter so that the register
-// patch is indexed statically and only the boundary block (i == IC or j == IC) needs a mask:
-// finished blocks (i < IC, j < IC) simply drop out of the unrolled loops.
+// Columns 16*IC .. 16*IC+15.  One barrier per column: before it the owners publish column c of
+// the Schur complement (for the elimination) and row c of Y (for the inverse); after it every
+// thread updates its live patches of both.  Only lower-triangular patches (j <= i) are live, so
+// the two register patches cost 2 x 36 doubles.  IC is a template parameter: patch indices are
+// static and only the boundary block needs a mask.
 template <int IC>
-__device__ __forceinline__ void p2_eliminate_block(double (&acc)[8][8], double* colbuf, double* pivbuf, int ty, int tx,
-                                                   int tid, int j0, int* info) {
+__device__ __forceinline__ void p2_block(double (&acc)[8][8], double (&yac)[8][8], double* colbuf, double* rowbuf,
+                                         double* pivbuf, int ty, int tx, int tid, int j0, int* info) {
 #pragma unroll 1
   for (int cc = 0; cc < 16; ++cc) {
     const int c = IC * 16 + cc;
     double* cb = colbuf + (c & 1) * 128;
+    double* rb = rowbuf + (c & 1) * 128;
     if (tx == cc) {
 #pragma unroll
       for (int i = IC; i < 8; ++i) cb[ty + 16 * i] = acc[i][IC];
+    }
+    if (ty == cc) {
+#pragma unroll
+      for (int j = 0; j <= IC; ++j) rb[tx + 16 * j] = yac[IC][j];
     }
     __syncthreads();
     const double piv = cb[c];
@@ -96,116 +102,76 @@ __device__ __forceinline__ void p2_eliminate_block(double (&acc)[8][8], double* 
       pivbuf[c] = piv;
       if (!ok) atomicCAS(info, 0, j0 + c + 1);
     }
-    double ri[8], cj[8];
+    double ri[8], cj[8], yj[8];
 #pragma unroll
-    for (int i = IC; i < 8; ++i) ri[i] = cb[ty + 16 * i] * rcp;
-    if (ty <= cc) ri[IC] = 0.0;                 // rows at or above the pivot
+    for (int i = IC; i < 8; ++i) ri[i] = cb[ty + 16 * i] * rcp;      // multipliers l~_{r,c}
+    if (ty <= cc) ri[IC] = 0.0;                                      // rows at or above the pivot
 #pragma unroll
     for (int j = IC; j < 8; ++j) cj[j] = cb[tx + 16 * j];
-    if (tx <= cc) cj[IC] = 0.0;                 // columns at or left of the pivot
+    if (tx <= cc) cj[IC] = 0.0;                                      // columns at or left of the pivot
 #pragma unroll
-    for (int i = IC; i < 8; ++i)
+    for (int j = 0; j <= IC; ++j) yj[j] = rb[tx + 16 * j];           // Y[c][.] (zero right of c by construction)
 #pragma unroll
-      for (int j = IC; j < 8; ++j) acc[i][j] = fma(-ri[i], cj[j], acc[i][j]);
-  }
-}
-
-// Same elimination applied to the identity: Y <- Ltilde^-1 (rows i >= IC, columns j <= IC are live).
-template <int IC>
-__device__ __forceinline__ void p2_invert_block(double (&acc)[8][8], const double* sL, double* rowbuf, int ty, int tx) {
-#pragma unroll 1
-  for (int cc = 0; cc < 16; ++cc) {
-    const int c = IC * 16 + cc;
-    if (c == 127) break;
-    double* rb = rowbuf + (c & 1) * 128;
-    if (ty == cc) {
+    for (int i = IC; i < 8; ++i) {
 #pragma unroll
-      for (int j = 0; j <= IC; ++j) rb[tx + 16 * j] = acc[IC][j];
+      for (int j = IC; j <= i; ++j) acc[i][j] = fma(-ri[i], cj[j], acc[i][j]);
+#pragma unroll
+      for (int j = 0; j <= IC; ++j) yac[i][j] = fma(-ri[i], yj[j], yac[i][j]);
     }
-    __syncthreads();
-    double ri[8], yj[8];
-#pragma unroll
-    for (int i = IC; i < 8; ++i) ri[i] = sL[(ty + 16 * i) * P2_PITCH + c];
-    if (ty <= cc) ri[IC] = 0.0;
-#pragma unroll
-    for (int j = 0; j <= IC; ++j) yj[j] = rb[tx + 16 * j];
-#pragma unroll
-    for (int i = IC; i < 8; ++i)
-#pragma unroll
-      for (int j = 0; j <= IC; ++j) acc[i][j] = fma(-ri[i], yj[j], acc[i][j]);
   }
 }
 
 __global__ void __launch_bounds__(256, 1) potf2inv_kernel(double* __restrict__ A, int64_t ld, double* __restrict__ Linv,
                                                           int64_t ldi, int j0, int* __restrict__ info) {
   extern __shared__ __align__(16) double p2_smem[];
-  double* sL = p2_smem;                       // [128][129] unit-lower multipliers
-  double* colbuf = sL + 128 * P2_PITCH;       // [2][128]
+  double* colbuf = p2_smem;                   // [2][128]
   double* rowbuf = colbuf + 256;              // [2][128]
   double* pivbuf = rowbuf + 256;              // [128]
-  double* rcpbuf = pivbuf + 128;              // [128] 1/piv
-  double* rsbuf = rcpbuf + 128;               // [128] 1/sqrt(piv)
+  double* rsbuf = pivbuf + 128;               // [128] 1/sqrt(piv)
 
   const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
-  double acc[8][8];
+  double acc[8][8], yac[8][8];
 #pragma unroll
   for (int i = 0; i < 8; ++i)
 #pragma unroll
-    for (int j = 0; j < 8; ++j) acc[i][j] = A[(int64_t)(ty + 16 * i) * ld + tx + 16 * j];
+    for (int j = 0; j <= i; ++j) {
+      acc[i][j] = A[(int64_t)(ty + 16 * i) * ld + tx + 16 * j];
+      yac[i][j] = (i == j && ty == tx) ? 1.0 : 0.0;
+    }
 
-  // ---- phase 1: elimination ------------------------------------------------
-  p2_eliminate_block<0>(acc, colbuf, pivbuf, ty, tx, tid, j0, info);
-  p2_eliminate_block<1>(acc, colbuf, pivbuf, ty, tx, tid, j0, info);
-  p2_eliminate_block<2>(acc, colbuf, pivbuf, ty, tx, tid, j0, info);
-  p2_eliminate_block<3>(acc, colbuf, pivbuf, ty, tx, tid, j0, info);
-  p2_eliminate_block<4>(acc, colbuf, pivbuf, ty, tx, tid, j0, info);
-  p2_eliminate_block<5>(acc, colbuf, pivbuf, ty, tx, tid, j0, info);
-  p2_eliminate_block<6>(acc, colbuf, pivbuf, ty, tx, tid, j0, info);
-  p2_eliminate_block<7>(acc, colbuf, pivbuf, ty, tx, tid, j0, info);
+  p2_block<0>(acc, yac, colbuf, rowbuf, pivbuf, ty, tx, tid, j0, info);
+  p2_block<1>(acc, yac, colbuf, rowbuf, pivbuf, ty, tx, tid, j0, info);
+  p2_block<2>(acc, yac, colbuf, rowbuf, pivbuf, ty, tx, tid, j0, info);
+  p2_block<3>(acc, yac, colbuf, rowbuf, pivbuf, ty, tx, tid, j0, info);
+  p2_block<4>(acc, yac, colbuf, rowbuf, pivbuf, ty, tx, tid, j0, info);
+  p2_block<5>(acc, yac, colbuf, rowbuf, pivbuf, ty, tx, tid, j0, info);
+  p2_block<6>(acc, yac, colbuf, rowbuf, pivbuf, ty, tx, tid, j0, info);
+  p2_block<7>(acc, yac, colbuf, rowbuf, pivbuf, ty, tx, tid, j0, info);
   __syncthreads();
   if (tid < 128) {
     const double piv = pivbuf[tid];
-    const bool ok = piv > 0.0;
-    rcpbuf[tid] = ok ? 1.0 / piv : 0.0;
-    rsbuf[tid] = ok ? 1.0 / sqrt(piv) : 0.0;
+    rsbuf[tid] = piv > 0.0 ? 1.0 / sqrt(piv) : 0.0;
   }
   __syncthreads();
 
-  // ---- write L, stash multipliers -------------------------------------------
+  // L = Ltilde D^1/2 (acc holds the un-normalised columns), Linv = D^-1/2 Y; zeros above the diagonal
 #pragma unroll
   for (int i = 0; i < 8; ++i)
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const int r = ty + 16 * i, c = tx + 16 * j;
-      double l;
-      if (r > c) {
-        l = acc[i][j] * rsbuf[c];
-        sL[r * P2_PITCH + c] = acc[i][j] * rcpbuf[c];
-      } else if (r == c) {
-        l = pivbuf[c] * rsbuf[c];
-      } else {
-        l = 0.0;
+      double l = 0.0, li = 0.0;
+      if (j <= i) {
+        if (r > c) {
+          l = acc[i][j] * rsbuf[c];
+          li = yac[i][j] * rsbuf[r];
+        } else if (r == c) {
+          l = pivbuf[c] * rsbuf[c];
+          li = rsbuf[r];
+        }
       }
       A[(int64_t)r * ld + c] = l;
-      acc[i][j] = (r == c) ? 1.0 : 0.0;       // becomes Y = Ltilde^-1
-    }
-  __syncthreads();
-
-  // ---- phase 2: Y <- Ltilde^-1 ----------------------------------------------
-  p2_invert_block<0>(acc, sL, rowbuf, ty, tx);
-  p2_invert_block<1>(acc, sL, rowbuf, ty, tx);
-  p2_invert_block<2>(acc, sL, rowbuf, ty, tx);
-  p2_invert_block<3>(acc, sL, rowbuf, ty, tx);
-  p2_invert_block<4>(acc, sL, rowbuf, ty, tx);
-  p2_invert_block<5>(acc, sL, rowbuf, ty, tx);
-  p2_invert_block<6>(acc, sL, rowbuf, ty, tx);
-  p2_invert_block<7>(acc, sL, rowbuf, ty, tx);
-#pragma unroll
-  for (int i = 0; i < 8; ++i)
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const int r = ty + 16 * i, c = tx + 16 * j;
-      Linv[(int64_t)r * ldi + c] = (r >= c) ? acc[i][j] * rsbuf[r] : 0.0;
+      Linv[(int64_t)r * ldi + c] = li;
     }
 }
 

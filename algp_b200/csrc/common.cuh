@@ -87,6 +87,37 @@ __device__ __forceinline__ double exp_nonpos(double x) {
   return __hiloint2double(__double2hiint(p) + (k << 20), __double2loint(p));
 }
 
+// exp(x) * tab-scale for x <= 0 with a 16-entry table tab[j] = scale * 2^(j/16) (shared memory):
+// n = rint(16 x / ln2), r = x - n ln2/16 (|r| <= 0.0217, two-part Cody-Waite), degree-7 Taylor
+// polynomial (truncation 1.2e-18), result = tab[n & 15] * p(r) * 2^(n >> 4).  11 fp64 ops; 1.5 ulp.
+// x is clamped at -650 through its high word (x <= 0: more negative = larger unsigned high word) so
+// the exponent-field add never leaves the normal range for any sane scale.
+__device__ __forceinline__ double exp_nonpos_tab(double x, const double* __restrict__ tab) {
+  if ((unsigned)__double2hiint(x) > 0xC0845000u) x = -650.0;
+  const double magic = 6755399441055744.0;   // 1.5 * 2^52
+  double nf = fma(x, 23.083120654223414, magic);
+  const int n = __double2loint(nf);
+  nf -= magic;
+  double r = fma(nf, -0.04332169877307024, x);
+  r = fma(nf, -1.1926343307941173e-11, r);
+  double p = 1.984126984126984e-04;           // 1/7!
+  p = fma(p, r, 1.388888888888889e-03);
+  p = fma(p, r, 8.333333333333333e-03);
+  p = fma(p, r, 4.1666666666666664e-02);
+  p = fma(p, r, 1.6666666666666666e-01);
+  p = fma(p, r, 0.5);
+  p = fma(p, r, 1.0);
+  p = fma(p, r, 1.0);
+  p *= tab[n & 15];
+  return __hiloint2double(__double2hiint(p) + ((n >> 4) << 20), __double2loint(p));
+}
+
+// 2^(j/16), j = 0..15 (correctly rounded)
+static __device__ __constant__ double c_exp2_16th[16] = {
+    1.0, 1.0442737824274138, 1.0905077326652577, 1.1387886347566916, 1.189207115002721, 1.241857812073484,
+    1.2968395546510096, 1.3542555469368927, 1.4142135623730951, 1.4768261459394993, 1.5422108254079407,
+    1.6104903319492543, 1.681792830507429, 1.7562521603732995, 1.8340080864093424, 1.9152065613971474};
+
 // k(x,x') for already length-scaled squared distance r2
 __device__ __forceinline__ double kern_from_r2(double r2, int kind, double os) {
   if (kind == 0) return os * exp_nonpos(-0.5 * r2);

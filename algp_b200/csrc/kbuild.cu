@@ -36,15 +36,22 @@ template <typename T> struct Vec;
 template <> struct Vec<double> { static constexpr int N = 2; typedef double2 type; };
 template <> struct Vec<float> { static constexpr int N = 4; typedef float4 type; };
 
-template <typename T, int KIND> __device__ __forceinline__ T kern_eval(T r2, T os);
-template <> __device__ __forceinline__ double kern_eval<double, 0>(double r2, double os) { return os * exp_nonpos(-0.5 * r2); }
-template <> __device__ __forceinline__ double kern_eval<double, 1>(double r2, double os) {
-  const double s3 = 1.7320508075688772;
-  const double r = sqrt(r2);
-  return os * fma(s3, r, 1.0) * exp_nonpos(-s3 * r);
+// Coordinates are pre-scaled by inv_ls * KSCALE so that q = -sum df^2 is directly the exponent:
+//   RBF     KSCALE = sqrt(1/2):  k = s^2 exp(q)
+//   Matern  KSCALE = sqrt(3):    k = s^2 (1 + r') exp(-r'),  r' = sqrt(-q)
+// and s^2 is folded into the exp table, so an RBF element costs 11 fp64 ops after the distance.
+template <int KIND> __host__ __device__ constexpr double kscale() { return KIND == 0 ? 0.70710678118654752 : 1.7320508075688772; }
+template <typename T, int KIND> __device__ __forceinline__ T kern_eval(T q, const double* tab, T os);
+template <> __device__ __forceinline__ double kern_eval<double, 0>(double q, const double* tab, double) { return exp_nonpos_tab(q, tab); }
+template <> __device__ __forceinline__ double kern_eval<double, 1>(double q, const double* tab, double) {
+  const double r = sqrt(-q);
+  return (1.0 + r) * exp_nonpos_tab(-r, tab);
 }
-template <> __device__ __forceinline__ float kern_eval<float, 0>(float r2, float os) { return kern_from_r2f(r2, 0, os); }
-template <> __device__ __forceinline__ float kern_eval<float, 1>(float r2, float os) { return kern_from_r2f(r2, 1, os); }
+template <> __device__ __forceinline__ float kern_eval<float, 0>(float q, const double*, float os) { return os * expf(q); }
+template <> __device__ __forceinline__ float kern_eval<float, 1>(float q, const double*, float os) {
+  const float r = sqrtf(-q);
+  return os * (1.0f + r) * expf(-r);
+}
 
 #define KB_ROWS 64
 
@@ -52,8 +59,8 @@ template <> __device__ __forceinline__ float kern_eval<float, 1>(float r2, float
 // row loop is distance -> kernel -> 16-byte store with no masking.
 template <typename T, int D, int KIND, bool DOT, bool FAST>
 __device__ __forceinline__ void kbuild_rows(const KbuildArgs& a, const T (*sx1)[ALGP_MAX_D], const T (*sx2)[128 * Vec<T>::N],
-                                            const T (*x2r)[D == 0 ? 1 : D], const T* dv, double (*sred)[4], int d, int wr,
-                                            int wc, int lane, int64_t row0, int64_t c0, int lc) {
+                                            const T (*x2r)[D == 0 ? 1 : D], const T* dv, double (*sred)[4], const double* tab,
+                                            int d, int wr, int wc, int lane, int64_t row0, int64_t c0, int lc) {
   constexpr int VEC = Vec<T>::N;
   const T os = (T)a.kp.outputscale;
   T* outp = (T*)a.out + (row0 + (int64_t)wr * 32) * a.ld + c0;
@@ -66,20 +73,20 @@ __device__ __forceinline__ void kbuild_rows(const KbuildArgs& a, const T (*sx1)[
     T val[VEC];
 #pragma unroll
     for (int v = 0; v < VEC; ++v) {
-      T r2 = (T)0;
+      T q = (T)0;                                  // -sum df^2 over pre-scaled coordinates
       if (D == 0) {
         for (int j = 0; j < d; ++j) {
           T df = sx1[r][j] - sx2[j][lc + v];
-          r2 = fma(df, df, r2);
+          q = fma(-df, df, q);
         }
       } else {
 #pragma unroll
         for (int j = 0; j < (D == 0 ? 1 : D); ++j) {
           T df = sx1[r][j] - x2r[v][j];
-          r2 = fma(df, df, r2);
+          q = fma(-df, df, q);
         }
       }
-      T k = kern_eval<T, KIND>(r2, os);
+      T k = kern_eval<T, KIND>(q, tab, os);
       if (!FAST) {
         const int64_t gc = c0 + v;
         if (!((gr < a.n1) && (gc < a.n2))) k = (T)0;
@@ -117,10 +124,12 @@ __global__ void __launch_bounds__(256) kbuild_kernel(const KbuildArgs a) {
   __shared__ __align__(16) T sx1[KB_ROWS][ALGP_MAX_D];
   __shared__ T sx2[D == 0 ? ALGP_MAX_D : 1][TILE_C];
   __shared__ double sred[KB_ROWS][4];
+  __shared__ double stab[16];
 
   const int d = (D == 0) ? a.kp.d : D;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int wr = warp >> 2, wc = warp & 3;
+  if (tid < 16) stab[tid] = a.kp.outputscale * c_exp2_16th[tid];
   const int64_t row0 = (int64_t)blockIdx.y * KB_ROWS;
   const int64_t col0 = (int64_t)blockIdx.x * TILE_C;
   const int64_t c0 = col0 + (int64_t)wc * 32 * VEC + lane * VEC;
@@ -130,7 +139,7 @@ __global__ void __launch_bounds__(256) kbuild_kernel(const KbuildArgs a) {
     int r = i / d, j = i - r * d;
     int64_t gr = row0 + r;
     double v = (gr < a.n1) ? a.x1[gr * d + j] : 0.0;
-    sx1[r][j] = (T)((T)v * (T)a.kp.inv_ls[j]);
+    sx1[r][j] = (T)((T)v * (T)(a.kp.inv_ls[j] * kscale<KIND>()));
   }
   T x2r[VEC][D == 0 ? 1 : D];
   if (D == 0) {
@@ -138,7 +147,7 @@ __global__ void __launch_bounds__(256) kbuild_kernel(const KbuildArgs a) {
       int c = i / d, j = i - c * d;
       int64_t gc = col0 + c;
       double v = (gc < a.n2) ? a.x2[gc * d + j] : 0.0;
-      sx2[j][c] = (T)((T)v * (T)a.kp.inv_ls[j]);
+      sx2[j][c] = (T)((T)v * (T)(a.kp.inv_ls[j] * kscale<KIND>()));
     }
   } else {
 #pragma unroll
@@ -147,7 +156,7 @@ __global__ void __launch_bounds__(256) kbuild_kernel(const KbuildArgs a) {
       for (int j = 0; j < (D == 0 ? 1 : D); ++j) {
         int64_t gc = c0 + v;
         double xv = (gc < a.n2) ? a.x2[gc * d + j] : 0.0;
-        x2r[v][j] = (T)((T)xv * (T)a.kp.inv_ls[j]);
+        x2r[v][j] = (T)((T)xv * (T)(a.kp.inv_ls[j] * kscale<KIND>()));
       }
   }
   T dv[VEC];
@@ -160,9 +169,9 @@ __global__ void __launch_bounds__(256) kbuild_kernel(const KbuildArgs a) {
   const bool touches_diag = (row0 < col0 + TILE_C) && (col0 < row0 + KB_ROWS);
   const bool fast = (row0 + KB_ROWS <= a.n1) && (col0 + TILE_C <= a.n2) && !(diag_work && touches_diag);
   if (fast)
-    kbuild_rows<T, D, KIND, DOT, true>(a, sx1, sx2, x2r, dv, sred, d, wr, wc, lane, row0, c0, lc);
+    kbuild_rows<T, D, KIND, DOT, true>(a, sx1, sx2, x2r, dv, sred, stab, d, wr, wc, lane, row0, c0, lc);
   else
-    kbuild_rows<T, D, KIND, DOT, false>(a, sx1, sx2, x2r, dv, sred, d, wr, wc, lane, row0, c0, lc);
+    kbuild_rows<T, D, KIND, DOT, false>(a, sx1, sx2, x2r, dv, sred, stab, d, wr, wc, lane, row0, c0, lc);
 
   if (DOT) {
     __syncthreads();
@@ -185,6 +194,8 @@ __global__ void __launch_bounds__(256) kbuild_kernel(const KbuildArgs a) {
 template <int D, int KIND>
 __global__ void __launch_bounds__(256) kbuild_sym_kernel(const KbuildArgs a) {
   __shared__ double sT[KS_T][KS_T + 1];
+  __shared__ double stab[16];
+  if (threadIdx.x < 16) stab[threadIdx.x] = a.kp.outputscale * c_exp2_16th[threadIdx.x];
   const int L = blockIdx.x;
   int ti = (int)((sqrt(8.0 * (double)L + 1.0) - 1.0) * 0.5);
   while ((ti + 1) * (ti + 2) / 2 <= L) ++ti;
@@ -202,11 +213,12 @@ __global__ void __launch_bounds__(256) kbuild_sym_kernel(const KbuildArgs a) {
     const int64_t gc = c0 + 2 * tx + (q & 1) + 32 * (q >> 1);
 #pragma unroll
     for (int j = 0; j < DD; ++j) {
-      xr[q][j] = (j < d && gr < a.n1) ? a.x1[gr * d + j] * a.kp.inv_ls[j] : 0.0;
-      xc[q][j] = (j < d && gc < a.n1) ? a.x1[gc * d + j] * a.kp.inv_ls[j] : 0.0;
+      xr[q][j] = (j < d && gr < a.n1) ? a.x1[gr * d + j] * (a.kp.inv_ls[j] * kscale<KIND>()) : 0.0;
+      xc[q][j] = (j < d && gc < a.n1) ? a.x1[gc * d + j] * (a.kp.inv_ls[j] * kscale<KIND>()) : 0.0;
     }
   }
   const double os = a.kp.outputscale;
+  __syncthreads();                               // stab
   const bool fast = (ti != tj) && (r0 + KS_T <= a.n1);      // off-diagonal and fully inside: no masks, no diagonal work
   double* outp = (double*)a.out;
 #pragma unroll
@@ -219,13 +231,13 @@ __global__ void __launch_bounds__(256) kbuild_sym_kernel(const KbuildArgs a) {
 #pragma unroll
       for (int e = 0; e < 2; ++e) {
         const int qc = e + 2 * b;
-        double r2 = 0.0;
+        double qq = 0.0;
 #pragma unroll
         for (int j = 0; j < DD; ++j) {
           const double df = xr[qa][j] - xc[qc][j];
-          r2 = fma(df, df, r2);
+          qq = fma(-df, df, qq);
         }
-        double k = kern_eval<double, KIND>(r2, os);
+        double k = kern_eval<double, KIND>(qq, stab, os);
         if (!fast) {
           const int64_t gc = c0 + 2 * tx + e + 32 * b;
           if (!((gr < a.n1) && (gc < a.n1))) k = 0.0;

@@ -18,6 +18,7 @@
 //   append             posterior rank-1 downdate after an acquisition, as one new column of Wt
 #include "common.cuh"
 #include <math.h>
+#include <stdlib.h>
 
 #define ALGP_CONST 1.4189385332046727   // 0.5*log(2*pi*e), utils.py:10
 
@@ -49,38 +50,30 @@ __device__ __forceinline__ void ld256_l1(const double* p, double& a, double& b, 
 // ---------------------------------------------------------------------------
 // k <= 8: one warp per candidate
 //
-// The 8 rows of Wt a candidate needs are streamed through a per-warp cp.async ring in shared
-// memory: SC_STAGES stages of 32 doubles per row.  Lane (g,t) copies the 16-byte granules
-// {t, t+4, t+8, t+12} of row g's chunk and later reads back exactly those bytes, so the ring
-// needs no warp synchronisation at all -- cp.async.wait_group orders a lane's own copies.
-// The k-order inside a chunk is permuted by this assignment, which is harmless: A and B
-// operand of the DMMA are the same register, and the permutation depends on t only.
-// Row pitch 320 B makes the 16-byte reads of a quarter-warp hit 32 distinct banks.
+// Lane (g,t) streams row g of the candidate with 256-bit loads: per 128-byte line the four
+// t-lanes take 32 B each, so every request is a whole line and the 4 doubles a lane holds feed
+// 4 DMMAs as BOTH operands (the k-order inside a line is permuted by t, which a Gram matrix
+// does not care about).  UNROLL lines per row are requested before the first MMA of an
+// iteration; PREFETCH additionally issues the next iteration's loads before this one's MMAs
+// (register double buffering).  A shared-memory cp.async ring was tried and was slower: the
+// data then crosses the LSU twice (LDGSTS + LDS) and the kernel becomes LSU-bound.
 // ---------------------------------------------------------------------------
-#define SC_STAGES 4
-#define SC_CHUNK 32
-#define SC_PITCH 320
-#define SC_STAGE_BYTES (8 * SC_PITCH)
-#define SC_WARP_BYTES (SC_STAGES * SC_STAGE_BYTES)
-#define SC_THREADS 128
-
-// granule i of chunk c: doubles [c*32 + 8i + 2t, +2) of the row (row already points at 2t)
-__device__ __forceinline__ void sc_issue(unsigned char* my, const double* row, int c, bool active, int ncols16) {
-  unsigned char* dst = my + (c & (SC_STAGES - 1)) * SC_STAGE_BYTES;
-  const double* src = row + c * SC_CHUNK;
+template <int UNROLL>
+__device__ __forceinline__ void sc_load(double (&v)[4 * UNROLL], const double* p, bool active, int k0, int ncols16) {
 #pragma unroll
-  for (int i = 0; i < 4; ++i)
-    if (active && c * SC_CHUNK + 8 * i < ncols16) cp_async16(dst + i * 64, src + 8 * i);
+  for (int u = 0; u < UNROLL; ++u) {
+    v[4 * u] = v[4 * u + 1] = v[4 * u + 2] = v[4 * u + 3] = 0.0;
+    if (active && k0 + 16 * u < ncols16) ld256(p + k0 + 16 * u, v[4 * u], v[4 * u + 1], v[4 * u + 2], v[4 * u + 3]);
+  }
 }
 
-__global__ void __launch_bounds__(SC_THREADS) score_sets_k8_kernel(const ScoreArgs a) {
-  extern __shared__ __align__(16) unsigned char sc_smem[];
+template <int UNROLL, bool PREFETCH, int THREADS>
+__global__ void __launch_bounds__(THREADS) score_sets_k8_kernel(const ScoreArgs a) {
   const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
-  unsigned char* my = sc_smem + (threadIdx.x >> 5) * SC_WARP_BYTES + g * SC_PITCH + t * 16;
   const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
   const int d = a.kp.d;
-  const int nch = (a.ncols16 + SC_CHUNK - 1) / SC_CHUNK;
+  constexpr int STEP = 16 * UNROLL;
 
   for (int64_t cand = warp0; cand < a.B; cand += nwarps) {
     // slot g of this candidate (4 lanes per slot)
@@ -95,37 +88,30 @@ __global__ void __launch_bounds__(SC_THREADS) score_sets_k8_kernel(const ScoreAr
       int o_act = __shfl_sync(0xffffffffu, (int)active, 4 * s);
       if (s < g && o_act && o_idx == my_idx) active = false;
     }
-    const double* row = a.Wt + (int64_t)(active ? my_idx : 0) * a.ldw + 2 * t;
+    const double* row = a.Wt + (int64_t)(active ? my_idx : 0) * a.ldw + 4 * t;
 
-#pragma unroll
-    for (int s = 0; s < SC_STAGES - 1; ++s) {
-      if (s < nch) sc_issue(my, row, s, active, a.ncols16);
-      cp_async_commit();
-    }
     double c0[4], c1[4];
 #pragma unroll
     for (int q = 0; q < 4; ++q) c0[q] = c1[q] = 0.0;
-    for (int c = 0; c < nch; ++c) {
-      cp_async_wait<SC_STAGES - 2>();
-      const unsigned char* src = my + (c & (SC_STAGES - 1)) * SC_STAGE_BYTES;
-      double2 v[4];
+    // empty / duplicate slots issue no loads; the MMA itself is warp-wide
+    if (PREFETCH) {
+      double cur[4 * UNROLL], nxt[4 * UNROLL];
+      sc_load<UNROLL>(cur, row, active, 0, a.ncols16);
+      for (int k0 = 0; k0 < a.ncols16; k0 += STEP) {
+        sc_load<UNROLL>(nxt, row, active, k0 + STEP, a.ncols16);
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        v[i] = make_double2(0.0, 0.0);
-        if (active && c * SC_CHUNK + 8 * i < a.ncols16) v[i] = *reinterpret_cast<const double2*>(src + i * 64);
-      }
-      {
-        const int nx = c + SC_STAGES - 1;
-        if (nx < nch) sc_issue(my, row, nx, active, a.ncols16);
-        cp_async_commit();
-      }
+        for (int q = 0; q < 4 * UNROLL; ++q) dmma884(c0[q & 3], c1[q & 3], cur[q], cur[q]);
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        dmma884(c0[i], c1[i], v[i].x, v[i].x);
-        dmma884(c0[i], c1[i], v[i].y, v[i].y);
+        for (int q = 0; q < 4 * UNROLL; ++q) cur[q] = nxt[q];
+      }
+    } else {
+      for (int k0 = 0; k0 < a.ncols16; k0 += STEP) {
+        double v[4 * UNROLL];
+        sc_load<UNROLL>(v, row, active, k0, a.ncols16);
+#pragma unroll
+        for (int q = 0; q < 4 * UNROLL; ++q) dmma884(c0[q & 3], c1[q & 3], v[q], v[q]);
       }
     }
-    cp_async_wait<0>();
     const double G0 = (c0[0] + c0[1]) + (c0[2] + c0[3]);   // G[g][2t]
     const double G1 = (c1[0] + c1[1]) + (c1[2] + c1[3]);   // G[g][2t+1]
 
@@ -177,6 +163,14 @@ __global__ void __launch_bounds__(SC_THREADS) score_sets_k8_kernel(const ScoreAr
     }
     if (lane == 0) a.scores[cand] = a.H_base + nnew * ALGP_CONST + 0.5 * (logdet - term);
   }
+}
+
+template <int UNROLL, bool PREFETCH, int THREADS>
+static void score_k8_launch(const ScoreArgs& a, int sms, int blocks_per_sm, cudaStream_t st) {
+  const int wpb = THREADS / 32;
+  int64_t want = (a.B + wpb - 1) / wpb;
+  int64_t cap = (int64_t)sms * blocks_per_sm;
+  score_sets_k8_kernel<UNROLL, PREFETCH, THREADS><<<(int)(want < cap ? want : cap), THREADS, 0, st>>>(a);
 }
 
 // ---------------------------------------------------------------------------
@@ -308,11 +302,21 @@ extern "C" int algp_score_sets(const double* Wt, int64_t ldw, int64_t ncols, con
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   if (k <= 8) {
-    // persistent: 5 CTAs of 4 warps per SM (40 KB of ring each), warps stride over the candidates
-    const int wpb = SC_THREADS / 32;
-    int64_t want = (B + wpb - 1) / wpb;
-    int grid = (int)(want < (int64_t)sms * 5 ? want : (int64_t)sms * 5);
-    score_sets_k8_kernel<<<grid, SC_THREADS, wpb * SC_WARP_BYTES, st>>>(a);
+    // persistent grid, warps stride over the candidates.  ALGP_SCORE_VARIANT selects a tuning variant
+    // (bench / profiling only); the default is the fastest measured on B200.
+    static int variant = -1;
+    if (variant < 0) {
+      const char* e = getenv("ALGP_SCORE_VARIANT");
+      variant = e ? atoi(e) : 0;
+    }
+    switch (variant) {
+      case 1: score_k8_launch<4, false, 128>(a, sms, 8, st); break;
+      case 2: score_k8_launch<2, true, 128>(a, sms, 8, st); break;
+      case 3: score_k8_launch<4, true, 128>(a, sms, 6, st); break;
+      case 4: score_k8_launch<2, false, 128>(a, sms, 12, st); break;
+      case 5: score_k8_launch<1, true, 256>(a, sms, 8, st); break;
+      default: score_k8_launch<2, false, 256>(a, sms, 8, st); break;
+    }
   } else {
     const int kp = (k + 7) / 8, kk = kp * 8;
     size_t smem = ((size_t)kk * (kk + 1) + kk + (size_t)kk * d) * 8 + (size_t)kk * 4 + 16;
