@@ -63,56 +63,83 @@ __device__ __forceinline__ void kbuild_rows(const KbuildArgs& a, const T (*sx1)[
                                             int d, int wr, int wc, int lane, int64_t row0, int64_t c0, int lc) {
   constexpr int VEC = Vec<T>::N;
   const T os = (T)a.kp.outputscale;
-  T* outp = (T*)a.out + (row0 + (int64_t)wr * 32) * a.ld + c0;
+  T* outp0 = (T*)a.out + (row0 + (int64_t)wr * 32) * a.ld + c0;
   const bool col_ok = FAST || (c0 < a.n2_pad);
-#pragma unroll 2
-  for (int rr = 0; rr < 32; ++rr, outp += a.ld) {
-    const int r = wr * 32 + rr;
-    const int64_t gr = row0 + r;
-    if (!FAST && gr >= a.n1_pad) break;          // warp-uniform
-    T val[VEC];
+  // rows in groups of 8: with the fused row-dot the 8 per-lane partials are reduced together by a
+  // butterfly reduce-scatter (9 double shuffles per 8 rows instead of 40)
+#pragma unroll 1
+  for (int r8 = 0; r8 < 32; r8 += 8) {
+    T* outp = outp0;
+    double part[8];
 #pragma unroll
-    for (int v = 0; v < VEC; ++v) {
-      T q = (T)0;                                  // -sum df^2 over pre-scaled coordinates
-      if (D == 0) {
-        for (int j = 0; j < d; ++j) {
-          T df = sx1[r][j] - sx2[j][lc + v];
-          q = fma(-df, df, q);
-        }
-      } else {
+    for (int u = 0; u < 8; ++u) {
+      const int r = wr * 32 + r8 + u;
+      const int64_t gr = row0 + r;
+      part[u] = 0.0;
+      if (!FAST && gr >= a.n1_pad) continue;       // warp-uniform
+      T val[VEC];
 #pragma unroll
-        for (int j = 0; j < (D == 0 ? 1 : D); ++j) {
-          T df = sx1[r][j] - x2r[v][j];
-          q = fma(-df, df, q);
+      for (int v = 0; v < VEC; ++v) {
+        T q = (T)0;                                  // -sum df^2 over pre-scaled coordinates
+        if (D == 0) {
+          for (int j = 0; j < d; ++j) {
+            T df = sx1[r][j] - sx2[j][lc + v];
+            q = fma(-df, df, q);
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < (D == 0 ? 1 : D); ++j) {
+            T df = sx1[r][j] - x2r[v][j];
+            q = fma(-df, df, q);
+          }
         }
+        T k = kern_eval<T, KIND>(q, tab, os);
+        if (!FAST) {
+          const int64_t gc = c0 + v;
+          if (!((gr < a.n1) && (gc < a.n2))) k = (T)0;
+          if (gr == gc) {
+            if (gr < a.n1) {
+              double add = a.diag_scalar + (a.diag_add ? a.diag_add[gr] : 0.0);
+              k = (T)((double)k + add);
+            } else if (a.pad_identity) {
+              k = (T)1;
+            }
+          }
+        }
+        val[v] = k;
       }
-      T k = kern_eval<T, KIND>(q, tab, os);
-      if (!FAST) {
-        const int64_t gc = c0 + v;
-        if (!((gr < a.n1) && (gc < a.n2))) k = (T)0;
-        if (gr == gc) {
-          if (gr < a.n1) {
-            double add = a.diag_scalar + (a.diag_add ? a.diag_add[gr] : 0.0);
-            k = (T)((double)k + add);
-          } else if (a.pad_identity) {
-            k = (T)1;
+      if (col_ok) {
+        typename Vec<T>::type pk;
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) ((T*)&pk)[v] = val[v];
+        *reinterpret_cast<typename Vec<T>::type*>(outp + (int64_t)(r8 + u) * a.ld) = pk;
+      }
+      if (DOT) {
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) part[u] = fma((double)val[v], (double)dv[v], part[u]);
+      }
+    }
+    if (DOT) {
+      // reduce-scatter: after the three exchange steps lane l holds the sum over its 8-lane group of row (l & 7)...
+#pragma unroll
+      for (int s = 0; s < 3; ++s) {
+        const int h = 4 >> s;                        // 4, 2, 1 rows kept per lane after this step
+        const bool upper = (lane & h) != 0;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          if (u < h) {
+            const double keep = upper ? part[u + h] : part[u];
+            const double send = upper ? part[u] : part[u + h];
+            part[u] = keep + __shfl_xor_sync(0xffffffffu, send, h);
           }
         }
       }
-      val[v] = k;
-    }
-    if (col_ok) {
-      typename Vec<T>::type pk;
-#pragma unroll
-      for (int v = 0; v < VEC; ++v) ((T*)&pk)[v] = val[v];
-      *reinterpret_cast<typename Vec<T>::type*>(outp) = pk;
-    }
-    if (DOT) {
-      double part = 0.0;
-#pragma unroll
-      for (int v = 0; v < VEC; ++v) part += (double)val[v] * (double)dv[v];
-      part = warp_sum(part);
-      if (lane == 0) sred[r][wc] = part;
+      // ... then two plain steps across the four 8-lane groups
+      double sum = part[0];
+      sum += __shfl_xor_sync(0xffffffffu, sum, 8);
+      sum += __shfl_xor_sync(0xffffffffu, sum, 16);
+      // lane l (< 8) holds row index: bit 2 of l selected rows {4..7}, bit 1 then {2,3}/{6,7}, bit 0 the odd one
+      if (lane < 8) sred[wr * 32 + r8 + lane][wc] = sum;
     }
   }
 }
@@ -184,87 +211,83 @@ __global__ void __launch_bounds__(256) kbuild_kernel(const KbuildArgs a) {
 }
 
 // ---------------------------------------------------------------------------
-// Symmetric build K(X,X): one CTA per lower 64x64 tile (I >= J) evaluates the tile once and
-// stores it twice -- directly at (I,J) and, through a shared-memory transpose, at (J,I) -- so
-// the fp64 work is halved while every global store stays a 256-byte row segment.  Thread
-// (ty,tx) of a 16x16 grid owns rows ty+16a, columns {2tx,2tx+1}+32b; all coordinates live in
-// registers.
+// Symmetric build K(X,X): one CTA per lower 128x128 tile (I >= J) evaluates the tile once and
+// stores it twice, at (I,J) and transposed at (J,I), halving the fp64 work.  A lane owns 2x2
+// micro-blocks (rows 2mr..2mr+1, cols 2mc..2mc+1 of an 8x16 warp patch), so both stores are
+// 16-byte vectors: 8 lanes cover 128 contiguous bytes of a direct row, 4 lanes cover 64
+// contiguous bytes of a mirrored row -- no shared-memory transpose.
 // ---------------------------------------------------------------------------
-#define KS_T 64
+#define KS_T 128
 template <int D, int KIND>
 __global__ void __launch_bounds__(256) kbuild_sym_kernel(const KbuildArgs a) {
-  __shared__ double sT[KS_T][KS_T + 1];
+  __shared__ __align__(16) double sxr[KS_T][D], sxc[KS_T][D];
   __shared__ double stab[16];
-  if (threadIdx.x < 16) stab[threadIdx.x] = a.kp.outputscale * c_exp2_16th[threadIdx.x];
   const int L = blockIdx.x;
   int ti = (int)((sqrt(8.0 * (double)L + 1.0) - 1.0) * 0.5);
   while ((ti + 1) * (ti + 2) / 2 <= L) ++ti;
   while (ti * (ti + 1) / 2 > L) --ti;
   const int tj = L - ti * (ti + 1) / 2;
-  const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int64_t r0 = (int64_t)ti * KS_T, c0 = (int64_t)tj * KS_T;
-  const int d = (D == 0) ? a.kp.d : D;
-  constexpr int DD = (D == 0) ? ALGP_MAX_D : D;
-
-  double xr[4][DD], xc[4][DD];
+  if (tid < 16) stab[tid] = a.kp.outputscale * c_exp2_16th[tid];
+  {
+    const int64_t gx = (tid < KS_T) ? r0 + tid : c0 + (tid - KS_T);
+    double* dst = (tid < KS_T) ? sxr[tid] : sxc[tid - KS_T];
 #pragma unroll
-  for (int q = 0; q < 4; ++q) {
-    const int64_t gr = r0 + ty + 16 * q;
-    const int64_t gc = c0 + 2 * tx + (q & 1) + 32 * (q >> 1);
-#pragma unroll
-    for (int j = 0; j < DD; ++j) {
-      xr[q][j] = (j < d && gr < a.n1) ? a.x1[gr * d + j] * (a.kp.inv_ls[j] * kscale<KIND>()) : 0.0;
-      xc[q][j] = (j < d && gc < a.n1) ? a.x1[gc * d + j] * (a.kp.inv_ls[j] * kscale<KIND>()) : 0.0;
-    }
+    for (int j = 0; j < D; ++j) dst[j] = (gx < a.n1) ? a.x1[gx * D + j] * (a.kp.inv_ls[j] * kscale<KIND>()) : 0.0;
   }
-  const double os = a.kp.outputscale;
-  __syncthreads();                               // stab
-  const bool fast = (ti != tj) && (r0 + KS_T <= a.n1);      // off-diagonal and fully inside: no masks, no diagonal work
-  double* outp = (double*)a.out;
-#pragma unroll
-  for (int qa = 0; qa < 4; ++qa) {
-    const int r = ty + 16 * qa;
-    const int64_t gr = r0 + r;
-#pragma unroll
-    for (int b = 0; b < 2; ++b) {
-      double val[2];
-#pragma unroll
-      for (int e = 0; e < 2; ++e) {
-        const int qc = e + 2 * b;
-        double qq = 0.0;
-#pragma unroll
-        for (int j = 0; j < DD; ++j) {
-          const double df = xr[qa][j] - xc[qc][j];
-          qq = fma(-df, df, qq);
-        }
-        double k = kern_eval<double, KIND>(qq, stab, os);
-        if (!fast) {
-          const int64_t gc = c0 + 2 * tx + e + 32 * b;
-          if (!((gr < a.n1) && (gc < a.n1))) k = 0.0;
-          if (gr == gc) {
-            if (gr < a.n1) k += a.diag_scalar + (a.diag_add ? a.diag_add[gr] : 0.0);
-            else if (a.pad_identity) k = 1.0;
-          }
-        }
-        val[e] = k;
-      }
-      const int c = 2 * tx + 32 * b;
-      *reinterpret_cast<double2*>(outp + gr * a.ld + c0 + c) = make_double2(val[0], val[1]);
-      if (ti != tj) {
-        sT[c][r] = val[0];
-        sT[c + 1][r] = val[1];
-      }
-    }
-  }
-  if (ti == tj) return;                           // block-uniform
   __syncthreads();
+
+  const int mr = lane >> 3, mc = lane & 7;
+  const bool mirror = (ti != tj);
+  const bool fast = mirror && (r0 + KS_T <= a.n1);          // off-diagonal and fully inside: no masks
+  const double os = a.kp.outputscale;
+  double* outp = (double*)a.out;
+#pragma unroll 1
+  for (int pr = 2 * warp; pr < 2 * warp + 2; ++pr) {
+    const int rl = pr * 8 + 2 * mr;                          // local row of the micro-block
+    double xr[2][D];
 #pragma unroll
-  for (int qa = 0; qa < 4; ++qa) {
-    const int r = ty + 16 * qa;                  // row of the mirrored tile = column of the original
+    for (int e = 0; e < 2; ++e)
 #pragma unroll
-    for (int b = 0; b < 2; ++b) {
-      const int c = 2 * tx + 32 * b;
-      *reinterpret_cast<double2*>(outp + (c0 + r) * a.ld + r0 + c) = make_double2(sT[r][c], sT[r][c + 1]);
+      for (int j = 0; j < D; ++j) xr[e][j] = sxr[rl + e][j];
+#pragma unroll 2
+    for (int pc = 0; pc < 8; ++pc) {
+      const int cl = pc * 16 + 2 * mc;
+      double v[2][2];
+#pragma unroll
+      for (int f = 0; f < 2; ++f) {
+        double xc[D];
+#pragma unroll
+        for (int j = 0; j < D; ++j) xc[j] = sxc[cl + f][j];
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          double q = 0.0;
+#pragma unroll
+          for (int j = 0; j < D; ++j) {
+            const double df = xr[e][j] - xc[j];
+            q = fma(-df, df, q);
+          }
+          double k = kern_eval<double, KIND>(q, stab, os);
+          if (!fast) {
+            const int64_t gr = r0 + rl + e, gc = c0 + cl + f;
+            if (!((gr < a.n1) && (gc < a.n1))) k = 0.0;
+            if (gr == gc) {
+              if (gr < a.n1) k += a.diag_scalar + (a.diag_add ? a.diag_add[gr] : 0.0);
+              else if (a.pad_identity) k = 1.0;
+            }
+          }
+          v[e][f] = k;
+        }
+      }
+#pragma unroll
+      for (int e = 0; e < 2; ++e)
+        *reinterpret_cast<double2*>(outp + (r0 + rl + e) * a.ld + c0 + cl) = make_double2(v[e][0], v[e][1]);
+      if (mirror) {
+#pragma unroll
+        for (int f = 0; f < 2; ++f)
+          *reinterpret_cast<double2*>(outp + (c0 + cl + f) * a.ld + r0 + rl) = make_double2(v[0][f], v[1][f]);
+      }
     }
   }
 }

@@ -73,40 +73,51 @@ class ClockSampler(object):
     """SM clock and throttle reasons DURING the timed region (B200_PROFILING.md), polled through NVML
     every few ms (the timed region is tens of ms; spawning nvidia-smi would see one sample)."""
 
+    BITS = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "sw_thermal_slowdown": 0x20, "hw_thermal_slowdown": 0x40}
+
     def __init__(self, index=0):
         self.rows = []
         self.stop = False
         self.index = index
         self.max_mhz = None
-        self.t = threading.Thread(target=self.run, daemon=True)
-
-    def run(self):
-        try:
+        self.nv = self.h = None
+        try:                                        # NVML start-up takes ~100 ms: do it before the timed region
             import pynvml as nv
             nv.nvmlInit()
-            h = nv.nvmlDeviceGetHandleByIndex(self.index)
-            self.max_mhz = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
-            get_reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or \
+            self.h = nv.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = float(nv.nvmlDeviceGetMaxClockInfo(self.h, nv.NVML_CLOCK_SM))
+            self.get_reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or \
                 nv.nvmlDeviceGetCurrentClocksThrottleReasons
-            bits = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "sw_thermal_slowdown": 0x20, "hw_thermal_slowdown": 0x40}
+            self.nv = nv
+        except Exception as e:
+            self.err = repr(e)
+        self.t = threading.Thread(target=self.run, daemon=True)
+
+    def sample(self):
+        mhz = float(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM))
+        r = int(self.get_reasons(self.h))
+        self.rows.append((mhz, [k for k, b in self.BITS.items() if r & b]))
+
+    def run(self):
+        if self.nv is not None:
             while not self.stop:
-                mhz = float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
-                r = int(get_reasons(h))
-                self.rows.append((mhz, [k for k, b in bits.items() if r & b]))
+                try:
+                    self.sample()
+                except Exception:
+                    break
                 time.sleep(0.002)
-        except Exception as e:                      # NVML missing: fall back to one nvidia-smi sample
-            try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=clocks.sm,clocks.max.sm",
-                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
-                a, b = [float(v) for v in out.strip().split(",")]
-                self.rows.append((a, []))
-                self.max_mhz = b
-            except Exception:
-                self.rows.append((float("nan"), ["unavailable: %r" % (e,)]))
+            return
+        try:                                        # NVML missing: one nvidia-smi sample
+            out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=clocks.sm,clocks.max.sm",
+                                  "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+            a, b = [float(v) for v in out.strip().split(",")]
+            self.rows.append((a, []))
+            self.max_mhz = b
+        except Exception:
+            self.rows.append((float("nan"), ["unavailable"]))
 
     def __enter__(self):
         self.t.start()
-        time.sleep(0.02)
         return self
 
     def __exit__(self, *a):
