@@ -26,7 +26,7 @@
 #define G_STAGES 4
 #define G_PITCH_K 20
 #define G_PITCH_MN 132
-#define G_SMEM_BYTES(TM, TN) (G_STAGES * ((TM) + (TN)) * G_PITCH_K * 8)   // 163840 for 128x128, 81920 for 64x64
+#define G_SMEM_BYTES(TM, TN, ST) ((ST) * ((TM) + (TN)) * G_PITCH_K * 8)   // 163840 for 128x128x4, 92160 for 128x64x3
 
 enum { LAY_KMAJ = 0, LAY_MNMAJ = 1 };
 enum { TM_FULL = 0, TM_LOWER = 1 };
@@ -77,7 +77,7 @@ __device__ __forceinline__ double g_frag(const double* s, int row, int k) {
 // SUBC: the update C <- C - A*B (alpha = -1, beta = 1: every Cholesky trailing update).  The
 // accumulators start as C, loaded while the cp.async prologue is in flight, and B fragments are
 // negated, so the epilogue is a plain store and no C read sits exposed after the last MMA.
-template <int ALAY, int BLAY, int TM, int TN, bool SUBC>
+template <int ALAY, int BLAY, int TM, int TN, bool SUBC, int NSTAGE>
 __global__ void __launch_bounds__(256, (TM == 128 && TN == 128) ? 1 : 2) gemm_f64_kernel(const GemmArgs p) {
   constexpr int MI = TM / 16, NI = TN / 32;     // 8x8 accumulator blocks per warp (rows x cols)
   constexpr int WM = TM / 2, WN = TN / 4;       // warp sub-tile
@@ -90,7 +90,14 @@ __global__ void __launch_bounds__(256, (TM == 128 && TN == 128) ? 1 : 2) gemm_f6
 
   // ---- tile map -----------------------------------------------------------
   int mt, nt;
-  if (p.tmap == TM_LOWER) {
+  if (p.tmap == TM_LOWER && TN * 2 == TM) {
+    // half-width column tiles: row mt owns column tiles 0 .. 2*mt+1, mt*(mt+1) tiles precede it
+    int L = blockIdx.x;
+    mt = (int)((sqrt(4.0 * (double)L + 1.0) - 1.0) * 0.5);
+    while ((mt + 1) * (mt + 2) <= L) ++mt;
+    while (mt * (mt + 1) > L) --mt;
+    nt = L - mt * (mt + 1);
+  } else if (p.tmap == TM_LOWER) {
     int L = blockIdx.x;
     mt = (int)((sqrt(8.0 * (double)L + 1.0) - 1.0) * 0.5);
     while ((mt + 1) * (mt + 2) / 2 <= L) ++mt;
@@ -122,7 +129,7 @@ __global__ void __launch_bounds__(256, (TM == 128 && TN == 128) ? 1 : 2) gemm_f6
 
   // ---- pipeline prologue --------------------------------------------------
 #pragma unroll
-  for (int s = 0; s < G_STAGES - 1; ++s) {
+  for (int s = 0; s < NSTAGE - 1; ++s) {
     if (s < KT) {
       double* sa = g_smem + (size_t)s * STAGE;
       g_load_tile<ALAY, TM>(sa, A, p.lda, m0, kb + s * GK, tid);
@@ -146,18 +153,18 @@ __global__ void __launch_bounds__(256, (TM == 128 && TN == 128) ? 1 : 2) gemm_f6
     }
 
   for (int kt = 0; kt < KT; ++kt) {
-    cp_async_wait<G_STAGES - 2>();
+    cp_async_wait<NSTAGE - 2>();
     __syncthreads();
     {
-      int nk = kt + G_STAGES - 1;
+      int nk = kt + NSTAGE - 1;
       if (nk < KT) {
-        double* sa = g_smem + (size_t)(nk % G_STAGES) * STAGE;
+        double* sa = g_smem + (size_t)(nk % NSTAGE) * STAGE;
         g_load_tile<ALAY, TM>(sa, A, p.lda, m0, kb + nk * GK, tid);
         g_load_tile<BLAY, TN>(sa + OPER_A, B, p.ldb, n0, kb + nk * GK, tid);
       }
       cp_async_commit();
     }
-    const double* sa = g_smem + (size_t)(kt % G_STAGES) * STAGE;
+    const double* sa = g_smem + (size_t)(kt % NSTAGE) * STAGE;
     const double* sb = sa + OPER_A;
 #pragma unroll
     for (int ks = 0; ks < GK / 4; ++ks) {
