@@ -166,8 +166,31 @@ class GPFactor(object):
              ptr(V), V.stride(0) if V is not None else 0, ptr(rn), stream())
         return V, rn
 
-    def mean_var(self, xs, y0, ymean, test_var=None, want_var=True, max_rows=65536):
-        """Posterior mean (and latent variance) at xs: utils.py:300-308 without the inverse."""
+    def split_tf32(self, M):
+        """fp64 device matrix -> (hi, lo) float32 planes for the tcgen05 TF32 path."""
+        rows, cols = M.shape
+        hi = torch.empty((rows, cols), dtype=torch.float32, device=M.device)
+        lo = torch.empty((rows, cols), dtype=torch.float32, device=M.device)
+        call("algp_split_tf32", ptr(M), rows, cols, M.stride(0), ptr(hi), ptr(lo), cols, stream())
+        return hi, lo
+
+    def whiten_norm_tf32(self, Ks):
+        """Squared row norms of V = Ks L^-T per 128-column tile through split-TF32 tcgen05 MMAs."""
+        if getattr(self, "_linv_tf32", None) is None:
+            self._linv_tf32 = self.split_tf32(self.Linv)
+        lh, ll = self._linv_tf32
+        kh, kl = self.split_tf32(Ks)
+        Mpad = Ks.shape[0]
+        rn = torch.empty((Mpad, self.Npad // BLK), dtype=torch.float64, device=Ks.device)
+        call("algp_trmm_rt_tf32", ptr(kh), ptr(kl), Mpad, kh.stride(0), ptr(lh), ptr(ll), self.Npad, lh.stride(0),
+             ptr(rn), stream())
+        return rn
+
+    def mean_var(self, xs, y0, ymean, test_var=None, want_var=True, max_rows=65536, precision="fp64"):
+        """Posterior mean (and latent variance) at xs: utils.py:300-308 without the inverse.
+        precision="tf32" runs the O(N^2 M) variance step on the tcgen05 tensor cores (1e-4 tier)."""
+        if precision not in ("fp64", "tf32"):
+            raise ValueError("precision must be 'fp64' or 'tf32'")
         alpha, _ = self.solve(y0)
         M = xs.shape[0]
         mu = torch.empty(M, dtype=torch.float64, device=xs.device)
@@ -177,7 +200,10 @@ class GPFactor(object):
             Ks, part = self.cross(xs[lo:hi], alpha)
             mu[lo:hi] = rowsum(part, 1.0, ymean, rows=hi - lo)
             if want_var:
-                _, rn = self.whiten(Ks, want_V=False)
+                if precision == "tf32":
+                    rn = self.whiten_norm_tf32(Ks)
+                else:
+                    _, rn = self.whiten(Ks, want_V=False)
                 tv = None if test_var is None else test_var[lo:hi].contiguous()
                 var[lo:hi] = rowsum(rn, -1.0, self.hyper.outputscale, tv, rows=hi - lo)
             del Ks

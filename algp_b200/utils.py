@@ -124,7 +124,7 @@ def _posterior(gp, hyper, train_x, train_y, test_x, train_var, test_var, want_va
     tv = None if test_var is None else engine.to_dev(np.asarray(test_var, dtype=np.float64), device=dev)
     M = xs.shape[0]
     if not want_cov:
-        mu, var = f.mean_var(xs, y0, ymean, tv, want_var=want_var)
+        mu, var = f.mean_var(xs, y0, ymean, tv, want_var=want_var, precision=getattr(gp, "precision", "fp64"))
         mu_h = mu.cpu().numpy()
         var_h = var.cpu().numpy() if want_var else None
         f.check()

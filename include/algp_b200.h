@@ -77,6 +77,16 @@ int algp_trmm_rt(const double* Ks, int64_t mpad, int64_t ldk, const double* Linv
 int algp_gemm_nt(const double* A, int64_t lda, const double* B, int64_t ldb, double* C, int64_t ldc,
                  int64_t mpad, int64_t npad, int64_t kpad, double alpha, double beta, int lower_only, void* stream);
 
+/* ---- K2': TF32 mode of the variance path (tcgen05 tensor cores, TMEM accumulators) ---- */
+/* fp64 matrix -> fp32 hi / lo planes with hi exactly representable in TF32 (x ~= hi + lo) */
+int algp_split_tf32(const double* src, int64_t rows, int64_t cols, int64_t ld, float* hi, float* lo,
+                    int64_t ldo, void* stream);
+/* Same row-norm partials as algp_trmm_rt (rn_partial[m][t], t < npad/128) computed as the split-TF32
+ * product K_hi L_hi^T + K_hi L_lo^T + K_lo L_hi^T with fp32 accumulation: the 1e-4 tier of the
+ * variance (utils.py:305-308) at ~8x the fp64 rate. */
+int algp_trmm_rt_tf32(const float* Khi, const float* Klo, int64_t mpad, int64_t ldk, const float* Lhi,
+                      const float* Llo, int64_t npad, int64_t ldl, double* rn_partial, void* stream);
+
 /* ---- K4: marginal-likelihood gradient (GPR.fit, models.py:145-158) ---------- */
 /* Ainv (lower triangle) = Linv^T Linv = A^-1 */
 int algp_potri_lower(const double* Linv, int64_t npad, int64_t ldi, double* Ainv, int64_t lda, void* stream);

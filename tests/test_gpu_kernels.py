@@ -234,3 +234,33 @@ def test_argmax_first_max_semantics():
     _lib.call("algp_argmax", _lib.ptr(xd), len(x), 7, _lib.ptr(out), _lib.ptr(state_work), _lib.stream())
     assert int(out[1].item()) == 1 + 7
     assert out[0:1].view(torch.float64).item() == 5.0
+
+
+# ---------------------------------------------------------------- TF32 mode (tcgen05)
+def test_split_tf32_planes():
+    rng = np.random.default_rng(0)
+    M = rng.normal(size=(256, 384)) * np.exp(rng.normal(size=(256, 384)) * 3)
+    f = engine.GPFactor.__new__(engine.GPFactor)
+    hi, lo = engine.GPFactor.split_tf32(f, dev(M))
+    hi, lo = hi.cpu().numpy(), lo.cpu().numpy()
+    assert (hi.view(np.uint32) & 0x1FFF == 0).all()                 # exactly representable in TF32
+    np.testing.assert_allclose(hi.astype(np.float64) + lo.astype(np.float64), M, rtol=2e-7 * 2 ** -10 + 1e-10, atol=0)
+    assert np.abs(lo).max() <= np.abs(M).max() * 2.0 ** -10
+
+
+@pytest.mark.parametrize("N,M", [(128, 128), (300, 150), (640, 1000), (1536, 700)])
+def test_variance_tf32_tier(N, M):
+    """precision='tf32': split-TF32 tcgen05 path against the fp64 oracle at the north star's 1e-4 tier
+    (absolute, relative to the prior scale s^2 = 1)."""
+    x, var, th, hy, A = spd_problem(N, N + 7)
+    rng = np.random.default_rng(N)
+    xs = rng.uniform(0, 40, size=(M, 2))
+    y = rng.normal(size=N)
+    f = engine.GPFactor(hy, dev(x), diag_add=dev(var))
+    mu64, v64 = f.mean_var(dev(xs), dev(y - y.mean()), float(y.mean()))
+    mu32, v32 = f.mean_var(dev(xs), dev(y - y.mean()), float(y.mean()), precision="tf32")
+    f.check()
+    _, v_o = O.predictive_distribution_chol(O.OracleGP(th, "fp64"), x, y, xs, var, return_var=True)
+    np.testing.assert_allclose(v64.cpu().numpy(), v_o, rtol=0, atol=1e-9)
+    np.testing.assert_allclose(v32.cpu().numpy(), v_o, rtol=0, atol=1e-4)
+    np.testing.assert_array_equal(mu32.cpu().numpy(), mu64.cpu().numpy())   # the mean stays fp64
