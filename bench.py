@@ -215,7 +215,7 @@ def fit_predict_bench(torch, engine, n_train, grid_side, reps, peak_hbm):
     y0 = engine.to_dev(y - y.mean())
     var = engine.to_dev(np.full(n_train, STATIC_STD ** 2))
     ev = lambda: torch.cuda.Event(enable_timing=True)
-    names = ["kbuild_train", "potrf", "trtri", "solve", "kbuild_cross_mean", "variance_trmm"]
+    names = ["kbuild_train", "potrf", "trtri", "solve", "kbuild_cross_mean", "variance_trmm", "variance_tf32"]
     times = {k: [] for k in names + ["total"]}
     M = xs.shape[0]
     Npad = max(128, engine.pad_to(n_train))
@@ -249,18 +249,27 @@ def fit_predict_bench(torch, engine, n_train, grid_side, reps, peak_hbm):
         _, rn = f.whiten(Ks, want_V=False)
         v = engine.rowsum(rn, -1.0, hy.outputscale, None, rows=M)
         marks[6].record()
+        # TF32 mode of the same step: split K(X*,X) and Linv into fp32 hi/lo planes + tcgen05 split-TF32 TRMM
+        rn32 = f.whiten_norm_tf32(Ks)
+        v32 = engine.rowsum(rn32, -1.0, hy.outputscale, None, rows=M)
+        marks[7].record()
         torch.cuda.synchronize()
+        f._linv_tf32 = None
+        del rn32
         if int(info.item()) != 0:
             raise RuntimeError("fit_predict bench: matrix not positive definite")
         if rep == 0:
             continue           # warm-up
         for i, k in enumerate(names):
             times[k].append(marks[i].elapsed_time(marks[i + 1]))
-        times["total"].append(marks[0].elapsed_time(marks[-1]))
+        times["total"].append(marks[0].elapsed_time(marks[6]))
+        tf32_err = float((v32 - v).abs().max().item())
     med = {k: float(np.median(v)) for k, v in times.items()}
     N = float(max(128, engine.pad_to(n_train)))
     Mp = float(max(128, engine.pad_to(M)))
-    out = {"n_train": n_train, "n_test": M, "ms": med["total"], "ms_by_stage": med,
+    out = {"n_train": n_train, "n_test": M, "ms": med["total"],
+           "ms_tf32_mode": med["total"] - med["variance_trmm"] + med["variance_tf32"],
+           "tf32_max_abs_var_diff_vs_fp64": tf32_err, "ms_by_stage": med,
            "var_min": float(v.min().item()), "var_max": float(v.max().item()),
            "rooflines": {
                "kbuild_train": {"bound": "hbm", "achieved": 8 * N * N / med["kbuild_train"] / 1e6, "peak": peak_hbm, "unit": "GB/s"},
@@ -268,6 +277,9 @@ def fit_predict_bench(torch, engine, n_train, grid_side, reps, peak_hbm):
                "potrf": {"bound": "fp64 tensor (DMMA)", "achieved": N ** 3 / 3 / med["potrf"] / 1e9, "unit": "TFLOP/s"},
                "trtri": {"bound": "fp64 tensor (DMMA)", "achieved": N ** 3 / 3 / med["trtri"] / 1e9, "unit": "TFLOP/s"},
                "variance_trmm": {"bound": "fp64 tensor (DMMA)", "achieved": N * N * Mp / med["variance_trmm"] / 1e9, "unit": "TFLOP/s"},
+               "variance_tf32": {"bound": "tf32 tensor (tcgen05), 3 MMAs per product, incl. the hi/lo split passes",
+                                 "achieved": 3 * N * N * Mp / med["variance_tf32"] / 1e9, "unit": "TFLOP/s(tf32)",
+                                 "effective_fp64_equiv_tflops": N * N * Mp / med["variance_tf32"] / 1e9},
            }}
     for r in out["rooflines"].values():
         if "peak" in r:
@@ -290,6 +302,28 @@ def dgemm_peak(torch, n=8192, reps=3):
         torch.cuda.synchronize()
         best = min(best, e0.elapsed_time(e1))
     return 2.0 * n ** 3 / best / 1e9
+
+
+def tf32_gemm_peak(torch, n=8192, reps=3):
+    """cuBLAS TF32 GEMM rate (fp32 operands, allow_tf32): the tcgen05 roofline denominator."""
+    old = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = True
+    try:
+        a = torch.randn(n, n, dtype=torch.float32, device="cuda")
+        b = torch.randn(n, n, dtype=torch.float32, device="cuda")
+        torch.matmul(a, b)
+        torch.cuda.synchronize()
+        best = 1e9
+        for _ in range(reps):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            torch.matmul(a, b)
+            e1.record()
+            torch.cuda.synchronize()
+            best = min(best, e0.elapsed_time(e1))
+        return 2.0 * n ** 3 / best / 1e9
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = old
 
 
 def run_ours(args, rank, world, local_rank):
@@ -415,11 +449,16 @@ def run_ours(args, rank, world, local_rank):
             fits = [fit_predict_bench(torch, engine, 4096, 64, 5, peak_hbm)]
             if not args.skip_large:
                 fits.append(fit_predict_bench(torch, engine, 16384, 256, 2, peak_hbm))
+            tf32_peak = tf32_gemm_peak(torch)
+            extra["tf32_gemm_peak_tflops_cublas_8192"] = tf32_peak
             for f in fits:
                 for r in f["rooflines"].values():
                     if r["unit"] == "TFLOP/s":
                         r["peak"] = fp64_peak
                         r["frac"] = r["achieved"] / fp64_peak
+                    elif r["unit"].startswith("TFLOP/s(tf32)"):
+                        r["peak"] = tf32_peak
+                        r["frac"] = r["achieved"] / tf32_peak
             extra["fit_predict"] = fits
         except Exception as e:       # the headline line must still print
             extra["fit_predict_error"] = repr(e)
