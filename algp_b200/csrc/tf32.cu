@@ -8,15 +8,17 @@
 //
 //   split_tf32_kernel   fp64 matrix -> fp32 hi / lo planes (one HBM pass; hi has its low 13 mantissa
 //                       bits cleared so the tensor core's own truncation is exact)
-//   trmm_tf32x3_kernel  one CTA per 128 x 256 output tile: 4 loader/epilogue warps + 1 MMA warp.
-//                       Loaders cp.async 16-byte row chunks straight into the UMMA K-major
-//                       no-swizzle core-matrix layout ([8-row group][16 B chunk][row][16 B]);
-//                       full/empty mbarriers form a 4-stage ring; one thread issues 6
-//                       tcgen05.mma.kind::tf32 (M128 N256 K8) per 16-wide k-stage into a 256-column
-//                       TMEM accumulator; tcgen05.commit frees the stage.  Epilogue: tcgen05.ld
-//                       32x32b, a thread owns a whole accumulator row, squares and sums it --
-//                       V is never written.  Triangular k-range (Linv is lower triangular).
+//   trmm_tf32x3_kernel  one CTA per 128 x 256 output tile: 4 epilogue warps (one lane of warp 0 is
+//                       the TMA producer) + 1 MMA warp.  The producer issues four 2-D TMA tile
+//                       loads per 16-wide k-stage (A_hi, A_lo: 128 x 64 B; B_hi, B_lo: 256 x 64 B,
+//                       SWIZZLE_64B) that complete on the stage's `full` mbarrier; one thread issues
+//                       6 tcgen05.mma.kind::tf32 (M128 N256 K8) per stage into a 256-column TMEM
+//                       accumulator and tcgen05.commit releases the stage (`empty` mbarrier):
+//                       a 4-stage ring with no thread ever touching operand bytes.  Epilogue:
+//                       tcgen05.ld 32x32b, a thread owns a whole accumulator row, squares and sums
+//                       it -- V is never written.  Triangular k-range (Linv is lower triangular).
 #include "common.cuh"
+#include <cuda.h>
 
 #define T3_TM 128
 #define T3_TN 256
@@ -25,8 +27,7 @@
 #define T3_A_BYTES (T3_TM * T3_KC * 4) // 8 KB
 #define T3_B_BYTES (T3_TN * T3_KC * 4) // 16 KB
 #define T3_STAGE_BYTES (2 * T3_A_BYTES + 2 * T3_B_BYTES)   // A_hi, A_lo, B_hi, B_lo = 48 KB
-#define T3_SMEM_BYTES (T3_STAGES * T3_STAGE_BYTES + 1024)
-#define T3_LOADERS 128
+#define T3_SMEM_BYTES (T3_STAGES * T3_STAGE_BYTES + 1024)   // + slack to align the ring to 1024 B
 #define T3_THREADS 160
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -59,11 +60,20 @@ __device__ __forceinline__ void tc_mma_tf32(uint32_t tmem_d, uint64_t desc_a, ui
       ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
       : "memory");
 }
-// K-major, no swizzle: core matrix = 8 rows x 16 B contiguous; LBO = distance between the two 16-byte
-// k-chunks of one MMA, SBO = distance between 8-row groups (cute::UMMA::SmemDescriptor, version 1)
-__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
-  return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) |
-         ((uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32) | (1ull << 46);
+// K-major SWIZZLE_64B operand tile: rows of 64 B, 8-row groups 512 B apart (SBO); the 16-byte chunks of
+// a row are XOR-swizzled by the hardware on both the TMA write and the MMA read
+// (cute::UMMA::SmemDescriptor: version 1, layout_type 4, LBO field 1 for swizzled K-major layouts)
+__device__ __forceinline__ uint64_t umma_desc_sw64(uint32_t saddr) {
+  return (uint64_t)((saddr >> 4) & 0x3FFF) | (1ull << 16) | ((uint64_t)(512 >> 4) << 32) | (1ull << 46) | (4ull << 61);
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* b, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(b)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* tm, int c_inner, int c_outer, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+      ::"r"(dst), "l"(tm), "r"(c_inner), "r"(c_outer), "r"(smem_u32(bar))
+      : "memory");
 }
 // cute::UMMA::InstrDescriptor: c_format F32 (1) [4,6), a/b_format TF32 (2) [7,10) / [10,13), K-major, N>>3 [17,23), M>>4 [24,29)
 __host__ __device__ constexpr uint32_t umma_idesc_tf32(int M, int N) {
@@ -91,21 +101,19 @@ __global__ void split_tf32_kernel(const double* __restrict__ src, int64_t rows, 
 }
 
 struct T3Args {
-  const float* Ahi; const float* Alo; int64_t lda;   // [mpad x npad] K(X*,X)
-  const float* Bhi; const float* Blo; int64_t ldb;   // [npad x npad] Linv (lower)
   int MT, NT;                                        // 128-row tiles, 256-col tiles (last may be half)
   int64_t npad;
   double* rn_partial; int rn_nt;                     // [mpad x npad/128]
 };
 
-// tile offset: [8-row group][16-byte chunk][row in group][16 B]
-__device__ __forceinline__ uint32_t t3_off(int r, int kc) { return (uint32_t)((r >> 3) * 512 + kc * 128 + (r & 7) * 16); }
-
-__global__ void __launch_bounds__(T3_THREADS, 1) trmm_tf32x3_kernel(const T3Args p) {
-  extern __shared__ __align__(1024) unsigned char t3_smem[];
+__global__ void __launch_bounds__(T3_THREADS, 1)
+trmm_tf32x3_kernel(const T3Args p, const __grid_constant__ CUtensorMap tm_ahi, const __grid_constant__ CUtensorMap tm_alo,
+                   const __grid_constant__ CUtensorMap tm_bhi, const __grid_constant__ CUtensorMap tm_blo) {
+  extern __shared__ unsigned char t3_smem_raw[];
   __shared__ uint64_t full_bar[T3_STAGES], empty_bar[T3_STAGES], done_bar;
   __shared__ uint32_t tmem_slot;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t ring = (smem_u32(t3_smem_raw) + 1023u) & ~1023u;      // swizzle atoms need aligned tiles
 
   // tile map: groups of 16 m-tiles sweep the n-tiles together, long (large nt) tiles first, so that
   // concurrent CTAs stream the same k-window of A and the same rows of B through L2
@@ -122,7 +130,7 @@ __global__ void __launch_bounds__(T3_THREADS, 1) trmm_tf32x3_kernel(const T3Args
 
   if (tid == 0) {
     for (int s = 0; s < T3_STAGES; ++s) {
-      mbar_init(&full_bar[s], T3_LOADERS);
+      mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
     }
     mbar_init(&done_bar, 1);
@@ -138,44 +146,21 @@ __global__ void __launch_bounds__(T3_THREADS, 1) trmm_tf32x3_kernel(const T3Args
   const uint32_t tmem = tmem_slot;
 
   if (warp < 4) {
-    // ===================== loaders =====================
-    const int rows_total = T3_TM + T3_TM + ncols + ncols;      // A_hi, A_lo, B_hi, B_lo rows per stage
-    for (int it = 0; it < KT + T3_STAGES - 1; ++it) {
-      if (it < KT) {
+    if (tid == 0) {
+      // ===================== TMA producer (one thread) =====================
+      for (int it = 0; it < KT; ++it) {
         const int s = it % T3_STAGES, u = it / T3_STAGES;
         if (u > 0) mbar_wait(&empty_bar[s], (u - 1) & 1);       // the MMAs that read this slot are done
-        unsigned char* st = t3_smem + (size_t)s * T3_STAGE_BYTES;
-        const int64_t k0 = (int64_t)it * T3_KC;
-        // 4 consecutive threads fetch the 4 chunks (64 contiguous bytes) of one row; a warp fills
-        // one 8-row group = 512 contiguous bytes of shared memory
-        for (int q = tid; q < rows_total * 4; q += T3_LOADERS) {
-          const int rr = q >> 2, kc = q & 3;
-          const float* src;
-          unsigned char* dst;
-          if (rr < T3_TM) {
-            src = p.Ahi + (m0 + rr) * p.lda;
-            dst = st + t3_off(rr, kc);
-          } else if (rr < 2 * T3_TM) {
-            src = p.Alo + (m0 + rr - T3_TM) * p.lda;
-            dst = st + T3_A_BYTES + t3_off(rr - T3_TM, kc);
-          } else if (rr < 2 * T3_TM + ncols) {
-            src = p.Bhi + (n0 + rr - 2 * T3_TM) * p.ldb;
-            dst = st + 2 * T3_A_BYTES + t3_off(rr - 2 * T3_TM, kc);
-          } else {
-            src = p.Blo + (n0 + rr - 2 * T3_TM - ncols) * p.ldb;
-            dst = st + 2 * T3_A_BYTES + T3_B_BYTES + t3_off(rr - 2 * T3_TM - ncols, kc);
-          }
-          cp_async16(dst, src + k0 + kc * 4);
-        }
-      }
-      cp_async_commit();
-      const int done_it = it - (T3_STAGES - 1);                 // this group has landed after the wait below
-      if (done_it >= 0) {
-        cp_async_wait<T3_STAGES - 1>();
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the tensor core
-        mbar_arrive(&full_bar[done_it % T3_STAGES]);
+        const uint32_t st = ring + (uint32_t)s * T3_STAGE_BYTES;
+        const int k0 = it * T3_KC;
+        mbar_expect_tx(&full_bar[s], T3_STAGE_BYTES);           // out-of-range rows of a half tile are zero-filled and counted
+        tma_load_2d(st, &tm_ahi, k0, (int)m0, &full_bar[s]);
+        tma_load_2d(st + T3_A_BYTES, &tm_alo, k0, (int)m0, &full_bar[s]);
+        tma_load_2d(st + 2 * T3_A_BYTES, &tm_bhi, k0, (int)n0, &full_bar[s]);
+        tma_load_2d(st + 2 * T3_A_BYTES + T3_B_BYTES, &tm_blo, k0, (int)n0, &full_bar[s]);
       }
     }
+    __syncwarp();
     // ===================== epilogue =====================
     if (valid_tile) {
       mbar_wait(&done_bar, 0);
@@ -212,13 +197,13 @@ __global__ void __launch_bounds__(T3_THREADS, 1) trmm_tf32x3_kernel(const T3Args
       const int s = it % T3_STAGES, u = it / T3_STAGES;
       mbar_wait(&full_bar[s], u & 1);
       tc_fence_after();
-      const uint32_t a_hi = smem_u32(t3_smem + (size_t)s * T3_STAGE_BYTES);
+      const uint32_t a_hi = ring + (uint32_t)s * T3_STAGE_BYTES;
       const uint32_t a_lo = a_hi + T3_A_BYTES, b_hi = a_hi + 2 * T3_A_BYTES, b_lo = b_hi + T3_B_BYTES;
 #pragma unroll
-      for (int ks = 0; ks < T3_KC / 8; ++ks) {                  // one MMA consumes K = 8 fp32 = two 16-byte chunks
-        const uint32_t off = ks * 2 * 128;
-        const uint64_t dah = umma_desc(a_hi + off, 128, 512), dal = umma_desc(a_lo + off, 128, 512);
-        const uint64_t dbh = umma_desc(b_hi + off, 128, 512), dbl = umma_desc(b_lo + off, 128, 512);
+      for (int ks = 0; ks < T3_KC / 8; ++ks) {                  // one MMA consumes K = 8 fp32 = 32 B of every row
+        const uint32_t off = ks * 32;
+        const uint64_t dah = umma_desc_sw64(a_hi + off), dal = umma_desc_sw64(a_lo + off);
+        const uint64_t dbh = umma_desc_sw64(b_hi + off), dbl = umma_desc_sw64(b_lo + off);
         tc_mma_tf32(tmem, dah, dbh, idesc, (it | ks) != 0);
         tc_mma_tf32(tmem, dah, dbl, idesc, 1);
         tc_mma_tf32(tmem, dal, dbh, idesc, 1);
@@ -233,6 +218,34 @@ __global__ void __launch_bounds__(T3_THREADS, 1) trmm_tf32x3_kernel(const T3Args
   if (warp == 4) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(T3_TN));
   }
+}
+
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no link-time libcuda dependency)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)p;
+  }
+  return fn;
+}
+// fp32 [rows x cols] row-major (ld floats): boxes of box_rows x 16 floats (64 B), SWIZZLE_64B
+static int make_tmap(CUtensorMap* tm, const float* base, int64_t rows, int64_t cols, int64_t ld, int box_rows) {
+  EncodeTiledFn enc = get_encode_fn();
+  if (!enc) return ALGP_ERR_UNSUPPORTED;
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
+  cuuint32_t box[2] = {T3_KC, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? ALGP_OK : ALGP_ERR_INVALID;
 }
 
 extern "C" int algp_split_tf32(const double* src, int64_t rows, int64_t cols, int64_t ld, float* hi, float* lo,
@@ -266,16 +279,21 @@ extern "C" int algp_trmm_rt_tf32(const float* Khi, const float* Klo, int64_t mpa
     ALGP_CUDA(cudaFuncSetAttribute(trmm_tf32x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, T3_SMEM_BYTES));
     configured = true;
   }
+  if (((uintptr_t)Khi | (uintptr_t)Klo | (uintptr_t)Lhi | (uintptr_t)Llo) & 15) return ALGP_ERR_INVALID;
+  CUtensorMap ta_hi, ta_lo, tb_hi, tb_lo;
+  int rc;
+  if ((rc = make_tmap(&ta_hi, Khi, mpad, npad, ldk, T3_TM))) return rc;
+  if ((rc = make_tmap(&ta_lo, Klo, mpad, npad, ldk, T3_TM))) return rc;
+  if ((rc = make_tmap(&tb_hi, Lhi, npad, npad, ldl, T3_TN))) return rc;
+  if ((rc = make_tmap(&tb_lo, Llo, npad, npad, ldl, T3_TN))) return rc;
   T3Args a;
-  a.Ahi = Khi; a.Alo = Klo; a.lda = ldk;
-  a.Bhi = Lhi; a.Blo = Llo; a.ldb = ldl;
   a.MT = (int)(mpad / T3_TM);
   a.NT = (int)((npad + T3_TN - 1) / T3_TN);
   a.npad = npad;
   a.rn_partial = rn_partial; a.rn_nt = (int)(npad / ALGP_BLK);
   const int groups = (a.MT + 15) / 16;
   const int64_t grid = (int64_t)groups * 16 * a.NT;
-  trmm_tf32x3_kernel<<<(unsigned)grid, T3_THREADS, T3_SMEM_BYTES, (cudaStream_t)stream>>>(a);
+  trmm_tf32x3_kernel<<<(unsigned)grid, T3_THREADS, T3_SMEM_BYTES, (cudaStream_t)stream>>>(a, ta_hi, ta_lo, tb_hi, tb_lo);
   ALGP_LAUNCH_CHECK();
   return ALGP_OK;
 }
