@@ -153,7 +153,7 @@ trmm_tf32x3_kernel(const T3Args p, const __grid_constant__ CUtensorMap tm_ahi, c
         if (u > 0) mbar_wait(&empty_bar[s], (u - 1) & 1);       // the MMAs that read this slot are done
         const uint32_t st = ring + (uint32_t)s * T3_STAGE_BYTES;
         const int k0 = it * T3_KC;
-        mbar_expect_tx(&full_bar[s], T3_STAGE_BYTES);           // out-of-range rows of a half tile are zero-filled and counted
+        mbar_expect_tx(&full_bar[s], T3_STAGE_BYTES);
         tma_load_2d(st, &tm_ahi, k0, (int)m0, &full_bar[s]);
         tma_load_2d(st + T3_A_BYTES, &tm_alo, k0, (int)m0, &full_bar[s]);
         tma_load_2d(st + 2 * T3_A_BYTES, &tm_bhi, k0, (int)n0, &full_bar[s]);
@@ -284,8 +284,11 @@ extern "C" int algp_trmm_rt_tf32(const float* Khi, const float* Klo, int64_t mpa
   int rc;
   if ((rc = make_tmap(&ta_hi, Khi, mpad, npad, ldk, T3_TM))) return rc;
   if ((rc = make_tmap(&ta_lo, Klo, mpad, npad, ldk, T3_TM))) return rc;
-  if ((rc = make_tmap(&tb_hi, Lhi, npad, npad, ldl, T3_TN))) return rc;
-  if ((rc = make_tmap(&tb_lo, Llo, npad, npad, ldl, T3_TN))) return rc;
+  // the L planes are allocated with rows rounded up to 256 (see header), so a half-width last tile never
+  // depends on out-of-bounds fill
+  const int64_t lrows = (npad + T3_TN - 1) / T3_TN * T3_TN;
+  if ((rc = make_tmap(&tb_hi, Lhi, lrows, npad, ldl, T3_TN))) return rc;
+  if ((rc = make_tmap(&tb_lo, Llo, lrows, npad, ldl, T3_TN))) return rc;
   T3Args a;
   a.MT = (int)(mpad / T3_TM);
   a.NT = (int)((npad + T3_TN - 1) / T3_TN);

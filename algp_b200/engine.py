@@ -166,18 +166,21 @@ class GPFactor(object):
              ptr(V), V.stride(0) if V is not None else 0, ptr(rn), stream())
         return V, rn
 
-    def split_tf32(self, M):
-        """fp64 device matrix -> (hi, lo) float32 planes for the tcgen05 TF32 path."""
+    def split_tf32(self, M, row_multiple=1):
+        """fp64 device matrix -> (hi, lo) float32 planes for the tcgen05 TF32 path (allocation rows
+        rounded up to row_multiple, extra rows zero)."""
         rows, cols = M.shape
-        hi = torch.empty((rows, cols), dtype=torch.float32, device=M.device)
-        lo = torch.empty((rows, cols), dtype=torch.float32, device=M.device)
+        arows = pad_to(rows, row_multiple)
+        alloc = torch.empty if arows == rows else torch.zeros
+        hi = alloc((arows, cols), dtype=torch.float32, device=M.device)
+        lo = alloc((arows, cols), dtype=torch.float32, device=M.device)
         call("algp_split_tf32", ptr(M), rows, cols, M.stride(0), ptr(hi), ptr(lo), cols, stream())
         return hi, lo
 
     def whiten_norm_tf32(self, Ks):
         """Squared row norms of V = Ks L^-T per 128-column tile through split-TF32 tcgen05 MMAs."""
         if getattr(self, "_linv_tf32", None) is None:
-            self._linv_tf32 = self.split_tf32(self.Linv)
+            self._linv_tf32 = self.split_tf32(self.Linv, row_multiple=256)
         lh, ll = self._linv_tf32
         kh, kl = self.split_tf32(Ks)
         Mpad = Ks.shape[0]

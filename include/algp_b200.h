@@ -83,7 +83,8 @@ int algp_split_tf32(const double* src, int64_t rows, int64_t cols, int64_t ld, f
                     int64_t ldo, void* stream);
 /* Same row-norm partials as algp_trmm_rt (rn_partial[m][t], t < npad/128) computed as the split-TF32
  * product K_hi L_hi^T + K_hi L_lo^T + K_lo L_hi^T with fp32 accumulation: the 1e-4 tier of the
- * variance (utils.py:305-308) at ~8x the fp64 rate. */
+ * variance (utils.py:305-308).  The L planes must be ALLOCATED with their row count rounded up to a
+ * multiple of 256 (rows past npad are never used in the result). */
 int algp_trmm_rt_tf32(const float* Khi, const float* Klo, int64_t mpad, int64_t ldk, const float* Lhi,
                       const float* Llo, int64_t npad, int64_t ldl, double* rn_partial, void* stream);
 

@@ -243,6 +243,7 @@ def test_split_tf32_planes():
     f = engine.GPFactor.__new__(engine.GPFactor)
     hi, lo = engine.GPFactor.split_tf32(f, dev(M))
     hi, lo = hi.cpu().numpy(), lo.cpu().numpy()
+    assert hi.shape == (256, 384)
     assert (hi.view(np.uint32) & 0x1FFF == 0).all()                 # exactly representable in TF32
     np.testing.assert_allclose(hi.astype(np.float64) + lo.astype(np.float64), M, rtol=2e-7 * 2 ** -10 + 1e-10, atol=0)
     assert np.abs(lo).max() <= np.abs(M).max() * 2.0 ** -10
