@@ -14,6 +14,7 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--n", type=int, default=4096)
 ap.add_argument("--side", type=int, default=64)
 ap.add_argument("--reps", type=int, default=2)
+ap.add_argument("--tf32", action="store_true")
 a = ap.parse_args()
 rng = np.random.default_rng(1)
 x = rng.uniform(0, a.side, size=(a.n, 2))
@@ -28,7 +29,7 @@ for rep in range(a.reps):
     e[0].record()
     f = engine.GPFactor(hy, xd, diag_add=var)
     e[1].record()
-    mu, v = f.mean_var(xsd, y0, float(y.mean()))
+    mu, v = f.mean_var(xsd, y0, float(y.mean()), precision="tf32" if a.tf32 else "fp64")
     e[2].record()
     torch.cuda.synchronize()
     f.check()
