@@ -17,7 +17,7 @@ from . import engine
 
 
 def run_episode(hyper, X, static_flags, mobile_flags, static_std, mobile_std, batches, per_batch, path_fn,
-                capacity=None, return_scores=False):
+                capacity=None, return_scores=False, distributed=True):
     """Returns dict(picks=[[...] per batch], best_paths=[...], H=[entropy after each batch], ms_per_batch).
 
     static_flags / mobile_flags: boolean per location (agent.py:298,302).
@@ -40,7 +40,12 @@ def run_episode(hyper, X, static_flags, mobile_flags, static_std, mobile_std, ba
         picks = state.greedy(per_batch, d_s)
         out["picks"].append(picks)
         paths = np.ascontiguousarray(path_fn(b, picks), dtype=np.int32)
-        score, best = adist.sharded_best(state, paths, None, delta_scalar=d_m, skip=skip)
+        if distributed:
+            score, best = adist.sharded_best(state, paths, None, delta_scalar=d_m, skip=skip)
+        else:
+            sc = state.score_sets(engine.to_dev(paths, dtype=torch.int32, device=dev), None, delta_scalar=d_m, skip=skip)
+            pair = state.argmax(sc).cpu()
+            score, best = float(pair[0:1].view(torch.float64).item()), int(pair[1].item())
         if len(paths) == 1:                                       # agent.py:362-363
             best = 0
         out["best_paths"].append(int(best))

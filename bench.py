@@ -287,6 +287,41 @@ def fit_predict_bench(torch, engine, n_train, grid_side, reps, peak_hbm):
     return out
 
 
+def episode_bench(torch, engine, side=200, n_pilot=1024, acquisitions=500, per_batch=4, n_paths=256, path_len=16):
+    """BASELINE configs[4]: active-sampling episode on a side x side field: `acquisitions` static picks in batches
+    of `per_batch` (greedy, rank-1 appends), each batch followed by scoring `n_paths` candidate paths of `path_len`
+    mobile readings and committing the winner.  Path enumeration (env.py) is the planner's job: paths here are
+    synthetic straight runs starting at the batch's picks."""
+    from algp_b200.episode import run_episode
+    import oracle as O
+    grid, _ = O.gaussian_mixture_field(side, side, seed=1)
+    n = len(grid)
+    rng = np.random.default_rng(3)
+    static = np.zeros(n, bool)
+    static[rng.choice(n, n_pilot, replace=False)] = True
+    mobile = np.zeros(n, bool)
+    hyper = engine.Hyper(np.log([side / 16.0] * 2), 0.0, np.log(1e-2), "rbf")
+    batches = acquisitions // per_batch
+
+    def path_fn(b, picks):
+        prng = np.random.default_rng(1000 + b)
+        starts = np.array(picks)[prng.integers(0, len(picks), n_paths)]
+        r, c = starts // side, starts % side
+        dr, dc = prng.integers(-1, 2, n_paths), prng.integers(-1, 2, n_paths)
+        steps = np.arange(1, path_len + 1)[None, :]
+        rr = np.clip(r[:, None] + dr[:, None] * steps, 0, side - 1)
+        cc = np.clip(c[:, None] + dc[:, None] * steps, 0, side - 1)
+        return (rr * side + cc).astype(np.int32)
+
+    Xd = engine.to_dev(grid)
+    run_episode(hyper, Xd, static, mobile, STATIC_STD, MOBILE_STD, 2, per_batch, path_fn, distributed=False)   # warm-up
+    res = run_episode(hyper, Xd, static, mobile, STATIC_STD, MOBILE_STD, batches, per_batch, path_fn, distributed=False)
+    return {"field": "%dx%d" % (side, side), "n_locations": n, "pilot_samples": n_pilot, "acquisitions": batches * per_batch,
+            "paths_per_batch": n_paths, "path_len": path_len, "ms_per_acquisition": res["ms_per_acquisition"],
+            "ms_per_batch": res["ms_per_batch"], "mobile_committed": int(res["mobile"].sum()),
+            "entropy_first_last": [res["H"][0], res["H"][-1]]}
+
+
 def dgemm_peak(torch, n=8192, reps=3):
     """cuBLAS fp64 GEMM rate on this box: the DMMA roofline denominator (not in MEASURED_PEAKS.json)."""
     a = torch.randn(n, n, dtype=torch.float64, device="cuda")
@@ -462,6 +497,10 @@ def run_ours(args, rank, world, local_rank):
             extra["fit_predict"] = fits
         except Exception as e:       # the headline line must still print
             extra["fit_predict_error"] = repr(e)
+        try:
+            extra["episode"] = episode_bench(torch, engine)
+        except Exception as e:
+            extra["episode_error"] = repr(e)
         if world == 1 and not args.no_cpu:
             ctx = cpu_reference_setup()
             cpu_score_sample(ctx, 0, 1)
