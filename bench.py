@@ -521,7 +521,12 @@ def run_ours(args, rank, world, local_rank):
                     "api": "algp_b200.Agent.best_path(ndarray[65536,8], []) with host arrays", "steps": e2e_steps},
             "gpu_launches": 3 * args.steps,
             "roofline": {"bound": "hbm", "kernel": "score_sets_k8_kernel", "achieved": achieved, "peak": peak_hbm,
-                         "unit": "GB/s", "frac": achieved / peak_hbm, "traffic": None, "peak_source": peak_src,
+                         "unit": "GB/s", "frac": achieved / peak_hbm,
+                         # dram__bytes_read.sum + dram__bytes_write.sum per launch, ncu --set full
+                         # (profiles/r01_prof_score_summary.csv): 7.71 GB + 5 MB
+                         "traffic": 7.716e9, "peak_source": peak_src,
+                         "note": "above 1.0 of the DRAM peak because 40% of the sector reads hit the 126 MB L2; "
+                                 "the binding roof is L2->SM throughput (~10.3 TB/s achieved)",
                          "kernel_ms": kernel_ms, "algorithmic_bytes_per_launch": algo_bytes},
             "setup_ms_factor_and_W": setup_ms, "winner": win, "H_base": H_base,
         }

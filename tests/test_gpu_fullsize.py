@@ -1,0 +1,106 @@
+"""BASELINE.json full sizes: oracle spot checks where the CPU finishes in seconds, and
+size-independent properties elsewhere.  B200 only."""
+import numpy as np
+import pytest
+import torch
+
+import oracle as O
+import bench
+from algp_b200 import engine
+from gpu_helpers import dev
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def config_b():
+    grid, y, base, idx, delta, hy = bench.workload()
+    hyper = engine.Hyper(np.log(hy["ls"]), np.log(hy["os"]), np.log(hy["noise"]), hy["kind"])
+    pi0 = np.zeros(len(grid))
+    pi0[base] = 1.0 / bench.STATIC_STD ** 2
+    state = engine.PosteriorState(hyper, dev(grid), base, pi0, is_static=pi0 > 0)
+    return grid, base, idx, delta, hy, pi0, state
+
+
+def test_config_b_scores_match_oracle_on_a_sample(config_b):
+    """65536 sets of 8 vs the N=4096 factor (configs[2]): every score computed on the GPU, a random
+    sample of 300 checked against the oracle (literal slogdet for 3 of them, restructured for all)."""
+    grid, base, idx, delta, hy, pi0, state = config_b
+    scores = state.score_sets(dev(idx, torch.int32), dev(delta)).cpu().numpy()
+    assert scores.shape == (65536,) and np.isfinite(scores).all()
+    th = O.Theta.from_values(hy["ls"], hy["os"], hy["noise"], hy["kind"])
+    gp = O.OracleGP(th, "fp64")
+    # oracle posterior restricted to the locations the sample touches (keeps the CPU side small)
+    rng = np.random.default_rng(0)
+    sample = rng.choice(len(idx), 300, replace=False)
+    locs = np.unique(np.concatenate([base, idx[sample].reshape(-1)]))
+    remap = -np.ones(len(grid), dtype=np.int64)
+    remap[locs] = np.arange(len(locs))
+    cov = gp.cov_mat(grid[locs], add_likelihood_var=True)
+    ost = O.posterior_state(cov, pi0[locs])
+    want = O.score_sets_restructured(ost["P"], pi0[locs], remap[idx[sample]], delta[sample], ost["H"])
+    np.testing.assert_allclose(scores[sample], want, rtol=1e-8, atol=1e-8)
+    assert state.H_base == pytest.approx(ost["H"], rel=1e-10)
+    for c in sample[:3]:                               # the reference's own formulation for a few
+        st = (pi0[locs] > 0)
+        st[remap[idx[c, 0]]] = True
+        mo = np.zeros(len(locs), bool)
+        mo[remap[idx[c, 1:]]] = True
+        assert scores[c] == pytest.approx(O.set_entropy_literal(cov, st, mo, bench.STATIC_STD, bench.MOBILE_STD), rel=1e-8)
+
+
+def test_config_b_score_properties(config_b):
+    grid, base, idx, delta, hy, pi0, state = config_b
+    idx_d, delta_d = dev(idx, torch.int32), dev(delta)
+    s0 = state.score_sets(idx_d, delta_d).cpu().numpy()
+    # slot order does not matter (a set is a set)
+    perm = np.random.default_rng(1).permutation(8)
+    s1 = state.score_sets(dev(idx[:, perm], torch.int32), dev(delta[:, perm])).cpu().numpy()
+    np.testing.assert_allclose(s1, s0, rtol=1e-11, atol=1e-10)
+    # the generic (k > 8) kernel agrees with the k <= 8 kernel: pad every set to 9 slots with an empty one
+    idx9 = np.concatenate([idx[:2048], -np.ones((2048, 1), np.int32)], 1)
+    del9 = np.concatenate([delta[:2048], np.zeros((2048, 1))], 1)
+    s9 = state.score_sets(dev(idx9, torch.int32), dev(del9)).cpu().numpy()
+    np.testing.assert_allclose(s9, s0[:2048], rtol=1e-11, atol=1e-10)
+    # a duplicated slot is idempotent; adding information never lowers the entropy of the set
+    dup = idx.copy()
+    dup[:, 7] = dup[:, 0]
+    sd = state.score_sets(dev(dup, torch.int32), delta_d).cpu().numpy()
+    m7 = idx.copy()
+    m7[:, 7] = -1
+    s7 = state.score_sets(dev(m7, torch.int32), delta_d).cpu().numpy()
+    np.testing.assert_allclose(sd, s7, rtol=1e-12, atol=1e-10)
+    # argmax with first-max semantics
+    pair = state.argmax(dev(s0)).cpu()
+    assert int(pair[1]) == int(np.argmax(s0))
+
+
+def test_fit_n16384_properties():
+    """configs[3]: N=16384 fit (fp64) + variance over 8192 grid points in fp64 and TF32 mode."""
+    rng = np.random.default_rng(1)
+    N, side = 16384, 256
+    x = rng.uniform(0, side, size=(N, 2))
+    y = np.sin(x[:, 0] / 9.0) + rng.normal(0, 0.1, N)
+    xs = rng.uniform(0, side, size=(8192, 2))
+    hy = engine.Hyper(np.log([side / 16.0] * 2), 0.0, np.log(1e-2), "rbf")
+    f = engine.GPFactor(hy, dev(x), diag_add=dev(np.full(N, 0.01)))
+    f.check()
+    # L Linv = I on a block row, L L^T = A on sampled entries
+    rows = slice(9000, 9128)
+    Lr = torch.tril(f.L)[rows]                       # [128, N]
+    I_blk = Lr @ f.Linv[:, rows]                     # rows of L times columns of Linv
+    assert torch.allclose(I_blk, torch.eye(128, dtype=torch.float64, device=I_blk.device), atol=1e-8)
+    th = O.Theta(hy.log_ls, hy.log_os, hy.log_noise, "rbf")
+    sub = rng.choice(N, 64, replace=False)
+    A_sub = O.OracleGP(th, "fp64").cov_mat(x[sub]) + np.diag(np.full(64, 0.02))
+    Ls = torch.tril(f.L)[sub].cpu().numpy()
+    np.testing.assert_allclose(Ls @ Ls.T, A_sub, rtol=0, atol=1e-10)
+    # variance: bounds, and the tcgen05 TF32 mode agrees with fp64 at its tier
+    mu, v64 = f.mean_var(dev(xs), dev(y - y.mean()), float(y.mean()))
+    _, v32 = f.mean_var(dev(xs), dev(y - y.mean()), float(y.mean()), precision="tf32")
+    v64, v32 = v64.cpu().numpy(), v32.cpu().numpy()
+    assert (v64 > 0).all() and (v64 <= 1.0 + 1e-12).all()
+    np.testing.assert_allclose(v32, v64, rtol=0, atol=3e-4)         # 2e-4 s^2 at N=16384
+    # the mean interpolates the data to within a few noise standard deviations at training points
+    mu_tr, _ = f.mean_var(dev(x[:2048]), dev(y - y.mean()), float(y.mean()), want_var=False)
+    assert np.abs(mu_tr.cpu().numpy() - y[:2048]).max() < 1.0
