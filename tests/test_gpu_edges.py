@@ -1,0 +1,118 @@
+"""Edge cases through the reference-facing API: tiny / ragged sizes, 1-D inputs, empty and degenerate
+candidate sets (the reference tests none of these; its NumPy code defines the expected behaviour)."""
+import numpy as np
+import pytest
+import torch
+
+import oracle as O
+import algp_b200
+from algp_b200 import engine
+from gpu_helpers import dev, hyper_pair
+from test_gpu_api import make_gpr
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("N,M", [(1, 1), (2, 5), (127, 1), (129, 3)])
+def test_tiny_and_ragged_sizes(N, M):
+    rng = np.random.default_rng(N * 10 + M)
+    x, xs = rng.uniform(0, 5, (N, 2)), rng.uniform(0, 5, (M, 2))
+    y = rng.normal(size=N)
+    var = np.full(N, 0.05)
+    th, hy = hyper_pair([1.5, 2.0], 0.7, 0.1, "matern")
+    gp = make_gpr("matern", th.log_lengthscale, th.log_outputscale, th.log_noise, x, y, var)
+    mu, v = algp_b200.predictive_distribution(gp, x, y, xs, var, return_var=True)
+    mu_o, v_o = O.predictive_distribution_chol(O.OracleGP(th, "fp64"), x, y, xs, var, return_var=True)
+    np.testing.assert_allclose(mu, mu_o, rtol=1e-10, atol=1e-11)
+    np.testing.assert_allclose(v, v_o, rtol=0, atol=1e-10)
+    _, cov, mi = algp_b200.predictive_distribution(gp, x, y, xs, var, test_var=np.full(M, 0.01), return_cov=True, return_mi=True)
+    _, cov_o, mi_o = O.predictive_distribution_chol(O.OracleGP(th, "fp64"), x, y, xs, var, test_var=np.full(M, 0.01),
+                                                     return_cov=True, return_mi=True)
+    np.testing.assert_allclose(cov, cov_o, rtol=0, atol=1e-10)
+    assert mi == pytest.approx(mi_o, rel=1e-8, abs=1e-10)
+
+
+def test_one_dimensional_inputs_and_no_train_var():
+    rng = np.random.default_rng(0)
+    x = np.sort(rng.uniform(0, 10, 50))                 # 1-D array, like a 1-D field
+    y = np.sin(x)
+    xs = np.linspace(0, 10, 17)
+    th, hy = hyper_pair([1.2], 1.0, 0.01, "rbf")
+    gp = make_gpr("rbf", th.log_lengthscale, th.log_outputscale, th.log_noise, x, y, np.full(50, 1e-5))
+    mu, v = algp_b200.predictive_distribution(gp, x, y, xs, None, return_var=True)          # train_var=None (utils.py:293)
+    mu_o, v_o = O.predictive_distribution_chol(O.OracleGP(th, "fp64"), x, y, xs, None, return_var=True)
+    np.testing.assert_allclose(mu, mu_o, rtol=1e-9, atol=1e-9)
+    np.testing.assert_allclose(v, v_o, rtol=0, atol=1e-9)
+    K = gp.cov_mat(x, xs)
+    assert K.shape == (50, 17)
+    np.testing.assert_allclose(K, O.kernel_matrix(th, x, xs), rtol=1e-12, atol=1e-14)
+    assert gp.get_embeddings(x).shape == (50, 1)
+
+
+def test_degenerate_candidate_sets():
+    rng = np.random.default_rng(2)
+    X = rng.uniform(0, 10, (150, 2))
+    th, hy = hyper_pair([2.0, 2.0], 1.0, 0.05, "rbf")
+    pi0 = np.zeros(150)
+    pi0[:40] = 100.0
+    pi0[30:60] += 1.0
+    state = engine.PosteriorState(hy, dev(X), np.nonzero(pi0 > 0)[0], pi0)
+    cov = O.OracleGP(th, "fp64").cov_mat(X, add_likelihood_var=True)
+    ost = O.posterior_state(cov, pi0)
+    # all slots empty -> H(B); zero increments -> H(B); one candidate only
+    idx = np.array([[-1, -1, -1], [5, 70, 71], [70, 70, 70]], dtype=np.int32)
+    delta = np.array([[1.0, 1.0, 1.0], [0.0, 0.0, 0.0], [1.0, 1.0, 1.0]])
+    got = state.score_sets(dev(idx, torch.int32), dev(delta)).cpu().numpy()
+    want = O.score_sets_restructured(ost["P"], pi0, idx, delta, ost["H"])
+    np.testing.assert_allclose(got, want, rtol=1e-9, atol=1e-10)
+    assert got[0] == pytest.approx(ost["H"]) and got[1] == pytest.approx(ost["H"])
+    one = state.score_sets(dev(idx[2:3], torch.int32), dev(delta[2:3])).cpu().numpy()
+    assert one[0] == pytest.approx(want[2], rel=1e-10)
+    # 20-slot candidates (generic kernel) that are mostly empty
+    idx20 = -np.ones((5, 20), dtype=np.int32)
+    idx20[:, 3] = [61, 62, 63, 64, 65]
+    idx20[:, 17] = [100, 101, 102, 103, 104]
+    d20 = np.ones((5, 20))
+    got20 = state.score_sets(dev(idx20, torch.int32), dev(d20)).cpu().numpy()
+    np.testing.assert_allclose(got20, O.score_sets_restructured(ost["P"], pi0, idx20, d20, ost["H"]), rtol=1e-9, atol=1e-10)
+
+
+class _Env(object):
+    def __init__(self, X):
+        self.X, self.test_X, self.num_samples = X, X[:3], len(X)
+
+
+def _agent(X, static_idx, mobile_idx, kind="rbf"):
+    ag = algp_b200.Agent.__new__(algp_b200.Agent)
+    ag.env = _Env(X)
+    ag.static_std, ag.mobile_std, ag.criterion = 0.1, 1.0, 'entropy'
+    ag.static_data = [[1.0] if i in static_idx else [] for i in range(len(X))]
+    ag.mobile_data = [[1.0, 2.0] if i in mobile_idx else [] for i in range(len(X))]
+    ind, y, var = ag.get_sampled_dataset()
+    th, hy = hyper_pair([2.0, 2.0], 1.0, 0.05, kind)
+    ag.gp = make_gpr(kind, th.log_lengthscale, th.log_outputscale, th.log_noise,
+                     X[ind] if len(ind) else X[:1], y if len(ind) else np.zeros(1), var if len(ind) else np.ones(1))
+    ag._post_update()
+    return ag, th
+
+
+def test_agent_edge_semantics():
+    rng = np.random.default_rng(5)
+    X = rng.uniform(0, 8, (40, 2))
+    # nothing sampled yet: greedy from an empty base set (agent.py:308 would slogdet a 0x0 matrix: entropy 0)
+    ag, th = _agent(X, set(), set())
+    cov = O.OracleGP(th, "fp64").cov_mat(X, add_likelihood_var=True)
+    picks = ag.greedy(3)
+    assert picks == O.greedy_restructured(cov, np.zeros(40, bool), np.zeros(40, bool), 0.1, 1.0, 3)
+    # everything already static: np.argmax of all -inf is 0 (agent.py:349)
+    ag2, _ = _agent(X, set(range(40)), set())
+    assert ag2.greedy(2) == [0, 0]
+    # paths that add nothing new tie at H(B): first path wins (agent.py:402)
+    ag3, _ = _agent(X, {1, 2, 3}, {4, 5, 6})
+    assert ag3.best_path([[4, 5], [5, 6], [4]], [7]) == 0
+    assert ag3.best_path([[4, 5]], [7]) == 0                                   # single path: agent.py:362-363
+    # lists of different lengths, duplicates, overlap with the new static waypoint
+    paths = [[10, 11, 12, 10], [7, 20], [21, 22, 23, 24, 25, 26, 27, 28, 29]]
+    st = np.zeros(40, bool); st[[1, 2, 3]] = True
+    mo = np.zeros(40, bool); mo[[4, 5, 6]] = True
+    assert ag3.best_path(paths, [7]) == O.best_path_literal(cov, st, mo, 0.1, 1.0, paths, [7])
