@@ -9,9 +9,8 @@ and ``best_path`` (agent.py:358-403).
 (HotPath + the reference's sample bookkeeping) for use without the reference.
 
 The episode loops (run_ipp, run_greedy_ipp, run_naive, ...) are callers and
-stay in the reference.  The mutual-information criterion (agent.py:330-339)
-is off by default in the reference (run.py:218) and is not accelerated yet:
-it raises NotImplementedError.
+stay in the reference.  Both criteria are covered: 'entropy' (the reference's
+default, run.py:218) and 'mutual_information' (agent.py:330-339, 388-397).
 """
 from copy import deepcopy
 
@@ -134,20 +133,43 @@ class HotPath(object):
         self._hot_state = dict(hyper=hyper.key(), pi=pi.copy(), state=state)
         return state, pi
 
-    def _check_criterion(self):
-        if getattr(self, "criterion", "entropy") == 'mutual_information':
-            raise NotImplementedError("mutual_information scoring is not accelerated yet (SURVEY.md 8f #4)")
+    def _use_mi(self):
+        crit = getattr(self, "criterion", "entropy")
+        assert crit in ['entropy', 'mutual_information']                 # agent.py:128
+        return crit == 'mutual_information'
 
     def greedy(self, num_samples):
         """agent.py:295-356: greedily pick ``num_samples`` static locations by entropy gain."""
-        self._check_criterion()
         static_sampled, mobile_sampled = self._sample_flags()
         state, pi = self._state_for(static_sampled, mobile_sampled, capacity=num_samples + 16)
         d = 1.0 / self.static_std ** 2
-        picks = state.greedy(num_samples, d)
+        if self._use_mi():
+            picks = self._greedy_mi(state, pi.copy(), num_samples, d)
+        else:
+            picks = state.greedy(num_samples, d)
         # keep the cache key in step with the appended picks so best_path can reuse the state
         pi = self._hot_state["pi"]
         for j in picks:
+            pi[j] += d
+        return picks
+
+    def _greedy_mi(self, state, pi, num_samples, d):
+        """Mutual-information greedy (agent.py:330-339): the entropy term comes from the posterior state,
+        the two complement terms from an MIContext that is re-factored after every pick."""
+        picks = []
+        pair = torch.empty(2, dtype=torch.int64, device=state.X.device)
+        for _ in range(num_samples):
+            ctx = engine.MIContext(state.hyper, state.X, pi)
+            ent_a = state.H_base_dev + state.greedy_utilities(d)
+            ut = ctx.greedy_utilities(ent_a, self.static_std, self.mobile_std).contiguous()
+            state.argmax(ut, 0, out=pair)
+            state.append(pair[1:2], d, mark_static=True)
+            j = int(pair[1].item())
+            # H(B + j) = ent_a_j
+            state.H_base_dev.copy_(ent_a[j:j + 1])
+            state._H_base = None
+            ctx.check()
+            picks.append(j)
             pi[j] += d
         return picks
 
@@ -155,7 +177,6 @@ class HotPath(object):
         """agent.py:358-403: index of the path whose mobile samples maximise the joint entropy."""
         if len(paths_mobile_indices) == 1:
             return 0
-        self._check_criterion()
         static_sampled, org_mobile = self._sample_flags()
         static_sampled[static_indices] = True
         state, pi = self._state_for(static_sampled, org_mobile, capacity=0)
@@ -172,7 +193,14 @@ class HotPath(object):
         if getattr(state, "_skip_src", None) is None or not np.array_equal(state._skip_src, org_mobile):
             state._skip_src = org_mobile.copy()
             state._skip = engine.to_dev(org_mobile.astype(np.uint8), dtype=torch.uint8)
-        scores = state.score_sets(engine.to_dev(idx, dtype=torch.int32), None, delta_scalar=dm, skip=state._skip)
+        idx_d = engine.to_dev(idx, dtype=torch.int32)
+        scores = state.score_sets(idx_d, None, delta_scalar=dm, skip=state._skip)
+        if self._use_mi():
+            ctx = getattr(state, "_mi_ctx", None)
+            if ctx is None:
+                ctx = state._mi_ctx = engine.MIContext(state.hyper, state.X, pi, full_inverse=True)
+                ctx.check()
+            scores = ctx.path_utilities(scores, idx_d, state._skip, self.static_std, self.mobile_std).contiguous()
         pair = state.argmax(scores)
         self._last_path_scores = scores
         return int(pair[1].item())
@@ -181,7 +209,7 @@ class HotPath(object):
 def patch(agent_cls):
     """Install the accelerated hot path on the reference's Agent class (agent.py:12)."""
     for name in ("update_model", "get_sampled_dataset", "_post_update", "predict", "greedy", "best_path",
-                 "_device_X", "_state_for", "_check_criterion", "_sample_flags"):
+                 "_device_X", "_state_for", "_use_mi", "_greedy_mi", "_sample_flags"):
         setattr(agent_cls, name, HotPath.__dict__[name])
     agent_cls.cov_matrix = HotPath.__dict__["cov_matrix"]
     return agent_cls

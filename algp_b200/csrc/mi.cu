@@ -1,0 +1,166 @@
+// Mutual-information criterion (reference agent.py:330-339 greedy, 388-397 best_path):
+//     ut = H(Sigma_SS + D_S) + H(Sigma_AbarAbar) - H(Sigma + D),   Abar = unsampled locations,
+// i.e. I(y_S ; f_Abar).  The reference pays two more n x n slogdets PER CANDIDATE.  With
+// A2 = Sigma_AbarAbar and A3 = Sigma + D factored once per base set, a candidate that touches the
+// locations C only needs k x k blocks of the two inverses:
+//     logdet Sigma_{Abar\C}      = logdet A2 + logdet [A2^-1]_CC                       (C new in Abar)
+//     logdet(A3 + E_C Delta E_C^T) = logdet A3 + sum log|Delta| + logdet|Delta^-1 + [A3^-1]_CC|
+// (Delta = change of the per-location noise variance; it is negative where a static-only location
+// gains a mobile reading, which makes Delta^-1 + [A3^-1]_CC symmetric quasi-definite: a pivot-free
+// LDL^T exists and log|det| is the sum of log|pivot|.)
+#include "common.cuh"
+
+// out[c] = sum_{r>=c} M[r][c]^2 : diag(A^-1) from the inverse factor; chunked partials, fixed order
+#define MI_CHUNK 256
+__global__ void colsumsq_lower_kernel(const double* __restrict__ M, int64_t n, int64_t ld, double* __restrict__ partial) {
+  const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t r0 = (int64_t)blockIdx.y * MI_CHUNK;
+  if (c >= n) return;
+  int64_t rb = r0 > c ? r0 : c;
+  int64_t re = r0 + MI_CHUNK < n ? r0 + MI_CHUNK : n;
+  double s0 = 0.0, s1 = 0.0;
+  int64_t r = rb;
+  for (; r + 1 < re; r += 2) {
+    const double a = M[r * ld + c], b = M[(r + 1) * ld + c];
+    s0 = fma(a, a, s0);
+    s1 = fma(b, b, s1);
+  }
+  if (r < re) { const double a = M[r * ld + c]; s0 = fma(a, a, s0); }
+  partial[(int64_t)blockIdx.y * n + c] = s0 + s1;
+}
+__global__ void mi_colsum_kernel(const double* __restrict__ partial, int64_t n, int chunks, double* __restrict__ out) {
+  const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= n) return;
+  double s = 0.0;
+  for (int k = 0; k < chunks; ++k) s += partial[(int64_t)k * n + c];
+  out[c] = s;
+}
+
+extern "C" int64_t algp_colsumsq_work_doubles(int64_t n) { return ((n + MI_CHUNK - 1) / MI_CHUNK) * n; }
+
+extern "C" int algp_colsumsq_lower(const double* M, int64_t n, int64_t ld, double* out, double* work, void* stream) {
+  if (!M || !out || !work || n < 0 || ld < n) return ALGP_ERR_INVALID;
+  if (n == 0) return ALGP_OK;
+  const int chunks = (int)((n + MI_CHUNK - 1) / MI_CHUNK);
+  cudaStream_t st = (cudaStream_t)stream;
+  colsumsq_lower_kernel<<<dim3((unsigned)((n + 127) / 128), chunks), 128, 0, st>>>(M, n, ld, work);
+  ALGP_LAUNCH_CHECK();
+  mi_colsum_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(work, n, chunks, out);
+  ALGP_LAUNCH_CHECK();
+  return ALGP_OK;
+}
+
+struct MiArgs {
+  const double* inv2; int64_t ld2;      // A2^-1 (lower triangle valid), indexed by position in Abar
+  const int32_t* pos2;                  // [n]: position of a location in Abar, -1 if sampled
+  const double* inv3; int64_t ld3;      // A3^-1 (lower triangle valid), indexed by location
+  const int32_t* idx; int k; int64_t B; // [B x k] candidate locations (-1 = empty)
+  const uint8_t* skip;                  // [n] or null: already-mobile locations add nothing
+  double delta_new;                     // variance change of a brand-new location
+  double delta_old;                     // variance change of an already-sampled (static-only) location
+  double* out;                          // [B x 3]: logdet [A2^-1]_CC, number of new locations, sum log|Delta| + logdet|...|
+};
+
+// un-normalised elimination of the lower triangle of a kk x kk matrix in shared memory; returns sum log|pivot|
+__device__ double mi_logabsdet(double* M, int kk, int pitch, int tid) {
+  double acc = 0.0;
+  for (int c = 0; c < kk; ++c) {
+    const double piv = M[c * pitch + c];
+    const double inv = 1.0 / piv;
+    if (tid == 0) acc += log(fabs(piv));
+    const int rem = kk - 1 - c;
+    for (int e = tid; e < rem * rem; e += blockDim.x) {
+      const int r = c + 1 + e / rem, cc = c + 1 + e % rem;
+      if (cc <= r) M[r * pitch + cc] = fma(-M[r * pitch + c] * inv, M[cc * pitch + c], M[r * pitch + cc]);
+    }
+    __syncthreads();
+  }
+  return acc;   // valid in thread 0
+}
+
+__global__ void __launch_bounds__(256) mi_terms_kernel(const MiArgs a) {
+  extern __shared__ __align__(16) double mi_smem[];
+  const int k = a.k, pitch = k + 1;
+  double* M = mi_smem;                    // [k][k+1]
+  double* dl = M + k * pitch;             // [k] Delta of the slot (0 = inactive)
+  int* loc = (int*)(dl + k);              // [k] location, -1 inactive
+  int* p2 = loc + k;                      // [k] position in Abar, -1 if not new
+  const int tid = threadIdx.x;
+  for (int64_t cand = blockIdx.x; cand < a.B; cand += gridDim.x) {
+    __syncthreads();
+    for (int s = tid; s < k; s += blockDim.x) {
+      int ix = a.idx[cand * k + s];
+      bool act = ix >= 0 && !(a.skip && a.skip[ix]);
+      for (int q = 0; q < s && act; ++q)
+        if (a.idx[cand * k + q] == ix) act = false;          // duplicates are idempotent (agent.py:377)
+      loc[s] = act ? ix : -1;
+      const int pp = act ? a.pos2[ix] : -1;
+      p2[s] = pp;
+      dl[s] = act ? (pp >= 0 ? a.delta_new : a.delta_old) : 0.0;
+    }
+    __syncthreads();
+    // ---- term 2: logdet [A2^-1]_CC over the brand-new locations --------------------------------
+    for (int e = tid; e < k * k; e += blockDim.x) {
+      const int r = e / k, c = e % k;
+      if (c > r) continue;
+      double v = (r == c) ? 1.0 : 0.0;                        // inactive slots: identity
+      if (p2[r] >= 0 && p2[c] >= 0) {
+        const int hi = p2[r] > p2[c] ? p2[r] : p2[c], lo = p2[r] > p2[c] ? p2[c] : p2[r];
+        v = a.inv2[(int64_t)hi * a.ld2 + lo];
+      } else if (r != c) {
+        v = 0.0;
+      }
+      M[r * pitch + c] = v;
+    }
+    __syncthreads();
+    const double t2 = mi_logabsdet(M, k, pitch, tid);
+    // ---- term 3: sum log|Delta| + logdet|Delta^-1 + [A3^-1]_CC| -------------------------------
+    for (int e = tid; e < k * k; e += blockDim.x) {
+      const int r = e / k, c = e % k;
+      if (c > r) continue;
+      double v = (r == c) ? 1.0 : 0.0;
+      if (loc[r] >= 0 && loc[c] >= 0) {
+        const int hi = loc[r] > loc[c] ? loc[r] : loc[c], lo = loc[r] > loc[c] ? loc[c] : loc[r];
+        v = a.inv3[(int64_t)hi * a.ld3 + lo] + ((r == c) ? 1.0 / dl[r] : 0.0);
+      } else if (r != c) {
+        v = 0.0;
+      }
+      M[r * pitch + c] = v;
+    }
+    __syncthreads();
+    const double t3 = mi_logabsdet(M, k, pitch, tid);
+    if (tid == 0) {
+      double nnew = 0.0, sl = 0.0;
+      for (int s = 0; s < k; ++s) {
+        if (p2[s] >= 0) nnew += 1.0;
+        if (loc[s] >= 0) sl += log(fabs(dl[s]));
+      }
+      a.out[cand * 3 + 0] = t2;
+      a.out[cand * 3 + 1] = nnew;
+      a.out[cand * 3 + 2] = sl + t3;
+    }
+  }
+}
+
+extern "C" int algp_mi_terms(const double* inv2, int64_t ld2, const int32_t* pos2, const double* inv3, int64_t ld3,
+                             const int32_t* idx, int k, int64_t B, const uint8_t* skip, double delta_new, double delta_old,
+                             double* out3, void* stream) {
+  if (!inv3 || !pos2 || !idx || !out3 || k < 1 || k > 128 || B < 0 || delta_new == 0.0 || delta_old == 0.0) return ALGP_ERR_INVALID;
+  if (B == 0) return ALGP_OK;
+  MiArgs a;
+  a.inv2 = inv2; a.ld2 = ld2; a.pos2 = pos2; a.inv3 = inv3; a.ld3 = ld3; a.idx = idx; a.k = k; a.B = B; a.skip = skip;
+  a.delta_new = delta_new; a.delta_old = delta_old; a.out = out3;
+  size_t smem = ((size_t)k * (k + 1) + k) * 8 + (size_t)2 * k * 4 + 16;
+  static size_t configured = 0;
+  if (smem > configured) {
+    ALGP_CUDA(cudaFuncSetAttribute(mi_terms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = smem;
+  }
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  int grid = (int)(B < (int64_t)sms * 2 ? B : (int64_t)sms * 2);
+  mi_terms_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(a);
+  ALGP_LAUNCH_CHECK();
+  return ALGP_OK;
+}

@@ -346,3 +346,81 @@ class PosteriorState(object):
         if return_utilities:
             return picks, torch.stack(uts).cpu().numpy()
         return picks
+
+
+class MIContext(object):
+    """The two extra factorizations the mutual-information criterion needs for one sampled set
+    (reference agent.py:330-339): A2 = Sigma_AbarAbar (unsampled locations) and A3 = Sigma + D
+    (D = per-location noise variance on the sampled locations, 0 elsewhere)."""
+
+    def __init__(self, hyper, X, pi, full_inverse=False):
+        dev = X.device
+        self.n = X.shape[0]
+        pi = np.asarray(pi, dtype=np.float64)
+        sampled = pi > 0
+        abar = np.nonzero(~sampled)[0]
+        self.n_abar = len(abar)
+        pos2 = -np.ones(self.n, dtype=np.int32)
+        pos2[abar] = np.arange(self.n_abar, dtype=np.int32)
+        self.pos2 = to_dev(pos2, dtype=torch.int32, device=dev)
+        self.inv2 = self.inv3 = None
+        if self.n_abar:
+            xa = X.index_select(0, to_dev(abar, dtype=torch.int64, device=dev)).contiguous()
+            self.f2 = GPFactor(hyper, xa, diag_add=None, diag_scalar=hyper.noise)        # cov_matrix[~S][:, ~S]
+            self.ld2 = self.f2.logdet_quad()[0:1]
+            self.diag2 = self._inv_diag(self.f2)[:self.n_abar]
+            if full_inverse:
+                self.inv2 = self._inverse(self.f2)
+        else:
+            self.f2 = None
+            self.ld2 = torch.zeros(1, dtype=torch.float64, device=dev)
+            self.diag2 = torch.ones(1, dtype=torch.float64, device=dev)
+        var_all = np.where(sampled, 1.0 / np.where(sampled, pi, 1.0), 0.0)               # agent.py:334-337
+        self.f3 = GPFactor(hyper, X, diag_add=to_dev(var_all, device=dev), diag_scalar=hyper.noise)
+        self.ld3 = self.f3.logdet_quad()[0:1]
+        self.diag3 = self._inv_diag(self.f3)[:self.n]
+        if full_inverse:
+            self.inv3 = self._inverse(self.f3)
+
+    @staticmethod
+    def _inv_diag(f):
+        out = torch.empty(f.Npad, dtype=torch.float64, device=f.L.device)
+        work = torch.empty(_lib.lib.algp_colsumsq_work_doubles(f.Npad), dtype=torch.float64, device=f.L.device)
+        call("algp_colsumsq_lower", ptr(f.Linv), f.Npad, f.Npad, ptr(out), ptr(work), stream())
+        return out
+
+    @staticmethod
+    def _inverse(f):
+        inv = torch.empty((f.Npad, f.Npad), dtype=torch.float64, device=f.L.device)
+        call("algp_potri_lower", ptr(f.Linv), f.Npad, f.Npad, ptr(inv), f.Npad, stream())
+        return inv
+
+    def check(self):
+        if self.f2 is not None:
+            self.f2.check()
+        self.f3.check()
+
+    def greedy_utilities(self, ent_a, static_std, mobile_std):
+        """ut_i = ent_a_i + H(Sigma_{Abar \\ i}) - H(Sigma + D + Delta_i e_i e_i^T) for every location
+        (agent.py:330-339); ent_a is -inf where the location is already static."""
+        ss2, ms2 = static_std ** 2, mobile_std ** 2
+        vboth = 1.0 / (1.0 / ss2 + 1.0 / ms2)
+        is_new = self.pos2 >= 0
+        d2 = self.diag2[self.pos2.clamp_min(0).long()]
+        ent_abar = torch.where(is_new, (self.n_abar - 1) * CONST + 0.5 * (self.ld2 + torch.log(d2)),
+                               self.n_abar * CONST + 0.5 * self.ld2)
+        delta = torch.where(is_new, torch.full_like(d2, ss2), torch.full_like(d2, vboth - ms2))
+        ent_all = self.n * CONST + 0.5 * (self.ld3 + torch.log1p(delta * self.diag3))
+        return ent_a + ent_abar - ent_all
+
+    def path_utilities(self, ent_a, idx, skip, static_std, mobile_std):
+        """ut_p = ent_a_p + H(Sigma_{Abar \\ C_p}) - H(Sigma + D + E_C Delta E_C^T) (agent.py:388-397)."""
+        ss2, ms2 = static_std ** 2, mobile_std ** 2
+        vboth = 1.0 / (1.0 / ss2 + 1.0 / ms2)
+        B, k = idx.shape
+        out = torch.empty((B, 3), dtype=torch.float64, device=idx.device)
+        call("algp_mi_terms", ptr(self.inv2), self.inv2.stride(0) if self.inv2 is not None else 0, ptr(self.pos2),
+             ptr(self.inv3), self.inv3.stride(0), ptr(idx), k, B, ptr(skip), float(ms2), float(vboth - ss2), ptr(out), stream())
+        ent_abar = (self.n_abar - out[:, 1]) * CONST + 0.5 * (self.ld2 + out[:, 0])
+        ent_all = self.n * CONST + 0.5 * (self.ld3 + out[:, 2])
+        return ent_a + ent_abar - ent_all

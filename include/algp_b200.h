@@ -129,6 +129,18 @@ int algp_append(double* Wt, int64_t ldw, int64_t ncols, const double* X, int64_t
                 int mark_static, double* work, void* stream);
 int64_t algp_append_work_doubles(int64_t n);
 
+/* ---- mutual-information criterion (agent.py:330-339, 388-397) ---------------------- */
+/* out[c] = sum_{r>=c} M[r][c]^2 = diag(A^-1) from the inverse factor; work: algp_colsumsq_work_doubles(n) */
+int algp_colsumsq_lower(const double* M, int64_t n, int64_t ld, double* out, double* work, void* stream);
+int64_t algp_colsumsq_work_doubles(int64_t n);
+/* Per candidate c: out3[c] = {logdet [A2^-1]_CC over its brand-new locations, their count,
+ * sum log|Delta| + logdet|Delta^-1 + [A3^-1]_CC| over all its active locations}.  inv2 / inv3 are
+ * the inverses (lower triangle valid, algp_potri_lower) of Sigma_AbarAbar and Sigma + D; pos2[n] maps a
+ * location to its row in inv2 (-1 = sampled); skip[n] marks already-mobile locations (no-ops). */
+int algp_mi_terms(const double* inv2, int64_t ld2, const int32_t* pos2, const double* inv3, int64_t ld3,
+                  const int32_t* idx, int k, int64_t B, const uint8_t* skip, double delta_new, double delta_old,
+                  double* out3, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -165,12 +165,34 @@ def test_agent_matches_reference_golden(golden_dir, kind):
     assert best == int(g["best_path"])
 
 
-def test_agent_mutual_information_is_refused_not_faked(golden_dir):
-    g = load(golden_dir, "ref_agent_rbf_entropy.npz")
+def test_agent_mutual_information_matches_reference(golden_dir):
+    """criterion='mutual_information' (agent.py:330-339, 388-397) against the reference's own picks and,
+    utility by utility, against the literal loops."""
+    g = load(golden_dir, "ref_agent_rbf_mutual_information.npz")
     ag = agent_from_golden(g, "rbf")
     ag.criterion = 'mutual_information'
-    with pytest.raises(NotImplementedError):
-        ag.greedy(1)
+    th = O.Theta(g["log_ls"], float(g["log_os"]), float(g["log_noise"]), "rbf")
+    cov = O.OracleGP(th, "fp64").cov_mat(g["X"], add_likelihood_var=True)
+    ss, ms = ag.static_std, ag.mobile_std
+    assert ag.greedy(3) == [int(v) for v in g["greedy"]]
+    paths = unflatten(g["path_lens"], g["path_flat"])
+    static_idx = [int(v) for v in g["static_indices"]]
+    assert ag.best_path(paths, static_idx) == int(g["best_path"])
+    best, ut = O.best_path_literal(cov, g["static_sampled"], g["mobile_sampled"], ss, ms, paths, static_idx,
+                                   criterion="mutual_information", return_utilities=True)
+    np.testing.assert_allclose(ag._last_path_scores.cpu().numpy(), ut, rtol=1e-8, atol=1e-8)
+    # first-pick utilities against the literal loop
+    ag2 = agent_from_golden(g, "rbf")
+    ag2.criterion = 'mutual_information'
+    static, mobile = ag2._sample_flags()
+    state, pi = ag2._state_for(static, mobile, capacity=8)
+    ctx = engine.MIContext(state.hyper, state.X, pi)
+    ent_a = state.H_base_dev + state.greedy_utilities(1 / ss ** 2)
+    got = ctx.greedy_utilities(ent_a, ss, ms).cpu().numpy()
+    _, u_lit = O.greedy_literal(cov, static, mobile, ss, ms, 1, criterion="mutual_information", return_utilities=True)
+    fin = np.isfinite(u_lit[0])
+    assert (np.isfinite(got) == fin).all()
+    np.testing.assert_allclose(got[fin], u_lit[0][fin], rtol=1e-8, atol=1e-8)
 
 
 def test_state_dict_roundtrip_and_unknown_kernel():
