@@ -1,0 +1,7 @@
+#!/bin/bash
+mkdir -p gpurun_out
+( time timeout 1500 python -m pytest tests/ -x -q -m gpu -p no:cacheprovider ) > gpurun_out/pytest_all.log 2>&1; echo "pytest rc=$?"
+timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1; echo "smoke rc=$?"
+( time timeout 900 python bench.py ) > gpurun_out/bench_default.log 2> gpurun_out/bench_default.err; echo "bench rc=$?"
+( time timeout 900 python bench.py --impl reference --steps 5 --warmup 1 ) > gpurun_out/bench_ref.log 2> gpurun_out/bench_ref.err; echo "ref rc=$?"
+tail -4 gpurun_out/pytest_all.log; tail -1 gpurun_out/smoke.log; tail -4 gpurun_out/bench_default.err; tail -4 gpurun_out/bench_ref.err; cut -c1-400 gpurun_out/bench_ref.log
