@@ -98,6 +98,25 @@ class HotPath(object):
         return predictive_distribution(self.gp, train_x, train_y, x, train_var, return_var=return_var,
                                        return_cov=return_cov, return_mi=return_mi)
 
+    def prediction_vs_distance(self, test_every, num_runs):
+        """agent.py:497-518: posterior on growing prefixes of the collected readings.  The reference
+        re-solves the GP for each prefix; here one factorisation of the longest prefix serves them all."""
+        from .utils import predictive_distribution_prefixes
+        total = test_every * num_runs
+        inds = np.array(self.collected['ind'][:total])
+        valid = inds != -1
+        x = self.env.X[inds[valid]]
+        var = np.array(self.collected['std'])[:total][valid] ** 2
+        y = np.array(self.collected['y'])[:total][valid].astype(np.float64)
+        # prefix c of the raw list = the first cumsum(valid)[c-1] valid readings
+        nvalid = np.cumsum(valid)
+        counts = [int(nvalid[min(c, len(nvalid)) - 1]) for c in range(test_every, total + 1, test_every)]
+        res = predictive_distribution_prefixes(self.gp, x, y, self.env.test_X, var, counts, return_mi=True, return_cov=True)
+        all_error = [float(np.mean(np.abs(self.env.test_Y - mu))) for mu, _, _ in res]      # utils.compute_mae
+        all_mi = [mi for _, _, mi in res]
+        all_var = [float(np.diag(cov).mean()) for _, cov, _ in res]
+        return {'mean': res[-1][0], 'error': all_error, 'mi': all_mi, 'mean_var': all_var}
+
     # ---- scoring ----------------------------------------------------------------
     def _device_X(self):
         if getattr(self, "_hot_X", None) is None:
@@ -209,6 +228,7 @@ class HotPath(object):
 def patch(agent_cls):
     """Install the accelerated hot path on the reference's Agent class (agent.py:12)."""
     for name in ("update_model", "get_sampled_dataset", "_post_update", "predict", "greedy", "best_path",
+                 "prediction_vs_distance",
                  "_device_X", "_state_for", "_use_mi", "_greedy_mi", "_sample_flags"):
         setattr(agent_cls, name, HotPath.__dict__[name])
     agent_cls.cov_matrix = HotPath.__dict__["cov_matrix"]

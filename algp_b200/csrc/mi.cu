@@ -164,3 +164,51 @@ extern "C" int algp_mi_terms(const double* inv2, int64_t ld2, const int32_t* pos
   ALGP_LAUNCH_CHECK();
   return ALGP_OK;
 }
+
+
+// ---------------------------------------------------------------------------
+// Growing-prefix posteriors (reference agent.py:497-518 re-solves the GP for every prefix of the
+// collected samples).  The factor of a leading principal sub-matrix is the leading block of the full
+// factor, and so is its inverse, so with V = K(X*,X) Linv^T of the FULL ordered set
+//     var_p[m]  = k** - sum_{j<p} V[m][j]^2
+//     mean_p[m] = sum_{j<p} V[m][j] (beta[j] - ybar_p gamma[j]) + ybar_p,  beta = Linv y, gamma = Linv 1
+// for every prefix length p: one pass over V with running sums.  out[i][m] = {sum V beta, sum V gamma, sum V^2}
+// over j < prefix[i]; one warp per test row, prefixes ascending.
+// ---------------------------------------------------------------------------
+__global__ void prefix_reduce_kernel(const double* __restrict__ V, int64_t ldv, int64_t rows, const double* __restrict__ beta,
+                                     const double* __restrict__ gamma, const int32_t* __restrict__ prefix, int nprefix,
+                                     double* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const int64_t m = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (m >= rows) return;
+  const double* row = V + m * ldv;
+  double t1 = 0.0, t2 = 0.0, t3 = 0.0;
+  int lo = 0;
+  for (int i = 0; i < nprefix; ++i) {
+    const int hi = prefix[i];
+    double s1 = 0.0, s2 = 0.0, s3 = 0.0;
+    for (int j = lo + lane; j < hi; j += 32) {
+      const double v = row[j];
+      s1 = fma(v, beta[j], s1);
+      s2 = fma(v, gamma[j], s2);
+      s3 = fma(v, v, s3);
+    }
+    t1 += warp_sum(s1);
+    t2 += warp_sum(s2);
+    t3 += warp_sum(s3);
+    if (lane == 0) {
+      double* o = out + ((int64_t)i * rows + m) * 3;
+      o[0] = t1; o[1] = t2; o[2] = t3;
+    }
+    lo = hi;
+  }
+}
+
+extern "C" int algp_prefix_reduce(const double* V, int64_t ldv, int64_t rows, const double* beta, const double* gamma,
+                                  const int32_t* prefix_dev, int nprefix, double* out, void* stream) {
+  if (!V || !beta || !gamma || !prefix_dev || !out || rows < 0 || nprefix < 0) return ALGP_ERR_INVALID;
+  if (rows == 0 || nprefix == 0) return ALGP_OK;
+  prefix_reduce_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, (cudaStream_t)stream>>>(V, ldv, rows, beta, gamma, prefix_dev, nprefix, out);
+  ALGP_LAUNCH_CHECK();
+  return ALGP_OK;
+}

@@ -171,3 +171,76 @@ def predictive_distribution(gp, train_x, train_y, test_x, train_var=None, test_v
     if return_cov and return_mi:
         res = (mu, cov_h, mi)
     return res
+
+
+def predictive_distribution_prefixes(gp, train_x, train_y, test_x, train_var, counts, test_var=None,
+                                     return_var=False, return_cov=False, return_mi=False):
+    """[predictive_distribution(gp, train_x[:c], train_y[:c], test_x, train_var[:c], ...) for c in counts]
+    -- the loop of Agent.prediction_vs_distance (agent.py:497-518) -- from ONE factorisation: the Cholesky
+    factor (and its inverse) of a leading sub-matrix is the leading block of the full factor, so every prefix
+    posterior is a running sum over the columns of V = K(X*,X) Linv^T.  `counts` must be ascending."""
+    from . import engine, _lib
+    from ._lib import call, ptr, stream
+    counts = [int(c) for c in counts]
+    assert counts == sorted(counts) and counts[0] >= 1 and counts[-1] <= len(train_y)
+    hyper = gp.hyper()
+    nmax = counts[-1]
+    train_x = np.asarray(to_numpy(train_x), dtype=np.float64)[:nmax]
+    if train_x.ndim == 1:
+        train_x = train_x[:, None]
+    test_x = np.asarray(to_numpy(test_x), dtype=np.float64)
+    if test_x.ndim == 1:
+        test_x = test_x[:, None]
+    y = np.asarray(to_numpy(train_y), dtype=np.float64).reshape(-1)[:nmax]
+    tvar = None if train_var is None else np.asarray(train_var, dtype=np.float64)[:nmax]
+    f = _factor_for(gp, hyper, train_x, tvar)
+    dev = f.L.device
+    xs = engine.to_dev(test_x, device=dev)
+    M = xs.shape[0]
+    Ks, _ = f.cross(xs)
+    V, _ = f.whiten(Ks, want_V=True, want_norm=False)
+    yp = torch.zeros(f.Npad, dtype=torch.float64, device=dev)
+    yp[:nmax] = engine.to_dev(y, device=dev)
+    ones = torch.zeros(f.Npad, dtype=torch.float64, device=dev)
+    ones[:nmax] = 1.0
+    beta, gamma = torch.empty_like(yp), torch.empty_like(yp)
+    call("algp_gemv_lower", ptr(f.Linv), f.Npad, f.Npad, ptr(yp), ptr(beta), stream())
+    call("algp_gemv_lower", ptr(f.Linv), f.Npad, f.Npad, ptr(ones), ptr(gamma), stream())
+    pre = engine.to_dev(np.asarray(counts, dtype=np.int32), dtype=torch.int32, device=dev)
+    out = torch.empty((len(counts), M, 3), dtype=torch.float64, device=dev)
+    call("algp_prefix_reduce", ptr(V), V.stride(0), M, ptr(beta), ptr(gamma), ptr(pre), len(counts), ptr(out), stream())
+    sums = out.cpu().numpy()
+    f.check()
+    tv = np.zeros(M) if test_var is None else np.asarray(test_var, dtype=np.float64)
+    want_full = return_cov or return_mi
+    Kxx = None
+    if want_full:
+        Mpad = Ks.shape[0]
+        tvd = None if test_var is None else engine.to_dev(tv, device=dev)
+        Kxx, _ = engine.kbuild(hyper, xs, None, Mpad, Mpad, diag_add=tvd, diag_scalar=0.0, pad_identity=True)
+        ld_xx = engine.chol_logdet(Kxx.clone(), M) if return_mi else None
+    results = []
+    for i, c in enumerate(counts):
+        ybar = float(np.mean(y[:c]))                                    # utils.py:294 on the prefix
+        mu = sums[i, :, 0] - ybar * sums[i, :, 1] + ybar
+        if not (return_var or return_cov or return_mi):
+            results.append(mu)
+            continue
+        res = None
+        if return_var:
+            res = (mu, hyper.outputscale + tv - sums[i, :, 2])
+        if want_full:
+            Vp = V.clone()
+            Vp[:, c:] = 0.0
+            cov = Kxx.clone()
+            engine.gemm_nt(Vp, Vp, cov, -1.0, 1.0)                      # utils.py:305 on the prefix
+            cov_h = cov[:M, :M].cpu().numpy() if return_cov else None
+            if return_cov:
+                res = (mu, cov_h)
+            if return_mi:
+                mi = 0.5 * (ld_xx - engine.chol_logdet(cov, M))         # utils.py:314
+                res = (mu, mi)
+            if return_cov and return_mi:
+                res = (mu, cov_h, mi)
+        results.append(res)
+    return results

@@ -141,6 +141,13 @@ int algp_mi_terms(const double* inv2, int64_t ld2, const int32_t* pos2, const do
                   const int32_t* idx, int k, int64_t B, const uint8_t* skip, double delta_new, double delta_old,
                   double* out3, void* stream);
 
+/* ---- growing-prefix posteriors (agent.py:497-518) ------------------------------------- */
+/* out[i][m] = {sum_j V[m][j] beta[j], sum_j V[m][j] gamma[j], sum_j V[m][j]^2} over j < prefix[i]
+ * (prefix ascending, device int32): mean and variance of the GP fitted to the first prefix[i] training
+ * rows, for every i, from ONE factorisation of the full ordered set. */
+int algp_prefix_reduce(const double* V, int64_t ldv, int64_t rows, const double* beta, const double* gamma,
+                       const int32_t* prefix_dev, int nprefix, double* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

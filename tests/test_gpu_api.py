@@ -310,3 +310,70 @@ def test_episode_matches_literal_reference_loops(kind):
     ost = O.posterior_state(cov, pi_fin)
     np.testing.assert_allclose(res["state"].diagP.cpu().numpy(), np.diag(ost["P"]), rtol=0, atol=1e-9)
     np.testing.assert_allclose(res["state"].pi.cpu().numpy(), pi_fin, rtol=1e-12)
+
+
+# ------------------------------------------------------------------ growing prefixes (agent.py:497-518)
+@pytest.mark.parametrize("kind", ["rbf", "matern"])
+def test_prefix_posteriors_match_per_prefix_solves(kind):
+    from algp_b200.utils import predictive_distribution_prefixes
+    X, yf, tr, ytr, rng = field_problem(20, 18, 200, seed=6)
+    order = rng.integers(0, len(X), 230)                 # with repeats: a location read twice (static, then mobile)
+    x = X[order]
+    y = np.maximum(0, yf[order] + rng.normal(0, 0.1, len(order)))
+    var = np.where(rng.random(len(order)) < 0.6, 0.01, 1.0)
+    te = rng.choice(len(X), 37, replace=False)
+    tvar = np.full(37, 0.02)
+    th, hy = hyper_pair([2.5, 3.0], 1.1, 0.03, kind)
+    gp = make_gpr(kind, th.log_lengthscale, th.log_outputscale, th.log_noise, x, y, var)
+    ogp = O.OracleGP(th, "fp64")
+    counts = [10, 25, 26, 130, 230]
+    res = predictive_distribution_prefixes(gp, x, y, X[te], var, counts, test_var=tvar, return_cov=True, return_mi=True)
+    resv = predictive_distribution_prefixes(gp, x, y, X[te], var, counts, return_var=True)
+    resm = predictive_distribution_prefixes(gp, x, y, X[te], var, counts)
+    for i, c in enumerate(counts):
+        mu_o, cov_o, mi_o = O.predictive_distribution_chol(ogp, x[:c], y[:c], X[te], var[:c], test_var=tvar,
+                                                           return_cov=True, return_mi=True)
+        mu, cov, mi = res[i]
+        np.testing.assert_allclose(mu, mu_o, rtol=1e-9, atol=1e-9)
+        np.testing.assert_allclose(cov, cov_o, rtol=0, atol=1e-9 * 1.1)
+        assert mi == pytest.approx(mi_o, rel=1e-8)
+        _, var_o = O.predictive_distribution_chol(ogp, x[:c], y[:c], X[te], var[:c], return_var=True)
+        np.testing.assert_allclose(resv[i][1], var_o, rtol=0, atol=1e-9 * 1.1)
+        np.testing.assert_allclose(resv[i][0], mu_o, rtol=1e-9, atol=1e-9)
+        np.testing.assert_allclose(resm[i], mu_o, rtol=1e-9, atol=1e-9)
+
+
+def test_prediction_vs_distance_matches_literal_loop():
+    X, yf, tr, ytr, rng = field_problem(15, 14, 50, seed=8)
+    te = rng.choice(len(X), 20, replace=False)
+    ag = algp_b200.Agent.__new__(algp_b200.Agent)
+    ag.env = GoldenEnv(dict(X=X, test_X=X[te]))
+    ag.env.test_Y = yf[te]
+    ag.static_std, ag.mobile_std, ag.criterion = 0.1, 1.0, 'entropy'
+    n_read = 60
+    inds = list(rng.integers(0, len(X), n_read))
+    inds[7] = -1                                          # an invalid reading is skipped (agent.py:504-505)
+    stds = [0.1 if rng.random() < 0.5 else 1.0 for _ in range(n_read)]
+    ys = [None if i == -1 else float(max(0, yf[i] + rng.normal(0, s))) for i, s in zip(inds, stds)]
+    ag.collected = {'ind': inds, 'std': stds, 'y': ys}
+    th, hy = hyper_pair([2.0, 2.5], 1.0, 0.05, "rbf")
+    ag.gp = make_gpr("rbf", th.log_lengthscale, th.log_outputscale, th.log_noise, X[:2], yf[:2], np.full(2, 0.01))
+    got = ag.prediction_vs_distance(test_every=12, num_runs=5)
+    ogp = O.OracleGP(th, "fp64")
+    count = 0
+    err, mis, mv = [], [], []
+    while count < 60:                                     # the reference loop, agent.py:503-516
+        count += 12
+        ii = np.array(inds[:count])
+        valid = ii != -1
+        x = X[ii[valid]]
+        var = np.array(stds)[:count][valid] ** 2
+        y = np.array([v for v in ys[:count] if v is not None])
+        mu, cov, mi = O.predictive_distribution_chol(ogp, x, y, X[te], var, return_mi=True, return_cov=True)
+        err.append(np.mean(np.abs(yf[te] - mu)))
+        mis.append(mi)
+        mv.append(np.diag(cov).mean())
+    np.testing.assert_allclose(got['error'], err, rtol=1e-8)
+    np.testing.assert_allclose(got['mi'], mis, rtol=1e-8)
+    np.testing.assert_allclose(got['mean_var'], mv, rtol=1e-8, atol=1e-10)
+    np.testing.assert_allclose(got['mean'], mu, rtol=1e-9, atol=1e-9)
