@@ -264,11 +264,35 @@ def fit_predict_bench(torch, engine, n_train, grid_side, reps, peak_hbm):
             times[k].append(marks[i].elapsed_time(marks[i + 1]))
         times["total"].append(marks[0].elapsed_time(marks[6]))
         tf32_err = float((v32 - v).abs().max().item())
+    # end to end through the reference-facing call with HOST arrays (utils.py:293): H2D of x / y / var / grid,
+    # kernel build + factor + solve + variance, D2H of mean and variance, fresh factor every call
+    import algp_b200
+    e2e = {}
+    gp = algp_b200.GPR(kernel_params={'type': 'rbf'})
+    var_h = np.full(n_train, STATIC_STD ** 2)
+    gp.reset(x, y, var_h)
+    with torch.no_grad():
+        gp.model.kernel_covar_module.base_kernel.log_lengthscale.copy_(torch.tensor(hy.log_ls).view(1, 1, -1))
+        gp.model.kernel_covar_module.log_outputscale.fill_(hy.log_os)
+        gp.likelihood.log_noise.fill_(hy.log_noise)
+    for mode in ("fp64", "tf32"):
+        gp.precision = mode
+        ts = []
+        for rep in range(reps + 1):
+            gp._cache.clear()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            mu_h, var_out = algp_b200.predictive_distribution(gp, x, y, xs, var_h, return_var=True)
+            ts.append((time.perf_counter() - t0) * 1e3)
+        e2e[mode] = float(np.median(ts[1:]))
+    e2e["h2d_bytes"] = int(x.nbytes + y.nbytes + var_h.nbytes + xs.nbytes)
+    e2e["d2h_bytes"] = int(mu_h.nbytes + var_out.nbytes)
     med = {k: float(np.median(v)) for k, v in times.items()}
     N = float(max(128, engine.pad_to(n_train)))
     Mp = float(max(128, engine.pad_to(M)))
     out = {"n_train": n_train, "n_test": M, "ms": med["total"],
            "ms_tf32_mode": med["total"] - med["variance_trmm"] + med["variance_tf32"],
+           "e2e_ms_host_arrays": e2e,
            "tf32_max_abs_var_diff_vs_fp64": tf32_err, "ms_by_stage": med,
            "var_min": float(v.min().item()), "var_max": float(v.max().item()),
            "rooflines": {
