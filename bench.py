@@ -530,6 +530,22 @@ def run_ours(args, rank, world, local_rank):
             cpu_score_sample(ctx, 0, 1)
             cnt = 12
             t = cpu_score_sample(ctx, 1, cnt)
+            # second metric on the CPU: the reference's predictive_distribution (float32 inv + two GEMMs,
+            # utils.py:296-308) at N=4096 / 64x64 grid, once
+            try:
+                import oracle as O
+                rng = np.random.default_rng(1)
+                xc = rng.uniform(0, 64, size=(4096, 2))
+                yyc, xxc = np.meshgrid(np.arange(64), np.arange(64), indexing="ij")
+                xsc = np.stack([yyc.ravel(), xxc.ravel()], 1).astype(np.float64)
+                yc = np.sin(xc[:, 0] / 9.0) + np.cos(xc[:, 1] / 7.0) + rng.normal(0, 0.1, 4096)
+                thc = O.Theta.from_values([4.0, 4.0], 1.0, 1e-2, "rbf")
+                t0 = time.perf_counter()
+                O.predictive_distribution(O.OracleGP(thc, "ref32"), xc, yc, xsc, np.full(4096, STATIC_STD ** 2), return_var=True)
+                extra["cpu_fit_predict_n4096"] = {"ms": (time.perf_counter() - t0) * 1e3, "cores": os.cpu_count(), "kind": "port",
+                                                  "what": "oracle ref32 predictive_distribution(return_var), N=4096, M=4096"}
+            except Exception as e:
+                extra["cpu_fit_predict_error"] = repr(e)
             cpu_base = {"value": cnt / t, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
                         "sample": "%d of the 65536 candidate sets, literal reference loop (fancy-index + "
                                   "np.linalg.slogdet of a 4104x4104 matrix per set, OpenBLAS threads)" % cnt}
