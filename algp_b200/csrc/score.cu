@@ -302,21 +302,10 @@ extern "C" int algp_score_sets(const double* Wt, int64_t ldw, int64_t ncols, con
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   if (k <= 8) {
-    // persistent grid, warps stride over the candidates.  ALGP_SCORE_VARIANT selects a tuning variant
-    // (bench / profiling only); the default is the fastest measured on B200.
-    static int variant = -1;
-    if (variant < 0) {
-      const char* e = getenv("ALGP_SCORE_VARIANT");
-      variant = e ? atoi(e) : 0;
-    }
-    switch (variant) {
-      case 1: score_k8_launch<4, false, 128>(a, sms, 8, st); break;
-      case 2: score_k8_launch<2, true, 128>(a, sms, 8, st); break;
-      case 3: score_k8_launch<4, true, 128>(a, sms, 6, st); break;
-      case 4: score_k8_launch<2, false, 128>(a, sms, 12, st); break;
-      case 5: score_k8_launch<1, true, 256>(a, sms, 8, st); break;
-      default: score_k8_launch<2, false, 256>(a, sms, 8, st); break;
-    }
+    // persistent grid of 8 CTAs x 8 warps per SM, warps stride over the candidates.  Two 128-byte lines per
+    // row in flight and no register prefetch was the fastest of the variants tried on B200
+    // (profiles/r01_score_variants.log): the kernel is bound by L2->SM throughput, not by latency.
+    score_k8_launch<2, false, 256>(a, sms, 8, st);
   } else {
     const int kp = (k + 7) / 8, kk = kp * 8;
     size_t smem = ((size_t)kk * (kk + 1) + kk + (size_t)kk * d) * 8 + (size_t)kk * 4 + 16;

@@ -564,7 +564,8 @@ def run_ours(args, rank, world, local_rank):
                          "unit": "GB/s", "frac": achieved / peak_hbm,
                          # dram__bytes_read.sum + dram__bytes_write.sum per launch, ncu --set full
                          # (profiles/r01_prof_score_summary.csv): 7.71 GB + 5 MB
-                         "traffic": 7.716e9, "peak_source": peak_src,
+                         "traffic": 7.716e9, "achieved_dram_gbs": 7.716 / kernel_ms * 1e3, "frac_dram": 7.716 / kernel_ms * 1e3 / peak_hbm,
+                         "peak_source": peak_src,
                          "note": "above 1.0 of the DRAM peak because 40% of the sector reads hit the 126 MB L2; "
                                  "the binding roof is L2->SM throughput (~10.3 TB/s achieved)",
                          "kernel_ms": kernel_ms, "algorithmic_bytes_per_launch": algo_bytes},
