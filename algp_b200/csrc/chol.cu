@@ -40,10 +40,11 @@ static int gemm_launch_t(GemmArgs a, int batch, cudaStream_t st) {
 
 template <int ALAY, int BLAY>
 static int gemm_launch_l(const GemmArgs& a, int batch, cudaStream_t st) {
-  // Latency shapes when the 128-tile grid cannot fill the SMs.  Row-norm partials are per
-  // 128-column tile (keep 128x128); an in-place launch (NT == 1) may only shrink its row extent.
+  // Latency shapes when the 128-tile grid cannot fill the SMs.  Row-norm partials are per 64-column
+  // tile (both shapes used with them have TN = 64); an in-place launch (NT == 1) may only shrink its
+  // row extent.
   int64_t tiles = (a.tmap == TM_LOWER) ? (int64_t)a.MT * (a.MT + 1) / 2 : (int64_t)a.MT * a.NT;
-  const bool small = !a.rn_partial && tiles * batch < 120;
+  const bool small = tiles * batch < 120;
   const bool subc = a.alpha == -1.0 && a.beta == 1.0 && a.store_c && !a.rn_partial && !a.inplace_rows && a.C;
   // Default for large launches: 128x64 tiles, 3 stages, so that two CTAs share an SM and overlap each
   // other's pipeline fill and epilogue (measured 8% faster than 128x128x4 on the N=16384 factorisation;
@@ -53,7 +54,11 @@ static int gemm_launch_l(const GemmArgs& a, int batch, cudaStream_t st) {
     const char* e = getenv("ALGP_GEMM_SHAPE");
     shape = e ? atoi(e) : 1;
   }
-  if (shape == 1 && !small && !a.rn_partial) {
+  if (a.rn_partial) {                                   // partial columns are 64 wide: TN = 64 shapes only
+    if (small) return gemm_launch_t<ALAY, BLAY, 64, 64, false>(a, batch, st);
+    return gemm_launch_t<ALAY, BLAY, 128, 64, false, 3>(a, batch, st);
+  }
+  if (shape == 1 && !small) {
     if (subc) return gemm_launch_t<ALAY, BLAY, 128, 64, true, 3>(a, batch, st);
     return gemm_launch_t<ALAY, BLAY, 128, 64, false, 3>(a, batch, st);
   }
@@ -463,8 +468,8 @@ extern "C" int algp_logdet_sumsq(const double* L, int64_t n, int64_t ld, const d
 // C-ABI views of the GEMM core used outside this file
 // ---------------------------------------------------------------------------
 // V = Ks * Linv^T restricted to the lower-triangular structure of Linv
-// (C[m][j] = sum_{k < (jt+1)*128} Ks[m][k] Linv[j][k]); optional store of V and
-// optional fused row partials  rn_partial[m][jt] = sum_{j in tile} V[m][j]^2.
+// (C[m][j] = sum_{k <= j} Ks[m][k] Linv[j][k], k-range cut per column tile); optional store of V and
+// optional fused row partials  rn_partial[m][jt] = sum_{j in 64-column tile jt} V[m][j]^2.
 extern "C" int algp_trmm_rt(const double* Ks, int64_t mpad, int64_t ldk, const double* Linv, int64_t npad, int64_t ldi,
                             double* V, int64_t ldv, double* rn_partial, void* stream) {
   if (!Ks || !Linv || mpad % ALGP_BLK || npad % ALGP_BLK || ldk < npad || ldi < npad || (ldk & 1) || (ldi & 1)) return ALGP_ERR_INVALID;
@@ -476,7 +481,7 @@ extern "C" int algp_trmm_rt(const double* Ks, int64_t mpad, int64_t ldk, const d
   g.C = V; g.ldc = ldv; g.store_c = V ? 1 : 0;
   g.MT = (int)(mpad / ALGP_BLK); g.NT = (int)(npad / ALGP_BLK); g.K = (int)npad;
   g.kend_rule = KE_NT1;
-  g.rn_partial = rn_partial; g.rn_nt = g.NT;
+  g.rn_partial = rn_partial; g.rn_nt = 2 * g.NT;       // one partial per 64-column tile
   return gemm_f64_launch(g, LAY_KMAJ, LAY_KMAJ, 1, (cudaStream_t)stream);
 }
 

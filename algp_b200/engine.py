@@ -161,7 +161,7 @@ class GPFactor(object):
         V = None
         if want_V:
             V = V_out if V_out is not None else torch.empty((Mpad, self.Npad), dtype=torch.float64, device=dev)
-        rn = torch.empty((Mpad, self.Npad // BLK), dtype=torch.float64, device=dev) if want_norm else None
+        rn = torch.empty((Mpad, self.Npad // 64), dtype=torch.float64, device=dev) if want_norm else None
         call("algp_trmm_rt", ptr(Ks), Mpad, Ks.stride(0), ptr(self.Linv), self.Npad, self.Npad,
              ptr(V), V.stride(0) if V is not None else 0, ptr(rn), stream())
         return V, rn

@@ -67,8 +67,8 @@ int64_t algp_gemv_work_doubles(int64_t n);
 /* out2[0] = log det A = 2 sum log L_ii (replaces slogdet, utils.py:193); out2[1] = |v|^2 if v */
 int algp_logdet_sumsq(const double* L, int64_t n, int64_t ld, const double* v, double* out2, void* stream);
 /* V = Ks L^-T using the triangular structure of Linv (cov_xa inv(cov_aa) cov_xa^T of
- * utils.py:300-305 is V V^T).  V may be NULL; rn_partial[m][t] (t < npad/128), if not
- * NULL, receives the row sums of V^2 per column tile: var = k** - sum_t rn_partial. */
+ * utils.py:300-305 is V V^T).  V may be NULL; rn_partial[m][t] (t < npad/64), if not
+ * NULL, receives the row sums of V^2 per 64-column tile: var = k** - sum_t rn_partial. */
 int algp_trmm_rt(const double* Ks, int64_t mpad, int64_t ldk, const double* Linv, int64_t npad, int64_t ldi,
                  double* V, int64_t ldv, double* rn_partial, void* stream);
 /* C = beta C + alpha A B^T (A [mpad x kpad], B [npad x kpad]).  lower_only: the lower triangle
