@@ -226,7 +226,11 @@ static int potrf_aux_get(PotrfAux** out) {
   if (dev < 0 || dev >= 64) return ALGP_ERR_UNSUPPORTED;
   PotrfAux& a = g_potrf_aux[dev];
   if (!a.aux) {
-    ALGP_CUDA(cudaStreamCreateWithFlags(&a.aux, cudaStreamNonBlocking));
+    // highest priority: the diagonal-block kernel and the panel solve are the critical path and must win
+    // SM slots against the thousands of queued CTAs of the concurrent trailing update
+    int prio_lo = 0, prio_hi = 0;
+    ALGP_CUDA(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+    ALGP_CUDA(cudaStreamCreateWithPriority(&a.aux, cudaStreamNonBlocking, prio_hi));
     ALGP_CUDA(cudaEventCreateWithFlags(&a.col_ready, cudaEventDisableTiming));
     ALGP_CUDA(cudaEventCreateWithFlags(&a.panel_ready, cudaEventDisableTiming));
   }
