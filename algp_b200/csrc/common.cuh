@@ -48,6 +48,25 @@ __device__ __forceinline__ void cp_async_wait() {
   asm volatile("cp.async.wait_group %0;\n" ::"n"(N));
 }
 
+// ---- mbarrier (split-phase CTA barrier) ------------------------------------
+__device__ __forceinline__ uint32_t smem_addr_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbarrier_init(uint64_t* b, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr_u32(b)), "r"(count));
+}
+__device__ __forceinline__ void mbarrier_arrive(uint64_t* b) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_addr_u32(b)) : "memory");
+}
+__device__ __forceinline__ void mbarrier_wait(uint64_t* b, uint32_t parity) {
+  const uint32_t addr = smem_addr_u32(b);
+  uint32_t ok;
+  do {
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok)
+                 : "r"(addr), "r"(parity)
+                 : "memory");
+  } while (!ok);
+}
+
 // FP64 tensor-core MMA.  On sm_100a every f64 mma.sync shape lowers to
 // DMMA.8x8x4 (checked with cuobjdump), so m8n8k4 is the native unit.
 // Fragments: a = A[lane>>2][lane&3], b = B[k=lane&3][n=lane>>2],
