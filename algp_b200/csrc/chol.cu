@@ -82,158 +82,90 @@ int gemm_f64_launch(const GemmArgs& a, int alay, int blay, int batch, cudaStream
 // ---------------------------------------------------------------------------
 // potf2inv: factor one 128x128 diagonal block and invert the factor, one CTA.
 //
-// 512 threads in a 32x16 grid; thread (ty,tx) owns the cyclic patch rows ty+32i,
+// 256 threads in a 16x16 grid; thread (ty,tx) owns the cyclic patch rows ty+16i,
 // cols tx+16j in registers, so every thread stays busy as the active window
 // shrinks.  The factorisation is an un-normalised elimination (LDL^T style: no
-// sqrt on the column-to-column critical path, one split-phase mbarrier per column
-// through double-buffered broadcasts, with in-kernel look-ahead: what the next
-// column needs is updated and published first); L = Ltilde D^1/2 is formed at the end.
+// sqrt on the column-to-column critical path, one __syncthreads per column
+// through double-buffered broadcasts); L = Ltilde D^1/2 is formed at the end.
 // The same multipliers are applied, in the same loop, to the identity, which
 // yields Y = Ltilde^-1 and hence L^-1 = D^-1/2 Y.
 // ---------------------------------------------------------------------------
-#define P2_SMEM_BYTES ((2 * 128 + 2 * 128 + 2 * 128 + 2) * 8)
-#define P2_THREADS 512
+#define P2_SMEM_BYTES ((2 * 128 + 2 * 128 + 2 * 128) * 8)
 
-// Thread (ty, tx) of a 32 x 16 grid owns rows ty + 32 i (i < 4) and columns tx + 16 j (j < 8).  A patch
-// (i, j) can hold lower-triangular entries only if j <= 2 i + 1: 20 live doubles per thread for the Schur
-// complement and 20 for Y.  512 threads = 4 warps per scheduler: the per-column dependency stalls of one
-// warp are covered by the others (with 256 threads the kernel ran at ~6 cycles per issued instruction).
-#define P2_LIVE(i, j) ((j) <= 2 * (i) + 1)
-
-// What step c+1 needs from step c, done FIRST so that it can be published before the bulk of the update:
-// column c+1 of the Schur complement (threads tx == cc1), the reciprocal of its pivot, and row c+1 of Y
-// (threads ty == r1).  IC1 = (c+1)/16 and IR1 = (c+1)/32 are template parameters so that the register
-// patches stay statically indexed.  The multipliers consumed here are zeroed afterwards so that the bulk
-// loops do not apply them twice.
-template <int IC, int IC1>
-__device__ __forceinline__ void p2_early(double (&acc)[4][8], double (&yac)[4][8], const double (&ri)[4], double (&riy)[4],
-                                         double (&cj)[8], const double (&yj)[8], double* cb1, double* rb1, double* rcp1,
-                                         double* pivbuf, int c1, int ty, int tx, int j0, int* info) {
-  constexpr int IR1 = IC1 / 2;
-  const int cc1 = c1 & 15, r1 = c1 & 31;
-  if (tx == cc1) {
-#pragma unroll
-    for (int i = IR1; i < 4; ++i) {
-      acc[i][IC1] = fma(-ri[i], cj[IC1], acc[i][IC1]);
-      cb1[ty + 32 * i] = acc[i][IC1];
-    }
-    cj[IC1] = 0.0;
-    if (ty == r1) {                                   // the next pivot: its reciprocal is published, nobody divides later
-      const double piv = acc[IR1][IC1];
-      const bool ok = piv > 0.0;
-      *rcp1 = ok ? 1.0 / piv : 0.0;
-      pivbuf[c1] = piv;
-      if (!ok) atomicCAS(info, 0, j0 + c1 + 1);
-    }
-  }
-  if (ty == r1) {
-#pragma unroll
-    for (int j = 0; j <= IC; ++j) yac[IR1][j] = fma(-ri[IR1], yj[j], yac[IR1][j]);
-#pragma unroll
-    for (int j = 0; j <= IC1; ++j) rb1[tx + 16 * j] = yac[IR1][j];
-    riy[IR1] = 0.0;
-  }
-}
-
-// Columns 16*IC .. 16*IC+15.  Per column: wait for the broadcasts of this step (split-phase mbarrier),
-// read them, do the look-ahead part and publish it, arrive, then update the live patches of the Schur
-// complement (acc) and of Y = Ltilde^-1 (yac).
+// Columns 16*IC .. 16*IC+15.  One barrier per column: before it the owners publish column c of
+// the Schur complement (for the elimination) and row c of Y (for the inverse); after it every
+// thread updates its live patches of both.  Only lower-triangular patches (j <= i) are live, so
+// the two register patches cost 2 x 36 doubles.  IC is a template parameter: patch indices are
+// static and only the boundary block needs a mask.
 template <int IC>
-__device__ __forceinline__ void p2_block(double (&acc)[4][8], double (&yac)[4][8], double* colbuf, double* rowbuf,
-                                         double* pivbuf, double* rcpbuf, uint64_t* bar, uint32_t& phase, int ty, int tx,
-                                         int j0, int* info) {
-  constexpr int IR = IC / 2;
+__device__ __forceinline__ void p2_block(double (&acc)[8][8], double (&yac)[8][8], double* colbuf, double* rowbuf,
+                                         double* pivbuf, int ty, int tx, int tid, int j0, int* info) {
 #pragma unroll 1
   for (int cc = 0; cc < 16; ++cc) {
     const int c = IC * 16 + cc;
-    mbarrier_wait(bar, phase);
-    phase ^= 1u;
-    const double* cb = colbuf + (c & 1) * 128;
-    const double* rb = rowbuf + (c & 1) * 128;
-    const double rcp = rcpbuf[c & 1];
-    double ri[4], riy[4], cj[8], yj[8];
+    double* cb = colbuf + (c & 1) * 128;
+    double* rb = rowbuf + (c & 1) * 128;
+    if (tx == cc) {
 #pragma unroll
-    for (int i = IR; i < 4; ++i) ri[i] = cb[ty + 32 * i] * rcp;      // multipliers l~_{r,c}
-    if (ty <= (c & 31)) ri[IR] = 0.0;                                // rows at or above the pivot
+      for (int i = IC; i < 8; ++i) cb[ty + 16 * i] = acc[i][IC];
+    }
+    if (ty == cc) {
 #pragma unroll
-    for (int i = IR; i < 4; ++i) riy[i] = ri[i];
+      for (int j = 0; j <= IC; ++j) rb[tx + 16 * j] = yac[IC][j];
+    }
+    __syncthreads();
+    const double piv = cb[c];
+    const bool ok = piv > 0.0;
+    const double rcp = ok ? 1.0 / piv : 0.0;
+    if (tid == 0) {
+      pivbuf[c] = piv;
+      if (!ok) atomicCAS(info, 0, j0 + c + 1);
+    }
+    double ri[8], cj[8], yj[8];
+#pragma unroll
+    for (int i = IC; i < 8; ++i) ri[i] = cb[ty + 16 * i] * rcp;      // multipliers l~_{r,c}
+    if (ty <= cc) ri[IC] = 0.0;                                      // rows at or above the pivot
 #pragma unroll
     for (int j = IC; j < 8; ++j) cj[j] = cb[tx + 16 * j];
     if (tx <= cc) cj[IC] = 0.0;                                      // columns at or left of the pivot
 #pragma unroll
     for (int j = 0; j <= IC; ++j) yj[j] = rb[tx + 16 * j];           // Y[c][.] (zero right of c by construction)
-
-    const int c1 = c + 1;
-    double* cb1 = colbuf + (c1 & 1) * 128;
-    double* rb1 = rowbuf + (c1 & 1) * 128;
-    if (cc < 15) {
-      p2_early<IC, IC>(acc, yac, ri, riy, cj, yj, cb1, rb1, rcpbuf + (c1 & 1), pivbuf, c1, ty, tx, j0, info);
-    } else if (IC < 7) {
-      p2_early<IC, (IC < 7 ? IC + 1 : 7)>(acc, yac, ri, riy, cj, yj, cb1, rb1, rcpbuf + (c1 & 1), pivbuf, c1, ty, tx, j0, info);
-    }
-    mbarrier_arrive(bar);
-
 #pragma unroll
-    for (int i = IR; i < 4; ++i) {
+    for (int i = IC; i < 8; ++i) {
 #pragma unroll
-      for (int j = IC; j < 8; ++j)
-        if (P2_LIVE(i, j)) acc[i][j] = fma(-ri[i], cj[j], acc[i][j]);
+      for (int j = IC; j <= i; ++j) acc[i][j] = fma(-ri[i], cj[j], acc[i][j]);
 #pragma unroll
-      for (int j = 0; j <= IC; ++j)
-        if (P2_LIVE(i, j)) yac[i][j] = fma(-riy[i], yj[j], yac[i][j]);
+      for (int j = 0; j <= IC; ++j) yac[i][j] = fma(-ri[i], yj[j], yac[i][j]);
     }
   }
 }
 
-__global__ void __launch_bounds__(P2_THREADS, 1) potf2inv_kernel(double* __restrict__ A, int64_t ld, double* __restrict__ Linv,
-                                                                 int64_t ldi, int j0, int* __restrict__ info) {
+__global__ void __launch_bounds__(256, 1) potf2inv_kernel(double* __restrict__ A, int64_t ld, double* __restrict__ Linv,
+                                                          int64_t ldi, int j0, int* __restrict__ info) {
   extern __shared__ __align__(16) double p2_smem[];
   double* colbuf = p2_smem;                   // [2][128]
   double* rowbuf = colbuf + 256;              // [2][128]
   double* pivbuf = rowbuf + 256;              // [128]
   double* rsbuf = pivbuf + 128;               // [128] 1/sqrt(piv)
-  double* rcpbuf = rsbuf + 128;               // [2] reciprocal of the pivot of the step being consumed
-  __shared__ uint64_t bar;
 
   const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
-  if (tid == 0) {
-    mbarrier_init(&bar, P2_THREADS);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  double acc[4][8], yac[4][8];
+  double acc[8][8], yac[8][8];
 #pragma unroll
-  for (int i = 0; i < 4; ++i)
+  for (int i = 0; i < 8; ++i)
 #pragma unroll
-    for (int j = 0; j < 8; ++j)
-      if (P2_LIVE(i, j)) {
-        acc[i][j] = A[(int64_t)(ty + 32 * i) * ld + tx + 16 * j];
-        yac[i][j] = (ty + 32 * i == tx + 16 * j) ? 1.0 : 0.0;
-      }
-  __syncthreads();
-  // publish step 0: column 0, row 0 of Y (= e_0), the first pivot
-  if (tx == 0) {
-#pragma unroll
-    for (int i = 0; i < 4; ++i) colbuf[ty + 32 * i] = acc[i][0];
-    if (ty == 0) {
-      const double piv = acc[0][0];
-      const bool ok = piv > 0.0;
-      rcpbuf[0] = ok ? 1.0 / piv : 0.0;
-      pivbuf[0] = piv;
-      if (!ok) atomicCAS(info, 0, j0 + 1);
+    for (int j = 0; j <= i; ++j) {
+      acc[i][j] = A[(int64_t)(ty + 16 * i) * ld + tx + 16 * j];
+      yac[i][j] = (i == j && ty == tx) ? 1.0 : 0.0;
     }
-  }
-  if (ty == 0) rowbuf[tx] = yac[0][0];
-  mbarrier_arrive(&bar);
 
-  uint32_t phase = 0;
-  p2_block<0>(acc, yac, colbuf, rowbuf, pivbuf, rcpbuf, &bar, phase, ty, tx, j0, info);
-  p2_block<1>(acc, yac, colbuf, rowbuf, pivbuf, rcpbuf, &bar, phase, ty, tx, j0, info);
-  p2_block<2>(acc, yac, colbuf, rowbuf, pivbuf, rcpbuf, &bar, phase, ty, tx, j0, info);
-  p2_block<3>(acc, yac, colbuf, rowbuf, pivbuf, rcpbuf, &bar, phase, ty, tx, j0, info);
-  p2_block<4>(acc, yac, colbuf, rowbuf, pivbuf, rcpbuf, &bar, phase, ty, tx, j0, info);
-  p2_block<5>(acc, yac, colbuf, rowbuf, pivbuf, rcpbuf, &bar, phase, ty, tx, j0, info);
-  p2_block<6>(acc, yac, colbuf, rowbuf, pivbuf, rcpbuf, &bar, phase, ty, tx, j0, info);
-  p2_block<7>(acc, yac, colbuf, rowbuf, pivbuf, rcpbuf, &bar, phase, ty, tx, j0, info);
+  p2_block<0>(acc, yac, colbuf, rowbuf, pivbuf, ty, tx, tid, j0, info);
+  p2_block<1>(acc, yac, colbuf, rowbuf, pivbuf, ty, tx, tid, j0, info);
+  p2_block<2>(acc, yac, colbuf, rowbuf, pivbuf, ty, tx, tid, j0, info);
+  p2_block<3>(acc, yac, colbuf, rowbuf, pivbuf, ty, tx, tid, j0, info);
+  p2_block<4>(acc, yac, colbuf, rowbuf, pivbuf, ty, tx, tid, j0, info);
+  p2_block<5>(acc, yac, colbuf, rowbuf, pivbuf, ty, tx, tid, j0, info);
+  p2_block<6>(acc, yac, colbuf, rowbuf, pivbuf, ty, tx, tid, j0, info);
+  p2_block<7>(acc, yac, colbuf, rowbuf, pivbuf, ty, tx, tid, j0, info);
   __syncthreads();
   if (tid < 128) {
     const double piv = pivbuf[tid];
@@ -243,12 +175,12 @@ __global__ void __launch_bounds__(P2_THREADS, 1) potf2inv_kernel(double* __restr
 
   // L = Ltilde D^1/2 (acc holds the un-normalised columns), Linv = D^-1/2 Y; zeros above the diagonal
 #pragma unroll
-  for (int i = 0; i < 4; ++i)
+  for (int i = 0; i < 8; ++i)
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      const int r = ty + 32 * i, c = tx + 16 * j;
+      const int r = ty + 16 * i, c = tx + 16 * j;
       double l = 0.0, li = 0.0;
-      if (P2_LIVE(i, j)) {
+      if (j <= i) {
         if (r > c) {
           l = acc[i][j] * rsbuf[c];
           li = yac[i][j] * rsbuf[r];
@@ -268,7 +200,7 @@ static int potf2inv_launch(double* A, int64_t ld, double* Linv, int64_t ldi, int
     ALGP_CUDA(cudaFuncSetAttribute(potf2inv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, P2_SMEM_BYTES));
     configured = true;
   }
-  potf2inv_kernel<<<1, P2_THREADS, P2_SMEM_BYTES, st>>>(A, ld, Linv, ldi, j0, info);
+  potf2inv_kernel<<<1, 256, P2_SMEM_BYTES, st>>>(A, ld, Linv, ldi, j0, info);
   ALGP_LAUNCH_CHECK();
   return ALGP_OK;
 }
