@@ -227,6 +227,8 @@ def fit_predict_bench(torch, engine, n_train, grid_side, reps, peak_hbm):
     Ks = torch.empty((Mpad, Npad), dtype=torch.float64, device=dev)
     work = torch.empty(max(2, _lib.lib.algp_trtri_work_doubles(Npad)), dtype=torch.float64, device=dev)
     info = torch.zeros(1, dtype=torch.int32, device=dev)
+    sampler = ClockSampler(torch.cuda.current_device())
+    sampler.__enter__()
     for rep in range(reps + 1):
         marks = [ev() for _ in range(len(names) + 1)]
         # keep the GPU busy while the host enqueues the first stages, so that event intervals are
@@ -264,6 +266,7 @@ def fit_predict_bench(torch, engine, n_train, grid_side, reps, peak_hbm):
             times[k].append(marks[i].elapsed_time(marks[i + 1]))
         times["total"].append(marks[0].elapsed_time(marks[6]))
         tf32_err = float((v32 - v).abs().max().item())
+    sampler.__exit__()
     # end to end through the reference-facing call with HOST arrays (utils.py:293): H2D of x / y / var / grid,
     # kernel build + factor + solve + variance, D2H of mean and variance, fresh factor every call
     import algp_b200
@@ -292,7 +295,7 @@ def fit_predict_bench(torch, engine, n_train, grid_side, reps, peak_hbm):
     Mp = float(max(128, engine.pad_to(M)))
     out = {"n_train": n_train, "n_test": M, "ms": med["total"],
            "ms_tf32_mode": med["total"] - med["variance_trmm"] + med["variance_tf32"],
-           "e2e_ms_host_arrays": e2e,
+           "e2e_ms_host_arrays": e2e, "clocks": sampler.summary(),
            "tf32_max_abs_var_diff_vs_fp64": tf32_err, "ms_by_stage": med,
            "var_min": float(v.min().item()), "var_max": float(v.max().item()),
            "rooflines": {
@@ -346,8 +349,10 @@ def episode_bench(torch, engine, side=200, n_pilot=1024, acquisitions=500, per_b
             "entropy_first_last": [res["H"][0], res["H"][-1]]}
 
 
-def dgemm_peak(torch, n=8192, reps=3):
-    """cuBLAS fp64 GEMM rate on this box: the DMMA roofline denominator (not in MEASURED_PEAKS.json)."""
+def dgemm_peak(torch, n=8192, reps=3, sustained_s=1.5):
+    """cuBLAS fp64 GEMM rate on this box: the DMMA roofline denominator (not in MEASURED_PEAKS.json).
+    Returns (burst, sustained): best single call, and the mean over ~sustained_s of back-to-back calls
+    (what a kernel inside a long fp64 phase can expect under the power cap)."""
     a = torch.randn(n, n, dtype=torch.float64, device="cuda")
     b = torch.randn(n, n, dtype=torch.float64, device="cuda")
     torch.matmul(a, b)
@@ -360,7 +365,15 @@ def dgemm_peak(torch, n=8192, reps=3):
         e1.record()
         torch.cuda.synchronize()
         best = min(best, e0.elapsed_time(e1))
-    return 2.0 * n ** 3 / best / 1e9
+    calls = max(4, int(sustained_s * 1e3 / best))
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(calls):
+        torch.matmul(a, b)
+    e1.record()
+    torch.cuda.synchronize()
+    sustained = 2.0 * n ** 3 * calls / e0.elapsed_time(e1) / 1e9
+    return 2.0 * n ** 3 / best / 1e9, sustained
 
 
 def tf32_gemm_peak(torch, n=8192, reps=3):
@@ -503,8 +516,9 @@ def run_ours(args, rank, world, local_rank):
     cpu_base = None
     if rank == 0:
         try:
-            fp64_peak = dgemm_peak(torch)
+            fp64_peak, fp64_sustained = dgemm_peak(torch)
             extra["fp64_gemm_peak_tflops_cublas_8192"] = fp64_peak
+            extra["fp64_gemm_sustained_tflops_cublas_8192"] = fp64_sustained
             fits = [fit_predict_bench(torch, engine, 4096, 64, 5, peak_hbm)]
             if not args.skip_large:
                 fits.append(fit_predict_bench(torch, engine, 16384, 256, 2, peak_hbm))
@@ -513,8 +527,11 @@ def run_ours(args, rank, world, local_rank):
             for f in fits:
                 for r in f["rooflines"].values():
                     if r["unit"] == "TFLOP/s":
-                        r["peak"] = fp64_peak
-                        r["frac"] = r["achieved"] / fp64_peak
+                        # burst figure for the short N=4096 leg, sustained for the long N=16384 leg
+                        pk = fp64_peak if f["n_train"] <= 4096 else fp64_sustained
+                        r["peak"] = pk
+                        r["peak_kind"] = "cuBLAS dgemm burst" if f["n_train"] <= 4096 else "cuBLAS dgemm sustained"
+                        r["frac"] = r["achieved"] / pk
                     elif r["unit"].startswith("TFLOP/s(tf32)"):
                         r["peak"] = tf32_peak
                         r["frac"] = r["achieved"] / tf32_peak
