@@ -251,21 +251,31 @@ def fit_predict_bench(torch, engine, n_train, grid_side, reps, peak_hbm):
         _, rn = f.whiten(Ks, want_V=False)
         v = engine.rowsum(rn, -1.0, hy.outputscale, None, rows=M)
         marks[6].record()
-        # TF32 mode of the same step: split K(X*,X) and Linv into fp32 hi/lo planes + tcgen05 split-TF32 TRMM
-        rn32 = f.whiten_norm_tf32(Ks)
-        v32 = engine.rowsum(rn32, -1.0, hy.outputscale, None, rows=M)
         marks[7].record()
         torch.cuda.synchronize()
-        f._linv_tf32 = None
-        del rn32
         if int(info.item()) != 0:
             raise RuntimeError("fit_predict bench: matrix not positive definite")
         if rep == 0:
             continue           # warm-up
-        for i, k in enumerate(names):
+        for i, k in enumerate(names[:-1]):
             times[k].append(marks[i].elapsed_time(marks[i + 1]))
         times["total"].append(marks[0].elapsed_time(marks[6]))
-        tf32_err = float((v32 - v).abs().max().item())
+    # TF32 mode of the variance step, timed in its own loop (a run uses one mode or the other; interleaving
+    # would let the tensor-core power draw of this stage throttle the next repetition's fp64 factorisation):
+    # split K(X*,X) and Linv into fp32 hi/lo planes + tcgen05 split-TF32 TRMM
+    times["variance_tf32"] = []
+    for rep in range(reps + 1):
+        f._linv_tf32 = None
+        t0, t1 = ev(), ev()
+        t0.record()
+        rn32 = f.whiten_norm_tf32(Ks)
+        v32 = engine.rowsum(rn32, -1.0, hy.outputscale, None, rows=M)
+        t1.record()
+        torch.cuda.synchronize()
+        if rep:
+            times["variance_tf32"].append(t0.elapsed_time(t1))
+        del rn32
+    tf32_err = float((v32 - v).abs().max().item())
     sampler.__exit__()
     # end to end through the reference-facing call with HOST arrays (utils.py:293): H2D of x / y / var / grid,
     # kernel build + factor + solve + variance, D2H of mean and variance, fresh factor every call
