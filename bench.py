@@ -524,7 +524,9 @@ def run_ours(args, rank, world, local_rank):
 
     extra = {}
     cpu_base = None
-    if rank == 0:
+    # the fit+predict / episode / CPU legs explain the N=1 line; at N>1 only the sharded metric is measured
+    # (the other ranks would idle at the barrier while rank 0 ran them)
+    if rank == 0 and world == 1:
         try:
             fp64_peak, fp64_sustained = dgemm_peak(torch)
             extra["fp64_gemm_peak_tflops_cublas_8192"] = fp64_peak
