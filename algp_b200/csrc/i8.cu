@@ -1,0 +1,361 @@
+// fp64-grade predictive variance on the INT8 tensor cores (tcgen05.mma.kind::i8, TMEM s32 accumulators).
+//
+// var_m = k** - |V_m|^2, V = K(X*,X) L^-T (reference utils.py:300-308) is N^2 M flops and, in fp64, is
+// pinned to the DMMA roof (35 TFLOP/s on B200).  tcgen05 has no f64 kind, but it multiplies 8-bit integers
+// with EXACT 32-bit accumulation at ~100x the DMMA rate, so the product is evaluated as an error-free
+// digit expansion (Ozaki scheme): every row r of an operand is scaled by a power of two 2^-e_r to
+// |y| < 1 and written as S signed base-128 digits
+//        y = sum_p d_p 2^(-6-7p),   d_p in [-64, 64]            (exact for S = 8: 56 bits)
+// so  (A B^T)[m][j] = 2^(eA_m + eB_j - 12) * sum_g 2^(-7g) G_g[m][j],   G_g = sum_{p+q=g} A_p B_q^T.
+// Each G_g is an integer GEMM: |d d'| <= 2^12, K <= 2^14 terms, <= 8 (p,q) pairs -> < 2^29, no overflow,
+// no rounding.  Groups g >= S are dropped (relative 2^(-7S) of the row scales), the rest is summed in fp64
+// in the epilogue, low order first.  S = 7 (28 GEMMs) or 8 (36 GEMMs) meets the fp64 tier.
+//
+//   split_i8_kernel   fp64 matrix -> S int8 digit planes + the row scale 2^e_r (one CTA per row; the row
+//                     maximum fixes e_r, the second read of the row hits L2)
+//   trmm_i8_kernel    one CTA per 128 x 64 tile of V.  All S group accumulators of the tile live in TMEM
+//                     at once (S x 64 columns: the whole 512-column TMEM for S = 8), so the operand
+//                     digits stream through shared memory exactly once.  One producer thread issues two
+//                     3-D TMA loads per 32-byte k-stage (box = 32 B x rows x S planes, SWIZZLE_32B); one
+//                     thread issues the S(S+1)/2 MMAs (M128 N64 K32) of the stage and commits the stage's
+//                     `empty` mbarrier; 4-stage ring.  Epilogue: tcgen05.ld, Horner in fp64 over the
+//                     groups, column scale, square, row sum -- V is never written.  k-range stops at the
+//                     tile's last column (Linv is lower triangular).
+#include "common.cuh"
+#include <cuda.h>
+
+#define I8_TM 128
+#define I8_TN 64
+#define I8_KC 32                        // bytes (= int8 digits) of k per row per stage = one MMA's K
+#define I8_THREADS 160
+#define I8_MAX_S 8
+
+namespace {
+
+__device__ __forceinline__ uint32_t s_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void commit_to(uint64_t* b) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(s_u32(b)) : "memory");
+}
+__device__ __forceinline__ void expect_tx(uint64_t* b, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(s_u32(b)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* tm, int c0, int c1, int c2, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+      ::"r"(dst), "l"(tm), "r"(c0), "r"(c1), "r"(c2), "r"(s_u32(bar))
+      : "memory");
+}
+// D[tmem] (+)= A[smem] B[smem]^T, signed 8-bit operands, s32 accumulator
+__device__ __forceinline__ void mma_i8(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// K-major SWIZZLE_32B operand tile: rows of 32 B, 8-row groups 256 B apart (SBO); cute::UMMA::SmemDescriptor
+// version 1 (bit 46), layout_type 6 = SWIZZLE_32B (bits 61-63), LBO field 1 (unused for swizzled K-major)
+__device__ __forceinline__ uint64_t desc_sw32(uint32_t saddr) {
+  return (uint64_t)((saddr >> 4) & 0x3FFF) | (1ull << 16) | ((uint64_t)(256 >> 4) << 32) | (1ull << 46) | (6ull << 61);
+}
+// cute::UMMA::InstrDescriptor: c_format S32 (2) [4,6), a/b_format signed 8-bit (1) [7,10) / [10,13), K-major,
+// N>>3 [17,23), M>>4 [24,29)
+__host__ __device__ constexpr uint32_t idesc_i8(int M, int N) {
+  return (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+// ---------------------------------------------------------------------------------------------
+template <int S>
+__global__ void __launch_bounds__(256)
+split_i8_kernel(const double* __restrict__ src, int64_t cols, int64_t ld, int8_t* __restrict__ planes, int64_t ldp,
+                int64_t plane_stride, double* __restrict__ row_scale) {
+  __shared__ double red[8];
+  const int64_t row = blockIdx.x;
+  const double* x = src + row * ld;
+  const int tid = threadIdx.x;
+  double mx = 0.0;
+  for (int64_t c = (int64_t)tid * 2; c < cols; c += 512) {
+    const double2 v = *reinterpret_cast<const double2*>(x + c);
+    mx = fmax(mx, fmax(fabs(v.x), fabs(v.y)));
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  if ((tid & 31) == 0) red[tid >> 5] = mx;
+  __syncthreads();
+  mx = red[0];
+#pragma unroll
+  for (int w = 1; w < 8; ++w) mx = fmax(mx, red[w]);
+  int e = 0;
+  if (mx > 0.0) (void)frexp(mx, &e);                // mx = f 2^e, f in [0.5, 1): |x| 2^-e < 1
+  if (tid == 0) row_scale[row] = ldexp(1.0, e);
+  const double sc = ldexp(1.0, 6 - e);              // t0 = 64 y
+  int8_t* out = planes + row * ldp;
+  for (int64_t c = (int64_t)tid * 16; c < cols; c += 256 * 16) {
+    double t[16];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const double2 v = *reinterpret_cast<const double2*>(x + c + 2 * i);
+      t[2 * i] = v.x * sc;
+      t[2 * i + 1] = v.y * sc;
+    }
+#pragma unroll
+    for (int p = 0; p < S; ++p) {
+      uint32_t w[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        uint32_t pack = 0;
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+          const int i = q * 4 + b;
+          const double d = rint(t[i]);              // |t| <= 64: the digit, exact
+          t[i] = (t[i] - d) * 128.0;                // exact remainder, next digit's scale
+          pack |= ((uint32_t)(__double2int_rn(d)) & 0xFFu) << (8 * b);
+        }
+        w[q] = pack;
+      }
+      *reinterpret_cast<uint4*>(out + (int64_t)p * plane_stride + c) = make_uint4(w[0], w[1], w[2], w[3]);
+    }
+  }
+}
+
+struct I8Args {
+  int MT, NT;                          // 128-row tiles of K, 64-row tiles of Linv
+  const double* scale_a;               // [mpad]  2^eA_m
+  const double* scale_b;               // [npad]  2^eB_j
+  double* rn_partial; int rn_nt;       // [mpad x npad/64]
+};
+
+template <int S>
+struct I8Cfg {
+  static constexpr int A_PLANE = I8_TM * I8_KC;                       // 4 KB
+  static constexpr int B_PLANE = I8_TN * I8_KC;                       // 2 KB
+  static constexpr int A_BYTES = S * A_PLANE;
+  static constexpr int B_BYTES = S * B_PLANE;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;               // S x 6 KB
+  static constexpr int STAGES = (S >= 8) ? 4 : ((200 * 1024) / STAGE_BYTES > 6 ? 6 : (200 * 1024) / STAGE_BYTES);
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024;
+  static constexpr int TMEM_COLS = (S * I8_TN > 256) ? 512 : ((S * I8_TN > 128) ? 256 : 128);
+};
+
+template <int S>
+__global__ void __launch_bounds__(I8_THREADS, 1)
+trmm_i8_kernel(const I8Args p, const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b) {
+  using C = I8Cfg<S>;
+  extern __shared__ unsigned char i8_smem_raw[];
+  __shared__ uint64_t full_bar[C::STAGES], empty_bar[C::STAGES], done_bar;
+  __shared__ uint32_t tmem_slot;
+  __shared__ double sb_s[I8_TN];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t ring = (s_u32(i8_smem_raw) + 1023u) & ~1023u;
+
+  // tile map: groups of 16 m-tiles sweep the n-tiles together, long (large nt) tiles first, so concurrent
+  // CTAs stream the same k-window of the K digits and the same Linv rows through L2
+  constexpr int GM = 16;
+  const int per_group = GM * p.NT;
+  const int mg = blockIdx.x / per_group, rem = blockIdx.x % per_group;
+  const int nt = p.NT - 1 - rem / GM;
+  const int mt = mg * GM + rem % GM;
+  const bool valid_tile = mt < p.MT;                 // block-uniform
+  const int m0 = mt * I8_TM, n0 = nt * I8_TN;
+  const int KT = valid_tile ? (n0 + I8_TN) / I8_KC : 0;   // Linv[j][k] = 0 for k > j
+
+  if (tid == 0) {
+    for (int s = 0; s < C::STAGES; ++s) {
+      mbarrier_init(&full_bar[s], 1);
+      mbarrier_init(&empty_bar[s], 1);
+    }
+    mbarrier_init(&done_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 4) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s_u32(&tmem_slot)), "r"(C::TMEM_COLS));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  if (tid < I8_TN && valid_tile) sb_s[tid] = p.scale_b[n0 + tid];
+  fence_before();
+  __syncthreads();
+  fence_after();
+  const uint32_t tmem = tmem_slot;
+
+  if (warp < 4) {
+    if (tid == 0) {
+      // ===================== TMA producer (one thread) =====================
+      for (int it = 0; it < KT; ++it) {
+        const int s = it % C::STAGES, u = it / C::STAGES;
+        if (u > 0) mbarrier_wait(&empty_bar[s], (u - 1) & 1);     // the MMAs that read this slot are done
+        const uint32_t st = ring + (uint32_t)s * C::STAGE_BYTES;
+        expect_tx(&full_bar[s], C::STAGE_BYTES);
+        tma_load_3d(st, &tm_a, it * I8_KC, m0, 0, &full_bar[s]);
+        tma_load_3d(st + C::A_BYTES, &tm_b, it * I8_KC, n0, 0, &full_bar[s]);
+      }
+    }
+    __syncwarp();
+    // ===================== epilogue =====================
+    if (valid_tile) {
+      mbarrier_wait(&done_bar, 0);
+      fence_after();
+      const int row = warp * 32 + lane;                          // TMEM lane = accumulator row
+      double ss = 0.0;
+#pragma unroll 1
+      for (int c0 = 0; c0 < I8_TN; c0 += 16) {
+        double v[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] = 0.0;
+#pragma unroll
+        for (int g = S - 1; g >= 0; --g) {
+          uint32_t r[16];
+          const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)(g * I8_TN + c0);
+          asm volatile(
+              "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+              : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+                "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+              : "r"(taddr));
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[i] = fma(v[i], 0.0078125, (double)(int)r[i]);   // Horner in 2^-7
+        }
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const double t = v[i] * sb_s[c0 + i];
+          ss = fma(t, t, ss);
+        }
+      }
+      const double sa = p.scale_a[m0 + row] * (1.0 / 4096.0);   // 2^(eA_m - 12)
+      p.rn_partial[(int64_t)(m0 + row) * p.rn_nt + nt] = ss * sa * sa;
+    }
+  } else if (warp == 4 && lane == 0) {
+    // ===================== MMA issuer (one thread) =====================
+    const uint32_t idesc = idesc_i8(I8_TM, I8_TN);
+    for (int it = 0; it < KT; ++it) {
+      const int s = it % C::STAGES, u = it / C::STAGES;
+      mbarrier_wait(&full_bar[s], u & 1);
+      fence_after();
+      const uint32_t a0 = ring + (uint32_t)s * C::STAGE_BYTES, b0 = a0 + C::A_BYTES;
+      const uint64_t da0 = desc_sw32(a0), db0 = desc_sw32(b0);
+#pragma unroll
+      for (int g = 0; g < S; ++g) {
+#pragma unroll
+        for (int pa = 0; pa <= g; ++pa) {
+          const int qb = g - pa;
+          mma_i8(tmem + (uint32_t)(g * I8_TN), da0 + (uint64_t)((pa * C::A_PLANE) >> 4), db0 + (uint64_t)((qb * C::B_PLANE) >> 4),
+                 idesc, (it != 0 || pa != 0) ? 1u : 0u);
+        }
+      }
+      commit_to(&empty_bar[s]);                                  // arrives when these MMAs have read the stage
+    }
+    if (valid_tile) commit_to(&done_bar);                        // accumulators complete
+  }
+
+  fence_before();
+  __syncthreads();
+  if (warp == 4) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(C::TMEM_COLS));
+  }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)p;
+  }
+  return fn;
+}
+// int8 digit planes [S][rows][ld bytes]: boxes of 32 B x box_rows x S planes, SWIZZLE_32B
+int make_tmap3(CUtensorMap* tm, const int8_t* base, int64_t rows, int64_t cols, int64_t ld, int64_t plane_stride, int S,
+               int box_rows) {
+  EncodeTiledFn enc = encode_fn();
+  if (!enc) return ALGP_ERR_UNSUPPORTED;
+  cuuint64_t dims[3] = {(cuuint64_t)cols, (cuuint64_t)rows, (cuuint64_t)S};
+  cuuint64_t strides[2] = {(cuuint64_t)ld, (cuuint64_t)plane_stride};
+  cuuint32_t box[3] = {I8_KC, (cuuint32_t)box_rows, (cuuint32_t)S};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, (void*)base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? ALGP_OK : ALGP_ERR_INVALID;
+}
+
+template <int S>
+int launch_split(const double* src, int64_t rows, int64_t cols, int64_t ld, int8_t* planes, int64_t ldp, int64_t plane_stride,
+                 double* row_scale, cudaStream_t st) {
+  split_i8_kernel<S><<<(unsigned)rows, 256, 0, st>>>(src, cols, ld, planes, ldp, plane_stride, row_scale);
+  ALGP_LAUNCH_CHECK();
+  return ALGP_OK;
+}
+
+template <int S>
+int launch_trmm(const I8Args& a, const CUtensorMap& ta, const CUtensorMap& tb, cudaStream_t st) {
+  using C = I8Cfg<S>;
+  static bool configured = false;
+  if (!configured) {
+    ALGP_CUDA(cudaFuncSetAttribute(trmm_i8_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+    configured = true;
+  }
+  const int groups = (a.MT + 15) / 16;
+  const int64_t grid = (int64_t)groups * 16 * a.NT;
+  trmm_i8_kernel<S><<<(unsigned)grid, I8_THREADS, C::SMEM_BYTES, st>>>(a, ta, tb);
+  ALGP_LAUNCH_CHECK();
+  return ALGP_OK;
+}
+
+}  // namespace
+
+extern "C" int algp_split_i8(const double* src, int64_t rows, int64_t cols, int64_t ld, int nslices, int8_t* planes,
+                             int64_t ldp, int64_t plane_stride, double* row_scale, void* stream) {
+  if (!src || !planes || !row_scale || rows < 0 || cols < 0 || (cols & 15) || (ld & 1) || (ldp & 15) || ld < cols ||
+      ldp < cols || plane_stride < rows * ldp || (plane_stride & 15) || nslices < 2 || nslices > I8_MAX_S)
+    return ALGP_ERR_INVALID;
+  if (((uintptr_t)src | (uintptr_t)planes) & 15) return ALGP_ERR_INVALID;
+  if (rows == 0 || cols == 0) return ALGP_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (nslices) {
+    case 2: return launch_split<2>(src, rows, cols, ld, planes, ldp, plane_stride, row_scale, st);
+    case 3: return launch_split<3>(src, rows, cols, ld, planes, ldp, plane_stride, row_scale, st);
+    case 4: return launch_split<4>(src, rows, cols, ld, planes, ldp, plane_stride, row_scale, st);
+    case 5: return launch_split<5>(src, rows, cols, ld, planes, ldp, plane_stride, row_scale, st);
+    case 6: return launch_split<6>(src, rows, cols, ld, planes, ldp, plane_stride, row_scale, st);
+    case 7: return launch_split<7>(src, rows, cols, ld, planes, ldp, plane_stride, row_scale, st);
+    default: return launch_split<8>(src, rows, cols, ld, planes, ldp, plane_stride, row_scale, st);
+  }
+}
+
+// rn_partial[m][t] (t < npad/64) = sum over 64-column tile t of (K Linv^T)[m][.]^2 from the digit planes
+extern "C" int algp_trmm_rt_i8(const int8_t* Kp, const double* Kscale, int64_t mpad, int64_t ldk, int64_t k_plane_stride,
+                               const int8_t* Lp, const double* Lscale, int64_t npad, int64_t ldl, int64_t l_plane_stride,
+                               int nslices, double* rn_partial, void* stream) {
+  if (!Kp || !Kscale || !Lp || !Lscale || !rn_partial || mpad % ALGP_BLK || npad % ALGP_BLK || ldk < npad || ldl < npad ||
+      (ldk & 15) || (ldl & 15) || (k_plane_stride & 15) || (l_plane_stride & 15) || nslices < 2 || nslices > I8_MAX_S ||
+      npad > 32768)
+    return ALGP_ERR_INVALID;           // K <= 2^15 keeps every group sum below 2^31 (8 pairs x 2^15 x 2^12 = 2^30)
+  if (mpad == 0 || npad == 0) return ALGP_OK;
+  if (((uintptr_t)Kp | (uintptr_t)Lp) & 15) return ALGP_ERR_INVALID;
+  CUtensorMap ta, tb;
+  int rc;
+  if ((rc = make_tmap3(&ta, Kp, mpad, npad, ldk, k_plane_stride, nslices, I8_TM))) return rc;
+  if ((rc = make_tmap3(&tb, Lp, npad, npad, ldl, l_plane_stride, nslices, I8_TN))) return rc;
+  I8Args a;
+  a.MT = (int)(mpad / I8_TM);
+  a.NT = (int)(npad / I8_TN);
+  a.scale_a = Kscale;
+  a.scale_b = Lscale;
+  a.rn_partial = rn_partial;
+  a.rn_nt = a.NT;
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (nslices) {
+    case 2: return launch_trmm<2>(a, ta, tb, st);
+    case 3: return launch_trmm<3>(a, ta, tb, st);
+    case 4: return launch_trmm<4>(a, ta, tb, st);
+    case 5: return launch_trmm<5>(a, ta, tb, st);
+    case 6: return launch_trmm<6>(a, ta, tb, st);
+    case 7: return launch_trmm<7>(a, ta, tb, st);
+    default: return launch_trmm<8>(a, ta, tb, st);
+  }
+}

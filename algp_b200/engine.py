@@ -17,6 +17,7 @@ from . import _lib
 from ._lib import call, ptr, stream
 
 BLK = 128
+I8_SLICES = 8          # digit planes of the INT8 variance path: 8 x 7 bits covers the fp64 mantissa
 CONST = 0.5 * np.log(2 * np.pi * np.exp(1))        # utils.py:10
 KIND = {"rbf": 0, None: 0, "matern": 1}
 
@@ -189,11 +190,34 @@ class GPFactor(object):
              ptr(rn), stream())
         return rn
 
+    def split_i8(self, M, nslices):
+        """fp64 device matrix -> (planes int8 [nslices, rows, cols], row_scale [rows]) digit expansion for the
+        INT8 tensor-core path."""
+        rows, cols = M.shape
+        planes = torch.empty((nslices, rows, cols), dtype=torch.int8, device=M.device)
+        scale = torch.empty(rows, dtype=torch.float64, device=M.device)
+        call("algp_split_i8", ptr(M), rows, cols, M.stride(0), nslices, ptr(planes), cols, rows * cols, ptr(scale), stream())
+        return planes, scale
+
+    def whiten_norm_i8(self, Ks, nslices=I8_SLICES):
+        """Squared row norms of V = Ks L^-T per 64-column tile through exact INT8 digit GEMMs (fp64 tier)."""
+        cache = getattr(self, "_linv_i8", None)
+        if cache is None or cache[0] != nslices:
+            self._linv_i8 = cache = (nslices,) + self.split_i8(self.Linv, nslices)
+        _, lp, ls = cache
+        kp, ks = self.split_i8(Ks, nslices)
+        Mpad = Ks.shape[0]
+        rn = torch.empty((Mpad, self.Npad // 64), dtype=torch.float64, device=Ks.device)
+        call("algp_trmm_rt_i8", ptr(kp), ptr(ks), Mpad, kp.stride(1), kp.stride(0), ptr(lp), ptr(ls), self.Npad,
+             lp.stride(1), lp.stride(0), nslices, ptr(rn), stream())
+        return rn
+
     def mean_var(self, xs, y0, ymean, test_var=None, want_var=True, max_rows=65536, precision="fp64"):
         """Posterior mean (and latent variance) at xs: utils.py:300-308 without the inverse.
-        precision="tf32" runs the O(N^2 M) variance step on the tcgen05 tensor cores (1e-4 tier)."""
-        if precision not in ("fp64", "tf32"):
-            raise ValueError("precision must be 'fp64' or 'tf32'")
+        precision="tf32" runs the O(N^2 M) variance step on the tcgen05 tensor cores (1e-4 tier);
+        precision="i8" runs it as exact INT8 digit GEMMs on the same tensor cores (fp64 tier)."""
+        if precision not in ("fp64", "tf32", "i8"):
+            raise ValueError("precision must be 'fp64', 'i8' or 'tf32'")
         alpha, _ = self.solve(y0)
         M = xs.shape[0]
         mu = torch.empty(M, dtype=torch.float64, device=xs.device)
@@ -205,6 +229,8 @@ class GPFactor(object):
             if want_var:
                 if precision == "tf32":
                     rn = self.whiten_norm_tf32(Ks)
+                elif precision == "i8":
+                    rn = self.whiten_norm_i8(Ks)
                 else:
                     _, rn = self.whiten(Ks, want_V=False)
                 tv = None if test_var is None else test_var[lo:hi].contiguous()

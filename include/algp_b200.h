@@ -88,6 +88,20 @@ int algp_split_tf32(const double* src, int64_t rows, int64_t cols, int64_t ld, f
 int algp_trmm_rt_tf32(const float* Khi, const float* Klo, int64_t mpad, int64_t ldk, const float* Lhi,
                       const float* Llo, int64_t npad, int64_t ldl, double* rn_partial, void* stream);
 
+/* ---- K2'': fp64-grade variance on the INT8 tensor cores (tcgen05 kind::i8, exact s32 accumulation) ---- */
+/* fp64 matrix -> `nslices` (2..8) signed base-128 digit planes of every row scaled by a power of two:
+ * src[r][c] = row_scale[r] * sum_p planes[p][r][c] * 2^(-6-7p) (+ a remainder below 2^(-7 nslices) row_scale[r]).
+ * planes is [nslices][rows][ldp] bytes (plane_stride bytes apart), cols % 16 == 0. */
+int algp_split_i8(const double* src, int64_t rows, int64_t cols, int64_t ld, int nslices, int8_t* planes,
+                  int64_t ldp, int64_t plane_stride, double* row_scale, void* stream);
+/* Same row-norm partials as algp_trmm_rt (rn_partial[m][t], t < npad/64) from the digit planes of K [mpad x npad]
+ * and Linv [npad x npad]: the digit products are exact integer GEMMs, groups of equal weight are summed in
+ * fp64 (error ~ 2^(-7 nslices) of the row scales): the fp64 tier of the variance (utils.py:305-308) at
+ * several times the DMMA rate.  npad <= 32768. */
+int algp_trmm_rt_i8(const int8_t* Kp, const double* Kscale, int64_t mpad, int64_t ldk, int64_t k_plane_stride,
+                    const int8_t* Lp, const double* Lscale, int64_t npad, int64_t ldl, int64_t l_plane_stride,
+                    int nslices, double* rn_partial, void* stream);
+
 /* ---- K4: marginal-likelihood gradient (GPR.fit, models.py:145-158) ---------- */
 /* Ainv (lower triangle) = Linv^T Linv = A^-1 */
 int algp_potri_lower(const double* Linv, int64_t npad, int64_t ldi, double* Ainv, int64_t lda, void* stream);

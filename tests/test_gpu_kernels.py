@@ -265,3 +265,59 @@ def test_variance_tf32_tier(N, M):
     np.testing.assert_allclose(v64.cpu().numpy(), v_o, rtol=0, atol=1e-9)
     np.testing.assert_allclose(v32.cpu().numpy(), v_o, rtol=0, atol=1e-4)
     np.testing.assert_array_equal(mu32.cpu().numpy(), mu64.cpu().numpy())   # the mean stays fp64
+
+
+# ---------------------------------------------------------------- INT8 digit mode (tcgen05 kind::i8)
+@pytest.mark.parametrize("S", [2, 5, 7, 8])
+def test_split_i8_planes(S):
+    """Digit expansion: |d| <= 64 and the planes reconstruct every row to 2^(-7S) of its scale."""
+    rng = np.random.default_rng(S)
+    M = rng.normal(size=(256, 384)) * np.exp(rng.normal(size=(256, 384)) * 3)
+    M[3] = 0.0                                           # an all-zero row
+    M[5, 7] = 1.0; M[5, 8:] *= 1e-30                     # power-of-two row maximum
+    f = engine.GPFactor.__new__(engine.GPFactor)
+    planes, scale = engine.GPFactor.split_i8(f, dev(M), S)
+    planes, scale = planes.cpu().numpy().astype(np.float64), scale.cpu().numpy()
+    assert planes.shape == (S, 256, 384) and np.abs(planes).max() <= 64
+    mx = np.abs(M).max(axis=1)
+    nz = mx > 0
+    assert (scale[nz] > mx[nz]).all() and (scale[nz] <= 2 * mx[nz]).all()      # 2^e with |row| / 2^e in [0.5, 1)
+    assert np.array_equal(np.log2(scale), np.round(np.log2(scale)))
+    rec = sum(planes[p] * 2.0 ** (-6 - 7 * p) for p in range(S)) * scale[:, None]
+    assert (np.abs(rec - M) <= 2.0 ** (-7 * S) * scale[:, None]).all()
+
+
+@pytest.mark.parametrize("N,M", [(128, 128), (300, 150), (640, 1000), (1536, 700)])
+def test_variance_i8_fp64_tier(N, M):
+    """precision='i8': exact INT8 digit GEMMs on tcgen05 against the fp64 oracle at the fp64 tier
+    (abs 1e-9 relative to the prior scale s^2 = 1), and bit-identical means."""
+    x, var, th, hy, A = spd_problem(N, N + 7)
+    rng = np.random.default_rng(N)
+    xs = rng.uniform(0, 40, size=(M, 2))
+    y = rng.normal(size=N)
+    f = engine.GPFactor(hy, dev(x), diag_add=dev(var))
+    mu64, v64 = f.mean_var(dev(xs), dev(y - y.mean()), float(y.mean()))
+    mu8, v8 = f.mean_var(dev(xs), dev(y - y.mean()), float(y.mean()), precision="i8")
+    f.check()
+    _, v_o = O.predictive_distribution_chol(O.OracleGP(th, "fp64"), x, y, xs, var, return_var=True)
+    np.testing.assert_allclose(v8.cpu().numpy(), v_o, rtol=0, atol=1e-9)
+    np.testing.assert_allclose(v8.cpu().numpy(), v64.cpu().numpy(), rtol=0, atol=1e-10)
+    np.testing.assert_array_equal(mu8.cpu().numpy(), mu64.cpu().numpy())
+
+
+def test_trmm_i8_slices_converge():
+    """Each extra digit plane buys ~7 bits: the row norms converge geometrically to the DMMA result."""
+    N, M = 512, 256
+    x, var, th, hy, A = spd_problem(N, N + 3)
+    rng = np.random.default_rng(5)
+    xs = rng.uniform(0, 40, size=(M, 2))
+    f = engine.GPFactor(hy, dev(x), diag_add=dev(var))
+    Ks, _ = f.cross(dev(xs))
+    _, rn = f.whiten(Ks, want_V=False)
+    ref = rn.sum(1).cpu().numpy()
+    errs = []
+    for S in (3, 4, 5, 6, 7, 8):
+        got = f.whiten_norm_i8(Ks, nslices=S).sum(1).cpu().numpy()
+        errs.append(np.abs(got - ref).max())
+    assert errs[-1] < 1e-12 and errs[-2] < 1e-10
+    assert all(errs[i + 1] < errs[i] / 16 or errs[i + 1] < 1e-13 for i in range(len(errs) - 1)), errs
