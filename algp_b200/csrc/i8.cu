@@ -11,18 +11,25 @@
 // no rounding.  Groups g >= S are dropped (relative 2^(-7S) of the row scales), the rest is summed in fp64
 // in the epilogue, low order first.  S = 7 (28 GEMMs) or 8 (36 GEMMs) meets the fp64 tier.
 //
-//   split_i8_kernel   fp64 matrix -> S int8 digit planes + the row scale 2^e_r (one CTA per row; the row
-//                     maximum fixes e_r, the second read of the row hits L2)
+//   split_i8_kernel   fp64 matrix -> S int8 digit planes + the row scale 2^e_r (one CTA per 8 rows; the row
+//                     maximum fixes e_r, the second read of the rows hits L1/L2).  The planes are written
+//                     in the MMA's own operand layout, tile by tile:
+//                         [row tile][32-byte k chunk][plane][row group of 8][k half][8 rows][16 B]
+//                     (the K-major no-swizzle canonical layout: 8 x 16 B core matrices, LBO 128 B between
+//                     the k halves, SBO 256 B between row groups), so one k-stage of one operand -- all
+//                     S planes -- is ONE contiguous block of global memory.
 //   trmm_i8_kernel    one CTA per 128 x 64 tile of V.  All S group accumulators of the tile live in TMEM
 //                     at once (S x 64 columns: the whole 512-column TMEM for S = 8), so the operand
 //                     digits stream through shared memory exactly once.  One producer thread issues two
-//                     3-D TMA loads per 32-byte k-stage (box = 32 B x rows x S planes, SWIZZLE_32B); one
-//                     thread issues the S(S+1)/2 MMAs (M128 N64 K32) of the stage and commits the stage's
-//                     `empty` mbarrier; 4-stage ring.  Epilogue: tcgen05.ld, Horner in fp64 over the
+//                     bulk copies (cp.async.bulk, 32 KB + 16 KB contiguous for S = 8) per 32-byte k-stage
+//                     -- full-line L2 requests; a tensor-map box of 32-byte rows saturates the SM's
+//                     request path to the crossbar at one 32-byte sector per clock (ncu, r01) --; one
+//                     thread issues the stage's MMAs (M128 K32, N = 64..256: the B planes of a stage are one
+//                     contiguous operand, so one instruction covers up to 4 plane products) and commits the
+//                     stage's `empty` mbarrier; 4-stage ring.  Epilogue: tcgen05.ld, Horner in fp64 over the
 //                     groups, column scale, square, row sum -- V is never written.  k-range stops at the
 //                     tile's last column (Linv is lower triangular).
 #include "common.cuh"
-#include <cuda.h>
 
 #define I8_TM 128
 #define I8_TN 64
@@ -41,11 +48,10 @@ __device__ __forceinline__ void commit_to(uint64_t* b) {
 __device__ __forceinline__ void expect_tx(uint64_t* b, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(s_u32(b)), "r"(bytes) : "memory");
 }
-__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* tm, int c0, int c1, int c2, uint64_t* bar) {
-  asm volatile(
-      "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
-      ::"r"(dst), "l"(tm), "r"(c0), "r"(c1), "r"(c2), "r"(s_u32(bar))
-      : "memory");
+__device__ __forceinline__ void bulk_load(uint32_t dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst), "l"(src), "r"(bytes), "r"(s_u32(bar))
+               : "memory");
 }
 // D[tmem] (+)= A[smem] B[smem]^T, signed 8-bit operands, s32 accumulator
 __device__ __forceinline__ void mma_i8(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
@@ -55,10 +61,11 @@ __device__ __forceinline__ void mma_i8(uint32_t tmem_d, uint64_t desc_a, uint64_
       ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
       : "memory");
 }
-// K-major SWIZZLE_32B operand tile: rows of 32 B, 8-row groups 256 B apart (SBO); cute::UMMA::SmemDescriptor
-// version 1 (bit 46), layout_type 6 = SWIZZLE_32B (bits 61-63), LBO field 1 (unused for swizzled K-major)
-__device__ __forceinline__ uint64_t desc_sw32(uint32_t saddr) {
-  return (uint64_t)((saddr >> 4) & 0x3FFF) | (1ull << 16) | ((uint64_t)(256 >> 4) << 32) | (1ull << 46) | (6ull << 61);
+// K-major no-swizzle (INTERLEAVE) operand tile: 8 x 16 B core matrices; LBO = 128 B between the two 16-byte
+// k halves of an MMA, SBO = 256 B between 8-row groups (cute::UMMA::SmemDescriptor: version 1 at bit 46,
+// layout_type 0)
+__device__ __forceinline__ uint64_t desc_kmajor(uint32_t saddr) {
+  return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)(128 >> 4) << 16) | ((uint64_t)(256 >> 4) << 32) | (1ull << 46);
 }
 // cute::UMMA::InstrDescriptor: c_format S32 (2) [4,6), a/b_format signed 8-bit (1) [7,10) / [10,13), K-major,
 // N>>3 [17,23), M>>4 [24,29)
@@ -69,37 +76,47 @@ __host__ __device__ constexpr uint32_t idesc_i8(int M, int N) {
 // ---------------------------------------------------------------------------------------------
 template <int S>
 __global__ void __launch_bounds__(256)
-split_i8_kernel(const double* __restrict__ src, int64_t cols, int64_t ld, int8_t* __restrict__ planes, int64_t ldp,
-                int64_t plane_stride, double* __restrict__ row_scale) {
-  __shared__ double red[8];
-  const int64_t row = blockIdx.x;
-  const double* x = src + row * ld;
-  const int tid = threadIdx.x;
-  double mx = 0.0;
-  for (int64_t c = (int64_t)tid * 2; c < cols; c += 512) {
-    const double2 v = *reinterpret_cast<const double2*>(x + c);
-    mx = fmax(mx, fmax(fabs(v.x), fabs(v.y)));
+split_i8_kernel(const double* __restrict__ src, int64_t cols, int64_t ld, int tile_rows, int8_t* __restrict__ planes,
+                double* __restrict__ row_scale) {
+  __shared__ int exps[8];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int64_t row0 = (int64_t)blockIdx.x * 8;
+  {
+    // warp w: maximum of row row0 + w
+    const double* x = src + (row0 + warp) * ld;
+    double mx = 0.0;
+    for (int64_t c = (int64_t)lane * 2; c < cols; c += 64) {
+      const double2 v = *reinterpret_cast<const double2*>(x + c);
+      mx = fmax(mx, fmax(fabs(v.x), fabs(v.y)));
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    int e = 0;
+    if (mx > 0.0) (void)frexp(mx, &e);              // mx = f 2^e, f in [0.5, 1): |x| 2^-e < 1
+    if (lane == 0) {
+      exps[warp] = e;
+      row_scale[row0 + warp] = ldexp(1.0, e);
+    }
   }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-  if ((tid & 31) == 0) red[tid >> 5] = mx;
   __syncthreads();
-  mx = red[0];
-#pragma unroll
-  for (int w = 1; w < 8; ++w) mx = fmax(mx, red[w]);
-  int e = 0;
-  if (mx > 0.0) (void)frexp(mx, &e);                // mx = f 2^e, f in [0.5, 1): |x| 2^-e < 1
-  if (tid == 0) row_scale[row] = ldexp(1.0, e);
-  const double sc = ldexp(1.0, 6 - e);              // t0 = 64 y
-  int8_t* out = planes + row * ldp;
-  for (int64_t c = (int64_t)tid * 16; c < cols; c += 256 * 16) {
+  const int rr = tid & 7;                           // row inside the 8-row group
+  const int64_t row = row0 + rr;
+  const double* x = src + row * ld;
+  const double sc = ldexp(1.0, 6 - exps[rr]);       // t0 = 64 y
+  const int64_t tile = row / tile_rows;
+  const int64_t plane_bytes = (int64_t)tile_rows * I8_KC;
+  const int64_t kchunks = cols / I8_KC;
+  // byte offset of (row, k = 0, plane 0) inside its tile's first k chunk
+  const int64_t row_off = ((row % tile_rows) / 8) * 256 + rr * 16;
+  for (int64_t j = tid >> 3; j < cols / 16; j += 32) {          // 16-column pieces of the row
     double t[16];
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-      const double2 v = *reinterpret_cast<const double2*>(x + c + 2 * i);
+      const double2 v = *reinterpret_cast<const double2*>(x + j * 16 + 2 * i);
       t[2 * i] = v.x * sc;
       t[2 * i + 1] = v.y * sc;
     }
+    int8_t* out = planes + ((tile * kchunks + (j >> 1)) * S) * plane_bytes + row_off + (j & 1) * 128;
 #pragma unroll
     for (int p = 0; p < S; ++p) {
       uint32_t w[4];
@@ -115,13 +132,16 @@ split_i8_kernel(const double* __restrict__ src, int64_t cols, int64_t ld, int8_t
         }
         w[q] = pack;
       }
-      *reinterpret_cast<uint4*>(out + (int64_t)p * plane_stride + c) = make_uint4(w[0], w[1], w[2], w[3]);
+      *reinterpret_cast<uint4*>(out + (int64_t)p * plane_bytes) = make_uint4(w[0], w[1], w[2], w[3]);
     }
   }
 }
 
 struct I8Args {
   int MT, NT;                          // 128-row tiles of K, 64-row tiles of Linv
+  const int8_t* a_tiles;               // [MT][kchunks][S][128 x 32 B]
+  const int8_t* b_tiles;               // [NT][kchunks][S][ 64 x 32 B]
+  int kchunks;                         // npad / 32
   const double* scale_a;               // [mpad]  2^eA_m
   const double* scale_b;               // [npad]  2^eB_j
   double* rn_partial; int rn_nt;       // [mpad x npad/64]
@@ -141,7 +161,7 @@ struct I8Cfg {
 
 template <int S>
 __global__ void __launch_bounds__(I8_THREADS, 1)
-trmm_i8_kernel(const I8Args p, const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b) {
+trmm_i8_kernel(const I8Args p) {
   using C = I8Cfg<S>;
   extern __shared__ unsigned char i8_smem_raw[];
   __shared__ uint64_t full_bar[C::STAGES], empty_bar[C::STAGES], done_bar;
@@ -182,13 +202,15 @@ trmm_i8_kernel(const I8Args p, const __grid_constant__ CUtensorMap tm_a, const _
   if (warp < 4) {
     if (tid == 0) {
       // ===================== TMA producer (one thread) =====================
+      const int8_t* a_src = p.a_tiles + (int64_t)mt * p.kchunks * C::A_BYTES;
+      const int8_t* b_src = p.b_tiles + (int64_t)nt * p.kchunks * C::B_BYTES;
       for (int it = 0; it < KT; ++it) {
         const int s = it % C::STAGES, u = it / C::STAGES;
         if (u > 0) mbarrier_wait(&empty_bar[s], (u - 1) & 1);     // the MMAs that read this slot are done
         const uint32_t st = ring + (uint32_t)s * C::STAGE_BYTES;
         expect_tx(&full_bar[s], C::STAGE_BYTES);
-        tma_load_3d(st, &tm_a, it * I8_KC, m0, 0, &full_bar[s]);
-        tma_load_3d(st + C::A_BYTES, &tm_b, it * I8_KC, n0, 0, &full_bar[s]);
+        bulk_load(st, a_src + (int64_t)it * C::A_BYTES, C::A_BYTES, &full_bar[s]);
+        bulk_load(st + C::A_BYTES, b_src + (int64_t)it * C::B_BYTES, C::B_BYTES, &full_bar[s]);
       }
     }
     __syncwarp();
@@ -227,20 +249,23 @@ trmm_i8_kernel(const I8Args p, const __grid_constant__ CUtensorMap tm_a, const _
     }
   } else if (warp == 4 && lane == 0) {
     // ===================== MMA issuer (one thread) =====================
-    const uint32_t idesc = idesc_i8(I8_TM, I8_TN);
+    // The B digit planes of a stage are contiguous in shared memory ([plane][64 rows][32 B]), i.e. ONE K-major
+    // operand of (S - p) x 64 rows, and group g = p + q lives at TMEM columns g x 64: a single MMA of A_p against
+    // planes q0..q0+c-1 (N = 64c <= 256) lands every product in its own group.  S(S+1)/2 plane products become
+    // ~S(S+1)/8 + S/2 instructions and A_p is read from shared memory once per <= 4 products instead of once each.
     for (int it = 0; it < KT; ++it) {
       const int s = it % C::STAGES, u = it / C::STAGES;
       mbarrier_wait(&full_bar[s], u & 1);
       fence_after();
       const uint32_t a0 = ring + (uint32_t)s * C::STAGE_BYTES, b0 = a0 + C::A_BYTES;
-      const uint64_t da0 = desc_sw32(a0), db0 = desc_sw32(b0);
+      const uint64_t da0 = desc_kmajor(a0), db0 = desc_kmajor(b0);
 #pragma unroll
-      for (int g = 0; g < S; ++g) {
+      for (int pa = 0; pa < S; ++pa) {
 #pragma unroll
-        for (int pa = 0; pa <= g; ++pa) {
-          const int qb = g - pa;
-          mma_i8(tmem + (uint32_t)(g * I8_TN), da0 + (uint64_t)((pa * C::A_PLANE) >> 4), db0 + (uint64_t)((qb * C::B_PLANE) >> 4),
-                 idesc, (it != 0 || pa != 0) ? 1u : 0u);
+        for (int q0 = 0; q0 < S - pa; q0 += 4) {
+          const int cnt = (S - pa - q0) < 4 ? (S - pa - q0) : 4;
+          mma_i8(tmem + (uint32_t)((pa + q0) * I8_TN), da0 + (uint64_t)((pa * C::A_PLANE) >> 4),
+                 db0 + (uint64_t)((q0 * C::B_PLANE) >> 4), idesc_i8(I8_TM, cnt * I8_TN), (it != 0 || pa != 0) ? 1u : 0u);
         }
       }
       commit_to(&empty_bar[s]);                                  // arrives when these MMAs have read the stage
@@ -255,44 +280,16 @@ trmm_i8_kernel(const I8Args p, const __grid_constant__ CUtensorMap tm_a, const _
   }
 }
 
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
-                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-EncodeTiledFn encode_fn() {
-  static EncodeTiledFn fn = nullptr;
-  if (!fn) {
-    void* p = nullptr;
-    cudaDriverEntryPointQueryResult q;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
-        q == cudaDriverEntryPointSuccess)
-      fn = (EncodeTiledFn)p;
-  }
-  return fn;
-}
-// int8 digit planes [S][rows][ld bytes]: boxes of 32 B x box_rows x S planes, SWIZZLE_32B
-int make_tmap3(CUtensorMap* tm, const int8_t* base, int64_t rows, int64_t cols, int64_t ld, int64_t plane_stride, int S,
-               int box_rows) {
-  EncodeTiledFn enc = encode_fn();
-  if (!enc) return ALGP_ERR_UNSUPPORTED;
-  cuuint64_t dims[3] = {(cuuint64_t)cols, (cuuint64_t)rows, (cuuint64_t)S};
-  cuuint64_t strides[2] = {(cuuint64_t)ld, (cuuint64_t)plane_stride};
-  cuuint32_t box[3] = {I8_KC, (cuuint32_t)box_rows, (cuuint32_t)S};
-  cuuint32_t estr[3] = {1, 1, 1};
-  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, (void*)base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                   CU_TENSOR_MAP_SWIZZLE_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  return r == CUDA_SUCCESS ? ALGP_OK : ALGP_ERR_INVALID;
-}
-
 template <int S>
-int launch_split(const double* src, int64_t rows, int64_t cols, int64_t ld, int8_t* planes, int64_t ldp, int64_t plane_stride,
-                 double* row_scale, cudaStream_t st) {
-  split_i8_kernel<S><<<(unsigned)rows, 256, 0, st>>>(src, cols, ld, planes, ldp, plane_stride, row_scale);
+int launch_split(const double* src, int64_t rows, int64_t cols, int64_t ld, int tile_rows, int8_t* planes, double* row_scale,
+                 cudaStream_t st) {
+  split_i8_kernel<S><<<(unsigned)(rows / 8), 256, 0, st>>>(src, cols, ld, tile_rows, planes, row_scale);
   ALGP_LAUNCH_CHECK();
   return ALGP_OK;
 }
 
 template <int S>
-int launch_trmm(const I8Args& a, const CUtensorMap& ta, const CUtensorMap& tb, cudaStream_t st) {
+int launch_trmm(const I8Args& a, cudaStream_t st) {
   using C = I8Cfg<S>;
   static bool configured = false;
   if (!configured) {
@@ -301,61 +298,58 @@ int launch_trmm(const I8Args& a, const CUtensorMap& ta, const CUtensorMap& tb, c
   }
   const int groups = (a.MT + 15) / 16;
   const int64_t grid = (int64_t)groups * 16 * a.NT;
-  trmm_i8_kernel<S><<<(unsigned)grid, I8_THREADS, C::SMEM_BYTES, st>>>(a, ta, tb);
+  trmm_i8_kernel<S><<<(unsigned)grid, I8_THREADS, C::SMEM_BYTES, st>>>(a);
   ALGP_LAUNCH_CHECK();
   return ALGP_OK;
 }
 
 }  // namespace
 
-extern "C" int algp_split_i8(const double* src, int64_t rows, int64_t cols, int64_t ld, int nslices, int8_t* planes,
-                             int64_t ldp, int64_t plane_stride, double* row_scale, void* stream) {
-  if (!src || !planes || !row_scale || rows < 0 || cols < 0 || (cols & 15) || (ld & 1) || (ldp & 15) || ld < cols ||
-      ldp < cols || plane_stride < rows * ldp || (plane_stride & 15) || nslices < 2 || nslices > I8_MAX_S)
+extern "C" int algp_split_i8(const double* src, int64_t rows, int64_t cols, int64_t ld, int nslices, int tile_rows,
+                             int8_t* planes, double* row_scale, void* stream) {
+  if (!src || !planes || !row_scale || rows < 0 || cols < 0 || (cols % I8_KC) || (ld & 1) || ld < cols ||
+      (tile_rows != I8_TM && tile_rows != I8_TN) || rows % tile_rows || nslices < 2 || nslices > I8_MAX_S)
     return ALGP_ERR_INVALID;
   if (((uintptr_t)src | (uintptr_t)planes) & 15) return ALGP_ERR_INVALID;
   if (rows == 0 || cols == 0) return ALGP_OK;
   cudaStream_t st = (cudaStream_t)stream;
   switch (nslices) {
-    case 2: return launch_split<2>(src, rows, cols, ld, planes, ldp, plane_stride, row_scale, st);
-    case 3: return launch_split<3>(src, rows, cols, ld, planes, ldp, plane_stride, row_scale, st);
-    case 4: return launch_split<4>(src, rows, cols, ld, planes, ldp, plane_stride, row_scale, st);
-    case 5: return launch_split<5>(src, rows, cols, ld, planes, ldp, plane_stride, row_scale, st);
-    case 6: return launch_split<6>(src, rows, cols, ld, planes, ldp, plane_stride, row_scale, st);
-    case 7: return launch_split<7>(src, rows, cols, ld, planes, ldp, plane_stride, row_scale, st);
-    default: return launch_split<8>(src, rows, cols, ld, planes, ldp, plane_stride, row_scale, st);
+    case 2: return launch_split<2>(src, rows, cols, ld, tile_rows, planes, row_scale, st);
+    case 3: return launch_split<3>(src, rows, cols, ld, tile_rows, planes, row_scale, st);
+    case 4: return launch_split<4>(src, rows, cols, ld, tile_rows, planes, row_scale, st);
+    case 5: return launch_split<5>(src, rows, cols, ld, tile_rows, planes, row_scale, st);
+    case 6: return launch_split<6>(src, rows, cols, ld, tile_rows, planes, row_scale, st);
+    case 7: return launch_split<7>(src, rows, cols, ld, tile_rows, planes, row_scale, st);
+    default: return launch_split<8>(src, rows, cols, ld, tile_rows, planes, row_scale, st);
   }
 }
 
-// rn_partial[m][t] (t < npad/64) = sum over 64-column tile t of (K Linv^T)[m][.]^2 from the digit planes
-extern "C" int algp_trmm_rt_i8(const int8_t* Kp, const double* Kscale, int64_t mpad, int64_t ldk, int64_t k_plane_stride,
-                               const int8_t* Lp, const double* Lscale, int64_t npad, int64_t ldl, int64_t l_plane_stride,
-                               int nslices, double* rn_partial, void* stream) {
-  if (!Kp || !Kscale || !Lp || !Lscale || !rn_partial || mpad % ALGP_BLK || npad % ALGP_BLK || ldk < npad || ldl < npad ||
-      (ldk & 15) || (ldl & 15) || (k_plane_stride & 15) || (l_plane_stride & 15) || nslices < 2 || nslices > I8_MAX_S ||
-      npad > 32768)
+// rn_partial[m][t] (t < npad/64) = sum over 64-column tile t of (K Linv^T)[m][.]^2 from the digit tiles
+extern "C" int algp_trmm_rt_i8(const int8_t* Kt, const double* Kscale, int64_t mpad, const int8_t* Lt, const double* Lscale,
+                               int64_t npad, int nslices, double* rn_partial, void* stream) {
+  if (!Kt || !Kscale || !Lt || !Lscale || !rn_partial || mpad % ALGP_BLK || npad % ALGP_BLK || nslices < 2 ||
+      nslices > I8_MAX_S || npad > 32768)
     return ALGP_ERR_INVALID;           // K <= 2^15 keeps every group sum below 2^31 (8 pairs x 2^15 x 2^12 = 2^30)
   if (mpad == 0 || npad == 0) return ALGP_OK;
-  if (((uintptr_t)Kp | (uintptr_t)Lp) & 15) return ALGP_ERR_INVALID;
-  CUtensorMap ta, tb;
-  int rc;
-  if ((rc = make_tmap3(&ta, Kp, mpad, npad, ldk, k_plane_stride, nslices, I8_TM))) return rc;
-  if ((rc = make_tmap3(&tb, Lp, npad, npad, ldl, l_plane_stride, nslices, I8_TN))) return rc;
+  if (((uintptr_t)Kt | (uintptr_t)Lt) & 15) return ALGP_ERR_INVALID;
   I8Args a;
   a.MT = (int)(mpad / I8_TM);
   a.NT = (int)(npad / I8_TN);
+  a.a_tiles = Kt;
+  a.b_tiles = Lt;
+  a.kchunks = (int)(npad / I8_KC);
   a.scale_a = Kscale;
   a.scale_b = Lscale;
   a.rn_partial = rn_partial;
   a.rn_nt = a.NT;
   cudaStream_t st = (cudaStream_t)stream;
   switch (nslices) {
-    case 2: return launch_trmm<2>(a, ta, tb, st);
-    case 3: return launch_trmm<3>(a, ta, tb, st);
-    case 4: return launch_trmm<4>(a, ta, tb, st);
-    case 5: return launch_trmm<5>(a, ta, tb, st);
-    case 6: return launch_trmm<6>(a, ta, tb, st);
-    case 7: return launch_trmm<7>(a, ta, tb, st);
-    default: return launch_trmm<8>(a, ta, tb, st);
+    case 2: return launch_trmm<2>(a, st);
+    case 3: return launch_trmm<3>(a, st);
+    case 4: return launch_trmm<4>(a, st);
+    case 5: return launch_trmm<5>(a, st);
+    case 6: return launch_trmm<6>(a, st);
+    case 7: return launch_trmm<7>(a, st);
+    default: return launch_trmm<8>(a, st);
   }
 }

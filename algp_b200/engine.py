@@ -190,26 +190,25 @@ class GPFactor(object):
              ptr(rn), stream())
         return rn
 
-    def split_i8(self, M, nslices):
-        """fp64 device matrix -> (planes int8 [nslices, rows, cols], row_scale [rows]) digit expansion for the
-        INT8 tensor-core path."""
+    def split_i8(self, M, nslices, tile_rows):
+        """fp64 device matrix -> (digit tiles int8 [rows*cols*nslices], row_scale [rows]) for the INT8
+        tensor-core path (tile_rows = 128: left operand, 64: right operand)."""
         rows, cols = M.shape
-        planes = torch.empty((nslices, rows, cols), dtype=torch.int8, device=M.device)
+        tiles = torch.empty(nslices * rows * cols, dtype=torch.int8, device=M.device)
         scale = torch.empty(rows, dtype=torch.float64, device=M.device)
-        call("algp_split_i8", ptr(M), rows, cols, M.stride(0), nslices, ptr(planes), cols, rows * cols, ptr(scale), stream())
-        return planes, scale
+        call("algp_split_i8", ptr(M), rows, cols, M.stride(0), nslices, tile_rows, ptr(tiles), ptr(scale), stream())
+        return tiles, scale
 
     def whiten_norm_i8(self, Ks, nslices=I8_SLICES):
         """Squared row norms of V = Ks L^-T per 64-column tile through exact INT8 digit GEMMs (fp64 tier)."""
         cache = getattr(self, "_linv_i8", None)
         if cache is None or cache[0] != nslices:
-            self._linv_i8 = cache = (nslices,) + self.split_i8(self.Linv, nslices)
-        _, lp, ls = cache
-        kp, ks = self.split_i8(Ks, nslices)
+            self._linv_i8 = cache = (nslices,) + self.split_i8(self.Linv, nslices, 64)
+        _, lt, ls = cache
+        kt, ks = self.split_i8(Ks, nslices, 128)
         Mpad = Ks.shape[0]
         rn = torch.empty((Mpad, self.Npad // 64), dtype=torch.float64, device=Ks.device)
-        call("algp_trmm_rt_i8", ptr(kp), ptr(ks), Mpad, kp.stride(1), kp.stride(0), ptr(lp), ptr(ls), self.Npad,
-             lp.stride(1), lp.stride(0), nslices, ptr(rn), stream())
+        call("algp_trmm_rt_i8", ptr(kt), ptr(ks), Mpad, ptr(lt), ptr(ls), self.Npad, nslices, ptr(rn), stream())
         return rn
 
     def mean_var(self, xs, y0, ymean, test_var=None, want_var=True, max_rows=65536, precision="fp64"):

@@ -90,17 +90,18 @@ int algp_trmm_rt_tf32(const float* Khi, const float* Klo, int64_t mpad, int64_t 
 
 /* ---- K2'': fp64-grade variance on the INT8 tensor cores (tcgen05 kind::i8, exact s32 accumulation) ---- */
 /* fp64 matrix -> `nslices` (2..8) signed base-128 digit planes of every row scaled by a power of two:
- * src[r][c] = row_scale[r] * sum_p planes[p][r][c] * 2^(-6-7p) (+ a remainder below 2^(-7 nslices) row_scale[r]).
- * planes is [nslices][rows][ldp] bytes (plane_stride bytes apart), cols % 16 == 0. */
-int algp_split_i8(const double* src, int64_t rows, int64_t cols, int64_t ld, int nslices, int8_t* planes,
-                  int64_t ldp, int64_t plane_stride, double* row_scale, void* stream);
-/* Same row-norm partials as algp_trmm_rt (rn_partial[m][t], t < npad/64) from the digit planes of K [mpad x npad]
- * and Linv [npad x npad]: the digit products are exact integer GEMMs, groups of equal weight are summed in
- * fp64 (error ~ 2^(-7 nslices) of the row scales): the fp64 tier of the variance (utils.py:305-308) at
- * several times the DMMA rate.  npad <= 32768. */
-int algp_trmm_rt_i8(const int8_t* Kp, const double* Kscale, int64_t mpad, int64_t ldk, int64_t k_plane_stride,
-                    const int8_t* Lp, const double* Lscale, int64_t npad, int64_t ldl, int64_t l_plane_stride,
-                    int nslices, double* rn_partial, void* stream);
+ * src[r][c] = row_scale[r] * sum_p digit_p[r][c] * 2^(-6-7p) (+ a remainder below 2^(-7 nslices) row_scale[r]).
+ * The digits are written in the tensor core's operand layout, tile by tile (rows * cols * nslices bytes):
+ *   [row tile of tile_rows][32-column k chunk][plane][row group of 8][k half][8 rows][16 B]
+ * tile_rows = 128 for the left operand (K), 64 for the right one (Linv); rows % tile_rows == 0, cols % 32 == 0. */
+int algp_split_i8(const double* src, int64_t rows, int64_t cols, int64_t ld, int nslices, int tile_rows,
+                  int8_t* planes, double* row_scale, void* stream);
+/* Same row-norm partials as algp_trmm_rt (rn_partial[m][t], t < npad/64) from the digit tiles of K [mpad x npad]
+ * (tile_rows 128) and Linv [npad x npad] (tile_rows 64): the digit products are exact integer GEMMs, groups of
+ * equal weight are summed in fp64 (error ~ 2^(-7 nslices) of the row scales): the fp64 tier of the variance
+ * (utils.py:305-308) at several times the DMMA rate.  npad <= 32768. */
+int algp_trmm_rt_i8(const int8_t* Kt, const double* Kscale, int64_t mpad, const int8_t* Lt, const double* Lscale,
+                    int64_t npad, int nslices, double* rn_partial, void* stream);
 
 /* ---- K4: marginal-likelihood gradient (GPR.fit, models.py:145-158) ---------- */
 /* Ainv (lower triangle) = Linv^T Linv = A^-1 */

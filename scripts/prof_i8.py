@@ -1,5 +1,5 @@
 """Time / check the INT8 digit variance path against the DMMA path (dev + ncu target)."""
-import sys, time
+import sys, time, subprocess
 import numpy as np, torch
 sys.path.insert(0, ".")
 from algp_b200 import engine
@@ -25,20 +25,22 @@ def timed(fn, reps=3):
         best = min(best, e0.elapsed_time(e1))
     return best, out
 flops = float(f.Npad) ** 2 * Ks.shape[0]
+smi = subprocess.Popen(["nvidia-smi", "--query-gpu=clocks.sm,power.draw,clocks_throttle_reasons.active", "--format=csv,noheader",
+                        "-lms", "50"], stdout=open("gpurun_out/i8_smi.log", "w"))
 if check:
     t64, (_, rn64) = timed(lambda: f.whiten(Ks, want_V=False), reps=2)
     ref = rn64.sum(1)
     print("fp64 DMMA: %.2f ms  %.1f TFLOP/s" % (t64, flops / t64 / 1e9))
 for S in slices:
-    ts, _ = timed(lambda: f.split_i8(Ks, S))
+    ts, _ = timed(lambda: f.split_i8(Ks, S, 128))
     f._linv_i8 = None
     t8, rn8 = timed(lambda: f.whiten_norm_i8(Ks, nslices=S))
-    kp, ks = f.split_i8(Ks, S)
+    kp, ks = f.split_i8(Ks, S, 128)
     _, lp, ls = f._linv_i8
     def mm():
         rn = torch.empty((Ks.shape[0], f.Npad // 64), dtype=torch.float64, device=Ks.device)
-        engine.call("algp_trmm_rt_i8", engine.ptr(kp), engine.ptr(ks), Ks.shape[0], kp.stride(1), kp.stride(0), engine.ptr(lp),
-                    engine.ptr(ls), f.Npad, lp.stride(1), lp.stride(0), S, engine.ptr(rn), engine.stream())
+        engine.call("algp_trmm_rt_i8", engine.ptr(kp), engine.ptr(ks), Ks.shape[0], engine.ptr(lp), engine.ptr(ls), f.Npad, S,
+                    engine.ptr(rn), engine.stream())
         return rn
     tm, _ = timed(mm)
     ops = flops * S * (S + 1) / 2
@@ -47,3 +49,11 @@ for S in slices:
     if check:
         msg += "  max|d rn| = %.3e" % float((rn8.sum(1) - ref).abs().max())
     print(msg)
+smi.terminate()
+import collections
+rows = [l.strip().split(", ") for l in open("gpurun_out/i8_smi.log") if l.strip()]
+busy = [r for r in rows if float(r[1].split()[0]) > 500]
+if busy:
+    mhz = sorted(int(r[0].split()[0]) for r in busy)
+    print("under load (>500 W): %d samples, SM MHz median %d min %d, power max %.0f W, reasons %s" % (
+        len(busy), mhz[len(mhz) // 2], mhz[0], max(float(r[1].split()[0]) for r in busy), collections.Counter(r[2] for r in busy)))

@@ -268,16 +268,23 @@ def test_variance_tf32_tier(N, M):
 
 
 # ---------------------------------------------------------------- INT8 digit mode (tcgen05 kind::i8)
-@pytest.mark.parametrize("S", [2, 5, 7, 8])
-def test_split_i8_planes(S):
+def untile_i8(tiles, rows, cols, S, tile_rows):
+    """[row tile][32-col k chunk][plane][row group][k half][8 rows][16 B] (include/algp_b200.h) -> [S, rows, cols]"""
+    t = tiles.reshape(rows // tile_rows, cols // 32, S, tile_rows // 8, 2, 8, 16)
+    return t.transpose(2, 0, 3, 5, 1, 4, 6).reshape(S, rows, cols)
+
+
+@pytest.mark.parametrize("S,tile_rows", [(2, 128), (5, 64), (7, 128), (8, 64)])
+def test_split_i8_planes(S, tile_rows):
     """Digit expansion: |d| <= 64 and the planes reconstruct every row to 2^(-7S) of its scale."""
     rng = np.random.default_rng(S)
     M = rng.normal(size=(256, 384)) * np.exp(rng.normal(size=(256, 384)) * 3)
     M[3] = 0.0                                           # an all-zero row
     M[5, 7] = 1.0; M[5, 8:] *= 1e-30                     # power-of-two row maximum
     f = engine.GPFactor.__new__(engine.GPFactor)
-    planes, scale = engine.GPFactor.split_i8(f, dev(M), S)
-    planes, scale = planes.cpu().numpy().astype(np.float64), scale.cpu().numpy()
+    tiles, scale = engine.GPFactor.split_i8(f, dev(M), S, tile_rows)
+    planes = untile_i8(tiles.cpu().numpy(), 256, 384, S, tile_rows).astype(np.float64)
+    scale = scale.cpu().numpy()
     assert planes.shape == (S, 256, 384) and np.abs(planes).max() <= 64
     mx = np.abs(M).max(axis=1)
     nz = mx > 0
