@@ -17,7 +17,7 @@ from . import _lib
 from ._lib import call, ptr, stream
 
 BLK = 128
-I8_SLICES = 8          # digit planes of the INT8 variance path: 8 x 7 bits covers the fp64 mantissa
+I8_SLICES = 7          # digit planes of the INT8 variance path: 7 x 7 = 49 bits below each row's scale (8 = 56 bits)
 CONST = 0.5 * np.log(2 * np.pi * np.exp(1))        # utils.py:10
 KIND = {"rbf": 0, None: 0, "matern": 1}
 

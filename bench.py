@@ -276,6 +276,21 @@ def fit_predict_bench(torch, engine, n_train, grid_side, reps, peak_hbm):
             times["variance_tf32"].append(t0.elapsed_time(t1))
         del rn32
     tf32_err = float((v32 - v).abs().max().item())
+    # INT8 digit mode of the same step (fp64 tier): digit split of K(X*,X) and Linv + exact tcgen05 kind::i8 GEMMs
+    times["variance_i8"] = []
+    for rep in range(reps + 1):
+        f._linv_i8 = None
+        t0, t1 = ev(), ev()
+        t0.record()
+        rn8 = f.whiten_norm_i8(Ks)
+        v8 = engine.rowsum(rn8, -1.0, hy.outputscale, None, rows=M)
+        t1.record()
+        torch.cuda.synchronize()
+        if rep:
+            times["variance_i8"].append(t0.elapsed_time(t1))
+        del rn8
+    i8_err = float((v8 - v).abs().max().item())
+    f._linv_i8 = None
     sampler.__exit__()
     # end to end through the reference-facing call with HOST arrays (utils.py:293): H2D of x / y / var / grid,
     # kernel build + factor + solve + variance, D2H of mean and variance, fresh factor every call
@@ -288,7 +303,7 @@ def fit_predict_bench(torch, engine, n_train, grid_side, reps, peak_hbm):
         gp.model.kernel_covar_module.base_kernel.log_lengthscale.copy_(torch.tensor(hy.log_ls).view(1, 1, -1))
         gp.model.kernel_covar_module.log_outputscale.fill_(hy.log_os)
         gp.likelihood.log_noise.fill_(hy.log_noise)
-    for mode in ("fp64", "tf32"):
+    for mode in ("fp64", "i8", "tf32"):
         gp.precision = mode
         ts = []
         for rep in range(reps + 1):
@@ -304,9 +319,11 @@ def fit_predict_bench(torch, engine, n_train, grid_side, reps, peak_hbm):
     N = float(max(128, engine.pad_to(n_train)))
     Mp = float(max(128, engine.pad_to(M)))
     out = {"n_train": n_train, "n_test": M, "ms": med["total"],
+           "ms_i8_mode": med["total"] - med["variance_trmm"] + med["variance_i8"],
            "ms_tf32_mode": med["total"] - med["variance_trmm"] + med["variance_tf32"],
            "e2e_ms_host_arrays": e2e, "clocks": sampler.summary(),
-           "tf32_max_abs_var_diff_vs_fp64": tf32_err, "ms_by_stage": med,
+           "tf32_max_abs_var_diff_vs_fp64": tf32_err, "i8_max_abs_var_diff_vs_fp64": i8_err,
+           "i8_digit_planes": engine.I8_SLICES, "ms_by_stage": med,
            "var_min": float(v.min().item()), "var_max": float(v.max().item()),
            "rooflines": {
                "kbuild_train": {"bound": "hbm", "achieved": 8 * N * N / med["kbuild_train"] / 1e6, "peak": peak_hbm, "unit": "GB/s"},
@@ -314,6 +331,9 @@ def fit_predict_bench(torch, engine, n_train, grid_side, reps, peak_hbm):
                "potrf": {"bound": "fp64 tensor (DMMA)", "achieved": N ** 3 / 3 / med["potrf"] / 1e9, "unit": "TFLOP/s"},
                "trtri": {"bound": "fp64 tensor (DMMA)", "achieved": N ** 3 / 3 / med["trtri"] / 1e9, "unit": "TFLOP/s"},
                "variance_trmm": {"bound": "fp64 tensor (DMMA)", "achieved": N * N * Mp / med["variance_trmm"] / 1e9, "unit": "TFLOP/s"},
+               "variance_i8": {"bound": "int8 tensor (tcgen05 kind::i8), S(S+1)/2 exact digit GEMMs per product, incl. the digit split passes",
+                               "achieved": engine.I8_SLICES * (engine.I8_SLICES + 1) / 2 * N * N * Mp / med["variance_i8"] / 1e9,
+                               "unit": "TOP/s(int8)", "effective_fp64_equiv_tflops": N * N * Mp / med["variance_i8"] / 1e9},
                "variance_tf32": {"bound": "tf32 tensor (tcgen05), 3 MMAs per product, incl. the hi/lo split passes",
                                  "achieved": 3 * N * N * Mp / med["variance_tf32"] / 1e9, "unit": "TFLOP/s(tf32)",
                                  "effective_fp64_equiv_tflops": N * N * Mp / med["variance_tf32"] / 1e9},
@@ -406,6 +426,27 @@ def tf32_gemm_peak(torch, n=8192, reps=3):
         return 2.0 * n ** 3 / best / 1e9
     finally:
         torch.backends.cuda.matmul.allow_tf32 = old
+
+
+def int8_gemm_peak(torch, n=8192, reps=3):
+    """cuBLASLt int8 x int8 -> int32 GEMM throughput (TOP/s) through torch._int_mm: the roofline denominator of the
+    INT8 digit mode (the driver's MEASURED_PEAKS.json has no int8 figure).  None if the library path is unavailable."""
+    try:
+        a = torch.randint(-64, 64, (n, n), dtype=torch.int8, device="cuda")
+        b = torch.randint(-64, 64, (n, n), dtype=torch.int8, device="cuda")
+        torch._int_mm(a, b)
+        torch.cuda.synchronize()
+        best = 1e30
+        for _ in range(reps):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            torch._int_mm(a, b)
+            e1.record()
+            torch.cuda.synchronize()
+            best = min(best, e0.elapsed_time(e1))
+        return 2.0 * n ** 3 / best / 1e9
+    except Exception:
+        return None
 
 
 def run_ours(args, rank, world, local_rank):
@@ -536,6 +577,8 @@ def run_ours(args, rank, world, local_rank):
                 fits.append(fit_predict_bench(torch, engine, 16384, 256, 2, peak_hbm))
             tf32_peak = tf32_gemm_peak(torch)
             extra["tf32_gemm_peak_tflops_cublas_8192"] = tf32_peak
+            i8_peak = int8_gemm_peak(torch)
+            extra["int8_gemm_peak_tops_cublaslt_8192"] = i8_peak
             for f in fits:
                 for r in f["rooflines"].values():
                     if r["unit"] == "TFLOP/s":
@@ -547,6 +590,10 @@ def run_ours(args, rank, world, local_rank):
                     elif r["unit"].startswith("TFLOP/s(tf32)"):
                         r["peak"] = tf32_peak
                         r["frac"] = r["achieved"] / tf32_peak
+                    elif r["unit"].startswith("TOP/s(int8)"):
+                        r["peak"] = i8_peak if i8_peak else 4500.0
+                        r["peak_kind"] = "cuBLASLt int8 GEMM burst" if i8_peak else "nominal dense int8"
+                        r["frac"] = r["achieved"] / r["peak"]
             extra["fit_predict"] = fits
         except Exception as e:       # the headline line must still print
             extra["fit_predict_error"] = repr(e)

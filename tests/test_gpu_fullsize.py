@@ -98,9 +98,11 @@ def test_fit_n16384_properties():
     # variance: bounds, and the tcgen05 TF32 mode agrees with fp64 at its tier
     mu, v64 = f.mean_var(dev(xs), dev(y - y.mean()), float(y.mean()))
     _, v32 = f.mean_var(dev(xs), dev(y - y.mean()), float(y.mean()), precision="tf32")
-    v64, v32 = v64.cpu().numpy(), v32.cpu().numpy()
+    _, v8 = f.mean_var(dev(xs), dev(y - y.mean()), float(y.mean()), precision="i8")
+    v64, v32, v8 = v64.cpu().numpy(), v32.cpu().numpy(), v8.cpu().numpy()
     assert (v64 > 0).all() and (v64 <= 1.0 + 1e-12).all()
     np.testing.assert_allclose(v32, v64, rtol=0, atol=3e-4)         # 2e-4 s^2 at N=16384
+    np.testing.assert_allclose(v8, v64, rtol=0, atol=1e-10)         # INT8 digit mode: fp64 tier (1e-9 s^2) with margin
     # the mean interpolates the data to within a few noise standard deviations at training points
     mu_tr, _ = f.mean_var(dev(x[:2048]), dev(y - y.mean()), float(y.mean()), want_var=False)
     assert np.abs(mu_tr.cpu().numpy() - y[:2048]).max() < 1.0
