@@ -252,17 +252,15 @@ static int potrf_panel(double* A, int64_t ld, double* Linv, int64_t ldi, int j, 
   return gemm_f64_launch(g, LAY_KMAJ, LAY_KMAJ, 1, st);
 }
 
-extern "C" int algp_potrf(double* A, int64_t npad, int64_t ld, double* Linv, int64_t ldi, int* info_dev, void* stream) {
-  if (!A || !Linv || !info_dev || npad < 0 || npad % ALGP_BLK || ld < npad || ldi < npad || (ld & 1) || (ldi & 1))
-    return ALGP_ERR_INVALID;
-  cudaStream_t st = (cudaStream_t)stream;
+// Factor the npad x npad block at A (diagonal 128-blocks of Linv receive inv(L_jj)).  *info_dev is NOT reset:
+// a failing pivot records col0 + column + 1 unless an earlier failure is already recorded.
+int potrf_block(double* A, int64_t npad, int64_t ld, double* Linv, int64_t ldi, int* info_dev, int col0, cudaStream_t st) {
   PotrfAux* ax = nullptr;
   int rc = potrf_aux_get(&ax);
   if (rc) return rc;
-  ALGP_CUDA(cudaMemsetAsync(info_dev, 0, sizeof(int), st));
   const int nb = (int)(npad / ALGP_BLK);
   if (nb == 0) return ALGP_OK;
-  rc = potf2inv_launch(A, ld, Linv, ldi, 0, info_dev, st);
+  rc = potf2inv_launch(A, ld, Linv, ldi, col0, info_dev, st);
   if (rc) return rc;
   rc = potrf_panel(A, ld, Linv, ldi, 0, nb, st);
   if (rc) return rc;
@@ -282,7 +280,7 @@ extern "C" int algp_potrf(double* A, int64_t npad, int64_t ld, double* Linv, int
     ALGP_CUDA(cudaEventRecord(ax->col_ready, st));
     ALGP_CUDA(cudaStreamWaitEvent(ax->aux, ax->col_ready, 0));
     rc = potf2inv_launch(A + (int64_t)(j + 1) * ALGP_BLK * (ld + 1), ld, Linv + (int64_t)(j + 1) * ALGP_BLK * (ldi + 1), ldi,
-                         (j + 1) * ALGP_BLK, info_dev, ax->aux);
+                         col0 + (j + 1) * ALGP_BLK, info_dev, ax->aux);
     if (rc) return rc;
     rc = potrf_panel(A, ld, Linv, ldi, j + 1, nb, ax->aux);
     if (rc) return rc;
@@ -300,6 +298,14 @@ extern "C" int algp_potrf(double* A, int64_t npad, int64_t ld, double* Linv, int
     ALGP_CUDA(cudaStreamWaitEvent(st, ax->panel_ready, 0));
   }
   return ALGP_OK;
+}
+
+extern "C" int algp_potrf(double* A, int64_t npad, int64_t ld, double* Linv, int64_t ldi, int* info_dev, void* stream) {
+  if (!A || !Linv || !info_dev || npad < 0 || npad % ALGP_BLK || ld < npad || ldi < npad || (ld & 1) || (ldi & 1))
+    return ALGP_ERR_INVALID;
+  cudaStream_t st = (cudaStream_t)stream;
+  ALGP_CUDA(cudaMemsetAsync(info_dev, 0, sizeof(int), st));
+  return potrf_block(A, npad, ld, Linv, ldi, info_dev, 0, st);
 }
 
 // ---------------------------------------------------------------------------

@@ -30,12 +30,9 @@
 //                     groups, column scale, square, row sum -- V is never written.  k-range stops at the
 //                     tile's last column (Linv is lower triangular).
 #include "common.cuh"
+#include "i8.cuh"
 
-#define I8_TM 128
-#define I8_TN 64
-#define I8_KC 32                        // bytes (= int8 digits) of k per row per stage = one MMA's K
 #define I8_THREADS 160
-#define I8_MAX_S 8
 
 namespace {
 
@@ -137,16 +134,6 @@ split_i8_kernel(const double* __restrict__ src, int64_t cols, int64_t ld, int ti
   }
 }
 
-struct I8Args {
-  int MT, NT;                          // 128-row tiles of K, 64-row tiles of Linv
-  const int8_t* a_tiles;               // [MT][kchunks][S][128 x 32 B]
-  const int8_t* b_tiles;               // [NT][kchunks][S][ 64 x 32 B]
-  int kchunks;                         // npad / 32
-  const double* scale_a;               // [mpad]  2^eA_m
-  const double* scale_b;               // [npad]  2^eB_j
-  double* rn_partial; int rn_nt;       // [mpad x npad/64]
-};
-
 template <int S>
 struct I8Cfg {
   static constexpr int A_PLANE = I8_TM * I8_KC;                       // 4 KB
@@ -159,9 +146,11 @@ struct I8Cfg {
   static constexpr int TMEM_COLS = (S * I8_TN > 256) ? 512 : ((S * I8_TN > 128) ? 256 : 128);
 };
 
-template <int S>
+// MODE 0: row sums of squares per 64-column tile (variance path, nothing else is written)
+// MODE 1: C = alpha A B^T + beta C (optionally stored transposed)
+template <int S, int MODE>
 __global__ void __launch_bounds__(I8_THREADS, 1)
-trmm_i8_kernel(const I8Args p) {
+gemm_i8_kernel(const I8Gemm p) {
   using C = I8Cfg<S>;
   extern __shared__ unsigned char i8_smem_raw[];
   __shared__ uint64_t full_bar[C::STAGES], empty_bar[C::STAGES], done_bar;
@@ -170,16 +159,23 @@ trmm_i8_kernel(const I8Args p) {
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const uint32_t ring = (s_u32(i8_smem_raw) + 1023u) & ~1023u;
 
-  // tile map: groups of 16 m-tiles sweep the n-tiles together, long (large nt) tiles first, so concurrent
-  // CTAs stream the same k-window of the K digits and the same Linv rows through L2
+  // tile map: groups of 16 m-tiles sweep the n-tiles together, so concurrent CTAs stream the same k-window of
+  // the A digits and the same B rows through L2; the order flags put the tiles with the longest k-range first
   constexpr int GM = 16;
-  const int per_group = GM * p.NT;
-  const int mg = blockIdx.x / per_group, rem = blockIdx.x % per_group;
-  const int nt = p.NT - 1 - rem / GM;
+  const int per_group = GM * p.NT, groups = (p.MT + GM - 1) / GM;
+  int mg = blockIdx.x / per_group;
+  const int rem = blockIdx.x % per_group;
+  if (p.mt_desc) mg = groups - 1 - mg;
+  const int nt = p.nt_desc ? p.NT - 1 - rem / GM : rem / GM;
   const int mt = mg * GM + rem % GM;
-  const bool valid_tile = mt < p.MT;                 // block-uniform
   const int m0 = mt * I8_TM, n0 = nt * I8_TN;
-  const int KT = valid_tile ? (n0 + I8_TN) / I8_KC : 0;   // Linv[j][k] = 0 for k > j
+  bool valid_tile = mt < p.MT;                       // block-uniform
+  if (p.lower_only && n0 >= m0 + I8_TM) valid_tile = false;
+  int kbeg = 0, kend = p.kchunks;
+  if (p.kbeg_rule == I8_KB_NT) kbeg = n0 / I8_KC;                                  // B[j][k] = 0 for k < j
+  if (p.kend_rule == I8_KE_NT) kend = min(kend, (n0 + I8_TN) / I8_KC);             // B[j][k] = 0 for k > j
+  if (p.kend_rule == I8_KE_MT) kend = min(kend, (m0 + I8_TM) / I8_KC);             // A[i][k] = 0 for k > i
+  const int KT = valid_tile ? max(kend - kbeg, 0) : 0;
 
   if (tid == 0) {
     for (int s = 0; s < C::STAGES; ++s) {
@@ -202,8 +198,8 @@ trmm_i8_kernel(const I8Args p) {
   if (warp < 4) {
     if (tid == 0) {
       // ===================== TMA producer (one thread) =====================
-      const int8_t* a_src = p.a_tiles + (int64_t)mt * p.kchunks * C::A_BYTES;
-      const int8_t* b_src = p.b_tiles + (int64_t)nt * p.kchunks * C::B_BYTES;
+      const int8_t* a_src = p.a_tiles + ((int64_t)mt * p.kchunks + kbeg) * C::A_BYTES;
+      const int8_t* b_src = p.b_tiles + ((int64_t)nt * p.kchunks + kbeg) * C::B_BYTES;
       for (int it = 0; it < KT; ++it) {
         const int s = it % C::STAGES, u = it / C::STAGES;
         if (u > 0) mbarrier_wait(&empty_bar[s], (u - 1) & 1);     // the MMAs that read this slot are done
@@ -216,36 +212,67 @@ trmm_i8_kernel(const I8Args p) {
     __syncwarp();
     // ===================== epilogue =====================
     if (valid_tile) {
-      mbarrier_wait(&done_bar, 0);
-      fence_after();
       const int row = warp * 32 + lane;                          // TMEM lane = accumulator row
+      const double sa = p.scale_a[m0 + row] * (1.0 / 4096.0);   // 2^(eA_m - 12)
+      if (KT > 0) {
+        mbarrier_wait(&done_bar, 0);
+        fence_after();
+      }
       double ss = 0.0;
 #pragma unroll 1
       for (int c0 = 0; c0 < I8_TN; c0 += 16) {
         double v[16];
 #pragma unroll
         for (int i = 0; i < 16; ++i) v[i] = 0.0;
+        if (KT > 0) {
 #pragma unroll
-        for (int g = S - 1; g >= 0; --g) {
-          uint32_t r[16];
-          const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)(g * I8_TN + c0);
-          asm volatile(
-              "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-              : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-                "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-              : "r"(taddr));
-          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+          for (int g = S - 1; g >= 0; --g) {
+            uint32_t r[16];
+            const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)(g * I8_TN + c0);
+            asm volatile(
+                "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+                  "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+                : "r"(taddr));
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-          for (int i = 0; i < 16; ++i) v[i] = fma(v[i], 0.0078125, (double)(int)r[i]);   // Horner in 2^-7
+            for (int i = 0; i < 16; ++i) v[i] = fma(v[i], 0.0078125, (double)(int)r[i]);   // Horner in 2^-7
+          }
         }
+        if (MODE == 0) {
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          const double t = v[i] * sb_s[c0 + i];
-          ss = fma(t, t, ss);
+          for (int i = 0; i < 16; ++i) {
+            const double t = v[i] * sb_s[c0 + i];
+            ss = fma(t, t, ss);
+          }
+        } else {
+          const double as = p.alpha * sa;
+          if (!p.transposed) {
+            // thread = row: 16 consecutive doubles (one 128-byte line) per chunk
+            double* crow = p.C + (int64_t)(m0 + row) * p.ldc + n0 + c0;
+#pragma unroll
+            for (int i = 0; i < 16; i += 2) {
+              double2 o = make_double2(v[i] * sb_s[c0 + i] * as, v[i + 1] * sb_s[c0 + i + 1] * as);
+              if (p.beta != 0.0) {
+                const double2 old = *reinterpret_cast<const double2*>(crow + i);
+                o.x = fma(p.beta, old.x, o.x);
+                o.y = fma(p.beta, old.y, o.y);
+              }
+              *reinterpret_cast<double2*>(crow + i) = o;
+            }
+          } else {
+            // C^T: the 32 lanes of a warp are 32 consecutive elements of one row of the transposed matrix
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              double* ct = p.C + (int64_t)(n0 + c0 + i) * p.ldc + m0 + row;
+              double o = v[i] * sb_s[c0 + i] * as;
+              if (p.beta != 0.0) o = fma(p.beta, *ct, o);
+              *ct = o;
+            }
+          }
         }
       }
-      const double sa = p.scale_a[m0 + row] * (1.0 / 4096.0);   // 2^(eA_m - 12)
-      p.rn_partial[(int64_t)(m0 + row) * p.rn_nt + nt] = ss * sa * sa;
+      if (MODE == 0) p.rn_partial[(int64_t)(m0 + row) * p.rn_nt + nt] = ss * sa * sa;
     }
   } else if (warp == 4 && lane == 0) {
     // ===================== MMA issuer (one thread) =====================
@@ -270,7 +297,7 @@ trmm_i8_kernel(const I8Args p) {
       }
       commit_to(&empty_bar[s]);                                  // arrives when these MMAs have read the stage
     }
-    if (valid_tile) commit_to(&done_bar);                        // accumulators complete
+    if (KT > 0) commit_to(&done_bar);                            // accumulators complete
   }
 
   fence_before();
@@ -288,31 +315,30 @@ int launch_split(const double* src, int64_t rows, int64_t cols, int64_t ld, int 
   return ALGP_OK;
 }
 
-template <int S>
-int launch_trmm(const I8Args& a, cudaStream_t st) {
+template <int S, int MODE>
+int launch_gemm(const I8Gemm& a, cudaStream_t st) {
   using C = I8Cfg<S>;
   static bool configured = false;
   if (!configured) {
-    ALGP_CUDA(cudaFuncSetAttribute(trmm_i8_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+    ALGP_CUDA(cudaFuncSetAttribute(gemm_i8_kernel<S, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
     configured = true;
   }
   const int groups = (a.MT + 15) / 16;
   const int64_t grid = (int64_t)groups * 16 * a.NT;
-  trmm_i8_kernel<S><<<(unsigned)grid, I8_THREADS, C::SMEM_BYTES, st>>>(a);
+  gemm_i8_kernel<S, MODE><<<(unsigned)grid, I8_THREADS, C::SMEM_BYTES, st>>>(a);
   ALGP_LAUNCH_CHECK();
   return ALGP_OK;
 }
 
 }  // namespace
 
-extern "C" int algp_split_i8(const double* src, int64_t rows, int64_t cols, int64_t ld, int nslices, int tile_rows,
-                             int8_t* planes, double* row_scale, void* stream) {
+int i8_split(const double* src, int64_t rows, int64_t cols, int64_t ld, int nslices, int tile_rows, int8_t* planes,
+             double* row_scale, cudaStream_t st) {
   if (!src || !planes || !row_scale || rows < 0 || cols < 0 || (cols % I8_KC) || (ld & 1) || ld < cols ||
       (tile_rows != I8_TM && tile_rows != I8_TN) || rows % tile_rows || nslices < 2 || nslices > I8_MAX_S)
     return ALGP_ERR_INVALID;
   if (((uintptr_t)src | (uintptr_t)planes) & 15) return ALGP_ERR_INVALID;
   if (rows == 0 || cols == 0) return ALGP_OK;
-  cudaStream_t st = (cudaStream_t)stream;
   switch (nslices) {
     case 2: return launch_split<2>(src, rows, cols, ld, tile_rows, planes, row_scale, st);
     case 3: return launch_split<3>(src, rows, cols, ld, tile_rows, planes, row_scale, st);
@@ -324,15 +350,47 @@ extern "C" int algp_split_i8(const double* src, int64_t rows, int64_t cols, int6
   }
 }
 
+// C (or row-norm partials) from digit tiles; see I8Gemm in i8.cuh
+int i8_gemm(const I8Gemm& a, int nslices, cudaStream_t st) {
+  if (!a.a_tiles || !a.b_tiles || !a.scale_a || !a.scale_b || a.MT < 0 || a.NT < 0 || a.kchunks < 0 || nslices < 2 ||
+      nslices > I8_MAX_S || a.kchunks > 32768 / I8_KC)
+    return ALGP_ERR_INVALID;           // K <= 2^15 keeps every group sum below 2^31 (8 pairs x 2^15 x 2^12 = 2^30)
+  if (a.MT == 0 || a.NT == 0) return ALGP_OK;
+  if (((uintptr_t)a.a_tiles | (uintptr_t)a.b_tiles) & 15) return ALGP_ERR_INVALID;
+  if (a.C) {
+    if (a.rn_partial || a.ldc < 2 || (a.ldc & 1) || ((uintptr_t)a.C & 15)) return ALGP_ERR_INVALID;
+    switch (nslices) {
+      case 2: return launch_gemm<2, 1>(a, st);
+      case 3: return launch_gemm<3, 1>(a, st);
+      case 4: return launch_gemm<4, 1>(a, st);
+      case 5: return launch_gemm<5, 1>(a, st);
+      case 6: return launch_gemm<6, 1>(a, st);
+      case 7: return launch_gemm<7, 1>(a, st);
+      default: return launch_gemm<8, 1>(a, st);
+    }
+  }
+  if (!a.rn_partial) return ALGP_ERR_INVALID;
+  switch (nslices) {
+    case 2: return launch_gemm<2, 0>(a, st);
+    case 3: return launch_gemm<3, 0>(a, st);
+    case 4: return launch_gemm<4, 0>(a, st);
+    case 5: return launch_gemm<5, 0>(a, st);
+    case 6: return launch_gemm<6, 0>(a, st);
+    case 7: return launch_gemm<7, 0>(a, st);
+    default: return launch_gemm<8, 0>(a, st);
+  }
+}
+
+extern "C" int algp_split_i8(const double* src, int64_t rows, int64_t cols, int64_t ld, int nslices, int tile_rows,
+                             int8_t* planes, double* row_scale, void* stream) {
+  return i8_split(src, rows, cols, ld, nslices, tile_rows, planes, row_scale, (cudaStream_t)stream);
+}
+
 // rn_partial[m][t] (t < npad/64) = sum over 64-column tile t of (K Linv^T)[m][.]^2 from the digit tiles
 extern "C" int algp_trmm_rt_i8(const int8_t* Kt, const double* Kscale, int64_t mpad, const int8_t* Lt, const double* Lscale,
                                int64_t npad, int nslices, double* rn_partial, void* stream) {
-  if (!Kt || !Kscale || !Lt || !Lscale || !rn_partial || mpad % ALGP_BLK || npad % ALGP_BLK || nslices < 2 ||
-      nslices > I8_MAX_S || npad > 32768)
-    return ALGP_ERR_INVALID;           // K <= 2^15 keeps every group sum below 2^31 (8 pairs x 2^15 x 2^12 = 2^30)
-  if (mpad == 0 || npad == 0) return ALGP_OK;
-  if (((uintptr_t)Kt | (uintptr_t)Lt) & 15) return ALGP_ERR_INVALID;
-  I8Args a;
+  if (!rn_partial || mpad < 0 || npad < 0 || mpad % ALGP_BLK || npad % ALGP_BLK) return ALGP_ERR_INVALID;
+  I8Gemm a = i8_gemm_default();
   a.MT = (int)(mpad / I8_TM);
   a.NT = (int)(npad / I8_TN);
   a.a_tiles = Kt;
@@ -340,16 +398,34 @@ extern "C" int algp_trmm_rt_i8(const int8_t* Kt, const double* Kscale, int64_t m
   a.kchunks = (int)(npad / I8_KC);
   a.scale_a = Kscale;
   a.scale_b = Lscale;
+  a.kend_rule = I8_KE_NT;              // Linv is lower triangular
+  a.nt_desc = 1;
   a.rn_partial = rn_partial;
   a.rn_nt = a.NT;
-  cudaStream_t st = (cudaStream_t)stream;
-  switch (nslices) {
-    case 2: return launch_trmm<2>(a, st);
-    case 3: return launch_trmm<3>(a, st);
-    case 4: return launch_trmm<4>(a, st);
-    case 5: return launch_trmm<5>(a, st);
-    case 6: return launch_trmm<6>(a, st);
-    case 7: return launch_trmm<7>(a, st);
-    default: return launch_trmm<8>(a, st);
-  }
+  return i8_gemm(a, nslices, (cudaStream_t)stream);
+}
+
+// C [mpad x npad] = alpha A B^T + beta C from the digit tiles of A [mpad x kpad] (tile_rows 128) and B [npad x kpad]
+// (tile_rows 64); transposed != 0 stores C^T ([npad x mpad], ldc its row stride)
+extern "C" int algp_gemm_nt_i8(const int8_t* At, const double* Ascale, int64_t mpad, const int8_t* Bt, const double* Bscale,
+                               int64_t npad, int64_t kpad, int nslices, double alpha, double beta, double* C, int64_t ldc,
+                               int transposed, int lower_only, void* stream) {
+  if (!C || mpad < 0 || npad < 0 || kpad < 0 || mpad % I8_TM || npad % I8_TN || kpad % I8_KC ||
+      ldc < (transposed ? mpad : npad))
+    return ALGP_ERR_INVALID;
+  I8Gemm a = i8_gemm_default();
+  a.MT = (int)(mpad / I8_TM);
+  a.NT = (int)(npad / I8_TN);
+  a.a_tiles = At;
+  a.b_tiles = Bt;
+  a.kchunks = (int)(kpad / I8_KC);
+  a.scale_a = Ascale;
+  a.scale_b = Bscale;
+  a.C = C;
+  a.ldc = ldc;
+  a.alpha = alpha;
+  a.beta = beta;
+  a.transposed = transposed ? 1 : 0;
+  a.lower_only = lower_only ? 1 : 0;
+  return i8_gemm(a, nslices, (cudaStream_t)stream);
 }

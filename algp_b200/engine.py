@@ -17,6 +17,9 @@ from . import _lib
 from ._lib import call, ptr, stream
 
 BLK = 128
+I8_FACTOR_SLICES = 8   # digit planes of the recursive INT8 factorisation (56 bits: fp64-grade trailing updates)
+I8_FACTOR_BASE = 2048  # blocks of this many rows or fewer are factored by the DMMA kernels
+I8_FACTOR_MIN = 8192   # factor="auto": smallest padded N that takes the INT8 factorisation
 I8_SLICES = 7          # digit planes of the INT8 variance path: 7 x 7 = 49 bits below each row's scale (8 = 56 bits)
 CONST = 0.5 * np.log(2 * np.pi * np.exp(1))        # utils.py:10
 KIND = {"rbf": 0, None: 0, "matern": 1}
@@ -104,10 +107,26 @@ def rowsum(partial, scale=1.0, bias=0.0, addvec=None, rows=None):
     return out
 
 
+def potrf_inv_i8(A, Linv, info, nslices=None, base=None):
+    """In place: lower triangle of A <- L, Linv <- L^-1, through the recursive INT8 digit factorisation."""
+    nslices = I8_FACTOR_SLICES if nslices is None else nslices
+    base = I8_FACTOR_BASE if base is None else base
+    npad = A.shape[0]
+    nbytes = _lib.lib.algp_potrf_inv_i8_work_bytes(npad, nslices, base)
+    work = torch.empty(nbytes, dtype=torch.uint8, device=A.device)
+    call("algp_potrf_inv_i8", ptr(A), npad, A.stride(0), ptr(Linv), Linv.stride(0), nslices, base, ptr(work), nbytes,
+         ptr(info), stream())
+    del work
+
+
 class GPFactor(object):
     """Cholesky factor and explicit inverse factor of the training covariance."""
 
-    def __init__(self, hyper, x, diag_add=None, diag_scalar=None, keep_linv=True):
+    def __init__(self, hyper, x, diag_add=None, diag_scalar=None, keep_linv=True, factor="dmma"):
+        """factor="dmma": algp_potrf + algp_trtri (fp64 tensor cores); factor="i8": the recursive factorisation
+        whose products run as exact INT8 digit GEMMs (same fp64 tier, faster from N ~ 8192 up); "auto" picks."""
+        if factor not in ("dmma", "i8", "auto"):
+            raise ValueError("factor must be 'dmma', 'i8' or 'auto'")
         self.hyper = hyper
         self.x = x
         self.N = x.shape[0]
@@ -118,11 +137,16 @@ class GPFactor(object):
         self.L, _ = kbuild(hyper, x, None, self.Npad, self.Npad, diag_add, diag_scalar, True)
         self.Linv = torch.empty((self.Npad, self.Npad), dtype=torch.float64, device=dev)
         self.info = torch.zeros(1, dtype=torch.int32, device=dev)
-        call("algp_potrf", ptr(self.L), self.Npad, self.Npad, ptr(self.Linv), self.Npad, ptr(self.info), stream())
-        nwork = _lib.lib.algp_trtri_work_doubles(self.Npad)
-        work = torch.empty(max(2, nwork), dtype=torch.float64, device=dev)
-        call("algp_trtri", ptr(self.L), self.Npad, self.Npad, ptr(self.Linv), self.Npad, ptr(work), 1, stream())
-        del work
+        if factor == "auto":
+            factor = "i8" if self.Npad >= I8_FACTOR_MIN else "dmma"
+        if factor == "i8" and self.Npad > I8_FACTOR_BASE:
+            potrf_inv_i8(self.L, self.Linv, self.info)
+        else:
+            call("algp_potrf", ptr(self.L), self.Npad, self.Npad, ptr(self.Linv), self.Npad, ptr(self.info), stream())
+            nwork = _lib.lib.algp_trtri_work_doubles(self.Npad)
+            work = torch.empty(max(2, nwork), dtype=torch.float64, device=dev)
+            call("algp_trtri", ptr(self.L), self.Npad, self.Npad, ptr(self.Linv), self.Npad, ptr(work), 1, stream())
+            del work
         self._ld2 = None
 
     def check(self):

@@ -91,13 +91,15 @@ def _factor_for(gp, hyper, train_x, train_var):
     """Device factor of cov_aa (utils.py:296), cached on the GPR until its data or theta change."""
     from . import engine
     cache = getattr(gp, "_cache", None)
-    key = ("factor", _digest(train_x, train_var), hyper.key())
+    prec = getattr(gp, "precision", "fp64")
+    # precision "i8": factor through the recursive INT8 digit factorisation when N is large enough to pay
+    key = ("factor", _digest(train_x, train_var), hyper.key(), prec == "i8")
     if cache is not None and cache.get("factor_key") == key:
         return cache["factor"]
     dev = engine.require_cuda()
     x = engine.to_dev(train_x, device=dev)
     wn = None if train_var is None else engine.to_dev(np.asarray(train_var, dtype=np.float64), device=dev)
-    f = engine.GPFactor(hyper, x, diag_add=wn, diag_scalar=hyper.noise)
+    f = engine.GPFactor(hyper, x, diag_add=wn, diag_scalar=hyper.noise, factor="auto" if prec == "i8" else "dmma")
     if cache is not None:
         cache.clear()
         cache["factor_key"] = key

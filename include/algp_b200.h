@@ -103,6 +103,21 @@ int algp_split_i8(const double* src, int64_t rows, int64_t cols, int64_t ld, int
 int algp_trmm_rt_i8(const int8_t* Kt, const double* Kscale, int64_t mpad, const int8_t* Lt, const double* Lscale,
                     int64_t npad, int nslices, double* rn_partial, void* stream);
 
+/* C [mpad x npad] = alpha A B^T + beta C from the digit tiles of A [mpad x kpad] (tile_rows 128) and
+ * B [npad x kpad] (tile_rows 64), fp64-grade with nslices = 8; transposed != 0 stores C^T ([npad x mpad], ldc its
+ * row stride); lower_only skips the tiles entirely above the diagonal.  mpad % 128 == 0, npad % 64 == 0,
+ * kpad % 32 == 0, kpad <= 32768. */
+int algp_gemm_nt_i8(const int8_t* At, const double* Ascale, int64_t mpad, const int8_t* Bt, const double* Bscale,
+                    int64_t npad, int64_t kpad, int nslices, double alpha, double beta, double* C, int64_t ldc,
+                    int transposed, int lower_only, void* stream);
+/* algp_potrf + algp_trtri in one call with the O(n^3) work on the INT8 tensor cores: recursive 2 x 2 splitting
+ * (L21 = A21 Linv11^T, A22 -= L21 L21^T, Linv21 = -Linv22 L21 Linv11) whose products are exact digit GEMMs;
+ * blocks of `base` rows or fewer (base % 128 == 0) use the DMMA kernels.  A's lower triangle becomes L, Linv
+ * the full lower-triangular inverse; *info_dev as algp_potrf.  work: algp_potrf_inv_i8_work_bytes() bytes. */
+int algp_potrf_inv_i8(double* A, int64_t npad, int64_t ld, double* Linv, int64_t ldi, int nslices, int64_t base,
+                      void* work, int64_t work_bytes, int* info_dev, void* stream);
+int64_t algp_potrf_inv_i8_work_bytes(int64_t npad, int nslices, int64_t base);
+
 /* ---- K4: marginal-likelihood gradient (GPR.fit, models.py:145-158) ---------- */
 /* Ainv (lower triangle) = Linv^T Linv = A^-1 */
 int algp_potri_lower(const double* Linv, int64_t npad, int64_t ldi, double* Ainv, int64_t lda, void* stream);

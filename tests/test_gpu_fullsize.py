@@ -103,6 +103,17 @@ def test_fit_n16384_properties():
     assert (v64 > 0).all() and (v64 <= 1.0 + 1e-12).all()
     np.testing.assert_allclose(v32, v64, rtol=0, atol=3e-4)         # 2e-4 s^2 at N=16384
     np.testing.assert_allclose(v8, v64, rtol=0, atol=1e-10)         # INT8 digit mode: fp64 tier (1e-9 s^2) with margin
+    # the recursive INT8 digit factorisation reproduces the DMMA factor and inverse
+    f8 = engine.GPFactor(hy, dev(x), diag_add=dev(np.full(N, 0.01)), factor="i8")
+    f8.check()
+    assert float((torch.tril(f8.L) - torch.tril(f.L)).abs().max()) < 1e-11
+    assert float((f8.Linv - f.Linv).abs().max()) < 1e-9 * float(f.Linv.abs().max())
+    ld8, ld64 = float(f8.logdet_quad()[0]), float(f.logdet_quad()[0])
+    assert abs(ld8 - ld64) <= 1e-10 * abs(ld64)
+    mu8f, v8f = f8.mean_var(dev(xs), dev(y - y.mean()), float(y.mean()), precision="i8")
+    np.testing.assert_allclose(v8f.cpu().numpy(), v64, rtol=0, atol=1e-9)
+    np.testing.assert_allclose(mu8f.cpu().numpy(), mu.cpu().numpy(), rtol=1e-9, atol=1e-9)
+    del f8
     # the mean interpolates the data to within a few noise standard deviations at training points
     mu_tr, _ = f.mean_var(dev(x[:2048]), dev(y - y.mean()), float(y.mean()), want_var=False)
     assert np.abs(mu_tr.cpu().numpy() - y[:2048]).max() < 1.0

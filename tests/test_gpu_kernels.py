@@ -5,6 +5,7 @@ import torch
 
 import oracle as O
 from algp_b200 import _lib, engine
+from algp_b200._lib import call, ptr, stream
 from gpu_helpers import dev, field_problem, hyper_pair
 
 pytestmark = pytest.mark.gpu
@@ -328,3 +329,58 @@ def test_trmm_i8_slices_converge():
         errs.append(np.abs(got - ref).max())
     assert errs[-1] < 1e-12 and errs[-2] < 1e-10
     assert all(errs[i + 1] < errs[i] / 16 or errs[i + 1] < 1e-13 for i in range(len(errs) - 1)), errs
+
+
+def test_gemm_nt_i8_matches_numpy():
+    """C = alpha A B^T + beta C from digit tiles (8 planes): fp64-grade, normal and transposed stores."""
+    rng = np.random.default_rng(11)
+    M, N, K = 256, 192, 320
+    A = rng.normal(size=(M, K)) * np.exp(rng.normal(size=(M, 1)) * 2)
+    B = rng.normal(size=(N, K)) * np.exp(rng.normal(size=(N, 1)) * 2)
+    C0 = rng.normal(size=(M, N))
+    f = engine.GPFactor.__new__(engine.GPFactor)
+    at, asc = engine.GPFactor.split_i8(f, dev(A), 8, 128)
+    bt, bsc = engine.GPFactor.split_i8(f, dev(B), 8, 64)
+    ref = A @ B.T
+    tol = 1e-13 * np.abs(A).max(1)[:, None] * np.abs(B).max(1)[None, :] * K
+    C = dev(C0.copy())
+    call("algp_gemm_nt_i8", ptr(at), ptr(asc), M, ptr(bt), ptr(bsc), N, K, 8, -0.5, 2.0, ptr(C), N, 0, 0, stream())
+    assert (np.abs(C.cpu().numpy() - (-0.5 * ref + 2.0 * C0)) <= tol + 1e-14).all()
+    Ct = dev(np.zeros((N, M)))
+    call("algp_gemm_nt_i8", ptr(at), ptr(asc), M, ptr(bt), ptr(bsc), N, K, 8, 1.0, 0.0, ptr(Ct), M, 1, 0, stream())
+    assert (np.abs(Ct.cpu().numpy().T - ref) <= tol).all()
+
+
+@pytest.mark.parametrize("N,base", [(256, 128), (640, 128), (1000, 256), (1536, 512), (2304, 256)])
+def test_potrf_inv_i8_matches_dmma(N, base):
+    """Recursive INT8 digit factorisation: L and L^-1 agree with the DMMA potrf + trtri and with the oracle."""
+    x, var, th, hy, A = spd_problem(N, N + 1)
+    f64 = engine.GPFactor(hy, dev(x), diag_add=dev(var))
+    f8 = engine.GPFactor.__new__(engine.GPFactor)
+    Npad = f64.Npad
+    L, _ = engine.kbuild(hy, dev(x), None, Npad, Npad, dev(var), hy.noise, True)
+    Linv = torch.full((Npad, Npad), float("nan"), dtype=torch.float64, device=L.device)
+    info = torch.zeros(1, dtype=torch.int32, device=L.device)
+    engine.potrf_inv_i8(L, Linv, info, nslices=8, base=base)
+    assert int(info.item()) == 0
+    Lh, Lr = torch.tril(L).cpu().numpy()[:N, :N], torch.tril(f64.L).cpu().numpy()[:N, :N]
+    Lo = np.linalg.cholesky(A)
+    np.testing.assert_allclose(Lh, Lo, rtol=0, atol=1e-11)
+    np.testing.assert_allclose(Lr, Lo, rtol=0, atol=1e-11)
+    Li = Linv.cpu().numpy()
+    assert np.isfinite(Li).all() and np.abs(np.triu(Li, 1)).max() == 0.0          # clean lower-triangular inverse
+    Li_ref = f64.Linv.cpu().numpy()
+    scale = np.abs(Li_ref).max()
+    np.testing.assert_allclose(Li, Li_ref, rtol=0, atol=1e-9 * scale)
+    np.testing.assert_allclose((Li[:N, :N] @ Lo), np.eye(N), rtol=0, atol=1e-9)
+
+
+def test_potrf_inv_i8_reports_not_pd():
+    x, var, th, hy, A = spd_problem(700, 3)
+    Npad = 768
+    L, _ = engine.kbuild(hy, dev(x), None, Npad, Npad, dev(var), hy.noise, True)
+    L[600, 600] = -5.0
+    Linv = torch.empty((Npad, Npad), dtype=torch.float64, device=L.device)
+    info = torch.zeros(1, dtype=torch.int32, device=L.device)
+    engine.potrf_inv_i8(L, Linv, info, nslices=8, base=256)
+    assert int(info.item()) == 601
