@@ -291,6 +291,26 @@ def fit_predict_bench(torch, engine, n_train, grid_side, reps, peak_hbm):
         del rn8
     i8_err = float((v8 - v).abs().max().item())
     f._linv_i8 = None
+    # INT8 digit mode of the factorisation (precision "i8" takes it from N = 8192): recursive potrf + inverse whose
+    # products are exact digit GEMMs; timed in its own loop (kernel build excluded: same as the fp64 run's)
+    use_i8_factor = Npad >= engine.I8_FACTOR_MIN
+    times["factor_i8"] = []
+    if use_i8_factor:
+        L_ref, Linv_ref = torch.tril(A), Linv.clone()
+        for rep in range(reps + 1):
+            engine.kbuild(hy, xd, None, Npad, Npad, var, hy.noise, True, out=A)
+            t0, t1 = ev(), ev()
+            t0.record()
+            engine.potrf_inv_i8(A, Linv, info)
+            t1.record()
+            torch.cuda.synchronize()
+            if rep:
+                times["factor_i8"].append(t0.elapsed_time(t1))
+        i8_factor_err = {"max_abs_dL": float((torch.tril(A) - L_ref).abs().max().item()),
+                         "max_abs_dLinv_rel": float(((Linv - Linv_ref).abs().max() / Linv_ref.abs().max()).item())}
+        del L_ref, Linv_ref
+    else:
+        i8_factor_err = None
     sampler.__exit__()
     # end to end through the reference-facing call with HOST arrays (utils.py:293): H2D of x / y / var / grid,
     # kernel build + factor + solve + variance, D2H of mean and variance, fresh factor every call
@@ -315,11 +335,16 @@ def fit_predict_bench(torch, engine, n_train, grid_side, reps, peak_hbm):
         e2e[mode] = float(np.median(ts[1:]))
     e2e["h2d_bytes"] = int(x.nbytes + y.nbytes + var_h.nbytes + xs.nbytes)
     e2e["d2h_bytes"] = int(mu_h.nbytes + var_out.nbytes)
-    med = {k: float(np.median(v)) for k, v in times.items()}
+    med = {k: (float(np.median(v)) if len(v) else None) for k, v in times.items()}
     N = float(max(128, engine.pad_to(n_train)))
     Mp = float(max(128, engine.pad_to(M)))
     out = {"n_train": n_train, "n_test": M, "ms": med["total"],
-           "ms_i8_mode": med["total"] - med["variance_trmm"] + med["variance_i8"],
+           "ms_i8_mode": (med["total"] - med["variance_trmm"] + med["variance_i8"]
+                          - ((med["potrf"] + med["trtri"] - med["factor_i8"]) if use_i8_factor else 0.0)),
+           "i8_factorisation": ({"used_in_i8_mode": True, "ms": med["factor_i8"], "digit_planes": engine.I8_FACTOR_SLICES,
+                                 "base_rows": engine.I8_FACTOR_BASE, "vs_dmma": i8_factor_err,
+                                 "fp64_equiv_tflops": 2 * N ** 3 / 3 / med["factor_i8"] / 1e9}
+                                if use_i8_factor else {"used_in_i8_mode": False}),
            "ms_tf32_mode": med["total"] - med["variance_trmm"] + med["variance_tf32"],
            "e2e_ms_host_arrays": e2e, "clocks": sampler.summary(),
            "tf32_max_abs_var_diff_vs_fp64": tf32_err, "i8_max_abs_var_diff_vs_fp64": i8_err,
