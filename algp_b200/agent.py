@@ -21,7 +21,7 @@ from . import engine
 from .models import GPR
 from .utils import predictive_distribution
 
-MAX_SET = 128      # slots per candidate the scoring kernel accepts (algp_score_sets)
+MAX_SET = engine.MAX_SET      # slots per candidate the scoring kernels accept (algp_score_sets / _large)
 
 
 def _flags(data):

@@ -59,6 +59,7 @@ struct MiArgs {
   double delta_new;                     // variance change of a brand-new location
   double delta_old;                     // variance change of an already-sampled (static-only) location
   double* out;                          // [B x 3]: logdet [A2^-1]_CC, number of new locations, sum log|Delta| + logdet|...|
+  double* work;                         // k > 128: [grid][k][k+1] elimination scratch in global memory
 };
 
 // un-normalised elimination of the lower triangle of a kk x kk matrix in shared memory; returns sum log|pivot|
@@ -78,11 +79,12 @@ __device__ double mi_logabsdet(double* M, int kk, int pitch, int tid) {
   return acc;   // valid in thread 0
 }
 
+template <bool GLOBAL_M>
 __global__ void __launch_bounds__(256) mi_terms_kernel(const MiArgs a) {
   extern __shared__ __align__(16) double mi_smem[];
   const int k = a.k, pitch = k + 1;
-  double* M = mi_smem;                    // [k][k+1]
-  double* dl = M + k * pitch;             // [k] Delta of the slot (0 = inactive)
+  double* M = GLOBAL_M ? a.work + (size_t)blockIdx.x * k * pitch : mi_smem;   // [k][k+1]
+  double* dl = GLOBAL_M ? mi_smem : M + k * pitch;                            // [k] Delta of the slot (0 = inactive)
   int* loc = (int*)(dl + k);              // [k] location, -1 inactive
   int* p2 = loc + k;                      // [k] position in Abar, -1 if not new
   const int tid = threadIdx.x;
@@ -142,27 +144,58 @@ __global__ void __launch_bounds__(256) mi_terms_kernel(const MiArgs a) {
   }
 }
 
-extern "C" int algp_mi_terms(const double* inv2, int64_t ld2, const int32_t* pos2, const double* inv3, int64_t ld3,
-                             const int32_t* idx, int k, int64_t B, const uint8_t* skip, double delta_new, double delta_old,
-                             double* out3, void* stream) {
-  if (!inv3 || !pos2 || !idx || !out3 || k < 1 || k > 128 || B < 0 || delta_new == 0.0 || delta_old == 0.0) return ALGP_ERR_INVALID;
+#define MI_MAXK 128
+#define MI_MAXK_LARGE 2048
+
+extern "C" int64_t algp_mi_terms_large_work_doubles(int k, int64_t B) {
+  if (k <= MI_MAXK || B <= 0) return 0;
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int64_t grid = B < (int64_t)sms * 2 ? B : (int64_t)sms * 2;
+  return grid * k * ((int64_t)k + 1);
+}
+
+extern "C" int algp_mi_terms_large(const double* inv2, int64_t ld2, const int32_t* pos2, const double* inv3, int64_t ld3,
+                                   const int32_t* idx, int k, int64_t B, const uint8_t* skip, double delta_new,
+                                   double delta_old, double* out3, double* work, int64_t work_doubles, void* stream) {
+  if (!inv3 || !pos2 || !idx || !out3 || k < 1 || k > MI_MAXK_LARGE || B < 0 || delta_new == 0.0 || delta_old == 0.0)
+    return ALGP_ERR_INVALID;
   if (B == 0) return ALGP_OK;
+  const bool large = k > MI_MAXK;
+  if (large && (!work || work_doubles < algp_mi_terms_large_work_doubles(k, B))) return ALGP_ERR_INVALID;
   MiArgs a;
   a.inv2 = inv2; a.ld2 = ld2; a.pos2 = pos2; a.inv3 = inv3; a.ld3 = ld3; a.idx = idx; a.k = k; a.B = B; a.skip = skip;
-  a.delta_new = delta_new; a.delta_old = delta_old; a.out = out3;
-  size_t smem = ((size_t)k * (k + 1) + k) * 8 + (size_t)2 * k * 4 + 16;
-  static size_t configured = 0;
-  if (smem > configured) {
-    ALGP_CUDA(cudaFuncSetAttribute(mi_terms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = smem;
-  }
+  a.delta_new = delta_new; a.delta_old = delta_old; a.out = out3; a.work = work;
+  size_t smem = ((large ? 0 : (size_t)k * (k + 1)) + k) * 8 + (size_t)2 * k * 4 + 16;
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   int grid = (int)(B < (int64_t)sms * 2 ? B : (int64_t)sms * 2);
-  mi_terms_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(a);
+  if (large) {
+    static size_t configured = 0;
+    if (smem > configured) {
+      ALGP_CUDA(cudaFuncSetAttribute(mi_terms_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      configured = smem;
+    }
+    mi_terms_kernel<true><<<grid, 256, smem, (cudaStream_t)stream>>>(a);
+  } else {
+    static size_t configured = 0;
+    if (smem > configured) {
+      ALGP_CUDA(cudaFuncSetAttribute(mi_terms_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      configured = smem;
+    }
+    mi_terms_kernel<false><<<grid, 256, smem, (cudaStream_t)stream>>>(a);
+  }
   ALGP_LAUNCH_CHECK();
   return ALGP_OK;
+}
+
+extern "C" int algp_mi_terms(const double* inv2, int64_t ld2, const int32_t* pos2, const double* inv3, int64_t ld3,
+                             const int32_t* idx, int k, int64_t B, const uint8_t* skip, double delta_new, double delta_old,
+                             double* out3, void* stream) {
+  if (k > MI_MAXK) return ALGP_ERR_INVALID;
+  return algp_mi_terms_large(inv2, ld2, pos2, inv3, ld3, idx, k, B, skip, delta_new, delta_old, out3, nullptr, 0, stream);
 }
 
 

@@ -38,6 +38,7 @@ struct ScoreArgs {
   int64_t B;
   double H_base;
   double* scores;          // [B]
+  double* work;            // k > 128: [grid][kk][kk+1] elimination scratch in global memory
 };
 
 __device__ __forceinline__ void ld256(const double* p, double& a, double& b, double& c, double& d) {
@@ -174,15 +175,19 @@ static void score_k8_launch(const ScoreArgs& a, int sms, int blocks_per_sm, cuda
 }
 
 // ---------------------------------------------------------------------------
-// k <= 128: one CTA per candidate
+// k <= 128: one CTA per candidate, the k x k matrix in shared memory.
+// 128 < k <= 2048 (long paths, agent.py:373-400 scores paths of "tens to hundreds" of mobile locations):
+// the same kernel with the matrix in a per-CTA global scratch (L2 resident).
 // ---------------------------------------------------------------------------
 #define SG_MAXK 128
+#define SG_MAXK_LARGE 2048
+template <bool GLOBAL_M>
 __global__ void __launch_bounds__(256) score_sets_generic_kernel(const ScoreArgs a) {
   extern __shared__ __align__(16) double sg_smem[];
   const int k = a.k;
   const int kp = (k + 7) >> 3, kk = kp * 8, pitch = kk + 1;
-  double* M = sg_smem;                       // [kk][kk+1]
-  double* sqd = M + kk * pitch;              // [kk] sqrt(delta) or 0
+  double* M = GLOBAL_M ? a.work + (size_t)blockIdx.x * kk * pitch : sg_smem;   // [kk][kk+1]
+  double* sqd = GLOBAL_M ? sg_smem : M + kk * pitch;                           // [kk] sqrt(delta) or 0
   double* sx = sqd + kk;                     // [kk][d] scaled coordinates
   int* sidx = (int*)(sx + kk * a.kp.d);      // [kk]
 
@@ -282,13 +287,39 @@ __global__ void __launch_bounds__(256) score_sets_generic_kernel(const ScoreArgs
 
 int make_kernel_params(KernelParams* kp, int d, const double* log_ls_host, double log_os, int kind);
 
+extern "C" int algp_score_sets_large(const double* Wt, int64_t ldw, int64_t ncols, const double* X, int d,
+                                     const double* log_ls_host, double log_os, int kind, double noise,
+                                     const double* pi0, const int32_t* idx, const double* delta, double delta_scalar,
+                                     const uint8_t* skip, int k, int64_t B, double H_base, double* scores, double* work,
+                                     int64_t work_doubles, void* stream);
+
 extern "C" int algp_score_sets(const double* Wt, int64_t ldw, int64_t ncols, const double* X, int d,
                                const double* log_ls_host, double log_os, int kind, double noise,
                                const double* pi0, const int32_t* idx, const double* delta, double delta_scalar,
                                const uint8_t* skip, int k, int64_t B, double H_base, double* scores, void* stream) {
-  if (!Wt || !X || !pi0 || !idx || !scores || k < 1 || k > SG_MAXK || B < 0 || ncols < 0) return ALGP_ERR_INVALID;
+  return algp_score_sets_large(Wt, ldw, ncols, X, d, log_ls_host, log_os, kind, noise, pi0, idx, delta, delta_scalar, skip,
+                               k <= SG_MAXK ? k : -1, B, H_base, scores, nullptr, 0, stream);
+}
+
+extern "C" int64_t algp_score_sets_large_work_doubles(int k, int64_t B) {
+  if (k <= SG_MAXK || B <= 0) return 0;
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int64_t kk = (k + 7) / 8 * 8, grid = B < (int64_t)sms * 2 ? B : (int64_t)sms * 2;
+  return grid * kk * (kk + 1);
+}
+
+extern "C" int algp_score_sets_large(const double* Wt, int64_t ldw, int64_t ncols, const double* X, int d,
+                                     const double* log_ls_host, double log_os, int kind, double noise,
+                                     const double* pi0, const int32_t* idx, const double* delta, double delta_scalar,
+                                     const uint8_t* skip, int k, int64_t B, double H_base, double* scores, double* work,
+                                     int64_t work_doubles, void* stream) {
+  if (!Wt || !X || !pi0 || !idx || !scores || k < 1 || k > SG_MAXK_LARGE || B < 0 || ncols < 0) return ALGP_ERR_INVALID;
   if ((ldw & 3) || ((uintptr_t)Wt & 31)) return ALGP_ERR_INVALID;       // 256-bit row loads
+  if (k > SG_MAXK && B > 0 && (!work || work_doubles < algp_score_sets_large_work_doubles(k, B))) return ALGP_ERR_INVALID;
   ScoreArgs a;
+  a.work = work;
   int rc = make_kernel_params(&a.kp, d, log_ls_host, log_os, kind);
   if (rc) return rc;
   a.noise = noise; a.Wt = Wt; a.ldw = ldw;
@@ -306,16 +337,26 @@ extern "C" int algp_score_sets(const double* Wt, int64_t ldw, int64_t ncols, con
     // row in flight and no register prefetch was the fastest of the variants tried on B200
     // (profiles/r01_score_variants.log): the kernel is bound by L2->SM throughput, not by latency.
     score_k8_launch<2, false, 256>(a, sms, 8, st);
-  } else {
+  } else if (k <= SG_MAXK) {
     const int kp = (k + 7) / 8, kk = kp * 8;
     size_t smem = ((size_t)kk * (kk + 1) + kk + (size_t)kk * d) * 8 + (size_t)kk * 4 + 16;
     static size_t configured = 0;
     if (smem > configured) {
-      ALGP_CUDA(cudaFuncSetAttribute(score_sets_generic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      ALGP_CUDA(cudaFuncSetAttribute(score_sets_generic_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       configured = smem;
     }
     int grid = (int)(B < (int64_t)sms * 2 ? B : (int64_t)sms * 2);
-    score_sets_generic_kernel<<<grid, 256, smem, st>>>(a);
+    score_sets_generic_kernel<false><<<grid, 256, smem, st>>>(a);
+  } else {
+    const int kp = (k + 7) / 8, kk = kp * 8;
+    size_t smem = ((size_t)kk + (size_t)kk * d) * 8 + (size_t)kk * 4 + 16;
+    static size_t configured = 0;
+    if (smem > configured) {
+      ALGP_CUDA(cudaFuncSetAttribute(score_sets_generic_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      configured = smem;
+    }
+    int grid = (int)(B < (int64_t)sms * 2 ? B : (int64_t)sms * 2);
+    score_sets_generic_kernel<true><<<grid, 256, smem, st>>>(a);
   }
   ALGP_LAUNCH_CHECK();
   return ALGP_OK;

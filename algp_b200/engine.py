@@ -17,6 +17,8 @@ from . import _lib
 from ._lib import call, ptr, stream
 
 BLK = 128
+MAX_SET_SMEM = 128     # slots per candidate that fit the shared-memory scoring kernel; longer paths use the global-scratch variant
+MAX_SET = 2048         # slots per candidate algp_score_sets_large accepts
 I8_FACTOR_SLICES = 8   # digit planes of the recursive INT8 factorisation (56 bits: fp64-grade trailing updates)
 I8_FACTOR_BASE = 2048  # blocks of this many rows or fewer are factored by the DMMA kernels
 I8_FACTOR_MIN = 8192   # factor="auto": smallest padded N that takes the INT8 factorisation
@@ -345,6 +347,14 @@ class PosteriorState(object):
             out = torch.empty(B, dtype=torch.float64, device=idx.device)
         ls, ls_p = _lib.host_f64(self.hyper.log_ls)
         hb = self.H_base if H_base is None else H_base
+        if k > MAX_SET_SMEM:
+            # long paths: the k x k matrix of a candidate lives in a global scratch instead of shared memory
+            nwork = _lib.lib.algp_score_sets_large_work_doubles(k, B)
+            work = torch.empty(max(1, nwork), dtype=torch.float64, device=idx.device)
+            call("algp_score_sets_large", ptr(self.Wt), self.ldw, self.ncols, ptr(self.X), self.hyper.d, ls_p,
+                 self.hyper.log_os, self.hyper.kind, self.hyper.noise, ptr(self.pi), ptr(idx), ptr(delta),
+                 float(delta_scalar), ptr(skip), k, B, float(hb), ptr(out), ptr(work), nwork, stream())
+            return out
         call("algp_score_sets", ptr(self.Wt), self.ldw, self.ncols, ptr(self.X), self.hyper.d, ls_p,
              self.hyper.log_os, self.hyper.kind, self.hyper.noise, ptr(self.pi), ptr(idx), ptr(delta),
              float(delta_scalar), ptr(skip), k, B, float(hb), ptr(out), stream())
@@ -468,8 +478,11 @@ class MIContext(object):
         vboth = 1.0 / (1.0 / ss2 + 1.0 / ms2)
         B, k = idx.shape
         out = torch.empty((B, 3), dtype=torch.float64, device=idx.device)
-        call("algp_mi_terms", ptr(self.inv2), self.inv2.stride(0) if self.inv2 is not None else 0, ptr(self.pos2),
-             ptr(self.inv3), self.inv3.stride(0), ptr(idx), k, B, ptr(skip), float(ms2), float(vboth - ss2), ptr(out), stream())
+        nwork = _lib.lib.algp_mi_terms_large_work_doubles(k, B)
+        work = torch.empty(max(1, nwork), dtype=torch.float64, device=idx.device)
+        call("algp_mi_terms_large", ptr(self.inv2), self.inv2.stride(0) if self.inv2 is not None else 0, ptr(self.pos2),
+             ptr(self.inv3), self.inv3.stride(0), ptr(idx), k, B, ptr(skip), float(ms2), float(vboth - ss2), ptr(out),
+             ptr(work), nwork, stream())
         ent_abar = (self.n_abar - out[:, 1]) * CONST + 0.5 * (self.ld2 + out[:, 0])
         ent_all = self.n * CONST + 0.5 * (self.ld3 + out[:, 2])
         return ent_a + ent_abar - ent_all

@@ -143,6 +143,14 @@ int algp_score_sets(const double* Wt, int64_t ldw, int64_t ncols, const double* 
                     const double* log_ls_host, double log_os, int kind, double noise,
                     const double* pi0, const int32_t* idx, const double* delta, double delta_scalar,
                     const uint8_t* skip, int k, int64_t B, double H_base, double* scores, void* stream);
+/* The same scores for long paths: 128 < k <= 2048 slots per candidate (the reference scores paths of "tens to
+ * hundreds" of mobile locations, agent.py:373-400).  The k x k conditional covariance of a candidate lives in
+ * `work` (algp_score_sets_large_work_doubles(k, B) doubles) instead of shared memory; k <= 128 ignores work. */
+int algp_score_sets_large(const double* Wt, int64_t ldw, int64_t ncols, const double* X, int d,
+                          const double* log_ls_host, double log_os, int kind, double noise, const double* pi0,
+                          const int32_t* idx, const double* delta, double delta_scalar, const uint8_t* skip, int k,
+                          int64_t B, double H_base, double* scores, double* work, int64_t work_doubles, void* stream);
+int64_t algp_score_sets_large_work_doubles(int k, int64_t B);
 /* greedy utilities for every location (k = 1 closed form, agent.py:341) */
 int algp_greedy_utilities(const double* diagP, const double* pi, const uint8_t* is_static, double d_static,
                           int64_t n, double* ut, void* stream);
@@ -170,6 +178,11 @@ int64_t algp_colsumsq_work_doubles(int64_t n);
 int algp_mi_terms(const double* inv2, int64_t ld2, const int32_t* pos2, const double* inv3, int64_t ld3,
                   const int32_t* idx, int k, int64_t B, const uint8_t* skip, double delta_new, double delta_old,
                   double* out3, void* stream);
+/* algp_mi_terms for 128 < k <= 2048 (scratch: algp_mi_terms_large_work_doubles(k, B) doubles) */
+int algp_mi_terms_large(const double* inv2, int64_t ld2, const int32_t* pos2, const double* inv3, int64_t ld3,
+                        const int32_t* idx, int k, int64_t B, const uint8_t* skip, double delta_new, double delta_old,
+                        double* out3, double* work, int64_t work_doubles, void* stream);
+int64_t algp_mi_terms_large_work_doubles(int k, int64_t B);
 
 /* ---- growing-prefix posteriors (agent.py:497-518) ------------------------------------- */
 /* out[i][m] = {sum_j V[m][j] beta[j], sum_j V[m][j] gamma[j], sum_j V[m][j]^2} over j < prefix[i]

@@ -116,3 +116,27 @@ def test_agent_edge_semantics():
     st = np.zeros(40, bool); st[[1, 2, 3]] = True
     mo = np.zeros(40, bool); mo[[4, 5, 6]] = True
     assert ag3.best_path(paths, [7]) == O.best_path_literal(cov, st, mo, 0.1, 1.0, paths, [7])
+
+
+@pytest.mark.parametrize("criterion", ["entropy", "mutual_information"])
+def test_long_paths_match_literal_loop(criterion):
+    """Paths of hundreds of mobile locations (agent.py:373-400 scores whatever env.get_all_paths returns): more than
+    the 128 slots of the shared-memory kernel, ragged, with repeats and already-sampled locations."""
+    rng = np.random.default_rng(9)
+    n = 700
+    X = rng.uniform(0, 30, (n, 2))
+    static = set(rng.choice(n, 60, replace=False).tolist())
+    mobile = set(rng.choice(n, 40, replace=False).tolist())
+    ag, th = _agent(X, static, mobile)
+    ag.criterion = criterion
+    cov = O.OracleGP(th, "fp64").cov_mat(X, add_likelihood_var=True)
+    lens = [130, 257, 301, 12, 200, 129]
+    paths = [rng.choice(n, L, replace=True).tolist() for L in lens]
+    paths.append(paths[1][:200])                      # a prefix of another path
+    st = np.zeros(n, bool); st[list(static)] = True
+    mo = np.zeros(n, bool); mo[list(mobile)] = True
+    new_static = [int(i) for i in rng.choice(n, 3, replace=False)]
+    want, ut = O.best_path_literal(cov, st, mo, 0.1, 1.0, paths, new_static, criterion=criterion, return_utilities=True)
+    assert ag.best_path(paths, new_static) == want
+    got = ag._last_path_scores.cpu().numpy()
+    np.testing.assert_allclose(got, ut, rtol=1e-8, atol=1e-8)
