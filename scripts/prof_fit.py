@@ -15,6 +15,7 @@ ap.add_argument("--n", type=int, default=4096)
 ap.add_argument("--side", type=int, default=64)
 ap.add_argument("--reps", type=int, default=2)
 ap.add_argument("--tf32", action="store_true")
+ap.add_argument("--i8", action="store_true")
 a = ap.parse_args()
 rng = np.random.default_rng(1)
 x = rng.uniform(0, a.side, size=(a.n, 2))
@@ -27,9 +28,9 @@ var = engine.to_dev(np.full(a.n, 0.01))
 for rep in range(a.reps):
     e = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
     e[0].record()
-    f = engine.GPFactor(hy, xd, diag_add=var)
+    f = engine.GPFactor(hy, xd, diag_add=var, factor="auto" if a.i8 else "dmma")
     e[1].record()
-    mu, v = f.mean_var(xsd, y0, float(y.mean()), precision="tf32" if a.tf32 else "fp64")
+    mu, v = f.mean_var(xsd, y0, float(y.mean()), precision="tf32" if a.tf32 else ("i8" if a.i8 else "fp64"))
     e[2].record()
     torch.cuda.synchronize()
     f.check()
