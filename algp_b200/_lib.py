@@ -24,6 +24,7 @@ SIGNATURES = {
     "algp_rowsum": (C.c_int, [_p, _i64, _i32, _f64, _f64, _p, _p, _p]),
     "algp_scatter_add": (C.c_int, [_p, _i64, _p, _i64, _f64, _p]),
     "algp_potrf": (C.c_int, [_p, _i64, _i64, _p, _i64, _p, _p]),
+    "algp_set_potf2_rank": (C.c_int, [_i32]),
     "algp_trtri": (C.c_int, [_p, _i64, _i64, _p, _i64, _p, _i32, _p]),
     "algp_trtri_work_doubles": (_i64, [_i64]),
     "algp_gemv_lower": (C.c_int, [_p, _i64, _i64, _p, _p, _p]),

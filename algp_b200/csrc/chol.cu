@@ -194,13 +194,190 @@ __global__ void __launch_bounds__(256, 1) potf2inv_kernel(double* __restrict__ A
     }
 }
 
+// ---------------------------------------------------------------------------
+// Rank-R variant: R columns per barrier.  The owners publish R raw columns of the Schur complement and R raw
+// rows of Y; every thread then eliminates the R x R pivot block REDUNDANTLY in registers (R dependent
+// reciprocals instead of R barrier + shared-memory round trips), brings its own rows / columns of the R
+// published vectors up to date with the same multipliers, and applies one rank-R update to its patches.
+// The column-to-column chain (publish -> barrier -> read -> reciprocal -> update) is paid once per R columns.
+// ---------------------------------------------------------------------------
+#define PR_SMEM_DOUBLES(R) (2 * (R) * 128 + 2 * (R) * 128 + 128 + 128)
+
+template <int IC, int R>
+__device__ __forceinline__ void pr_block(double (&acc)[8][8], double (&yac)[8][8], double* colbuf, double* rowbuf,
+                                         double* pivbuf, int ty, int tx, int tid, int j0, int* info) {
+#pragma unroll 1
+  for (int cc = 0; cc < 16; cc += R) {
+    const int c = IC * 16 + cc;
+    double* cb = colbuf + ((c / R) & 1) * (R * 128);
+    double* rb = rowbuf + ((c / R) & 1) * (R * 128);
+    {
+      const int q = tx - cc;
+      if (q >= 0 && q < R) {
+#pragma unroll
+        for (int i = IC; i < 8; ++i) cb[q * 128 + ty + 16 * i] = acc[i][IC];
+      }
+      const int qy = ty - cc;
+      if (qy >= 0 && qy < R) {
+#pragma unroll
+        for (int j = 0; j <= IC; ++j) rb[qy * 128 + tx + 16 * j] = yac[IC][j];
+      }
+    }
+    __syncthreads();
+    // ---- R x R pivot block, eliminated redundantly by every thread ----
+    double P[R][R], M[R][R], rcp[R];
+#pragma unroll
+    for (int a = 0; a < R; ++a)
+#pragma unroll
+      for (int b = 0; b <= a; ++b) P[a][b] = cb[b * 128 + c + a];
+#pragma unroll
+    for (int b = 0; b < R; ++b) {
+      const double piv = P[b][b];
+      const bool ok = piv > 0.0;
+      rcp[b] = ok ? 1.0 / piv : 0.0;
+      if (tid == 0) {
+        pivbuf[c + b] = piv;
+        if (!ok) atomicCAS(info, 0, j0 + c + b + 1);
+      }
+#pragma unroll
+      for (int a = b + 1; a < R; ++a) M[a][b] = P[a][b] * rcp[b];
+#pragma unroll
+      for (int a = b + 1; a < R; ++a)
+#pragma unroll
+        for (int b2 = b + 1; b2 <= a; ++b2) P[a][b2] = fma(-M[a][b], P[b2][b], P[a][b2]);
+    }
+    // ---- multipliers of this thread's rows for the R columns (normalised, masked at or above each pivot) ----
+    double ri[R][8];
+#pragma unroll
+    for (int i = IC; i < 8; ++i) {
+#pragma unroll
+      for (int b = 0; b < R; ++b) {
+        double v = cb[b * 128 + ty + 16 * i];
+#pragma unroll
+        for (int b1 = 0; b1 < b; ++b1) v = fma(-ri[b1][i], P[b][b1], v);
+        ri[b][i] = v * rcp[b];
+        if (i == IC && ty <= cc + b) ri[b][i] = 0.0;
+      }
+    }
+    // ---- per column patch: the R updated (un-normalised) column values, then the rank-R update ----
+#pragma unroll
+    for (int j = IC; j < 8; ++j) {
+      double cj[R];
+#pragma unroll
+      for (int b = 0; b < R; ++b) {
+        double v = cb[b * 128 + tx + 16 * j];
+#pragma unroll
+        for (int b1 = 0; b1 < b; ++b1) v = fma(-cj[b1], M[b][b1], v);
+        cj[b] = v;
+        if (j == IC && tx <= cc + b) cj[b] = 0.0;
+      }
+#pragma unroll
+      for (int i = j; i < 8; ++i) {
+        double t = acc[i][j];
+#pragma unroll
+        for (int b = 0; b < R; ++b) t = fma(-ri[b][i], cj[b], t);
+        acc[i][j] = t;
+      }
+    }
+#pragma unroll
+    for (int j = 0; j <= IC; ++j) {
+      double yj[R];
+#pragma unroll
+      for (int b = 0; b < R; ++b) {
+        double v = rb[b * 128 + tx + 16 * j];                       // Y[c+b][.], zero right of its diagonal
+#pragma unroll
+        for (int b1 = 0; b1 < b; ++b1) v = fma(-M[b][b1], yj[b1], v);
+        yj[b] = v;
+      }
+#pragma unroll
+      for (int i = IC; i < 8; ++i) {
+        double t = yac[i][j];
+#pragma unroll
+        for (int b = 0; b < R; ++b) t = fma(-ri[b][i], yj[b], t);
+        yac[i][j] = t;
+      }
+    }
+  }
+}
+
+template <int R>
+__global__ void __launch_bounds__(256, 1) potf2inv_rank_kernel(double* __restrict__ A, int64_t ld, double* __restrict__ Linv,
+                                                               int64_t ldi, int j0, int* __restrict__ info) {
+  extern __shared__ __align__(16) double pr_smem[];
+  double* colbuf = pr_smem;                   // [2][R][128]
+  double* rowbuf = colbuf + 2 * R * 128;      // [2][R][128]
+  double* pivbuf = rowbuf + 2 * R * 128;      // [128]
+  double* rsbuf = pivbuf + 128;               // [128] 1/sqrt(piv)
+
+  const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
+  double acc[8][8], yac[8][8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j <= i; ++j) {
+      acc[i][j] = A[(int64_t)(ty + 16 * i) * ld + tx + 16 * j];
+      yac[i][j] = (i == j && ty == tx) ? 1.0 : 0.0;
+    }
+
+  pr_block<0, R>(acc, yac, colbuf, rowbuf, pivbuf, ty, tx, tid, j0, info);
+  pr_block<1, R>(acc, yac, colbuf, rowbuf, pivbuf, ty, tx, tid, j0, info);
+  pr_block<2, R>(acc, yac, colbuf, rowbuf, pivbuf, ty, tx, tid, j0, info);
+  pr_block<3, R>(acc, yac, colbuf, rowbuf, pivbuf, ty, tx, tid, j0, info);
+  pr_block<4, R>(acc, yac, colbuf, rowbuf, pivbuf, ty, tx, tid, j0, info);
+  pr_block<5, R>(acc, yac, colbuf, rowbuf, pivbuf, ty, tx, tid, j0, info);
+  pr_block<6, R>(acc, yac, colbuf, rowbuf, pivbuf, ty, tx, tid, j0, info);
+  pr_block<7, R>(acc, yac, colbuf, rowbuf, pivbuf, ty, tx, tid, j0, info);
+  __syncthreads();
+  if (tid < 128) {
+    const double piv = pivbuf[tid];
+    rsbuf[tid] = piv > 0.0 ? 1.0 / sqrt(piv) : 0.0;
+  }
+  __syncthreads();
+
+  // L = Ltilde D^1/2 (acc holds the un-normalised columns), Linv = D^-1/2 Y; zeros above the diagonal
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int r = ty + 16 * i, c = tx + 16 * j;
+      double l = 0.0, li = 0.0;
+      if (j <= i) {
+        if (r > c) {
+          l = acc[i][j] * rsbuf[c];
+          li = yac[i][j] * rsbuf[r];
+        } else if (r == c) {
+          l = pivbuf[c] * rsbuf[c];
+          li = rsbuf[r];
+        }
+      }
+      A[(int64_t)r * ld + c] = l;
+      Linv[(int64_t)r * ldi + c] = li;
+    }
+}
+
+// 1 = one column per barrier (potf2inv_kernel), 2 / 4 = rank-R steps.  Measured on B200 (scripts/prof_potf2.py):
+// 46.4 / 41.1 / 43.5 us per 128-block: the kernel is bound by instruction issue at two warps per scheduler
+// (~115 issued instructions per column per warp, a third of them DFMA), not by the barrier chain.
+static int g_potf2_rank = 2;
+extern "C" int algp_set_potf2_rank(int r) {
+  if (r != 1 && r != 2 && r != 4) return ALGP_ERR_INVALID;
+  g_potf2_rank = r;
+  return ALGP_OK;
+}
+
 static int potf2inv_launch(double* A, int64_t ld, double* Linv, int64_t ldi, int j0, int* info, cudaStream_t st) {
   static bool configured = false;
   if (!configured) {
     ALGP_CUDA(cudaFuncSetAttribute(potf2inv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, P2_SMEM_BYTES));
     configured = true;
   }
-  potf2inv_kernel<<<1, 256, P2_SMEM_BYTES, st>>>(A, ld, Linv, ldi, j0, info);
+  if (g_potf2_rank == 4) {
+    potf2inv_rank_kernel<4><<<1, 256, PR_SMEM_DOUBLES(4) * 8, st>>>(A, ld, Linv, ldi, j0, info);
+  } else if (g_potf2_rank == 2) {
+    potf2inv_rank_kernel<2><<<1, 256, PR_SMEM_DOUBLES(2) * 8, st>>>(A, ld, Linv, ldi, j0, info);
+  } else {
+    potf2inv_kernel<<<1, 256, P2_SMEM_BYTES, st>>>(A, ld, Linv, ldi, j0, info);
+  }
   ALGP_LAUNCH_CHECK();
   return ALGP_OK;
 }

@@ -54,6 +54,9 @@ int algp_scatter_add(double* M, int64_t ld, const int32_t* row_of_col, int64_t n
  * inv(L_jj) into the diagonal 128-blocks of Linv.  *info_dev = 0, or the
  * 1-based column at which the matrix stopped being positive definite. */
 int algp_potrf(double* A, int64_t npad, int64_t ld, double* Linv, int64_t ldi, int* info_dev, void* stream);
+/* Diagonal-block kernel of algp_potrf: columns eliminated per barrier (1, 2 or 4; default 2).  A tuning /
+ * testing knob: all three give the same factor up to rounding. */
+int algp_set_potf2_rank(int r);
 /* Completes Linv = L^-1 from its diagonal blocks (recursive doubling).
  * work: algp_trtri_work_doubles(npad) doubles. */
 int algp_trtri(const double* L, int64_t npad, int64_t ld, double* Linv, int64_t ldi, double* work,

@@ -16,7 +16,10 @@ ap.add_argument("--side", type=int, default=64)
 ap.add_argument("--reps", type=int, default=2)
 ap.add_argument("--tf32", action="store_true")
 ap.add_argument("--i8", action="store_true")
+ap.add_argument("--rank", type=int, default=2)
 a = ap.parse_args()
+from algp_b200._lib import call as _call
+_call("algp_set_potf2_rank", a.rank)
 rng = np.random.default_rng(1)
 x = rng.uniform(0, a.side, size=(a.n, 2))
 yy, xx = np.meshgrid(np.arange(a.side), np.arange(a.side), indexing="ij")

@@ -384,3 +384,31 @@ def test_potrf_inv_i8_reports_not_pd():
     info = torch.zeros(1, dtype=torch.int32, device=L.device)
     engine.potrf_inv_i8(L, Linv, info, nslices=8, base=256)
     assert int(info.item()) == 601
+
+
+@pytest.mark.parametrize("N", [128, 200, 645, 1000])
+def test_potf2_rank_variants_agree(N):
+    """The diagonal-block kernel eliminates 1, 2 or 4 columns per barrier: same L and L^-1, and the same
+    not-positive-definite column."""
+    x, var, th, hy, A = spd_problem(N, N + 2)
+    Lo = np.linalg.cholesky(A)
+    try:
+        for r in (1, 2, 4):
+            call("algp_set_potf2_rank", r)
+            f = engine.GPFactor(hy, dev(x), diag_add=dev(var))
+            f.check()
+            np.testing.assert_allclose(np.tril(f.L.cpu().numpy())[:N, :N], Lo, rtol=0, atol=1e-11)
+            Li = f.Linv.cpu().numpy()[:N, :N]
+            np.testing.assert_allclose(Li @ Lo, np.eye(N), rtol=0, atol=1e-9)
+            assert np.abs(np.triu(f.Linv.cpu().numpy(), 1)).max() == 0.0
+            # a negative pivot in the middle of a 4-column step
+            Npad = f.Npad
+            Abad, _ = engine.kbuild(hy, dev(x), None, Npad, Npad, dev(var), hy.noise, True)
+            bad = min(N - 1, 70)
+            Abad[bad, bad] = -1.0
+            Linv = torch.empty_like(Abad)
+            info = torch.zeros(1, dtype=torch.int32, device=Abad.device)
+            call("algp_potrf", ptr(Abad), Npad, Npad, ptr(Linv), Npad, ptr(info), stream())
+            assert int(info.item()) == bad + 1
+    finally:
+        call("algp_set_potf2_rank", 2)
