@@ -194,6 +194,28 @@ int64_t algp_mi_terms_large_work_doubles(int k, int64_t B);
 int algp_prefix_reduce(const double* V, int64_t ldv, int64_t rows, const double* beta, const double* gamma,
                        const int32_t* prefix_dev, int nprefix, double* out, void* stream);
 
+/* ---- path enumeration feeding Agent.best_path (host code, no GPU work) ---------------------------
+ * The expansion-tree search of FieldEnv.get_all_paths (env.py:197-310) on a planning graph given in CSR form:
+ * node_rc[n][2] = (row, col) of every node, neighbours adj[adj_ptr[v] .. adj_ptr[v+1]) in the graph's own
+ * adjacency order, eidx[eidx_ptr[e] .. eidx_ptr[e+1]) = field locations sampled along directed entry e (the
+ * edge's `indices`, the same list in both directions).  Breadth-first expansion from start_node with the given
+ * heading, U-turns forbidden, children pruned by g + bounding-box lower bound > least_cost + slack, equal
+ * (pose, heading, visited, g) children merged; every root path of the expansion DAG to a node that visited all
+ * waypoints is returned in networkx.all_shortest_paths order.  n_waypoints <= 64.  *handle_out owns the result
+ * until algp_paths_free. */
+int algp_paths_enumerate(int32_t n_nodes, const int32_t* node_rc, const int64_t* adj_ptr, const int32_t* adj,
+                         const int64_t* eidx_ptr, const int32_t* eidx, int32_t start_node, int32_t heading_r,
+                         int32_t heading_c, const int32_t* waypoint_nodes, int32_t n_waypoints, double least_cost,
+                         double slack, int64_t max_tree_nodes, void** handle_out);
+/* sizes[0..5] = {paths, total path nodes, total indices, tree nodes, merged children, longest index list} */
+int algp_paths_sizes(const void* handle, int64_t* sizes, double* least_cost);
+/* ragged copies: path_ptr[paths+1] / path_nodes, idx_ptr[paths+1] / idx, cost[paths]; any pointer may be NULL */
+int algp_paths_fetch(const void* handle, int64_t* path_ptr, int32_t* path_nodes, int64_t* idx_ptr, int32_t* idx,
+                     double* cost);
+/* slots[paths][k] (-1 = empty): the candidate matrix algp_score_sets / Agent.best_path take */
+int algp_paths_fill_slots(const void* handle, int32_t* slots, int64_t k);
+int algp_paths_free(void* handle);
+
 #ifdef __cplusplus
 }
 #endif

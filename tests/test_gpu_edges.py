@@ -140,3 +140,36 @@ def test_long_paths_match_literal_loop(criterion):
     assert ag.best_path(paths, new_static) == want
     got = ag._last_path_scores.cpu().numpy()
     np.testing.assert_allclose(got, ut, rtol=1e-8, atol=1e-8)
+
+
+def test_enumerated_paths_score_the_same_as_lists():
+    """Path enumeration -> slot matrix -> best_path on the device: the array form (no host lists) picks the path the
+    list form and the literal reference loop pick (golden graph of the reference's default field: 860 locations)."""
+    import os
+    from algp_b200 import paths as P
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_paths.npz"))
+    k = 2
+    c = {name: g["c%d_%s" % (k, name)] for name in ("rc", "adj_ptr", "adj", "eptr", "eidx", "start", "heading", "waypoints",
+                                                     "least_cost", "slack")}
+    nodes = [tuple(r) for r in c["rc"].tolist()]
+    ps = P.enumerate_paths_arrays(nodes, c["rc"], c["adj_ptr"], c["adj"], c["eptr"], c["eidx"], int(c["start"]),
+                                  tuple(c["heading"].tolist()), c["waypoints"], float(c["least_cost"]), float(c["slack"]))
+    assert len(ps) > 100
+    n = 860
+    rng = np.random.default_rng(2)
+    X = rng.uniform(0, 30, (n, 2))
+    static = set(rng.choice(n, 50, replace=False).tolist())
+    mobile = set(rng.choice(n, 30, replace=False).tolist())
+    ag, th = _agent(X, static, mobile)
+    cov = O.OracleGP(th, "fp64").cov_mat(X, add_likelihood_var=True)
+    st = np.zeros(n, bool); st[list(static)] = True
+    mo = np.zeros(n, bool); mo[list(mobile)] = True
+    new_static = [int(i) for i in rng.choice(n, 4, replace=False)]
+    lists = ps.indices()
+    want, ut = O.best_path_literal(cov, st, mo, 0.1, 1.0, lists, new_static, return_utilities=True)
+    assert ag.best_path(lists, new_static) == want
+    s_list = ag._last_path_scores.cpu().numpy()
+    assert ag.best_path(ps.slots(), new_static) == want
+    s_arr = ag._last_path_scores.cpu().numpy()
+    np.testing.assert_allclose(s_list, ut, rtol=1e-8, atol=1e-8)
+    np.testing.assert_allclose(s_arr, ut, rtol=1e-8, atol=1e-8)
