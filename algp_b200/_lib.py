@@ -37,6 +37,7 @@ SIGNATURES = {
     "algp_trmm_rt_tf32": (C.c_int, [_p, _p, _i64, _i64, _p, _p, _i64, _i64, _p, _p]),
     "algp_split_i8": (C.c_int, [_p, _i64, _i64, _i64, _i32, _i32, _p, _p, _p]),
     "algp_trmm_rt_i8": (C.c_int, [_p, _p, _i64, _p, _p, _i64, _i32, _p, _p]),
+    "algp_trmm_rt_store_i8": (C.c_int, [_p, _p, _i64, _p, _p, _i64, _i32, _p, _i64, _p, _p]),
     "algp_gemm_nt_i8": (C.c_int, [_p, _p, _i64, _p, _p, _i64, _i64, _i32, _f64, _f64, _p, _i64, _i32, _i32, _p]),
     "algp_potrf_inv_i8": (C.c_int, [_p, _i64, _i64, _p, _i64, _i32, _i64, _p, _i64, _p, _p]),
     "algp_potrf_inv_i8_work_bytes": (_i64, [_i64, _i32, _i64]),

@@ -148,7 +148,8 @@ class HotPath(object):
                 and st["state"].ldw - st["state"].ncols >= capacity:
             return st["state"], pi
         base = np.nonzero(pi > 0)[0]
-        state = engine.PosteriorState(hyper, self._device_X(), base, pi, is_static=static_sampled, capacity=capacity)
+        state = engine.PosteriorState(hyper, self._device_X(), base, pi, is_static=static_sampled, capacity=capacity,
+                                      precision=getattr(self.gp, "precision", "fp64"))
         self._hot_state = dict(hyper=hyper.key(), pi=pi.copy(), state=state)
         return state, pi
 

@@ -247,12 +247,17 @@ gemm_i8_kernel(const I8Gemm p) {
           }
         } else {
           const double as = p.alpha * sa;
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            v[i] *= sb_s[c0 + i];
+            ss = fma(v[i], v[i], ss);                 // row norms of A B^T ride along when asked for
+          }
           if (!p.transposed) {
             // thread = row: 16 consecutive doubles (one 128-byte line) per chunk
             double* crow = p.C + (int64_t)(m0 + row) * p.ldc + n0 + c0;
 #pragma unroll
             for (int i = 0; i < 16; i += 2) {
-              double2 o = make_double2(v[i] * sb_s[c0 + i] * as, v[i + 1] * sb_s[c0 + i + 1] * as);
+              double2 o = make_double2(v[i] * as, v[i + 1] * as);
               if (p.beta != 0.0) {
                 const double2 old = *reinterpret_cast<const double2*>(crow + i);
                 o.x = fma(p.beta, old.x, o.x);
@@ -265,14 +270,14 @@ gemm_i8_kernel(const I8Gemm p) {
 #pragma unroll
             for (int i = 0; i < 16; ++i) {
               double* ct = p.C + (int64_t)(n0 + c0 + i) * p.ldc + m0 + row;
-              double o = v[i] * sb_s[c0 + i] * as;
+              double o = v[i] * as;
               if (p.beta != 0.0) o = fma(p.beta, *ct, o);
               *ct = o;
             }
           }
         }
       }
-      if (MODE == 0) p.rn_partial[(int64_t)(m0 + row) * p.rn_nt + nt] = ss * sa * sa;
+      if (MODE == 0 || p.rn_partial) p.rn_partial[(int64_t)(m0 + row) * p.rn_nt + nt] = ss * sa * sa;
     }
   } else if (warp == 4 && lane == 0) {
     // ===================== MMA issuer (one thread) =====================
@@ -358,7 +363,7 @@ int i8_gemm(const I8Gemm& a, int nslices, cudaStream_t st) {
   if (a.MT == 0 || a.NT == 0) return ALGP_OK;
   if (((uintptr_t)a.a_tiles | (uintptr_t)a.b_tiles) & 15) return ALGP_ERR_INVALID;
   if (a.C) {
-    if (a.rn_partial || a.ldc < 2 || (a.ldc & 1) || ((uintptr_t)a.C & 15)) return ALGP_ERR_INVALID;
+    if (a.ldc < 2 || (a.ldc & 1) || ((uintptr_t)a.C & 15)) return ALGP_ERR_INVALID;
     switch (nslices) {
       case 2: return launch_gemm<2, 1>(a, st);
       case 3: return launch_gemm<3, 1>(a, st);
@@ -407,6 +412,29 @@ extern "C" int algp_trmm_rt_i8(const int8_t* Kt, const double* Kscale, int64_t m
 
 // C [mpad x npad] = alpha A B^T + beta C from the digit tiles of A [mpad x kpad] (tile_rows 128) and B [npad x kpad]
 // (tile_rows 64); transposed != 0 stores C^T ([npad x mpad], ldc its row stride)
+// V = K Linv^T stored [mpad x npad] (row stride ldv) AND its row-norm partials rn_partial[m][t] (t < npad/64): the
+// W^T build of the posterior state (Sigma_{:,B} L^-T) on the INT8 tensor cores
+extern "C" int algp_trmm_rt_store_i8(const int8_t* Kt, const double* Kscale, int64_t mpad, const int8_t* Lt,
+                                     const double* Lscale, int64_t npad, int nslices, double* V, int64_t ldv,
+                                     double* rn_partial, void* stream) {
+  if (!V || mpad < 0 || npad < 0 || mpad % ALGP_BLK || npad % ALGP_BLK || ldv < npad) return ALGP_ERR_INVALID;
+  I8Gemm a = i8_gemm_default();
+  a.MT = (int)(mpad / I8_TM);
+  a.NT = (int)(npad / I8_TN);
+  a.a_tiles = Kt;
+  a.b_tiles = Lt;
+  a.kchunks = (int)(npad / I8_KC);
+  a.scale_a = Kscale;
+  a.scale_b = Lscale;
+  a.kend_rule = I8_KE_NT;              // Linv is lower triangular
+  a.nt_desc = 1;
+  a.C = V;
+  a.ldc = ldv;
+  a.rn_partial = rn_partial;
+  a.rn_nt = a.NT;
+  return i8_gemm(a, nslices, (cudaStream_t)stream);
+}
+
 extern "C" int algp_gemm_nt_i8(const int8_t* At, const double* Ascale, int64_t mpad, const int8_t* Bt, const double* Bscale,
                                int64_t npad, int64_t kpad, int nslices, double alpha, double beta, double* C, int64_t ldc,
                                int transposed, int lower_only, void* stream) {

@@ -22,6 +22,7 @@ MAX_SET = 2048         # slots per candidate algp_score_sets_large accepts
 I8_FACTOR_SLICES = 8   # digit planes of the recursive INT8 factorisation (56 bits: fp64-grade trailing updates)
 I8_FACTOR_BASE = 2048  # blocks of this many rows or fewer are factored by the DMMA kernels
 I8_FACTOR_MIN = 8192   # factor="auto": smallest padded N that takes the INT8 factorisation
+I8_MAX_K = 32768       # k extent the digit GEMM accepts (8 pairs x 2^15 x 2^12 < 2^31)
 I8_SLICES = 7          # digit planes of the INT8 variance path: 7 x 7 = 49 bits below each row's scale (8 = 56 bits)
 CONST = 0.5 * np.log(2 * np.pi * np.exp(1))        # utils.py:10
 KIND = {"rbf": 0, None: 0, "matern": 1}
@@ -140,7 +141,7 @@ class GPFactor(object):
         self.Linv = torch.empty((self.Npad, self.Npad), dtype=torch.float64, device=dev)
         self.info = torch.zeros(1, dtype=torch.int32, device=dev)
         if factor == "auto":
-            factor = "i8" if self.Npad >= I8_FACTOR_MIN else "dmma"
+            factor = "i8" if I8_FACTOR_MIN <= self.Npad <= 2 * I8_MAX_K else "dmma"
         if factor == "i8" and self.Npad > I8_FACTOR_BASE:
             potrf_inv_i8(self.L, self.Linv, self.info)
         else:
@@ -237,12 +238,27 @@ class GPFactor(object):
         call("algp_trmm_rt_i8", ptr(kt), ptr(ks), Mpad, ptr(lt), ptr(ls), self.Npad, nslices, ptr(rn), stream())
         return rn
 
+    def whiten_store_i8(self, Ks, V_out, nslices=I8_FACTOR_SLICES):
+        """V_out[:, :Npad] = Ks L^-T through exact INT8 digit GEMMs; returns the row-norm partials [Mpad, Npad/64]."""
+        cache = getattr(self, "_linv_i8", None)
+        if cache is None or cache[0] != nslices:
+            self._linv_i8 = cache = (nslices,) + self.split_i8(self.Linv, nslices, 64)
+        _, lt, ls = cache
+        kt, ks = self.split_i8(Ks, nslices, 128)
+        Mpad = Ks.shape[0]
+        rn = torch.empty((Mpad, self.Npad // 64), dtype=torch.float64, device=Ks.device)
+        call("algp_trmm_rt_store_i8", ptr(kt), ptr(ks), Mpad, ptr(lt), ptr(ls), self.Npad, nslices, ptr(V_out),
+             V_out.stride(0), ptr(rn), stream())
+        return rn
+
     def mean_var(self, xs, y0, ymean, test_var=None, want_var=True, max_rows=65536, precision="fp64"):
         """Posterior mean (and latent variance) at xs: utils.py:300-308 without the inverse.
         precision="tf32" runs the O(N^2 M) variance step on the tcgen05 tensor cores (1e-4 tier);
         precision="i8" runs it as exact INT8 digit GEMMs on the same tensor cores (fp64 tier)."""
         if precision not in ("fp64", "tf32", "i8"):
             raise ValueError("precision must be 'fp64', 'i8' or 'tf32'")
+        if precision == "i8" and self.Npad > I8_MAX_K:
+            precision = "fp64"        # beyond the exact-accumulation range of the digit GEMM: DMMA path
         alpha, _ = self.solve(y0)
         M = xs.shape[0]
         mu = torch.empty(M, dtype=torch.float64, device=xs.device)
@@ -292,7 +308,9 @@ class PosteriorState(object):
     H_base = H(B), the running precisions pi and static flags.  ``capacity`` extra
     columns are reserved for rank-1 appends (greedy commits)."""
 
-    def __init__(self, hyper, X, base_idx, pi0, is_static=None, capacity=0):
+    def __init__(self, hyper, X, base_idx, pi0, is_static=None, capacity=0, precision="fp64"):
+        """precision="i8": the factor (from N = 8192) and the W^T build (from N = 1024) run as exact INT8 digit
+        GEMMs with 8 planes (fp64-grade) instead of DMMA."""
         dev = X.device
         self.hyper = hyper
         self.X = X
@@ -316,13 +334,17 @@ class PosteriorState(object):
             bidx = to_dev(base_idx, dtype=torch.int64, device=dev)
             xb = X.index_select(0, bidx).contiguous()
             inv_pi = to_dev(1.0 / pi0[base_idx], device=dev)
-            self.factor = GPFactor(hyper, xb, diag_add=inv_pi, diag_scalar=hyper.noise)
+            self.factor = GPFactor(hyper, xb, diag_add=inv_pi, diag_scalar=hyper.noise,
+                                   factor="auto" if precision == "i8" else "dmma")
             self.Npad = self.factor.Npad
             self.ldw = pad_to(self.Npad + capacity, 16)
             Ks, _ = kbuild(hyper, X, xb, self.n_pad, self.Npad)
             call("algp_scatter_add", ptr(Ks), Ks.stride(0), ptr(bidx.to(torch.int32)), self.N0, hyper.noise, stream())
             self.Wt = torch.zeros((self.n_pad, self.ldw), dtype=torch.float64, device=dev)
-            _, rn = self.factor.whiten(Ks, want_V=True, want_norm=True, V_out=self.Wt)
+            if precision == "i8" and 1024 <= self.Npad <= I8_MAX_K:
+                rn = self.factor.whiten_store_i8(Ks, self.Wt)
+            else:
+                _, rn = self.factor.whiten(Ks, want_V=True, want_norm=True, V_out=self.Wt)
             del Ks
             self.diagP = rowsum(rn, -1.0, prior, rows=self.n)
             ldq = self.factor.logdet_quad()

@@ -106,6 +106,10 @@ int algp_split_i8(const double* src, int64_t rows, int64_t cols, int64_t ld, int
 int algp_trmm_rt_i8(const int8_t* Kt, const double* Kscale, int64_t mpad, const int8_t* Lt, const double* Lscale,
                     int64_t npad, int nslices, double* rn_partial, void* stream);
 
+/* algp_trmm_rt with V stored ([mpad x npad], row stride ldv) and, if rn_partial is not NULL, the same row-norm
+ * partials, from the digit tiles: the W^T = Sigma_{:,B} L^-T build of the posterior state. */
+int algp_trmm_rt_store_i8(const int8_t* Kt, const double* Kscale, int64_t mpad, const int8_t* Lt, const double* Lscale,
+                          int64_t npad, int nslices, double* V, int64_t ldv, double* rn_partial, void* stream);
 /* C [mpad x npad] = alpha A B^T + beta C from the digit tiles of A [mpad x kpad] (tile_rows 128) and
  * B [npad x kpad] (tile_rows 64), fp64-grade with nslices = 8; transposed != 0 stores C^T ([npad x mpad], ldc its
  * row stride); lower_only skips the tiles entirely above the diagonal.  mpad % 128 == 0, npad % 64 == 0,

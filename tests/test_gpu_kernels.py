@@ -412,3 +412,22 @@ def test_potf2_rank_variants_agree(N):
             assert int(info.item()) == bad + 1
     finally:
         call("algp_set_potf2_rank", 2)
+
+
+def test_posterior_state_i8_build_matches_dmma():
+    """precision='i8': W^T = Sigma_{:,B} L^-T and diag(P) through the digit GEMM (store + row-norm epilogue) agree with
+    the DMMA build, and so do the scores computed from them."""
+    X, y, tr, ytr, rng = field_problem(48, 48, 1100, seed=4)
+    th, hy = hyper_pair([3.0, 3.0], 1.0, 0.01, "rbf")
+    n = len(X)
+    pi0 = np.zeros(n); pi0[tr] = 100.0
+    s64 = engine.PosteriorState(hy, dev(X), tr, pi0, is_static=pi0 > 0)
+    s8 = engine.PosteriorState(hy, dev(X), tr, pi0, is_static=pi0 > 0, precision="i8")
+    assert s8.Npad >= 1024                                       # the digit path is the one that ran
+    np.testing.assert_allclose(s8.Wt.cpu().numpy(), s64.Wt.cpu().numpy(), rtol=0, atol=1e-11)
+    np.testing.assert_allclose(s8.diagP.cpu().numpy(), s64.diagP.cpu().numpy(), rtol=0, atol=1e-11)
+    free = np.setdiff1d(np.arange(n), tr)
+    idx = rng.choice(free, (500, 8)).astype(np.int32)
+    sc64 = s64.score_sets(dev(idx, torch.int32), None, delta_scalar=1.0).cpu().numpy()
+    sc8 = s8.score_sets(dev(idx, torch.int32), None, delta_scalar=1.0).cpu().numpy()
+    np.testing.assert_allclose(sc8, sc64, rtol=1e-10, atol=1e-9)
