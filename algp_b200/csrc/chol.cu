@@ -357,7 +357,9 @@ __global__ void __launch_bounds__(256, 1) potf2inv_rank_kernel(double* __restric
 
 // 1 = one column per barrier (potf2inv_kernel), 2 / 4 = rank-R steps.  Measured on B200 (scripts/prof_potf2.py):
 // 46.4 / 41.1 / 43.5 us per 128-block: the kernel is bound by instruction issue at two warps per scheduler
-// (~115 issued instructions per column per warp, a third of them DFMA), not by the barrier chain.
+// (~115 issued instructions per column per warp, a third of them DFMA), not by the barrier chain.  A DMMA-fragment
+// variant (8x8 tiles dealt to the warps, one DMMA per tile per 4-column step) was correct but 2x slower: per-tile
+// addressing and activity tests cost more issue slots than the eight DFMAs a DMMA replaces.
 static int g_potf2_rank = 2;
 extern "C" int algp_set_potf2_rank(int r) {
   if (r != 1 && r != 2 && r != 4) return ALGP_ERR_INVALID;

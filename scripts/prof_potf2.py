@@ -9,7 +9,8 @@ x = engine.to_dev(rng.uniform(0, 10, size=(128, 2)))
 hy = engine.Hyper(np.log([2.0, 2.0]), 0.0, np.log(1e-2), "rbf")
 A0, _ = engine.kbuild(hy, x, None, 128, 128, None, hy.noise, True)
 A = A0.clone(); Linv = torch.empty_like(A); info = torch.zeros(1, dtype=torch.int32, device=A.device)
-for r in (1, 2, 4):
+ranks = [int(v) for v in sys.argv[1].split(',')] if len(sys.argv) > 1 else [1, 2, 4]
+for r in ranks:
     call("algp_set_potf2_rank", r)
     ts = []
     for rep in range(6):
