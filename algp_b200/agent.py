@@ -13,6 +13,7 @@ stay in the reference.  Both criteria are covered: 'entropy' (the reference's
 default, run.py:218) and 'mutual_information' (agent.py:330-339, 388-397).
 """
 from copy import deepcopy
+from itertools import chain
 
 import numpy as np
 import torch
@@ -29,15 +30,29 @@ def _flags(data):
 
 
 def _pad_paths(paths, org_mobile):
-    """list-of-lists -> [P, k] int32 (-1 padded) holding each path's NEW mobile locations."""
-    rows = []
-    for p in paths:
-        p = np.unique(np.asarray(p, dtype=np.int64).reshape(-1))
-        rows.append(p[~org_mobile[p]])
-    k = max(1, max(len(r) for r in rows))
-    idx = np.full((len(rows), k), -1, dtype=np.int32)
-    for c, r in enumerate(rows):
-        idx[c, :len(r)] = r
+    """list-of-lists -> [P, k] int32 (-1 padded) holding each path's mobile locations that are not mobile-sampled
+    yet.  Repeats inside a path stay: the scoring kernels treat duplicate slots as idempotent (agent.py:377 sets a
+    boolean flag).  One pass over the Python lists, everything else vectorised."""
+    P = len(paths)
+    try:
+        lens = np.fromiter(map(len, paths), dtype=np.int64, count=P)
+        flat = np.fromiter(chain.from_iterable(paths), dtype=np.int64, count=int(lens.sum()))
+    except (TypeError, ValueError):                      # nested / array-valued entries: flatten path by path
+        arrs = [np.asarray(p, dtype=np.int64).reshape(-1) for p in paths]
+        lens = np.array([len(r) for r in arrs], dtype=np.int64)
+        flat = np.concatenate(arrs) if arrs else np.zeros(0, dtype=np.int64)
+    if flat.size == 0:
+        return np.full((P, 1), -1, dtype=np.int32)
+    rows = np.repeat(np.arange(P), lens)
+    keep = ~org_mobile[flat]
+    kept_before = np.cumsum(keep)
+    row_start = np.cumsum(lens) - lens
+    base = np.where(row_start > 0, kept_before[np.maximum(row_start, 1) - 1], 0)   # kept slots before each path
+    cols = kept_before - 1 - base[rows]
+    counts = np.bincount(rows[keep], minlength=P)
+    k = max(1, int(counts.max()) if counts.size else 1)
+    idx = np.full((P, k), -1, dtype=np.int32)
+    idx[rows[keep], cols[keep]] = flat[keep]
     return idx
 
 

@@ -404,6 +404,92 @@ def episode_bench(torch, engine, side=200, n_pilot=1024, acquisitions=500, per_b
             "entropy_first_last": [res["H"][0], res["H"][-1]]}
 
 
+def default_scale_bench(torch, engine, cpu_sample=24):
+    """BASELINE configs[0] scale (the reference's own CPU-runnable case): a planning step on an 860-location field with
+    d = 6 inputs and a Matern-1.5 kernel -- enumerate the candidate paths through 5 waypoints on the reference's
+    planning graph (tests/golden/ref_paths.npz, case 4: 945 paths of up to 55 mobile readings), then
+    Agent.greedy(4) + Agent.best_path(paths) through the reference-facing API with host lists.  The CPU side is the
+    oracle's literal reference loops (agent.py:295-403) on a sample of the paths, scaled to all of them."""
+    import algp_b200
+    from algp_b200 import paths as P
+    import oracle as O
+    gpath = os.path.join(os.path.dirname(os.path.abspath(__file__)), "tests", "golden", "ref_paths.npz")
+    if not os.path.exists(gpath):
+        return {"skipped": "tests/golden/ref_paths.npz not found"}
+    g = np.load(gpath)
+    k = 4
+    c = {name: g["c%d_%s" % (k, name)] for name in ("rc", "adj_ptr", "adj", "eptr", "eidx", "start", "heading", "waypoints",
+                                                     "least_cost", "slack")}
+    nodes = [tuple(r) for r in c["rc"].tolist()]
+    enum = lambda: P.enumerate_paths_arrays(nodes, c["rc"], c["adj_ptr"], c["adj"], c["eptr"], c["eidx"], int(c["start"]),
+                                            tuple(c["heading"].tolist()), c["waypoints"], float(c["least_cost"]), float(c["slack"]))
+    enum()
+    t0 = time.perf_counter()
+    ps = enum()
+    slots = ps.slots()
+    enum_ms = (time.perf_counter() - t0) * 1e3
+    lists = ps.indices()
+    n, d = 860, 6
+    rng = np.random.default_rng(5)
+    cells = rng.choice(30 * 30, n, replace=False)
+    X = np.column_stack([cells // 30, (cells % 30) * 2.0, rng.integers(0, 2, (n, 4))]).astype(np.float64)
+    static = rng.choice(n, 300, replace=False)
+    mobile = rng.choice(np.setdiff1d(np.arange(n), static), 60, replace=False)
+
+    class Env(object):
+        pass
+    env = Env()
+    env.X, env.test_X, env.num_samples = X, X[:40], n
+    ag = algp_b200.Agent.__new__(algp_b200.Agent)
+    ag.env, ag.static_std, ag.mobile_std, ag.criterion = env, STATIC_STD, MOBILE_STD, 'entropy'
+    ag.static_data = [[] for _ in range(n)]
+    ag.mobile_data = [[] for _ in range(n)]
+    for i in static:
+        ag.static_data[i] = [0.5]
+    for i in mobile:
+        ag.mobile_data[i] = [0.4, 0.6]
+    ls, os_, noise = [3.0, 6.0, 1.5, 1.5, 1.5, 1.5], 1.0, 1e-2
+    ind, yv, var = ag.get_sampled_dataset()
+    ag.gp = algp_b200.GPR(kernel_params={'type': 'matern'})
+    ag.gp.reset(X[ind], yv, var)
+    with torch.no_grad():
+        ag.gp.model.kernel_covar_module.base_kernel.log_lengthscale.copy_(torch.tensor(np.log(ls)).view(1, 1, -1))
+        ag.gp.model.kernel_covar_module.log_outputscale.fill_(float(np.log(os_)))
+        ag.gp.likelihood.log_noise.fill_(float(np.log(noise)))
+    ag._post_update()
+
+    def step(paths_arg):
+        ag._hot_state = None                       # a fresh base set every planning step, as in run.py
+        picks = ag.greedy(4)
+        return picks, ag.best_path(paths_arg, picks)
+
+    step(lists)
+    torch.cuda.synchronize()
+    ts_l, ts_a = [], []
+    for _ in range(5):
+        t0 = time.perf_counter(); picks, best = step(lists); torch.cuda.synchronize(); ts_l.append((time.perf_counter() - t0) * 1e3)
+        t0 = time.perf_counter(); picks_a, best_a = step(slots); torch.cuda.synchronize(); ts_a.append((time.perf_counter() - t0) * 1e3)
+    # CPU: the literal loops of the reference on the same inputs
+    th = O.Theta.from_values(ls, os_, noise, "matern")
+    cov = O.OracleGP(th, "ref32").cov_mat(X, add_likelihood_var=True)
+    st = np.zeros(n, bool); st[static] = True
+    mo = np.zeros(n, bool); mo[mobile] = True
+    t0 = time.perf_counter()
+    cpu_picks = O.greedy_literal(cov, st, mo, STATIC_STD, MOBILE_STD, 4)
+    cpu_greedy_ms = (time.perf_counter() - t0) * 1e3
+    sample = lists[:cpu_sample]
+    t0 = time.perf_counter()
+    O.best_path_literal(cov, st, mo, STATIC_STD, MOBILE_STD, sample, cpu_picks)
+    cpu_paths_ms = (time.perf_counter() - t0) * 1e3 * len(lists) / len(sample)
+    return {"field_locations": n, "d": d, "kernel": "matern", "n_base": int(len(ind)), "paths": len(lists),
+            "longest_path": int(slots.shape[1]), "path_enumeration_ms": enum_ms,
+            "greedy4_plus_best_path_ms": {"lists": float(np.median(ts_l)), "slot_array": float(np.median(ts_a))},
+            "picks": [int(p) for p in picks], "best_path": int(best), "same_choice_array_form": bool(best == best_a and picks == picks_a),
+            "cpu_literal_loops_ms": {"greedy4": cpu_greedy_ms, "best_path_scaled": cpu_paths_ms, "cores": os.cpu_count(),
+                                     "sample": "%d of %d paths" % (len(sample), len(lists)),
+                                     "same_picks": bool([int(p) for p in cpu_picks] == [int(p) for p in picks])}}
+
+
 def dgemm_peak(torch, n=8192, reps=3, sustained_s=1.5):
     """cuBLAS fp64 GEMM rate on this box: the DMMA roofline denominator (not in MEASURED_PEAKS.json).
     Returns (burst, sustained): best single call, and the mean over ~sustained_s of back-to-back calls
@@ -636,6 +722,11 @@ def run_ours(args, rank, world, local_rank):
             extra["episode"] = episode_bench(torch, engine)
         except Exception as e:
             extra["episode_error"] = repr(e)
+        if not args.no_cpu:
+            try:
+                extra["default_scale_step"] = default_scale_bench(torch, engine)
+            except Exception as e:
+                extra["default_scale_error"] = repr(e)
         if world == 1 and not args.no_cpu:
             ctx = cpu_reference_setup()
             cpu_score_sample(ctx, 0, 1)
