@@ -66,6 +66,9 @@ SIGNATURES = {
     "algp_append": (C.c_int, [_p, _i64, _i64, _p, _i64, _i32, _p, _f64, _i32, _f64, _p, _p, _p, _p, _f64,
                               _i32, _p, _p]),
     "algp_append_work_doubles": (_i64, [_i64]),
+    "algp_append_block": (C.c_int, [_p, _i64, _i64, _p, _i64, _i32, _p, _f64, _i32, _f64, _p, _p, _p, _p, _i32, _p, _f64,
+                                    _i32, _p, _p]),
+    "algp_append_block_work_doubles": (_i64, []),
 }
 
 ERR_NOT_PD = 3

@@ -507,6 +507,238 @@ __global__ void append_commit_kernel(double* __restrict__ Wt, int64_t ldw, int c
   if (loc < n) Wt[loc * ldw + col] = w[loc];
 }
 
+// ---------------------------------------------------------------------------
+// Block append: commit k <= 16 locations at once (the mobile readings of the chosen path, agent.py:179-192).
+// k rank-1 appends read Wt k times (HBM-bound, 8 n N bytes each); here Wt is read ONCE:
+//   1. the k x k block P_CC = Sigma_CC - Wt_C Wt_C^T (one warp per pair),
+//   2. its sequential elimination in one warp: denom_c and T[r][c] = w_c[j_r], exactly the values the k
+//      successive rank-1 appends would produce at the chosen rows,
+//   3. one pass over the locations: each warp takes 4 rows of Wt at a time, the k chosen rows are staged in
+//      shared memory by 256-column chunk, 4 x 16 dot products accumulate in registers, then
+//      w_c[loc] = (P0[loc,j_c] - sum_{c'<c} w_c'[loc] T[c][c']) / denom_c, written as k new columns.
+// ---------------------------------------------------------------------------
+#define AB_K 16          // slots per block
+#define AB_LB 4          // rows of Wt a warp carries at a time
+#define AB_CH 256        // columns staged per chunk
+struct AppendBlockArgs {
+  KernelParams kp;
+  double noise;
+  double* Wt; int64_t ldw; int ncols;
+  const double* X; int64_t n;
+  double* diagP; double* pi; uint8_t* is_static;
+  const long long* idx;                    // [k] chosen locations (device), distinct
+  const double* delta; double delta_scalar;
+  int k, mark_static;
+  double* pcc;                             // [AB_K x AB_K] P_CC, then T
+  double* denom;                           // [AB_K]
+};
+
+__global__ void __launch_bounds__(256) append_block_pairs_kernel(const AppendBlockArgs a) {
+  const int lane = threadIdx.x & 31;
+  const int pair = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int r = pair / AB_K, c = pair % AB_K;
+  if (r >= a.k || c > r) return;
+  const long long jr = a.idx[r], jc = a.idx[c];
+  const double* rr = a.Wt + jr * a.ldw;
+  const double* rc = a.Wt + jc * a.ldw;
+  double s = 0.0;
+  for (int q = lane; q < a.ncols; q += 32) s = fma(rr[q], rc[q], s);
+  s = warp_sum(s);
+  if (lane == 0) {
+    const int d = a.kp.d;
+    double r2 = 0.0;
+    for (int q = 0; q < d; ++q) {
+      const double df = (a.X[jr * d + q] - a.X[jc * d + q]) * a.kp.inv_ls[q];
+      r2 = fma(df, df, r2);
+    }
+    const double v = kern_from_r2(r2, a.kp.kind, a.kp.outputscale) + ((jr == jc) ? a.noise : 0.0) - s;
+    a.pcc[r * AB_K + c] = v;
+    a.pcc[c * AB_K + r] = v;
+  }
+}
+
+__global__ void append_block_eliminate_kernel(const AppendBlockArgs a) {
+  // one warp; lane r owns row r of the k x k block
+  __shared__ double P[AB_K][AB_K + 1];
+  const int r = threadIdx.x;
+  const int k = a.k;
+  if (r < k)
+    for (int c = 0; c < k; ++c) P[r][c] = a.pcc[r * AB_K + c];
+  __syncwarp();
+  for (int c = 0; c < k; ++c) {
+    const double dl = a.delta ? a.delta[c] : a.delta_scalar;
+    const double den = sqrt(P[c][c] + 1.0 / dl);
+    __syncwarp();
+    double w = 0.0;
+    if (r < k) w = P[r][c] / den;                  // w_c at location j_r
+    __syncwarp();
+    if (r < k) {
+      P[r][c] = w;                                 // column c now holds T[r][c] = w_c[j_r]
+      if (r == 0) a.denom[c] = den;
+    }
+    __syncwarp();
+    if (r < k)
+      for (int s2 = c + 1; s2 < k; ++s2) P[r][s2] = fma(-w, P[s2][c], P[r][s2]);
+    __syncwarp();
+  }
+  if (r < k) {
+    for (int c = 0; c < k; ++c) a.pcc[r * AB_K + c] = P[r][c];
+    const long long j = a.idx[r];
+    a.pi[j] += a.delta ? a.delta[r] : a.delta_scalar;
+    if (a.mark_static) a.is_static[j] = 1;
+  }
+}
+
+__global__ void __launch_bounds__(256) append_block_kernel(const AppendBlockArgs a) {
+  extern __shared__ __align__(16) double ab_smem[];
+  double* rows = ab_smem;                          // [AB_K][AB_CH] chunk of the chosen rows
+  double* Ts = rows + AB_K * AB_CH;                // [AB_K][AB_K] T
+  double* dn = Ts + AB_K * AB_K;                   // [AB_K] denom
+  double* xj = dn + AB_K;                          // [AB_K][d] scaled coordinates of the chosen locations
+  double* stage = xj + AB_K * ALGP_MAX_D;          // [8 warps][AB_LB][AB_K] per-warp scratch
+  long long* jloc = (long long*)(stage + 8 * AB_LB * AB_K);   // [AB_K]
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int k = a.k, d = a.kp.d;
+  for (int e = tid; e < AB_K * AB_K; e += 256) Ts[e] = a.pcc[e];
+  if (tid < AB_K) {
+    dn[tid] = tid < k ? a.denom[tid] : 1.0;
+    jloc[tid] = tid < k ? a.idx[tid] : -1;
+  }
+  for (int e = tid; e < AB_K * d; e += 256) {
+    const int c = e / d, q = e % d;
+    xj[c * ALGP_MAX_D + q] = c < k ? a.X[a.idx[c] * d + q] * a.kp.inv_ls[q] : 0.0;
+  }
+  double* mine = stage + warp * AB_LB * AB_K;
+  const int64_t groups = (a.n + 8 * AB_LB - 1) / (8 * AB_LB);
+  for (int64_t g = blockIdx.x; g < groups; g += gridDim.x) {
+    const int64_t loc0 = g * (8 * AB_LB) + warp * AB_LB;
+    double acc[AB_LB][AB_K];
+#pragma unroll
+    for (int l = 0; l < AB_LB; ++l)
+#pragma unroll
+      for (int c = 0; c < AB_K; ++c) acc[l][c] = 0.0;
+    for (int c0 = 0; c0 < a.ncols; c0 += AB_CH) {
+      __syncthreads();                             // the previous chunk is consumed
+      for (int e = tid; e < AB_K * (AB_CH / 2); e += 256) {
+        const int c = e / (AB_CH / 2), q = (e % (AB_CH / 2)) * 2;
+        double2 v = make_double2(0.0, 0.0);
+        if (c < k) {
+          const double* src = a.Wt + a.idx[c] * a.ldw + c0 + q;
+          if (c0 + q + 1 < a.ncols) v = *reinterpret_cast<const double2*>(src);
+          else if (c0 + q < a.ncols) v.x = src[0];
+        }
+        *reinterpret_cast<double2*>(rows + c * AB_CH + q) = v;
+      }
+      __syncthreads();
+#pragma unroll
+      for (int it = 0; it < AB_CH / 64; ++it) {
+        const int q = it * 64 + 2 * lane;
+        double2 x[AB_LB];
+#pragma unroll
+        for (int l = 0; l < AB_LB; ++l) {
+          x[l] = make_double2(0.0, 0.0);
+          const int64_t loc = loc0 + l;
+          if (loc < a.n) {
+            const double* src = a.Wt + loc * a.ldw + c0 + q;
+            if (c0 + q + 1 < a.ncols) x[l] = *reinterpret_cast<const double2*>(src);
+            else if (c0 + q < a.ncols) x[l].x = src[0];
+          }
+        }
+#pragma unroll
+        for (int c = 0; c < AB_K; ++c) {
+          const double2 y = *reinterpret_cast<const double2*>(rows + c * AB_CH + q);
+#pragma unroll
+          for (int l = 0; l < AB_LB; ++l) acc[l][c] = fma(x[l].x, y.x, fma(x[l].y, y.y, acc[l][c]));
+        }
+      }
+    }
+    // butterfly: every lane ends with all AB_LB x AB_K dot products; lane t keeps entry t (and t + 32)
+#pragma unroll
+    for (int l = 0; l < AB_LB; ++l)
+#pragma unroll
+      for (int c = 0; c < AB_K; ++c) {
+        const double v = warp_sum(acc[l][c]);
+        if (lane == ((l * AB_K + c) & 31)) mine[l * AB_K + c] = v;
+      }
+    __syncwarp();
+    // P0[loc, j_c] = Sigma[loc, j_c] - dot
+    for (int t = lane; t < AB_LB * AB_K; t += 32) {
+      const int l = t / AB_K, c = t % AB_K;
+      const int64_t loc = loc0 + l;
+      double p = 0.0;
+      if (loc < a.n && c < k) {
+        double r2 = 0.0;
+        for (int q = 0; q < d; ++q) {
+          const double df = a.X[loc * d + q] * a.kp.inv_ls[q] - xj[c * ALGP_MAX_D + q];
+          r2 = fma(df, df, r2);
+        }
+        p = kern_from_r2(r2, a.kp.kind, a.kp.outputscale) + ((loc == jloc[c]) ? a.noise : 0.0) - mine[t];
+      }
+      mine[t] = p;
+    }
+    __syncwarp();
+    // the k successive rank-1 columns of this row: lane l < AB_LB owns row loc0 + l
+    if (lane < AB_LB && loc0 + lane < a.n) {
+      double* pr = mine + lane * AB_K;
+      double ss = 0.0;
+      for (int c = 0; c < k; ++c) {
+        double v = pr[c];
+        for (int c1 = 0; c1 < c; ++c1) v = fma(-pr[c1], Ts[c * AB_K + c1], v);
+        v /= dn[c];
+        pr[c] = v;                                   // w_c[loc]
+        ss = fma(v, v, ss);
+      }
+      a.diagP[loc0 + lane] -= ss;
+    }
+    __syncwarp();
+    for (int t = lane; t < AB_LB * AB_K; t += 32) {
+      const int l = t / AB_K, c = t % AB_K;
+      if (loc0 + l < a.n && c < k) a.Wt[(loc0 + l) * a.ldw + a.ncols + c] = mine[t];
+    }
+    __syncwarp();
+  }
+}
+
+extern "C" int64_t algp_append_block_work_doubles(void) { return AB_K * AB_K + AB_K; }
+
+// Commit k (1..16) DISTINCT locations idx[k] (device int64) with precision increments delta[k] (device, or NULL for
+// delta_scalar): the same k new columns of Wt, diagP, pi and flags as k successive algp_append calls in that order.
+extern "C" int algp_append_block(double* Wt, int64_t ldw, int64_t ncols, const double* X, int64_t n, int d,
+                                 const double* log_ls_host, double log_os, int kind, double noise, double* diagP,
+                                 double* pi, uint8_t* is_static, const void* idx_dev, int k, const double* delta_dev,
+                                 double delta_scalar, int mark_static, double* work, void* stream) {
+  if (!Wt || !X || !diagP || !pi || !is_static || !idx_dev || !work || ncols < 0 || k < 1 || k > AB_K || ncols + k > ldw ||
+      (ldw & 1) || (!delta_dev && !(delta_scalar > 0.0)))
+    return ALGP_ERR_INVALID;
+  AppendBlockArgs a;
+  int rc = make_kernel_params(&a.kp, d, log_ls_host, log_os, kind);
+  if (rc) return rc;
+  a.noise = noise; a.Wt = Wt; a.ldw = ldw; a.ncols = (int)ncols; a.X = X; a.n = n;
+  a.diagP = diagP; a.pi = pi; a.is_static = is_static; a.idx = (const long long*)idx_dev;
+  a.delta = delta_dev; a.delta_scalar = delta_scalar; a.k = k; a.mark_static = mark_static;
+  a.pcc = work; a.denom = work + AB_K * AB_K;
+  if (n == 0) return ALGP_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  append_block_pairs_kernel<<<AB_K * AB_K / 8, 256, 0, st>>>(a);
+  ALGP_LAUNCH_CHECK();
+  append_block_eliminate_kernel<<<1, 32, 0, st>>>(a);
+  ALGP_LAUNCH_CHECK();
+  const size_t smem = (size_t)(AB_K * AB_CH + AB_K * AB_K + AB_K + AB_K * ALGP_MAX_D + 8 * AB_LB * AB_K) * 8 + AB_K * 8;
+  static bool configured = false;
+  if (!configured) {
+    ALGP_CUDA(cudaFuncSetAttribute(append_block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = true;
+  }
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int64_t groups = (n + 8 * AB_LB - 1) / (8 * AB_LB);
+  const int grid = (int)(groups < (int64_t)sms * 2 ? groups : (int64_t)sms * 2);
+  append_block_kernel<<<grid, 256, smem, st>>>(a);
+  ALGP_LAUNCH_CHECK();
+  return ALGP_OK;
+}
+
 extern "C" int64_t algp_append_work_doubles(int64_t n) { return n + 2; }
 
 extern "C" int algp_append(double* Wt, int64_t ldw, int64_t ncols, const double* X, int64_t n, int d,

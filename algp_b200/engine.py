@@ -406,6 +406,24 @@ class PosteriorState(object):
              C.c_void_p(j_dev.data_ptr()), float(delta), int(mark_static), ptr(self._appwork), stream())
         self.ncols += 1
 
+    def append_block(self, idx, delta, mark_static=False):
+        """Commit the DISTINCT locations idx (host ints or a device int64 tensor) with precision increment delta each:
+        the same columns as successive append() calls, with Wt read once per 16 locations."""
+        if not torch.is_tensor(idx):
+            idx = to_dev(np.asarray(idx, dtype=np.int64), dtype=torch.int64, device=self.X.device)
+        k_all = int(idx.shape[0])
+        if self.ncols + k_all > self.ldw:
+            raise RuntimeError("PosteriorState capacity exhausted (%d columns)" % self.ldw)
+        if getattr(self, "_blkwork", None) is None:
+            self._blkwork = torch.empty(_lib.lib.algp_append_block_work_doubles(), dtype=torch.float64, device=self.X.device)
+        ls, ls_p = _lib.host_f64(self.hyper.log_ls)
+        for lo in range(0, k_all, 16):
+            k = min(16, k_all - lo)
+            call("algp_append_block", ptr(self.Wt), self.ldw, self.ncols, ptr(self.X), self.n, self.hyper.d, ls_p,
+                 self.hyper.log_os, self.hyper.kind, self.hyper.noise, ptr(self.diagP), ptr(self.pi), ptr(self.is_static),
+                 C.c_void_p(idx.data_ptr() + 8 * lo), k, None, float(delta), int(mark_static), ptr(self._blkwork), stream())
+            self.ncols += k
+
     def greedy(self, num_samples, d_static, return_utilities=False):
         """Agent.greedy's selection loop (agent.py:313-354) entirely on the device:
         utilities -> argmax -> rank-1 append, one host read at the end."""

@@ -4,8 +4,9 @@ reference agent.py:125-229, reduced to its GP arithmetic).
 Per batch: `greedy` picks `per_batch` static locations (agent.py:141), the candidate paths through
 them are scored by joint entropy (agent.py:168), the winner's mobile readings are committed
 (agent.py:179-192).  Every commit is a rank-1 downdate of the posterior stored as one appended
-column of Wt, so nothing is re-factorised.  Path enumeration itself (env.py:197-310) is the
-planner's job and out of scope; callers pass the candidate paths per batch (`path_fn`).
+column of Wt, so nothing is re-factorised; a path's readings are committed as one block append
+(Wt read once per 16 readings).  Callers pass the candidate paths per batch (`path_fn`);
+algp_b200.paths enumerates them on the reference's planning graph.
 With torch.distributed initialised, each rank scores a contiguous block of the paths and every
 rank applies the same commits (algp_b200.dist).
 """
@@ -52,16 +53,16 @@ def run_episode(hyper, X, static_flags, mobile_flags, static_std, mobile_std, ba
         if return_scores:
             out["scores"].append(score)
         # commit the winner's NEW mobile readings (the flag is boolean: repeats add nothing)
-        seen = set()
+        seen = []
         for j in paths[best]:
             j = int(j)
             if j < 0 or mobile[j] or j in seen:
                 continue
-            seen.add(j)
-            jbuf.fill_(j)
-            state.append(jbuf, d_m, mark_static=False)
+            seen.append(j)
             mobile[j] = True
         if seen:
+            # one block append: Wt is read once for the whole path instead of once per reading
+            state.append_block(seen, d_m, mark_static=False)
             skip = engine.to_dev(mobile.astype(np.uint8), dtype=torch.uint8, device=dev)
         # H(B + path) is exactly the winning score
         state.H_base_dev.fill_(score)

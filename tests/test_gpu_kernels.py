@@ -431,3 +431,30 @@ def test_posterior_state_i8_build_matches_dmma():
     sc64 = s64.score_sets(dev(idx, torch.int32), None, delta_scalar=1.0).cpu().numpy()
     sc8 = s8.score_sets(dev(idx, torch.int32), None, delta_scalar=1.0).cpu().numpy()
     np.testing.assert_allclose(sc8, sc64, rtol=1e-10, atol=1e-9)
+
+
+@pytest.mark.parametrize("k", [1, 5, 16, 23])
+def test_append_block_equals_successive_appends(k):
+    """k locations committed at once: the same Wt columns, diag(P), precisions and scores as k rank-1 appends."""
+    X, y, tr, ytr, rng = field_problem(30, 34, 300, seed=8)
+    th, hy = hyper_pair([3.0, 2.5], 1.3, 0.02, "matern")
+    n = len(X)
+    pi0 = np.zeros(n); pi0[tr] = 100.0
+    free = np.setdiff1d(np.arange(n), tr)
+    chosen = rng.choice(free, k, replace=False)
+    chosen[0] = tr[3]                                   # an already-sampled location gets more precision
+    seq = engine.PosteriorState(hy, dev(X), tr, pi0, is_static=pi0 > 0, capacity=40)
+    blk = engine.PosteriorState(hy, dev(X), tr, pi0, is_static=pi0 > 0, capacity=40)
+    jb = torch.empty(1, dtype=torch.int64, device=seq.X.device)
+    for j in chosen:
+        jb.fill_(int(j))
+        seq.append(jb, 1.0, mark_static=False)
+    blk.append_block([int(j) for j in chosen], 1.0, mark_static=False)
+    assert blk.ncols == seq.ncols == seq.Npad + k
+    np.testing.assert_allclose(blk.Wt.cpu().numpy(), seq.Wt.cpu().numpy(), rtol=0, atol=1e-12)
+    np.testing.assert_allclose(blk.diagP.cpu().numpy(), seq.diagP.cpu().numpy(), rtol=0, atol=1e-12)
+    np.testing.assert_array_equal(blk.pi.cpu().numpy(), seq.pi.cpu().numpy())
+    np.testing.assert_array_equal(blk.is_static.cpu().numpy(), seq.is_static.cpu().numpy())
+    idx = rng.choice(free, (64, 8)).astype(np.int32)
+    np.testing.assert_allclose(blk.score_sets(dev(idx, torch.int32), None, delta_scalar=1.0).cpu().numpy(),
+                               seq.score_sets(dev(idx, torch.int32), None, delta_scalar=1.0).cpu().numpy(), rtol=1e-11, atol=1e-10)
