@@ -22,6 +22,7 @@ from . import engine
 from .models import GPR
 from .utils import predictive_distribution
 
+STATE_SPARE_COLUMNS = 256   # room for samples added between two planning steps without re-factorising
 MAX_SET = engine.MAX_SET      # slots per candidate the scoring kernels accept (algp_score_sets / _large)
 
 
@@ -154,19 +155,48 @@ class HotPath(object):
         return cached[1].copy(), cached[2].copy()
 
     def _state_for(self, static_sampled, mobile_sampled, capacity):
-        """Posterior state whose base set carries exactly these flags; reused when the cached one
-        (e.g. left by greedy with its picks appended) already matches."""
+        """Posterior state whose base set carries exactly these flags.  The cached one is reused when it already
+        matches (e.g. left by greedy with its picks appended), EXTENDED by block appends when the flags only gained
+        samples since (the usual case between two planning steps: nothing is re-factorised), rebuilt otherwise
+        (new hyper-parameters, samples removed, no spare columns)."""
         pi = static_sampled / self.static_std ** 2 + mobile_sampled / self.mobile_std ** 2
         hyper = self.gp.hyper()
         st = getattr(self, "_hot_state", None)
-        if st is not None and st["hyper"] == hyper.key() and np.array_equal(st["pi"], pi) \
-                and st["state"].ldw - st["state"].ncols >= capacity:
-            return st["state"], pi
+        if st is not None and st["hyper"] == hyper.key():
+            state = st["state"]
+            room = state.ldw - state.ncols
+            if np.array_equal(st["pi"], pi) and room >= capacity:
+                return state, pi
+            diff = pi - st["pi"]
+            new = np.nonzero(diff > 0)[0]
+            if state.N0 > 0 and (diff >= 0).all() and 0 < len(new) <= engine.MAX_SET and room >= capacity + len(new):
+                self._extend_state(st, new, diff[new], static_sampled)
+                st["pi"] = pi.copy()
+                return state, pi
         base = np.nonzero(pi > 0)[0]
-        state = engine.PosteriorState(hyper, self._device_X(), base, pi, is_static=static_sampled, capacity=capacity,
+        state = engine.PosteriorState(hyper, self._device_X(), base, pi, is_static=static_sampled,
+                                      capacity=capacity + STATE_SPARE_COLUMNS,
                                       precision=getattr(self.gp, "precision", "fp64"))
-        self._hot_state = dict(hyper=hyper.key(), pi=pi.copy(), state=state)
+        self._hot_state = dict(hyper=hyper.key(), pi=pi.copy(), state=state, static=np.array(static_sampled, dtype=bool))
         return state, pi
+
+    def _extend_state(self, st, new, delta, static_sampled):
+        """Add precision `delta` at the locations `new` to the cached state: H(B') is the joint entropy of the added
+        set given B (one scoring call), the posterior follows by block appends (Wt read once per 16 locations)."""
+        state = st["state"]
+        dev = state.X.device
+        idx = engine.to_dev(np.asarray(new, dtype=np.int32)[None, :], dtype=torch.int32, device=dev)
+        dl = engine.to_dev(np.asarray(delta, dtype=np.float64)[None, :], device=dev)
+        h_new = float(state.score_sets(idx, dl)[0].item())
+        newly_static = np.asarray(static_sampled, dtype=bool)[new] & ~st["static"][new]
+        for mark in (True, False):
+            sel = newly_static == mark
+            if sel.any():
+                state.append_block(np.asarray(new)[sel], np.asarray(delta)[sel], mark_static=mark)
+        st["static"] = np.array(static_sampled, dtype=bool)
+        state.H_base_dev.fill_(h_new)
+        state._H_base = h_new
+        state._mi_ctx = None
 
     def _use_mi(self):
         crit = getattr(self, "criterion", "entropy")
@@ -186,6 +216,7 @@ class HotPath(object):
         pi = self._hot_state["pi"]
         for j in picks:
             pi[j] += d
+            self._hot_state["static"][j] = True
         return picks
 
     def _greedy_mi(self, state, pi, num_samples, d):

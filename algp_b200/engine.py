@@ -417,11 +417,18 @@ class PosteriorState(object):
         if getattr(self, "_blkwork", None) is None:
             self._blkwork = torch.empty(_lib.lib.algp_append_block_work_doubles(), dtype=torch.float64, device=self.X.device)
         ls, ls_p = _lib.host_f64(self.hyper.log_ls)
+        dl_dev, dl_scalar = None, 0.0
+        if np.ndim(delta) == 0 and not torch.is_tensor(delta):
+            dl_scalar = float(delta)
+        else:                                            # one precision increment per location
+            dl_dev = delta if torch.is_tensor(delta) else to_dev(np.asarray(delta, dtype=np.float64), device=self.X.device)
         for lo in range(0, k_all, 16):
             k = min(16, k_all - lo)
             call("algp_append_block", ptr(self.Wt), self.ldw, self.ncols, ptr(self.X), self.n, self.hyper.d, ls_p,
                  self.hyper.log_os, self.hyper.kind, self.hyper.noise, ptr(self.diagP), ptr(self.pi), ptr(self.is_static),
-                 C.c_void_p(idx.data_ptr() + 8 * lo), k, None, float(delta), int(mark_static), ptr(self._blkwork), stream())
+                 C.c_void_p(idx.data_ptr() + 8 * lo), k,
+                 None if dl_dev is None else C.c_void_p(dl_dev.data_ptr() + 8 * lo), dl_scalar, int(mark_static),
+                 ptr(self._blkwork), stream())
             self.ncols += k
 
     def greedy(self, num_samples, d_static, return_utilities=False):

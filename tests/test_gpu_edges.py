@@ -173,3 +173,42 @@ def test_enumerated_paths_score_the_same_as_lists():
     s_arr = ag._last_path_scores.cpu().numpy()
     np.testing.assert_allclose(s_list, ut, rtol=1e-8, atol=1e-8)
     np.testing.assert_allclose(s_arr, ut, rtol=1e-8, atol=1e-8)
+
+
+def test_state_is_extended_not_rebuilt_between_planning_steps():
+    """Between two planning steps the sample flags only gain entries: the cached posterior state is extended by block
+    appends (same object, more columns) and gives the picks / path / scores of a state factored from scratch."""
+    rng = np.random.default_rng(12)
+    n = 400
+    X = rng.uniform(0, 20, (n, 2))
+    static0 = set(rng.choice(n, 40, replace=False).tolist())
+    mobile0 = set(rng.choice(n, 25, replace=False).tolist())
+    ag, th = _agent(X, static0, mobile0)
+    picks = ag.greedy(3)
+    paths = [rng.choice(n, L, replace=False).tolist() for L in (12, 30, 7, 18)]
+    best = ag.best_path(paths, picks)
+    state0 = ag._hot_state["state"]
+    ncols0 = state0.ncols
+    # the robot collects: the picks become static samples, the chosen path's locations mobile samples
+    for j in picks:
+        ag.static_data[j] = ag.static_data[j] + [1.0]
+    for j in paths[best]:
+        ag.mobile_data[j] = ag.mobile_data[j] + [0.7]
+    ag.collected = {'ind': list(range(len(picks) + len(paths[best]))), 'std': [], 'y': []}     # changes the flag stamp
+    picks2 = ag.greedy(2)
+    paths2 = [rng.choice(n, L, replace=False).tolist() for L in (9, 21, 140, 33)]
+    best2 = ag.best_path(paths2, picks2)
+    scores2 = ag._last_path_scores.cpu().numpy()
+    assert ag._hot_state["state"] is state0 and state0.ncols > ncols0            # extended in place
+    # the same situation on an agent that never saw the first step
+    static1 = static0 | set(picks)
+    mobile1 = mobile0 | set(paths[best])
+    fresh, _ = _agent(X, static1, mobile1)
+    assert fresh.greedy(2) == picks2
+    assert fresh.best_path(paths2, picks2) == best2
+    np.testing.assert_allclose(scores2, fresh._last_path_scores.cpu().numpy(), rtol=1e-10, atol=1e-9)
+    cov = O.OracleGP(th, "fp64").cov_mat(X, add_likelihood_var=True)
+    st = np.zeros(n, bool); st[list(static1)] = True
+    mo = np.zeros(n, bool); mo[list(mobile1)] = True
+    assert O.greedy_restructured(cov, st, mo, 0.1, 1.0, 2) == picks2
+    assert O.best_path_literal(cov, st, mo, 0.1, 1.0, paths2, picks2) == best2
