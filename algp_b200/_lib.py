@@ -35,9 +35,10 @@ SIGNATURES = {
     "algp_gemm_nt": (C.c_int, [_p, _i64, _p, _i64, _p, _i64, _i64, _i64, _i64, _f64, _f64, _i32, _p]),
     "algp_split_tf32": (C.c_int, [_p, _i64, _i64, _i64, _p, _p, _i64, _p]),
     "algp_trmm_rt_tf32": (C.c_int, [_p, _p, _i64, _i64, _p, _p, _i64, _i64, _p, _p]),
-    "algp_split_i8": (C.c_int, [_p, _i64, _i64, _i64, _i32, _i32, _p, _p, _p]),
-    "algp_trmm_rt_i8": (C.c_int, [_p, _p, _i64, _p, _p, _i64, _i32, _p, _p]),
-    "algp_trmm_rt_store_i8": (C.c_int, [_p, _p, _i64, _p, _p, _i64, _i32, _p, _i64, _p, _p]),
+    "algp_split_i8": (C.c_int, [_p, _i64, _i64, _i64, _i32, _i32, _p, _p, _p, _p]),
+    "algp_i8_mask_bytes": (_i64, [_i64, _i64, _i32]),
+    "algp_trmm_rt_i8": (C.c_int, [_p, _p, _p, _i64, _p, _p, _p, _i64, _i32, _p, _p]),
+    "algp_trmm_rt_store_i8": (C.c_int, [_p, _p, _p, _i64, _p, _p, _p, _i64, _i32, _p, _i64, _p, _p]),
     "algp_gemm_nt_i8": (C.c_int, [_p, _p, _i64, _p, _p, _i64, _i64, _i32, _f64, _f64, _p, _i64, _i32, _i32, _p]),
     "algp_potrf_inv_i8": (C.c_int, [_p, _i64, _i64, _p, _i64, _i32, _i64, _p, _i64, _p, _p]),
     "algp_potrf_inv_i8_work_bytes": (_i64, [_i64, _i32, _i64]),

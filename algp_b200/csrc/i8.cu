@@ -74,7 +74,7 @@ __host__ __device__ constexpr uint32_t idesc_i8(int M, int N) {
 template <int S>
 __global__ void __launch_bounds__(256)
 split_i8_kernel(const double* __restrict__ src, int64_t cols, int64_t ld, int tile_rows, int8_t* __restrict__ planes,
-                double* __restrict__ row_scale) {
+                double* __restrict__ row_scale, unsigned int* __restrict__ mask_words, int64_t mask_ld) {
   __shared__ int exps[8];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int64_t row0 = (int64_t)blockIdx.x * 8;
@@ -102,34 +102,53 @@ split_i8_kernel(const double* __restrict__ src, int64_t cols, int64_t ld, int ti
   const double sc = ldexp(1.0, 6 - exps[rr]);       // t0 = 64 y
   const int64_t tile = row / tile_rows;
   const int64_t plane_bytes = (int64_t)tile_rows * I8_KC;
-  const int64_t kchunks = cols / I8_KC;
+  const int64_t kchunks = cols / I8_KC, pieces = cols / 16;
   // byte offset of (row, k = 0, plane 0) inside its tile's first k chunk
   const int64_t row_off = ((row % tile_rows) / 8) * 256 + rr * 16;
-  for (int64_t j = tid >> 3; j < cols / 16; j += 32) {          // 16-column pieces of the row
-    double t[16];
+  // a warp covers 4 consecutive 16-column pieces (= 2 k chunks) of its 8 rows per iteration
+  for (int64_t j0 = 4 * warp; j0 < pieces; j0 += 32) {
+    const int64_t j = j0 + (lane >> 3);
+    const bool valid = j < pieces;
+    unsigned int occ = 0;                            // bit p: this thread wrote a non-zero digit into plane p
+    if (valid) {
+      double t[16];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const double2 v = *reinterpret_cast<const double2*>(x + j * 16 + 2 * i);
-      t[2 * i] = v.x * sc;
-      t[2 * i + 1] = v.y * sc;
-    }
-    int8_t* out = planes + ((tile * kchunks + (j >> 1)) * S) * plane_bytes + row_off + (j & 1) * 128;
-#pragma unroll
-    for (int p = 0; p < S; ++p) {
-      uint32_t w[4];
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        uint32_t pack = 0;
-#pragma unroll
-        for (int b = 0; b < 4; ++b) {
-          const int i = q * 4 + b;
-          const double d = rint(t[i]);              // |t| <= 64: the digit, exact
-          t[i] = (t[i] - d) * 128.0;                // exact remainder, next digit's scale
-          pack |= ((uint32_t)(__double2int_rn(d)) & 0xFFu) << (8 * b);
-        }
-        w[q] = pack;
+      for (int i = 0; i < 8; ++i) {
+        const double2 v = *reinterpret_cast<const double2*>(x + j * 16 + 2 * i);
+        t[2 * i] = v.x * sc;
+        t[2 * i + 1] = v.y * sc;
       }
-      *reinterpret_cast<uint4*>(out + (int64_t)p * plane_bytes) = make_uint4(w[0], w[1], w[2], w[3]);
+      int8_t* out = planes + ((tile * kchunks + (j >> 1)) * S) * plane_bytes + row_off + (j & 1) * 128;
+#pragma unroll
+      for (int p = 0; p < S; ++p) {
+        uint32_t w[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          uint32_t pack = 0;
+#pragma unroll
+          for (int b = 0; b < 4; ++b) {
+            const int i = q * 4 + b;
+            const double d = rint(t[i]);              // |t| <= 64: the digit, exact
+            t[i] = (t[i] - d) * 128.0;                // exact remainder, next digit's scale
+            pack |= ((uint32_t)(__double2int_rn(d)) & 0xFFu) << (8 * b);
+          }
+          w[q] = pack;
+        }
+        if ((w[0] | w[1] | w[2] | w[3]) != 0u) occ |= 1u << p;
+        *reinterpret_cast<uint4*>(out + (int64_t)p * plane_bytes) = make_uint4(w[0], w[1], w[2], w[3]);
+      }
+    }
+    if (mask_words) {
+      // plane occupancy of (row tile, k chunk): lanes 0-15 hold chunk j0/2, lanes 16-31 chunk j0/2 + 1
+#pragma unroll
+      for (int o = 1; o < 16; o <<= 1) occ |= __shfl_xor_sync(0xffffffffu, occ, o);
+      if ((lane & 15) == 0 && occ != 0u) {
+        const int64_t kc = (j0 >> 1) + (lane >> 4);
+        if (kc < kchunks) {
+          const int64_t byte = tile * mask_ld + kc;
+          atomicOr(mask_words + (byte >> 2), occ << (8 * (int)(byte & 3)));
+        }
+      }
     }
   }
 }
@@ -145,6 +164,37 @@ struct I8Cfg {
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024;
   static constexpr int TMEM_COLS = (S * I8_TN > 256) ? 512 : ((S * I8_TN > 128) ? 256 : 128);
 };
+
+// sequential reader of one tile's occupancy bytes, eight at a time, the next word prefetched
+struct MaskReader {
+  const uint8_t* m;
+  int base, kend;
+  unsigned long long cur, nxt;
+  __device__ MaskReader(const uint8_t* m_, int kbeg, int kend_) : m(m_), base(kbeg & ~7), kend(kend_), cur(~0ull), nxt(~0ull) {
+    if (m) {
+      cur = *reinterpret_cast<const unsigned long long*>(m + base);
+      if (base + 8 < kend) nxt = *reinterpret_cast<const unsigned long long*>(m + base + 8);
+    }
+  }
+  __device__ __forceinline__ uint32_t get(int kc) {
+    if (!m) return 0xffu;
+    if ((kc & ~7) != base) {
+      base += 8;
+      cur = nxt;
+      if (base + 8 < kend) nxt = *reinterpret_cast<const unsigned long long*>(m + base + 8);
+    }
+    return (uint32_t)(cur >> (8 * (kc & 7))) & 0xffu;
+  }
+};
+
+// some digit product p + q < S has both planes occupied
+template <int S>
+__device__ __forceinline__ bool stage_needed(uint32_t ma, uint32_t mb) {
+  bool need = false;
+#pragma unroll
+  for (int pa = 0; pa < S; ++pa) need = need || (((ma >> pa) & 1u) && (mb & ((1u << (S - pa)) - 1u)));
+  return need;
+}
 
 // MODE 0: row sums of squares per 64-column tile (variance path, nothing else is written)
 // MODE 1: C = alpha A B^T + beta C (optionally stored transposed)
@@ -194,19 +244,52 @@ gemm_i8_kernel(const I8Gemm p) {
   __syncthreads();
   fence_after();
   const uint32_t tmem = tmem_slot;
+  // the accumulators start from zero, so every MMA accumulates: with occupancy masks there is no fixed "first"
+  // product per group
+  if (warp < 4 && KT > 0) {
+#pragma unroll 1
+    for (int c0 = 0; c0 < S * I8_TN; c0 += 16) {
+      const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0;
+      asm volatile(
+          "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1};"
+          ::"r"(taddr), "r"(0u) : "memory");
+    }
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+  }
+  fence_before();
+  __syncthreads();
+  fence_after();
+  // plane-occupancy masks of the two operands' tiles (one byte per 32-byte k chunk, bit p = plane p holds a
+  // non-zero digit): chunks and planes that are all zero are neither loaded nor multiplied
+  const uint8_t* am = p.a_mask ? p.a_mask + (int64_t)mt * p.mask_ld : nullptr;
+  const uint8_t* bm = p.b_mask ? p.b_mask + (int64_t)nt * p.mask_ld : nullptr;
+  constexpr uint32_t ALLP = (1u << S) - 1u;
 
   if (warp < 4) {
-    if (tid == 0) {
+    if (tid == 0 && KT > 0) {
       // ===================== TMA producer (one thread) =====================
-      const int8_t* a_src = p.a_tiles + ((int64_t)mt * p.kchunks + kbeg) * C::A_BYTES;
-      const int8_t* b_src = p.b_tiles + ((int64_t)nt * p.kchunks + kbeg) * C::B_BYTES;
-      for (int it = 0; it < KT; ++it) {
+      const int8_t* a_src = p.a_tiles + (int64_t)mt * p.kchunks * C::A_BYTES;
+      const int8_t* b_src = p.b_tiles + (int64_t)nt * p.kchunks * C::B_BYTES;
+      MaskReader ra(am, kbeg, kend), rb(bm, kbeg, kend);
+      int it = 0;
+      for (int kc = kbeg; kc < kend; ++kc) {
+        const uint32_t ma = ra.get(kc) & ALLP, mb = rb.get(kc) & ALLP;
+        if (!stage_needed<S>(ma, mb)) continue;
         const int s = it % C::STAGES, u = it / C::STAGES;
+        ++it;
         if (u > 0) mbarrier_wait(&empty_bar[s], (u - 1) & 1);     // the MMAs that read this slot are done
         const uint32_t st = ring + (uint32_t)s * C::STAGE_BYTES;
-        expect_tx(&full_bar[s], C::STAGE_BYTES);
-        bulk_load(st, a_src + (int64_t)it * C::A_BYTES, C::A_BYTES, &full_bar[s]);
-        bulk_load(st + C::A_BYTES, b_src + (int64_t)it * C::B_BYTES, C::B_BYTES, &full_bar[s]);
+        const int8_t* asrc = a_src + (int64_t)kc * C::A_BYTES;
+        if (ma == ALLP) {
+          expect_tx(&full_bar[s], C::STAGE_BYTES);
+          bulk_load(st, asrc, C::A_BYTES, &full_bar[s]);
+        } else {
+          expect_tx(&full_bar[s], (uint32_t)__popc(ma) * C::A_PLANE + C::B_BYTES);
+#pragma unroll
+          for (int pa = 0; pa < S; ++pa)
+            if ((ma >> pa) & 1u) bulk_load(st + pa * C::A_PLANE, asrc + pa * C::A_PLANE, C::A_PLANE, &full_bar[s]);
+        }
+        bulk_load(st + C::A_BYTES, b_src + (int64_t)kc * C::B_BYTES, C::B_BYTES, &full_bar[s]);
       }
     }
     __syncwarp();
@@ -279,30 +362,38 @@ gemm_i8_kernel(const I8Gemm p) {
       }
       if (MODE == 0 || p.rn_partial) p.rn_partial[(int64_t)(m0 + row) * p.rn_nt + nt] = ss * sa * sa;
     }
-  } else if (warp == 4 && lane == 0) {
+  } else if (warp == 4 && lane == 0 && KT > 0) {
     // ===================== MMA issuer (one thread) =====================
     // The B digit planes of a stage are contiguous in shared memory ([plane][64 rows][32 B]), i.e. ONE K-major
     // operand of (S - p) x 64 rows, and group g = p + q lives at TMEM columns g x 64: a single MMA of A_p against
     // planes q0..q0+c-1 (N = 64c <= 256) lands every product in its own group.  S(S+1)/2 plane products become
     // ~S(S+1)/8 + S/2 instructions and A_p is read from shared memory once per <= 4 products instead of once each.
-    for (int it = 0; it < KT; ++it) {
+    MaskReader ra(am, kbeg, kend), rb(bm, kbeg, kend);
+    int it = 0;
+    for (int kc = kbeg; kc < kend; ++kc) {
+      const uint32_t ma = ra.get(kc) & ALLP, mb = rb.get(kc) & ALLP;
+      if (!stage_needed<S>(ma, mb)) continue;
       const int s = it % C::STAGES, u = it / C::STAGES;
+      ++it;
       mbarrier_wait(&full_bar[s], u & 1);
       fence_after();
       const uint32_t a0 = ring + (uint32_t)s * C::STAGE_BYTES, b0 = a0 + C::A_BYTES;
       const uint64_t da0 = desc_kmajor(a0), db0 = desc_kmajor(b0);
 #pragma unroll
       for (int pa = 0; pa < S; ++pa) {
+        if (!((ma >> pa) & 1u)) continue;
 #pragma unroll
         for (int q0 = 0; q0 < S - pa; q0 += 4) {
           const int cnt = (S - pa - q0) < 4 ? (S - pa - q0) : 4;
+          if (((mb >> q0) & ((1u << cnt) - 1u)) == 0u) continue;
           mma_i8(tmem + (uint32_t)((pa + q0) * I8_TN), da0 + (uint64_t)((pa * C::A_PLANE) >> 4),
-                 db0 + (uint64_t)((q0 * C::B_PLANE) >> 4), idesc_i8(I8_TM, cnt * I8_TN), (it != 0 || pa != 0) ? 1u : 0u);
+                 db0 + (uint64_t)((q0 * C::B_PLANE) >> 4), idesc_i8(I8_TM, cnt * I8_TN), 1u);
         }
       }
       commit_to(&empty_bar[s]);                                  // arrives when these MMAs have read the stage
     }
-    if (KT > 0) commit_to(&done_bar);                            // accumulators complete
+    if (it > 0) commit_to(&done_bar);                            // accumulators complete
+    else mbarrier_arrive(&done_bar);                             // every chunk was skipped: the zeros stand
   }
 
   fence_before();
@@ -314,8 +405,11 @@ gemm_i8_kernel(const I8Gemm p) {
 
 template <int S>
 int launch_split(const double* src, int64_t rows, int64_t cols, int64_t ld, int tile_rows, int8_t* planes, double* row_scale,
-                 cudaStream_t st) {
-  split_i8_kernel<S><<<(unsigned)(rows / 8), 256, 0, st>>>(src, cols, ld, tile_rows, planes, row_scale);
+                 uint8_t* mask, cudaStream_t st) {
+  const int64_t mask_ld = i8_mask_ld(cols);
+  if (mask) ALGP_CUDA(cudaMemsetAsync(mask, 0, (size_t)(rows / tile_rows) * mask_ld, st));
+  split_i8_kernel<S><<<(unsigned)(rows / 8), 256, 0, st>>>(src, cols, ld, tile_rows, planes, row_scale,
+                                                           reinterpret_cast<unsigned int*>(mask), mask_ld);
   ALGP_LAUNCH_CHECK();
   return ALGP_OK;
 }
@@ -338,20 +432,21 @@ int launch_gemm(const I8Gemm& a, cudaStream_t st) {
 }  // namespace
 
 int i8_split(const double* src, int64_t rows, int64_t cols, int64_t ld, int nslices, int tile_rows, int8_t* planes,
-             double* row_scale, cudaStream_t st) {
+             double* row_scale, uint8_t* mask, cudaStream_t st) {
+  if (mask && ((uintptr_t)mask & 7)) return ALGP_ERR_INVALID;
   if (!src || !planes || !row_scale || rows < 0 || cols < 0 || (cols % I8_KC) || (ld & 1) || ld < cols ||
       (tile_rows != I8_TM && tile_rows != I8_TN) || rows % tile_rows || nslices < 2 || nslices > I8_MAX_S)
     return ALGP_ERR_INVALID;
   if (((uintptr_t)src | (uintptr_t)planes) & 15) return ALGP_ERR_INVALID;
   if (rows == 0 || cols == 0) return ALGP_OK;
   switch (nslices) {
-    case 2: return launch_split<2>(src, rows, cols, ld, tile_rows, planes, row_scale, st);
-    case 3: return launch_split<3>(src, rows, cols, ld, tile_rows, planes, row_scale, st);
-    case 4: return launch_split<4>(src, rows, cols, ld, tile_rows, planes, row_scale, st);
-    case 5: return launch_split<5>(src, rows, cols, ld, tile_rows, planes, row_scale, st);
-    case 6: return launch_split<6>(src, rows, cols, ld, tile_rows, planes, row_scale, st);
-    case 7: return launch_split<7>(src, rows, cols, ld, tile_rows, planes, row_scale, st);
-    default: return launch_split<8>(src, rows, cols, ld, tile_rows, planes, row_scale, st);
+    case 2: return launch_split<2>(src, rows, cols, ld, tile_rows, planes, row_scale, mask, st);
+    case 3: return launch_split<3>(src, rows, cols, ld, tile_rows, planes, row_scale, mask, st);
+    case 4: return launch_split<4>(src, rows, cols, ld, tile_rows, planes, row_scale, mask, st);
+    case 5: return launch_split<5>(src, rows, cols, ld, tile_rows, planes, row_scale, mask, st);
+    case 6: return launch_split<6>(src, rows, cols, ld, tile_rows, planes, row_scale, mask, st);
+    case 7: return launch_split<7>(src, rows, cols, ld, tile_rows, planes, row_scale, mask, st);
+    default: return launch_split<8>(src, rows, cols, ld, tile_rows, planes, row_scale, mask, st);
   }
 }
 
@@ -362,6 +457,8 @@ int i8_gemm(const I8Gemm& a, int nslices, cudaStream_t st) {
     return ALGP_ERR_INVALID;           // K <= 2^15 keeps every group sum below 2^31 (8 pairs x 2^15 x 2^12 = 2^30)
   if (a.MT == 0 || a.NT == 0) return ALGP_OK;
   if (((uintptr_t)a.a_tiles | (uintptr_t)a.b_tiles) & 15) return ALGP_ERR_INVALID;
+  if (((uintptr_t)a.a_mask | (uintptr_t)a.b_mask) & 7) return ALGP_ERR_INVALID;
+  if ((a.a_mask || a.b_mask) && a.mask_ld < (a.kchunks + 7) / 8 * 8) return ALGP_ERR_INVALID;
   if (a.C) {
     if (a.ldc < 2 || (a.ldc & 1) || ((uintptr_t)a.C & 15)) return ALGP_ERR_INVALID;
     switch (nslices) {
@@ -387,13 +484,19 @@ int i8_gemm(const I8Gemm& a, int nslices, cudaStream_t st) {
 }
 
 extern "C" int algp_split_i8(const double* src, int64_t rows, int64_t cols, int64_t ld, int nslices, int tile_rows,
-                             int8_t* planes, double* row_scale, void* stream) {
-  return i8_split(src, rows, cols, ld, nslices, tile_rows, planes, row_scale, (cudaStream_t)stream);
+                             int8_t* planes, double* row_scale, uint8_t* mask, void* stream) {
+  return i8_split(src, rows, cols, ld, nslices, tile_rows, planes, row_scale, mask, (cudaStream_t)stream);
+}
+
+extern "C" int64_t algp_i8_mask_bytes(int64_t rows, int64_t cols, int tile_rows) {
+  if (rows < 0 || cols < 0 || (tile_rows != I8_TM && tile_rows != I8_TN)) return 0;
+  return (rows + tile_rows - 1) / tile_rows * i8_mask_ld(cols) + 8;
 }
 
 // rn_partial[m][t] (t < npad/64) = sum over 64-column tile t of (K Linv^T)[m][.]^2 from the digit tiles
-extern "C" int algp_trmm_rt_i8(const int8_t* Kt, const double* Kscale, int64_t mpad, const int8_t* Lt, const double* Lscale,
-                               int64_t npad, int nslices, double* rn_partial, void* stream) {
+extern "C" int algp_trmm_rt_i8(const int8_t* Kt, const double* Kscale, const uint8_t* Kmask, int64_t mpad, const int8_t* Lt,
+                               const double* Lscale, const uint8_t* Lmask, int64_t npad, int nslices, double* rn_partial,
+                               void* stream) {
   if (!rn_partial || mpad < 0 || npad < 0 || mpad % ALGP_BLK || npad % ALGP_BLK) return ALGP_ERR_INVALID;
   I8Gemm a = i8_gemm_default();
   a.MT = (int)(mpad / I8_TM);
@@ -407,6 +510,7 @@ extern "C" int algp_trmm_rt_i8(const int8_t* Kt, const double* Kscale, int64_t m
   a.nt_desc = 1;
   a.rn_partial = rn_partial;
   a.rn_nt = a.NT;
+  a.a_mask = Kmask; a.b_mask = Lmask; a.mask_ld = i8_mask_ld(npad);
   return i8_gemm(a, nslices, (cudaStream_t)stream);
 }
 
@@ -414,9 +518,9 @@ extern "C" int algp_trmm_rt_i8(const int8_t* Kt, const double* Kscale, int64_t m
 // (tile_rows 64); transposed != 0 stores C^T ([npad x mpad], ldc its row stride)
 // V = K Linv^T stored [mpad x npad] (row stride ldv) AND its row-norm partials rn_partial[m][t] (t < npad/64): the
 // W^T build of the posterior state (Sigma_{:,B} L^-T) on the INT8 tensor cores
-extern "C" int algp_trmm_rt_store_i8(const int8_t* Kt, const double* Kscale, int64_t mpad, const int8_t* Lt,
-                                     const double* Lscale, int64_t npad, int nslices, double* V, int64_t ldv,
-                                     double* rn_partial, void* stream) {
+extern "C" int algp_trmm_rt_store_i8(const int8_t* Kt, const double* Kscale, const uint8_t* Kmask, int64_t mpad,
+                                     const int8_t* Lt, const double* Lscale, const uint8_t* Lmask, int64_t npad, int nslices,
+                                     double* V, int64_t ldv, double* rn_partial, void* stream) {
   if (!V || mpad < 0 || npad < 0 || mpad % ALGP_BLK || npad % ALGP_BLK || ldv < npad) return ALGP_ERR_INVALID;
   I8Gemm a = i8_gemm_default();
   a.MT = (int)(mpad / I8_TM);
@@ -432,6 +536,7 @@ extern "C" int algp_trmm_rt_store_i8(const int8_t* Kt, const double* Kscale, int
   a.ldc = ldv;
   a.rn_partial = rn_partial;
   a.rn_nt = a.NT;
+  a.a_mask = Kmask; a.b_mask = Lmask; a.mask_ld = i8_mask_ld(npad);
   return i8_gemm(a, nslices, (cudaStream_t)stream);
 }
 

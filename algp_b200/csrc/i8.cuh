@@ -23,16 +23,22 @@ struct I8Gemm {
   double* C; int64_t ldc;              // MODE 1: C = alpha A B^T + beta C
   double alpha, beta;
   int transposed;                      // MODE 1: store C^T (ldc = row stride of the transposed matrix)
+  const uint8_t* a_mask;               // [MT][mask_ld] plane-occupancy byte per 32-byte k chunk (NULL: all occupied)
+  const uint8_t* b_mask;               // [NT][mask_ld]
+  int64_t mask_ld;                     // i8_mask_ld(K)
 };
+
+inline int64_t i8_mask_ld(int64_t cols) { return (cols / I8_KC + 7) / 8 * 8; }
 
 inline I8Gemm i8_gemm_default() {
   I8Gemm g;
   g.MT = g.NT = 0; g.a_tiles = g.b_tiles = nullptr; g.kchunks = 0; g.scale_a = g.scale_b = nullptr;
   g.kbeg_rule = g.kend_rule = I8_K_FULL; g.lower_only = 0; g.mt_desc = g.nt_desc = 0;
   g.rn_partial = nullptr; g.rn_nt = 0; g.C = nullptr; g.ldc = 0; g.alpha = 1.0; g.beta = 0.0; g.transposed = 0;
+  g.a_mask = g.b_mask = nullptr; g.mask_ld = 0;
   return g;
 }
 
 int i8_split(const double* src, int64_t rows, int64_t cols, int64_t ld, int nslices, int tile_rows, int8_t* planes,
-             double* row_scale, cudaStream_t st);
+             double* row_scale, uint8_t* mask, cudaStream_t st);
 int i8_gemm(const I8Gemm& a, int nslices, cudaStream_t st);

@@ -65,8 +65,8 @@ int rec(double* A, int64_t n, int64_t ld, double* Li, int64_t ldi, int col0, con
   if ((rc = rec(A, h, ld, Li, ldi, col0, w))) return rc;
 
   // L21 = A21 Linv11^T   [h2 x h], k <= j
-  if ((rc = i8_split(A21, h2, h, ld, w.S, I8_TM, w.da, w.sa, w.st))) return rc;
-  if ((rc = i8_split(Li, h, h, ldi, w.S, I8_TN, w.db, w.sb, w.st))) return rc;
+  if ((rc = i8_split(A21, h2, h, ld, w.S, I8_TM, w.da, w.sa, nullptr, w.st))) return rc;
+  if ((rc = i8_split(Li, h, h, ldi, w.S, I8_TN, w.db, w.sb, nullptr, w.st))) return rc;
   I8Gemm g = i8_gemm_default();
   g.MT = (int)(h2 / I8_TM); g.NT = (int)(h / I8_TN); g.kchunks = (int)(h / I8_KC);
   g.a_tiles = w.da; g.scale_a = w.sa; g.b_tiles = w.db; g.scale_b = w.sb;
@@ -75,8 +75,8 @@ int rec(double* A, int64_t n, int64_t ld, double* Li, int64_t ldi, int col0, con
   if ((rc = i8_gemm(g, w.S, w.st))) return rc;
 
   // A22 -= L21 L21^T     [h2 x h2], K = h, lower tiles
-  if ((rc = i8_split(A21, h2, h, ld, w.S, I8_TM, w.da, w.sa, w.st))) return rc;
-  if ((rc = i8_split(A21, h2, h, ld, w.S, I8_TN, w.db, w.sb, w.st))) return rc;
+  if ((rc = i8_split(A21, h2, h, ld, w.S, I8_TM, w.da, w.sa, nullptr, w.st))) return rc;
+  if ((rc = i8_split(A21, h2, h, ld, w.S, I8_TN, w.db, w.sb, nullptr, w.st))) return rc;
   g = i8_gemm_default();
   g.MT = (int)(h2 / I8_TM); g.NT = (int)(h2 / I8_TN); g.kchunks = (int)(h / I8_KC);
   g.a_tiles = w.da; g.scale_a = w.sa; g.b_tiles = w.db; g.scale_b = w.sb;
@@ -87,10 +87,10 @@ int rec(double* A, int64_t n, int64_t ld, double* Li, int64_t ldi, int col0, con
   if ((rc = rec(A22, h2, ld, Li22, ldi, col0 + (int)h, w))) return rc;
 
   // W^T = (L21 T1^T)^T, T1 = Linv11^T   [W is h2 x h], k >= j
-  if ((rc = i8_split(A21, h2, h, ld, w.S, I8_TM, w.da, w.sa, w.st))) return rc;
+  if ((rc = i8_split(A21, h2, h, ld, w.S, I8_TM, w.da, w.sa, nullptr, w.st))) return rc;
   transpose_kernel<<<dim3((unsigned)(h / 32), (unsigned)(h / 32)), dim3(32, 8), 0, w.st>>>(Li, ldi, w.t1, h);
   ALGP_LAUNCH_CHECK();
-  if ((rc = i8_split(w.t1, h, h, h, w.S, I8_TN, w.db, w.sb, w.st))) return rc;
+  if ((rc = i8_split(w.t1, h, h, h, w.S, I8_TN, w.db, w.sb, nullptr, w.st))) return rc;
   g = i8_gemm_default();
   g.MT = (int)(h2 / I8_TM); g.NT = (int)(h / I8_TN); g.kchunks = (int)(h / I8_KC);
   g.a_tiles = w.da; g.scale_a = w.sa; g.b_tiles = w.db; g.scale_b = w.sb;
@@ -99,8 +99,8 @@ int rec(double* A, int64_t n, int64_t ld, double* Li, int64_t ldi, int col0, con
   if ((rc = i8_gemm(g, w.S, w.st))) return rc;
 
   // Linv21 = -Linv22 (W^T)^T   [h2 x h], K = h2, k <= i
-  if ((rc = i8_split(Li22, h2, h2, ldi, w.S, I8_TM, w.da, w.sa, w.st))) return rc;
-  if ((rc = i8_split(w.t1, h, h2, h2, w.S, I8_TN, w.db, w.sb, w.st))) return rc;
+  if ((rc = i8_split(Li22, h2, h2, ldi, w.S, I8_TM, w.da, w.sa, nullptr, w.st))) return rc;
+  if ((rc = i8_split(w.t1, h, h2, h2, w.S, I8_TN, w.db, w.sb, nullptr, w.st))) return rc;
   g = i8_gemm_default();
   g.MT = (int)(h2 / I8_TM); g.NT = (int)(h / I8_TN); g.kchunks = (int)(h2 / I8_KC);
   g.a_tiles = w.da; g.scale_a = w.sa; g.b_tiles = w.db; g.scale_b = w.sb;

@@ -217,38 +217,45 @@ class GPFactor(object):
              ptr(rn), stream())
         return rn
 
-    def split_i8(self, M, nslices, tile_rows):
+    def split_i8(self, M, nslices, tile_rows, want_mask=False):
         """fp64 device matrix -> (digit tiles int8 [rows*cols*nslices], row_scale [rows]) for the INT8
-        tensor-core path (tile_rows = 128: left operand, 64: right operand)."""
+        tensor-core path (tile_rows = 128: left operand, 64: right operand); with want_mask also the
+        plane-occupancy bytes per (row tile, 32-column chunk) that let the GEMM skip all-zero digit tiles."""
         rows, cols = M.shape
         tiles = torch.empty(nslices * rows * cols, dtype=torch.int8, device=M.device)
         scale = torch.empty(rows, dtype=torch.float64, device=M.device)
-        call("algp_split_i8", ptr(M), rows, cols, M.stride(0), nslices, tile_rows, ptr(tiles), ptr(scale), stream())
+        mask = None
+        if want_mask:
+            mask = torch.empty(_lib.lib.algp_i8_mask_bytes(rows, cols, tile_rows), dtype=torch.uint8, device=M.device)
+        call("algp_split_i8", ptr(M), rows, cols, M.stride(0), nslices, tile_rows, ptr(tiles), ptr(scale), ptr(mask), stream())
+        if want_mask:
+            return tiles, scale, mask
         return tiles, scale
 
-    def whiten_norm_i8(self, Ks, nslices=I8_SLICES):
-        """Squared row norms of V = Ks L^-T per 64-column tile through exact INT8 digit GEMMs (fp64 tier)."""
+    def _linv_digits(self, nslices):
         cache = getattr(self, "_linv_i8", None)
         if cache is None or cache[0] != nslices:
-            self._linv_i8 = cache = (nslices,) + self.split_i8(self.Linv, nslices, 64)
-        _, lt, ls = cache
-        kt, ks = self.split_i8(Ks, nslices, 128)
+            self._linv_i8 = cache = (nslices,) + self.split_i8(self.Linv, nslices, 64, want_mask=True)
+        return cache[1], cache[2], cache[3]
+
+    def whiten_norm_i8(self, Ks, nslices=I8_SLICES, use_masks=True):
+        """Squared row norms of V = Ks L^-T per 64-column tile through exact INT8 digit GEMMs (fp64 tier)."""
+        lt, ls, lm = self._linv_digits(nslices)
+        kt, ks, km = self.split_i8(Ks, nslices, 128, want_mask=True)
         Mpad = Ks.shape[0]
         rn = torch.empty((Mpad, self.Npad // 64), dtype=torch.float64, device=Ks.device)
-        call("algp_trmm_rt_i8", ptr(kt), ptr(ks), Mpad, ptr(lt), ptr(ls), self.Npad, nslices, ptr(rn), stream())
+        call("algp_trmm_rt_i8", ptr(kt), ptr(ks), ptr(km) if use_masks else None, Mpad, ptr(lt), ptr(ls),
+             ptr(lm) if use_masks else None, self.Npad, nslices, ptr(rn), stream())
         return rn
 
     def whiten_store_i8(self, Ks, V_out, nslices=I8_FACTOR_SLICES):
         """V_out[:, :Npad] = Ks L^-T through exact INT8 digit GEMMs; returns the row-norm partials [Mpad, Npad/64]."""
-        cache = getattr(self, "_linv_i8", None)
-        if cache is None or cache[0] != nslices:
-            self._linv_i8 = cache = (nslices,) + self.split_i8(self.Linv, nslices, 64)
-        _, lt, ls = cache
-        kt, ks = self.split_i8(Ks, nslices, 128)
+        lt, ls, lm = self._linv_digits(nslices)
+        kt, ks, km = self.split_i8(Ks, nslices, 128, want_mask=True)
         Mpad = Ks.shape[0]
         rn = torch.empty((Mpad, self.Npad // 64), dtype=torch.float64, device=Ks.device)
-        call("algp_trmm_rt_store_i8", ptr(kt), ptr(ks), Mpad, ptr(lt), ptr(ls), self.Npad, nslices, ptr(V_out),
-             V_out.stride(0), ptr(rn), stream())
+        call("algp_trmm_rt_store_i8", ptr(kt), ptr(ks), ptr(km), Mpad, ptr(lt), ptr(ls), ptr(lm), self.Npad, nslices,
+             ptr(V_out), V_out.stride(0), ptr(rn), stream())
         return rn
 
     def mean_var(self, xs, y0, ymean, test_var=None, want_var=True, max_rows=65536, precision="fp64"):

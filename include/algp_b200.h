@@ -96,20 +96,28 @@ int algp_trmm_rt_tf32(const float* Khi, const float* Klo, int64_t mpad, int64_t 
  * src[r][c] = row_scale[r] * sum_p digit_p[r][c] * 2^(-6-7p) (+ a remainder below 2^(-7 nslices) row_scale[r]).
  * The digits are written in the tensor core's operand layout, tile by tile (rows * cols * nslices bytes):
  *   [row tile of tile_rows][32-column k chunk][plane][row group of 8][k half][8 rows][16 B]
- * tile_rows = 128 for the left operand (K), 64 for the right one (Linv); rows % tile_rows == 0, cols % 32 == 0. */
+ * tile_rows = 128 for the left operand (K), 64 for the right one (Linv); rows % tile_rows == 0, cols % 32 == 0.
+ * mask (or NULL): algp_i8_mask_bytes(rows, cols, tile_rows) bytes, 8-byte aligned; receives one occupancy byte
+ * per (row tile, k chunk), bit p set iff plane p of that tile chunk holds a non-zero digit (row stride
+ * round_up(cols / 32, 8) bytes).  The GEMMs skip the products, loads and whole k chunks that the masks prove zero:
+ * exact, and a large saving when the operands decay away from a diagonal (kernel matrices of spatially ordered
+ * points). */
 int algp_split_i8(const double* src, int64_t rows, int64_t cols, int64_t ld, int nslices, int tile_rows,
-                  int8_t* planes, double* row_scale, void* stream);
+                  int8_t* planes, double* row_scale, uint8_t* mask, void* stream);
+int64_t algp_i8_mask_bytes(int64_t rows, int64_t cols, int tile_rows);
 /* Same row-norm partials as algp_trmm_rt (rn_partial[m][t], t < npad/64) from the digit tiles of K [mpad x npad]
  * (tile_rows 128) and Linv [npad x npad] (tile_rows 64): the digit products are exact integer GEMMs, groups of
  * equal weight are summed in fp64 (error ~ 2^(-7 nslices) of the row scales): the fp64 tier of the variance
- * (utils.py:305-308) at several times the DMMA rate.  npad <= 32768. */
-int algp_trmm_rt_i8(const int8_t* Kt, const double* Kscale, int64_t mpad, const int8_t* Lt, const double* Lscale,
-                    int64_t npad, int nslices, double* rn_partial, void* stream);
-
+ * (utils.py:305-308) at several times the DMMA rate.  Kmask / Lmask: occupancy masks from algp_split_i8 or NULL.
+ * npad <= 32768. */
+int algp_trmm_rt_i8(const int8_t* Kt, const double* Kscale, const uint8_t* Kmask, int64_t mpad, const int8_t* Lt,
+                    const double* Lscale, const uint8_t* Lmask, int64_t npad, int nslices, double* rn_partial,
+                    void* stream);
 /* algp_trmm_rt with V stored ([mpad x npad], row stride ldv) and, if rn_partial is not NULL, the same row-norm
  * partials, from the digit tiles: the W^T = Sigma_{:,B} L^-T build of the posterior state. */
-int algp_trmm_rt_store_i8(const int8_t* Kt, const double* Kscale, int64_t mpad, const int8_t* Lt, const double* Lscale,
-                          int64_t npad, int nslices, double* V, int64_t ldv, double* rn_partial, void* stream);
+int algp_trmm_rt_store_i8(const int8_t* Kt, const double* Kscale, const uint8_t* Kmask, int64_t mpad, const int8_t* Lt,
+                          const double* Lscale, const uint8_t* Lmask, int64_t npad, int nslices, double* V, int64_t ldv,
+                          double* rn_partial, void* stream);
 /* C [mpad x npad] = alpha A B^T + beta C from the digit tiles of A [mpad x kpad] (tile_rows 128) and
  * B [npad x kpad] (tile_rows 64), fp64-grade with nslices = 8; transposed != 0 stores C^T ([npad x mpad], ldc its
  * row stride); lower_only skips the tiles entirely above the diagonal.  mpad % 128 == 0, npad % 64 == 0,

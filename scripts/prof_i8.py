@@ -35,14 +35,17 @@ for S in slices:
     ts, _ = timed(lambda: f.split_i8(Ks, S, 128))
     f._linv_i8 = None
     t8, rn8 = timed(lambda: f.whiten_norm_i8(Ks, nslices=S))
-    kp, ks = f.split_i8(Ks, S, 128)
-    _, lp, ls = f._linv_i8
-    def mm():
+    kp, ks, km = f.split_i8(Ks, S, 128, want_mask=True)
+    lp, ls, lm = f._linv_digits(S)
+    def mm(masks=True):
         rn = torch.empty((Ks.shape[0], f.Npad // 64), dtype=torch.float64, device=Ks.device)
-        engine.call("algp_trmm_rt_i8", engine.ptr(kp), engine.ptr(ks), Ks.shape[0], engine.ptr(lp), engine.ptr(ls), f.Npad, S,
-                    engine.ptr(rn), engine.stream())
+        engine.call("algp_trmm_rt_i8", engine.ptr(kp), engine.ptr(ks), engine.ptr(km) if masks else None, Ks.shape[0],
+                    engine.ptr(lp), engine.ptr(ls), engine.ptr(lm) if masks else None, f.Npad, S, engine.ptr(rn), engine.stream())
         return rn
     tm, _ = timed(mm)
+    tm0, _ = timed(lambda: mm(False))
+    occ = [float(((km >> p) & 1).float().mean()) for p in range(S)]
+    print("   plane occupancy of K tiles", [round(o, 3) for o in occ], " mma without masks %.2f ms" % tm0)
     ops = flops * S * (S + 1) / 2
     msg = "i8 S=%d: total %.2f ms (split K %.2f ms, mma %.2f ms = %.0f TOP/s int8, %.1f TFLOP/s fp64-equivalent)" % (
         S, t8, ts, tm, ops / tm / 1e9, flops / tm / 1e9)

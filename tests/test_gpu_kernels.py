@@ -458,3 +458,48 @@ def test_append_block_equals_successive_appends(k):
     idx = rng.choice(free, (64, 8)).astype(np.int32)
     np.testing.assert_allclose(blk.score_sets(dev(idx, torch.int32), None, delta_scalar=1.0).cpu().numpy(),
                                seq.score_sets(dev(idx, torch.int32), None, delta_scalar=1.0).cpu().numpy(), rtol=1e-11, atol=1e-10)
+
+
+def test_split_i8_occupancy_masks():
+    """mask[tile][chunk] bit p <=> plane p of that (row tile, 32-column chunk) holds a non-zero digit."""
+    rng = np.random.default_rng(21)
+    S, tile_rows, rows, cols = 7, 64, 192, 320
+    M = rng.normal(size=(rows, cols))
+    M[:, 0] = 3.0                                            # every row's scale is 4: digits of the other columns shift down
+    M[64:128, 32:96] = 0.0                                   # two all-zero chunks of the second tile
+    M[128:, 160:192] = 2.0 ** -30 * rng.normal(size=(64, 32))   # a chunk that only reaches the low planes
+    f = engine.GPFactor.__new__(engine.GPFactor)
+    tiles, scale, mask = engine.GPFactor.split_i8(f, dev(M), S, tile_rows, want_mask=True)
+    planes = untile_i8(tiles.cpu().numpy(), rows, cols, S, tile_rows)
+    want = np.zeros((rows // tile_rows, cols // 32), dtype=np.uint8)
+    for p in range(S):
+        nz = (planes[p].reshape(rows // tile_rows, tile_rows, cols // 32, 32) != 0).any(axis=(1, 3))
+        want |= (nz.astype(np.uint8) << p)
+    ld = (cols // 32 + 7) // 8 * 8
+    got = mask.cpu().numpy()[: (rows // tile_rows) * ld].reshape(rows // tile_rows, ld)
+    np.testing.assert_array_equal(got[:, : cols // 32], want)
+    assert (got[:, cols // 32:] == 0).all()
+    assert want[1, 1] == 0 and want[1, 2] == 0 and want[2, 5] != 0 and (want[2, 5] & 0b111) == 0
+
+
+@pytest.mark.parametrize("S", [5, 7, 8])
+def test_trmm_i8_masked_equals_unmasked_on_sparse_operands(S):
+    """Occupancy masks only skip digit tiles that are exactly zero: same result bit for bit, on operands whose
+    entries decay away from the diagonal (so that many tiles / planes are empty), and the fp64 tier vs DMMA."""
+    rng = np.random.default_rng(S)
+    N, M = 768, 512
+    x = np.sort(rng.uniform(0, 400, N))[:, None]             # 1-D, sorted: K(X,X) and Linv decay away from the diagonal
+    xs = np.sort(rng.uniform(0, 400, M))[:, None]
+    th, hy = hyper_pair([2.0], 1.0, 0.05, "rbf")
+    f = engine.GPFactor(hy, dev(x), diag_add=None)
+    f.check()
+    Ks, _ = f.cross(dev(xs))
+    _, rn = f.whiten(Ks, want_V=False)
+    ref = rn.sum(1).cpu().numpy()
+    masked = f.whiten_norm_i8(Ks, nslices=S, use_masks=True).cpu().numpy()
+    plain = f.whiten_norm_i8(Ks, nslices=S, use_masks=False).cpu().numpy()
+    np.testing.assert_array_equal(masked, plain)
+    tol = {5: 1e-7, 7: 1e-10, 8: 1e-11}[S]
+    np.testing.assert_allclose(masked.sum(1), ref, rtol=0, atol=tol)
+    _, _, km = f.split_i8(Ks, S, 128, want_mask=True)
+    assert float((km == 0).float().mean()) > 0.3             # the case really exercises skipped chunks
