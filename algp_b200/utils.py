@@ -87,19 +87,28 @@ def _digest(*arrays):
     return h.digest()
 
 
-def _factor_for(gp, hyper, train_x, train_var):
-    """Device factor of cov_aa (utils.py:296), cached on the GPR until its data or theta change."""
+def _factor_for(gp, hyper, train_x, train_var, reorder=False):
+    """Device factor of cov_aa (utils.py:296), cached on the GPR until its data or theta change.
+    reorder: factor the training set in Z-curve order (f.perm maps factor rows to the caller's rows); only
+    order-independent consumers (posterior mean / variance) may ask for it."""
     from . import engine
     cache = getattr(gp, "_cache", None)
     prec = getattr(gp, "precision", "fp64")
     # precision "i8": factor through the recursive INT8 digit factorisation when N is large enough to pay
-    key = ("factor", _digest(train_x, train_var), hyper.key(), prec == "i8")
+    key = ("factor", _digest(train_x, train_var), hyper.key(), prec == "i8", bool(reorder))
     if cache is not None and cache.get("factor_key") == key:
         return cache["factor"]
     dev = engine.require_cuda()
     x = engine.to_dev(train_x, device=dev)
     wn = None if train_var is None else engine.to_dev(np.asarray(train_var, dtype=np.float64), device=dev)
+    perm = box = None
+    if reorder:
+        perm, lo, hi = engine.morton_perm(x)
+        box = (lo, hi)
+        x = x.index_select(0, perm).contiguous()
+        wn = None if wn is None else wn.index_select(0, perm).contiguous()
     f = engine.GPFactor(hyper, x, diag_add=wn, diag_scalar=hyper.noise, factor="auto" if prec == "i8" else "dmma")
+    f.perm, f.box = perm, box
     if cache is not None:
         cache.clear()
         cache["factor_key"] = key
@@ -119,14 +128,29 @@ def _posterior(gp, hyper, train_x, train_y, test_x, train_var, test_var, want_va
         test_x = test_x[:, None]
     train_y = np.asarray(to_numpy(train_y), dtype=np.float64).reshape(-1)
     ymean = float(np.mean(train_y))                                   # utils.py:294
-    f = _factor_for(gp, hyper, train_x, train_var)
+    prec = getattr(gp, "precision", "fp64")
+    # the mean / variance path does not depend on the order of the points: in INT8 digit mode both sets are sorted
+    # along a Z curve so that far-apart (test tile, train chunk) pairs become all-zero digit tiles the GEMM skips
+    reorder = (not want_cov) and prec == "i8" and len(train_y) >= engine.I8_REORDER_MIN
+    f = _factor_for(gp, hyper, train_x, train_var, reorder=reorder)
     dev = f.L.device
     xs = engine.to_dev(test_x, device=dev)
     y0 = engine.to_dev(train_y - ymean, device=dev)
     tv = None if test_var is None else engine.to_dev(np.asarray(test_var, dtype=np.float64), device=dev)
     M = xs.shape[0]
     if not want_cov:
-        mu, var = f.mean_var(xs, y0, ymean, tv, want_var=want_var, precision=getattr(gp, "precision", "fp64"))
+        tperm = None
+        if reorder:
+            y0 = y0.index_select(0, f.perm)
+            tperm, _, _ = engine.morton_perm(xs, f.box[0], f.box[1])
+            xs = xs.index_select(0, tperm).contiguous()
+            tv = None if tv is None else tv.index_select(0, tperm).contiguous()
+        mu, var = f.mean_var(xs, y0, ymean, tv, want_var=want_var, precision=prec)
+        if tperm is not None:
+            inv = torch.empty_like(tperm)
+            inv[tperm] = torch.arange(M, device=dev)
+            mu = mu.index_select(0, inv)
+            var = var.index_select(0, inv) if want_var else None
         mu_h = mu.cpu().numpy()
         var_h = var.cpu().numpy() if want_var else None
         f.check()

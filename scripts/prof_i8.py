@@ -7,12 +7,18 @@ N = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
 M = int(sys.argv[2]) if len(sys.argv) > 2 else 4096
 slices = [int(s) for s in sys.argv[3].split(",")] if len(sys.argv) > 3 else [8]
 check = (len(sys.argv) <= 4) or sys.argv[4] != "nocheck"
+morton = len(sys.argv) > 5 and sys.argv[5] == "morton"
 rng = np.random.default_rng(1)
 side = int(np.sqrt(M))
 x = rng.uniform(0, side, size=(N, 2))
 yy, xx = np.meshgrid(np.arange(side), np.arange(side), indexing="ij")
 xs = np.stack([yy.ravel(), xx.ravel()], 1).astype(np.float64)
 hy = engine.Hyper(np.log([side / 16.0, side / 16.0]), 0.0, np.log(1e-2), "rbf")
+if morton:
+    xd, xsd = engine.to_dev(x), engine.to_dev(xs)
+    p1, lo, hi = engine.morton_perm(xd)
+    p2, _, _ = engine.morton_perm(xsd, lo, hi)
+    x, xs = xd[p1].cpu().numpy(), xsd[p2].cpu().numpy()
 f = engine.GPFactor(hy, engine.to_dev(x), diag_add=engine.to_dev(np.full(N, 0.01)))
 f.check()
 Ks, _ = f.cross(engine.to_dev(xs))

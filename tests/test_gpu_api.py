@@ -377,3 +377,30 @@ def test_prediction_vs_distance_matches_literal_loop():
     np.testing.assert_allclose(got['mi'], mis, rtol=1e-8)
     np.testing.assert_allclose(got['mean_var'], mv, rtol=1e-8, atol=1e-10)
     np.testing.assert_allclose(got['mean'], mu, rtol=1e-9, atol=1e-9)
+
+
+def test_i8_precision_reorders_points_and_matches_fp64():
+    """gp.precision = 'i8' from N = 2048: training and test points are sorted along a Z curve internally (so that the
+    digit GEMM can skip far-apart tiles); the caller sees the same mean / variance, in the caller's order."""
+    rng = np.random.default_rng(31)
+    N, M = 2304, 1500
+    x = rng.uniform(0, 120, (N, 2))
+    xs = rng.uniform(-5, 125, (M, 2))                      # some test points outside the training box
+    y = np.sin(x[:, 0] / 7.0) + np.cos(x[:, 1] / 5.0) + rng.normal(0, 0.1, N)
+    var = rng.uniform(0.01, 0.02, N)
+    tvar = rng.uniform(0.0, 0.01, M)
+    th, hy = hyper_pair([6.0, 5.0], 1.0, 0.01, "rbf")
+    gp = make_gpr("rbf", th.log_lengthscale, th.log_outputscale, th.log_noise, x, y, var)
+    mu64, v64 = algp_b200.predictive_distribution(gp, x, y, xs, var, tvar, return_var=True)
+    gp.precision = "i8"
+    mu8, v8 = algp_b200.predictive_distribution(gp, x, y, xs, var, tvar, return_var=True)
+    f = gp._cache["factor"]
+    assert f.perm is not None and sorted(f.perm.cpu().tolist()) == list(range(N))
+    np.testing.assert_allclose(mu8, mu64, rtol=1e-9, atol=1e-9)
+    np.testing.assert_allclose(v8, v64, rtol=0, atol=1e-9)
+    mu_o, v_o = O.predictive_distribution_chol(O.OracleGP(th, "fp64"), x, y, xs, var, tvar, return_var=True)
+    np.testing.assert_allclose(mu8, mu_o, rtol=1e-9, atol=1e-9)
+    np.testing.assert_allclose(v8, v_o, rtol=0, atol=1e-9)
+    # a covariance request must not see the reordered factor
+    mu_c, cov = algp_b200.predictive_distribution(gp, x, y, xs[:64], var, tvar[:64], return_cov=True)
+    np.testing.assert_allclose(np.diag(cov), v64[:64], rtol=0, atol=1e-9)
