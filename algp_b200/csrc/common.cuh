@@ -67,6 +67,16 @@ __device__ __forceinline__ void mbarrier_wait(uint64_t* b, uint32_t parity) {
   } while (!ok);
 }
 
+// one non-blocking poll of a phase (true once the phase with this parity has completed)
+__device__ __forceinline__ bool mbarrier_test(uint64_t* b, uint32_t parity) {
+  uint32_t ok;
+  asm volatile("{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+               : "=r"(ok)
+               : "r"(smem_addr_u32(b)), "r"(parity)
+               : "memory");
+  return ok != 0;
+}
+
 // FP64 tensor-core MMA.  On sm_100a every f64 mma.sync shape lowers to
 // DMMA.8x8x4 (checked with cuobjdump), so m8n8k4 is the native unit.
 // Fragments: a = A[lane>>2][lane&3], b = B[k=lane&3][n=lane>>2],

@@ -32,7 +32,7 @@
 #include "common.cuh"
 #include "i8.cuh"
 
-#define I8_THREADS 160
+#define I8_THREADS 192                  // 4 epilogue warps, warp 4: MMA issuer, warp 5: bulk-copy producer
 
 namespace {
 
@@ -49,14 +49,6 @@ __device__ __forceinline__ void bulk_load(uint32_t dst, const void* src, uint32_
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                ::"r"(dst), "l"(src), "r"(bytes), "r"(s_u32(bar))
                : "memory");
-}
-// D[tmem] (+)= A[smem] B[smem]^T, signed 8-bit operands, s32 accumulator
-__device__ __forceinline__ void mma_i8(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
-      : "memory");
 }
 // K-major no-swizzle (INTERLEAVE) operand tile: 8 x 16 B core matrices; LBO = 128 B between the two 16-byte
 // k halves of an MMA, SBO = 256 B between 8-row groups (cute::UMMA::SmemDescriptor: version 1 at bit 46,
@@ -165,35 +157,30 @@ struct I8Cfg {
   static constexpr int TMEM_COLS = (S * I8_TN > 256) ? 512 : ((S * I8_TN > 128) ? 256 : 128);
 };
 
-// sequential reader of one tile's occupancy bytes, eight at a time, the next word prefetched
-struct MaskReader {
-  const uint8_t* m;
-  int base, kend;
-  unsigned long long cur, nxt;
-  __device__ MaskReader(const uint8_t* m_, int kbeg, int kend_) : m(m_), base(kbeg & ~7), kend(kend_), cur(~0ull), nxt(~0ull) {
-    if (m) {
-      cur = *reinterpret_cast<const unsigned long long*>(m + base);
-      if (base + 8 < kend) nxt = *reinterpret_cast<const unsigned long long*>(m + base + 8);
-    }
-  }
-  __device__ __forceinline__ uint32_t get(int kc) {
-    if (!m) return 0xffu;
-    if ((kc & ~7) != base) {
-      base += 8;
-      cur = nxt;
-      if (base + 8 < kend) nxt = *reinterpret_cast<const unsigned long long*>(m + base + 8);
-    }
-    return (uint32_t)(cur >> (8 * (kc & 7))) & 0xffu;
-  }
-};
-
-// some digit product p + q < S has both planes occupied
+// One lane's view of one k chunk: 0 if the chunk needs nothing, else bit 31 | occupied A planes | occupied B planes
+// << 8.  Plane p of A meets plane q of B only if p + q < S, so a chunk is needed iff the lowest occupied planes
+// already qualify.
 template <int S>
-__device__ __forceinline__ bool stage_needed(uint32_t ma, uint32_t mb) {
-  bool need = false;
-#pragma unroll
-  for (int pa = 0; pa < S; ++pa) need = need || (((ma >> pa) & 1u) && (mb & ((1u << (S - pa)) - 1u)));
-  return need;
+__device__ __forceinline__ uint32_t plan_word(const uint8_t* am, const uint8_t* bm, int kc, int kend) {
+  if (kc >= kend) return 0u;
+  constexpr uint32_t ALLP = (1u << S) - 1u;
+  const uint32_t a = (am ? (uint32_t)am[kc] : 0xffu) & ALLP, b = (bm ? (uint32_t)bm[kc] : 0xffu) & ALLP;
+  if (a == 0u || b == 0u) return 0u;
+  if ((__ffs(a) - 1) + (__ffs(b) - 1) > S - 1) return 0u;
+  return 0x80000000u | a | (b << 8);
+}
+// B planes a stage has to bring: the prefix that the lowest occupied A plane can reach, up to the highest occupied
+template <int S>
+__device__ __forceinline__ int b_prefix(uint32_t ma, uint32_t mb) {
+  return min(S - (__ffs(ma) - 1), 32 - __clz(mb));
+}
+// D[tmem] += A[smem] B[smem]^T, signed 8-bit operands, s32 accumulators (zero-initialised: always accumulating)
+__device__ __forceinline__ void mma_i8_acc(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.eq.u32 p, 1, 1;\n\t"
+      "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc)
+      : "memory");
 }
 
 // MODE 0: row sums of squares per 64-column tile (variance path, nothing else is written)
@@ -266,39 +253,13 @@ gemm_i8_kernel(const I8Gemm p) {
   constexpr uint32_t ALLP = (1u << S) - 1u;
 
   if (warp < 4) {
-    if (tid == 0 && KT > 0) {
-      // ===================== TMA producer (one thread) =====================
-      const int8_t* a_src = p.a_tiles + (int64_t)mt * p.kchunks * C::A_BYTES;
-      const int8_t* b_src = p.b_tiles + (int64_t)nt * p.kchunks * C::B_BYTES;
-      MaskReader ra(am, kbeg, kend), rb(bm, kbeg, kend);
-      int it = 0;
-      for (int kc = kbeg; kc < kend; ++kc) {
-        const uint32_t ma = ra.get(kc) & ALLP, mb = rb.get(kc) & ALLP;
-        if (!stage_needed<S>(ma, mb)) continue;
-        const int s = it % C::STAGES, u = it / C::STAGES;
-        ++it;
-        if (u > 0) mbarrier_wait(&empty_bar[s], (u - 1) & 1);     // the MMAs that read this slot are done
-        const uint32_t st = ring + (uint32_t)s * C::STAGE_BYTES;
-        const int8_t* asrc = a_src + (int64_t)kc * C::A_BYTES;
-        if (ma == ALLP) {
-          expect_tx(&full_bar[s], C::STAGE_BYTES);
-          bulk_load(st, asrc, C::A_BYTES, &full_bar[s]);
-        } else {
-          expect_tx(&full_bar[s], (uint32_t)__popc(ma) * C::A_PLANE + C::B_BYTES);
-#pragma unroll
-          for (int pa = 0; pa < S; ++pa)
-            if ((ma >> pa) & 1u) bulk_load(st + pa * C::A_PLANE, asrc + pa * C::A_PLANE, C::A_PLANE, &full_bar[s]);
-        }
-        bulk_load(st + C::A_BYTES, b_src + (int64_t)kc * C::B_BYTES, C::B_BYTES, &full_bar[s]);
-      }
-    }
-    __syncwarp();
     // ===================== epilogue =====================
     if (valid_tile) {
       const int row = warp * 32 + lane;                          // TMEM lane = accumulator row
       const double sa = p.scale_a[m0 + row] * (1.0 / 4096.0);   // 2^(eA_m - 12)
       if (KT > 0) {
-        mbarrier_wait(&done_bar, 0);
+        // sleep between polls: four spinning warps would take issue slots from the two single-lane roles
+        while (!mbarrier_test(&done_bar, 0)) __nanosleep(256);
         fence_after();
       }
       double ss = 0.0;
@@ -362,38 +323,101 @@ gemm_i8_kernel(const I8Gemm p) {
       }
       if (MODE == 0 || p.rn_partial) p.rn_partial[(int64_t)(m0 + row) * p.rn_nt + nt] = ss * sa * sa;
     }
-  } else if (warp == 4 && lane == 0 && KT > 0) {
-    // ===================== MMA issuer (one thread) =====================
+  } else if (warp == 5 && KT > 0) {
+    // ===================== bulk-copy producer (warp 5; lane 0 issues) =====================
+    // The 32 lanes decode 32 k chunks' occupancy bytes at once; lane 0 then walks the chunks that need work.
+    const int8_t* a_src = p.a_tiles + (int64_t)mt * p.kchunks * C::A_BYTES;
+    const int8_t* b_src = p.b_tiles + (int64_t)nt * p.kchunks * C::B_BYTES;
+    int it = 0;
+    for (int kb = kbeg; kb < kend; kb += 32) {
+      const uint32_t w = plan_word<S>(am, bm, kb + lane, kend);
+      uint32_t bits = __ballot_sync(0xffffffffu, w != 0u);
+      while (bits) {
+        const int l = __ffs(bits) - 1;
+        bits &= bits - 1;
+        const uint32_t ws = __shfl_sync(0xffffffffu, w, l);
+        if (lane == 0) {
+          const uint32_t ma = ws & 0xffu, mb = (ws >> 8) & 0xffu;
+          const int kc = kb + l, s = it % C::STAGES, u = it / C::STAGES;
+          if (u > 0) mbarrier_wait(&empty_bar[s], (u - 1) & 1);   // the MMAs that read this slot are done
+          const uint32_t st = ring + (uint32_t)s * C::STAGE_BYTES;
+          const int8_t* asrc = a_src + (int64_t)kc * C::A_BYTES;
+          const int nB = b_prefix<S>(ma, mb);
+          expect_tx(&full_bar[s], (uint32_t)(__popc(ma) * C::A_PLANE + nB * C::B_PLANE));
+          if (ma == ALLP) {
+            bulk_load(st, asrc, C::A_BYTES, &full_bar[s]);
+          } else {
+#pragma unroll
+            for (int pa = 0; pa < S; ++pa)
+              if ((ma >> pa) & 1u) bulk_load(st + pa * C::A_PLANE, asrc + pa * C::A_PLANE, C::A_PLANE, &full_bar[s]);
+          }
+          bulk_load(st + C::A_BYTES, b_src + (int64_t)kc * C::B_BYTES, (uint32_t)(nB * C::B_PLANE), &full_bar[s]);
+        }
+        ++it;
+      }
+    }
+  } else if (warp == 4 && KT > 0) {
+    // ===================== MMA issuer (warp 4; lane 0 issues) =====================
     // The B digit planes of a stage are contiguous in shared memory ([plane][64 rows][32 B]), i.e. ONE K-major
     // operand of (S - p) x 64 rows, and group g = p + q lives at TMEM columns g x 64: a single MMA of A_p against
     // planes q0..q0+c-1 (N = 64c <= 256) lands every product in its own group.  S(S+1)/2 plane products become
     // ~S(S+1)/8 + S/2 instructions and A_p is read from shared memory once per <= 4 products instead of once each.
-    MaskReader ra(am, kbeg, kend), rb(bm, kbeg, kend);
     int it = 0;
-    for (int kc = kbeg; kc < kend; ++kc) {
-      const uint32_t ma = ra.get(kc) & ALLP, mb = rb.get(kc) & ALLP;
-      if (!stage_needed<S>(ma, mb)) continue;
-      const int s = it % C::STAGES, u = it / C::STAGES;
-      ++it;
-      mbarrier_wait(&full_bar[s], u & 1);
-      fence_after();
-      const uint32_t a0 = ring + (uint32_t)s * C::STAGE_BYTES, b0 = a0 + C::A_BYTES;
-      const uint64_t da0 = desc_kmajor(a0), db0 = desc_kmajor(b0);
+    for (int kb = kbeg; kb < kend; kb += 32) {
+      const uint32_t w = plan_word<S>(am, bm, kb + lane, kend);
+      uint32_t bits = __ballot_sync(0xffffffffu, w != 0u);
+      while (bits) {
+        const int l = __ffs(bits) - 1;
+        bits &= bits - 1;
+        const uint32_t ws = __shfl_sync(0xffffffffu, w, l);
+        if (lane == 0) {
+          const uint32_t ma = ws & 0xffu, mb = (ws >> 8) & 0xffu;
+          const int s = it % C::STAGES, u = it / C::STAGES;
+          mbarrier_wait(&full_bar[s], u & 1);
+          fence_after();
+          const uint32_t a0 = ring + (uint32_t)s * C::STAGE_BYTES, b0 = a0 + C::A_BYTES;
+          const uint64_t da0 = desc_kmajor(a0), db0 = desc_kmajor(b0);
+          if (ma == ALLP && mb == ALLP) {
+            // dense chunk: the fixed schedule, every operand a compile-time offset
 #pragma unroll
-      for (int pa = 0; pa < S; ++pa) {
-        if (!((ma >> pa) & 1u)) continue;
+            for (int pa = 0; pa < S; ++pa) {
 #pragma unroll
-        for (int q0 = 0; q0 < S - pa; q0 += 4) {
-          const int cnt = (S - pa - q0) < 4 ? (S - pa - q0) : 4;
-          if (((mb >> q0) & ((1u << cnt) - 1u)) == 0u) continue;
-          mma_i8(tmem + (uint32_t)((pa + q0) * I8_TN), da0 + (uint64_t)((pa * C::A_PLANE) >> 4),
-                 db0 + (uint64_t)((q0 * C::B_PLANE) >> 4), idesc_i8(I8_TM, cnt * I8_TN), 1u);
+              for (int q0 = 0; q0 < S - pa; q0 += 4) {
+                const int cnt = (S - pa - q0) < 4 ? (S - pa - q0) : 4;
+                mma_i8_acc(tmem + (uint32_t)((pa + q0) * I8_TN), da0 + (uint64_t)((pa * C::A_PLANE) >> 4),
+                           db0 + (uint64_t)((q0 * C::B_PLANE) >> 4), idesc_i8(I8_TM, cnt * I8_TN));
+              }
+            }
+          } else {
+            // sparse chunk: per occupied A plane, the reachable B planes in two groups of four; a group is
+            // multiplied up to its highest occupied plane (N = 64 x that many), empty groups are skipped
+            const uint32_t idesc0 = idesc_i8(I8_TM, 0);
+#pragma unroll
+            for (int pa = 0; pa < S; ++pa) {
+              if (!((ma >> pa) & 1u)) continue;
+              const uint32_t reach = mb & ((1u << (S - pa)) - 1u);
+              const uint32_t g0 = reach & 0xFu, g1 = reach >> 4;
+              const uint64_t da = da0 + (uint64_t)((pa * C::A_PLANE) >> 4);
+              if (g0) {
+                const uint32_t cnt = 32u - (uint32_t)__clz(g0);
+                mma_i8_acc(tmem + (uint32_t)(pa * I8_TN), da, db0, idesc0 | ((cnt * (I8_TN >> 3)) << 17));
+              }
+              if (S - pa > 4 && g1) {
+                const uint32_t cnt = 32u - (uint32_t)__clz(g1);
+                mma_i8_acc(tmem + (uint32_t)((pa + 4) * I8_TN), da, db0 + (uint64_t)((4 * C::B_PLANE) >> 4),
+                           idesc0 | ((cnt * (I8_TN >> 3)) << 17));
+              }
+            }
+          }
+          commit_to(&empty_bar[s]);                              // arrives when these MMAs have read the stage
         }
+        ++it;
       }
-      commit_to(&empty_bar[s]);                                  // arrives when these MMAs have read the stage
     }
-    if (it > 0) commit_to(&done_bar);                            // accumulators complete
-    else mbarrier_arrive(&done_bar);                             // every chunk was skipped: the zeros stand
+    if (lane == 0) {
+      if (it > 0) commit_to(&done_bar);                          // accumulators complete
+      else mbarrier_arrive(&done_bar);                           // every chunk was skipped: the zeros stand
+    }
   }
 
   fence_before();
