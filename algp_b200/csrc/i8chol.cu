@@ -46,6 +46,7 @@ struct Work {
   double* trtri_work;  // base-case trtri scratch
   int8_t* da; double* sa;   // left-operand digits + scales
   int8_t* db; double* sb;   // right-operand digits + scales
+  uint8_t* ma; uint8_t* mb; // their plane-occupancy masks (spatially ordered points: far blocks are empty)
   int* info;
   cudaStream_t st;
 };
@@ -65,21 +66,23 @@ int rec(double* A, int64_t n, int64_t ld, double* Li, int64_t ldi, int col0, con
   if ((rc = rec(A, h, ld, Li, ldi, col0, w))) return rc;
 
   // L21 = A21 Linv11^T   [h2 x h], k <= j
-  if ((rc = i8_split(A21, h2, h, ld, w.S, I8_TM, w.da, w.sa, nullptr, w.st))) return rc;
-  if ((rc = i8_split(Li, h, h, ldi, w.S, I8_TN, w.db, w.sb, nullptr, w.st))) return rc;
+  if ((rc = i8_split(A21, h2, h, ld, w.S, I8_TM, w.da, w.sa, w.ma, w.st))) return rc;
+  if ((rc = i8_split(Li, h, h, ldi, w.S, I8_TN, w.db, w.sb, w.mb, w.st))) return rc;
   I8Gemm g = i8_gemm_default();
   g.MT = (int)(h2 / I8_TM); g.NT = (int)(h / I8_TN); g.kchunks = (int)(h / I8_KC);
   g.a_tiles = w.da; g.scale_a = w.sa; g.b_tiles = w.db; g.scale_b = w.sb;
+  g.a_mask = w.ma; g.b_mask = w.mb; g.mask_ld = i8_mask_ld((int64_t)g.kchunks * I8_KC);
   g.kend_rule = I8_KE_NT; g.nt_desc = 1;
   g.C = A21; g.ldc = ld;
   if ((rc = i8_gemm(g, w.S, w.st))) return rc;
 
   // A22 -= L21 L21^T     [h2 x h2], K = h, lower tiles
-  if ((rc = i8_split(A21, h2, h, ld, w.S, I8_TM, w.da, w.sa, nullptr, w.st))) return rc;
-  if ((rc = i8_split(A21, h2, h, ld, w.S, I8_TN, w.db, w.sb, nullptr, w.st))) return rc;
+  if ((rc = i8_split(A21, h2, h, ld, w.S, I8_TM, w.da, w.sa, w.ma, w.st))) return rc;
+  if ((rc = i8_split(A21, h2, h, ld, w.S, I8_TN, w.db, w.sb, w.mb, w.st))) return rc;
   g = i8_gemm_default();
   g.MT = (int)(h2 / I8_TM); g.NT = (int)(h2 / I8_TN); g.kchunks = (int)(h / I8_KC);
   g.a_tiles = w.da; g.scale_a = w.sa; g.b_tiles = w.db; g.scale_b = w.sb;
+  g.a_mask = w.ma; g.b_mask = w.mb; g.mask_ld = i8_mask_ld((int64_t)g.kchunks * I8_KC);
   g.lower_only = 1;
   g.C = A22; g.ldc = ld; g.alpha = -1.0; g.beta = 1.0;
   if ((rc = i8_gemm(g, w.S, w.st))) return rc;
@@ -87,23 +90,25 @@ int rec(double* A, int64_t n, int64_t ld, double* Li, int64_t ldi, int col0, con
   if ((rc = rec(A22, h2, ld, Li22, ldi, col0 + (int)h, w))) return rc;
 
   // W^T = (L21 T1^T)^T, T1 = Linv11^T   [W is h2 x h], k >= j
-  if ((rc = i8_split(A21, h2, h, ld, w.S, I8_TM, w.da, w.sa, nullptr, w.st))) return rc;
+  if ((rc = i8_split(A21, h2, h, ld, w.S, I8_TM, w.da, w.sa, w.ma, w.st))) return rc;
   transpose_kernel<<<dim3((unsigned)(h / 32), (unsigned)(h / 32)), dim3(32, 8), 0, w.st>>>(Li, ldi, w.t1, h);
   ALGP_LAUNCH_CHECK();
-  if ((rc = i8_split(w.t1, h, h, h, w.S, I8_TN, w.db, w.sb, nullptr, w.st))) return rc;
+  if ((rc = i8_split(w.t1, h, h, h, w.S, I8_TN, w.db, w.sb, w.mb, w.st))) return rc;
   g = i8_gemm_default();
   g.MT = (int)(h2 / I8_TM); g.NT = (int)(h / I8_TN); g.kchunks = (int)(h / I8_KC);
   g.a_tiles = w.da; g.scale_a = w.sa; g.b_tiles = w.db; g.scale_b = w.sb;
+  g.a_mask = w.ma; g.b_mask = w.mb; g.mask_ld = i8_mask_ld((int64_t)g.kchunks * I8_KC);
   g.kbeg_rule = I8_KB_NT;
   g.C = w.t1; g.ldc = h2; g.transposed = 1;          // t1 <- W^T [h x h2] (its digits were taken above)
   if ((rc = i8_gemm(g, w.S, w.st))) return rc;
 
   // Linv21 = -Linv22 (W^T)^T   [h2 x h], K = h2, k <= i
-  if ((rc = i8_split(Li22, h2, h2, ldi, w.S, I8_TM, w.da, w.sa, nullptr, w.st))) return rc;
-  if ((rc = i8_split(w.t1, h, h2, h2, w.S, I8_TN, w.db, w.sb, nullptr, w.st))) return rc;
+  if ((rc = i8_split(Li22, h2, h2, ldi, w.S, I8_TM, w.da, w.sa, w.ma, w.st))) return rc;
+  if ((rc = i8_split(w.t1, h, h2, h2, w.S, I8_TN, w.db, w.sb, w.mb, w.st))) return rc;
   g = i8_gemm_default();
   g.MT = (int)(h2 / I8_TM); g.NT = (int)(h / I8_TN); g.kchunks = (int)(h2 / I8_KC);
   g.a_tiles = w.da; g.scale_a = w.sa; g.b_tiles = w.db; g.scale_b = w.sb;
+  g.a_mask = w.ma; g.b_mask = w.mb; g.mask_ld = i8_mask_ld((int64_t)g.kchunks * I8_KC);
   g.kend_rule = I8_KE_MT; g.mt_desc = 1;
   g.C = Li21; g.ldc = ldi; g.alpha = -1.0;
   return i8_gemm(g, w.S, w.st);
@@ -122,6 +127,7 @@ extern "C" int64_t algp_potrf_inv_i8_work_bytes(int64_t npad, int nslices, int64
   b += align256(algp_trtri_work_doubles(base < npad ? base : npad) * 8 + 16);
   b += 2 * align256(h * h * (int64_t)nslices);                // da, db
   b += 2 * align256(h * 8);                                   // sa, sb
+  b += 2 * align256((h / I8_TN + 1) * i8_mask_ld(h) + 8);     // occupancy masks
   return b + 256;
 }
 
@@ -152,5 +158,7 @@ extern "C" int algp_potrf_inv_i8(double* A, int64_t npad, int64_t ld, double* Li
   w.db = (int8_t*)p; p += align256(h * h * (int64_t)nslices);
   w.sa = (double*)p; p += align256(h * 8);
   w.sb = (double*)p; p += align256(h * 8);
+  w.ma = (uint8_t*)p; p += align256((h / I8_TN + 1) * i8_mask_ld(h) + 8);
+  w.mb = (uint8_t*)p; p += align256((h / I8_TN + 1) * i8_mask_ld(h) + 8);
   return rec(A, npad, ld, Linv, ldi, 0, w);
 }

@@ -22,7 +22,7 @@ MAX_SET = 2048         # slots per candidate algp_score_sets_large accepts
 I8_FACTOR_SLICES = 8   # digit planes of the recursive INT8 factorisation (56 bits: fp64-grade trailing updates)
 I8_FACTOR_BASE = 2048  # blocks of this many rows or fewer are factored by the DMMA kernels
 I8_FACTOR_MIN = 8192   # factor="auto": smallest padded N that takes the INT8 factorisation
-I8_REORDER_MIN = 2048  # precision "i8": from this many training points the posterior path sorts train / test points along a Z curve
+I8_REORDER_MIN = 8192  # precision "i8": from this many training points the posterior path sorts train / test points along a Z curve
 I8_MAX_K = 32768       # k extent the digit GEMM accepts (8 pairs x 2^15 x 2^12 < 2^31)
 I8_SLICES = 7          # digit planes of the INT8 variance path: 7 x 7 = 49 bits below each row's scale (8 = 56 bits)
 CONST = 0.5 * np.log(2 * np.pi * np.exp(1))        # utils.py:10
@@ -114,11 +114,10 @@ def morton_perm(x, lo=None, hi=None):
     bits = max(1, min(16, 62 // d))
     span = torch.clamp(hi - lo, min=1e-300)
     q = torch.clamp(((x - lo) / span * (1 << bits)).to(torch.int64), 0, (1 << bits) - 1)
-    code = torch.zeros(n, dtype=torch.int64, device=x.device)
-    for b in range(bits):
-        for j in range(d):
-            code |= ((q[:, j] >> b) & 1) << (b * d + j)
-    return torch.argsort(code, stable=True), lo, hi
+    b = torch.arange(bits, device=x.device, dtype=torch.int64)
+    shift = b[None, :] * d + torch.arange(d, device=x.device, dtype=torch.int64)[:, None]     # [d, bits]
+    code = (((q[:, :, None] >> b[None, None, :]) & 1) << shift[None, :, :]).sum(dim=(1, 2))   # bit b of dim j -> bit b d + j
+    return torch.argsort(code), lo, hi
 
 
 def rowsum(partial, scale=1.0, bias=0.0, addvec=None, rows=None):

@@ -10,6 +10,8 @@ slices = [int(s) for s in sys.argv[3].split(",")] if len(sys.argv) > 3 else [8]
 rng = np.random.default_rng(1)
 side = 256 if N > 4096 else 64
 x = engine.to_dev(rng.uniform(0, side, size=(N, 2)))
+if len(sys.argv) > 4 and sys.argv[4] == "morton":
+    x = x[engine.morton_perm(x)[0]].contiguous()
 hy = engine.Hyper(np.log([side / 16.0, side / 16.0]), 0.0, np.log(1e-2), "rbf")
 var = engine.to_dev(np.full(N, 0.01))
 Npad = engine.pad_to(N)

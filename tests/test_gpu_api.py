@@ -379,10 +379,12 @@ def test_prediction_vs_distance_matches_literal_loop():
     np.testing.assert_allclose(got['mean'], mu, rtol=1e-9, atol=1e-9)
 
 
-def test_i8_precision_reorders_points_and_matches_fp64():
-    """gp.precision = 'i8' from N = 2048: training and test points are sorted along a Z curve internally (so that the
+def test_i8_precision_reorders_points_and_matches_fp64(monkeypatch):
+    """gp.precision = "i8" from N = engine.I8_REORDER_MIN (lowered here): training and test points are sorted along a
+    Z curve internally (so that the
     digit GEMM can skip far-apart tiles); the caller sees the same mean / variance, in the caller's order."""
     rng = np.random.default_rng(31)
+    monkeypatch.setattr(engine, "I8_REORDER_MIN", 2048)
     N, M = 2304, 1500
     x = rng.uniform(0, 120, (N, 2))
     xs = rng.uniform(-5, 125, (M, 2))                      # some test points outside the training box
