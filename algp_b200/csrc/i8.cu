@@ -336,22 +336,24 @@ gemm_i8_kernel(const I8Gemm p) {
         const int l = __ffs(bits) - 1;
         bits &= bits - 1;
         const uint32_t ws = __shfl_sync(0xffffffffu, w, l);
-        if (lane == 0) {
+        {
+          // lane 0 reserves the slot and announces the bytes; then lane p copies A plane p (if occupied) and lane S
+          // the B prefix, so the stage's copies go out as one warp instruction instead of up to S + 1 serial ones
           const uint32_t ma = ws & 0xffu, mb = (ws >> 8) & 0xffu;
           const int kc = kb + l, s = it % C::STAGES, u = it / C::STAGES;
-          if (u > 0) mbarrier_wait(&empty_bar[s], (u - 1) & 1);   // the MMAs that read this slot are done
-          const uint32_t st = ring + (uint32_t)s * C::STAGE_BYTES;
-          const int8_t* asrc = a_src + (int64_t)kc * C::A_BYTES;
           const int nB = b_prefix<S>(ma, mb);
-          expect_tx(&full_bar[s], (uint32_t)(__popc(ma) * C::A_PLANE + nB * C::B_PLANE));
-          if (ma == ALLP) {
-            bulk_load(st, asrc, C::A_BYTES, &full_bar[s]);
-          } else {
-#pragma unroll
-            for (int pa = 0; pa < S; ++pa)
-              if ((ma >> pa) & 1u) bulk_load(st + pa * C::A_PLANE, asrc + pa * C::A_PLANE, C::A_PLANE, &full_bar[s]);
+          if (lane == 0) {
+            if (u > 0) mbarrier_wait(&empty_bar[s], (u - 1) & 1);   // the MMAs that read this slot are done
+            expect_tx(&full_bar[s], (uint32_t)(__popc(ma) * C::A_PLANE + nB * C::B_PLANE));
           }
-          bulk_load(st + C::A_BYTES, b_src + (int64_t)kc * C::B_BYTES, (uint32_t)(nB * C::B_PLANE), &full_bar[s]);
+          __syncwarp();
+          const uint32_t st = ring + (uint32_t)s * C::STAGE_BYTES;
+          if (lane < S) {
+            if ((ma >> lane) & 1u)
+              bulk_load(st + lane * C::A_PLANE, a_src + (int64_t)kc * C::A_BYTES + lane * C::A_PLANE, C::A_PLANE, &full_bar[s]);
+          } else if (lane == S) {
+            bulk_load(st + C::A_BYTES, b_src + (int64_t)kc * C::B_BYTES, (uint32_t)(nB * C::B_PLANE), &full_bar[s]);
+          }
         }
         ++it;
       }
