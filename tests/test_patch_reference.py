@@ -38,3 +38,27 @@ def test_patch_keeps_reference_signatures(golden_dir):
         assert list(inspect.signature(getattr(algp_b200.utils, n)).parameters) == \
             list(inspect.signature(getattr(ref_utils, n)).parameters), n
     assert algp_b200.CONST == ref_utils.CONST
+
+
+def test_patch_env_keeps_reference_signature():
+    """algp_b200.paths.patch_env(FieldEnv) replaces get_all_paths with the same parameter list (env.py:197)."""
+    import types
+    for name in ["seaborn", "ipdb", "matplotlib", "matplotlib.pyplot"]:
+        sys.modules.setdefault(name, types.ModuleType(name))
+    import networkx
+    if not hasattr(networkx, "nx"):
+        networkx.nx = networkx
+    sys.path.insert(0, REF)
+    try:
+        import env as ref_env
+    finally:
+        sys.path.remove(REF)
+    from algp_b200 import paths as P
+    before = list(inspect.signature(ref_env.FieldEnv.get_all_paths).parameters)
+    original = ref_env.FieldEnv.get_all_paths
+    try:
+        P.patch_env(ref_env.FieldEnv)
+        assert list(inspect.signature(ref_env.FieldEnv.get_all_paths).parameters) == before
+        assert ref_env.FieldEnv.get_all_paths is not original
+    finally:
+        ref_env.FieldEnv.get_all_paths = original
