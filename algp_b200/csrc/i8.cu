@@ -152,7 +152,11 @@ struct I8Cfg {
   static constexpr int A_BYTES = S * A_PLANE;
   static constexpr int B_BYTES = S * B_PLANE;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;               // S x 6 KB
+#ifndef I8_STAGES_OVERRIDE
   static constexpr int STAGES = (S >= 8) ? 4 : ((200 * 1024) / STAGE_BYTES > 6 ? 6 : (200 * 1024) / STAGE_BYTES);
+#else
+  static constexpr int STAGES = I8_STAGES_OVERRIDE;   // pipeline-depth experiments (scripts/gpu_stages.sh): 3 stages already saturate
+#endif
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024;
   static constexpr int TMEM_COLS = (S * I8_TN > 256) ? 512 : ((S * I8_TN > 128) ? 256 : 128);
 };
