@@ -161,22 +161,20 @@ struct I8Cfg {
   static constexpr int TMEM_COLS = (S * I8_TN > 256) ? 512 : ((S * I8_TN > 128) ? 256 : 128);
 };
 
-// One lane's view of one k chunk: 0 if the chunk needs nothing, else bit 31 | occupied A planes | occupied B planes
-// << 8.  Plane p of A meets plane q of B only if p + q < S, so a chunk is needed iff the lowest occupied planes
-// already qualify.
+// One lane's view of one k chunk: 0 if the chunk needs nothing, else bit 31 | pmin | qmin << 4 | qmax << 8 with
+// pmin / qmin the lowest occupied digit plane of the A / B tile chunk and qmax the highest occupied B plane.
+// Plane p of A meets plane q of B only if p + q < S, so a chunk is needed iff pmin + qmin < S; it then needs the A
+// planes [pmin, S-1-qmin] and, for A plane p, the B planes [qmin, min(S-p, qmax+1)).  Empty planes INSIDE those
+// ranges are multiplied as the zeros they are: the ranges keep the per-chunk schedule to a handful of instructions.
 template <int S>
 __device__ __forceinline__ uint32_t plan_word(const uint8_t* am, const uint8_t* bm, int kc, int kend) {
   if (kc >= kend) return 0u;
   constexpr uint32_t ALLP = (1u << S) - 1u;
   const uint32_t a = (am ? (uint32_t)am[kc] : 0xffu) & ALLP, b = (bm ? (uint32_t)bm[kc] : 0xffu) & ALLP;
   if (a == 0u || b == 0u) return 0u;
-  if ((__ffs(a) - 1) + (__ffs(b) - 1) > S - 1) return 0u;
-  return 0x80000000u | a | (b << 8);
-}
-// B planes a stage has to bring: the prefix that the lowest occupied A plane can reach, up to the highest occupied
-template <int S>
-__device__ __forceinline__ int b_prefix(uint32_t ma, uint32_t mb) {
-  return min(S - (__ffs(ma) - 1), 32 - __clz(mb));
+  const uint32_t pmin = (uint32_t)__ffs(a) - 1u, qmin = (uint32_t)__ffs(b) - 1u, qmax = 31u - (uint32_t)__clz(b);
+  if (pmin + qmin > (uint32_t)(S - 1)) return 0u;
+  return 0x80000000u | pmin | (qmin << 4) | (qmax << 8);
 }
 // D[tmem] += A[smem] B[smem]^T, signed 8-bit operands, s32 accumulators (zero-initialised: always accumulating)
 __device__ __forceinline__ void mma_i8_acc(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc) {
@@ -254,7 +252,6 @@ gemm_i8_kernel(const I8Gemm p) {
   // non-zero digit): chunks and planes that are all zero are neither loaded nor multiplied
   const uint8_t* am = p.a_mask ? p.a_mask + (int64_t)mt * p.mask_ld : nullptr;
   const uint8_t* bm = p.b_mask ? p.b_mask + (int64_t)nt * p.mask_ld : nullptr;
-  constexpr uint32_t ALLP = (1u << S) - 1u;
 
   if (warp < 4) {
     // ===================== epilogue =====================
@@ -343,20 +340,23 @@ gemm_i8_kernel(const I8Gemm p) {
         {
           // lane 0 reserves the slot and announces the bytes; then lane p copies A plane p (if occupied) and lane S
           // the B prefix, so the stage's copies go out as one warp instruction instead of up to S + 1 serial ones
-          const uint32_t ma = ws & 0xffu, mb = (ws >> 8) & 0xffu;
+          // lane 0 reserves the slot and announces the bytes; lane 1 copies the A planes [pmin, S-1-qmin], lane 2 the
+          // B planes [qmin, min(S-pmin, qmax+1)): both ranges are contiguous in the tiled digit layout
+          const int pmin = ws & 0xf, qmin = (ws >> 4) & 0xf, qmax = (ws >> 8) & 0xf;
           const int kc = kb + l, s = it % C::STAGES, u = it / C::STAGES;
-          const int nB = b_prefix<S>(ma, mb);
+          const int nA = S - qmin - pmin, nB = min(S - pmin, qmax + 1) - qmin;
           if (lane == 0) {
             if (u > 0) mbarrier_wait(&empty_bar[s], (u - 1) & 1);   // the MMAs that read this slot are done
-            expect_tx(&full_bar[s], (uint32_t)(__popc(ma) * C::A_PLANE + nB * C::B_PLANE));
+            expect_tx(&full_bar[s], (uint32_t)(nA * C::A_PLANE + nB * C::B_PLANE));
           }
           __syncwarp();
           const uint32_t st = ring + (uint32_t)s * C::STAGE_BYTES;
-          if (lane < S) {
-            if ((ma >> lane) & 1u)
-              bulk_load(st + lane * C::A_PLANE, a_src + (int64_t)kc * C::A_BYTES + lane * C::A_PLANE, C::A_PLANE, &full_bar[s]);
-          } else if (lane == S) {
-            bulk_load(st + C::A_BYTES, b_src + (int64_t)kc * C::B_BYTES, (uint32_t)(nB * C::B_PLANE), &full_bar[s]);
+          if (lane == 1) {
+            bulk_load(st + pmin * C::A_PLANE, a_src + (int64_t)kc * C::A_BYTES + pmin * C::A_PLANE, (uint32_t)(nA * C::A_PLANE),
+                      &full_bar[s]);
+          } else if (lane == 2) {
+            bulk_load(st + C::A_BYTES + qmin * C::B_PLANE, b_src + (int64_t)kc * C::B_BYTES + qmin * C::B_PLANE,
+                      (uint32_t)(nB * C::B_PLANE), &full_bar[s]);
           }
         }
         ++it;
@@ -377,14 +377,14 @@ gemm_i8_kernel(const I8Gemm p) {
         bits &= bits - 1;
         const uint32_t ws = __shfl_sync(0xffffffffu, w, l);
         if (lane == 0) {
-          const uint32_t ma = ws & 0xffu, mb = (ws >> 8) & 0xffu;
+          const int pmin = ws & 0xf, qmin = (ws >> 4) & 0xf, qmax = (ws >> 8) & 0xf;
           const int s = it % C::STAGES, u = it / C::STAGES;
           mbarrier_wait(&full_bar[s], u & 1);
           fence_after();
           const uint32_t a0 = ring + (uint32_t)s * C::STAGE_BYTES, b0 = a0 + C::A_BYTES;
           const uint64_t da0 = desc_kmajor(a0), db0 = desc_kmajor(b0);
-          if (ma == ALLP && mb == ALLP) {
-            // dense chunk: the fixed schedule, every operand a compile-time offset
+          if ((ws & 0xfffu) == (uint32_t)((S - 1) << 8)) {
+            // dense chunk (pmin = qmin = 0, qmax = S-1): the fixed schedule, every operand a compile-time offset
 #pragma unroll
             for (int pa = 0; pa < S; ++pa) {
 #pragma unroll
@@ -395,24 +395,22 @@ gemm_i8_kernel(const I8Gemm p) {
               }
             }
           } else {
-            // sparse chunk: per occupied A plane, the reachable B planes in two groups of four; a group is
-            // multiplied up to its highest occupied plane (N = 64 x that many), empty groups are skipped
+            // sparse chunk: A planes [pmin, S-1-qmin]; plane p meets the B planes [qmin, min(S-p, qmax+1)), issued as
+            // one MMA of up to four planes (N = 64 per plane) plus a second one when more than four remain
             const uint32_t idesc0 = idesc_i8(I8_TM, 0);
-#pragma unroll
-            for (int pa = 0; pa < S; ++pa) {
-              if (!((ma >> pa) & 1u)) continue;
-              const uint32_t reach = mb & ((1u << (S - pa)) - 1u);
-              const uint32_t g0 = reach & 0xFu, g1 = reach >> 4;
-              const uint64_t da = da0 + (uint64_t)((pa * C::A_PLANE) >> 4);
-              if (g0) {
-                const uint32_t cnt = 32u - (uint32_t)__clz(g0);
-                mma_i8_acc(tmem + (uint32_t)(pa * I8_TN), da, db0, idesc0 | ((cnt * (I8_TN >> 3)) << 17));
-              }
-              if (S - pa > 4 && g1) {
-                const uint32_t cnt = 32u - (uint32_t)__clz(g1);
-                mma_i8_acc(tmem + (uint32_t)((pa + 4) * I8_TN), da, db0 + (uint64_t)((4 * C::B_PLANE) >> 4),
-                           idesc0 | ((cnt * (I8_TN >> 3)) << 17));
-              }
+            const uint64_t db = db0 + (uint64_t)(qmin * (C::B_PLANE >> 4));
+            uint64_t da = da0 + (uint64_t)(pmin * (C::A_PLANE >> 4));
+            uint32_t td = tmem + (uint32_t)((pmin + qmin) * I8_TN);
+#pragma unroll 1
+            for (int pa = pmin; pa <= S - 1 - qmin; ++pa) {
+              const int n = min(S - pa, qmax + 1) - qmin;
+              const int c0 = min(n, 4);
+              mma_i8_acc(td, da, db, idesc0 | ((uint32_t)(c0 * (I8_TN >> 3)) << 17));
+              if (n > 4)
+                mma_i8_acc(td + 4 * I8_TN, da, db + (uint64_t)((4 * C::B_PLANE) >> 4),
+                           idesc0 | ((uint32_t)((n - 4) * (I8_TN >> 3)) << 17));
+              da += (uint64_t)(C::A_PLANE >> 4);
+              td += I8_TN;
             }
           }
           commit_to(&empty_bar[s]);                              // arrives when these MMAs have read the stage
