@@ -17,6 +17,7 @@ ap.add_argument("--reps", type=int, default=2)
 ap.add_argument("--tf32", action="store_true")
 ap.add_argument("--i8", action="store_true")
 ap.add_argument("--rank", type=int, default=2)
+ap.add_argument("--zorder", action="store_true", help="sort train / test points along a Z curve as precision i8 does")
 a = ap.parse_args()
 from algp_b200._lib import call as _call
 _call("algp_set_potf2_rank", a.rank)
@@ -28,6 +29,10 @@ y = np.sin(x[:, 0] / 9.0) + rng.normal(0, 0.1, a.n)
 hy = engine.Hyper(np.log([a.side / 16.0] * 2), 0.0, np.log(1e-2), "rbf")
 xd, xsd, y0 = engine.to_dev(x), engine.to_dev(xs), engine.to_dev(y - y.mean())
 var = engine.to_dev(np.full(a.n, 0.01))
+if a.zorder:
+    perm, lo, hi = engine.morton_perm(xd)
+    xd, y0 = xd[perm].contiguous(), y0[perm].contiguous()
+    xsd = xsd[engine.morton_perm(xsd, lo, hi)[0]].contiguous()
 for rep in range(a.reps):
     e = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
     e[0].record()
