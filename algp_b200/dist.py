@@ -65,3 +65,77 @@ def sharded_best(state, idx_all, delta_all=None, delta_scalar=0.0, skip=None, gr
     else:
         pair = pack_pair(-np.inf, np.iinfo(np.int64).max, dev)
     return allgather_argmax(pair, group)
+
+
+def sharded_mean_var(hyper, train_x, train_var, y0, ymean, xs, test_var=None, precision="i8", group=None, src=0):
+    """Posterior mean / latent variance over the test rows `xs`, sharded across the ranks of one box.
+
+    The training-set factorisation stays on ONE GPU (rank `src`), as for the scoring path; its inverse factor and
+    the weights alpha are broadcast once (NCCL over NVLink: 8 N^2 bytes), then every rank evaluates a contiguous
+    block of test rows -- they are independent given the factor -- and the blocks are all-gathered.  With
+    precision "i8" and N >= engine.I8_REORDER_MIN the points are sorted along a Z curve first, so a rank's block is
+    also spatially compact.  All arguments are device tensors on this rank's GPU and identical on every rank;
+    returns (mu[M], var[M]) on every rank, in the caller's row order."""
+    from . import engine
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    dev = xs.device
+    N, M = train_x.shape[0], xs.shape[0]
+    reorder = precision == "i8" and N >= engine.I8_REORDER_MIN
+    tperm = None
+    if reorder:
+        perm, lo, hi = engine.morton_perm(train_x)
+        train_x = train_x.index_select(0, perm).contiguous()
+        train_var = None if train_var is None else train_var.index_select(0, perm).contiguous()
+        y0 = y0.index_select(0, perm)
+        tperm, _, _ = engine.morton_perm(xs, lo, hi)
+        xs = xs.index_select(0, tperm).contiguous()
+        test_var = None if test_var is None else test_var.index_select(0, tperm).contiguous()
+    Npad = max(engine.BLK, engine.pad_to(N))
+    if rank == src:
+        f = engine.GPFactor(hyper, train_x, diag_add=train_var, diag_scalar=hyper.noise,
+                            factor="auto" if precision == "i8" else "dmma")
+        alpha, _ = f.solve(y0)
+        head = torch.cat([alpha, f.info.to(torch.float64)])
+    else:
+        f = engine.GPFactor.__new__(engine.GPFactor)
+        f.hyper, f.x, f.N, f.Npad, f.L = hyper, train_x, N, Npad, None
+        f.Linv = torch.empty((Npad, Npad), dtype=torch.float64, device=dev)
+        f.info = torch.zeros(1, dtype=torch.int32, device=dev)
+        f.perm = f.box = None
+        head = torch.empty(Npad + 1, dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.broadcast(f.Linv, src=src, group=group)
+        dist.broadcast(head, src=src, group=group)
+    alpha = head[:Npad].contiguous()
+    f.info = head[Npad:].to(torch.int32)
+    # equal padded shards so that one all-gather returns everything
+    per = (M + world - 1) // world
+    lo_r, hi_r = min(M, rank * per), min(M, (rank + 1) * per)
+    mu_loc = torch.zeros(per, dtype=torch.float64, device=dev)
+    var_loc = torch.zeros(per, dtype=torch.float64, device=dev)
+    if hi_r > lo_r:
+        Ks, part = f.cross(xs[lo_r:hi_r], alpha)
+        mu_loc[:hi_r - lo_r] = engine.rowsum(part, 1.0, ymean, rows=hi_r - lo_r)
+        if precision == "i8" and f.Npad <= engine.I8_MAX_K:
+            rn = f.whiten_norm_i8(Ks)
+        elif precision == "tf32":
+            rn = f.whiten_norm_tf32(Ks)
+        else:
+            _, rn = f.whiten(Ks, want_V=False)
+        tv = None if test_var is None else test_var[lo_r:hi_r].contiguous()
+        var_loc[:hi_r - lo_r] = engine.rowsum(rn, -1.0, hyper.outputscale, tv, rows=hi_r - lo_r)
+    if world > 1:
+        mu_all = torch.empty(per * world, dtype=torch.float64, device=dev)
+        var_all = torch.empty(per * world, dtype=torch.float64, device=dev)
+        dist.all_gather_into_tensor(mu_all, mu_loc, group=group)
+        dist.all_gather_into_tensor(var_all, var_loc, group=group)
+    else:
+        mu_all, var_all = mu_loc, var_loc
+    mu, var = mu_all[:M], var_all[:M]
+    if tperm is not None:
+        inv = torch.empty_like(tperm)
+        inv[tperm] = torch.arange(M, device=dev)
+        mu, var = mu.index_select(0, inv), var.index_select(0, inv)
+    f.check()
+    return mu, var

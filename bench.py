@@ -511,6 +511,37 @@ def default_scale_bench(torch, engine, cpu_sample=24):
                                      "same_picks": bool([int(p) for p in cpu_picks] == [int(p) for p in picks])}}
 
 
+def sharded_fit_predict_bench(torch, dist, engine, dev, world, n_train=16384, grid_side=256, reps=2):
+    """GP fit+predict ms at N = 16384 over the 256 x 256 grid with the test rows sharded over the ranks: kernel build +
+    factor + alpha on rank 0, NCCL broadcast of Linv, every rank its block of rows, all-gather.  Max over ranks."""
+    from algp_b200 import dist as adist
+    rng = np.random.default_rng(1)
+    x = rng.uniform(0, grid_side, size=(n_train, 2))
+    yy, xx = np.meshgrid(np.arange(grid_side), np.arange(grid_side), indexing="ij")
+    xs = np.stack([yy.ravel(), xx.ravel()], 1).astype(np.float64)
+    y = np.sin(x[:, 0] / 9.0) + np.cos(x[:, 1] / 7.0) + rng.normal(0, 0.1, n_train)
+    hy = engine.Hyper(np.log([grid_side / 16.0] * 2), 0.0, np.log(1e-2), "rbf")
+    xd, xsd = engine.to_dev(x, device=dev), engine.to_dev(xs, device=dev)
+    y0 = engine.to_dev(y - y.mean(), device=dev)
+    var = engine.to_dev(np.full(n_train, STATIC_STD ** 2), device=dev)
+    ts = []
+    for rep in range(reps + 1):
+        dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        mu, v = adist.sharded_mean_var(hy, xd, var, y0, float(y.mean()), xsd, precision="i8")
+        e1.record()
+        torch.cuda.synchronize()
+        tt = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        if rep:
+            ts.append(float(tt.item()))
+    return {"n_train": n_train, "n_test": int(xs.shape[0]), "mode": "INT8 digit mode, test rows sharded over %d ranks" % world,
+            "ms": float(np.median(ts)), "var_min": float(v.min().item()), "var_max": float(v.max().item()),
+            "linv_broadcast_bytes": int(8 * n_train * n_train)}
+
+
 def dgemm_peak(torch, n=8192, reps=3, sustained_s=1.5):
     """cuBLAS fp64 GEMM rate on this box: the DMMA roofline denominator (not in MEASURED_PEAKS.json).
     Returns (burst, sustained): best single call, and the mean over ~sustained_s of back-to-back calls
@@ -707,7 +738,14 @@ def run_ours(args, rank, world, local_rank):
 
     extra = {}
     cpu_base = None
-    # the fit+predict / episode / CPU legs explain the N=1 line; at N>1 only the sharded metric is measured
+    if world > 1 and not args.skip_large:
+        # second metric at N > 1: the factorisation stays on rank 0, its inverse factor is broadcast, the 256 x 256
+        # grid of test rows is sharded over the ranks (algp_b200.dist.sharded_mean_var), INT8 digit mode
+        try:
+            extra["fit_predict_sharded"] = sharded_fit_predict_bench(torch, dist, engine, dev, world)
+        except Exception as e:
+            extra["fit_predict_sharded_error"] = repr(e)
+    # the fit+predict / episode / CPU legs explain the N=1 line; at N>1 only the sharded metrics are measured
     # (the other ranks would idle at the barrier while rank 0 ran them)
     if rank == 0 and world == 1:
         try:

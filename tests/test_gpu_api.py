@@ -406,3 +406,22 @@ def test_i8_precision_reorders_points_and_matches_fp64(monkeypatch):
     # a covariance request must not see the reordered factor
     mu_c, cov = algp_b200.predictive_distribution(gp, x, y, xs[:64], var, tvar[:64], return_cov=True)
     np.testing.assert_allclose(np.diag(cov), v64[:64], rtol=0, atol=1e-9)
+
+
+@pytest.mark.parametrize("precision", ["fp64", "i8"])
+def test_sharded_mean_var_single_rank_equals_posterior(precision, monkeypatch):
+    """dist.sharded_mean_var with one rank is the plain posterior path (same factor, same row order)."""
+    from algp_b200 import dist as adist
+    monkeypatch.setattr(engine, "I8_REORDER_MIN", 1024)
+    rng = np.random.default_rng(41)
+    N, M = 1300, 777
+    x = rng.uniform(0, 90, (N, 2))
+    xs = rng.uniform(0, 90, (M, 2))
+    y = np.sin(x[:, 0] / 6.0) + rng.normal(0, 0.1, N)
+    var = rng.uniform(0.01, 0.02, N)
+    th, hy = hyper_pair([5.0, 5.0], 1.0, 0.01, "rbf")
+    dev_ = lambda a: engine.to_dev(np.asarray(a, dtype=np.float64))
+    mu, v = adist.sharded_mean_var(hy, dev_(x), dev_(var), dev_(y - y.mean()), float(y.mean()), dev_(xs), precision=precision)
+    mu_o, v_o = O.predictive_distribution_chol(O.OracleGP(th, "fp64"), x, y, xs, var, None, return_var=True)
+    np.testing.assert_allclose(mu.cpu().numpy(), mu_o, rtol=1e-9, atol=1e-9)
+    np.testing.assert_allclose(v.cpu().numpy(), v_o, rtol=0, atol=1e-9)
