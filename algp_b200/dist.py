@@ -67,6 +67,22 @@ def sharded_best(state, idx_all, delta_all=None, delta_scalar=0.0, skip=None, gr
     return allgather_argmax(pair, group)
 
 
+def row_block(total, rank, world):
+    """Equal padded blocks for one all-gather: (rows per rank, lo, hi) of `rank`'s block of `total` rows."""
+    per = (int(total) + int(world) - 1) // int(world)
+    return per, min(total, rank * per), min(total, (rank + 1) * per)
+
+
+def gather_rows(local, total, group=None):
+    """All-gather the ranks' padded row blocks (1-D tensors of equal length) and cut the padding."""
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    if world == 1:
+        return local[:total]
+    out = torch.empty(local.shape[0] * world, dtype=local.dtype, device=local.device)
+    dist.all_gather_into_tensor(out, local.contiguous(), group=group)
+    return out[:total]
+
+
 def sharded_mean_var(hyper, train_x, train_var, y0, ymean, xs, test_var=None, precision="i8", group=None, src=0):
     """Posterior mean / latent variance over the test rows `xs`, sharded across the ranks of one box.
 
@@ -110,8 +126,7 @@ def sharded_mean_var(hyper, train_x, train_var, y0, ymean, xs, test_var=None, pr
     alpha = head[:Npad].contiguous()
     f.info = head[Npad:].to(torch.int32)
     # equal padded shards so that one all-gather returns everything
-    per = (M + world - 1) // world
-    lo_r, hi_r = min(M, rank * per), min(M, (rank + 1) * per)
+    per, lo_r, hi_r = row_block(M, rank, world)
     mu_loc = torch.zeros(per, dtype=torch.float64, device=dev)
     var_loc = torch.zeros(per, dtype=torch.float64, device=dev)
     if hi_r > lo_r:
@@ -125,14 +140,7 @@ def sharded_mean_var(hyper, train_x, train_var, y0, ymean, xs, test_var=None, pr
             _, rn = f.whiten(Ks, want_V=False)
         tv = None if test_var is None else test_var[lo_r:hi_r].contiguous()
         var_loc[:hi_r - lo_r] = engine.rowsum(rn, -1.0, hyper.outputscale, tv, rows=hi_r - lo_r)
-    if world > 1:
-        mu_all = torch.empty(per * world, dtype=torch.float64, device=dev)
-        var_all = torch.empty(per * world, dtype=torch.float64, device=dev)
-        dist.all_gather_into_tensor(mu_all, mu_loc, group=group)
-        dist.all_gather_into_tensor(var_all, var_loc, group=group)
-    else:
-        mu_all, var_all = mu_loc, var_loc
-    mu, var = mu_all[:M], var_all[:M]
+    mu, var = gather_rows(mu_loc, M, group), gather_rows(var_loc, M, group)
     if tperm is not None:
         inv = torch.empty_like(tperm)
         inv[tperm] = torch.arange(M, device=dev)

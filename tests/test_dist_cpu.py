@@ -66,3 +66,38 @@ def test_allgather_argmax_world2_gloo(case):
     want = (float(scores.max()), int(np.argmax(scores)))
     for _, got in res:
         assert got == want
+
+
+def _rows_worker(rank, world, port, total, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from algp_b200.dist import gather_rows, row_block
+        per, lo, hi = row_block(total, rank, world)
+        local = torch.full((per,), -1.0, dtype=torch.float64)
+        local[:hi - lo] = torch.arange(lo, hi, dtype=torch.float64) * 2.0     # "variance" of row r = 2 r
+        q.put((rank, gather_rows(local, total).numpy()))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("total", [1, 5, 64, 1001])
+def test_sharded_rows_world2_gloo(total):
+    """The row sharding of dist.sharded_mean_var: equal padded blocks, one all-gather, padding cut, every rank
+    ends with all rows in order (an odd total leaves the last block short; total = 1 leaves rank 1 empty)."""
+    from algp_b200.dist import row_block
+    blocks = [row_block(total, r, 2) for r in range(2)]
+    assert blocks[0][1] == 0 and blocks[-1][2] == total and blocks[0][2] == blocks[1][1]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29850 + (os.getpid() % 100)
+    procs = [ctx.Process(target=_rows_worker, args=(r, 2, port, total, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = dict(q.get(timeout=120) for _ in range(2))
+    for p in procs:
+        p.join(timeout=60)
+    want = np.arange(total) * 2.0
+    for r in range(2):
+        np.testing.assert_array_equal(got[r], want)
