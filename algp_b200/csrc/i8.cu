@@ -53,9 +53,16 @@ __device__ __forceinline__ void bulk_load(uint32_t dst, const void* src, uint32_
 // K-major no-swizzle (INTERLEAVE) operand tile: 8 x 16 B core matrices; LBO = 128 B between the two 16-byte
 // k halves of an MMA, SBO = 256 B between 8-row groups (cute::UMMA::SmemDescriptor: version 1 at bit 46,
 // layout_type 0)
-__device__ __forceinline__ uint64_t desc_kmajor(uint32_t saddr) {
-  return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)(128 >> 4) << 16) | ((uint64_t)(256 >> 4) << 32) | (1ull << 46);
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(pred));
+  return pred != 0;
 }
+// The low word holds the start address (>> 4, 14 bits) and the LBO, the high word the SBO and the version: operand
+// offsets only ever touch the low word (shared memory is < 256 KB, no carry), so descriptors are handled as 32-bit
+// values -- 64-bit adds with carry are what kept them out of the uniform datapath.
+__device__ __forceinline__ uint32_t desc_kmajor_lo(uint32_t saddr) { return ((saddr >> 4) & 0x3FFFu) | ((128u >> 4) << 16); }
+#define I8_DESC_HI ((256u >> 4) | (1u << 14))
 // cute::UMMA::InstrDescriptor: c_format S32 (2) [4,6), a/b_format signed 8-bit (1) [7,10) / [10,13), K-major,
 // N>>3 [17,23), M>>4 [24,29)
 __host__ __device__ constexpr uint32_t idesc_i8(int M, int N) {
@@ -177,11 +184,12 @@ __device__ __forceinline__ uint32_t plan_word(const uint8_t* am, const uint8_t* 
   return 0x80000000u | pmin | (qmin << 4) | (qmax << 8);
 }
 // D[tmem] += A[smem] B[smem]^T, signed 8-bit operands, s32 accumulators (zero-initialised: always accumulating)
-__device__ __forceinline__ void mma_i8_acc(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc) {
+__device__ __forceinline__ void mma_i8_acc(uint32_t tmem_d, uint32_t desc_a_lo, uint32_t desc_b_lo, uint32_t idesc) {
   asm volatile(
-      "{\n\t.reg .pred p;\n\tsetp.eq.u32 p, 1, 1;\n\t"
-      "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc)
+      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\tsetp.eq.u32 p, 1, 1;\n\t"
+      "mov.b64 da, {%1, %4};\n\tmov.b64 db, {%2, %4};\n\t"
+      "tcgen05.mma.cta_group::1.kind::i8 [%0], da, db, %3, p;\n\t}"
+      ::"r"(tmem_d), "r"(desc_a_lo), "r"(desc_b_lo), "r"(idesc), "r"(I8_DESC_HI)
       : "memory");
 }
 
@@ -195,7 +203,9 @@ gemm_i8_kernel(const I8Gemm p) {
   __shared__ uint64_t full_bar[C::STAGES], empty_bar[C::STAGES], done_bar;
   __shared__ uint32_t tmem_slot;
   __shared__ double sb_s[I8_TN];
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  // the warp index is broadcast from lane 0 so that the compiler can prove the role branches warp-uniform (the
+  // role bodies then keep their addresses and descriptors in uniform registers)
+  const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0), lane = tid & 31;
   const uint32_t ring = (s_u32(i8_smem_raw) + 1023u) & ~1023u;
 
   // tile map: groups of 16 m-tiles sweep the n-tiles together, so concurrent CTAs stream the same k-window of
@@ -325,8 +335,11 @@ gemm_i8_kernel(const I8Gemm p) {
       if (MODE == 0 || p.rn_partial) p.rn_partial[(int64_t)(m0 + row) * p.rn_nt + nt] = ss * sa * sa;
     }
   } else if (warp == 5 && KT > 0) {
-    // ===================== bulk-copy producer (warp 5; lane 0 issues) =====================
-    // The 32 lanes decode 32 k chunks' occupancy bytes at once; lane 0 then walks the chunks that need work.
+    // ===================== bulk-copy producer (warp 5) =====================
+    // The 32 lanes decode 32 k chunks' occupancy bytes at once; the warp then walks the chunks that need work in
+    // warp-uniform control flow.  Every per-chunk value is broadcast with redux.sync, which the compiler knows to be
+    // warp-uniform: slot addresses, byte counts and barrier addresses then live in uniform registers, and the copies
+    // are issued without the per-instruction R2UR "waterfall" loop that a shuffled (formally divergent) value costs.
     const int8_t* a_src = p.a_tiles + (int64_t)mt * p.kchunks * C::A_BYTES;
     const int8_t* b_src = p.b_tiles + (int64_t)nt * p.kchunks * C::B_BYTES;
     int it = 0;
@@ -336,28 +349,20 @@ gemm_i8_kernel(const I8Gemm p) {
       while (bits) {
         const int l = __ffs(bits) - 1;
         bits &= bits - 1;
-        const uint32_t ws = __shfl_sync(0xffffffffu, w, l);
-        {
-          // lane 0 reserves the slot and announces the bytes; then lane p copies A plane p (if occupied) and lane S
-          // the B prefix, so the stage's copies go out as one warp instruction instead of up to S + 1 serial ones
-          // lane 0 reserves the slot and announces the bytes; lane 1 copies the A planes [pmin, S-1-qmin], lane 2 the
-          // B planes [qmin, min(S-pmin, qmax+1)): both ranges are contiguous in the tiled digit layout
-          const int pmin = ws & 0xf, qmin = (ws >> 4) & 0xf, qmax = (ws >> 8) & 0xf;
-          const int kc = kb + l, s = it % C::STAGES, u = it / C::STAGES;
-          const int nA = S - qmin - pmin, nB = min(S - pmin, qmax + 1) - qmin;
-          if (lane == 0) {
-            if (u > 0) mbarrier_wait(&empty_bar[s], (u - 1) & 1);   // the MMAs that read this slot are done
-            expect_tx(&full_bar[s], (uint32_t)(nA * C::A_PLANE + nB * C::B_PLANE));
-          }
-          __syncwarp();
+        const uint32_t ws = __reduce_or_sync(0xffffffffu, lane == l ? w : 0u);
+        // A planes [pmin, S-1-qmin] and B planes [qmin, min(S-pmin, qmax+1)): both ranges are contiguous in the tiled
+        // digit layout, one bulk copy each
+        const int pmin = ws & 0xf, qmin = (ws >> 4) & 0xf, qmax = (ws >> 8) & 0xf;
+        const int kc = kb + l, s = it % C::STAGES, u = it / C::STAGES;
+        const int nA = S - qmin - pmin, nB = min(S - pmin, qmax + 1) - qmin;
+        if (u > 0) mbarrier_wait(&empty_bar[s], (u - 1) & 1);     // the MMAs that read this slot are done
+        if (elect_one()) {
           const uint32_t st = ring + (uint32_t)s * C::STAGE_BYTES;
-          if (lane == 1) {
-            bulk_load(st + pmin * C::A_PLANE, a_src + (int64_t)kc * C::A_BYTES + pmin * C::A_PLANE, (uint32_t)(nA * C::A_PLANE),
-                      &full_bar[s]);
-          } else if (lane == 2) {
-            bulk_load(st + C::A_BYTES + qmin * C::B_PLANE, b_src + (int64_t)kc * C::B_BYTES + qmin * C::B_PLANE,
-                      (uint32_t)(nB * C::B_PLANE), &full_bar[s]);
-          }
+          expect_tx(&full_bar[s], (uint32_t)(nA * C::A_PLANE + nB * C::B_PLANE));
+          bulk_load(st + pmin * C::A_PLANE, a_src + (int64_t)kc * C::A_BYTES + pmin * C::A_PLANE, (uint32_t)(nA * C::A_PLANE),
+                    &full_bar[s]);
+          bulk_load(st + C::A_BYTES + qmin * C::B_PLANE, b_src + (int64_t)kc * C::B_BYTES + qmin * C::B_PLANE,
+                    (uint32_t)(nB * C::B_PLANE), &full_bar[s]);
         }
         ++it;
       }
@@ -368,6 +373,8 @@ gemm_i8_kernel(const I8Gemm p) {
     // operand of (S - p) x 64 rows, and group g = p + q lives at TMEM columns g x 64: a single MMA of A_p against
     // planes q0..q0+c-1 (N = 64c <= 256) lands every product in its own group.  S(S+1)/2 plane products become
     // ~S(S+1)/8 + S/2 instructions and A_p is read from shared memory once per <= 4 products instead of once each.
+    // Control flow and operands are warp-uniform (ballot / redux.sync), see the producer: descriptors, TMEM addresses
+    // and instruction descriptors are computed in uniform registers, a handful of instructions per MMA.
     int it = 0;
     for (int kb = kbeg; kb < kend; kb += 32) {
       const uint32_t w = plan_word<S>(am, bm, kb + lane, kend);
@@ -375,14 +382,13 @@ gemm_i8_kernel(const I8Gemm p) {
       while (bits) {
         const int l = __ffs(bits) - 1;
         bits &= bits - 1;
-        const uint32_t ws = __shfl_sync(0xffffffffu, w, l);
-        if (lane == 0) {
-          const int pmin = ws & 0xf, qmin = (ws >> 4) & 0xf, qmax = (ws >> 8) & 0xf;
-          const int s = it % C::STAGES, u = it / C::STAGES;
-          mbarrier_wait(&full_bar[s], u & 1);
-          fence_after();
-          const uint32_t a0 = ring + (uint32_t)s * C::STAGE_BYTES, b0 = a0 + C::A_BYTES;
-          const uint64_t da0 = desc_kmajor(a0), db0 = desc_kmajor(b0);
+        const uint32_t ws = __reduce_or_sync(0xffffffffu, lane == l ? w : 0u);
+        const int s = it % C::STAGES, u = it / C::STAGES;
+        mbarrier_wait(&full_bar[s], u & 1);
+        fence_after();
+        const uint32_t a0 = ring + (uint32_t)s * C::STAGE_BYTES, b0 = a0 + C::A_BYTES;
+        const uint32_t da0 = desc_kmajor_lo(a0), db0 = desc_kmajor_lo(b0);
+        if (elect_one()) {
           if ((ws & 0xfffu) == (uint32_t)((S - 1) << 8)) {
             // dense chunk (pmin = qmin = 0, qmax = S-1): the fixed schedule, every operand a compile-time offset
 #pragma unroll
@@ -390,35 +396,39 @@ gemm_i8_kernel(const I8Gemm p) {
 #pragma unroll
               for (int q0 = 0; q0 < S - pa; q0 += 4) {
                 const int cnt = (S - pa - q0) < 4 ? (S - pa - q0) : 4;
-                mma_i8_acc(tmem + (uint32_t)((pa + q0) * I8_TN), da0 + (uint64_t)((pa * C::A_PLANE) >> 4),
-                           db0 + (uint64_t)((q0 * C::B_PLANE) >> 4), idesc_i8(I8_TM, cnt * I8_TN));
+                mma_i8_acc(tmem + (uint32_t)((pa + q0) * I8_TN), da0 + (uint32_t)((pa * C::A_PLANE) >> 4),
+                           db0 + (uint32_t)((q0 * C::B_PLANE) >> 4), idesc_i8(I8_TM, cnt * I8_TN));
               }
             }
           } else {
-            // sparse chunk: A planes [pmin, S-1-qmin]; plane p meets the B planes [qmin, min(S-p, qmax+1)), issued as
-            // one MMA of up to four planes (N = 64 per plane) plus a second one when more than four remain
+            // sparse chunk: the L = S - pmin - qmin A planes from pmin on; the i-th of them meets min(L - i, W) B planes
+            // from qmin on (W = qmax + 1 - qmin), issued as one MMA of up to four planes (N = 64 per plane) plus a
+            // second one when more than four remain.  Unrolled over i: every offset is a compile-time constant.
+            const int pmin = ws & 0xf, qmin = (ws >> 4) & 0xf, qmax = (ws >> 8) & 0xf;
+            const int L = S - pmin - qmin, W = qmax + 1 - qmin;
             const uint32_t idesc0 = idesc_i8(I8_TM, 0);
-            const uint64_t db = db0 + (uint64_t)(qmin * (C::B_PLANE >> 4));
-            uint64_t da = da0 + (uint64_t)(pmin * (C::A_PLANE >> 4));
-            uint32_t td = tmem + (uint32_t)((pmin + qmin) * I8_TN);
-#pragma unroll 1
-            for (int pa = pmin; pa <= S - 1 - qmin; ++pa) {
-              const int n = min(S - pa, qmax + 1) - qmin;
-              const int c0 = min(n, 4);
-              mma_i8_acc(td, da, db, idesc0 | ((uint32_t)(c0 * (I8_TN >> 3)) << 17));
-              if (n > 4)
-                mma_i8_acc(td + 4 * I8_TN, da, db + (uint64_t)((4 * C::B_PLANE) >> 4),
-                           idesc0 | ((uint32_t)((n - 4) * (I8_TN >> 3)) << 17));
-              da += (uint64_t)(C::A_PLANE >> 4);
-              td += I8_TN;
+            const uint32_t db = db0 + (uint32_t)(qmin * (C::B_PLANE >> 4));
+            const uint32_t da = da0 + (uint32_t)(pmin * (C::A_PLANE >> 4));
+            const uint32_t td = tmem + (uint32_t)((pmin + qmin) * I8_TN);
+#pragma unroll
+            for (int i = 0; i < S; ++i) {
+              if (i < L) {
+                const int n = (L - i < W) ? L - i : W;
+                const int c0 = (n < 4) ? n : 4;
+                mma_i8_acc(td + (uint32_t)(i * I8_TN), da + (uint32_t)(i * (C::A_PLANE >> 4)), db,
+                           idesc0 | ((uint32_t)(c0 * (I8_TN >> 3)) << 17));
+                if (n > 4)
+                  mma_i8_acc(td + (uint32_t)((i + 4) * I8_TN), da + (uint32_t)(i * (C::A_PLANE >> 4)),
+                             db + (uint32_t)((4 * C::B_PLANE) >> 4), idesc0 | ((uint32_t)((n - 4) * (I8_TN >> 3)) << 17));
+              }
             }
           }
-          commit_to(&empty_bar[s]);                              // arrives when these MMAs have read the stage
+          commit_to(&empty_bar[s]);                               // arrives when these MMAs have read the stage
         }
         ++it;
       }
     }
-    if (lane == 0) {
+    if (elect_one()) {
       if (it > 0) commit_to(&done_bar);                          // accumulators complete
       else mbarrier_arrive(&done_bar);                           // every chunk was skipped: the zeros stand
     }
