@@ -54,6 +54,7 @@ SIGNATURES = {
     "algp_score_sets_large": (C.c_int, [_p, _i64, _i64, _p, _i32, _p, _f64, _i32, _f64, _p, _p, _p, _f64, _p,
                                         _i32, _i64, _f64, _p, _p, _i64, _p]),
     "algp_score_sets_large_work_doubles": (_i64, [_i32, _i64]),
+    "algp_score_sets_cov": (C.c_int, [_p, _i64, _p, _p, _p, _f64, _p, _i32, _i64, _f64, _p, _p]),
     "algp_mi_terms_large": (C.c_int, [_p, _i64, _p, _p, _i64, _p, _i32, _i64, _p, _f64, _f64, _p, _p, _i64, _p]),
     "algp_mi_terms_large_work_doubles": (_i64, [_i32, _i64]),
     "algp_paths_enumerate": (C.c_int, [_i32, _p, _p, _p, _p, _p, _i32, _i32, _i32, _p, _i32, _f64, _f64, _i64, _p]),

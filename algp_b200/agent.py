@@ -176,7 +176,8 @@ class HotPath(object):
         base = np.nonzero(pi > 0)[0]
         state = engine.PosteriorState(hyper, self._device_X(), base, pi, is_static=static_sampled,
                                       capacity=capacity + STATE_SPARE_COLUMNS,
-                                      precision=getattr(self.gp, "precision", "fp64"))
+                                      precision=getattr(self.gp, "precision", "fp64"),
+                                      cov_mode=getattr(self, "cov_mode", "auto"))
         self._hot_state = dict(hyper=hyper.key(), pi=pi.copy(), state=state, static=np.array(static_sampled, dtype=bool))
         return state, pi
 

@@ -1,0 +1,211 @@
+// Candidate scoring from a resident posterior covariance ("If the build precomputes P (allowed)").
+//
+// score.cu streams k rows of Wt (N doubles each) per candidate to form the Gram matrix G = Wt_C Wt_C^T: 262 KB per
+// candidate at N = 4096, k = 8, and the kernel sits on the L2 -> SM delivery roof.  When the same factored base set
+// is scored again and again (many candidate batches per planning step, agent.py:373-400), the n x n posterior
+// covariance
+//     P = Sigma + sigma_n^2 I - Wt Wt^T                      (lower triangle; one SYRK per base set)
+// is cheaper to keep: a candidate then needs the k(k+1)/2 entries P[c_i][c_j] and nothing else --
+//     logdet(I + D P_CC D),  D = diag(sqrt(delta))          (same matrix as score.cu, same elimination order)
+// i.e. 36 eight-byte gathers instead of 32 768 doubles for k = 8.
+//
+//   score_cov_k8      one THREAD per candidate, k <= 8: the 36 entries and the elimination live in registers
+//   score_cov_generic one CTA per candidate, k <= 128: the k x k matrix in shared memory (as score_sets_generic)
+//
+// Slot semantics are those of score.cu (reference agent.py:377-400): idx < 0 or delta <= 0 or skip[idx] = empty slot,
+// duplicates inside a set count once (the first), score = H_base + n_new CONST + (logdet - sum log((pi0+delta)/pi0)) / 2.
+#include "common.cuh"
+#include <math.h>
+
+#define ALGP_CONST 1.4189385332046727   // 0.5*log(2*pi*e), utils.py:10
+
+namespace {
+
+struct CovArgs {
+  const double* P;         // [n x ldp] lower triangle of the posterior covariance of the base set
+  int64_t ldp;
+  const double* pi0;       // [n] base precisions (0 = unsampled)
+  const int32_t* idx;      // [B x k]   (-1 = empty slot)
+  const double* delta;     // [B x k] or null
+  double delta_scalar;
+  const uint8_t* skip;     // [n] or null
+  int k;
+  int64_t B;
+  double H_base;
+  double* scores;          // [B]
+};
+
+__device__ __forceinline__ double ldg_nc(const double* p) {
+  double v;
+  asm volatile("ld.global.nc.L1::no_allocate.f64 %0, [%1];" : "=d"(v) : "l"(p));
+  return v;
+}
+
+__global__ void __launch_bounds__(128) score_cov_k8_kernel(const CovArgs a) {
+  const int64_t cand = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (cand >= a.B) return;
+  int ix[8];
+  double sq[8];
+  double term = 0.0, nnew = 0.0;
+#pragma unroll
+  for (int s = 0; s < 8; ++s) {
+    int id = -1;
+    double dl = 0.0;
+    if (s < a.k) {
+      id = a.idx[cand * a.k + s];
+      dl = a.delta ? a.delta[cand * a.k + s] : a.delta_scalar;
+    }
+    bool act = id >= 0 && dl > 0.0;
+    if (act && a.skip && a.skip[id]) act = false;
+#pragma unroll
+    for (int q = 0; q < s; ++q)
+      if (ix[q] == id) act = false;          // ix[q] >= 0 only for active slots: duplicates count once
+    ix[s] = act ? id : -1;
+    sq[s] = act ? sqrt(dl) : 0.0;
+    if (act) {
+      const double p0 = a.pi0[id];
+      term += log(p0 + dl) - (p0 > 0.0 ? log(p0) : 0.0);
+      nnew += (p0 > 0.0) ? 0.0 : 1.0;
+    }
+  }
+  // all gathers first (36 independent loads in flight), then the arithmetic
+  double m[36];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+#pragma unroll
+    for (int j = 0; j <= i; ++j) {
+      const int e = i * (i + 1) / 2 + j;
+      m[e] = 0.0;
+      if (ix[i] >= 0 && ix[j] >= 0) {
+        const int hi = ix[i] > ix[j] ? ix[i] : ix[j], lo = ix[i] > ix[j] ? ix[j] : ix[i];
+        m[e] = ldg_nc(a.P + (int64_t)hi * a.ldp + lo);
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+#pragma unroll
+    for (int j = 0; j <= i; ++j) {
+      const int e = i * (i + 1) / 2 + j;
+      m[e] = m[e] * sq[i] * sq[j] + ((i == j) ? 1.0 : 0.0);
+    }
+  }
+  // un-normalised elimination on the lower triangle (the order of score_sets_k8_kernel)
+  double logdet = 0.0;
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    const double piv = m[c * (c + 1) / 2 + c];
+#pragma unroll
+    for (int r = c + 1; r < 8; ++r) {
+      const double f = m[r * (r + 1) / 2 + c] / piv;
+#pragma unroll
+      for (int cc = c + 1; cc <= r; ++cc) m[r * (r + 1) / 2 + cc] = fma(-f, m[cc * (cc + 1) / 2 + c], m[r * (r + 1) / 2 + cc]);
+    }
+    logdet += log(piv);
+  }
+  a.scores[cand] = a.H_base + nnew * ALGP_CONST + 0.5 * (logdet - term);
+}
+
+#define SC_MAXK 128
+__global__ void __launch_bounds__(256) score_cov_generic_kernel(const CovArgs a) {
+  extern __shared__ __align__(16) double sc_smem[];
+  const int k = a.k, pitch = k + 1;
+  double* M = sc_smem;                       // [k][k+1]
+  double* sqd = M + k * pitch;               // [k]
+  int* sidx = (int*)(sqd + k);               // [k]
+  __shared__ double s_t[8], s_n[8];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (int64_t cand = blockIdx.x; cand < a.B; cand += gridDim.x) {
+    __syncthreads();
+    for (int s = tid; s < k; s += 256) {
+      const int id = a.idx[cand * k + s];
+      const double dl = a.delta ? a.delta[cand * k + s] : a.delta_scalar;
+      bool act = id >= 0 && dl > 0.0;
+      if (act && a.skip && a.skip[id]) act = false;
+      for (int q = 0; q < s && act; ++q) {
+        const int oid = a.idx[cand * k + q];
+        const double odl = a.delta ? a.delta[cand * k + q] : a.delta_scalar;
+        if (oid == id && odl > 0.0) act = false;
+      }
+      sidx[s] = act ? id : -1;
+      sqd[s] = act ? sqrt(dl) : 0.0;
+    }
+    __syncthreads();
+    for (int e = tid; e < k * k; e += 256) {
+      const int r = e / k, c = e % k;
+      if (c > r) continue;
+      double m = (r == c) ? 1.0 : 0.0;
+      const int ir = sidx[r], ic = sidx[c];
+      if (ir >= 0 && ic >= 0) {
+        const int hi = ir > ic ? ir : ic, lo = ir > ic ? ic : ir;
+        m = fma(ldg_nc(a.P + (int64_t)hi * a.ldp + lo), sqd[r] * sqd[c], m);
+      }
+      M[r * pitch + c] = m;
+    }
+    __syncthreads();
+    double logdet = 0.0;
+    for (int c = 0; c < k; ++c) {
+      const double piv = M[c * pitch + c];
+      const double inv = 1.0 / piv;
+      if (tid == 0) logdet += log(piv);
+      const int rem = k - 1 - c;
+      for (int e = tid; e < rem * rem; e += 256) {
+        const int r = c + 1 + e / rem, cc = c + 1 + e % rem;
+        if (cc <= r) M[r * pitch + cc] = fma(-M[r * pitch + c] * inv, M[cc * pitch + c], M[r * pitch + cc]);
+      }
+      __syncthreads();
+    }
+    double term = 0.0, nnew = 0.0;
+    for (int s = tid; s < k; s += 256)
+      if (sidx[s] >= 0) {
+        const double p0 = a.pi0[sidx[s]];
+        const double dl = sqd[s] * sqd[s];
+        term += log(p0 + dl) - (p0 > 0.0 ? log(p0) : 0.0);
+        nnew += (p0 > 0.0) ? 0.0 : 1.0;
+      }
+    term = warp_sum(term);
+    nnew = warp_sum(nnew);
+    if (lane == 0) { s_t[warp] = term; s_n[warp] = nnew; }
+    __syncthreads();
+    if (tid == 0) {
+      double tt = 0.0, nn = 0.0;
+      for (int w = 0; w < 8; ++w) { tt += s_t[w]; nn += s_n[w]; }
+      a.scores[cand] = a.H_base + nn * ALGP_CONST + 0.5 * (logdet - tt);
+    }
+  }
+}
+
+}  // namespace
+
+// scores[c] = H(base set + candidate set c) from the lower triangle of the posterior covariance P [n x ldp] of the
+// base set (P = Sigma + sigma_n^2 I - Wt Wt^T): the restructured form of the slogdet loops of agent.py:373-400 /
+// utils.py:188-194 with the Schur complement read instead of recomputed.  k <= 128.
+extern "C" int algp_score_sets_cov(const double* P, int64_t ldp, const double* pi0, const int32_t* idx, const double* delta,
+                                   double delta_scalar, const uint8_t* skip, int k, int64_t B, double H_base, double* scores,
+                                   void* stream) {
+  if (!P || !pi0 || !idx || !scores || k < 1 || B < 0 || ldp < 1) return ALGP_ERR_INVALID;
+  if (k > SC_MAXK) return ALGP_ERR_UNSUPPORTED;
+  if (B == 0) return ALGP_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  CovArgs a;
+  a.P = P; a.ldp = ldp; a.pi0 = pi0; a.idx = idx; a.delta = delta; a.delta_scalar = delta_scalar; a.skip = skip;
+  a.k = k; a.B = B; a.H_base = H_base; a.scores = scores;
+  if (k <= 8) {
+    score_cov_k8_kernel<<<(unsigned)((B + 127) / 128), 128, 0, st>>>(a);
+  } else {
+    const size_t smem = (size_t)k * (k + 1) * sizeof(double) + (size_t)k * sizeof(double) + (size_t)k * sizeof(int) + 16;
+    static bool configured = false;
+    if (!configured) {
+      ALGP_CUDA(cudaFuncSetAttribute(score_cov_generic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)((size_t)SC_MAXK * (SC_MAXK + 1) * 8 + SC_MAXK * 12 + 16)));
+      configured = true;
+    }
+    int dev = 0, sms = 148;
+    ALGP_CUDA(cudaGetDevice(&dev));
+    ALGP_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    const int64_t cap = (int64_t)sms * 4;
+    score_cov_generic_kernel<<<(unsigned)(B < cap ? B : cap), 256, smem, st>>>(a);
+  }
+  ALGP_LAUNCH_CHECK();
+  return ALGP_OK;
+}

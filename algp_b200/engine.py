@@ -332,10 +332,19 @@ class PosteriorState(object):
     H_base = H(B), the running precisions pi and static flags.  ``capacity`` extra
     columns are reserved for rank-1 appends (greedy commits)."""
 
-    def __init__(self, hyper, X, base_idx, pi0, is_static=None, capacity=0, precision="fp64"):
+    def __init__(self, hyper, X, base_idx, pi0, is_static=None, capacity=0, precision="fp64", cov_mode="auto"):
         """precision="i8": the factor (from N = 8192) and the W^T build (from N = 1024) run as exact INT8 digit
-        GEMMs with 8 planes (fp64-grade) instead of DMMA."""
+        GEMMs with 8 planes (fp64-grade) instead of DMMA.
+        cov_mode: "never" scores candidate sets by streaming rows of Wt; "always" builds the resident posterior
+        covariance P (build_cov) before the first scoring call; "auto" (default) builds it once the scoring work
+        streamed against an unchanged state would have paid for the build (see score_sets)."""
+        if cov_mode not in ("auto", "never", "always"):
+            raise ValueError("cov_mode must be 'auto', 'never' or 'always'")
         dev = X.device
+        self.precision = precision
+        self.cov_mode = cov_mode
+        self.P = None                  # [n_pad x n_pad] lower triangle of Sigma + noise I - Wt Wt^T, or None
+        self._stream_s = 0.0           # estimated seconds of Wt streaming since the state last changed
         self.hyper = hyper
         self.X = X
         self.n = X.shape[0]
@@ -349,7 +358,7 @@ class PosteriorState(object):
         prior = hyper.outputscale + hyper.noise           # diag of cov_matrix (agent.py:90)
         if self.N0 == 0:
             self.Npad = 0
-            self.ldw = pad_to(max(16, capacity), 16)
+            self.ldw = pad_to(max(32, capacity), 32)
             self.Wt = torch.zeros((self.n_pad, self.ldw), dtype=torch.float64, device=dev)
             self.diagP = torch.full((self.n,), prior, dtype=torch.float64, device=dev)
             self.H_base_dev = torch.zeros(1, dtype=torch.float64, device=dev)
@@ -361,7 +370,7 @@ class PosteriorState(object):
             self.factor = GPFactor(hyper, xb, diag_add=inv_pi, diag_scalar=hyper.noise,
                                    factor="auto" if precision == "i8" else "dmma")
             self.Npad = self.factor.Npad
-            self.ldw = pad_to(self.Npad + capacity, 16)
+            self.ldw = pad_to(self.Npad + capacity, 32)      # multiple of the digit GEMM's k chunk (build_cov)
             Ks, _ = kbuild(hyper, X, xb, self.n_pad, self.Npad)
             call("algp_scatter_add", ptr(Ks), Ks.stride(0), ptr(bidx.to(torch.int32)), self.N0, hyper.noise, stream())
             self.Wt = torch.zeros((self.n_pad, self.ldw), dtype=torch.float64, device=dev)
@@ -386,6 +395,57 @@ class PosteriorState(object):
             self._H_base = float(self.H_base_dev.item())
         return self._H_base
 
+    # ---- resident posterior covariance ("If the build precomputes P (allowed)") ----
+    COV_MAX_K = 128                # slots per candidate algp_score_sets_cov accepts
+    STREAM_BYTES_PER_S = 10.0e12   # measured L2->SM delivery of score_sets_k8_kernel (profiles/r01_prof_score_summary.csv)
+    COV_FLOPS_PER_S = {"fp64": 30.0e12, "i8": 100.0e12}   # lower-triangle SYRK rates of algp_gemm_nt / algp_gemm_nt_i8
+
+    def cov_build_seconds(self):
+        """Model of the build_cov() time: n_pad^2 x ncols flops (lower triangle of a SYRK) at the measured rates."""
+        kind = "i8" if (self.precision == "i8" and 1024 <= pad_to(self.ncols, 32) <= I8_MAX_K) else "fp64"
+        return float(self.n_pad) ** 2 * max(self.ncols, 1) / self.COV_FLOPS_PER_S[kind] + 1.0e-3
+
+    def build_cov(self):
+        """P = Sigma + sigma_n^2 I - Wt Wt^T, lower triangle, [n_pad x n_pad] fp64 resident in HBM: the posterior
+        covariance of the current base set over all field locations.  Candidate scoring then gathers k(k+1)/2
+        entries per set (algp_score_sets_cov) instead of streaming k rows of Wt.  One kernel-matrix build plus one
+        SYRK (DMMA, or exact INT8 digit GEMM with precision "i8"); dropped by append / append_block."""
+        P, _ = kbuild(self.hyper, self.X, None, self.n_pad, self.n_pad, diag_scalar=self.hyper.noise)
+        kpad = pad_to(self.ncols, 32)
+        if self.ncols > 0:
+            W = self.Wt[:, :kpad]
+            if self.precision == "i8" and 1024 <= kpad <= I8_MAX_K:
+                at, asc = GPFactor.split_i8(None, W, I8_FACTOR_SLICES, 128)
+                bt, bsc = GPFactor.split_i8(None, W, I8_FACTOR_SLICES, 64)
+                call("algp_gemm_nt_i8", ptr(at), ptr(asc), self.n_pad, ptr(bt), ptr(bsc), self.n_pad, kpad,
+                     I8_FACTOR_SLICES, -1.0, 1.0, ptr(P), P.stride(0), 0, 1, stream())
+                del at, bt
+            else:
+                call("algp_gemm_nt", ptr(self.Wt), self.ldw, ptr(self.Wt), self.ldw, ptr(P), P.stride(0), self.n_pad,
+                     self.n_pad, kpad, -1.0, 1.0, 1, stream())
+        self.P = P
+        return P
+
+    def drop_cov(self):
+        self.P = None
+        self._stream_s = 0.0
+
+    def _want_cov(self, B, k):
+        """Rent-or-buy: stream rows of Wt until the streaming done against this unchanged state would have paid
+        for the covariance build, then build it (at most twice the cost of the better choice in hindsight)."""
+        if self.P is not None:
+            return k <= self.COV_MAX_K
+        if self.cov_mode == "never" or k > self.COV_MAX_K or self.ncols == 0:
+            return False
+        if self.cov_mode == "auto":
+            if self._stream_s < self.cov_build_seconds():
+                return False
+            free, total = torch.cuda.mem_get_info(self.X.device)
+            if 8.0 * self.n_pad * self.n_pad * 2.5 > free:          # P plus the transient digit planes of Wt
+                return False
+        self.build_cov()
+        return True
+
     def score_sets(self, idx, delta=None, delta_scalar=0.0, H_base=None, out=None, skip=None):
         """scores[c] = H(S1_c) for candidate sets idx [B,k] (int32 device tensor, -1 = empty)."""
         B, k = idx.shape
@@ -393,6 +453,11 @@ class PosteriorState(object):
             out = torch.empty(B, dtype=torch.float64, device=idx.device)
         ls, ls_p = _lib.host_f64(self.hyper.log_ls)
         hb = self.H_base if H_base is None else H_base
+        if self._want_cov(B, k):
+            call("algp_score_sets_cov", ptr(self.P), self.P.stride(0), ptr(self.pi), ptr(idx), ptr(delta),
+                 float(delta_scalar), ptr(skip), k, B, float(hb), ptr(out), stream())
+            return out
+        self._stream_s += 8.0 * B * k * max(self.ncols, 1) / self.STREAM_BYTES_PER_S
         if k > MAX_SET_SMEM:
             # long paths: the k x k matrix of a candidate lives in a global scratch instead of shared memory
             nwork = _lib.lib.algp_score_sets_large_work_doubles(k, B)
@@ -425,6 +490,7 @@ class PosteriorState(object):
         if self.ncols >= self.ldw:
             raise RuntimeError("PosteriorState capacity exhausted (%d columns)" % self.ldw)
         ls, ls_p = _lib.host_f64(self.hyper.log_ls)
+        self.drop_cov()
         call("algp_append", ptr(self.Wt), self.ldw, self.ncols, ptr(self.X), self.n, self.hyper.d, ls_p,
              self.hyper.log_os, self.hyper.kind, self.hyper.noise, ptr(self.diagP), ptr(self.pi), ptr(self.is_static),
              C.c_void_p(j_dev.data_ptr()), float(delta), int(mark_static), ptr(self._appwork), stream())
@@ -440,6 +506,7 @@ class PosteriorState(object):
             raise RuntimeError("PosteriorState capacity exhausted (%d columns)" % self.ldw)
         if getattr(self, "_blkwork", None) is None:
             self._blkwork = torch.empty(_lib.lib.algp_append_block_work_doubles(), dtype=torch.float64, device=self.X.device)
+        self.drop_cov()
         ls, ls_p = _lib.host_f64(self.hyper.log_ls)
         dl_dev, dl_scalar = None, 0.0
         if np.ndim(delta) == 0 and not torch.is_tensor(delta):

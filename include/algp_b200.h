@@ -166,6 +166,14 @@ int algp_score_sets_large(const double* Wt, int64_t ldw, int64_t ncols, const do
                           const int32_t* idx, const double* delta, double delta_scalar, const uint8_t* skip, int k,
                           int64_t B, double H_base, double* scores, double* work, int64_t work_doubles, void* stream);
 int64_t algp_score_sets_large_work_doubles(int k, int64_t B);
+/* The same scores from a RESIDENT posterior covariance of the base set, P = Sigma + sigma_n^2 I - Wt Wt^T
+ * (lower triangle of an [n x ldp] matrix; build it with algp_kbuild + algp_gemm_nt / algp_gemm_nt_i8, lower_only):
+ * a candidate reads its k(k+1)/2 entries P[c_i][c_j] instead of k rows of Wt.  The Schur complement of
+ * agent.py:373-400 / utils.py:188-194 is then a gather; pays off when one base set is scored many times.
+ * k <= 128 (ALGP_ERR_UNSUPPORTED beyond: use algp_score_sets_large). */
+int algp_score_sets_cov(const double* P, int64_t ldp, const double* pi0, const int32_t* idx, const double* delta,
+                        double delta_scalar, const uint8_t* skip, int k, int64_t B, double H_base, double* scores,
+                        void* stream);
 /* greedy utilities for every location (k = 1 closed form, agent.py:341) */
 int algp_greedy_utilities(const double* diagP, const double* pi, const uint8_t* is_static, double d_static,
                           int64_t n, double* ut, void* stream);

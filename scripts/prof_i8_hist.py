@@ -53,6 +53,7 @@ for q0 in range(S):
 H = torch.einsum("pk,qrk->pqr", cntA, cntB).cpu().numpy()                                   # pairs per (pmin,qmin,qmax)
 total_pairs = float(MT) * float(inrange.sum())
 chunks = mmas = 0.0
+nbytes = 0.0
 cols = 0.0
 cyc = 0.0
 byN = {}
@@ -64,6 +65,7 @@ for p in range(S):
             if c == 0 or p + q0 > S - 1:
                 continue
             chunks += c
+            nbytes += c * ((S - q0 - p) * 4096 + (min(S - p, q1 + 1) - q0) * 2048)
             nm = 0
             for pa in range(p, S - q0):
                 n = min(S - pa, q1 + 1) - q0
@@ -79,6 +81,7 @@ print("MMAs %.3e (%.2f per surviving chunk), columns %.3e; dense schedule would 
 print("MMAs by planes-per-instruction:", {k: "%.3e" % v for k, v in sorted(byN.items())})
 print("chunks by MMA count:", {k: "%.3e" % v for k, v in sorted(bycount.items())})
 clk = 1.9e9
+print("operand bytes through L2->SM: %.1f GB (dense schedule: %.1f GB); at 10.3 TB/s: %.1f ms" % (nbytes / 1e9, total_pairs * S * 6144 / 1e9, nbytes / 10.3e12 * 1e3))
 print("tensor floor (N/2 cycles): %.1f ms; with the 60-cycle minimum: %.1f ms (148 SMs, %.1f GHz)" % (cols / 2 / 148 / clk * 1e3, cyc / 148 / clk * 1e3, clk / 1e9))
 for ov in (50, 100, 150, 200, 300):
     print("  + %d cycles per surviving chunk: %.1f ms" % (ov, (cyc + ov * chunks) / 148 / clk * 1e3))

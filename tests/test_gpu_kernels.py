@@ -199,6 +199,94 @@ def test_score_sets_matches_oracle(kind, k):
     assert int(np.argmax(got)) == int(np.argmax(want))
 
 
+@pytest.mark.parametrize("kind", ["rbf", "matern"])
+@pytest.mark.parametrize("k", [1, 5, 8, 11, 40, 128])
+def test_score_sets_resident_cov_matches_oracle(kind, k):
+    """cov_mode="always": the posterior covariance P of the base set is built once (kernel matrix + SYRK) and every
+    candidate is scored from its k(k+1)/2 gathered entries -- same oracle, same slot semantics (empty, duplicate and
+    zero-increment slots, skip flags) as the streaming kernels."""
+    X, th, hy, static, mobile, pi0, cov, ss, ms, rng = scoring_problem(kind, d_extra=(1 if k == 11 else 0))
+    n = len(X)
+    Bc = 300 if k <= 8 else 40
+    idx = np.full((Bc, k), -1, dtype=np.int32)
+    delta = np.zeros((Bc, k))
+    for c in range(Bc):
+        m = int(rng.integers(1, k + 1))
+        sel = rng.choice(n, m, replace=False)
+        idx[c, :m] = sel
+        delta[c, :m] = np.where(rng.random(m) < 0.3, 1 / ss ** 2, 1 / ms ** 2)
+        if m >= 3 and c % 4 == 0:
+            idx[c, m - 1] = idx[c, 0]
+        if m >= 2 and c % 5 == 0:
+            delta[c, 1] = 0.0
+    base = np.nonzero(pi0 > 0)[0]
+    state = engine.PosteriorState(hy, dev(X), base, pi0, cov_mode="always")
+    stream = engine.PosteriorState(hy, dev(X), base, pi0, cov_mode="never")
+    skip = np.zeros(n, dtype=np.uint8)
+    skip[rng.choice(n, n // 10, replace=False)] = 1
+    for sk in (None, dev(skip, torch.uint8)):
+        got = state.score_sets(dev(idx, torch.int32), dev(delta), skip=sk).cpu().numpy()
+        assert state.P is not None and stream.P is None
+        ref = stream.score_sets(dev(idx, torch.int32), dev(delta), skip=sk).cpu().numpy()
+        np.testing.assert_allclose(got, ref, rtol=1e-11, atol=1e-10)
+    ost = O.posterior_state(cov, pi0)
+    Pd = np.tril(state.P.cpu().numpy()[:n, :n])
+    np.testing.assert_allclose(Pd, np.tril(ost["P"]), rtol=0, atol=1e-10)
+    want = O.score_sets_restructured(ost["P"], pi0, idx, delta, ost["H"])
+    got = state.score_sets(dev(idx, torch.int32), dev(delta)).cpu().numpy()
+    np.testing.assert_allclose(got, want, rtol=1e-8, atol=1e-9)
+    assert int(np.argmax(got)) == int(np.argmax(want))
+
+
+def test_resident_cov_policy_and_invalidation():
+    """cov_mode="auto" streams until the streamed work would have paid for the build, then switches; a commit
+    (append) drops the covariance, and scores after the commit are those of a freshly built state."""
+    X, th, hy, static, mobile, pi0, cov, ss, ms, rng = scoring_problem("rbf")
+    n = len(X)
+    base = np.nonzero(pi0 > 0)[0]
+    state = engine.PosteriorState(hy, dev(X), base, pi0, is_static=static, capacity=8)
+    free = np.nonzero(pi0 == 0)[0]
+    idx = rng.choice(free, (4000, 8)).astype(np.int32)
+    idx_d = dev(idx, torch.int32)
+    first = state.score_sets(idx_d, None, delta_scalar=1 / ms ** 2).cpu().numpy()
+    assert state.P is None                                         # one small batch does not pay for the build
+    state._stream_s = state.cov_build_seconds()                    # ... as if enough had been streamed
+    second = state.score_sets(idx_d, None, delta_scalar=1 / ms ** 2).cpu().numpy()
+    assert state.P is not None
+    np.testing.assert_allclose(second, first, rtol=1e-11, atol=1e-10)
+    j = torch.tensor([int(free[0])], dtype=torch.int64, device="cuda")
+    state.append(j, 1 / ss ** 2)
+    assert state.P is None and state._stream_s == 0.0
+    after = state.score_sets(idx_d, None, delta_scalar=1 / ms ** 2).cpu().numpy()
+    pi1 = pi0.copy(); pi1[free[0]] = 1 / ss ** 2
+    fresh = engine.PosteriorState(hy, dev(X), np.nonzero(pi1 > 0)[0], pi1, cov_mode="always")
+    want = fresh.score_sets(idx_d, None, delta_scalar=1 / ms ** 2, H_base=state.H_base).cpu().numpy()
+    np.testing.assert_allclose(after, want, rtol=1e-9, atol=1e-9)
+    never = engine.PosteriorState(hy, dev(X), base, pi0, cov_mode="never")
+    never._stream_s = 1e9
+    never.score_sets(idx_d, None, delta_scalar=1.0)
+    assert never.P is None
+    with pytest.raises(ValueError):
+        engine.PosteriorState(hy, dev(X), base, pi0, cov_mode="sometimes")
+
+
+def test_resident_cov_i8_build_matches_dmma():
+    """precision="i8": the SYRK of the covariance build runs as an exact INT8 digit GEMM (lower tiles only)."""
+    X, y, tr, ytr, rng = field_problem(48, 48, 1100, seed=4)
+    th, hy = hyper_pair([3.0, 3.0], 1.0, 0.01, "rbf")
+    n = len(X)
+    pi0 = np.zeros(n); pi0[tr] = 100.0
+    s64 = engine.PosteriorState(hy, dev(X), tr, pi0, is_static=pi0 > 0, cov_mode="always")
+    s8 = engine.PosteriorState(hy, dev(X), tr, pi0, is_static=pi0 > 0, precision="i8", cov_mode="always")
+    free = np.setdiff1d(np.arange(n), tr)
+    idx = dev(rng.choice(free, (500, 8)).astype(np.int32), torch.int32)
+    sc64 = s64.score_sets(idx, None, delta_scalar=1.0).cpu().numpy()
+    sc8 = s8.score_sets(idx, None, delta_scalar=1.0).cpu().numpy()
+    assert s8.P is not None and s64.P is not None
+    np.testing.assert_allclose(np.tril(s8.P.cpu().numpy()[:n, :n]), np.tril(s64.P.cpu().numpy()[:n, :n]), rtol=0, atol=1e-11)
+    np.testing.assert_allclose(sc8, sc64, rtol=1e-10, atol=1e-9)
+
+
 def test_score_sets_empty_base_and_scalar_delta():
     X, th, hy, static, mobile, pi0, cov, ss, ms, rng = scoring_problem("rbf")
     n = len(X)
