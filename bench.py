@@ -933,8 +933,9 @@ def run_ours(args, rank, world, local_rank):
                          # (profiles/r01_prof_score_summary.csv): 7.71 GB + 5 MB
                          "traffic": 7.716e9, "achieved_dram_gbs": 7.716 / kernel_ms * 1e3, "frac_dram": 7.716 / kernel_ms * 1e3 / peak_hbm,
                          "peak_source": peak_src,
-                         "note": "above 1.0 of the DRAM peak because 40% of the sector reads hit the 126 MB L2; "
-                                 "the binding roof is L2->SM throughput (~10.3 TB/s achieved)",
+                         "note": "above 1.0 of the DRAM peak because 40% of the sector reads hit the 126 MB L2; DRAM itself is "
+                                 "~73% busy (frac_dram) and the DMMA pipe 57%: no single roof is reached (bulk copies from a hot L2 "
+                                 "deliver 24 TB/s, profiles/r01_l2_multicast_microbench.log)",
                          "kernel_ms": kernel_ms, "algorithmic_bytes_per_launch": algo_bytes},
             "setup_ms_factor_and_W": setup_ms, "setup_ms_factor_and_W_i8": setup_ms_i8, "setup_i8_max_abs_dW": setup_i8_dW,
             "winner": win, "H_base": H_base,
