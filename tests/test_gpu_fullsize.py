@@ -49,6 +49,38 @@ def test_config_b_scores_match_oracle_on_a_sample(config_b):
         assert scores[c] == pytest.approx(O.set_entropy_literal(cov, st, mo, bench.STATIC_STD, bench.MOBILE_STD), rel=1e-8)
 
 
+def test_config_b_resident_cov_matches_streaming(config_b):
+    """configs[2] with the posterior covariance resident (DMMA and INT8 builds): all 65536 scores equal the streaming
+    kernel's, same winner; slot order still does not matter."""
+    grid, base, idx, delta, hy, pi0, state = config_b
+    idx_d, delta_d = dev(idx, torch.int32), dev(delta)
+    state.drop_cov()
+    mode = state.cov_mode
+    state.cov_mode = "never"
+    try:
+        s0 = state.score_sets(idx_d, delta_d).cpu().numpy()
+    finally:
+        state.cov_mode = mode
+    hyper = engine.Hyper(np.log(hy["ls"]), np.log(hy["os"]), np.log(hy["noise"]), hy["kind"])
+    P64 = None
+    for prec in ("fp64", "i8"):
+        st = engine.PosteriorState(hyper, dev(grid), base, pi0, is_static=pi0 > 0, precision=prec, cov_mode="always")
+        s1 = st.score_sets(idx_d, delta_d).cpu().numpy()
+        assert st.P is not None
+        np.testing.assert_allclose(s1, s0, rtol=1e-11, atol=1e-9)
+        assert int(np.argmax(s1)) == int(np.argmax(s0))
+        perm = np.random.default_rng(2).permutation(8)
+        s2 = st.score_sets(dev(idx[:, perm], torch.int32), dev(delta[:, perm])).cpu().numpy()
+        np.testing.assert_allclose(s2, s1, rtol=1e-11, atol=1e-10)
+        if prec == "fp64":
+            P64 = torch.tril(st.P)
+        else:
+            assert float((torch.tril(st.P) - P64).abs().max().item()) < 1e-11
+        del st
+    del P64
+    torch.cuda.empty_cache()
+
+
 def test_config_b_score_properties(config_b):
     grid, base, idx, delta, hy, pi0, state = config_b
     idx_d, delta_d = dev(idx, torch.int32), dev(delta)
