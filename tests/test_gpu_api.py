@@ -165,6 +165,31 @@ def test_agent_matches_reference_golden(golden_dir, kind):
     assert best == int(g["best_path"])
 
 
+@pytest.mark.parametrize("cov_mode", ["always", "auto"])
+@pytest.mark.parametrize("kind", ["rbf", "matern"])
+def test_agent_best_path_resident_cov_matches_reference_golden(golden_dir, kind, cov_mode):
+    """Agent.best_path with the resident posterior covariance (agent.cov_mode): the reference's own choice, whether the
+    covariance is built up front ("always") or by the rent-or-buy rule after repeated calls on an unchanged state
+    ("auto"); a greedy step afterwards (which commits samples) still matches the reference."""
+    g = load(golden_dir, "ref_agent_%s_entropy.npz" % kind)
+    ag = agent_from_golden(g, kind)
+    ag.cov_mode = cov_mode
+    paths = unflatten(g["path_lens"], g["path_flat"])
+    static_idx = [int(v) for v in g["static_indices"]]
+    assert ag.best_path(paths, static_idx) == int(g["best_path"])
+    state = ag._hot_state["state"]
+    if cov_mode == "always":
+        assert state.P is not None
+    else:
+        assert state.P is None                      # a few hundred candidates do not pay for the build ...
+        state._stream_s = state.cov_build_seconds()
+        assert ag.best_path(paths, static_idx) == int(g["best_path"])
+        assert state.P is not None                  # ... but enough of them do
+    assert ag.best_path(paths, static_idx) == int(g["best_path"])
+    ag2 = agent_from_golden(g, kind)
+    assert ag.greedy(3) == ag2.greedy(3)
+
+
 def test_agent_mutual_information_matches_reference(golden_dir):
     """criterion='mutual_information' (agent.py:330-339, 388-397) against the reference's own picks and,
     utility by utility, against the literal loops."""
