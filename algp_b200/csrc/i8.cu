@@ -32,6 +32,7 @@
 #include "common.cuh"
 #include "i8.cuh"
 
+#define I8_MAX_PLAN 1024                // k chunks per tile: K <= 32768
 #define I8_THREADS 192                  // 4 epilogue warps, warp 4: MMA issuer, warp 5: bulk-copy producer
 
 namespace {
@@ -193,6 +194,35 @@ __device__ __forceinline__ void mma_i8_acc(uint32_t tmem_d, uint32_t desc_a_lo, 
       : "memory");
 }
 
+// The MMAs of a sparse chunk with L A planes and W reachable B planes (W <= L), every offset and every instruction
+// descriptor a compile-time constant relative to the chunk's three bases: the i-th A plane meets min(L - i, W) B planes,
+// issued as one MMA of up to four planes (N = 64 per plane) plus a second one when more than four remain.
+template <int S, int L, int W>
+__device__ __forceinline__ void issue_sparse_lw(uint32_t td, uint32_t da, uint32_t db) {
+  using C = I8Cfg<S>;
+#pragma unroll
+  for (int i = 0; i < L; ++i) {
+    const int n = (L - i < W) ? L - i : W;
+    const int c0 = n < 4 ? n : 4;
+    mma_i8_acc(td + (uint32_t)(i * I8_TN), da + (uint32_t)(i * (C::A_PLANE >> 4)), db, idesc_i8(I8_TM, c0 * I8_TN));
+    if (n > 4)
+      mma_i8_acc(td + (uint32_t)((i + 4) * I8_TN), da + (uint32_t)(i * (C::A_PLANE >> 4)), db + (uint32_t)((4 * C::B_PLANE) >> 4),
+                 idesc_i8(I8_TM, (n - 4) * I8_TN));
+  }
+}
+// one switch over the S(S+1)/2 (L, W) pairs: a single indexed branch instead of a chain of compares
+template <int S>
+__device__ __forceinline__ void issue_sparse(int L, int W, uint32_t td, uint32_t da, uint32_t db) {
+#define I8_CASE(l, w) case (l) * 8 + (w): if constexpr ((l) <= S && (w) <= (l)) issue_sparse_lw<S, (l), (w)>(td, da, db); break;
+#define I8_ROW(l) I8_CASE(l, 1) I8_CASE(l, 2) I8_CASE(l, 3) I8_CASE(l, 4) I8_CASE(l, 5) I8_CASE(l, 6) I8_CASE(l, 7) I8_CASE(l, 8)
+  switch (L * 8 + W) {
+    I8_ROW(1) I8_ROW(2) I8_ROW(3) I8_ROW(4) I8_ROW(5) I8_ROW(6) I8_ROW(7) I8_ROW(8)
+    default: break;
+  }
+#undef I8_ROW
+#undef I8_CASE
+}
+
 // MODE 0: row sums of squares per 64-column tile (variance path, nothing else is written)
 // MODE 1: C = alpha A B^T + beta C (optionally stored transposed)
 template <int S, int MODE>
@@ -203,6 +233,8 @@ gemm_i8_kernel(const I8Gemm p) {
   __shared__ uint64_t full_bar[C::STAGES], empty_bar[C::STAGES], done_bar;
   __shared__ uint32_t tmem_slot;
   __shared__ double sb_s[I8_TN];
+  __shared__ uint32_t plan_s[I8_MAX_PLAN];   // the k chunks of this tile that need work, in order: plan word | chunk << 12
+  __shared__ int plan_n;
   // the warp index is broadcast from lane 0 so that the compiler can prove the role branches warp-uniform (the
   // role bodies then keep their addresses and descriptors in uniform registers)
   const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0), lane = tid & 31;
@@ -254,14 +286,31 @@ gemm_i8_kernel(const I8Gemm p) {
           ::"r"(taddr), "r"(0u) : "memory");
     }
     asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+  } else if (warp == 5) {
+    // plane-occupancy masks of the two operands' tiles (one byte per 32-byte k chunk, bit p = plane p holds a
+    // non-zero digit): chunks and planes that are all zero are neither loaded nor multiplied.  While warps 0-3 zero
+    // the accumulators, this warp decodes the whole k-range 32 chunks at a time and compacts the chunks that need
+    // work into plan_s: the role loops below are bound by their own instruction count (one warp alone issues one
+    // instruction per ~4.4 cycles, profiles/r01_i8_experiments.log), so everything that can be done here is.
+    const uint8_t* am = p.a_mask ? p.a_mask + (int64_t)mt * p.mask_ld : nullptr;
+    const uint8_t* bm = p.b_mask ? p.b_mask + (int64_t)nt * p.mask_ld : nullptr;
+    int cnt = 0;
+    if (KT > 0) {
+#pragma unroll 4
+      for (int kb = kbeg; kb < kend; kb += 32) {
+        const uint32_t w = plan_word<S>(am, bm, kb + lane, kend);
+        const uint32_t bits = __ballot_sync(0xffffffffu, w != 0u);
+        if (w != 0u) plan_s[cnt + __popc(bits & ((1u << lane) - 1u))] = 0x80000000u | (w & 0xfffu) | ((uint32_t)(kb + lane) << 12);
+        cnt += __popc(bits);
+      }
+    }
+    if (lane == 0) plan_n = cnt;
   }
   fence_before();
   __syncthreads();
   fence_after();
-  // plane-occupancy masks of the two operands' tiles (one byte per 32-byte k chunk, bit p = plane p holds a
-  // non-zero digit): chunks and planes that are all zero are neither loaded nor multiplied
-  const uint8_t* am = p.a_mask ? p.a_mask + (int64_t)mt * p.mask_ld : nullptr;
-  const uint8_t* bm = p.b_mask ? p.b_mask + (int64_t)nt * p.mask_ld : nullptr;
+  // warp-uniform by construction (broadcast from lane 0), so the role loops stay in uniform control flow
+  const int n_plan = __shfl_sync(0xffffffffu, plan_n, 0);
 
   if (warp < 4) {
     // ===================== epilogue =====================
@@ -342,100 +391,81 @@ gemm_i8_kernel(const I8Gemm p) {
     }
   } else if (warp == 5 && KT > 0) {
     // ===================== bulk-copy producer (warp 5) =====================
-    // The 32 lanes decode 32 k chunks' occupancy bytes at once; the warp then walks the chunks that need work in
-    // warp-uniform control flow.  Every per-chunk value is broadcast with redux.sync, which the compiler knows to be
-    // warp-uniform: slot addresses, byte counts and barrier addresses then live in uniform registers, and the copies
-    // are issued without the per-instruction R2UR "waterfall" loop that a shuffled (formally divergent) value costs.
+    // Warp-uniform control flow: the plan word comes from shared memory through a lane-0 broadcast (a result the
+    // compiler knows to be uniform), fetched one chunk ahead; the loop is unrolled over the ring's stages, so slot
+    // addresses and barrier addresses are constants and everything else lives in uniform registers.
     const int8_t* a_src = p.a_tiles + (int64_t)mt * p.kchunks * C::A_BYTES;
     const int8_t* b_src = p.b_tiles + (int64_t)nt * p.kchunks * C::B_BYTES;
-    int it = 0;
-    for (int kb = kbeg; kb < kend; kb += 32) {
-      const uint32_t w = plan_word<S>(am, bm, kb + lane, kend);
-      uint32_t bits = __ballot_sync(0xffffffffu, w != 0u);
-      while (bits) {
-        const int l = __ffs(bits) - 1;
-        bits &= bits - 1;
-        const uint32_t ws = __reduce_or_sync(0xffffffffu, lane == l ? w : 0u);
-        // A planes [pmin, S-1-qmin] and B planes [qmin, min(S-pmin, qmax+1)): both ranges are contiguous in the tiled
-        // digit layout, one bulk copy each
-        const int pmin = ws & 0xf, qmin = (ws >> 4) & 0xf, qmax = (ws >> 8) & 0xf;
-        const int kc = kb + l, s = it % C::STAGES, u = it / C::STAGES;
-        const int nA = S - qmin - pmin, nB = min(S - pmin, qmax + 1) - qmin;
-        if (u > 0) mbarrier_wait(&empty_bar[s], (u - 1) & 1);     // the MMAs that read this slot are done
-        if (elect_one()) {
-          const uint32_t st = ring + (uint32_t)s * C::STAGE_BYTES;
-          expect_tx(&full_bar[s], (uint32_t)(nA * C::A_PLANE + nB * C::B_PLANE));
-          bulk_load(st + pmin * C::A_PLANE, a_src + (int64_t)kc * C::A_BYTES + pmin * C::A_PLANE, (uint32_t)(nA * C::A_PLANE),
-                    &full_bar[s]);
-          bulk_load(st + C::A_BYTES + qmin * C::B_PLANE, b_src + (int64_t)kc * C::B_BYTES + qmin * C::B_PLANE,
-                    (uint32_t)(nB * C::B_PLANE), &full_bar[s]);
+    uint32_t ws_next = __shfl_sync(0xffffffffu, plan_s[0], 0);
+    uint32_t par = 1;                                              // parity of the empty phase of the previous round
+    for (int it0 = 0; it0 < n_plan; it0 += C::STAGES) {
+#pragma unroll
+      for (int s = 0; s < C::STAGES; ++s) {
+        const int it = it0 + s;
+        if (it < n_plan) {
+          const uint32_t ws = ws_next;
+          ws_next = __shfl_sync(0xffffffffu, plan_s[(it + 1) & (I8_MAX_PLAN - 1)], 0);
+          // A planes [pmin, S-1-qmin] and B planes [qmin, min(S-pmin, qmax+1)): both ranges are contiguous in the
+          // tiled digit layout, one bulk copy each
+          const int pmin = ws & 0xf, qmin = (ws >> 4) & 0xf, qmax = (ws >> 8) & 0xf;
+          const int kc = (int)((ws >> 12) & (I8_MAX_PLAN - 1));
+          const int nA = S - qmin - pmin, nB = min(S - pmin, qmax + 1) - qmin;
+          if (it0 > 0) mbarrier_wait(&empty_bar[s], par);          // the MMAs that read this slot are done
+          if (elect_one()) {
+            const uint32_t st = ring + (uint32_t)s * C::STAGE_BYTES;
+            expect_tx(&full_bar[s], (uint32_t)(nA * C::A_PLANE + nB * C::B_PLANE));
+            bulk_load(st + pmin * C::A_PLANE, a_src + (int64_t)kc * C::A_BYTES + pmin * C::A_PLANE,
+                      (uint32_t)(nA * C::A_PLANE), &full_bar[s]);
+            bulk_load(st + C::A_BYTES + qmin * C::B_PLANE, b_src + (int64_t)kc * C::B_BYTES + qmin * C::B_PLANE,
+                      (uint32_t)(nB * C::B_PLANE), &full_bar[s]);
+          }
         }
-        ++it;
       }
+      par ^= 1u;
     }
   } else if (warp == 4 && KT > 0) {
-    // ===================== MMA issuer (warp 4; lane 0 issues) =====================
+    // ===================== MMA issuer (warp 4; one elected lane issues) =====================
     // The B digit planes of a stage are contiguous in shared memory ([plane][64 rows][32 B]), i.e. ONE K-major
     // operand of (S - p) x 64 rows, and group g = p + q lives at TMEM columns g x 64: a single MMA of A_p against
     // planes q0..q0+c-1 (N = 64c <= 256) lands every product in its own group.  S(S+1)/2 plane products become
     // ~S(S+1)/8 + S/2 instructions and A_p is read from shared memory once per <= 4 products instead of once each.
-    // Control flow and operands are warp-uniform (ballot / redux.sync), see the producer: descriptors, TMEM addresses
-    // and instruction descriptors are computed in uniform registers, a handful of instructions per MMA.
-    int it = 0;
-    for (int kb = kbeg; kb < kend; kb += 32) {
-      const uint32_t w = plan_word<S>(am, bm, kb + lane, kend);
-      uint32_t bits = __ballot_sync(0xffffffffu, w != 0u);
-      while (bits) {
-        const int l = __ffs(bits) - 1;
-        bits &= bits - 1;
-        const uint32_t ws = __reduce_or_sync(0xffffffffu, lane == l ? w : 0u);
-        const int s = it % C::STAGES, u = it / C::STAGES;
-        mbarrier_wait(&full_bar[s], u & 1);
-        fence_after();
-        const uint32_t a0 = ring + (uint32_t)s * C::STAGE_BYTES, b0 = a0 + C::A_BYTES;
-        const uint32_t da0 = desc_kmajor_lo(a0), db0 = desc_kmajor_lo(b0);
-        if (elect_one()) {
-          if ((ws & 0xfffu) == (uint32_t)((S - 1) << 8)) {
-            // dense chunk (pmin = qmin = 0, qmax = S-1): the fixed schedule, every operand a compile-time offset
+    // Same uniform control flow as the producer; the MMAs of a sparse chunk come from a switch over its (L, W) shape
+    // with every offset and descriptor an immediate (issue_sparse).
+    uint32_t ws_next = __shfl_sync(0xffffffffu, plan_s[0], 0);
+    const uint32_t da_ring = desc_kmajor_lo(ring);
+    for (int it = 0; it < n_plan; ++it) {
+      const uint32_t ws = ws_next;
+      ws_next = __shfl_sync(0xffffffffu, plan_s[(it + 1) & (I8_MAX_PLAN - 1)], 0);
+      const int s = it % C::STAGES, u = it / C::STAGES;
+      const uint32_t da0 = da_ring + (uint32_t)s * (uint32_t)(C::STAGE_BYTES >> 4), db0 = da0 + (uint32_t)(C::A_BYTES >> 4);
+      const int pmin = ws & 0xf, qmin = (ws >> 4) & 0xf, qmax = (ws >> 8) & 0xf;
+      const int L = S - pmin - qmin;
+      int W = qmax + 1 - qmin;
+      W = W < L ? W : L;
+      mbarrier_wait(&full_bar[s], u & 1);
+      fence_after();
+      if (elect_one()) {
+        if ((ws & 0xfffu) == (uint32_t)((S - 1) << 8)) {
+          // dense chunk (pmin = qmin = 0, qmax = S-1): the fixed schedule, every operand a compile-time offset
 #pragma unroll
-            for (int pa = 0; pa < S; ++pa) {
+          for (int pa = 0; pa < S; ++pa) {
 #pragma unroll
-              for (int q0 = 0; q0 < S - pa; q0 += 4) {
-                const int cnt = (S - pa - q0) < 4 ? (S - pa - q0) : 4;
-                mma_i8_acc(tmem + (uint32_t)((pa + q0) * I8_TN), da0 + (uint32_t)((pa * C::A_PLANE) >> 4),
-                           db0 + (uint32_t)((q0 * C::B_PLANE) >> 4), idesc_i8(I8_TM, cnt * I8_TN));
-              }
-            }
-          } else {
-            // sparse chunk: the L = S - pmin - qmin A planes from pmin on; the i-th of them meets min(L - i, W) B planes
-            // from qmin on (W = qmax + 1 - qmin), issued as one MMA of up to four planes (N = 64 per plane) plus a
-            // second one when more than four remain.  Unrolled over i: every offset is a compile-time constant.
-            const int pmin = ws & 0xf, qmin = (ws >> 4) & 0xf, qmax = (ws >> 8) & 0xf;
-            const int L = S - pmin - qmin, W = qmax + 1 - qmin;
-            const uint32_t idesc0 = idesc_i8(I8_TM, 0);
-            const uint32_t db = db0 + (uint32_t)(qmin * (C::B_PLANE >> 4));
-            const uint32_t da = da0 + (uint32_t)(pmin * (C::A_PLANE >> 4));
-            const uint32_t td = tmem + (uint32_t)((pmin + qmin) * I8_TN);
-#pragma unroll
-            for (int i = 0; i < S; ++i) {
-              if (i < L) {
-                const int n = (L - i < W) ? L - i : W;
-                const int c0 = (n < 4) ? n : 4;
-                mma_i8_acc(td + (uint32_t)(i * I8_TN), da + (uint32_t)(i * (C::A_PLANE >> 4)), db,
-                           idesc0 | ((uint32_t)(c0 * (I8_TN >> 3)) << 17));
-                if (n > 4)
-                  mma_i8_acc(td + (uint32_t)((i + 4) * I8_TN), da + (uint32_t)(i * (C::A_PLANE >> 4)),
-                             db + (uint32_t)((4 * C::B_PLANE) >> 4), idesc0 | ((uint32_t)((n - 4) * (I8_TN >> 3)) << 17));
-              }
+            for (int q0 = 0; q0 < S - pa; q0 += 4) {
+              const int cnt = (S - pa - q0) < 4 ? (S - pa - q0) : 4;
+              mma_i8_acc(tmem + (uint32_t)((pa + q0) * I8_TN), da0 + (uint32_t)((pa * C::A_PLANE) >> 4),
+                         db0 + (uint32_t)((q0 * C::B_PLANE) >> 4), idesc_i8(I8_TM, cnt * I8_TN));
             }
           }
-          commit_to(&empty_bar[s]);                               // arrives when these MMAs have read the stage
+        } else {
+          // sparse chunk: the L = S - pmin - qmin A planes from pmin on against the W reachable B planes from qmin on
+          issue_sparse<S>(L, W, tmem + (uint32_t)((pmin + qmin) * I8_TN), da0 + (uint32_t)(pmin * (C::A_PLANE >> 4)),
+                          db0 + (uint32_t)(qmin * (C::B_PLANE >> 4)));
         }
-        ++it;
+        commit_to(&empty_bar[s]);                               // arrives when these MMAs have read the stage
       }
     }
     if (elect_one()) {
-      if (it > 0) commit_to(&done_bar);                          // accumulators complete
+      if (n_plan > 0) commit_to(&done_bar);                      // accumulators complete
       else mbarrier_arrive(&done_bar);                           // every chunk was skipped: the zeros stand
     }
   }
