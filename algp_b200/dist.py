@@ -97,7 +97,7 @@ def sharded_mean_var(hyper, train_x, train_var, y0, ymean, xs, test_var=None, pr
     rank = dist.get_rank(group) if dist.is_initialized() else 0
     dev = xs.device
     N, M = train_x.shape[0], xs.shape[0]
-    reorder = precision == "i8" and N >= engine.I8_REORDER_MIN
+    reorder = precision in engine.I8_FAMILY and N >= engine.I8_REORDER_MIN
     tperm = None
     if reorder:
         perm, lo, hi = engine.morton_perm(train_x)
@@ -110,7 +110,8 @@ def sharded_mean_var(hyper, train_x, train_var, y0, ymean, xs, test_var=None, pr
     Npad = max(engine.BLK, engine.pad_to(N))
     if rank == src:
         f = engine.GPFactor(hyper, train_x, diag_add=train_var, diag_scalar=hyper.noise,
-                            factor="auto" if precision == "i8" else "dmma")
+                            factor="auto" if precision in engine.I8_FAMILY else "dmma",
+                            factor_slices=engine.I8_FAST_FACTOR_SLICES if precision == "i8fast" else None)
         alpha, _ = f.solve(y0)
         head = torch.cat([alpha, f.info.to(torch.float64)])
     else:
@@ -132,8 +133,8 @@ def sharded_mean_var(hyper, train_x, train_var, y0, ymean, xs, test_var=None, pr
     if hi_r > lo_r:
         Ks, part = f.cross(xs[lo_r:hi_r], alpha)
         mu_loc[:hi_r - lo_r] = engine.rowsum(part, 1.0, ymean, rows=hi_r - lo_r)
-        if precision == "i8" and f.Npad <= engine.I8_MAX_K:
-            rn = f.whiten_norm_i8(Ks)
+        if precision in engine.I8_FAMILY and f.Npad <= engine.I8_MAX_K:
+            rn = f.whiten_norm_i8(Ks, nslices=engine.I8_FAST_SLICES if precision == "i8fast" else engine.I8_SLICES)
         elif precision == "tf32":
             rn = f.whiten_norm_tf32(Ks)
         else:

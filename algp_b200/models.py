@@ -112,8 +112,8 @@ class GPR(object):
         self.learn_likelihood_noise = learn_likelihood_noise     # accepted and ignored, as in models.py:101,119-120
         self.dtype = np.float64      # np.float32 reproduces the reference's float32 kernel matrix (utils.py:19)
         # O(N^3) / O(N^2 M) arithmetic: "fp64" = DMMA; "i8" = exact INT8 digit GEMMs on tcgen05 for the variance and,
-        # from N = 8192, the factorisation (same fp64 tier, ~3x faster at N = 16384); "tf32" = split-TF32 variance
-        # on tcgen05 (1e-4 tier)
+        # from N = 8192, the factorisation (same fp64 tier, ~7x faster at N = 16384); "i8fast" = the same digit path with
+        # 5 / 4 planes (1e-4 tier, faster and more accurate than "tf32"); "tf32" = split-TF32 variance on tcgen05 (1e-4 tier)
         self.precision = "fp64"
         self._cache = {}
 

@@ -95,7 +95,7 @@ def _factor_for(gp, hyper, train_x, train_var, reorder=False):
     cache = getattr(gp, "_cache", None)
     prec = getattr(gp, "precision", "fp64")
     # precision "i8": factor through the recursive INT8 digit factorisation when N is large enough to pay
-    key = ("factor", _digest(train_x, train_var), hyper.key(), prec == "i8", bool(reorder))
+    key = ("factor", _digest(train_x, train_var), hyper.key(), prec if prec in engine.I8_FAMILY else "dmma", bool(reorder))
     if cache is not None and cache.get("factor_key") == key:
         return cache["factor"]
     dev = engine.require_cuda()
@@ -107,7 +107,8 @@ def _factor_for(gp, hyper, train_x, train_var, reorder=False):
         box = (lo, hi)
         x = x.index_select(0, perm).contiguous()
         wn = None if wn is None else wn.index_select(0, perm).contiguous()
-    f = engine.GPFactor(hyper, x, diag_add=wn, diag_scalar=hyper.noise, factor="auto" if prec == "i8" else "dmma")
+    f = engine.GPFactor(hyper, x, diag_add=wn, diag_scalar=hyper.noise, factor="auto" if prec in engine.I8_FAMILY else "dmma",
+                        factor_slices=engine.I8_FAST_FACTOR_SLICES if prec == "i8fast" else None)
     f.perm, f.box = perm, box
     if cache is not None:
         cache.clear()
@@ -131,7 +132,7 @@ def _posterior(gp, hyper, train_x, train_y, test_x, train_var, test_var, want_va
     prec = getattr(gp, "precision", "fp64")
     # the mean / variance path does not depend on the order of the points: in INT8 digit mode both sets are sorted
     # along a Z curve so that far-apart (test tile, train chunk) pairs become all-zero digit tiles the GEMM skips
-    reorder = (not want_cov) and prec == "i8" and len(train_y) >= engine.I8_REORDER_MIN
+    reorder = (not want_cov) and prec in engine.I8_FAMILY and len(train_y) >= engine.I8_REORDER_MIN
     f = _factor_for(gp, hyper, train_x, train_var, reorder=reorder)
     dev = f.L.device
     xs = engine.to_dev(test_x, device=dev)

@@ -342,7 +342,8 @@ def fit_predict_bench(torch, engine, n_train, grid_side, reps, peak_hbm):
         gp.model.kernel_covar_module.base_kernel.log_lengthscale.copy_(torch.tensor(hy.log_ls).view(1, 1, -1))
         gp.model.kernel_covar_module.log_outputscale.fill_(hy.log_os)
         gp.likelihood.log_noise.fill_(hy.log_noise)
-    for mode in ("fp64", "i8", "tf32"):
+    ref64 = None
+    for mode in ("fp64", "i8", "i8fast", "tf32"):
         gp.precision = mode
         ts = []
         for rep in range(reps + 1):
@@ -352,6 +353,12 @@ def fit_predict_bench(torch, engine, n_train, grid_side, reps, peak_hbm):
             mu_h, var_out = algp_b200.predictive_distribution(gp, x, y, xs, var_h, return_var=True)
             ts.append((time.perf_counter() - t0) * 1e3)
         e2e[mode] = float(np.median(ts[1:]))
+        if mode == "fp64":
+            ref64 = (mu_h.copy(), var_out.copy())
+        else:
+            # accuracy of each mode through the same public call, against the fp64 (DMMA) mode
+            e2e[mode + "_max_abs_var_diff_vs_fp64"] = float(np.abs(var_out - ref64[1]).max())
+            e2e[mode + "_max_abs_mean_diff_over_max_abs_mean"] = float(np.abs(mu_h - ref64[0]).max() / np.abs(ref64[0]).max())
     e2e["h2d_bytes"] = int(x.nbytes + y.nbytes + var_h.nbytes + xs.nbytes)
     e2e["d2h_bytes"] = int(mu_h.nbytes + var_out.nbytes)
     med = {k: (float(np.median(v)) if len(v) else None) for k, v in times.items()}

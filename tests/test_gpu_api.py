@@ -404,6 +404,31 @@ def test_prediction_vs_distance_matches_literal_loop():
     np.testing.assert_allclose(got['mean'], mu, rtol=1e-9, atol=1e-9)
 
 
+def test_i8fast_precision_meets_the_1e4_tier(monkeypatch):
+    """gp.precision = "i8fast": the digit path with 5 planes in the factorisation and 4 in the variance product -- the
+    fp32 / TF32 tier of the north star (rel 1e-4 on mean and variance), against the fp64 oracle; the digit factorisation
+    and the Z-order staging are forced on at this size."""
+    rng = np.random.default_rng(32)
+    monkeypatch.setattr(engine, "I8_REORDER_MIN", 2048)
+    monkeypatch.setattr(engine, "I8_FACTOR_MIN", 2048)
+    N, M = 2304, 1500
+    x = rng.uniform(0, 120, (N, 2))
+    xs = rng.uniform(-5, 125, (M, 2))
+    y = np.sin(x[:, 0] / 7.0) + np.cos(x[:, 1] / 5.0) + rng.normal(0, 0.1, N)
+    var = rng.uniform(0.01, 0.02, N)
+    th, hy = hyper_pair([6.0, 5.0], 1.0, 0.01, "rbf")
+    gp = make_gpr("rbf", th.log_lengthscale, th.log_outputscale, th.log_noise, x, y, var)
+    gp.precision = "i8fast"
+    mu, v = algp_b200.predictive_distribution(gp, x, y, xs, var, return_var=True)
+    assert gp._cache["factor"].perm is not None
+    mu_o, v_o = O.predictive_distribution_chol(O.OracleGP(th, "fp64"), x, y, xs, var, return_var=True)
+    np.testing.assert_allclose(mu, mu_o, rtol=1e-4, atol=1e-4 * np.abs(mu_o).max())
+    np.testing.assert_allclose(v, v_o, rtol=1e-4, atol=1e-4)          # s^2 = 1: absolute 1e-4 of the prior variance
+    with pytest.raises(ValueError):
+        gp.precision = "i4"
+        algp_b200.predictive_distribution(gp, x, y, xs, var, return_var=True)
+
+
 def test_i8_precision_reorders_points_and_matches_fp64(monkeypatch):
     """gp.precision = "i8" from N = engine.I8_REORDER_MIN (lowered here): training and test points are sorted along a
     Z curve internally (so that the
