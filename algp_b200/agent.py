@@ -147,12 +147,16 @@ class HotPath(object):
         sample lists changed (every mutation in the reference goes through _add_samples / reset /
         a deepcopy, all of which change this stamp)."""
         col = getattr(self, "collected", None)
-        stamp = (id(self.static_data), id(self.mobile_data), -1 if col is None else len(col['ind']))
         cached = getattr(self, "_hot_flags", None)
-        if cached is None or col is None or cached[0] != stamp:
-            cached = (stamp, _flags(self.static_data), _flags(self.mobile_data))
+        # the cache holds the list objects themselves (compared with `is`), so a recycled id() after reset() /
+        # deepcopy can never pass for the old lists
+        fresh = (cached is not None and col is not None and cached[0] is self.static_data
+                 and cached[1] is self.mobile_data and cached[2] is col['ind'] and cached[3] == len(col['ind']))
+        if not fresh:
+            cached = (self.static_data, self.mobile_data, None if col is None else col['ind'],
+                      -1 if col is None else len(col['ind']), _flags(self.static_data), _flags(self.mobile_data))
             self._hot_flags = cached
-        return cached[1].copy(), cached[2].copy()
+        return cached[4].copy(), cached[5].copy()
 
     def _state_for(self, static_sampled, mobile_sampled, capacity):
         """Posterior state whose base set carries exactly these flags.  The cached one is reused when it already
@@ -275,11 +279,12 @@ class HotPath(object):
 
 def patch(agent_cls):
     """Install the accelerated hot path on the reference's Agent class (agent.py:12)."""
-    for name in ("update_model", "get_sampled_dataset", "_post_update", "predict", "greedy", "best_path",
-                 "prediction_vs_distance",
-                 "_device_X", "_state_for", "_use_mi", "_greedy_mi", "_sample_flags"):
-        setattr(agent_cls, name, HotPath.__dict__[name])
-    agent_cls.cov_matrix = HotPath.__dict__["cov_matrix"]
+    # everything HotPath defines -- the reference-facing methods, the cov_matrix property and every private helper they
+    # call -- so that a helper added later can never be left behind
+    for name, member in HotPath.__dict__.items():
+        if name.startswith("__"):
+            continue
+        setattr(agent_cls, name, member)
     return agent_cls
 
 
