@@ -54,6 +54,10 @@ SIGNATURES = {
     "algp_score_sets_large": (C.c_int, [_p, _i64, _i64, _p, _i32, _p, _f64, _i32, _f64, _p, _p, _p, _f64, _p,
                                         _i32, _i64, _f64, _p, _p, _i64, _p]),
     "algp_score_sets_large_work_doubles": (_i64, [_i32, _i64]),
+    "algp_score_sets_tiled": (C.c_int, [_p, _i64, _i64, _i64, _p, _i32, _p, _f64, _i32, _f64, _p, _p, _p, _f64, _p,
+                                        _i32, _i64, _f64, _p, _p, _i64, _p]),
+    "algp_score_sets_tiled_work_doubles": (_i64, [_i64]),
+    "algp_set_score_tile_cols": (C.c_int, [_i32]),
     "algp_score_sets_cov": (C.c_int, [_p, _i64, _p, _p, _p, _f64, _p, _i32, _i64, _f64, _p, _p]),
     "algp_mi_terms_large": (C.c_int, [_p, _i64, _p, _p, _i64, _p, _i32, _i64, _p, _f64, _f64, _p, _p, _i64, _p]),
     "algp_mi_terms_large_work_doubles": (_i64, [_i32, _i64]),
@@ -85,7 +89,7 @@ class AlgpError(RuntimeError):
 def _load():
     if not os.path.exists(LIB_PATH):
         raise RuntimeError(
-            "algp_b200: %s is missing. Build it with `python -m algp_b200.build` (nvcc, sm_100a). "
+            "algp_b200: %s is missing. Build it with `python algp_b200/build.py` (nvcc, sm_100a). "
             "There is no CPU fallback." % LIB_PATH)
     lib = C.CDLL(LIB_PATH)
     for name, (res, args) in SIGNATURES.items():

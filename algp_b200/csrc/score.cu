@@ -17,6 +17,7 @@
 //   argmax             (max value, then min index) == np.argmax first-max (agent.py:349,402)
 //   append             posterior rank-1 downdate after an acquisition, as one new column of Wt
 #include "common.cuh"
+#include "argmax.cuh"
 #include <math.h>
 #include <stdlib.h>
 
@@ -382,37 +383,6 @@ __global__ void greedy_utilities_kernel(const double* __restrict__ diagP, const 
   ut[i] = u;
 }
 
-struct ArgPair { double v; long long i; };
-
-__device__ __forceinline__ bool arg_better(double v, long long i, double bv, long long bi) {
-  return (v > bv) || (v == bv && i < bi);
-}
-
-__global__ void argmax_stage1_kernel(const double* __restrict__ x, int64_t n, int64_t idx_offset, ArgPair* __restrict__ part) {
-  __shared__ double sv[32];
-  __shared__ long long si[32];
-  double bv = -INFINITY;
-  long long bi = 0x7fffffffffffffffLL;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-    double v = x[i];
-    if (arg_better(v, i + idx_offset, bv, bi)) { bv = v; bi = i + idx_offset; }
-  }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    double ov = __shfl_xor_sync(0xffffffffu, bv, o);
-    long long oi = __shfl_xor_sync(0xffffffffu, bi, o);
-    if (arg_better(ov, oi, bv, bi)) { bv = ov; bi = oi; }
-  }
-  if ((threadIdx.x & 31) == 0) { sv[threadIdx.x >> 5] = bv; si[threadIdx.x >> 5] = bi; }
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    for (int w = 1; w < (int)(blockDim.x >> 5); ++w)
-      if (arg_better(sv[w], si[w], bv, bi)) { bv = sv[w]; bi = si[w]; }
-    part[blockIdx.x].v = bv;
-    part[blockIdx.x].i = bi;
-  }
-}
-
 __global__ void argmax_stage2_kernel(const ArgPair* __restrict__ part, int np, ArgPair* __restrict__ out) {
   double bv = -INFINITY;
   long long bi = 0x7fffffffffffffffLL;
@@ -427,7 +397,6 @@ __global__ void argmax_stage2_kernel(const ArgPair* __restrict__ part, int np, A
   if (threadIdx.x == 0) { out->v = bv; out->i = bi; }
 }
 
-#define ARGMAX_BLOCKS 148
 extern "C" int64_t algp_argmax_work_bytes(void) { return (int64_t)ARGMAX_BLOCKS * sizeof(ArgPair); }
 
 // out_pair: {double value; int64 index} on the device; index = position + idx_offset (global id of a shard)

@@ -456,11 +456,20 @@ class PosteriorState(object):
         self.build_cov()
         return True
 
+    # k <= 8: "stream" = score_sets_k8_kernel (rows of Wt end to end; default), "tiled" = csrc/scoretile.cu (columns in
+    # L2-sized chunks: 19x less DRAM traffic, the same time -- both sit on the L2 -> SM throughput cap)
+    score_mode = "stream"
+
+    def _want_tiled(self, B, k):
+        return self.score_mode == "tiled"
+
     def score_sets(self, idx, delta=None, delta_scalar=0.0, H_base=None, out=None, skip=None):
         """scores[c] = H(S1_c) for candidate sets idx [B,k] (int32 device tensor, -1 = empty)."""
         B, k = idx.shape
         if out is None:
             out = torch.empty(B, dtype=torch.float64, device=idx.device)
+        if B == 0:
+            return out
         ls, ls_p = _lib.host_f64(self.hyper.log_ls)
         hb = self.H_base if H_base is None else H_base
         if self._want_cov(B, k):
@@ -468,6 +477,15 @@ class PosteriorState(object):
                  float(delta_scalar), ptr(skip), k, B, float(hb), ptr(out), stream())
             return out
         self._stream_s += 8.0 * B * k * max(self.ncols, 1) / self.STREAM_BYTES_PER_S
+        if k <= 8 and self._want_tiled(B, k):
+            # large batches of small sets: columns of Wt in L2-sized chunks, 36-entry DFMA Gram (csrc/scoretile.cu)
+            nwork = _lib.lib.algp_score_sets_tiled_work_doubles(B)
+            if getattr(self, "_tilework", None) is None or self._tilework.numel() < nwork:
+                self._tilework = torch.empty(nwork, dtype=torch.float64, device=idx.device)
+            call("algp_score_sets_tiled", ptr(self.Wt), self.ldw, self.ncols, self.n_pad, ptr(self.X), self.hyper.d, ls_p,
+                 self.hyper.log_os, self.hyper.kind, self.hyper.noise, ptr(self.pi), ptr(idx), ptr(delta),
+                 float(delta_scalar), ptr(skip), k, B, float(hb), ptr(out), ptr(self._tilework), nwork, stream())
+            return out
         if k > MAX_SET_SMEM:
             # long paths: the k x k matrix of a candidate lives in a global scratch instead of shared memory
             nwork = _lib.lib.algp_score_sets_large_work_doubles(k, B)

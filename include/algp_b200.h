@@ -166,6 +166,18 @@ int algp_score_sets_large(const double* Wt, int64_t ldw, int64_t ncols, const do
                           const int32_t* idx, const double* delta, double delta_scalar, const uint8_t* skip, int k,
                           int64_t B, double H_base, double* scores, double* work, int64_t work_doubles, void* stream);
 int64_t algp_score_sets_large_work_doubles(int k, int64_t B);
+/* The same scores for k <= 8 with the columns of Wt processed in L2-sized chunks (one launch per chunk, partial
+ * Gram matrices G[B][36] in `work`): large batches of random sets re-read every row of Wt many times, and a chunk's
+ * slice of Wt (n_rows x chunk x 8 bytes, n_rows = rows the candidates can reference) stays L2-resident where whole
+ * rows do not.  A slot table (one pass over idx / delta / skip) is built first, a thread per candidate finishes
+ * (Sigma_CC, elimination, bookkeeping).  work: algp_score_sets_tiled_work_doubles(B) doubles, 16-byte aligned.  algp_set_score_tile_cols(c) forces the chunk (multiple of
+ * 64; 0 = derive from the L2 size). */
+int algp_score_sets_tiled(const double* Wt, int64_t ldw, int64_t ncols, int64_t n_rows, const double* X, int d,
+                          const double* log_ls_host, double log_os, int kind, double noise, const double* pi0,
+                          const int32_t* idx, const double* delta, double delta_scalar, const uint8_t* skip, int k,
+                          int64_t B, double H_base, double* scores, double* work, int64_t work_doubles, void* stream);
+int64_t algp_score_sets_tiled_work_doubles(int64_t B);
+int algp_set_score_tile_cols(int cols);
 /* The same scores from a RESIDENT posterior covariance of the base set, P = Sigma + sigma_n^2 I - Wt Wt^T
  * (lower triangle of an [n x ldp] matrix; build it with algp_kbuild + algp_gemm_nt / algp_gemm_nt_i8, lower_only):
  * a candidate reads its k(k+1)/2 entries P[c_i][c_j] instead of k rows of Wt.  The Schur complement of

@@ -200,6 +200,70 @@ def test_score_sets_matches_oracle(kind, k):
 
 
 @pytest.mark.parametrize("kind", ["rbf", "matern"])
+@pytest.mark.parametrize("k,tile", [(1, 64), (5, 64), (8, 64), (8, 128), (8, 0), (3, 192)])
+def test_score_sets_tiled_matches_oracle_and_streaming(kind, k, tile):
+    """csrc/scoretile.cu (columns of Wt in L2-sized chunks, 36-entry DFMA Gram, thread-per-candidate finish) against the
+    oracle and the row-streaming kernel: several chunks per candidate, a column count that is not a multiple of the
+    64-column step (appended columns), empty / duplicate / zero-increment slots and skip flags."""
+    from algp_b200 import _lib
+    X, th, hy, static, mobile, pi0, cov, ss, ms, rng = scoring_problem(kind, n_side=24, n_base=300, d_extra=(2 if k == 5 else 0))
+    n = len(X)
+    Bc = 500
+    idx = np.full((Bc, k), -1, dtype=np.int32)
+    delta = np.zeros((Bc, k))
+    for c in range(Bc):
+        m = int(rng.integers(1, k + 1))
+        idx[c, :m] = rng.choice(n, m, replace=False)
+        delta[c, :m] = np.where(rng.random(m) < 0.3, 1 / ss ** 2, 1 / ms ** 2)
+        if m >= 3 and c % 4 == 0:
+            idx[c, m - 1] = idx[c, 0]
+        if m >= 2 and c % 5 == 0:
+            delta[c, 1] = 0.0
+    base = np.nonzero(pi0 > 0)[0]
+    state = engine.PosteriorState(hy, dev(X), base, pi0, capacity=8, cov_mode="never")
+    picks = state.greedy(3, 1 / ss ** 2)                 # three appended columns: ncols = Npad + 3
+    pi1 = pi0.copy()
+    pi1[picks] += 1 / ss ** 2
+    ost = O.posterior_state(cov, pi1)
+    skip = np.zeros(n, dtype=np.uint8)
+    skip[rng.choice(n, n // 10, replace=False)] = 1
+    assert _lib.lib.algp_set_score_tile_cols(tile) == 0
+    try:
+        for sk in (None, skip):
+            skd = None if sk is None else dev(sk, torch.uint8)
+            state.score_mode = "tiled"
+            got = state.score_sets(dev(idx, torch.int32), dev(delta), skip=skd).cpu().numpy()
+            state.score_mode = "stream"
+            ref = state.score_sets(dev(idx, torch.int32), dev(delta), skip=skd).cpu().numpy()
+            np.testing.assert_allclose(got, ref, rtol=1e-11, atol=1e-10)
+            idx_o = idx if sk is None else np.where((idx >= 0) & (skip[np.maximum(idx, 0)] == 1), -1, idx)
+            want = O.score_sets_restructured(ost["P"], pi1, idx_o, delta, ost["H"])
+            np.testing.assert_allclose(got, want, rtol=1e-8, atol=1e-9)
+            assert int(np.argmax(got)) == int(np.argmax(want))
+        # scalar delta, one candidate, and B = 0
+        state.score_mode = "tiled"
+        one = state.score_sets(dev(idx[7:8], torch.int32), None, delta_scalar=1 / ms ** 2).cpu().numpy()
+        want1 = O.score_sets_restructured(ost["P"], pi1, idx[7:8], np.full((1, k), 1 / ms ** 2), ost["H"])
+        np.testing.assert_allclose(one, want1, rtol=1e-8, atol=1e-9)
+        assert state.score_sets(dev(idx[:0], torch.int32), dev(delta[:0])).numel() == 0
+    finally:
+        _lib.lib.algp_set_score_tile_cols(0)
+    assert _lib.lib.algp_set_score_tile_cols(100) == 1       # not a multiple of 64: rejected
+
+
+def test_score_sets_tiled_empty_base():
+    X, th, hy, static, mobile, pi0, cov, ss, ms, rng = scoring_problem("rbf")
+    n = len(X)
+    state = engine.PosteriorState(hy, dev(X), np.zeros(0, dtype=np.int64), np.zeros(n), capacity=4, cov_mode="never")
+    idx = np.stack([rng.choice(n, 6, replace=False) for _ in range(50)]).astype(np.int32)
+    delta = np.full(idx.shape, 1 / ms ** 2)
+    state.score_mode = "tiled"
+    got = state.score_sets(dev(idx, torch.int32), dev(delta)).cpu().numpy()
+    ost = O.posterior_state(cov, np.zeros(n))
+    np.testing.assert_allclose(got, O.score_sets_restructured(ost["P"], np.zeros(n), idx, delta, ost["H"]), rtol=1e-8, atol=1e-9)
+
+
+@pytest.mark.parametrize("kind", ["rbf", "matern"])
 @pytest.mark.parametrize("k", [1, 5, 8, 11, 40, 128])
 def test_score_sets_resident_cov_matches_oracle(kind, k):
     """cov_mode="always": the posterior covariance P of the base set is built once (kernel matrix + SYRK) and every
