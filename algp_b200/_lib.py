@@ -61,6 +61,7 @@ SIGNATURES = {
     "algp_score_sets_cov": (C.c_int, [_p, _i64, _p, _p, _p, _f64, _p, _i32, _i64, _f64, _p, _p]),
     "algp_mi_terms_large": (C.c_int, [_p, _i64, _p, _p, _i64, _p, _i32, _i64, _p, _f64, _f64, _p, _p, _i64, _p]),
     "algp_mi_terms_large_work_doubles": (_i64, [_i32, _i64]),
+    "algp_probe_l2_read": (C.c_int, [_p, _i64, _i32, _i32, _p, _p]),
     "algp_paths_enumerate": (C.c_int, [_i32, _p, _p, _p, _p, _p, _i32, _i32, _i32, _p, _i32, _f64, _f64, _i64, _p]),
     "algp_paths_sizes": (C.c_int, [_p, _p, _p]),
     "algp_paths_fetch": (C.c_int, [_p, _p, _p, _p, _p, _p]),
@@ -69,6 +70,12 @@ SIGNATURES = {
     "algp_greedy_utilities": (C.c_int, [_p, _p, _p, _f64, _i64, _p, _p]),
     "algp_argmax": (C.c_int, [_p, _i64, _i64, _p, _p, _p]),
     "algp_argmax_work_bytes": (_i64, []),
+    "algp_p2p_mailbox_bytes": (_i64, [_i32]),
+    "algp_p2p_create": (C.c_int, [_i64, C.POINTER(C.c_void_p), _p]),
+    "algp_p2p_open": (C.c_int, [_p, C.POINTER(C.c_void_p)]),
+    "algp_p2p_close": (C.c_int, [_p]),
+    "algp_p2p_destroy": (C.c_int, [_p]),
+    "algp_argmax_exchange": (C.c_int, [_p, _i64, _i64, _p, _p, _i32, _i32, _i64, _f64, _p, _p]),
     "algp_append": (C.c_int, [_p, _i64, _i64, _p, _i64, _i32, _p, _f64, _i32, _f64, _p, _p, _p, _p, _f64,
                               _i32, _p, _p]),
     "algp_append_work_doubles": (_i64, [_i64]),
@@ -110,8 +117,16 @@ def check(name, code):
         raise AlgpError(name, code, msg)
 
 
+# kernels launched per call of the multi-kernel entry points (everything else launches one; host-only entry points
+# never go through call()); bench.py reads launch_count around its timed region for the "gpu_launches" it reports
+KERNELS_PER_CALL = {"algp_argmax": 2, "algp_argmax_exchange": 2, "algp_append": 3, "algp_append_block": 3}
+launch_count = 0
+
+
 def call(name, *args):
     """Invoke a status-returning entry point and raise on failure."""
+    global launch_count
+    launch_count += KERNELS_PER_CALL.get(name, 1)
     check(name, getattr(lib, name)(*args))
 
 

@@ -264,6 +264,14 @@ class HotPath(object):
         if getattr(state, "_skip_src", None) is None or not np.array_equal(state._skip_src, org_mobile):
             state._skip_src = org_mobile.copy()
             state._skip = engine.to_dev(org_mobile.astype(np.uint8), dtype=torch.uint8)
+        if getattr(self, "shard_candidates", False) and not self._use_mi() and torch.distributed.is_available() \
+                and torch.distributed.is_initialized() and torch.distributed.get_world_size() > 1:
+            # one process per GPU, replicated agent: every rank scores a contiguous block of the paths and the
+            # per-rank winners are exchanged over NVLink (algp_b200.dist); all ranks return the same index
+            from . import dist as adist
+            score, best = adist.sharded_best(state, idx, None, delta_scalar=dm, skip=state._skip)
+            self._last_path_scores = None
+            return int(best)
         idx_d = engine.to_dev(idx, dtype=torch.int32)
         scores = state.score_sets(idx_d, None, delta_scalar=dm, skip=state._skip)
         if self._use_mi():

@@ -8,7 +8,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "libalgp_b200.so")
-SOURCES = ["abi.cu", "kbuild.cu", "chol.cu", "score.cu", "scoretile.cu", "mll.cu", "tf32.cu", "i8.cu", "i8chol.cu", "mi.cu", "paths.cu", "scorecov.cu"]
+SOURCES = ["abi.cu", "kbuild.cu", "chol.cu", "score.cu", "mll.cu", "tf32.cu", "i8.cu", "i8chol.cu", "mi.cu", "paths.cu", "scorecov.cu", "p2p.cu", "probe.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC"]
 

@@ -40,6 +40,10 @@ struct ScoreArgs {
   double H_base;
   double* scores;          // [B]
   double* work;            // k > 128: [grid][kk][kk+1] elimination scratch in global memory
+  // k <= 8, columns in L2-sized chunks (one launch per chunk, algp_score_sets_tiled): this launch covers columns
+  // [col0, col1); the accumulator fragments travel between launches through gpart [B][32 lanes][2]
+  int col0, col1, first, last;
+  double* gpart;
 };
 
 __device__ __forceinline__ void ld256(const double* p, double& a, double& b, double& c, double& d) {
@@ -95,27 +99,37 @@ __global__ void __launch_bounds__(THREADS) score_sets_k8_kernel(const ScoreArgs 
     double c0[4], c1[4];
 #pragma unroll
     for (int q = 0; q < 4; ++q) c0[q] = c1[q] = 0.0;
+    const int cend = a.col1 < a.ncols16 ? a.col1 : a.ncols16;
+    if (!a.first) {                                        // continue the Gram of the earlier column chunks
+      const double2 p = *reinterpret_cast<const double2*>(a.gpart + cand * 64 + 2 * lane);
+      c0[0] = p.x;
+      c1[0] = p.y;
+    }
     // empty / duplicate slots issue no loads; the MMA itself is warp-wide
     if (PREFETCH) {
       double cur[4 * UNROLL], nxt[4 * UNROLL];
-      sc_load<UNROLL>(cur, row, active, 0, a.ncols16);
-      for (int k0 = 0; k0 < a.ncols16; k0 += STEP) {
-        sc_load<UNROLL>(nxt, row, active, k0 + STEP, a.ncols16);
+      sc_load<UNROLL>(cur, row, active, a.col0, cend);
+      for (int k0 = a.col0; k0 < cend; k0 += STEP) {
+        sc_load<UNROLL>(nxt, row, active, k0 + STEP, cend);
 #pragma unroll
         for (int q = 0; q < 4 * UNROLL; ++q) dmma884(c0[q & 3], c1[q & 3], cur[q], cur[q]);
 #pragma unroll
         for (int q = 0; q < 4 * UNROLL; ++q) cur[q] = nxt[q];
       }
     } else {
-      for (int k0 = 0; k0 < a.ncols16; k0 += STEP) {
+      for (int k0 = a.col0; k0 < cend; k0 += STEP) {
         double v[4 * UNROLL];
-        sc_load<UNROLL>(v, row, active, k0, a.ncols16);
+        sc_load<UNROLL>(v, row, active, k0, cend);
 #pragma unroll
         for (int q = 0; q < 4 * UNROLL; ++q) dmma884(c0[q & 3], c1[q & 3], v[q], v[q]);
       }
     }
     const double G0 = (c0[0] + c0[1]) + (c0[2] + c0[3]);   // G[g][2t]
     const double G1 = (c1[0] + c1[1]) + (c1[2] + c1[3]);   // G[g][2t+1]
+    if (!a.last) {                                         // more column chunks to come: park the fragment
+      *reinterpret_cast<double2*>(a.gpart + cand * 64 + 2 * lane) = make_double2(G0, G1);
+      continue;
+    }
 
     // Sigma_CC from coordinates: lane needs x of slot g (row) and slots 2t, 2t+1 (cols)
     double r2a = 0.0, r2b = 0.0;
@@ -319,6 +333,7 @@ extern "C" int algp_score_sets_large(const double* Wt, int64_t ldw, int64_t ncol
   if (!Wt || !X || !pi0 || !idx || !scores || k < 1 || k > SG_MAXK_LARGE || B < 0 || ncols < 0) return ALGP_ERR_INVALID;
   if ((ldw & 3) || ((uintptr_t)Wt & 31)) return ALGP_ERR_INVALID;       // 256-bit row loads
   if (k > SG_MAXK && B > 0 && (!work || work_doubles < algp_score_sets_large_work_doubles(k, B))) return ALGP_ERR_INVALID;
+  if (work_doubles < 0 && (k > 8 || (-work_doubles) % 32 != 0)) return ALGP_ERR_INVALID;   // chunked k <= 8 (algp_score_sets_tiled)
   ScoreArgs a;
   a.work = work;
   int rc = make_kernel_params(&a.kp, d, log_ls_host, log_os, kind);
@@ -328,16 +343,32 @@ extern "C" int algp_score_sets_large(const double* Wt, int64_t ldw, int64_t ncol
   if (a.ncols16 > ldw) return ALGP_ERR_INVALID;
   a.X = X; a.pi0 = pi0; a.idx = idx; a.delta = delta; a.delta_scalar = delta_scalar; a.skip = skip;
   a.k = k; a.B = B; a.H_base = H_base; a.scores = scores;
+  a.col0 = 0; a.col1 = a.ncols16; a.first = 1; a.last = 1; a.gpart = nullptr;
   if (B == 0) return ALGP_OK;
   cudaStream_t st = (cudaStream_t)stream;
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   if (k <= 8) {
-    // persistent grid of 8 CTAs x 8 warps per SM, warps stride over the candidates.  Two 128-byte lines per
-    // row in flight and no register prefetch was the fastest of the variants tried on B200
-    // (profiles/r01_score_variants.log): the kernel is bound by L2->SM throughput, not by latency.
-    score_k8_launch<2, false, 256>(a, sms, 8, st);
+    // 256-thread CTAs (74 registers: 3 resident per SM), up to 32 CTAs per SM in the grid, warps stride over the
+    // candidates.  Two 128-byte lines per row in flight and no register prefetch was the fastest load schedule
+    // (profiles/r01_score_variants.log); MANY short CTAs beat a persistent resident grid (profiles/r02_score_tiling.log):
+    // CTAs that start at different times keep the warps of an SM out of phase, so loads and DMMAs overlap.
+    if (work && work_doubles < 0) {
+      // algp_score_sets_tiled: one launch per chunk of -work_doubles columns, accumulator fragments in work [B][64]
+      const int chunk = (int)(-work_doubles);
+      a.gpart = work;
+      for (int c0 = 0; c0 < a.ncols16 || c0 == 0; c0 += chunk) {
+        a.col0 = c0;
+        a.col1 = c0 + chunk;
+        a.first = c0 == 0;
+        a.last = c0 + chunk >= a.ncols16;
+        score_k8_launch<2, false, 256>(a, sms, 32, st);
+        ALGP_LAUNCH_CHECK();
+      }
+      return ALGP_OK;
+    }
+    score_k8_launch<2, false, 256>(a, sms, 32, st);
   } else if (k <= SG_MAXK) {
     const int kp = (k + 7) / 8, kk = kp * 8;
     size_t smem = ((size_t)kk * (kk + 1) + kk + (size_t)kk * d) * 8 + (size_t)kk * 4 + 16;
@@ -361,6 +392,47 @@ extern "C" int algp_score_sets_large(const double* Wt, int64_t ldw, int64_t ncol
   }
   ALGP_LAUNCH_CHECK();
   return ALGP_OK;
+}
+
+// ---------------------------------------------------------------------------
+// k <= 8 with the columns of Wt in L2-sized chunks.
+//
+// Large batches of random sets re-read every row of Wt many times (configs[2]: 65 536 sets over 12 288 distinct rows of
+// 32 KB, 403 MB against a 126 MB L2; ncu round 1: 7.7 GB of DRAM reads per launch for 0.4 GB of compulsory traffic).
+// With one launch per column chunk the slice of Wt a launch touches (n_rows x chunk x 8 B) is L2-sized and the
+// accumulator fragments wait in `work` between launches.  Measured on B200 (profiles/r02_score_tiling.log): 1.50 ms
+// at a 1024-column chunk against 1.65-1.70 ms for the single launch; smaller chunks lose more to the per-chunk
+// prologue than they gain in hit rate, and a 36-entry DFMA Gram (instead of the 64-entry DMMA tile) or a persistent
+// resident grid were both slower.
+// ---------------------------------------------------------------------------
+static int g_tile_cols = 0;       // 0 = derive from the L2 size; algp_set_score_tile_cols overrides (tuning / tests)
+
+extern "C" int algp_set_score_tile_cols(int cols) {
+  if (cols < 0 || (cols & 63)) return ALGP_ERR_INVALID;
+  g_tile_cols = cols;
+  return ALGP_OK;
+}
+
+extern "C" int64_t algp_score_sets_tiled_work_doubles(int64_t B) { return B > 0 ? B * 64 : 0; }
+
+extern "C" int algp_score_sets_tiled(const double* Wt, int64_t ldw, int64_t ncols, int64_t n_rows, const double* X, int d,
+                                     const double* log_ls_host, double log_os, int kind, double noise, const double* pi0,
+                                     const int32_t* idx, const double* delta, double delta_scalar, const uint8_t* skip,
+                                     int k, int64_t B, double H_base, double* scores, double* work, int64_t work_doubles,
+                                     void* stream) {
+  if (k < 1 || k > 8 || B < 0 || n_rows < 1) return ALGP_ERR_INVALID;
+  if (B > 0 && (!work || work_doubles < B * 64 || ((uintptr_t)work & 15))) return ALGP_ERR_INVALID;
+  int chunk = g_tile_cols;
+  if (chunk == 0) {
+    int dev = 0, l2 = 64 << 20;
+    ALGP_CUDA(cudaGetDevice(&dev));
+    ALGP_CUDA(cudaDeviceGetAttribute(&l2, cudaDevAttrL2CacheSize, dev));
+    // the slice of a launch about the size of the L2: 1024 columns for the 16 384 rows of configs[2]
+    int64_t c = ((int64_t)l2 / (8 * n_rows) + 32) / 64 * 64;
+    chunk = (int)(c < 256 ? 256 : c);
+  }
+  return algp_score_sets_large(Wt, ldw, ncols, X, d, log_ls_host, log_os, kind, noise, pi0, idx, delta, delta_scalar, skip, k,
+                               B, H_base, scores, B > 0 ? work : (double*)1, -(int64_t)chunk, stream);
 }
 
 // ---------------------------------------------------------------------------

@@ -43,27 +43,155 @@ def allgather_argmax(pair, group=None):
     return combine_pairs(vals, g[:, 1].numpy())
 
 
+class PeerExchange(object):
+    """The ranks' winner mailboxes mapped into each other over cudaIpc (csrc/p2p.cu): the exchange of the per-rank
+    {score, global index} pairs becomes plain NVLink stores from the last argmax kernel instead of an NCCL all-gather
+    launch.  One instance per process group; every rank must call argmax() the same number of times."""
+
+    def __init__(self, group=None, timeout_ms=20000.0):
+        import ctypes as C
+        from . import _lib
+        self.group = group
+        self.world = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+        self.timeout_ms = float(timeout_ms)
+        self.epoch = 0
+        self._lib = _lib
+        self.dev = torch.device("cuda", torch.cuda.current_device())
+        nbytes = _lib.lib.algp_p2p_mailbox_bytes(self.world)
+        if nbytes <= 0:
+            raise RuntimeError("PeerExchange supports up to 16 ranks")
+        self.local = C.c_void_p()
+        handle = (C.c_ubyte * 64)()
+        _lib.call("algp_p2p_create", nbytes, C.byref(self.local), C.cast(handle, C.c_void_p))
+        mine = torch.tensor(list(handle), dtype=torch.uint8, device=self.dev)
+        allh = torch.empty(64 * self.world, dtype=torch.uint8, device=self.dev)
+        dist.all_gather_into_tensor(allh, mine, group=group)
+        allh = allh.cpu().numpy().reshape(self.world, 64)
+        self.opened = []
+        ptrs = []
+        ok = 1
+        for r in range(self.world):
+            if r == self.rank:
+                ptrs.append(self.local.value)
+                continue
+            buf = (C.c_ubyte * 64)(*allh[r].tolist())
+            p = C.c_void_p()
+            rc = _lib.lib.algp_p2p_open(C.cast(buf, C.c_void_p), C.byref(p))
+            if rc != 0:
+                ok = 0
+                self.error = _lib.lib.algp_last_cuda_error().decode()
+                ptrs.append(0)
+            else:
+                self.opened.append(p)
+                ptrs.append(p.value)
+        # all ranks or none: a rank that could not map a peer must not leave the others waiting for its stores
+        flag = torch.tensor([ok], dtype=torch.int32, device=self.dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
+        if int(flag.item()) == 0:
+            self.close()
+            raise RuntimeError("cudaIpc peer mapping unavailable: " + getattr(self, "error", "on another rank"))
+        self.peers = torch.tensor(ptrs, dtype=torch.int64, device=self.dev)
+        self.out3 = torch.empty(3, dtype=torch.int64, device=self.dev)
+        self.work = torch.empty(_lib.lib.algp_argmax_work_bytes(), dtype=torch.uint8, device=self.dev)
+
+    def argmax(self, x, idx_offset=0):
+        """x: this rank's score block (1-D float64 CUDA tensor, or None / empty for an empty shard).
+        Returns the device tensor {score bits, global index, status}, identical on every rank."""
+        self.epoch += 1
+        n = 0 if x is None else int(x.shape[0])
+        self._lib.call("algp_argmax_exchange", self._lib.ptr(x) if n else None, n, int(idx_offset), self._lib.ptr(self.work),
+                       self._lib.ptr(self.peers), self.rank, self.world, self.epoch, self.timeout_ms,
+                       self._lib.ptr(self.out3), self._lib.stream())
+        return self.out3
+
+    def result(self, out3=None):
+        """(score, index) on the host; raises if a peer's pair did not arrive (24-byte D2H, synchronises)."""
+        h = (self.out3 if out3 is None else out3).cpu()
+        if int(h[2]) != 0:
+            raise RuntimeError("PeerExchange: a peer's winner did not arrive within %.0f ms (rank %d, epoch %d)"
+                               % (self.timeout_ms, self.rank, self.epoch))
+        return float(h[0:1].view(torch.float64).item()), int(h[1])
+
+    def close(self):
+        for p in getattr(self, "opened", []):
+            self._lib.lib.algp_p2p_close(p)
+        self.opened = []
+        if getattr(self, "local", None) is not None and self.local.value:
+            self._lib.lib.algp_p2p_destroy(self.local)
+            self.local = None
+
+
+_exchanges = {}
+
+
+def peer_exchange(group=None):
+    """The PeerExchange of `group` (created on first use, collectively), or None when peer mapping is unavailable
+    (then the NCCL all-gather carries the pairs).  ALGP_P2P=0 forces the NCCL path."""
+    import os
+    key = id(group) if group is not None else None
+    if key not in _exchanges:
+        ex = None
+        if os.environ.get("ALGP_P2P", "1") != "0":
+            try:
+                ex = PeerExchange(group)
+            except RuntimeError as e:
+                import warnings
+                warnings.warn("algp_b200.dist: falling back to the NCCL all-gather for the winner exchange: %s" % e)
+        _exchanges[key] = ex
+    return _exchanges[key]
+
+
+def shutdown():
+    """Unmap / free the mailboxes (call before destroy_process_group)."""
+    for ex in _exchanges.values():
+        if ex is not None:
+            ex.close()
+    _exchanges.clear()
+
+
 def pack_pair(value, index, device="cpu"):
     """Host-side constructor of the {score bits, index} pair (tests, empty shards)."""
     v = torch.tensor([value], dtype=torch.float64).view(torch.int64)
     return torch.cat([v, torch.tensor([index], dtype=torch.int64)]).to(device)
 
 
-def sharded_best(state, idx_all, delta_all=None, delta_scalar=0.0, skip=None, group=None):
-    """Score this rank's block of the global candidate array idx_all [B,k] (host int32) against the
-    replicated PosteriorState and return the global (score, index) winner on every rank."""
+def sharded_best(state, idx_all, delta_all=None, delta_scalar=0.0, skip=None, group=None, H_base=None, return_device=False,
+                 events=None):
+    """Score this rank's block of the global candidate array idx_all [B,k] (host int32 array, or an int32 device
+    tensor replicated on every rank) against the replicated PosteriorState and return the global (score, index) winner
+    on every rank.  The per-rank winners travel through the NVLink mailboxes of PeerExchange (NCCL all-gather when peer
+    mapping is unavailable, gloo on CPU tensors).  return_device=True (PeerExchange only) returns the device tensor
+    {score bits, index, status} without synchronising.  events = (start, end) CUDA events recorded around the scoring
+    kernel (bench.py's per-kernel timing)."""
     from . import engine
     world = dist.get_world_size(group) if dist.is_initialized() else 1
     rank = dist.get_rank(group) if dist.is_initialized() else 0
     lo, hi = shard_range(len(idx_all), rank, world)
     dev = state.X.device
+    scores = None
     if hi > lo:
-        idx = engine.to_dev(np.ascontiguousarray(idx_all[lo:hi]), dtype=torch.int32, device=dev)
-        dl = None if delta_all is None else engine.to_dev(np.ascontiguousarray(delta_all[lo:hi]), device=dev)
-        scores = state.score_sets(idx, dl, delta_scalar=delta_scalar, skip=skip)
+        if torch.is_tensor(idx_all):                  # candidates already on the device: this rank's block is a view
+            idx = idx_all[lo:hi]
+            dl = None if delta_all is None else delta_all[lo:hi]
+        else:
+            idx = engine.to_dev(np.ascontiguousarray(idx_all[lo:hi]), dtype=torch.int32, device=dev)
+            dl = None if delta_all is None else engine.to_dev(np.ascontiguousarray(delta_all[lo:hi]), device=dev)
+        if events is not None:
+            events[0].record()
+        scores = state.score_sets(idx, dl, delta_scalar=delta_scalar, skip=skip, H_base=H_base)
+        if events is not None:
+            events[1].record()
+    ex = peer_exchange(group) if (world > 1 and dev.type == "cuda") else None
+    if ex is not None:
+        out3 = ex.argmax(scores, idx_offset=lo)       # argmax + NVLink mailbox exchange in one kernel
+        return out3 if return_device else ex.result(out3)
+    if scores is not None:
         pair = state.argmax(scores, idx_offset=lo)
     else:
         pair = pack_pair(-np.inf, np.iinfo(np.int64).max, dev)
+    if return_device and world == 1:
+        return pair                                   # {score bits, index} on the device, no synchronisation
     return allgather_argmax(pair, group)
 
 

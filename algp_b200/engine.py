@@ -73,8 +73,42 @@ class Hyper(object):
         return (self.log_ls.tobytes(), self.log_os, self.log_noise, self.kind)
 
 
+class _Staging(object):
+    """Reusable pinned staging buffers for host -> device copies: two per device, each guarded by the event of the
+    last copy that read it, so a call neither allocates pinned memory nor waits for an unrelated earlier copy."""
+    MIN_BYTES = 1 << 20
+
+    def __init__(self):
+        self.slots = {}
+
+    def copy(self, t, device):
+        nbytes = t.numel() * t.element_size()
+        key = (device.index if device.index is not None else torch.cuda.current_device())
+        ring = self.slots.setdefault(key, {"bufs": [None, None], "events": [None, None], "next": 0})
+        i = ring["next"]
+        ring["next"] = 1 - i
+        buf = ring["bufs"][i]
+        if buf is None or buf.numel() < nbytes:
+            size = max(self.MIN_BYTES, 1 << (max(nbytes, 1) - 1).bit_length())
+            buf = ring["bufs"][i] = torch.empty(size, dtype=torch.uint8, pin_memory=True)
+            ring["events"][i] = None
+        ev = ring["events"][i]
+        if ev is not None:
+            ev.synchronize()                      # the copy that last read this buffer has finished
+        view = buf[:nbytes].view(t.dtype).view(t.shape)
+        view.copy_(t)
+        out = view.to(device, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(device))
+        ring["events"][i] = ev
+        return out
+
+
+_staging = _Staging()
+
+
 def to_dev(a, dtype=torch.float64, device=None):
-    """Host array -> device tensor through pinned memory (or pass a device tensor through)."""
+    """Host array -> device tensor through a reused pinned staging buffer (or pass a device tensor through)."""
     device = device or require_cuda()
     if isinstance(a, torch.Tensor):
         return a.to(device=device, dtype=dtype).contiguous()
@@ -82,7 +116,9 @@ def to_dev(a, dtype=torch.float64, device=None):
     t = torch.from_numpy(a)
     if t.dtype != dtype:
         t = t.to(dtype)
-    return t.pin_memory().to(device, non_blocking=True)
+    if t.numel() == 0:
+        return torch.empty(t.shape, dtype=dtype, device=device)
+    return _staging.copy(t, device if isinstance(device, torch.device) else torch.device(device))
 
 
 def kbuild(hyper, x1, x2=None, n1_pad=None, n2_pad=None, diag_add=None, diag_scalar=0.0, pad_identity=False,
@@ -456,12 +492,17 @@ class PosteriorState(object):
         self.build_cov()
         return True
 
-    # k <= 8: "stream" = score_sets_k8_kernel (rows of Wt end to end; default), "tiled" = csrc/scoretile.cu (columns in
-    # L2-sized chunks: 19x less DRAM traffic, the same time -- both sit on the L2 -> SM throughput cap)
-    score_mode = "stream"
+    # k <= 8: "stream" = one launch of score_sets_k8_kernel (rows of Wt end to end), "tiled" = one launch per L2-sized
+    # column chunk (algp_score_sets_tiled: 11 % faster on configs[2]), "auto" = tiled once the batch streams enough
+    # bytes for the L2 hit rate to matter
+    score_mode = "auto"
+    TILED_MIN_BYTES = 2.0e9
+    TILED_MIN_COLS = 2048
 
     def _want_tiled(self, B, k):
-        return self.score_mode == "tiled"
+        if self.score_mode != "auto":
+            return self.score_mode == "tiled"
+        return self.ncols >= self.TILED_MIN_COLS and 8.0 * B * k * self.ncols >= self.TILED_MIN_BYTES
 
     def score_sets(self, idx, delta=None, delta_scalar=0.0, H_base=None, out=None, skip=None):
         """scores[c] = H(S1_c) for candidate sets idx [B,k] (int32 device tensor, -1 = empty)."""
@@ -478,7 +519,7 @@ class PosteriorState(object):
             return out
         self._stream_s += 8.0 * B * k * max(self.ncols, 1) / self.STREAM_BYTES_PER_S
         if k <= 8 and self._want_tiled(B, k):
-            # large batches of small sets: columns of Wt in L2-sized chunks, 36-entry DFMA Gram (csrc/scoretile.cu)
+            # large batches of small sets: the same kernel, one launch per L2-sized column chunk
             nwork = _lib.lib.algp_score_sets_tiled_work_doubles(B)
             if getattr(self, "_tilework", None) is None or self._tilework.numel() < nwork:
                 self._tilework = torch.empty(nwork, dtype=torch.float64, device=idx.device)

@@ -48,21 +48,40 @@ def load_peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def field_grid():
+    """The synthetic field of SURVEY.md 8d: the product's own generate_gaussian_data (reference utils.py:90-108) with
+    numpy.random.default_rng(1)."""
+    from algp_b200.utils import generate_gaussian_data
+    grid, y = generate_gaussian_data(FIELD, FIELD, seed=1)
+    return grid.astype(np.float64), y
+
+
+def candidate_sets(rest, seed, n_cand=N_CAND):
+    """n_cand sets of K_SET distinct non-base locations: the first K_SET distinct values of 32 uniform draws per set
+    (vectorised; the same sets as the round-1 per-row np.unique loop)."""
+    rng = np.random.default_rng(seed)
+    pick = rng.integers(0, len(rest), size=(n_cand, 32))
+    idx = np.empty((n_cand, K_SET), dtype=np.int32)
+    for lo in range(0, n_cand, 8192):
+        p = pick[lo:lo + 8192]
+        same = p[:, :, None] == p[:, None, :]                                  # [c, j, i]: draw j equals draw i
+        earlier = np.tril(np.ones((32, 32), dtype=bool), -1)[None]              # i < j
+        first = ~(same & earlier).any(axis=2)                                  # draw j is the first of its value
+        rank = np.cumsum(first, axis=1)
+        keep = first & (rank <= K_SET)
+        assert (keep.sum(axis=1) == K_SET).all()
+        idx[lo:lo + 8192] = rest[p[keep].reshape(-1, K_SET)]
+    return idx
+
+
 def workload(seed_sets=2, n_cand=N_CAND):
     """Synthetic config B: field, base set (seed 1), candidate sets (seed_sets)."""
-    import oracle as O
-    grid, y = O.gaussian_mixture_field(FIELD, FIELD, seed=1)
+    grid, y = field_grid()
     n = len(grid)
     rng = np.random.default_rng(1)
     base = np.sort(rng.choice(n, N_BASE, replace=False))
     rest = np.setdiff1d(np.arange(n), base)
-    rng2 = np.random.default_rng(seed_sets)
-    # k distinct non-base locations per set: the first K_SET distinct values of 32 uniform draws
-    pick = rng2.integers(0, len(rest), size=(n_cand, 32))
-    idx = np.empty((n_cand, K_SET), dtype=np.int32)
-    for c in range(n_cand):
-        u = np.unique(pick[c], return_index=True)[1]
-        idx[c] = rest[pick[c][np.sort(u)[:K_SET]]]
+    idx = candidate_sets(rest, seed_sets, n_cand)
     delta = np.full((n_cand, K_SET), 1.0 / MOBILE_STD ** 2)
     delta[:, 0] = 1.0 / STATIC_STD ** 2        # one static + seven mobile readings per set
     hyper = dict(ls=[FIELD / 16.0, FIELD / 16.0], os=1.0, noise=1e-2, kind="rbf")
@@ -195,7 +214,8 @@ def config_dict():
                         "128x128 mixture-of-Gaussians field (n=16384 locations, d=2, RBF, ls=8, s2=1, noise=1e-2)",
             "candidates_per_gpu": N_CAND, "set_size": K_SET, "n_train": N_BASE, "n_locations": FIELD * FIELD,
             "l2_policy": "inputs larger than L2: each step streams the 537 MB W^T matrix (126 MB L2)",
-            "parallelism": "candidates sharded, factor replicated, 16-byte all-gather of per-rank winners"}
+            "parallelism": "candidates sharded, factor replicated, per-rank winners exchanged through NVLink peer-memory "
+                           "mailboxes from the argmax kernel (algp_b200.dist.sharded_best; NCCL all-gather as the fall-back)"}
 
 
 # --------------------------------------------------------------------------------------
@@ -402,14 +422,18 @@ def fit_predict_bench(torch, engine, n_train, grid_side, reps, peak_hbm):
     return out
 
 
-def episode_bench(torch, engine, side=200, n_pilot=1024, acquisitions=500, per_batch=4, n_paths=256, path_len=16):
+def episode_bench(torch, engine, side=200, n_pilot=1024, acquisitions=500, per_batch=4, n_paths=256, path_len=16,
+                  distributed=False, dist=None, rank=0, world=1, dev=None):
     """BASELINE configs[4]: active-sampling episode on a side x side field: `acquisitions` static picks in batches
     of `per_batch` (greedy, rank-1 appends), each batch followed by scoring `n_paths` candidate paths of `path_len`
     mobile readings and committing the winner.  Path enumeration (env.py) is the planner's job: paths here are
-    synthetic straight runs starting at the batch's picks."""
+    synthetic straight runs starting at the batch's picks.  distributed=True (N > 1): every rank holds the replicated
+    posterior state, scores a contiguous block of the paths (algp_b200.dist.sharded_best, winners over the NVLink
+    mailboxes) and applies the same commits; rank 0 then repeats the episode alone and the chosen indices must agree."""
     from algp_b200.episode import run_episode
-    import oracle as O
-    grid, _ = O.gaussian_mixture_field(side, side, seed=1)
+    from algp_b200.utils import generate_gaussian_data
+    grid, _ = generate_gaussian_data(side, side, seed=1)
+    grid = grid.astype(np.float64)
     n = len(grid)
     rng = np.random.default_rng(3)
     static = np.zeros(n, bool)
@@ -428,13 +452,72 @@ def episode_bench(torch, engine, side=200, n_pilot=1024, acquisitions=500, per_b
         cc = np.clip(c[:, None] + dc[:, None] * steps, 0, side - 1)
         return (rr * side + cc).astype(np.int32)
 
-    Xd = engine.to_dev(grid)
-    run_episode(hyper, Xd, static, mobile, STATIC_STD, MOBILE_STD, 2, per_batch, path_fn, distributed=False)   # warm-up
-    res = run_episode(hyper, Xd, static, mobile, STATIC_STD, MOBILE_STD, batches, per_batch, path_fn, distributed=False)
-    return {"field": "%dx%d" % (side, side), "n_locations": n, "pilot_samples": n_pilot, "acquisitions": batches * per_batch,
-            "paths_per_batch": n_paths, "path_len": path_len, "ms_per_acquisition": res["ms_per_acquisition"],
-            "ms_per_batch": res["ms_per_batch"], "mobile_committed": int(res["mobile"].sum()),
-            "entropy_first_last": [res["H"][0], res["H"][-1]]}
+    Xd = engine.to_dev(grid, device=dev)
+    run_episode(hyper, Xd, static, mobile, STATIC_STD, MOBILE_STD, 2, per_batch, path_fn, distributed=distributed)   # warm-up
+    if distributed:
+        dist.barrier()
+    res = run_episode(hyper, Xd, static, mobile, STATIC_STD, MOBILE_STD, batches, per_batch, path_fn, distributed=distributed)
+    ms_b, ms_a = res["ms_per_batch"], res["ms_per_acquisition"]
+    out = {"field": "%dx%d" % (side, side), "n_locations": n, "pilot_samples": n_pilot, "acquisitions": batches * per_batch,
+           "paths_per_batch": n_paths, "path_len": path_len, "mobile_committed": int(res["mobile"].sum()),
+           "entropy_first_last": [res["H"][0], res["H"][-1]]}
+    if distributed:
+        tt = torch.tensor([ms_b, ms_a], dtype=torch.float64, device=dev)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        ms_b, ms_a = float(tt[0].item()), float(tt[1].item())
+        out["gpus"] = world
+        out["paths_per_gpu"] = n_paths // world
+        picks, paths = res["picks"], res["best_paths"]
+        del res
+        # chosen-index agreement: every rank against rank 0, and rank 0's sharded run against its own single-GPU run
+        mine = torch.tensor([p for b in picks for p in b] + paths, dtype=torch.int64, device=dev)
+        ref = mine.clone()
+        dist.broadcast(ref, src=0)
+        same = torch.tensor([int(torch.equal(mine, ref))], dtype=torch.int32, device=dev)
+        dist.all_reduce(same, op=dist.ReduceOp.MIN)
+        out["all_ranks_chose_the_same_indices"] = bool(same.item())
+        if rank == 0:
+            solo = run_episode(hyper, Xd, static, mobile, STATIC_STD, MOBILE_STD, batches, per_batch, path_fn, distributed=False)
+            out["same_picks_and_paths_as_one_gpu"] = bool(solo["picks"] == picks and solo["best_paths"] == paths)
+            out["ms_per_acquisition_one_gpu_same_run"] = solo["ms_per_acquisition"]
+            out["entropy_last_one_gpu"] = solo["H"][-1]
+        dist.barrier()
+    out["ms_per_acquisition"] = ms_a
+    out["ms_per_batch"] = ms_b
+    return out
+
+
+def patched_reference_style_agent():
+    """A class with the reference Agent's sample bookkeeping (agent.py:47-82) and NO hot-path methods of its own,
+    run through algp_b200.patch(): the drop-in route of INTEGRATION.md (the reference's own agent.py cannot be imported
+    on the GPU box, so its bookkeeping is restated here)."""
+    import algp_b200
+
+    class RefAgent(object):
+        def __init__(self, env, gp, static_std, mobile_std, rng):
+            self.env, self.gp, self.static_std, self.mobile_std, self.rng = env, gp, static_std, mobile_std, rng
+            self.criterion = 'entropy'
+            self.reset()
+
+        def reset(self):
+            self.collected = {'ind': [], 'std': [], 'y': []}
+            self.static_data = [[] for _ in range(self.env.num_samples)]
+            self.mobile_data = [[] for _ in range(self.env.num_samples)]
+
+        def _add_samples(self, indices, stds):
+            all_y = [None] * len(indices)
+            for i in range(len(indices)):
+                idx = indices[i]
+                if idx == -1:
+                    continue
+                y = float(self.rng.normal(0.5, stds[i]))            # env.collect_samples: a noisy reading
+                all_y[i] = y
+                (self.static_data if stds[i] == self.static_std else self.mobile_data)[idx].append(y)
+            self.collected['ind'] += list(indices)
+            self.collected['std'] += list(stds)
+            self.collected['y'] += all_y
+
+    return algp_b200.patch(RefAgent)
 
 
 def default_scale_bench(torch, engine, cpu_sample=24):
@@ -473,14 +556,9 @@ def default_scale_bench(torch, engine, cpu_sample=24):
         pass
     env = Env()
     env.X, env.test_X, env.num_samples = X, X[:40], n
-    ag = algp_b200.Agent.__new__(algp_b200.Agent)
-    ag.env, ag.static_std, ag.mobile_std, ag.criterion = env, STATIC_STD, MOBILE_STD, 'entropy'
-    ag.static_data = [[] for _ in range(n)]
-    ag.mobile_data = [[] for _ in range(n)]
-    for i in static:
-        ag.static_data[i] = [0.5]
-    for i in mobile:
-        ag.mobile_data[i] = [0.4, 0.6]
+    ag = patched_reference_style_agent()(env, None, STATIC_STD, MOBILE_STD, np.random.default_rng(6))
+    ag._add_samples(list(static), [STATIC_STD] * len(static))
+    ag._add_samples(list(mobile) + list(mobile), [MOBILE_STD] * (2 * len(mobile)))
     ls, os_, noise = [3.0, 6.0, 1.5, 1.5, 1.5, 1.5], 1.0, 1e-2
     ind, yv, var = ag.get_sampled_dataset()
     ag.gp = algp_b200.GPR(kernel_params={'type': 'matern'})
@@ -514,7 +592,25 @@ def default_scale_bench(torch, engine, cpu_sample=24):
     t0 = time.perf_counter()
     O.best_path_literal(cov, st, mo, STATIC_STD, MOBILE_STD, sample, cpu_picks)
     cpu_paths_ms = (time.perf_counter() - t0) * 1e3 * len(lists) / len(sample)
+    # three more iterations of the run_ipp body (agent.py:133-201 with update=False) on the same patched agent: the
+    # picks and the winning path's readings are added through the reference's _add_samples, so every later greedy /
+    # best_path extends the cached posterior state instead of re-factorising
+    ipp_ms, same_state = [], []
+    ag._hot_state = None
+    for it in range(4):
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        pk = ag.greedy(4)
+        bp = ag.best_path(lists, pk)
+        torch.cuda.synchronize()
+        ipp_ms.append((time.perf_counter() - t0) * 1e3)
+        same_state.append(id(ag._hot_state["state"]))
+        seq = [int(j) for j in lists[bp]] + [int(j) for j in pk]
+        ag._add_samples(seq, [MOBILE_STD] * len(lists[bp]) + [STATIC_STD] * len(pk))
     return {"field_locations": n, "d": d, "kernel": "matern", "n_base": int(len(ind)), "paths": len(lists),
+            "agent": "reference-style class (agent.py:47-82 bookkeeping) through algp_b200.patch()",
+            "run_ipp_iterations_ms": [round(t, 3) for t in ipp_ms],
+            "posterior_state_extended_not_refactorised": bool(len(set(same_state)) == 1),
             "longest_path": int(slots.shape[1]), "path_enumeration_ms": enum_ms,
             "greedy4_plus_best_path_ms": {"lists": float(np.median(ts_l)), "slot_array": float(np.median(ts_a))},
             "picks": [int(p) for p in picks], "best_path": int(best), "same_choice_array_form": bool(best == best_a and picks == picks_a),
@@ -714,22 +810,170 @@ def resident_cov_bench(torch, engine, algp_b200, hyper, Xd, base, pi0, is_static
     return out
 
 
+def timed_steps(torch, dist, world, dev, fn, steps, warmup, sampler=None):
+    """W untimed + K timed calls of fn(i) bracketed by barrier + synchronize on both sides; CUDA events on the
+    current stream; the MAX over ranks of the elapsed time in ms."""
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+    for _ in range(warmup):
+        fn(None)
+    barrier()
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    if sampler is not None:
+        sampler.__enter__()
+    barrier()
+    t0.record()
+    last = None
+    for i in range(steps):
+        last = fn(i)
+    t1.record()
+    barrier()
+    if sampler is not None:
+        sampler.__exit__()
+    ms = t0.elapsed_time(t1)
+    if world > 1:
+        tt = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        ms = float(tt.item())
+    return ms, last
+
+
+def decode_winner(torch, res):
+    """(score, index) from what algp_b200.dist.sharded_best returned (device tensor or host tuple)."""
+    if torch.is_tensor(res):
+        h = res.cpu()
+        if h.numel() > 2 and int(h[2]) != 0:
+            raise RuntimeError("winner exchange timed out")
+        return float(h[0:1].view(torch.float64).item()), int(h[1])
+    return float(res[0]), int(res[1])
+
+
+def l2_probe(torch, mbytes=(32, 64)):
+    """L2 -> SM delivery rate measured in this run (algp_probe_l2_read): an L2-resident buffer read 40 times with the
+    scoring kernel's load instruction, every CTA a different part.  TB/s per buffer size."""
+    from algp_b200 import _lib
+    out = {}
+    sink = torch.zeros(1, dtype=torch.float64, device="cuda")
+    for mb in mbytes:
+        buf = torch.ones(mb << 20, dtype=torch.uint8, device="cuda")
+        best = 0.0
+        for ctas in (2, 4, 8):
+            _lib.call("algp_probe_l2_read", _lib.ptr(buf), buf.numel(), 4, ctas, _lib.ptr(sink), _lib.stream())
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            _lib.call("algp_probe_l2_read", _lib.ptr(buf), buf.numel(), 40, ctas, _lib.ptr(sink), _lib.stream())
+            e1.record()
+            torch.cuda.synchronize()
+            best = max(best, 40.0 * buf.numel() / (e0.elapsed_time(e1) / 1e3) / 1e12)
+        out["%dMB" % mb] = best
+        del buf
+    return out
+
+
+def ncu_dram_traffic(kernel_substr, files=("r02_prof_score_summary.csv", "r01_prof_score_summary.csv")):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of a kernel from the committed ncu summaries
+    (profiles/*.csv, written by scripts/ncu_summary.py from an `ncu --set full` capture): (bytes | None, file | None)."""
+    import csv
+    units = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0, "Tbyte": 1e12}
+    for name in files:
+        path = os.path.join(ROOT, "profiles", name)
+        if not os.path.exists(path):
+            continue
+        rows = list(csv.reader(open(path)))
+        if len(rows) < 3:
+            continue
+        hdr, unit = rows[0], rows[1]
+        try:
+            ir, iw = hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum")
+        except ValueError:
+            continue
+        vals = [float(r[ir]) * units.get(unit[ir], 1.0) + float(r[iw]) * units.get(unit[iw], 1.0)
+                for r in rows[2:] if r and kernel_substr in r[0]]
+        if vals:
+            return float(np.mean(vals)), "profiles/" + name
+    return None, None
+
+
+def strong_scaling_bench(torch, dist, adist, engine, state, idx0_d, delta0_d, H_base, rank, world, dev, steps, warmup):
+    """configs[2] read literally: ONE batch of 65 536 candidate sets sharded over the ranks (8 192 per GPU at N = 8)
+    through algp_b200.dist.sharded_best (winners exchanged over the NVLink mailboxes), next to the same batch on rank 0
+    alone in the same run, and to the same sharded step with the NCCL all-gather carrying the winners."""
+    out = {"scaling": "strong", "total_candidate_sets": N_CAND, "sets_per_gpu": N_CAND // world}
+    ms, last = timed_steps(torch, dist, world, dev,
+                           lambda i: adist.sharded_best(state, idx0_d, delta0_d, H_base=H_base, return_device=True),
+                           steps, warmup)
+    out["ms_per_step"] = ms / steps
+    out["value"] = N_CAND * steps / (ms / 1e3)
+    out["unit"] = UNIT
+    out["winner"] = decode_winner(torch, last)[1]
+    out["exchange"] = "nvlink mailboxes (csrc/p2p.cu)" if adist.peer_exchange() is not None else "nccl all-gather"
+    # comparator: the round-1 step (two argmax kernels + NCCL all-gather of 16 bytes per rank)
+    lo, hi = adist.shard_range(N_CAND, rank, world)
+    scores = torch.empty(hi - lo, dtype=torch.float64, device=dev)
+    pair = torch.empty(2, dtype=torch.int64, device=dev)
+    gathered = torch.empty(2 * world, dtype=torch.int64, device=dev)
+
+    def nccl_step(i):
+        state.score_sets(idx0_d[lo:hi], delta0_d[lo:hi], H_base=H_base, out=scores)
+        state.argmax(scores, idx_offset=lo, out=pair)
+        dist.all_gather_into_tensor(gathered, pair)
+    ms_n, _ = timed_steps(torch, dist, world, dev, nccl_step, steps, warmup)
+    out["ms_per_step_nccl_allgather"] = ms_n / steps
+    # the same batch on ONE GPU in the same run (rank 0 works, the others wait at the barrier)
+    full = torch.empty(N_CAND, dtype=torch.float64, device=dev)
+
+    def single_step(i):
+        if rank == 0:
+            state.score_sets(idx0_d, delta0_d, H_base=H_base, out=full)
+            state.argmax(full, idx_offset=0, out=pair)
+    ms_1, _ = timed_steps(torch, dist, world, dev, single_step, steps, warmup)
+    out["ms_per_step_one_gpu_same_run"] = ms_1 / steps
+    out["efficiency_vs_one_gpu_same_run"] = (ms_1 / steps) / (world * ms / steps)
+    if rank == 0:
+        out["winner_one_gpu"] = int(pair[1].item())
+    return out
+
+
+def resident_sharded_bench(torch, dist, adist, engine, hyper, Xd, base, pi0, is_static, idx_all_d, delta_all_d, idx0_d,
+                           delta0_d, H_base, world, dev, steps, warmup):
+    """The resident-covariance path at N GPUs: every rank builds P once (replicated, like the factor) and scores its
+    block by gathers; weak (65 536 sets per GPU) and strong (65 536 in total)."""
+    st = engine.PosteriorState(hyper, Xd, base, pi0, is_static=is_static, cov_mode="always")
+    out = {}
+    for name, ix, dl, total in (("weak", idx_all_d, delta_all_d, world * N_CAND), ("strong", idx0_d, delta0_d, N_CAND)):
+        ms, last = timed_steps(torch, dist, world, dev,
+                               lambda i: adist.sharded_best(st, ix, dl, H_base=H_base, return_device=True), steps, warmup)
+        out[name] = {"ms_per_step": ms / steps, "value": total * steps / (ms / 1e3), "unit": UNIT,
+                     "winner": decode_winner(torch, last)[1]}
+    del st
+    return out
+
+
 def run_ours(args, rank, world, local_rank):
     import torch
     import torch.distributed as dist
     import algp_b200
-    from algp_b200 import engine
+    from algp_b200 import _lib, engine
+    from algp_b200 import dist as adist
     if not torch.cuda.is_available():
         raise RuntimeError("bench.py needs a CUDA device (no CPU fallback)")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        import datetime
+        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=180))
     peak_hbm, peak_src = load_peaks()
+    steps, warmup = args.steps, max(3, args.warmup)
 
-    grid, y, base, idx, delta, hy = workload(seed_sets=2 + rank)
-    hyper = engine.Hyper(np.log(hy["ls"]), np.log(hy["os"]), np.log(hy["noise"]), hy["kind"])
+    # rank r's block of the weak-scaling run is the 65 536 sets of seed 2 + r; block 0 is configs[2]'s batch
+    grid, y, base, idx0, delta, hy = workload(seed_sets=2)
     n = len(grid)
+    rest = np.setdiff1d(np.arange(n), base)
+    idx_all = np.concatenate([idx0] + [candidate_sets(rest, 2 + r) for r in range(1, world)])
+    delta_all = np.tile(delta, (world, 1))
+    hyper = engine.Hyper(np.log(hy["ls"]), np.log(hy["os"]), np.log(hy["noise"]), hy["kind"])
     pi0 = np.zeros(n)
     pi0[base] = 1.0 / STATIC_STD ** 2
     is_static = (pi0 > 0)
@@ -745,64 +989,44 @@ def run_ours(args, rank, world, local_rank):
     e1.record()
     torch.cuda.synchronize()
     setup_ms = e0.elapsed_time(e1)
-    # the same one-off build with precision "i8" (W^T through the INT8 digit GEMM)
-    engine.PosteriorState(hyper, Xd, base, pi0, is_static=is_static, precision="i8")
-    torch.cuda.synchronize()
-    e0.record()
-    state8 = engine.PosteriorState(hyper, Xd, base, pi0, is_static=is_static, precision="i8")
-    e1.record()
-    torch.cuda.synchronize()
-    setup_ms_i8 = e0.elapsed_time(e1)
-    setup_i8_dW = float((state8.Wt - state.Wt).abs().max().item())
-    del state8
+    setup_ms_i8 = setup_i8_dW = None
+    if world == 1:
+        # the same one-off build with precision "i8" (W^T through the INT8 digit GEMM)
+        engine.PosteriorState(hyper, Xd, base, pi0, is_static=is_static, precision="i8")
+        torch.cuda.synchronize()
+        e0.record()
+        state8 = engine.PosteriorState(hyper, Xd, base, pi0, is_static=is_static, precision="i8")
+        e1.record()
+        torch.cuda.synchronize()
+        setup_ms_i8 = e0.elapsed_time(e1)
+        setup_i8_dW = float((state8.Wt - state.Wt).abs().max().item())
+        del state8
     H_base = state.H_base
 
-    idx_d = engine.to_dev(idx, dtype=torch.int32, device=dev)
-    delta_d = engine.to_dev(delta, device=dev)
-    scores = torch.empty(N_CAND, dtype=torch.float64, device=dev)
-    pair = torch.empty(2, dtype=torch.int64, device=dev)
-    gathered = torch.empty(2 * world, dtype=torch.int64, device=dev)
-    kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    idx_all_d = engine.to_dev(idx_all, dtype=torch.int32, device=dev)
+    delta_all_d = engine.to_dev(delta_all, device=dev)
+    idx0_d, delta0_d = idx_all_d[:N_CAND], delta_all_d[:N_CAND]
+    kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
 
-    def step(i=None):
-        if i is not None:
-            kev[i][0].record()
-        state.score_sets(idx_d, delta_d, H_base=H_base, out=scores)
-        if i is not None:
-            kev[i][1].record()
-        state.argmax(scores, idx_offset=rank * N_CAND, out=pair)
-        if world > 1:
-            dist.all_gather_into_tensor(gathered, pair)
+    # ---- headline: the product's sharded scoring step (algp_b200.dist.sharded_best): this rank's block of the global
+    # candidate array scored against the replicated factor, np.argmax, winners exchanged between the GPUs ----
+    def step(i):
+        return adist.sharded_best(state, idx_all_d, delta_all_d, H_base=H_base, return_device=True,
+                                  events=None if i is None else kev[i])
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    for _ in range(max(3, args.warmup)):
-        step()
-    barrier()
-    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    with ClockSampler(local_rank) as clk:
-        barrier()
-        t0.record()
-        for i in range(args.steps):
-            step(i)
-        t1.record()
-        barrier()
-    ms = t0.elapsed_time(t1)
+    for _ in range(warmup):
+        step(None)
+    torch.cuda.synchronize()
+    launches0 = _lib.launch_count
+    clk = ClockSampler(local_rank)
+    ms, last = timed_steps(torch, dist, world, dev, step, steps, 0, sampler=clk)
+    gpu_launches = _lib.launch_count - launches0
     kernel_ms = float(np.mean([a.elapsed_time(b) for a, b in kev]))
+    win_score, win = decode_winner(torch, last)
+    value = world * N_CAND * steps / (ms / 1e3)
+    exchange = None
     if world > 1:
-        tt = torch.tensor([ms], dtype=torch.float64, device=dev)
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        ms = float(tt.item())
-        g = gathered.cpu()
-        vals = g.view(world, 2)[:, 0:1].contiguous().view(torch.float64).numpy().reshape(-1)
-        ids = g.view(world, 2)[:, 1].numpy()
-        win = int(ids[np.lexsort((ids, -vals))[0]])
-    else:
-        win = int(pair[1].item())
-    value = world * N_CAND * args.steps / (ms / 1e3)
+        exchange = "nvlink mailboxes (csrc/p2p.cu)" if adist.peer_exchange() is not None else "nccl all-gather"
 
     # ---- end to end through the reference-facing call: Agent.best_path with HOST arrays ----
     class Env(object):
@@ -814,6 +1038,7 @@ def run_ours(args, rank, world, local_rank):
         ag = algp_b200.Agent.__new__(algp_b200.Agent)
         ag.env, ag.static_std, ag.mobile_std, ag.criterion = env, STATIC_STD, MOBILE_STD, 'entropy'
         ag.cov_mode = cov_mode
+        ag.shard_candidates = world > 1          # one process per GPU: every rank scores its block of the paths
         ag.static_data = [[0.0] if s else [] for s in is_static]
         ag.mobile_data = [[] for _ in range(n)]
         ag.collected = {'ind': list(base), 'std': [STATIC_STD] * len(base), 'y': [0.0] * len(base)}
@@ -826,15 +1051,18 @@ def run_ours(args, rank, world, local_rank):
         ag._post_update()
         return ag
     ag = make_agent("never")         # headline end-to-end number: the streaming path, as in `value`
-    # the reference call scores paths of mobile readings on top of static waypoints: here every set is
-    # 8 mobile slots and no new static waypoint (same kernel, same bytes per candidate)
-    e2e_steps = max(3, min(args.steps, 10))
+    # the reference call scores paths of mobile readings on top of static waypoints: here every set is 8 mobile slots
+    # and no new static waypoint (same kernel, same bytes per candidate).  At N > 1 the call receives the GLOBAL host
+    # array; every rank copies and scores its own block and all ranks return the same winner.
+    e2e_steps = max(3, min(steps, 10))
     for _ in range(3):
-        ag.best_path(idx, [])
-    barrier()
+        ag.best_path(idx_all, [])
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
     w0 = time.perf_counter()
     for _ in range(e2e_steps):
-        ag.best_path(idx, [])
+        e2e_win = ag.best_path(idx_all, [])
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - w0
     if world > 1:
@@ -845,12 +1073,20 @@ def run_ours(args, rank, world, local_rank):
 
     extra = {}
     cpu_base = None
-    if rank == 0 and world == 1:
-        try:
-            extra["resident_cov"] = resident_cov_bench(torch, engine, algp_b200, hyper, Xd, base, pi0, is_static, idx, idx_d,
-                                                       delta_d, H_base, scores.clone(), ms / args.steps, args.steps, make_agent)
-        except Exception as e:
-            extra["resident_cov_error"] = repr(e)
+    if world > 1:
+        for name, fn in (
+                ("strong_scaling", lambda: strong_scaling_bench(torch, dist, adist, engine, state, idx0_d, delta0_d, H_base, rank,
+                                                                 world, dev, steps, warmup)),
+                ("resident_cov_sharded", lambda: resident_sharded_bench(torch, dist, adist, engine, hyper, Xd, base, pi0, is_static,
+                                                                        idx_all_d, delta_all_d, idx0_d, delta0_d, H_base, world,
+                                                                        dev, steps, warmup)),
+                ("episode", lambda: episode_bench(torch, engine, distributed=True, dist=dist, rank=rank, world=world, dev=dev))):
+            try:
+                extra[name] = fn()
+            except Exception as e:
+                extra[name + "_error"] = repr(e)
+                if "timed out" in repr(e) or "NCCL" in repr(e):
+                    raise
     if world > 1 and not args.skip_large:
         # second metric at N > 1: the factorisation stays on rank 0, its inverse factor is broadcast, the 256 x 256
         # grid of test rows is sharded over the ranks (algp_b200.dist.sharded_mean_var), INT8 digit mode
@@ -858,9 +1094,20 @@ def run_ours(args, rank, world, local_rank):
             extra["fit_predict_sharded"] = sharded_fit_predict_bench(torch, dist, engine, dev, world)
         except Exception as e:
             extra["fit_predict_sharded_error"] = repr(e)
-    # the fit+predict / episode / CPU legs explain the N=1 line; at N>1 only the sharded metrics are measured
+    # the fit+predict / fit-loop / CPU legs explain the N=1 line; at N>1 only the sharded metrics are measured
     # (the other ranks would idle at the barrier while rank 0 ran them)
+    fp64_peak = None
     if rank == 0 and world == 1:
+        try:
+            extra["l2_to_sm_probe_tbs"] = l2_probe(torch)
+        except Exception as e:
+            extra["l2_probe_error"] = repr(e)
+        try:
+            extra["resident_cov"] = resident_cov_bench(torch, engine, algp_b200, hyper, Xd, base, pi0, is_static, idx0, idx0_d,
+                                                       delta0_d, H_base, state.score_sets(idx0_d, delta0_d, H_base=H_base).clone(),
+                                                       ms / steps, steps, make_agent)
+        except Exception as e:
+            extra["resident_cov_error"] = repr(e)
         try:
             fp64_peak, fp64_sustained = dgemm_peak(torch)
             extra["fp64_gemm_peak_tflops_cublas_8192"] = fp64_peak
@@ -899,7 +1146,7 @@ def run_ours(args, rank, world, local_rank):
                 extra["default_scale_step"] = default_scale_bench(torch, engine)
             except Exception as e:
                 extra["default_scale_error"] = repr(e)
-        if world == 1 and not args.no_cpu:
+        if not args.no_cpu:
             ctx = cpu_reference_setup()
             cpu_score_sample(ctx, 0, 1)
             cnt = 12
@@ -926,33 +1173,52 @@ def run_ours(args, rank, world, local_rank):
     if rank == 0:
         algo_bytes = 8.0 * N_BASE * K_SET * N_CAND           # s*N*k per candidate
         achieved = algo_bytes / (kernel_ms / 1e3) / 1e9
+        traffic, traffic_src = ncu_dram_traffic("score_sets_k8_kernel")
+        gram_flops = 2.0 * N_BASE * K_SET * K_SET * N_CAND   # the full 8 x 8 Gram the DMMA tiles compute
+        roof = {"bound": "hbm", "kernel": "score_sets_k8_kernel", "achieved": achieved, "peak": peak_hbm,
+                "unit": "GB/s", "frac": achieved / peak_hbm, "traffic": traffic, "traffic_source": traffic_src,
+                "peak_source": peak_src, "kernel_ms": kernel_ms, "algorithmic_bytes_per_launch": algo_bytes,
+                "note": "`achieved` is SURVEY 8d's no-reuse byte count over the kernel time: it exceeds the DRAM peak because part "
+                        "of the rows are served by the L2, so `frac` is not a fraction of a roof.  The resources this kernel "
+                        "actually loads are listed under `resources`; the binding one is the L2 -> SM delivery rate: all "
+                        "algorithmic bytes cross it exactly once."}
+        res = {}
+        if traffic is not None:
+            res["dram"] = {"bytes_per_launch_ncu": traffic, "achieved_gbs": traffic / (kernel_ms / 1e3) / 1e9, "peak_gbs": peak_hbm,
+                           "frac": traffic / (kernel_ms / 1e3) / 1e9 / peak_hbm}
+        probe = extra.get("l2_to_sm_probe_tbs")
+        if probe:
+            pk = max(probe.values())
+            res["l2_to_sm"] = {"achieved_tbs": achieved / 1e3, "peak_tbs_measured_in_run": pk, "frac": achieved / 1e3 / pk}
+        if fp64_peak:
+            res["fp64_tensor_dmma"] = {"achieved_tflops": gram_flops / (kernel_ms / 1e3) / 1e12, "peak_tflops_cublas_dgemm": fp64_peak,
+                                       "frac": gram_flops / (kernel_ms / 1e3) / 1e12 / fp64_peak}
+        if res:
+            roof["resources"] = res
+            roof["binding"] = max(res, key=lambda k: res[k]["frac"])
         line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
-            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warmup,
+            "ms_per_step": ms / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic", "config": config_dict(),
             "clocks": clk.summary(),
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(idx.nbytes), "d2h_bytes_per_step": 16,
-                    "api": "algp_b200.Agent.best_path(ndarray[65536,8], []) with host arrays", "steps": e2e_steps},
-            "gpu_launches": 3 * args.steps,
-            "roofline": {"bound": "hbm", "kernel": "score_sets_k8_kernel", "achieved": achieved, "peak": peak_hbm,
-                         "unit": "GB/s", "frac": achieved / peak_hbm,
-                         # dram__bytes_read.sum + dram__bytes_write.sum per launch, ncu --set full
-                         # (profiles/r01_prof_score_summary.csv): 7.71 GB + 5 MB
-                         "traffic": 7.716e9, "achieved_dram_gbs": 7.716 / kernel_ms * 1e3, "frac_dram": 7.716 / kernel_ms * 1e3 / peak_hbm,
-                         "peak_source": peak_src,
-                         "note": "above 1.0 of the DRAM peak because 40% of the sector reads hit the 126 MB L2; DRAM itself is "
-                                 "~73% busy (frac_dram) and the DMMA pipe 57%: no single roof is reached (bulk copies from a hot L2 "
-                                 "deliver 24 TB/s, profiles/r01_l2_multicast_microbench.log)",
-                         "kernel_ms": kernel_ms, "algorithmic_bytes_per_launch": algo_bytes},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(idx0.nbytes), "d2h_bytes_per_step": 16 if world == 1 else 24,
+                    "api": "algp_b200.Agent.best_path(ndarray[%d,8], []) with host arrays%s" %
+                           (world * N_CAND, "" if world == 1 else ", shard_candidates=True: every rank copies and scores its block"),
+                    "steps": e2e_steps, "winner": int(e2e_win)},
+            "gpu_launches": int(gpu_launches),
+            "roofline": roof,
             "setup_ms_factor_and_W": setup_ms, "setup_ms_factor_and_W_i8": setup_ms_i8, "setup_i8_max_abs_dW": setup_i8_dW,
-            "winner": win, "H_base": H_base,
+            "winner": win, "winner_score": win_score, "H_base": H_base,
         }
+        if exchange is not None:
+            line["winner_exchange"] = exchange
         if cpu_base is not None:
             line["cpu_baseline"] = cpu_base
         line.update(extra)
         print(json.dumps(line))
     if world > 1:
         dist.barrier()
+        adist.shutdown()
         dist.destroy_process_group()
 
 

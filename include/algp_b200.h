@@ -166,12 +166,11 @@ int algp_score_sets_large(const double* Wt, int64_t ldw, int64_t ncols, const do
                           const int32_t* idx, const double* delta, double delta_scalar, const uint8_t* skip, int k,
                           int64_t B, double H_base, double* scores, double* work, int64_t work_doubles, void* stream);
 int64_t algp_score_sets_large_work_doubles(int k, int64_t B);
-/* The same scores for k <= 8 with the columns of Wt processed in L2-sized chunks (one launch per chunk, partial
- * Gram matrices G[B][36] in `work`): large batches of random sets re-read every row of Wt many times, and a chunk's
- * slice of Wt (n_rows x chunk x 8 bytes, n_rows = rows the candidates can reference) stays L2-resident where whole
- * rows do not.  A slot table (one pass over idx / delta / skip) is built first, a thread per candidate finishes
- * (Sigma_CC, elimination, bookkeeping).  work: algp_score_sets_tiled_work_doubles(B) doubles, 16-byte aligned.  algp_set_score_tile_cols(c) forces the chunk (multiple of
- * 64; 0 = derive from the L2 size). */
+/* The same scores for k <= 8 with the columns of Wt processed in L2-sized chunks: one launch of the k <= 8 kernel
+ * per chunk, the accumulator fragments parked in `work` between launches.  Large batches of random sets re-read every
+ * row of Wt many times, and a chunk's slice of Wt (n_rows x chunk x 8 bytes, n_rows = rows the candidates can
+ * reference) fits the L2 where whole rows do not.  work: algp_score_sets_tiled_work_doubles(B) doubles, 16-byte
+ * aligned.  algp_set_score_tile_cols(c) forces the chunk (multiple of 64; 0 = derive from the L2 size). */
 int algp_score_sets_tiled(const double* Wt, int64_t ldw, int64_t ncols, int64_t n_rows, const double* X, int d,
                           const double* log_ls_host, double log_os, int kind, double noise, const double* pi0,
                           const int32_t* idx, const double* delta, double delta_scalar, const uint8_t* skip, int k,
@@ -193,6 +192,23 @@ int algp_greedy_utilities(const double* diagP, const double* pi, const uint8_t* 
  * work: algp_argmax_work_bytes() bytes. */
 int algp_argmax(const double* x, int64_t n, int64_t idx_offset, void* out_pair, void* work, void* stream);
 int64_t algp_argmax_work_bytes(void);
+/* ---- winner exchange between the GPUs of one box over NVLink peer memory (csrc/p2p.cu) ----
+ * Replaces the NCCL all-gather of one 16-byte {score, global index} pair per rank that follows the sharded scoring
+ * step: the last argmax kernel stores the rank's pair into a mailbox in every peer's memory, waits for
+ * the peers' pairs in its own and reduces them with the first-maximum rule.
+ * algp_p2p_create: cudaMalloc + zero a mailbox of `bytes` (algp_p2p_mailbox_bytes(world)) and export its 64-byte
+ * cudaIpc handle; algp_p2p_open maps a peer's handle; close / destroy undo them. */
+int64_t algp_p2p_mailbox_bytes(int world);
+int algp_p2p_create(int64_t bytes, void** local_ptr, void* handle64);
+int algp_p2p_open(const void* handle64, void** peer_ptr);
+int algp_p2p_close(void* peer_ptr);
+int algp_p2p_destroy(void* local_ptr);
+/* np.argmax of this rank's block x[n] (global ids = position + idx_offset; n = 0 = empty shard) exchanged with the
+ * `world` ranks whose mailboxes are listed in peers_dev (device array of `world` pointers, entry r = rank r's mailbox as
+ * mapped here).  out3 (device, 24 bytes) = {double value; int64 index; int64 status (0 ok, 1 = a peer timed out)},
+ * identical on every rank.  epoch = 1, 2, 3, ... in step on all ranks.  work: algp_argmax_work_bytes() bytes. */
+int algp_argmax_exchange(const double* x, int64_t n, int64_t idx_offset, void* work, const void* peers_dev, int rank,
+                         int world, int64_t epoch, double timeout_ms, void* out3, void* stream);
 /* Commit an acquisition at location *j_dev with precision increment delta: appends column
  * `ncols` to Wt, downdates diagP, raises pi[j] (and is_static[j] if mark_static).
  * work: algp_append_work_doubles(n) doubles. */
@@ -234,6 +250,12 @@ int64_t algp_mi_terms_large_work_doubles(int k, int64_t B);
  * rows, for every i, from ONE factorisation of the full ordered set. */
 int algp_prefix_reduce(const double* V, int64_t ldv, int64_t rows, const double* beta, const double* gamma,
                        const int32_t* prefix_dev, int nprefix, double* out, void* stream);
+
+/* ---- diagnostics (bench.py; not on the product path) ----
+ * L2 -> SM delivery rate: `bytes` of buf (L2-sized, 16-byte aligned) read `passes` times by sms x ctas_per_sm CTAs,
+ * every CTA a different part, with the 16-byte no-allocate loads of the scoring kernels.  Time it with CUDA events:
+ * bytes x passes / time is the roof of the row-streaming scoring kernel. */
+int algp_probe_l2_read(const void* buf, int64_t bytes, int passes, int ctas_per_sm, void* sink, void* stream);
 
 /* ---- path enumeration feeding Agent.best_path (host code, no GPU work) ---------------------------
  * The expansion-tree search of FieldEnv.get_all_paths (env.py:197-310) on a planning graph given in CSR form:

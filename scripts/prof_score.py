@@ -46,7 +46,7 @@ def run(mode, tile, reps):
 if args.mode == "sweep":
     ts, best, ref = run("stream", 0, args.reps)
     print("stream          : min %.3f ms median %.3f ms  best %d" % (min(ts), float(np.median(ts)), best))
-    for tile in (0, 128, 256, 384, 512, 768, 1024, 2048, 4096):
+    for tile in (0, 256, 512, 768, 1024, 1280, 1536, 2048, 4096):
         ts, b, s = run("tiled", tile, args.reps)
         print("tiled chunk %4d: min %.3f ms median %.3f ms  best %d  max|dscore| %.2e" %
               (tile, min(ts), float(np.median(ts)), b, float((s - ref).abs().max().item())))

@@ -202,8 +202,8 @@ def test_score_sets_matches_oracle(kind, k):
 @pytest.mark.parametrize("kind", ["rbf", "matern"])
 @pytest.mark.parametrize("k,tile", [(1, 64), (5, 64), (8, 64), (8, 128), (8, 0), (3, 192)])
 def test_score_sets_tiled_matches_oracle_and_streaming(kind, k, tile):
-    """csrc/scoretile.cu (columns of Wt in L2-sized chunks, 36-entry DFMA Gram, thread-per-candidate finish) against the
-    oracle and the row-streaming kernel: several chunks per candidate, a column count that is not a multiple of the
+    """algp_score_sets_tiled (one launch of the k <= 8 kernel per column chunk, accumulator fragments parked in a work
+    buffer between launches) against the oracle and the single launch: several chunks per candidate, a column count that is not a multiple of the
     64-column step (appended columns), empty / duplicate / zero-increment slots and skip flags."""
     from algp_b200 import _lib
     X, th, hy, static, mobile, pi0, cov, ss, ms, rng = scoring_problem(kind, n_side=24, n_base=300, d_extra=(2 if k == 5 else 0))
