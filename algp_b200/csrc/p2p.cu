@@ -150,9 +150,16 @@ extern "C" int algp_argmax_exchange(const double* x, int64_t n, int64_t idx_offs
     argmax_stage1_kernel<<<blocks, 256, 0, st>>>(x, n, idx_offset, (ArgPair*)work);
     ALGP_LAUNCH_CHECK();
   }
-  int dev = 0, khz = 1965000;
+  // the clock-rate attribute is a slow driver query (~1 ms): read it once per device
+  static int khz_of[64] = {0};
+  int dev = 0;
   ALGP_CUDA(cudaGetDevice(&dev));
-  ALGP_CUDA(cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, dev));
+  int khz = (dev >= 0 && dev < 64) ? khz_of[dev] : 0;
+  if (khz == 0) {
+    khz = 1965000;
+    ALGP_CUDA(cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, dev));
+    if (dev >= 0 && dev < 64) khz_of[dev] = khz;
+  }
   const long long cycles = (long long)(timeout_ms * (double)khz);
   argmax_exchange_kernel<<<1, 32, 0, st>>>((const ArgPair*)work, blocks, (P2PMailbox* const*)peers_dev, rank, world,
                                             (unsigned long long)epoch, cycles, (long long*)out3);
