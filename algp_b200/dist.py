@@ -225,7 +225,7 @@ def sharded_mean_var(hyper, train_x, train_var, y0, ymean, xs, test_var=None, pr
     rank = dist.get_rank(group) if dist.is_initialized() else 0
     dev = xs.device
     N, M = train_x.shape[0], xs.shape[0]
-    reorder = precision in engine.I8_FAMILY and N >= engine.I8_REORDER_MIN
+    reorder = engine.uses_digits(precision, N) and N >= engine.I8_REORDER_MIN
     tperm = None
     if reorder:
         perm, lo, hi = engine.morton_perm(train_x)
@@ -263,8 +263,10 @@ def sharded_mean_var(hyper, train_x, train_var, y0, ymean, xs, test_var=None, pr
         mu_loc[:hi_r - lo_r] = engine.rowsum(part, 1.0, ymean, rows=hi_r - lo_r)
         if precision in engine.I8_FAMILY and f.Npad <= engine.I8_MAX_K:
             rn = f.whiten_norm_i8(Ks, nslices=engine.I8_FAST_SLICES if precision == "i8fast" else engine.I8_SLICES)
-        elif precision == "tf32":
+        elif precision == "tf32" and f.Npad <= engine.TF32_MAX_N:
             rn = f.whiten_norm_tf32(Ks)
+        elif precision == "tf32":
+            rn = f.whiten_norm_i8(Ks, nslices=engine.I8_FAST_SLICES)
         else:
             _, rn = f.whiten(Ks, want_V=False)
         tv = None if test_var is None else test_var[lo_r:hi_r].contiguous()

@@ -24,13 +24,26 @@ I8_FACTOR_BASE = 2048  # blocks of this many rows or fewer are factored by the D
 I8_FACTOR_MIN = 8192   # factor="auto": smallest padded N that takes the INT8 factorisation
 I8_REORDER_MIN = 8192  # precision "i8": from this many training points the posterior path sorts train / test points along a Z curve
 I8_MAX_K = 32768       # k extent the digit GEMM accepts (8 pairs x 2^15 x 2^12 < 2^31)
-I8_SLICES = 7          # digit planes of the INT8 variance path: 7 x 7 = 49 bits below each row's scale (8 = 56 bits)
+# digit planes of the INT8 variance path.  8 planes (56 bits below each row's scale) keep the variance within 1e-14 s^2
+# of the DMMA result, i.e. the north star's RELATIVE 1e-9 holds down to posterior variances of 1e-5 s^2; 7 planes
+# (49 bits, 6e-13 s^2) are 24 % faster on the variance step and meet the tier relative to the prior scale only
+I8_SLICES = 8
 # precision "i8fast": the same digit path with fewer planes, for the 1e-4 tier of the north star (what the TF32 mode
 # targets): 5 planes (35 bits) in the factorisation, 4 (28 bits) in the variance product -- more accurate than the
 # split-TF32 path (fp32 accumulation) and 3-4x faster at N = 16384
 I8_FAST_FACTOR_SLICES = 5
 I8_FAST_SLICES = 4
 I8_FAMILY = ("i8", "i8fast")
+# precision "tf32" names the 1e-4 tier on the tensor cores.  Up to this many (padded) training points it is the
+# split-TF32 tcgen05 kernel (fp32 accumulation: 4.7e-5 s^2 at N = 4096); beyond, fp32 accumulation of N cancelling terms
+# leaves the tier (1.7e-4 s^2 at N = 16384, measured), and the same tier is served by the 4-plane digit GEMM
+# (5e-6 s^2, and faster there)
+TF32_MAX_N = 8192
+
+
+def uses_digits(precision, n_train):
+    """True when the O(N^2 M) variance step of this precision runs as INT8 digit GEMMs (so Z-ordering pays)."""
+    return precision in I8_FAMILY or (precision == "tf32" and pad_to(n_train) > TF32_MAX_N)
 CONST = 0.5 * np.log(2 * np.pi * np.exp(1))        # utils.py:10
 KIND = {"rbf": 0, None: 0, "matern": 1}
 
@@ -184,10 +197,13 @@ def potrf_inv_i8(A, Linv, info, nslices=None, base=None):
 class GPFactor(object):
     """Cholesky factor and explicit inverse factor of the training covariance."""
 
-    def __init__(self, hyper, x, diag_add=None, diag_scalar=None, keep_linv=True, factor="dmma", factor_slices=None):
+    def __init__(self, hyper, x, diag_add=None, diag_scalar=None, keep_linv=True, factor="dmma", factor_slices=None,
+                 buffers=None):
         """factor="dmma": algp_potrf + algp_trtri (fp64 tensor cores); factor="i8": the recursive factorisation
         whose products run as exact INT8 digit GEMMs (same fp64 tier, faster from N ~ 8192 up); "auto" picks.
-        factor_slices: digit planes of the "i8" factorisation (default I8_FACTOR_SLICES = 8, fp64-grade)."""
+        factor_slices: digit planes of the "i8" factorisation (default I8_FACTOR_SLICES = 8, fp64-grade).
+        buffers: dict of preallocated device buffers {"L", "Linv" [Npad x Npad], "info" int32[1], "trtri" work} that
+        a caller re-factorising the same-sized matrix many times (GPR.fit) keeps across calls."""
         if factor not in ("dmma", "i8", "auto"):
             raise ValueError("factor must be 'dmma', 'i8' or 'auto'")
         self.hyper = hyper
@@ -195,19 +211,27 @@ class GPFactor(object):
         self.N = x.shape[0]
         self.Npad = max(BLK, pad_to(self.N))
         dev = x.device
+        buffers = buffers if buffers is not None else {}
         if diag_scalar is None:
             diag_scalar = hyper.noise                       # add_likelihood_var=True, models.py:179-180
-        self.L, _ = kbuild(hyper, x, None, self.Npad, self.Npad, diag_add, diag_scalar, True)
-        self.Linv = torch.empty((self.Npad, self.Npad), dtype=torch.float64, device=dev)
-        self.info = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.L, _ = kbuild(hyper, x, None, self.Npad, self.Npad, diag_add, diag_scalar, True, out=buffers.get("L"))
+        self.Linv = buffers.get("Linv")
+        if self.Linv is None:
+            self.Linv = torch.empty((self.Npad, self.Npad), dtype=torch.float64, device=dev)
+        self.info = buffers.get("info")
+        if self.info is None:
+            self.info = torch.zeros(1, dtype=torch.int32, device=dev)
+        else:
+            self.info.zero_()
         if factor == "auto":
             factor = "i8" if I8_FACTOR_MIN <= self.Npad <= 2 * I8_MAX_K else "dmma"
         if factor == "i8" and self.Npad > I8_FACTOR_BASE:
             potrf_inv_i8(self.L, self.Linv, self.info, nslices=factor_slices)
         else:
             call("algp_potrf", ptr(self.L), self.Npad, self.Npad, ptr(self.Linv), self.Npad, ptr(self.info), stream())
-            nwork = _lib.lib.algp_trtri_work_doubles(self.Npad)
-            work = torch.empty(max(2, nwork), dtype=torch.float64, device=dev)
+            work = buffers.get("trtri")
+            if work is None:
+                work = torch.empty(max(2, _lib.lib.algp_trtri_work_doubles(self.Npad)), dtype=torch.float64, device=dev)
             call("algp_trtri", ptr(self.L), self.Npad, self.Npad, ptr(self.Linv), self.Npad, ptr(work), 1, stream())
             del work
         self._ld2 = None
@@ -298,8 +322,9 @@ class GPFactor(object):
             self._linv_i8 = cache = (nslices,) + self.split_i8(self.Linv, nslices, 64, want_mask=True)
         return cache[1], cache[2], cache[3]
 
-    def whiten_norm_i8(self, Ks, nslices=I8_SLICES, use_masks=True):
+    def whiten_norm_i8(self, Ks, nslices=None, use_masks=True):
         """Squared row norms of V = Ks L^-T per 64-column tile through exact INT8 digit GEMMs (fp64 tier)."""
+        nslices = I8_SLICES if nslices is None else nslices
         lt, ls, lm = self._linv_digits(nslices)
         kt, ks, km = self.split_i8(Ks, nslices, 128, want_mask=True)
         Mpad = Ks.shape[0]
@@ -320,7 +345,8 @@ class GPFactor(object):
 
     def mean_var(self, xs, y0, ymean, test_var=None, want_var=True, max_rows=65536, precision="fp64"):
         """Posterior mean (and latent variance) at xs: utils.py:300-308 without the inverse.
-        precision="tf32" runs the O(N^2 M) variance step on the tcgen05 tensor cores (1e-4 tier);
+        precision="tf32" runs the O(N^2 M) variance step on the tcgen05 tensor cores at the 1e-4 tier (split-TF32 MMAs up
+        to TF32_MAX_N training points, the 4-plane digit GEMM beyond);
         precision="i8" runs it as exact INT8 digit GEMMs on the same tensor cores (fp64 tier), "i8fast" as the same
         digit GEMMs with 4 planes (1e-4 tier)."""
         if precision not in ("fp64", "tf32", "i8", "i8fast"):
@@ -336,8 +362,10 @@ class GPFactor(object):
             Ks, part = self.cross(xs[lo:hi], alpha)
             mu[lo:hi] = rowsum(part, 1.0, ymean, rows=hi - lo)
             if want_var:
-                if precision == "tf32":
+                if precision == "tf32" and self.Npad <= TF32_MAX_N:
                     rn = self.whiten_norm_tf32(Ks)
+                elif precision == "tf32":
+                    rn = self.whiten_norm_i8(Ks, nslices=I8_FAST_SLICES)      # same tier, see TF32_MAX_N
                 elif precision == "i8":
                     rn = self.whiten_norm_i8(Ks)
                 elif precision == "i8fast":

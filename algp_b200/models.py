@@ -113,7 +113,8 @@ class GPR(object):
         self.dtype = np.float64      # np.float32 reproduces the reference's float32 kernel matrix (utils.py:19)
         # O(N^3) / O(N^2 M) arithmetic: "fp64" = DMMA; "i8" = exact INT8 digit GEMMs on tcgen05 for the variance and,
         # from N = 8192, the factorisation (same fp64 tier, ~7x faster at N = 16384); "i8fast" = the same digit path with
-        # 5 / 4 planes (1e-4 tier, faster and more accurate than "tf32"); "tf32" = split-TF32 variance on tcgen05 (1e-4 tier)
+        # 5 / 4 planes (1e-4 tier); "tf32" = the 1e-4 tier with an fp64 factor: split-TF32 variance on tcgen05 up to
+        # engine.TF32_MAX_N training points, the 4-plane digit GEMM beyond (where fp32 accumulation leaves the tier)
         self.precision = "fp64"
         self._cache = {}
 
@@ -175,9 +176,12 @@ class GPR(object):
         p_os = params['kernel_covar_module.log_outputscale']
         p_nz = params['likelihood.log_noise']
         initial_ll = final_ll = None
+        # x, y, var and the N x N work buffers stay on the device for the whole Adam loop
+        from .mll import MLLWorkspace
+        ws = MLLWorkspace(self._train_x, self._zero_mean_train_y, self._train_var)
         for i in range(self.max_iter):
             self.optimizer.zero_grad()
-            loss, g = self.loss_and_grad()
+            loss, g = ws.loss_and_grad(self.hyper())
             d = p_ls.numel()
             p_ls.grad = torch.tensor(g[:d], dtype=torch.float64).view_as(p_ls)
             p_os.grad = torch.tensor(g[d:d + 1], dtype=torch.float64).view_as(p_os)
@@ -190,6 +194,7 @@ class GPR(object):
                 initial_ll = -loss
             if i == self.max_iter - 1:
                 final_ll = -loss
+        del ws
         self._cache.clear()
         if initial_ll is not None:
             print('Initial LogLikelihood {:.3f} Final LogLikelihood {:.3f}'.format(initial_ll, final_ll))

@@ -132,7 +132,7 @@ def _posterior(gp, hyper, train_x, train_y, test_x, train_var, test_var, want_va
     prec = getattr(gp, "precision", "fp64")
     # the mean / variance path does not depend on the order of the points: in INT8 digit mode both sets are sorted
     # along a Z curve so that far-apart (test tile, train chunk) pairs become all-zero digit tiles the GEMM skips
-    reorder = (not want_cov) and prec in engine.I8_FAMILY and len(train_y) >= engine.I8_REORDER_MIN
+    reorder = (not want_cov) and engine.uses_digits(prec, len(train_y)) and len(train_y) >= engine.I8_REORDER_MIN
     f = _factor_for(gp, hyper, train_x, train_var, reorder=reorder)
     dev = f.L.device
     xs = engine.to_dev(test_x, device=dev)
