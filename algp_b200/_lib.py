@@ -47,6 +47,7 @@ SIGNATURES = {
     "algp_mll_grad_work_doubles": (_i64, [_i64]),
     "algp_colsumsq_lower": (C.c_int, [_p, _i64, _i64, _p, _p, _p]),
     "algp_colsumsq_work_doubles": (_i64, [_i64]),
+    "algp_inv_rank1_update": (C.c_int, [_p, _i64, _p, _i64, _p, _i32, _i64, _i32, _f64, _p, _p, _p]),
     "algp_mi_terms": (C.c_int, [_p, _i64, _p, _p, _i64, _p, _i32, _i64, _p, _f64, _f64, _p, _p]),
     "algp_prefix_reduce": (C.c_int, [_p, _i64, _i64, _p, _p, _p, _i32, _p, _p]),
     "algp_score_sets": (C.c_int, [_p, _i64, _i64, _p, _i32, _p, _f64, _i32, _f64, _p, _p, _p, _f64, _p,

@@ -119,15 +119,26 @@ class HotPath(object):
         re-solves the GP for each prefix; here one factorisation of the longest prefix serves them all."""
         from .utils import predictive_distribution_prefixes
         total = test_every * num_runs
-        inds = np.array(self.collected['ind'][:total])
+        inds = np.array(self.collected['ind'][:total], dtype=np.int64)
         valid = inds != -1
         x = self.env.X[inds[valid]]
-        var = np.array(self.collected['std'])[:total][valid] ** 2
-        y = np.array(self.collected['y'])[:total][valid].astype(np.float64)
-        # prefix c of the raw list = the first cumsum(valid)[c-1] valid readings
-        nvalid = np.cumsum(valid)
-        counts = [int(nvalid[min(c, len(nvalid)) - 1]) for c in range(test_every, total + 1, test_every)]
-        res = predictive_distribution_prefixes(self.gp, x, y, self.env.test_X, var, counts, return_mi=True, return_cov=True)
+        var = np.array(self.collected['std'], dtype=np.float64)[:total][valid] ** 2
+        y = np.array(self.collected['y'], dtype=object)[:total][valid].astype(np.float64)
+        # prefix c of the raw list = the first cumsum(valid)[c-1] valid readings (0 while the list is empty or holds
+        # only -1 gaps; the same count again once the list is exhausted)
+        nvalid = np.concatenate([[0], np.cumsum(valid)])
+        counts = [int(nvalid[min(c, len(inds))]) for c in range(test_every, total + 1, test_every)]
+        distinct = sorted(set(c for c in counts if c > 0))
+        by_count = {}
+        if distinct:
+            solved = predictive_distribution_prefixes(self.gp, x, y, self.env.test_X, var, distinct, return_mi=True, return_cov=True)
+            by_count = dict(zip(distinct, solved))
+        if 0 in counts:
+            # no reading yet: the reference's predictive_distribution on an empty training set gives mean(y of nothing)
+            # = NaN for the mean, the prior covariance and zero mutual information (utils.py:294-314)
+            prior = self.gp.cov_mat(self.env.test_X)
+            by_count[0] = (np.full(len(self.env.test_X), np.nan), prior, 0.0)
+        res = [by_count[c] for c in counts]
         all_error = [float(np.mean(np.abs(self.env.test_Y - mu))) for mu, _, _ in res]      # utils.compute_mae
         all_mi = [mi for _, _, mi in res]
         all_var = [float(np.diag(cov).mean()) for _, cov, _ in res]
@@ -225,12 +236,15 @@ class HotPath(object):
         return picks
 
     def _greedy_mi(self, state, pi, num_samples, d):
-        """Mutual-information greedy (agent.py:330-339): the entropy term comes from the posterior state,
-        the two complement terms from an MIContext that is re-factored after every pick."""
+        """Mutual-information greedy (agent.py:330-339): the entropy term comes from the posterior state, the two
+        complement terms from ONE MIContext (two n-scale factorizations) kept current across the picks by rank-1
+        updates (MIContext.commit)."""
         picks = []
         pair = torch.empty(2, dtype=torch.int64, device=state.X.device)
+        ctx = None
         for _ in range(num_samples):
-            ctx = engine.MIContext(state.hyper, state.X, pi)
+            if ctx is None:
+                ctx = engine.MIContext(state.hyper, state.X, pi)
             ent_a = state.H_base_dev + state.greedy_utilities(d)
             ut = ctx.greedy_utilities(ent_a, self.static_std, self.mobile_std).contiguous()
             state.argmax(ut, 0, out=pair)
@@ -242,6 +256,10 @@ class HotPath(object):
             ctx.check()
             picks.append(j)
             pi[j] += d
+            # the two complement factorizations follow the pick by rank-1 updates of their inverse diagonals and
+            # log-determinants; a context that has used up its correction slots is rebuilt
+            if not ctx.commit(j, self.static_std, self.mobile_std):
+                ctx = None
         return picks
 
     def best_path(self, paths_mobile_indices, static_indices):

@@ -21,11 +21,10 @@
 // ---------------------------------------------------------------------------
 template <int ALAY, int BLAY, int TM, int TN, bool SUBC, int NSTAGE = G_STAGES>
 static int gemm_launch_t(GemmArgs a, int batch, cudaStream_t st) {
-  static bool configured = false;
-  if (!configured) {
+  static AlgpPerDevice configured;
+  if (configured.raise(1)) {
     ALGP_CUDA(cudaFuncSetAttribute(gemm_f64_kernel<ALAY, BLAY, TM, TN, SUBC, NSTAGE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    G_SMEM_BYTES(TM, TN, NSTAGE)));
-    configured = true;
   }
   a.MT *= 128 / TM;                                  // callers count 128-tiles
   a.NT *= 128 / TN;
@@ -368,10 +367,9 @@ extern "C" int algp_set_potf2_rank(int r) {
 }
 
 static int potf2inv_launch(double* A, int64_t ld, double* Linv, int64_t ldi, int j0, int* info, cudaStream_t st) {
-  static bool configured = false;
-  if (!configured) {
+  static AlgpPerDevice configured;
+  if (configured.raise(1)) {
     ALGP_CUDA(cudaFuncSetAttribute(potf2inv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, P2_SMEM_BYTES));
-    configured = true;
   }
   if (g_potf2_rank == 4) {
     potf2inv_rank_kernel<4><<<1, 256, PR_SMEM_DOUBLES(4) * 8, st>>>(A, ld, Linv, ldi, j0, info);

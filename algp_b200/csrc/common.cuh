@@ -25,6 +25,24 @@ extern "C" int algp_set_cuda_error(cudaError_t e, const char* file, int line);
 
 #define ALGP_LAUNCH_CHECK() ALGP_CUDA(cudaGetLastError())
 
+// Per-device bookkeeping for cudaFuncSetAttribute (the attribute belongs to one device context, so a process-wide
+// "already configured" flag is wrong as soon as one process drives two GPUs).  Atomic, so concurrent host threads at
+// worst set the attribute twice.
+#include <atomic>
+#define ALGP_MAX_DEVICES 64
+struct AlgpPerDevice {
+  std::atomic<size_t> v[ALGP_MAX_DEVICES];
+  // true if `want` exceeds what this device was configured with so far (and records it)
+  bool raise(size_t want) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= ALGP_MAX_DEVICES) return true;
+    size_t cur = v[dev].load(std::memory_order_relaxed);
+    while (want > cur)
+      if (v[dev].compare_exchange_weak(cur, want, std::memory_order_relaxed)) return true;
+    return false;
+  }
+};
+
 struct KernelParams {
   int kind;                    // 0 = RBF, 1 = Matern nu=1.5
   int d;

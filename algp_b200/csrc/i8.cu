@@ -491,10 +491,9 @@ int launch_split(const double* src, int64_t rows, int64_t cols, int64_t ld, int 
 template <int S, int MODE>
 int launch_gemm(const I8Gemm& a, cudaStream_t st) {
   using C = I8Cfg<S>;
-  static bool configured = false;
-  if (!configured) {
+  static AlgpPerDevice configured;
+  if (configured.raise(1)) {
     ALGP_CUDA(cudaFuncSetAttribute(gemm_i8_kernel<S, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
-    configured = true;
   }
   const int groups = (a.MT + 15) / 16;
   const int64_t grid = (int64_t)groups * 16 * a.NT;

@@ -50,6 +50,55 @@ extern "C" int algp_colsumsq_lower(const double* M, int64_t n, int64_t ld, doubl
   return ALGP_OK;
 }
 
+// ---------------------------------------------------------------------------
+// Rank-1 maintenance of diag(A^-1) and logdet A across greedy picks: the mutual-information
+// criterion needs diag((Sigma_AbarAbar)^-1) and diag((Sigma + D)^-1); a pick changes Sigma_AbarAbar by deleting one
+// row / column and Sigma + D by one diagonal entry, so both inverses change by a rank-1 term instead of being
+// re-factorised (reference agent.py:330-339 recomputes two n x n slogdets per CANDIDATE; round 1 re-factorised per pick).
+//   col          column j of the ORIGINAL inverse (A0^-1 e_j, two triangular gemv passes over the inverse factor)
+//   U, coef, t   the t earlier corrections: current inverse = A0^-1 - sum_s coef[s] U[s] U[s]^T
+//   mode 0       delete row / column j:       inv' = inv - c c^T / c_j,            logdet += log c_j
+//   mode 1       A += delta e_j e_j^T:        inv' = inv - g c c^T, g = delta / (1 + delta c_j), logdet += log1p(delta c_j)
+// with c = column j of the CURRENT inverse.  Updates diag in place, appends U[t] = c, coef[t] = g.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) inv_rank1_update_kernel(const double* __restrict__ col, int64_t n, double* __restrict__ U,
+                                                               int64_t ldu, double* __restrict__ coef, int t, int64_t j, int mode,
+                                                               double delta, double* __restrict__ diag, double* __restrict__ logdet) {
+  __shared__ double w[64];            // coef[s] * U[s][j]
+  __shared__ double cj_s;
+  if (threadIdx.x < t) w[threadIdx.x] = coef[threadIdx.x] * U[(int64_t)threadIdx.x * ldu + j];
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double cj = col[j];
+    for (int s = 0; s < t; ++s) cj -= w[s] * U[(int64_t)s * ldu + j];
+    cj_s = cj;
+  }
+  __syncthreads();
+  const double cj = cj_s;
+  const double g = mode == 0 ? 1.0 / cj : delta / (1.0 + delta * cj);
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    double c = col[i];
+    for (int s = 0; s < t; ++s) c -= w[s] * U[(int64_t)s * ldu + i];
+    U[(int64_t)t * ldu + i] = c;
+    diag[i] -= g * c * c;
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    // coef[t] is only read by LATER launches (slots s < t here), so writing it now does not race
+    coef[t] = g;
+    logdet[0] += mode == 0 ? log(cj) : log1p(delta * cj);
+  }
+}
+
+extern "C" int algp_inv_rank1_update(const double* col, int64_t n, double* U, int64_t ldu, double* coef, int t, int64_t j,
+                                     int mode, double delta, double* diag, double* logdet, void* stream) {
+  if (!col || !U || !coef || !diag || !logdet || n < 1 || ldu < n || t < 0 || t >= 64 || j < 0 || j >= n || (mode != 0 && mode != 1))
+    return ALGP_ERR_INVALID;
+  const unsigned grid = (unsigned)((n + 255) / 256 < 592 ? (n + 255) / 256 : 592);
+  inv_rank1_update_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(col, n, U, ldu, coef, t, j, mode, delta, diag, logdet);
+  ALGP_LAUNCH_CHECK();
+  return ALGP_OK;
+}
+
 struct MiArgs {
   const double* inv2; int64_t ld2;      // A2^-1 (lower triangle valid), indexed by position in Abar
   const int32_t* pos2;                  // [n]: position of a location in Abar, -1 if sampled
@@ -163,7 +212,9 @@ extern "C" int algp_mi_terms_large(const double* inv2, int64_t ld2, const int32_
     return ALGP_ERR_INVALID;
   if (B == 0) return ALGP_OK;
   const bool large = k > MI_MAXK;
-  if (large && (!work || work_doubles < algp_mi_terms_large_work_doubles(k, B))) return ALGP_ERR_INVALID;
+  // the scratch may be smaller than the preferred size: fewer CTAs run (at least one candidate's k x (k+1) matrix)
+  const int64_t per_cta = (int64_t)k * ((int64_t)k + 1);
+  if (large && (!work || work_doubles < per_cta)) return ALGP_ERR_INVALID;
   MiArgs a;
   a.inv2 = inv2; a.ld2 = ld2; a.pos2 = pos2; a.inv3 = inv3; a.ld3 = ld3; a.idx = idx; a.k = k; a.B = B; a.skip = skip;
   a.delta_new = delta_new; a.delta_old = delta_old; a.out = out3; a.work = work;
@@ -172,18 +223,17 @@ extern "C" int algp_mi_terms_large(const double* inv2, int64_t ld2, const int32_
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   int grid = (int)(B < (int64_t)sms * 2 ? B : (int64_t)sms * 2);
+  if (large && work_doubles / per_cta < grid) grid = (int)(work_doubles / per_cta);
   if (large) {
-    static size_t configured = 0;
-    if (smem > configured) {
+    static AlgpPerDevice configured;
+    if (configured.raise(smem)) {
       ALGP_CUDA(cudaFuncSetAttribute(mi_terms_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      configured = smem;
     }
     mi_terms_kernel<true><<<grid, 256, smem, (cudaStream_t)stream>>>(a);
   } else {
-    static size_t configured = 0;
-    if (smem > configured) {
+    static AlgpPerDevice configured;
+    if (configured.raise(smem)) {
       ALGP_CUDA(cudaFuncSetAttribute(mi_terms_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      configured = smem;
     }
     mi_terms_kernel<false><<<grid, 256, smem, (cudaStream_t)stream>>>(a);
   }

@@ -332,7 +332,9 @@ extern "C" int algp_score_sets_large(const double* Wt, int64_t ldw, int64_t ncol
                                      int64_t work_doubles, void* stream) {
   if (!Wt || !X || !pi0 || !idx || !scores || k < 1 || k > SG_MAXK_LARGE || B < 0 || ncols < 0) return ALGP_ERR_INVALID;
   if ((ldw & 3) || ((uintptr_t)Wt & 31)) return ALGP_ERR_INVALID;       // 256-bit row loads
-  if (k > SG_MAXK && B > 0 && (!work || work_doubles < algp_score_sets_large_work_doubles(k, B))) return ALGP_ERR_INVALID;
+  // k > 128: the scratch may be smaller than the preferred size -- fewer CTAs run (at least one kk x (kk+1) matrix)
+  const int64_t kk_l = (k + 7) / 8 * 8, per_cta_l = kk_l * (kk_l + 1);
+  if (k > SG_MAXK && B > 0 && (!work || work_doubles < per_cta_l)) return ALGP_ERR_INVALID;
   if (work_doubles < 0 && (k > 8 || (-work_doubles) % 32 != 0)) return ALGP_ERR_INVALID;   // chunked k <= 8 (algp_score_sets_tiled)
   ScoreArgs a;
   a.work = work;
@@ -372,22 +374,21 @@ extern "C" int algp_score_sets_large(const double* Wt, int64_t ldw, int64_t ncol
   } else if (k <= SG_MAXK) {
     const int kp = (k + 7) / 8, kk = kp * 8;
     size_t smem = ((size_t)kk * (kk + 1) + kk + (size_t)kk * d) * 8 + (size_t)kk * 4 + 16;
-    static size_t configured = 0;
-    if (smem > configured) {
+    static AlgpPerDevice configured;
+    if (configured.raise(smem)) {
       ALGP_CUDA(cudaFuncSetAttribute(score_sets_generic_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      configured = smem;
     }
     int grid = (int)(B < (int64_t)sms * 2 ? B : (int64_t)sms * 2);
     score_sets_generic_kernel<false><<<grid, 256, smem, st>>>(a);
   } else {
     const int kp = (k + 7) / 8, kk = kp * 8;
     size_t smem = ((size_t)kk + (size_t)kk * d) * 8 + (size_t)kk * 4 + 16;
-    static size_t configured = 0;
-    if (smem > configured) {
+    static AlgpPerDevice configured;
+    if (configured.raise(smem)) {
       ALGP_CUDA(cudaFuncSetAttribute(score_sets_generic_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      configured = smem;
     }
     int grid = (int)(B < (int64_t)sms * 2 ? B : (int64_t)sms * 2);
+    if (work_doubles / per_cta_l < grid) grid = (int)(work_doubles / per_cta_l);
     score_sets_generic_kernel<true><<<grid, 256, smem, st>>>(a);
   }
   ALGP_LAUNCH_CHECK();
@@ -765,10 +766,9 @@ extern "C" int algp_append_block(double* Wt, int64_t ldw, int64_t ncols, const d
   append_block_eliminate_kernel<<<1, 32, 0, st>>>(a);
   ALGP_LAUNCH_CHECK();
   const size_t smem = (size_t)(AB_K * AB_CH + AB_K * AB_K + AB_K + AB_K * ALGP_MAX_D + 8 * AB_LB * AB_K) * 8 + AB_K * 8;
-  static bool configured = false;
-  if (!configured) {
+  static AlgpPerDevice configured;
+  if (configured.raise(1)) {
     ALGP_CUDA(cudaFuncSetAttribute(append_block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = true;
   }
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);

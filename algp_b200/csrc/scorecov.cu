@@ -194,11 +194,10 @@ extern "C" int algp_score_sets_cov(const double* P, int64_t ldp, const double* p
     score_cov_k8_kernel<<<(unsigned)((B + 127) / 128), 128, 0, st>>>(a);
   } else {
     const size_t smem = (size_t)k * (k + 1) * sizeof(double) + (size_t)k * sizeof(double) + (size_t)k * sizeof(int) + 16;
-    static bool configured = false;
-    if (!configured) {
+    static AlgpPerDevice configured;
+    if (configured.raise(1)) {
       ALGP_CUDA(cudaFuncSetAttribute(score_cov_generic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      (int)((size_t)SC_MAXK * (SC_MAXK + 1) * 8 + SC_MAXK * 12 + 16)));
-      configured = true;
     }
     int dev = 0, sms = 148;
     ALGP_CUDA(cudaGetDevice(&dev));

@@ -274,10 +274,9 @@ extern "C" int algp_trmm_rt_tf32(const float* Khi, const float* Klo, int64_t mpa
       (ldk & 3) || (ldl & 3))
     return ALGP_ERR_INVALID;
   if (mpad == 0 || npad == 0) return ALGP_OK;
-  static bool configured = false;
-  if (!configured) {
+  static AlgpPerDevice configured;
+  if (configured.raise(1)) {
     ALGP_CUDA(cudaFuncSetAttribute(trmm_tf32x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, T3_SMEM_BYTES));
-    configured = true;
   }
   if (((uintptr_t)Khi | (uintptr_t)Klo | (uintptr_t)Lhi | (uintptr_t)Llo) & 15) return ALGP_ERR_INVALID;
   CUtensorMap ta_hi, ta_lo, tb_hi, tb_lo;

@@ -378,6 +378,29 @@ class GPFactor(object):
         return mu, var
 
 
+SCRATCH_FREE_FRACTION = 0.25      # long-path scratch (k > 128) takes at most this share of the free device memory
+
+
+def scratch_for(owner, attr, preferred, minimum, device):
+    """(doubles, tensor): a scratch cached on `owner`, `preferred` doubles if a quarter of the free memory allows,
+    never less than `minimum` (one candidate's matrix; the kernels then run fewer CTAs)."""
+    if preferred <= 0:
+        return 0, None
+    free, _ = torch.cuda.mem_get_info(device)
+    cached = getattr(owner, attr, None)
+    have = 0 if cached is None else cached.numel()
+    budget = int(SCRATCH_FREE_FRACTION * (free + 8 * have)) // 8
+    want = max(int(minimum), min(int(preferred), budget))
+    if 8 * want > free + 8 * have:
+        raise MemoryError("scoring paths of this length needs %.1f GB of scratch, %.1f GB are free" % (8e-9 * want, 1e-9 * free))
+    if cached is None or cached.numel() < want:
+        cached = None
+        setattr(owner, attr, None)
+        cached = torch.empty(want, dtype=torch.float64, device=device)
+        setattr(owner, attr, cached)
+    return cached.numel(), cached
+
+
 def gemm_nt(A, B, C, alpha, beta, lower_only=False):
     call("algp_gemm_nt", ptr(A), A.stride(0), ptr(B), B.stride(0), ptr(C), C.stride(0),
          C.shape[0], C.shape[1], A.shape[1], float(alpha), float(beta), int(lower_only), stream())
@@ -557,8 +580,8 @@ class PosteriorState(object):
             return out
         if k > MAX_SET_SMEM:
             # long paths: the k x k matrix of a candidate lives in a global scratch instead of shared memory
-            nwork = _lib.lib.algp_score_sets_large_work_doubles(k, B)
-            work = torch.empty(max(1, nwork), dtype=torch.float64, device=idx.device)
+            kk = pad_to(k, 8)
+            nwork, work = scratch_for(self, "_largework", _lib.lib.algp_score_sets_large_work_doubles(k, B), kk * (kk + 1), idx.device)
             call("algp_score_sets_large", ptr(self.Wt), self.ldw, self.ncols, ptr(self.X), self.hyper.d, ls_p,
                  self.hyper.log_os, self.hyper.kind, self.hyper.noise, ptr(self.pi), ptr(idx), ptr(delta),
                  float(delta_scalar), ptr(skip), k, B, float(hb), ptr(out), ptr(work), nwork, stream())
@@ -661,7 +684,7 @@ class MIContext(object):
         if self.n_abar:
             xa = X.index_select(0, to_dev(abar, dtype=torch.int64, device=dev)).contiguous()
             self.f2 = GPFactor(hyper, xa, diag_add=None, diag_scalar=hyper.noise)        # cov_matrix[~S][:, ~S]
-            self.ld2 = self.f2.logdet_quad()[0:1]
+            self.ld2 = self.f2.logdet_quad()[0:1].clone()
             self.diag2 = self._inv_diag(self.f2)[:self.n_abar]
             if full_inverse:
                 self.inv2 = self._inverse(self.f2)
@@ -671,7 +694,7 @@ class MIContext(object):
             self.diag2 = torch.ones(1, dtype=torch.float64, device=dev)
         var_all = np.where(sampled, 1.0 / np.where(sampled, pi, 1.0), 0.0)               # agent.py:334-337
         self.f3 = GPFactor(hyper, X, diag_add=to_dev(var_all, device=dev), diag_scalar=hyper.noise)
-        self.ld3 = self.f3.logdet_quad()[0:1]
+        self.ld3 = self.f3.logdet_quad()[0:1].clone()
         self.diag3 = self._inv_diag(self.f3)[:self.n]
         if full_inverse:
             self.inv3 = self._inverse(self.f3)
@@ -694,6 +717,48 @@ class MIContext(object):
             self.f2.check()
         self.f3.check()
 
+    MAX_COMMITS = 48          # rank-1 corrections kept per context (algp_inv_rank1_update accepts t < 64)
+
+    def _column(self, f, j):
+        """Column j of the ORIGINAL inverse of a factored matrix: A0^-1 e_j (two triangular gemv passes)."""
+        e = torch.zeros(f.N, dtype=torch.float64, device=f.L.device)
+        e[j] = 1.0
+        return f.solve(e)[0]
+
+    def commit(self, j, static_std, mobile_std):
+        """A static reading is taken at location j (a greedy pick, agent.py:349-354): maintain diag(A2^-1), logdet A2
+        (row / column j leaves Sigma_AbarAbar if j was unsampled) and diag(A3^-1), logdet A3 (the noise variance of j
+        changes) by rank-1 updates instead of re-factorising.  Returns False when the context is full (rebuild it)."""
+        if getattr(self, "_t3", 0) >= self.MAX_COMMITS or getattr(self, "_t2", 0) >= self.MAX_COMMITS:
+            return False
+        dev = self.f3.L.device
+        ss2, ms2 = static_std ** 2, mobile_std ** 2
+        vboth = 1.0 / (1.0 / ss2 + 1.0 / ms2)
+        if getattr(self, "_U3", None) is None:
+            self._t3 = self._t2 = 0
+            self._U3 = torch.empty((self.MAX_COMMITS, self.f3.Npad), dtype=torch.float64, device=dev)
+            self._c3 = torch.zeros(64, dtype=torch.float64, device=dev)
+            if self.f2 is not None:
+                self._U2 = torch.empty((self.MAX_COMMITS, self.f2.Npad), dtype=torch.float64, device=dev)
+                self._c2 = torch.zeros(64, dtype=torch.float64, device=dev)
+            self._pos2_host = self.pos2.cpu().numpy()
+        p = int(self._pos2_host[j])
+        was_new = p >= 0
+        col3 = self._column(self.f3, j)
+        call("algp_inv_rank1_update", ptr(col3), self.n, ptr(self._U3), self._U3.stride(0), ptr(self._c3), self._t3, int(j), 1,
+             float(ss2 if was_new else vboth - ms2), ptr(self.diag3), ptr(self.ld3), stream())
+        self._t3 += 1
+        if was_new:
+            col2 = self._column(self.f2, p)
+            call("algp_inv_rank1_update", ptr(col2), self.f2.N, ptr(self._U2), self._U2.stride(0), ptr(self._c2), self._t2, p, 0,
+                 0.0, ptr(self.diag2), ptr(self.ld2), stream())
+            self._t2 += 1
+            self._pos2_host[j] = -1
+            self.pos2[j] = -1
+            self.n_abar -= 1
+        self.inv2 = self.inv3 = None          # full inverses (path scoring) are not maintained
+        return True
+
     def greedy_utilities(self, ent_a, static_std, mobile_std):
         """ut_i = ent_a_i + H(Sigma_{Abar \\ i}) - H(Sigma + D + Delta_i e_i e_i^T) for every location
         (agent.py:330-339); ent_a is -inf where the location is already static."""
@@ -713,8 +778,7 @@ class MIContext(object):
         vboth = 1.0 / (1.0 / ss2 + 1.0 / ms2)
         B, k = idx.shape
         out = torch.empty((B, 3), dtype=torch.float64, device=idx.device)
-        nwork = _lib.lib.algp_mi_terms_large_work_doubles(k, B)
-        work = torch.empty(max(1, nwork), dtype=torch.float64, device=idx.device)
+        nwork, work = scratch_for(self, "_largework", _lib.lib.algp_mi_terms_large_work_doubles(k, B), k * (k + 1), idx.device)
         call("algp_mi_terms_large", ptr(self.inv2), self.inv2.stride(0) if self.inv2 is not None else 0, ptr(self.pos2),
              ptr(self.inv3), self.inv3.stride(0), ptr(idx), k, B, ptr(skip), float(ms2), float(vboth - ss2), ptr(out),
              ptr(work), nwork, stream())

@@ -700,6 +700,56 @@ def fit_loop_bench(torch, engine, no_cpu=False):
     return out
 
 
+def mi_greedy_bench(torch, engine, picks=4):
+    """Mutual-information greedy at scale (agent.py:330-339): 128 x 128 field (n = 16384), 4096 static
+    samples, `picks` MI picks.  The two complement factorizations (12288^2 and 16384^2) are built ONCE per greedy call
+    and follow every pick by rank-1 updates of their inverse diagonals and log-dets (MIContext.commit); round 1
+    re-factorised both per pick, which is what `ms_context_build` costs."""
+    grid, _ = field_grid()
+    n = len(grid)
+    rng = np.random.default_rng(1)
+    base = np.sort(rng.choice(n, N_BASE, replace=False))
+    hyper = engine.Hyper(np.log([FIELD / 16.0] * 2), 0.0, np.log(1e-2), "rbf")
+    pi = np.zeros(n)
+    pi[base] = 1.0 / STATIC_STD ** 2
+    Xd = engine.to_dev(grid)
+    state = engine.PosteriorState(hyper, Xd, base, pi, is_static=pi > 0, capacity=picks + 16, cov_mode="never")
+    d = 1.0 / STATIC_STD ** 2
+    ev = lambda: torch.cuda.Event(enable_timing=True)
+    engine.MIContext(hyper, Xd, pi).check()                          # warm-up
+    e0, e1 = ev(), ev()
+    e0.record()
+    ctx = engine.MIContext(hyper, Xd, pi)
+    e1.record()
+    torch.cuda.synchronize()
+    build_ms = e0.elapsed_time(e1)
+    pair = torch.empty(2, dtype=torch.int64, device=Xd.device)
+    chosen, per_pick = [], []
+    for _ in range(picks):
+        a, b = ev(), ev()
+        a.record()
+        ent_a = state.H_base_dev + state.greedy_utilities(d)
+        ut = ctx.greedy_utilities(ent_a, STATIC_STD, MOBILE_STD).contiguous()
+        state.argmax(ut, 0, out=pair)
+        state.append(pair[1:2], d, mark_static=True)
+        j = int(pair[1].item())
+        state.H_base_dev.copy_(ent_a[j:j + 1])
+        state._H_base = None
+        ctx.commit(j, STATIC_STD, MOBILE_STD)
+        b.record()
+        torch.cuda.synchronize()
+        per_pick.append(a.elapsed_time(b))
+        chosen.append(j)
+        pi[j] += d
+    # the maintained quantities against a context factored from scratch on the final flags
+    fresh = engine.MIContext(hyper, Xd, pi)
+    err = {"logdet_unsampled": float((ctx.ld2 - fresh.ld2).abs().item()), "logdet_all": float((ctx.ld3 - fresh.ld3).abs().item()),
+           "inv_diag_all_rel": float(((ctx.diag3 - fresh.diag3).abs() / fresh.diag3).max().item())}
+    return {"n_locations": n, "n_static": N_BASE, "picks": chosen, "ms_context_build": build_ms,
+            "ms_per_pick_rank1_maintenance": [round(t, 3) for t in per_pick],
+            "ms_per_pick_refactorising_round1": build_ms, "after_%d_picks_vs_refactorisation" % picks: err}
+
+
 def sharded_fit_predict_bench(torch, dist, engine, dev, world, n_train=16384, grid_side=256, reps=2):
     """GP fit+predict ms at N = 16384 over the 256 x 256 grid with the test rows sharded over the ranks: kernel build +
     factor + alpha on rank 0, NCCL broadcast of Linv, every rank its block of rows, all-gather.  Max over ranks."""
@@ -1222,6 +1272,11 @@ def run_ours(args, rank, world, local_rank):
             extra["episode"] = episode_bench(torch, engine)
         except Exception as e:
             extra["episode_error"] = repr(e)
+        try:
+            extra["mi_greedy"] = mi_greedy_bench(torch, engine)
+        except Exception as e:
+            extra["mi_greedy_error"] = repr(e)
+        torch.cuda.empty_cache()
         try:
             extra["fit_loop"] = fit_loop_bench(torch, engine, no_cpu=args.no_cpu)
         except Exception as e:

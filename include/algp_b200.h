@@ -160,7 +160,9 @@ int algp_score_sets(const double* Wt, int64_t ldw, int64_t ncols, const double* 
                     const uint8_t* skip, int k, int64_t B, double H_base, double* scores, void* stream);
 /* The same scores for long paths: 128 < k <= 2048 slots per candidate (the reference scores paths of "tens to
  * hundreds" of mobile locations, agent.py:373-400).  The k x k conditional covariance of a candidate lives in
- * `work` (algp_score_sets_large_work_doubles(k, B) doubles) instead of shared memory; k <= 128 ignores work. */
+ * `work` instead of shared memory; k <= 128 ignores work.  algp_score_sets_large_work_doubles(k, B) is the PREFERRED
+ * size (one matrix per resident CTA); any work_doubles >= kk (kk + 1), kk = k rounded up to 8, is accepted and runs
+ * correspondingly fewer CTAs, so a caller can bound the scratch by the memory it has. */
 int algp_score_sets_large(const double* Wt, int64_t ldw, int64_t ncols, const double* X, int d,
                           const double* log_ls_host, double log_os, int kind, double noise, const double* pi0,
                           const int32_t* idx, const double* delta, double delta_scalar, const uint8_t* skip, int k,
@@ -231,6 +233,13 @@ int64_t algp_append_block_work_doubles(void);
 /* out[c] = sum_{r>=c} M[r][c]^2 = diag(A^-1) from the inverse factor; work: algp_colsumsq_work_doubles(n) */
 int algp_colsumsq_lower(const double* M, int64_t n, int64_t ld, double* out, double* work, void* stream);
 int64_t algp_colsumsq_work_doubles(int64_t n);
+/* Rank-1 maintenance of diag(A^-1) and logdet A across greedy picks (agent.py:330-339 recomputes two n x n slogdets
+ * per candidate): col = column j of the ORIGINAL inverse, U [>= t+1 rows x ldu] / coef[t+1] the earlier corrections
+ * (current inverse = A0^-1 - sum_s coef[s] U[s] U[s]^T).  mode 0: row / column j is deleted from A (logdet += log c_j);
+ * mode 1: A += delta e_j e_j^T (logdet += log1p(delta c_j)); c = column j of the current inverse.  diag[n] and the device
+ * scalar logdet are updated in place, U[t] = c and coef[t] are appended.  t < 64. */
+int algp_inv_rank1_update(const double* col, int64_t n, double* U, int64_t ldu, double* coef, int t, int64_t j, int mode,
+                          double delta, double* diag, double* logdet, void* stream);
 /* Per candidate c: out3[c] = {logdet [A2^-1]_CC over its brand-new locations, their count,
  * sum log|Delta| + logdet|Delta^-1 + [A3^-1]_CC| over all its active locations}.  inv2 / inv3 are
  * the inverses (lower triangle valid, algp_potri_lower) of Sigma_AbarAbar and Sigma + D; pos2[n] maps a
@@ -238,7 +247,8 @@ int64_t algp_colsumsq_work_doubles(int64_t n);
 int algp_mi_terms(const double* inv2, int64_t ld2, const int32_t* pos2, const double* inv3, int64_t ld3,
                   const int32_t* idx, int k, int64_t B, const uint8_t* skip, double delta_new, double delta_old,
                   double* out3, void* stream);
-/* algp_mi_terms for 128 < k <= 2048 (scratch: algp_mi_terms_large_work_doubles(k, B) doubles) */
+/* algp_mi_terms for 128 < k <= 2048 (scratch: algp_mi_terms_large_work_doubles(k, B) doubles preferred, any
+ * work_doubles >= k (k + 1) accepted: fewer CTAs run) */
 int algp_mi_terms_large(const double* inv2, int64_t ld2, const int32_t* pos2, const double* inv3, int64_t ld3,
                         const int32_t* idx, int k, int64_t B, const uint8_t* skip, double delta_new, double delta_old,
                         double* out3, double* work, int64_t work_doubles, void* stream);

@@ -220,6 +220,53 @@ def test_agent_mutual_information_matches_reference(golden_dir):
     np.testing.assert_allclose(got[fin], u_lit[0][fin], rtol=1e-8, atol=1e-8)
 
 
+@pytest.mark.parametrize("kind", ["rbf", "matern"])
+def test_mutual_information_rank1_maintenance_matches_refactorisation_and_literal_loop(kind):
+    """MIContext.commit (rank-1 updates of diag(A2^-1), diag(A3^-1) and the two log-dets after a pick)
+    against a context factored from scratch on the updated flags, and Agent.greedy with the MI criterion for 4 picks
+    -- unsampled AND mobile-only locations get picked -- against the literal loop of agent.py:313-354, utility by utility."""
+    X, yf, tr, ytr, rng = field_problem(12, 11, 40, seed=8)
+    n = len(X)
+    th, hy = hyper_pair([2.0, 2.5], 1.2, 0.05, kind)
+    ss, ms = 0.1, 1.0
+    static = np.zeros(n, bool); static[tr[:15]] = True
+    mobile = np.zeros(n, bool); mobile[tr[10:]] = True
+    pi = O.precisions_from_flags(static, mobile, ss, ms)
+    Xd = dev(X)
+    ctx = engine.MIContext(hy, Xd, pi)
+    mobile_only = np.nonzero(mobile & ~static)[0]
+    unsampled = np.nonzero(~(mobile | static))[0]
+    picks = [int(unsampled[3]), int(mobile_only[2]), int(unsampled[40]), int(unsampled[7]), int(mobile_only[0])]
+    for j in picks:
+        assert ctx.commit(j, ss, ms)
+        static[j] = True
+        pi = O.precisions_from_flags(static, mobile, ss, ms)
+        fresh = engine.MIContext(hy, Xd, pi)
+        assert ctx.n_abar == fresh.n_abar
+        np.testing.assert_allclose(ctx.ld2.cpu().numpy(), fresh.ld2.cpu().numpy(), rtol=1e-11, atol=1e-10)
+        np.testing.assert_allclose(ctx.ld3.cpu().numpy(), fresh.ld3.cpu().numpy(), rtol=1e-11, atol=1e-10)
+        np.testing.assert_allclose(ctx.diag3.cpu().numpy(), fresh.diag3.cpu().numpy(), rtol=1e-10, atol=1e-12)
+        p_old, p_new = ctx.pos2.cpu().numpy(), fresh.pos2.cpu().numpy()
+        assert ((p_old >= 0) == (p_new >= 0)).all()
+        keep = p_new >= 0
+        np.testing.assert_allclose(ctx.diag2.cpu().numpy()[p_old[keep]], fresh.diag2.cpu().numpy()[p_new[keep]], rtol=1e-10, atol=1e-12)
+    # through the agent: 4 MI picks against the literal loop
+    class Env(object):
+        pass
+    env = Env()
+    env.X, env.test_X, env.num_samples = X, X[:3], n
+    ag = algp_b200.Agent.__new__(algp_b200.Agent)
+    ag.env, ag.static_std, ag.mobile_std, ag.criterion = env, ss, ms, 'mutual_information'
+    st0 = np.zeros(n, bool); st0[tr[:15]] = True
+    ag.static_data = [[1.0] if st0[i] else [] for i in range(n)]
+    ag.mobile_data = [[1.0] if mobile[i] else [] for i in range(n)]
+    ag.gp = make_gpr(kind, th.log_lengthscale, th.log_outputscale, th.log_noise, X[tr], ytr, np.full(len(tr), ss ** 2))
+    ag._post_update()
+    cov = O.OracleGP(th, "fp64").cov_mat(X, add_likelihood_var=True)
+    want, ut = O.greedy_literal(cov, st0, mobile, ss, ms, 4, criterion="mutual_information", return_utilities=True)
+    assert ag.greedy(4) == [int(p) for p in want]
+
+
 def test_state_dict_roundtrip_and_unknown_kernel():
     x = np.random.default_rng(0).uniform(0, 5, (20, 2))
     gp = make_gpr("matern", np.log([1.5, 2.0]), 0.3, -2.0, x, x[:, 0], np.full(20, 0.01))
@@ -402,6 +449,39 @@ def test_prediction_vs_distance_matches_literal_loop():
     np.testing.assert_allclose(got['mi'], mis, rtol=1e-8)
     np.testing.assert_allclose(got['mean_var'], mv, rtol=1e-8, atol=1e-10)
     np.testing.assert_allclose(got['mean'], mu, rtol=1e-9, atol=1e-9)
+
+
+def test_prediction_vs_distance_degenerate_prefixes():
+    """Prefixes that hold no valid reading yet (only -1 gaps), and a request that runs past the end of the collected
+    list (the reference then repeats the last prefix): no assertion, no IndexError, reference-shaped results."""
+    X, yf, tr, ytr, rng = field_problem(12, 11, 30, seed=3)
+    te = rng.choice(len(X), 9, replace=False)
+    ag = algp_b200.Agent.__new__(algp_b200.Agent)
+    ag.env = GoldenEnv(dict(X=X, test_X=X[te]))
+    ag.env.test_Y = yf[te]
+    ag.static_std, ag.mobile_std, ag.criterion = 0.1, 1.0, 'entropy'
+    inds = [-1, -1, -1, 4, 9, -1, 17, 30]
+    stds = [0.1] * len(inds)
+    ys = [None if i == -1 else float(yf[i]) for i in inds]
+    ag.collected = {'ind': inds, 'std': stds, 'y': ys}
+    th, hy = hyper_pair([2.0, 2.5], 1.0, 0.05, "rbf")
+    ag.gp = make_gpr("rbf", th.log_lengthscale, th.log_outputscale, th.log_noise, X[:2], yf[:2], np.full(2, 0.01))
+    got = ag.prediction_vs_distance(test_every=3, num_runs=4)            # prefixes of 3, 6, 9 (-> 8), 12 (-> 8) entries
+    ogp = O.OracleGP(th, "fp64")
+    assert np.isnan(got['error'][0]) and got['mi'][0] == 0.0             # nothing read yet: NaN mean, prior covariance
+    assert got['mean_var'][0] == pytest.approx(np.exp(th.log_outputscale), rel=1e-12)
+    for slot, count in ((1, 6), (2, 8), (3, 8)):
+        ii = np.array(inds[:count])
+        valid = ii != -1
+        y = np.array([v for v in ys[:count] if v is not None])
+        mu, cov, mi = O.predictive_distribution_chol(ogp, X[ii[valid]], y, X[te], np.array(stds)[:count][valid] ** 2,
+                                                     return_mi=True, return_cov=True)
+        assert got['error'][slot] == pytest.approx(np.mean(np.abs(yf[te] - mu)), rel=1e-8)
+        assert got['mi'][slot] == pytest.approx(mi, rel=1e-8)
+        assert got['mean_var'][slot] == pytest.approx(np.diag(cov).mean(), rel=1e-8)
+    ag.collected = {'ind': [], 'std': [], 'y': []}
+    empty = ag.prediction_vs_distance(test_every=2, num_runs=2)
+    assert len(empty['error']) == 2 and all(np.isnan(e) for e in empty['error'])
 
 
 def test_i8fast_precision_meets_the_1e4_tier(monkeypatch):
