@@ -33,7 +33,7 @@
 #include "i8.cuh"
 
 #define I8_MAX_PLAN 1024                // k chunks per tile: K <= 32768
-#define I8_THREADS 192                  // 4 epilogue warps, warp 4: MMA issuer, warp 5: bulk-copy producer
+#define I8_THREADS 224                  // 4 epilogue warps, warps 4 and 6: MMA issuers (even / odd chunks), warp 5: bulk-copy producer
 
 namespace {
 
@@ -263,7 +263,7 @@ gemm_i8_kernel(const I8Gemm p) {
       mbarrier_init(&full_bar[s], 1);
       mbarrier_init(&empty_bar[s], 1);
     }
-    mbarrier_init(&done_bar, 1);
+    mbarrier_init(&done_bar, 2);                     // one arrival per MMA issuer warp
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 4) {
@@ -423,19 +423,27 @@ gemm_i8_kernel(const I8Gemm p) {
       }
       par ^= 1u;
     }
-  } else if (warp == 4 && KT > 0) {
-    // ===================== MMA issuer (warp 4; one elected lane issues) =====================
+  } else if ((warp == 4 || warp == 6) && KT > 0) {
+    // ===================== MMA issuers (warps 4 and 6; one elected lane each issues) =====================
+    // TWO issuers take the surviving chunks alternately (warp 4: even plan entries, warp 6: odd).  One issuer spends
+    // ~770 cycles per chunk on its control chain (full-barrier wait, plan look-ahead, elect, UTCIMMA dispatch, commit:
+    // profiles/r01_i8_phases.log) against ~380 cycles of tensor work, so the tensor pipe idled half the time; the
+    // MMAs of both warps enter the SM's one tensor pipe, which executes them in arrival order, and integer
+    // accumulation into a group's TMEM columns is exact and commutative, so the interleaving of the two streams does
+    // not change a bit of the result.  Each issuer commits its own chunks' `empty` barriers and arrives on done_bar
+    // (count 2) after its last MMA.
+    const int iss = __shfl_sync(0xffffffffu, (warp == 6) ? 1 : 0, 0);
     // The B digit planes of a stage are contiguous in shared memory ([plane][64 rows][32 B]), i.e. ONE K-major
     // operand of (S - p) x 64 rows, and group g = p + q lives at TMEM columns g x 64: a single MMA of A_p against
     // planes q0..q0+c-1 (N = 64c <= 256) lands every product in its own group.  S(S+1)/2 plane products become
     // ~S(S+1)/8 + S/2 instructions and A_p is read from shared memory once per <= 4 products instead of once each.
     // Same uniform control flow as the producer; the MMAs of a sparse chunk come from a switch over its (L, W) shape
     // with every offset and descriptor an immediate (issue_sparse).
-    uint32_t ws_next = __shfl_sync(0xffffffffu, plan_s[0], 0);
+    uint32_t ws_next = __shfl_sync(0xffffffffu, plan_s[iss], 0);
     const uint32_t da_ring = desc_kmajor_lo(ring);
-    for (int it = 0; it < n_plan; ++it) {
+    for (int it = iss; it < n_plan; it += 2) {
       const uint32_t ws = ws_next;
-      ws_next = __shfl_sync(0xffffffffu, plan_s[(it + 1) & (I8_MAX_PLAN - 1)], 0);
+      ws_next = __shfl_sync(0xffffffffu, plan_s[(it + 2) & (I8_MAX_PLAN - 1)], 0);
       const int s = it % C::STAGES, u = it / C::STAGES;
       const uint32_t da0 = da_ring + (uint32_t)s * (uint32_t)(C::STAGE_BYTES >> 4), db0 = da0 + (uint32_t)(C::A_BYTES >> 4);
       const int pmin = ws & 0xf, qmin = (ws >> 4) & 0xf, qmax = (ws >> 8) & 0xf;
@@ -465,8 +473,8 @@ gemm_i8_kernel(const I8Gemm p) {
       }
     }
     if (elect_one()) {
-      if (n_plan > 0) commit_to(&done_bar);                      // accumulators complete
-      else mbarrier_arrive(&done_bar);                           // every chunk was skipped: the zeros stand
+      if (n_plan > iss) commit_to(&done_bar);                    // this issuer's MMAs complete
+      else mbarrier_arrive(&done_bar);                           // it had no chunk (all skipped, or a single one)
     }
   }
 
