@@ -175,7 +175,87 @@ __global__ void __launch_bounds__(256) score_cov_generic_kernel(const CovArgs a)
   }
 }
 
+// ---------------------------------------------------------------------------
+// Keeping P alive across commits.  An acquisition is a rank-1 downdate of the posterior covariance, stored as one
+// new column of Wt (score.cu: append / append_block).  The resident P follows by
+//     P <- P - sum_c w_c w_c^T        over the k columns appended since P was last brought up to date
+// on the lower triangle: one pass over P (8 n^2 / 2 bytes read and written, HBM bound) for up to 16 columns.
+// 64 x 64 tiles of the lower triangle (diagonal tiles whole: the upper triangle of P is never read), 256 threads,
+// 4 x 4 elements per thread, the two 64 x k slabs of Wt staged in shared memory.
+// ---------------------------------------------------------------------------
+#define CD_T 64
+#define CD_MAXK 16
+__global__ void __launch_bounds__(256) cov_downdate_kernel(double* __restrict__ P, int64_t ldp, int64_t n, const double* __restrict__ Wt,
+                                                           int64_t ldw, int col0, int k, int tiles) {
+  __shared__ double wi[CD_T][CD_MAXK + 1], wj[CD_T][CD_MAXK + 1];
+  // blockIdx -> (ti, tj), tj <= ti
+  const int64_t b = blockIdx.x;
+  int ti = (int)((sqrt(8.0 * (double)b + 1.0) - 1.0) * 0.5);
+  while ((int64_t)(ti + 1) * (ti + 2) / 2 <= b) ++ti;
+  while ((int64_t)ti * (ti + 1) / 2 > b) --ti;
+  const int tj = (int)(b - (int64_t)ti * (ti + 1) / 2);
+  (void)tiles;
+  const int tid = threadIdx.x;
+  for (int e = tid; e < CD_T * k; e += 256) {
+    const int r = e / k, c = e % k;
+    const int64_t gi = (int64_t)ti * CD_T + r, gj = (int64_t)tj * CD_T + r;
+    wi[r][c] = gi < n ? Wt[gi * ldw + col0 + c] : 0.0;
+    wj[r][c] = gj < n ? Wt[gj * ldw + col0 + c] : 0.0;
+  }
+  __syncthreads();
+  const int ty = tid >> 4, tx = tid & 15;
+  double acc[4][4];
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int c = 0; c < 4; ++c) acc[a][c] = 0.0;
+  for (int q = 0; q < k; ++q) {
+    double ra[4], rb[4];
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+      ra[a] = wi[ty * 4 + a][q];
+      rb[a] = wj[tx * 4 + a][q];
+    }
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) acc[a][c] = fma(ra[a], rb[c], acc[a][c]);
+  }
+#pragma unroll
+  for (int a = 0; a < 4; ++a) {
+    const int64_t gi = (int64_t)ti * CD_T + ty * 4 + a;
+    const int64_t gj = (int64_t)tj * CD_T + tx * 4;
+    if (gi >= n) continue;
+    double* row = P + gi * ldp + gj;
+    if (gj + 3 < n) {
+      double2 lo = *reinterpret_cast<double2*>(row), hi = *reinterpret_cast<double2*>(row + 2);
+      lo.x -= acc[a][0]; lo.y -= acc[a][1]; hi.x -= acc[a][2]; hi.y -= acc[a][3];
+      *reinterpret_cast<double2*>(row) = lo;
+      *reinterpret_cast<double2*>(row + 2) = hi;
+    } else {
+#pragma unroll
+      for (int c = 0; c < 4; ++c)
+        if (gj + c < n) row[c] -= acc[a][c];
+    }
+  }
+}
+
 }  // namespace
+
+// P[i][j] -= sum_{c < k} Wt[i][col0 + c] Wt[j][col0 + c] on the lower triangle (j <= i) of the resident posterior
+// covariance P [n x ldp]: the k columns Wt gained through algp_append / algp_append_block since P was current.
+// k <= 16 per call; ldp even and P 16-byte aligned.
+extern "C" int algp_cov_downdate(double* P, int64_t ldp, int64_t n, const double* Wt, int64_t ldw, int64_t col0, int k,
+                                 void* stream) {
+  if (!P || !Wt || n < 1 || ldp < n || (ldp & 1) || ((uintptr_t)P & 15) || col0 < 0 || k < 1 || k > CD_MAXK || col0 + k > ldw)
+    return ALGP_ERR_INVALID;
+  const int64_t t = (n + CD_T - 1) / CD_T;
+  const int64_t blocks = t * (t + 1) / 2;
+  cov_downdate_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(P, ldp, n, Wt, ldw, (int)col0, k, (int)t);
+  ALGP_LAUNCH_CHECK();
+  return ALGP_OK;
+}
+
 
 // scores[c] = H(base set + candidate set c) from the lower triangle of the posterior covariance P [n x ldp] of the
 // base set (P = Sigma + sigma_n^2 I - Wt Wt^T): the restructured form of the slogdet loops of agent.py:373-400 /

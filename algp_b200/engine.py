@@ -434,13 +434,14 @@ class PosteriorState(object):
         GEMMs with 8 planes (fp64-grade) instead of DMMA.
         cov_mode: "never" scores candidate sets by streaming rows of Wt; "always" builds the resident posterior
         covariance P (build_cov) before the first scoring call; "auto" (default) builds it once the scoring work
-        streamed against an unchanged state would have paid for the build (see score_sets)."""
+        streamed against this state would have paid for the build (see score_sets).  A built P survives commits."""
         if cov_mode not in ("auto", "never", "always"):
             raise ValueError("cov_mode must be 'auto', 'never' or 'always'")
         dev = X.device
         self.precision = precision
         self.cov_mode = cov_mode
         self.P = None                  # [n_pad x n_pad] lower triangle of Sigma + noise I - Wt Wt^T, or None
+        self._P_ncols = 0              # columns of Wt that P accounts for (appends are folded in lazily: _sync_cov)
         self._stream_s = 0.0           # estimated seconds of Wt streaming since the state last changed
         self.hyper = hyper
         self.X = X
@@ -506,7 +507,8 @@ class PosteriorState(object):
         """P = Sigma + sigma_n^2 I - Wt Wt^T, lower triangle, [n_pad x n_pad] fp64 resident in HBM: the posterior
         covariance of the current base set over all field locations.  Candidate scoring then gathers k(k+1)/2
         entries per set (algp_score_sets_cov) instead of streaming k rows of Wt.  One kernel-matrix build plus one
-        SYRK (DMMA, or exact INT8 digit GEMM with precision "i8"); dropped by append / append_block."""
+        SYRK (DMMA, or exact INT8 digit GEMM with precision "i8").  append / append_block keep it: the new columns are
+        folded in by _sync_cov (P -= w w^T) before the next scoring call that reads it."""
         P, _ = kbuild(self.hyper, self.X, None, self.n_pad, self.n_pad, diag_scalar=self.hyper.noise)
         kpad = pad_to(self.ncols, 32)
         if self.ncols > 0:
@@ -521,17 +523,32 @@ class PosteriorState(object):
                 call("algp_gemm_nt", ptr(self.Wt), self.ldw, ptr(self.Wt), self.ldw, ptr(P), P.stride(0), self.n_pad,
                      self.n_pad, kpad, -1.0, 1.0, 1, stream())
         self.P = P
+        self._P_ncols = self.ncols
         return P
 
     def drop_cov(self):
         self.P = None
+        self._P_ncols = 0
         self._stream_s = 0.0
+
+    def _sync_cov(self):
+        """Bring the resident P up to date with the columns appended since it was built / last synchronised: every
+        commit is a rank-1 downdate of P stored as a column of Wt, so P -= w w^T over those columns (one pass over the
+        lower triangle per 16 columns) replaces the rebuild.  Lazy: runs before the next scoring call that reads P."""
+        while self.P is not None and self._P_ncols < self.ncols:
+            k = min(16, self.ncols - self._P_ncols)
+            call("algp_cov_downdate", ptr(self.P), self.P.stride(0), self.n_pad, ptr(self.Wt), self.ldw, self._P_ncols, k,
+                 stream())
+            self._P_ncols += k
 
     def _want_cov(self, B, k):
         """Rent-or-buy: stream rows of Wt until the streaming done against this unchanged state would have paid
         for the covariance build, then build it (at most twice the cost of the better choice in hindsight)."""
         if self.P is not None:
-            return k <= self.COV_MAX_K
+            if k > self.COV_MAX_K:
+                return False
+            self._sync_cov()
+            return True
         if self.cov_mode == "never" or k > self.COV_MAX_K or self.ncols == 0:
             return False
         if self.cov_mode == "auto":
@@ -610,7 +627,6 @@ class PosteriorState(object):
         if self.ncols >= self.ldw:
             raise RuntimeError("PosteriorState capacity exhausted (%d columns)" % self.ldw)
         ls, ls_p = _lib.host_f64(self.hyper.log_ls)
-        self.drop_cov()
         call("algp_append", ptr(self.Wt), self.ldw, self.ncols, ptr(self.X), self.n, self.hyper.d, ls_p,
              self.hyper.log_os, self.hyper.kind, self.hyper.noise, ptr(self.diagP), ptr(self.pi), ptr(self.is_static),
              C.c_void_p(j_dev.data_ptr()), float(delta), int(mark_static), ptr(self._appwork), stream())
@@ -626,7 +642,6 @@ class PosteriorState(object):
             raise RuntimeError("PosteriorState capacity exhausted (%d columns)" % self.ldw)
         if getattr(self, "_blkwork", None) is None:
             self._blkwork = torch.empty(_lib.lib.algp_append_block_work_doubles(), dtype=torch.float64, device=self.X.device)
-        self.drop_cov()
         ls, ls_p = _lib.host_f64(self.hyper.log_ls)
         dl_dev, dl_scalar = None, 0.0
         if np.ndim(delta) == 0 and not torch.is_tensor(delta):

@@ -923,6 +923,41 @@ def resident_cov_bench(torch, engine, algp_b200, hyper, Xd, base, pi0, is_static
         "streaming_for_comparison": N_CAND / (stream_ms / 1e3),
         "break_even_batches_fp64_build": bms / max(stream_ms - ms, 1e-9),
         "break_even_batches_i8_build": out["build_ms_i8"] / max(stream_ms - ms, 1e-9)}
+    # commits keep P alive: 4 greedy picks (rank-1 appends) + the 16 mobile readings of a path (one block append), then
+    # the new columns are folded into P by rank-k downdates and the next batch is scored from the same P
+    try:
+        st_c = engine.PosteriorState(hyper, Xd, base, pi0, is_static=is_static, capacity=64, cov_mode="always")
+        st_c.score_sets(batches[0], delta_d, H_base=H_base, out=scores)
+        torch.cuda.synchronize()
+        d_s, d_m = 1.0 / STATIC_STD ** 2, 1.0 / MOBILE_STD ** 2
+        e0.record()
+        picks = st_c.greedy(4, d_s)
+        path = [int(v) for v in rest[:4096:256].cpu().tolist() if int(v) not in picks][:16]
+        st_c.append_block(path, d_m, mark_static=False)
+        e1.record()
+        torch.cuda.synchronize()
+        commit_ms = e0.elapsed_time(e1)
+        e0.record()
+        st_c._sync_cov()
+        e1.record()
+        torch.cuda.synchronize()
+        sync_ms = e0.elapsed_time(e1)
+        e0.record()
+        sc_p = st_c.score_sets(batches[1], delta_d).clone()
+        e1.record()
+        torch.cuda.synchronize()
+        score_ms = e0.elapsed_time(e1)
+        st_c.cov_mode, keepP, st_c.P = "never", st_c.P, None
+        sc_s = st_c.score_sets(batches[1], delta_d)
+        out["across_commits"] = {
+            "what": "4 greedy picks + one 16-reading block append on a state with P resident; P is kept and brought up to date "
+                    "by algp_cov_downdate (2 passes over the lower triangle for the 20 new columns) instead of a rebuild",
+            "commit_ms": commit_ms, "downdate_ms": sync_ms, "rebuild_ms_for_comparison": bms, "score_from_P_ms": score_ms,
+            "max_abs_score_diff_vs_streaming_after_commits": float((sc_p - sc_s).abs().max().item()),
+            "downdate_gbs": 2 * 2 * 8.0 * st_c.n_pad * (st_c.n_pad + 64) / 2 / (sync_ms / 1e3) / 1e9}
+        del st_c, keepP
+    except Exception as e:
+        out["across_commits_error"] = repr(e)
     del st, states
     # through the reference-facing call with the default policy (cov_mode "auto"): the state streams until the
     # streamed work would have paid for the build, builds P inside one call, and gathers from then on

@@ -302,13 +302,14 @@ def test_score_sets_resident_cov_matches_oracle(kind, k):
     assert int(np.argmax(got)) == int(np.argmax(want))
 
 
-def test_resident_cov_policy_and_invalidation():
-    """cov_mode="auto" streams until the streamed work would have paid for the build, then switches; a commit
-    (append) drops the covariance, and scores after the commit are those of a freshly built state."""
+def test_resident_cov_policy_and_commits():
+    """cov_mode="auto" streams until the streamed work would have paid for the build, then switches; a commit (append
+    / append_block) KEEPS the covariance: the appended columns are folded in lazily by rank-k downdates
+    (algp_cov_downdate) before the next scoring call, and the scores are those of a freshly built state."""
     X, th, hy, static, mobile, pi0, cov, ss, ms, rng = scoring_problem("rbf")
     n = len(X)
     base = np.nonzero(pi0 > 0)[0]
-    state = engine.PosteriorState(hy, dev(X), base, pi0, is_static=static, capacity=8)
+    state = engine.PosteriorState(hy, dev(X), base, pi0, is_static=static, capacity=40)
     free = np.nonzero(pi0 == 0)[0]
     idx = rng.choice(free, (4000, 8)).astype(np.int32)
     idx_d = dev(idx, torch.int32)
@@ -318,14 +319,36 @@ def test_resident_cov_policy_and_invalidation():
     second = state.score_sets(idx_d, None, delta_scalar=1 / ms ** 2).cpu().numpy()
     assert state.P is not None
     np.testing.assert_allclose(second, first, rtol=1e-11, atol=1e-10)
+    P_before = state.P
+    pi1 = pi0.copy()
+    # one rank-1 commit, then a block of 19 (two downdate passes: 16 + 3 columns), then another single one
     j = torch.tensor([int(free[0])], dtype=torch.int64, device="cuda")
     state.append(j, 1 / ss ** 2)
-    assert state.P is None and state._stream_s == 0.0
+    pi1[free[0]] += 1 / ss ** 2
+    blk = free[5:24]
+    state.append_block(blk, 1 / ms ** 2, mark_static=False)
+    pi1[blk] += 1 / ms ** 2
+    assert state.P is P_before and state._P_ncols < state.ncols      # kept, not yet synchronised
     after = state.score_sets(idx_d, None, delta_scalar=1 / ms ** 2).cpu().numpy()
-    pi1 = pi0.copy(); pi1[free[0]] = 1 / ss ** 2
+    assert state.P is P_before and state._P_ncols == state.ncols
     fresh = engine.PosteriorState(hy, dev(X), np.nonzero(pi1 > 0)[0], pi1, cov_mode="always")
     want = fresh.score_sets(idx_d, None, delta_scalar=1 / ms ** 2, H_base=state.H_base).cpu().numpy()
     np.testing.assert_allclose(after, want, rtol=1e-9, atol=1e-9)
+    np.testing.assert_allclose(np.tril(state.P.cpu().numpy()[:n, :n]), np.tril(fresh.P.cpu().numpy()[:n, :n]), rtol=0, atol=1e-10)
+    state.score_mode = "stream"
+    mode, state.cov_mode = state.cov_mode, "never"
+    P_keep, state.P = state.P, None
+    streamed = state.score_sets(idx_d, None, delta_scalar=1 / ms ** 2).cpu().numpy()
+    state.P, state.cov_mode = P_keep, mode
+    np.testing.assert_allclose(after, streamed, rtol=1e-10, atol=1e-9)
+    state.append(torch.tensor([int(free[30])], dtype=torch.int64, device="cuda"), 1 / ss ** 2)
+    pi1[free[30]] += 1 / ss ** 2
+    again = state.score_sets(idx_d, None, delta_scalar=1 / ms ** 2).cpu().numpy()
+    fresh2 = engine.PosteriorState(hy, dev(X), np.nonzero(pi1 > 0)[0], pi1, cov_mode="always")
+    np.testing.assert_allclose(again, fresh2.score_sets(idx_d, None, delta_scalar=1 / ms ** 2, H_base=state.H_base).cpu().numpy(),
+                               rtol=1e-9, atol=1e-9)
+    state.drop_cov()
+    assert state.P is None and state._stream_s == 0.0
     never = engine.PosteriorState(hy, dev(X), base, pi0, cov_mode="never")
     never._stream_s = 1e9
     never.score_sets(idx_d, None, delta_scalar=1.0)
