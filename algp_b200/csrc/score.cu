@@ -73,15 +73,35 @@ __device__ __forceinline__ void sc_load(double (&v)[4 * UNROLL], const double* p
   }
 }
 
-template <int UNROLL, bool PREFETCH, int THREADS>
-__global__ void __launch_bounds__(THREADS) score_sets_k8_kernel(const ScoreArgs a) {
+// SPLIT = 2: the 8 warps of a CTA work on 4 candidates at a time, warp w and warp w + 4 each taking half of the columns
+// of candidate slot w; the second warp hands its accumulator fragment over through shared memory and moves on, the first
+// adds it and runs the epilogue.  Used for small batches only (fewer candidates than half the resident warp slots),
+// where whole-candidate work items leave most of the machine idle.
+template <int UNROLL, bool PREFETCH, int THREADS, int SPLIT>
+__global__ void __launch_bounds__(THREADS, 3) score_sets_k8_kernel(const ScoreArgs a) {
   const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
   const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
   const int d = a.kp.d;
   constexpr int STEP = 16 * UNROLL;
+  constexpr int CPB = THREADS / 32 / SPLIT;                 // candidates a CTA works on at a time
+  __shared__ double frag[SPLIT > 1 ? 2 : 1][SPLIT > 1 ? CPB : 1][64];
+  const int wic = threadIdx.x >> 5;
+  const int slot = SPLIT > 1 ? wic % CPB : 0, part = SPLIT > 1 ? wic / CPB : 0;
+  int par = 0;
 
-  for (int64_t cand = warp0; cand < a.B; cand += nwarps) {
+  for (int64_t it = SPLIT > 1 ? (int64_t)blockIdx.x : warp0; (SPLIT > 1 ? it * CPB : it) < a.B; it += SPLIT > 1 ? (int64_t)gridDim.x : nwarps) {
+    int64_t cand = it;
+    int col0 = a.col0, col1 = a.col1;
+    bool valid = true;
+    if (SPLIT > 1) {
+      cand = it * CPB + slot;
+      valid = cand < a.B;
+      if (!valid) cand = a.B - 1;                           // keeps the CTA's barrier count uniform; nothing is written
+      const int span = ((a.ncols16 + SPLIT - 1) / SPLIT + STEP - 1) / STEP * STEP;
+      col0 = part * span;
+      col1 = col0 + span;
+    }
     // slot g of this candidate (4 lanes per slot)
     int my_idx = (g < a.k) ? a.idx[cand * a.k + g] : -1;
     double my_delta = (g < a.k) ? (a.delta ? a.delta[cand * a.k + g] : a.delta_scalar) : 0.0;
@@ -99,7 +119,7 @@ __global__ void __launch_bounds__(THREADS) score_sets_k8_kernel(const ScoreArgs 
     double c0[4], c1[4];
 #pragma unroll
     for (int q = 0; q < 4; ++q) c0[q] = c1[q] = 0.0;
-    const int cend = a.col1 < a.ncols16 ? a.col1 : a.ncols16;
+    const int cend = col1 < a.ncols16 ? col1 : a.ncols16;
     if (!a.first) {                                        // continue the Gram of the earlier column chunks
       const double2 p = *reinterpret_cast<const double2*>(a.gpart + cand * 64 + 2 * lane);
       c0[0] = p.x;
@@ -108,8 +128,8 @@ __global__ void __launch_bounds__(THREADS) score_sets_k8_kernel(const ScoreArgs 
     // empty / duplicate slots issue no loads; the MMA itself is warp-wide
     if (PREFETCH) {
       double cur[4 * UNROLL], nxt[4 * UNROLL];
-      sc_load<UNROLL>(cur, row, active, a.col0, cend);
-      for (int k0 = a.col0; k0 < cend; k0 += STEP) {
+      sc_load<UNROLL>(cur, row, active, col0, cend);
+      for (int k0 = col0; k0 < cend; k0 += STEP) {
         sc_load<UNROLL>(nxt, row, active, k0 + STEP, cend);
 #pragma unroll
         for (int q = 0; q < 4 * UNROLL; ++q) dmma884(c0[q & 3], c1[q & 3], cur[q], cur[q]);
@@ -117,15 +137,24 @@ __global__ void __launch_bounds__(THREADS) score_sets_k8_kernel(const ScoreArgs 
         for (int q = 0; q < 4 * UNROLL; ++q) cur[q] = nxt[q];
       }
     } else {
-      for (int k0 = a.col0; k0 < cend; k0 += STEP) {
+      for (int k0 = col0; k0 < cend; k0 += STEP) {
         double v[4 * UNROLL];
         sc_load<UNROLL>(v, row, active, k0, cend);
 #pragma unroll
         for (int q = 0; q < 4 * UNROLL; ++q) dmma884(c0[q & 3], c1[q & 3], v[q], v[q]);
       }
     }
-    const double G0 = (c0[0] + c0[1]) + (c0[2] + c0[3]);   // G[g][2t]
-    const double G1 = (c1[0] + c1[1]) + (c1[2] + c1[3]);   // G[g][2t+1]
+    double G0 = (c0[0] + c0[1]) + (c0[2] + c0[3]);         // G[g][2t]
+    double G1 = (c1[0] + c1[1]) + (c1[2] + c1[3]);         // G[g][2t+1]
+    if (SPLIT > 1) {
+      if (part > 0) *reinterpret_cast<double2*>(&frag[par][slot][2 * lane]) = make_double2(G0, G1);
+      __syncthreads();
+      const double2 o = *reinterpret_cast<const double2*>(&frag[par][slot][2 * lane]);
+      par ^= 1;                                            // the other buffer next time: one barrier per iteration
+      if (part > 0 || !valid) continue;
+      G0 += o.x;
+      G1 += o.y;
+    }
     if (!a.last) {                                         // more column chunks to come: park the fragment
       *reinterpret_cast<double2*>(a.gpart + cand * 64 + 2 * lane) = make_double2(G0, G1);
       continue;
@@ -186,7 +215,16 @@ static void score_k8_launch(const ScoreArgs& a, int sms, int blocks_per_sm, cuda
   const int wpb = THREADS / 32;
   int64_t want = (a.B + wpb - 1) / wpb;
   int64_t cap = (int64_t)sms * blocks_per_sm;
-  score_sets_k8_kernel<UNROLL, PREFETCH, THREADS><<<(int)(want < cap ? want : cap), THREADS, 0, st>>>(a);
+  // half-size work items (SPLIT = 2) for batches that leave at least half of the resident warp slots (3 CTAs per SM)
+  // empty: 1000 candidates 0.078 -> 0.057 ms.  Larger batches lose more to the pairing barrier than the finer
+  // granularity returns (8192: 0.233 -> 0.259 ms, profiles/r02_score_tiling.log)
+  const int64_t slots = (int64_t)sms * 3 * wpb;
+  if (a.first && a.last && a.ncols16 >= 4 * 16 * UNROLL && 2 * a.B <= slots) {
+    want = (a.B + wpb / 2 - 1) / (wpb / 2);
+    score_sets_k8_kernel<UNROLL, PREFETCH, THREADS, 2><<<(int)(want < cap ? want : cap), THREADS, 0, st>>>(a);
+    return;
+  }
+  score_sets_k8_kernel<UNROLL, PREFETCH, THREADS, 1><<<(int)(want < cap ? want : cap), THREADS, 0, st>>>(a);
 }
 
 // ---------------------------------------------------------------------------
@@ -357,7 +395,7 @@ extern "C" int algp_score_sets_large(const double* Wt, int64_t ldw, int64_t ncol
     // (profiles/r01_score_variants.log); MANY short CTAs beat a persistent resident grid (profiles/r02_score_tiling.log):
     // CTAs that start at different times keep the warps of an SM out of phase, so loads and DMMAs overlap.
     if (work && work_doubles < 0) {
-      // algp_score_sets_tiled: one launch per chunk of -work_doubles columns, accumulator fragments in work [B][64]
+      // algp_score_sets_tiled, chunked: one launch per chunk of -work_doubles columns, accumulator fragments in work [B][64]
       const int chunk = (int)(-work_doubles);
       a.gpart = work;
       for (int c0 = 0; c0 < a.ncols16 || c0 == 0; c0 += chunk) {
@@ -409,7 +447,7 @@ extern "C" int algp_score_sets_large(const double* Wt, int64_t ldw, int64_t ncol
 static int g_tile_cols = 0;       // 0 = derive from the L2 size; algp_set_score_tile_cols overrides (tuning / tests)
 
 extern "C" int algp_set_score_tile_cols(int cols) {
-  if (cols < 0 || (cols & 63)) return ALGP_ERR_INVALID;
+  if (cols < -1 || (cols > 0 && (cols & 63))) return ALGP_ERR_INVALID;
   g_tile_cols = cols;
   return ALGP_OK;
 }
@@ -423,17 +461,26 @@ extern "C" int algp_score_sets_tiled(const double* Wt, int64_t ldw, int64_t ncol
                                      void* stream) {
   if (k < 1 || k > 8 || B < 0 || n_rows < 1) return ALGP_ERR_INVALID;
   if (B > 0 && (!work || work_doubles < B * 64 || ((uintptr_t)work & 15))) return ALGP_ERR_INVALID;
+  // g_tile_cols > 0: that chunk; -1: plain single launch; 0 (auto): chunked launches where ONE call streams enough for
+  // the L2 hit rate to pay for the per-chunk prologues (>= ~12 GB: 1.50 vs 1.69 ms on configs[2] for an isolated call;
+  // back-to-back calls on the same rows find part of them in L2 anyway and the two are level), else the single launch
   int chunk = g_tile_cols;
   if (chunk == 0) {
-    int dev = 0, l2 = 64 << 20;
-    ALGP_CUDA(cudaGetDevice(&dev));
-    ALGP_CUDA(cudaDeviceGetAttribute(&l2, cudaDevAttrL2CacheSize, dev));
-    // the slice of a launch about the size of the L2: 1024 columns for the 16 384 rows of configs[2]
-    int64_t c = ((int64_t)l2 / (8 * n_rows) + 32) / 64 * 64;
-    chunk = (int)(c < 256 ? 256 : c);
+    const double bytes = 8.0 * (double)B * k * (double)ncols;
+    if (bytes >= 12.0e9 && ncols >= 2048) {
+      int dev = 0, l2 = 64 << 20;
+      ALGP_CUDA(cudaGetDevice(&dev));
+      ALGP_CUDA(cudaDeviceGetAttribute(&l2, cudaDevAttrL2CacheSize, dev));
+      // the slice of a launch about the size of the L2: 1024 columns for the 16 384 rows of configs[2]
+      int64_t c = ((int64_t)l2 / (8 * n_rows) + 32) / 64 * 64;
+      chunk = (int)(c < 256 ? 256 : c);
+    }
   }
+  if (chunk > 0)
+    return algp_score_sets_large(Wt, ldw, ncols, X, d, log_ls_host, log_os, kind, noise, pi0, idx, delta, delta_scalar, skip,
+                                 k, B, H_base, scores, B > 0 ? work : (double*)1, -(int64_t)chunk, stream);
   return algp_score_sets_large(Wt, ldw, ncols, X, d, log_ls_host, log_os, kind, noise, pi0, idx, delta, delta_scalar, skip, k,
-                               B, H_base, scores, B > 0 ? work : (double*)1, -(int64_t)chunk, stream);
+                               B, H_base, scores, nullptr, 0, stream);
 }
 
 // ---------------------------------------------------------------------------

@@ -560,17 +560,13 @@ class PosteriorState(object):
         self.build_cov()
         return True
 
-    # k <= 8: "stream" = one launch of score_sets_k8_kernel (rows of Wt end to end), "tiled" = one launch per L2-sized
-    # column chunk (algp_score_sets_tiled: 11 % faster on configs[2]), "auto" = tiled once the batch streams enough
-    # bytes for the L2 hit rate to matter
+    # k <= 8: "auto" = algp_score_sets_tiled decides (one launch with a split tail; one launch per L2-sized column chunk
+    # for isolated calls that stream >= ~12 GB), "stream" = the plain single launch of algp_score_sets, "tiled" = same
+    # entry as "auto" (tests force the chunk through algp_set_score_tile_cols)
     score_mode = "auto"
-    TILED_MIN_BYTES = 2.0e9
-    TILED_MIN_COLS = 2048
 
     def _want_tiled(self, B, k):
-        if self.score_mode != "auto":
-            return self.score_mode == "tiled"
-        return self.ncols >= self.TILED_MIN_COLS and 8.0 * B * k * self.ncols >= self.TILED_MIN_BYTES
+        return self.score_mode != "stream"
 
     def score_sets(self, idx, delta=None, delta_scalar=0.0, H_base=None, out=None, skip=None):
         """scores[c] = H(S1_c) for candidate sets idx [B,k] (int32 device tensor, -1 = empty)."""
@@ -587,7 +583,7 @@ class PosteriorState(object):
             return out
         self._stream_s += 8.0 * B * k * max(self.ncols, 1) / self.STREAM_BYTES_PER_S
         if k <= 8 and self._want_tiled(B, k):
-            # large batches of small sets: the same kernel, one launch per L2-sized column chunk
+            # small sets with a workspace: split tail / column chunks decided by the library (csrc/score.cu)
             nwork = _lib.lib.algp_score_sets_tiled_work_doubles(B)
             if getattr(self, "_tilework", None) is None or self._tilework.numel() < nwork:
                 self._tilework = torch.empty(nwork, dtype=torch.float64, device=idx.device)
