@@ -284,6 +284,28 @@ def fit_predict_bench(torch, engine, n_train, grid_side, reps, peak_hbm):
         for i, k in enumerate(names[:-1]):
             times[k].append(marks[i].elapsed_time(marks[i + 1]))
         times["total"].append(marks[0].elapsed_time(marks[6]))
+    # comparator ("cuSOLVER potrf as a sanity ceiling"): torch.linalg.cholesky on the same padded matrix with
+    # the cuSOLVER backend; library code, not on the product path
+    cusolver_ms = None
+    try:
+        torch.backends.cuda.preferred_linalg_library("cusolver")
+        Ac, _ = engine.kbuild(hy, xd, None, Npad, Npad, var, hy.noise, True)
+        Asym = torch.tril(Ac) + torch.tril(Ac, -1).T
+        del Ac
+        torch.linalg.cholesky(Asym)
+        torch.cuda.synchronize()
+        cs = []
+        for _ in range(max(2, reps)):
+            t0, t1 = ev(), ev()
+            t0.record()
+            torch.linalg.cholesky(Asym)
+            t1.record()
+            torch.cuda.synchronize()
+            cs.append(t0.elapsed_time(t1))
+        cusolver_ms = float(np.median(cs))
+        del Asym
+    except Exception as e:
+        cusolver_ms = repr(e)
     # TF32 mode of the variance step, timed in its own loop (a run uses one mode or the other; interleaving
     # would let the tensor-core power draw of this stage throttle the next repetition's fp64 factorisation):
     # split K(X*,X) and Linv into fp32 hi/lo planes + tcgen05 split-TF32 TRMM
@@ -439,7 +461,9 @@ def fit_predict_bench(torch, engine, n_train, grid_side, reps, peak_hbm):
                "kbuild_cross_mean": {"bound": "hbm", "achieved": 8 * N * Mp / med["kbuild_cross_mean"] / 1e6, "peak": peak_hbm, "unit": "GB/s"},
                "solve": {"bound": "hbm", "achieved": 8 * N * N / med["solve"] / 1e6, "peak": peak_hbm, "unit": "GB/s",
                          "what": "alpha = Linv^T (Linv y): two triangular gemv passes, 8 N^2 / 2 bytes each (SURVEY 8d)"},
-               "potrf": {"bound": "fp64 tensor (DMMA)", "achieved": N ** 3 / 3 / med["potrf"] / 1e9, "unit": "TFLOP/s"},
+               "potrf": {"bound": "fp64 tensor (DMMA)", "achieved": N ** 3 / 3 / med["potrf"] / 1e9, "unit": "TFLOP/s",
+                         "ms": med["potrf"], "cusolver_potrf_ms_same_matrix": cusolver_ms,
+                         "note": "algp_potrf also inverts every 128 x 128 diagonal block (needed by the panel GEMM and by trtri)"},
                "trtri": {"bound": "fp64 tensor (DMMA)", "achieved": N ** 3 / 3 / med["trtri"] / 1e9, "unit": "TFLOP/s"},
                "variance_trmm": {"bound": "fp64 tensor (DMMA)", "achieved": N * N * Mp / med["variance_trmm"] / 1e9, "unit": "TFLOP/s"},
                "variance_i8": {"bound": "int8 tensor (tcgen05 kind::i8), S(S+1)/2 exact digit GEMMs per product, incl. the digit split "
@@ -1360,7 +1384,9 @@ def run_ours(args, rank, world, local_rank):
         res = {}
         if traffic is not None:
             res["dram"] = {"bytes_per_launch_ncu": traffic, "achieved_gbs": traffic / (kernel_ms / 1e3) / 1e9, "peak_gbs": peak_hbm,
-                           "frac": traffic / (kernel_ms / 1e3) / 1e9 / peak_hbm}
+                           "frac": traffic / (kernel_ms / 1e3) / 1e9 / peak_hbm,
+                           "note": "ncu replays a launch from flushed caches, the timed loop re-scores the same rows back to back "
+                                   "(part of them still in L2): an upper bound for the steady state, exact for an isolated call"}
         probe = extra.get("l2_to_sm_probe_tbs")
         if probe:
             pk = max(probe.values())
