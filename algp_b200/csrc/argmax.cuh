@@ -37,3 +37,38 @@ static __global__ void argmax_stage1_kernel(const double* __restrict__ x, int64_
 
 
 #define ARGMAX_BLOCKS 148
+#define ARGMAX_ONE_CTA_MAX (1 << 18)   // up to this many values one 1024-thread CTA scans the vector itself
+
+// block-wide first-maximum of (bv, bi) over a 1024-thread CTA; the result is valid in every thread of warp 0
+__device__ __forceinline__ void argmax_block_reduce_1024(double& bv, long long& bi) {
+  __shared__ double sv1k[32];
+  __shared__ long long si1k[32];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    double ov = __shfl_xor_sync(0xffffffffu, bv, o);
+    long long oi = __shfl_xor_sync(0xffffffffu, bi, o);
+    if (arg_better(ov, oi, bv, bi)) { bv = ov; bi = oi; }
+  }
+  if ((threadIdx.x & 31) == 0) { sv1k[threadIdx.x >> 5] = bv; si1k[threadIdx.x >> 5] = bi; }
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    bv = sv1k[threadIdx.x];
+    bi = si1k[threadIdx.x];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      double ov = __shfl_xor_sync(0xffffffffu, bv, o);
+      long long oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      if (arg_better(ov, oi, bv, bi)) { bv = ov; bi = oi; }
+    }
+  }
+}
+
+// scan x[n] (global ids = position + idx_offset) with the whole CTA: the first-maximum pair of this thread
+__device__ __forceinline__ void argmax_scan(const double* __restrict__ x, int64_t n, int64_t idx_offset, double& bv, long long& bi) {
+  bv = -INFINITY;
+  bi = 0x7fffffffffffffffLL;
+  for (int64_t i = threadIdx.x; i < n; i += blockDim.x) {
+    const double v = x[i];
+    if (arg_better(v, i + idx_offset, bv, bi)) { bv = v; bi = i + idx_offset; }
+  }
+}

@@ -31,20 +31,29 @@ __device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned l
   asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 
-// out3 = {double value; int64 index; int64 status}: status 0 = ok, 1 = a peer's pair did not arrive in time
-__global__ void argmax_exchange_kernel(const ArgPair* __restrict__ part, int np, P2PMailbox* const* __restrict__ peers,
-                                       int rank, int world, unsigned long long epoch, long long timeout_cycles,
-                                       long long* __restrict__ out3) {
+// out3 = {double value; int64 index; int64 status}: status 0 = ok, 1 = a peer's pair did not arrive in time.
+// DIRECT: the (1024-thread) CTA scans this rank's score block x[n] itself -- one launch for argmax + exchange;
+// otherwise one warp reduces the np block partials of argmax_stage1_kernel.
+template <bool DIRECT>
+__global__ void argmax_exchange_kernel(const ArgPair* __restrict__ part, int np, const double* __restrict__ x, int64_t n,
+                                       int64_t idx_offset, P2PMailbox* const* __restrict__ peers, int rank, int world,
+                                       unsigned long long epoch, long long timeout_cycles, long long* __restrict__ out3) {
   const int lane = threadIdx.x;
   double bv = -INFINITY;
   long long bi = 0x7fffffffffffffffLL;
-  for (int p = lane; p < np; p += 32)
-    if (arg_better(part[p].v, part[p].i, bv, bi)) { bv = part[p].v; bi = part[p].i; }
+  if (DIRECT) {
+    argmax_scan(x, n, idx_offset, bv, bi);
+    argmax_block_reduce_1024(bv, bi);
+    if (threadIdx.x >= 32) return;                       // warp 0 carries the exchange
+  } else {
+    for (int p = lane; p < np; p += 32)
+      if (arg_better(part[p].v, part[p].i, bv, bi)) { bv = part[p].v; bi = part[p].i; }
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    double ov = __shfl_xor_sync(0xffffffffu, bv, o);
-    long long oi = __shfl_xor_sync(0xffffffffu, bi, o);
-    if (arg_better(ov, oi, bv, bi)) { bv = ov; bi = oi; }
+    for (int o = 16; o > 0; o >>= 1) {
+      double ov = __shfl_xor_sync(0xffffffffu, bv, o);
+      long long oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      if (arg_better(ov, oi, bv, bi)) { bv = ov; bi = oi; }
+    }
   }
   // every lane holds this rank's winner; lane r delivers it to rank r (its own mailbox included)
   const int par = (int)(epoch & 1ull);
@@ -145,7 +154,8 @@ extern "C" int algp_argmax_exchange(const double* x, int64_t n, int64_t idx_offs
     return ALGP_ERR_INVALID;
   cudaStream_t st = (cudaStream_t)stream;
   int blocks = 0;
-  if (n > 0) {
+  const bool direct = n > 0 && n <= ARGMAX_ONE_CTA_MAX;
+  if (n > 0 && !direct) {
     blocks = (int)((n + 255) / 256 < ARGMAX_BLOCKS ? (n + 255) / 256 : ARGMAX_BLOCKS);
     argmax_stage1_kernel<<<blocks, 256, 0, st>>>(x, n, idx_offset, (ArgPair*)work);
     ALGP_LAUNCH_CHECK();
@@ -161,8 +171,12 @@ extern "C" int algp_argmax_exchange(const double* x, int64_t n, int64_t idx_offs
     if (dev >= 0 && dev < 64) khz_of[dev] = khz;
   }
   const long long cycles = (long long)(timeout_ms * (double)khz);
-  argmax_exchange_kernel<<<1, 32, 0, st>>>((const ArgPair*)work, blocks, (P2PMailbox* const*)peers_dev, rank, world,
-                                            (unsigned long long)epoch, cycles, (long long*)out3);
+  if (direct)
+    argmax_exchange_kernel<true><<<1, 1024, 0, st>>>((const ArgPair*)work, 0, x, n, idx_offset, (P2PMailbox* const*)peers_dev,
+                                                     rank, world, (unsigned long long)epoch, cycles, (long long*)out3);
+  else
+    argmax_exchange_kernel<false><<<1, 32, 0, st>>>((const ArgPair*)work, blocks, nullptr, 0, 0, (P2PMailbox* const*)peers_dev,
+                                                    rank, world, (unsigned long long)epoch, cycles, (long long*)out3);
   ALGP_LAUNCH_CHECK();
   return ALGP_OK;
 }

@@ -520,9 +520,24 @@ __global__ void argmax_stage2_kernel(const ArgPair* __restrict__ part, int np, A
 extern "C" int64_t algp_argmax_work_bytes(void) { return (int64_t)ARGMAX_BLOCKS * sizeof(ArgPair); }
 
 // out_pair: {double value; int64 index} on the device; index = position + idx_offset (global id of a shard)
+// one launch for vectors a single CTA scans in a few microseconds (the per-step argmax of a scoring batch)
+__global__ void __launch_bounds__(1024) argmax_one_cta_kernel(const double* __restrict__ x, int64_t n, int64_t idx_offset,
+                                                              ArgPair* __restrict__ out) {
+  double bv;
+  long long bi;
+  argmax_scan(x, n, idx_offset, bv, bi);
+  argmax_block_reduce_1024(bv, bi);
+  if (threadIdx.x == 0) { out->v = bv; out->i = bi; }
+}
+
 extern "C" int algp_argmax(const double* x, int64_t n, int64_t idx_offset, void* out_pair, void* work, void* stream) {
   if (!x || !out_pair || !work || n <= 0) return ALGP_ERR_INVALID;
   cudaStream_t st = (cudaStream_t)stream;
+  if (n <= ARGMAX_ONE_CTA_MAX) {
+    argmax_one_cta_kernel<<<1, 1024, 0, st>>>(x, n, idx_offset, (ArgPair*)out_pair);
+    ALGP_LAUNCH_CHECK();
+    return ALGP_OK;
+  }
   int blocks = (int)((n + 255) / 256 < ARGMAX_BLOCKS ? (n + 255) / 256 : ARGMAX_BLOCKS);
   argmax_stage1_kernel<<<blocks, 256, 0, st>>>(x, n, idx_offset, (ArgPair*)work);
   ALGP_LAUNCH_CHECK();

@@ -55,6 +55,8 @@ def test_mailbox_exchange_matches_numpy_argmax(world):
             sizes = rng.integers(0 if epoch % 3 == 0 else 1, 5000, world)
             if epoch == 5:
                 sizes[:] = 300
+            if epoch == 6:
+                sizes[0] = 300000                         # beyond the one-CTA scan: block partials + exchange
             blocks, offs, off = [], [], 0
             for r in range(world):
                 x = rng.normal(size=int(sizes[r]))

@@ -410,6 +410,17 @@ def test_argmax_first_max_semantics():
     _lib.call("algp_argmax", _lib.ptr(xd), len(x), 7, _lib.ptr(out), _lib.ptr(state_work), _lib.stream())
     assert int(out[1].item()) == 1 + 7
     assert out[0:1].view(torch.float64).item() == 5.0
+    # one-CTA path (n <= 2^18) and two-kernel path (beyond), ties, all -inf, a single value
+    rng = np.random.default_rng(3)
+    for n in (1, 31, 1024, 5000, 262144, 262145, 700001):
+        v = np.round(rng.normal(size=n), 2)
+        vd = dev(v)
+        _lib.call("algp_argmax", _lib.ptr(vd), n, 0, _lib.ptr(out), _lib.ptr(state_work), _lib.stream())
+        assert int(out[1].item()) == int(np.argmax(v)), n
+        assert out[0:1].view(torch.float64).item() == v.max()
+    inf = dev(np.full(777, -np.inf))
+    _lib.call("algp_argmax", _lib.ptr(inf), 777, 0, _lib.ptr(out), _lib.ptr(state_work), _lib.stream())
+    assert int(out[1].item()) == 0                                        # np.argmax of all -inf is 0 (agent.py:349)
 
 
 # ---------------------------------------------------------------- TF32 mode (tcgen05)
