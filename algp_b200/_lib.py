@@ -9,7 +9,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libalgp_b200.so")
+LIB_PATH = os.environ.get("ALGP_B200_LIB") or os.path.join(_HERE, "lib", "libalgp_b200.so")   # env override: tuning builds
 
 _p, _i64, _i32, _f64 = C.c_void_p, C.c_int64, C.c_int, C.c_double
 

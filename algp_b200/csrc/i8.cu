@@ -160,11 +160,18 @@ struct I8Cfg {
   static constexpr int A_BYTES = S * A_PLANE;
   static constexpr int B_BYTES = S * B_PLANE;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;               // S x 6 KB
+  // EVEN by construction: the two MMA issuer warps take the plan entries alternately, so with an even ring every stage
+  // belongs to one issuer.  With an odd ring a stage alternates between them, an issuer can get two phases ahead of
+  // the other on the same `full` barrier, and a parity wait then passes on the stale phase (observed: launch failure /
+  // hang with 3 and 5 stages).
 #ifndef I8_STAGES_OVERRIDE
-  static constexpr int STAGES = (S >= 8) ? 4 : ((200 * 1024) / STAGE_BYTES > 6 ? 6 : (200 * 1024) / STAGE_BYTES);
+  // as deep as 200 KB allow, at most 8: the 4-plane variance GEMM takes 27.8 / 18.5 / 17.9 / 16.1 ms with 2 / 4 / 6 / 8 stages
+  static constexpr int STAGES_RAW = (S >= 8) ? 4 : ((200 * 1024) / STAGE_BYTES > 8 ? 8 : (200 * 1024) / STAGE_BYTES);
 #else
-  static constexpr int STAGES = I8_STAGES_OVERRIDE;   // pipeline-depth experiments (scripts/gpu_stages.sh): 3 stages already saturate
+  static constexpr int STAGES_RAW = I8_STAGES_OVERRIDE;   // pipeline-depth experiments
 #endif
+  static constexpr int STAGES = STAGES_RAW & ~1;
+  static_assert(STAGES >= 2, "ring too shallow");
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024;
   static constexpr int TMEM_COLS = (S * I8_TN > 256) ? 512 : ((S * I8_TN > 128) ? 256 : 128);
 };
