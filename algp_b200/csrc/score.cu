@@ -22,6 +22,9 @@
 #include <stdlib.h>
 
 #define ALGP_CONST 1.4189385332046727   // 0.5*log(2*pi*e), utils.py:10
+// workspace of algp_score_sets_tiled: [arrival counters: SCORE_SPLIT_MAX_B uint32][fragments]
+#define SCORE_SPLIT_MAX_B 16384
+#define SCORE_COUNTER_DOUBLES (SCORE_SPLIT_MAX_B / 2)
 
 struct ScoreArgs {
   KernelParams kp;
@@ -44,6 +47,7 @@ struct ScoreArgs {
   // [col0, col1); the accumulator fragments travel between launches through gpart [B][32 lanes][2]
   int col0, col1, first, last;
   double* gpart;
+  unsigned int* counters;  // PARTS > 1: arrivals per candidate (zero at allocation; every call adds PARTS to each)
 };
 
 __device__ __forceinline__ void ld256(const double* p, double& a, double& b, double& c, double& d) {
@@ -73,32 +77,28 @@ __device__ __forceinline__ void sc_load(double (&v)[4 * UNROLL], const double* p
   }
 }
 
-// SPLIT = 2: the 8 warps of a CTA work on 4 candidates at a time, warp w and warp w + 4 each taking half of the columns
-// of candidate slot w; the second warp hands its accumulator fragment over through shared memory and moves on, the first
-// adds it and runs the epilogue.  Used for small batches only (fewer candidates than half the resident warp slots),
-// where whole-candidate work items leave most of the machine idle.
-template <int UNROLL, bool PREFETCH, int THREADS, int SPLIT>
+// PARTS > 1: a candidate is scored by PARTS independent warps, each over a slice of the columns.  A warp stores its
+// accumulator fragment to gpart[cand][part], fences, and bumps the candidate's arrival counter; the warp that arrives
+// last adds the other fragments and runs the epilogue ("last one out" -- no barrier, no extra launch; the counters are
+// never reset: every call adds exactly PARTS to each, so arrival order is the old value modulo PARTS).  A candidate is
+// ~90 us of one warp's time under load, so a batch smaller than the resident warp slots leaves most of the machine idle
+// and ends with a long tail: finer work items fix that for short path lists (up to ~1.5 x the warp slots; beyond, whole
+// candidates per warp stream better).
+template <int UNROLL, bool PREFETCH, int THREADS, int PARTS>
 __global__ void __launch_bounds__(THREADS, 3) score_sets_k8_kernel(const ScoreArgs a) {
   const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
   const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
   const int d = a.kp.d;
   constexpr int STEP = 16 * UNROLL;
-  constexpr int CPB = THREADS / 32 / SPLIT;                 // candidates a CTA works on at a time
-  __shared__ double frag[SPLIT > 1 ? 2 : 1][SPLIT > 1 ? CPB : 1][64];
-  const int wic = threadIdx.x >> 5;
-  const int slot = SPLIT > 1 ? wic % CPB : 0, part = SPLIT > 1 ? wic / CPB : 0;
-  int par = 0;
 
-  for (int64_t it = SPLIT > 1 ? (int64_t)blockIdx.x : warp0; (SPLIT > 1 ? it * CPB : it) < a.B; it += SPLIT > 1 ? (int64_t)gridDim.x : nwarps) {
+  for (int64_t it = warp0; it < a.B * PARTS; it += nwarps) {
     int64_t cand = it;
-    int col0 = a.col0, col1 = a.col1;
-    bool valid = true;
-    if (SPLIT > 1) {
-      cand = it * CPB + slot;
-      valid = cand < a.B;
-      if (!valid) cand = a.B - 1;                           // keeps the CTA's barrier count uniform; nothing is written
-      const int span = ((a.ncols16 + SPLIT - 1) / SPLIT + STEP - 1) / STEP * STEP;
+    int col0 = a.col0, col1 = a.col1, part = 0;
+    if (PARTS > 1) {
+      cand = it / PARTS;
+      part = (int)(it - cand * PARTS);
+      const int span = ((a.ncols16 + PARTS - 1) / PARTS + STEP - 1) / STEP * STEP;
       col0 = part * span;
       col1 = col0 + span;
     }
@@ -146,14 +146,23 @@ __global__ void __launch_bounds__(THREADS, 3) score_sets_k8_kernel(const ScoreAr
     }
     double G0 = (c0[0] + c0[1]) + (c0[2] + c0[3]);         // G[g][2t]
     double G1 = (c1[0] + c1[1]) + (c1[2] + c1[3]);         // G[g][2t+1]
-    if (SPLIT > 1) {
-      if (part > 0) *reinterpret_cast<double2*>(&frag[par][slot][2 * lane]) = make_double2(G0, G1);
-      __syncthreads();
-      const double2 o = *reinterpret_cast<const double2*>(&frag[par][slot][2 * lane]);
-      par ^= 1;                                            // the other buffer next time: one barrier per iteration
-      if (part > 0 || !valid) continue;
-      G0 += o.x;
-      G1 += o.y;
+    if (PARTS > 1) {
+      double* mine = a.gpart + (cand * PARTS + part) * 64 + 2 * lane;
+      *reinterpret_cast<double2*>(mine) = make_double2(G0, G1);
+      __threadfence();
+      __syncwarp();
+      unsigned int old = 0;
+      if (lane == 0) old = atomicAdd(a.counters + cand, 1u);
+      old = __shfl_sync(0xffffffffu, old, 0);
+      if (old % PARTS != PARTS - 1) continue;              // another warp finishes this candidate
+      __threadfence();
+#pragma unroll
+      for (int p = 0; p < PARTS; ++p) {
+        if (p == part) continue;
+        const double2 o = __ldcg(reinterpret_cast<const double2*>(a.gpart + (cand * PARTS + p) * 64 + 2 * lane));
+        G0 += o.x;
+        G1 += o.y;
+      }
     }
     if (!a.last) {                                         // more column chunks to come: park the fragment
       *reinterpret_cast<double2*>(a.gpart + cand * 64 + 2 * lane) = make_double2(G0, G1);
@@ -211,20 +220,14 @@ __global__ void __launch_bounds__(THREADS, 3) score_sets_k8_kernel(const ScoreAr
 }
 
 template <int UNROLL, bool PREFETCH, int THREADS>
-static void score_k8_launch(const ScoreArgs& a, int sms, int blocks_per_sm, cudaStream_t st) {
+static void score_k8_launch(const ScoreArgs& a, int sms, int blocks_per_sm, int parts, cudaStream_t st) {
   const int wpb = THREADS / 32;
-  int64_t want = (a.B + wpb - 1) / wpb;
+  int64_t want = (a.B * parts + wpb - 1) / wpb;
   int64_t cap = (int64_t)sms * blocks_per_sm;
-  // half-size work items (SPLIT = 2) for batches that leave at least half of the resident warp slots (3 CTAs per SM)
-  // empty: 1000 candidates 0.078 -> 0.057 ms.  Larger batches lose more to the pairing barrier than the finer
-  // granularity returns (8192: 0.233 -> 0.259 ms, profiles/r02_score_tiling.log)
-  const int64_t slots = (int64_t)sms * 3 * wpb;
-  if (a.first && a.last && a.ncols16 >= 4 * 16 * UNROLL && 2 * a.B <= slots) {
-    want = (a.B + wpb / 2 - 1) / (wpb / 2);
-    score_sets_k8_kernel<UNROLL, PREFETCH, THREADS, 2><<<(int)(want < cap ? want : cap), THREADS, 0, st>>>(a);
-    return;
-  }
-  score_sets_k8_kernel<UNROLL, PREFETCH, THREADS, 1><<<(int)(want < cap ? want : cap), THREADS, 0, st>>>(a);
+  const int grid = (int)(want < cap ? want : cap);
+  if (parts == 4) score_sets_k8_kernel<UNROLL, PREFETCH, THREADS, 4><<<grid, THREADS, 0, st>>>(a);
+  else if (parts == 2) score_sets_k8_kernel<UNROLL, PREFETCH, THREADS, 2><<<grid, THREADS, 0, st>>>(a);
+  else score_sets_k8_kernel<UNROLL, PREFETCH, THREADS, 1><<<grid, THREADS, 0, st>>>(a);
 }
 
 // ---------------------------------------------------------------------------
@@ -383,7 +386,7 @@ extern "C" int algp_score_sets_large(const double* Wt, int64_t ldw, int64_t ncol
   if (a.ncols16 > ldw) return ALGP_ERR_INVALID;
   a.X = X; a.pi0 = pi0; a.idx = idx; a.delta = delta; a.delta_scalar = delta_scalar; a.skip = skip;
   a.k = k; a.B = B; a.H_base = H_base; a.scores = scores;
-  a.col0 = 0; a.col1 = a.ncols16; a.first = 1; a.last = 1; a.gpart = nullptr;
+  a.col0 = 0; a.col1 = a.ncols16; a.first = 1; a.last = 1; a.gpart = nullptr; a.counters = nullptr;
   if (B == 0) return ALGP_OK;
   cudaStream_t st = (cudaStream_t)stream;
   int dev = 0, sms = 148;
@@ -397,18 +400,39 @@ extern "C" int algp_score_sets_large(const double* Wt, int64_t ldw, int64_t ncol
     if (work && work_doubles < 0) {
       // algp_score_sets_tiled, chunked: one launch per chunk of -work_doubles columns, accumulator fragments in work [B][64]
       const int chunk = (int)(-work_doubles);
-      a.gpart = work;
+      a.gpart = work + SCORE_COUNTER_DOUBLES;
       for (int c0 = 0; c0 < a.ncols16 || c0 == 0; c0 += chunk) {
         a.col0 = c0;
         a.col1 = c0 + chunk;
         a.first = c0 == 0;
         a.last = c0 + chunk >= a.ncols16;
-        score_k8_launch<2, false, 256>(a, sms, 32, st);
+        score_k8_launch<2, false, 256>(a, sms, 32, 1, st);
         ALGP_LAUNCH_CHECK();
       }
       return ALGP_OK;
     }
-    score_k8_launch<2, false, 256>(a, sms, 32, st);
+    if (work && work_doubles > 0) {
+      // algp_score_sets_tiled, one launch: small batches as PARTS column slices per candidate (see the kernel)
+      const int64_t slots = (int64_t)sms * 3 * 8;                  // resident warps: 3 CTAs of 8 per SM
+      // measured (profiles/r02_score_tiling.log 6d): 256 sets 0.081 -> 0.042 ms and 1000 sets 0.068 -> 0.049 ms with 4 parts,
+      // 4096 sets 0.145 -> 0.133 ms with 2; from 8192 sets on whole candidates per warp win (0.225 vs 0.251 ms)
+      int parts = 1;
+      if (2 * B <= slots) parts = 4;
+      else if (2 * B <= 3 * slots) parts = 2;
+      const char* e = getenv("ALGP_SCORE_PARTS");                  // tuning
+      if (e) parts = atoi(e);
+      if (parts != 2 && parts != 4) parts = 1;
+      if (parts > 1 && (a.ncols16 < 32 * parts || B > SCORE_SPLIT_MAX_B || work_doubles < SCORE_COUNTER_DOUBLES + B * parts * 64))
+        parts = 1;
+      if (parts > 1) {
+        a.counters = (unsigned int*)work;
+        a.gpart = work + SCORE_COUNTER_DOUBLES;
+      }
+      score_k8_launch<2, false, 256>(a, sms, 32, parts, st);
+      ALGP_LAUNCH_CHECK();
+      return ALGP_OK;
+    }
+    score_k8_launch<2, false, 256>(a, sms, 32, 1, st);
   } else if (k <= SG_MAXK) {
     const int kp = (k + 7) / 8, kk = kp * 8;
     size_t smem = ((size_t)kk * (kk + 1) + kk + (size_t)kk * d) * 8 + (size_t)kk * 4 + 16;
@@ -452,7 +476,11 @@ extern "C" int algp_set_score_tile_cols(int cols) {
   return ALGP_OK;
 }
 
-extern "C" int64_t algp_score_sets_tiled_work_doubles(int64_t B) { return B > 0 ? B * 64 : 0; }
+// counters + fragments: [B][64] between chunk launches, [B][4 parts][64] for batches small enough to be split
+extern "C" int64_t algp_score_sets_tiled_work_doubles(int64_t B) {
+  if (B <= 0) return 0;
+  return SCORE_COUNTER_DOUBLES + (B <= SCORE_SPLIT_MAX_B ? B * 4 * 64 : B * 64);
+}
 
 extern "C" int algp_score_sets_tiled(const double* Wt, int64_t ldw, int64_t ncols, int64_t n_rows, const double* X, int d,
                                      const double* log_ls_host, double log_os, int kind, double noise, const double* pi0,
@@ -460,7 +488,7 @@ extern "C" int algp_score_sets_tiled(const double* Wt, int64_t ldw, int64_t ncol
                                      int k, int64_t B, double H_base, double* scores, double* work, int64_t work_doubles,
                                      void* stream) {
   if (k < 1 || k > 8 || B < 0 || n_rows < 1) return ALGP_ERR_INVALID;
-  if (B > 0 && (!work || work_doubles < B * 64 || ((uintptr_t)work & 15))) return ALGP_ERR_INVALID;
+  if (B > 0 && (!work || work_doubles < algp_score_sets_tiled_work_doubles(B) || ((uintptr_t)work & 15))) return ALGP_ERR_INVALID;
   // g_tile_cols > 0: that chunk; -1: plain single launch; 0 (auto): chunked launches where ONE call streams enough for
   // the L2 hit rate to pay for the per-chunk prologues (>= ~12 GB: 1.50 vs 1.69 ms on configs[2] for an isolated call;
   // back-to-back calls on the same rows find part of them in L2 anyway and the two are level), else the single launch
@@ -480,7 +508,7 @@ extern "C" int algp_score_sets_tiled(const double* Wt, int64_t ldw, int64_t ncol
     return algp_score_sets_large(Wt, ldw, ncols, X, d, log_ls_host, log_os, kind, noise, pi0, idx, delta, delta_scalar, skip,
                                  k, B, H_base, scores, B > 0 ? work : (double*)1, -(int64_t)chunk, stream);
   return algp_score_sets_large(Wt, ldw, ncols, X, d, log_ls_host, log_os, kind, noise, pi0, idx, delta, delta_scalar, skip, k,
-                               B, H_base, scores, nullptr, 0, stream);
+                               B, H_base, scores, chunk < 0 ? nullptr : work, chunk < 0 ? 0 : work_doubles, stream);
 }
 
 // ---------------------------------------------------------------------------

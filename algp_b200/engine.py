@@ -586,7 +586,8 @@ class PosteriorState(object):
             # small sets with a workspace: split tail / column chunks decided by the library (csrc/score.cu)
             nwork = _lib.lib.algp_score_sets_tiled_work_doubles(B)
             if getattr(self, "_tilework", None) is None or self._tilework.numel() < nwork:
-                self._tilework = torch.empty(nwork, dtype=torch.float64, device=idx.device)
+                # zero-filled: the head of the buffer holds the arrival counters of the split-candidate kernel
+                self._tilework = torch.zeros(nwork, dtype=torch.float64, device=idx.device)
             call("algp_score_sets_tiled", ptr(self.Wt), self.ldw, self.ncols, self.n_pad, ptr(self.X), self.hyper.d, ls_p,
                  self.hyper.log_os, self.hyper.kind, self.hyper.noise, ptr(self.pi), ptr(idx), ptr(delta),
                  float(delta_scalar), ptr(skip), k, B, float(hb), ptr(out), ptr(self._tilework), nwork, stream())

@@ -168,12 +168,18 @@ int algp_score_sets_large(const double* Wt, int64_t ldw, int64_t ncols, const do
                           const int32_t* idx, const double* delta, double delta_scalar, const uint8_t* skip, int k,
                           int64_t B, double H_base, double* scores, double* work, int64_t work_doubles, void* stream);
 int64_t algp_score_sets_large_work_doubles(int k, int64_t B);
-/* The same scores for k <= 8 with a workspace, which lets the library pick the launch structure: the plain single
- * launch, or -- for one call that streams >= ~12 GB of rows -- one launch per L2-sized column chunk with the
- * accumulator fragments parked in `work` between launches (random sets re-read every row of Wt many times; a chunk's
- * slice of Wt, n_rows x chunk x 8 bytes, fits the L2 where whole rows do not: 1.50 vs 1.69 ms on configs[2]).
- * work: algp_score_sets_tiled_work_doubles(B) doubles, 16-byte aligned.  algp_set_score_tile_cols(c): c > 0 forces
- * chunked launches of c columns (multiple of 64), -1 the plain single launch, 0 the default policy. */
+/* The same scores for k <= 8 with a workspace, which lets the library pick the launch structure:
+ *  - small batches (up to ~1.5 x the resident warp slots, ~5000 sets): every candidate is scored by 2 or 4 independent warps,
+ *    each over a slice of the columns; fragments and per-candidate arrival counters live in `work`, the warp that
+ *    arrives last finishes the candidate (no barrier, no extra launch);
+ *  - one call that streams >= ~12 GB of rows: one launch per L2-sized column chunk with the accumulator fragments
+ *    parked in `work` between launches (random sets re-read every row of Wt many times; a chunk's slice of Wt, n_rows x
+ *    chunk x 8 bytes, fits the L2 where whole rows do not: 1.50 vs 1.69 ms on configs[2]);
+ *  - else the plain single launch.
+ * work: algp_score_sets_tiled_work_doubles(B) doubles, 16-byte aligned, ZERO-FILLED when allocated and then left to
+ * the library (its head holds arrival counters that are never reset); one workspace per stream.
+ * algp_set_score_tile_cols(c): c > 0 forces chunked launches of c columns (multiple of 64), -1 the plain single
+ * launch, 0 the default policy. */
 int algp_score_sets_tiled(const double* Wt, int64_t ldw, int64_t ncols, int64_t n_rows, const double* X, int d,
                           const double* log_ls_host, double log_os, int kind, double noise, const double* pi0,
                           const int32_t* idx, const double* delta, double delta_scalar, const uint8_t* skip, int k,

@@ -43,12 +43,18 @@ def run(B, mode, tile=0, env=None, reps=12):
     return e0.elapsed_time(e1) / reps, out.clone()
 
 
-for B in (1000, 4096, 8192, 12000, 16384, 24000, 32768, 65536):
-    os.environ["ALGP_SCORE_NOSPLIT"] = "1"
-    t0, ref = run(B, "stream")
-    os.environ.pop("ALGP_SCORE_NOSPLIT", None)
-    t1, s1 = run(B, "stream")
-    t3, s3 = run(B, "tiled", 1024)
-    print("B=%5d  whole candidates per warp %.4f ms | split where it saves rounds %.4f (%.0e) | chunks/1024 %.4f (%.0e)"
-          % (B, t0, t1, float((s1 - ref).abs().max()), t3, float((s3 - ref).abs().max())))
+for B in (256, 1000, 4096, 8192, 10000, 12000, 16384, 32768, 65536):
+    os.environ.pop("ALGP_SCORE_PARTS", None)
+    t0, ref = run(B, "tiled", -1)
+    line = "B=%5d  one warp per candidate %.4f ms" % (B, t0)
+    for parts in (2, 4):
+        if B > 16384:
+            continue
+        os.environ["ALGP_SCORE_PARTS"] = str(parts)
+        t, s_ = run(B, "tiled", 0)
+        line += " | %d warps per candidate %.4f (%.0e)" % (parts, t, float((s_ - ref).abs().max()))
+    os.environ.pop("ALGP_SCORE_PARTS", None)
+    t, s_ = run(B, "tiled", 0)
+    line += " | default policy %.4f (%.0e)" % (t, float((s_ - ref).abs().max()))
+    print(line)
 _lib.lib.algp_set_score_tile_cols(0)

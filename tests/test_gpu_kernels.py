@@ -200,10 +200,11 @@ def test_score_sets_matches_oracle(kind, k):
 
 
 @pytest.mark.parametrize("kind", ["rbf", "matern"])
-@pytest.mark.parametrize("k,tile", [(1, 64), (5, 64), (8, 64), (8, 128), (8, 0), (3, 192)])
-def test_score_sets_tiled_matches_oracle_and_streaming(kind, k, tile):
-    """algp_score_sets_tiled (one launch of the k <= 8 kernel per column chunk, accumulator fragments parked in a work
-    buffer between launches) against the oracle and the single launch: several chunks per candidate, a column count that is not a multiple of the
+@pytest.mark.parametrize("k,tile", [(1, 64), (5, 64), (8, 64), (8, 128), (8, 0), (3, 192), (8, -2), (6, -4)])
+def test_score_sets_tiled_matches_oracle_and_streaming(kind, k, tile, monkeypatch):
+    """algp_score_sets_tiled -- one launch of the k <= 8 kernel per column chunk with the accumulator fragments parked in
+    a work buffer, or (tile 0 / -2 / -4) one launch with 4 / 2 / 4 independent warps per candidate and a last-arriver
+    epilogue -- against the oracle and the plain single launch, several calls on the same workspace: several chunks per candidate, a column count that is not a multiple of the
     64-column step (appended columns), empty / duplicate / zero-increment slots and skip flags."""
     from algp_b200 import _lib
     X, th, hy, static, mobile, pi0, cov, ss, ms, rng = scoring_problem(kind, n_side=24, n_base=300, d_extra=(2 if k == 5 else 0))
@@ -227,6 +228,9 @@ def test_score_sets_tiled_matches_oracle_and_streaming(kind, k, tile):
     ost = O.posterior_state(cov, pi1)
     skip = np.zeros(n, dtype=np.uint8)
     skip[rng.choice(n, n // 10, replace=False)] = 1
+    if tile < 0:                                   # -2 / -4: the default policy with 2 / 4 warps per candidate forced
+        monkeypatch.setenv("ALGP_SCORE_PARTS", str(-tile))
+        tile = 0
     assert _lib.lib.algp_set_score_tile_cols(tile) == 0
     try:
         for sk in (None, skip):
