@@ -121,7 +121,7 @@ def check(name, code):
 
 # kernels launched per call of the multi-kernel entry points (everything else launches one; host-only entry points
 # never go through call()); bench.py reads launch_count around its timed region for the "gpu_launches" it reports
-KERNELS_PER_CALL = {"algp_argmax": 1, "algp_argmax_exchange": 1, "algp_append": 3, "algp_append_block": 3}   # argmax: 2 beyond 2^18 values
+KERNELS_PER_CALL = {"algp_argmax": 2, "algp_argmax_exchange": 2, "algp_append": 3, "algp_append_block": 3}   # argmax: 1 up to 2^14 values
 launch_count = 0
 
 

@@ -56,7 +56,7 @@ def test_mailbox_exchange_matches_numpy_argmax(world):
             if epoch == 5:
                 sizes[:] = 300
             if epoch == 6:
-                sizes[0] = 300000                         # beyond the one-CTA scan: block partials + exchange
+                sizes[0] = 30000                          # beyond the one-CTA scan: block partials + exchange
             blocks, offs, off = [], [], 0
             for r in range(world):
                 x = rng.normal(size=int(sizes[r]))

@@ -416,7 +416,7 @@ def test_argmax_first_max_semantics():
     assert out[0:1].view(torch.float64).item() == 5.0
     # one-CTA path (n <= 2^18) and two-kernel path (beyond), ties, all -inf, a single value
     rng = np.random.default_rng(3)
-    for n in (1, 31, 1024, 5000, 262144, 262145, 700001):
+    for n in (1, 31, 1024, 5000, 16384, 16385, 262145, 700001):
         v = np.round(rng.normal(size=n), 2)
         vd = dev(v)
         _lib.call("algp_argmax", _lib.ptr(vd), n, 0, _lib.ptr(out), _lib.ptr(state_work), _lib.stream())
