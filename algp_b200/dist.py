@@ -61,19 +61,29 @@ class PeerExchange(object):
         nbytes = _lib.lib.algp_p2p_mailbox_bytes(self.world)
         if nbytes <= 0:
             raise RuntimeError("PeerExchange supports up to 16 ranks")
+        # every rank takes part in both collectives below whatever happens locally: a rank whose export or mapping
+        # failed reports it through the MIN all-reduce instead of leaving the others waiting
         self.local = C.c_void_p()
         handle = (C.c_ubyte * 64)()
-        _lib.call("algp_p2p_create", nbytes, C.byref(self.local), C.cast(handle, C.c_void_p))
+        ok = 1
+        rc = _lib.lib.algp_p2p_create(nbytes, C.byref(self.local), C.cast(handle, C.c_void_p))
+        if rc != 0:
+            ok = 0
+            self.local = None
+            self.error = "algp_p2p_create: " + _lib.lib.algp_last_cuda_error().decode()
         mine = torch.tensor(list(handle), dtype=torch.uint8, device=self.dev)
         allh = torch.empty(64 * self.world, dtype=torch.uint8, device=self.dev)
         dist.all_gather_into_tensor(allh, mine, group=group)
         allh = allh.cpu().numpy().reshape(self.world, 64)
         self.opened = []
         ptrs = []
-        ok = 1
         for r in range(self.world):
             if r == self.rank:
-                ptrs.append(self.local.value)
+                ptrs.append(self.local.value if self.local is not None else 0)
+                continue
+            if not allh[r].any():                 # that rank could not export its mailbox
+                ok = 0
+                ptrs.append(0)
                 continue
             buf = (C.c_ubyte * 64)(*allh[r].tolist())
             p = C.c_void_p()
@@ -237,9 +247,8 @@ def sharded_mean_var(hyper, train_x, train_var, y0, ymean, xs, test_var=None, pr
         test_var = None if test_var is None else test_var.index_select(0, tperm).contiguous()
     Npad = max(engine.BLK, engine.pad_to(N))
     if rank == src:
-        f = engine.GPFactor(hyper, train_x, diag_add=train_var, diag_scalar=hyper.noise,
-                            factor="auto" if precision in engine.I8_FAMILY else "dmma",
-                            factor_slices=engine.I8_FAST_FACTOR_SLICES if precision == "i8fast" else None)
+        fkind, fslices = engine.factor_plan(precision, N)
+        f = engine.GPFactor(hyper, train_x, diag_add=train_var, diag_scalar=hyper.noise, factor=fkind, factor_slices=fslices)
         alpha, _ = f.solve(y0)
         head = torch.cat([alpha, f.info.to(torch.float64)])
     else:

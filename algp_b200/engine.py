@@ -35,10 +35,21 @@ I8_FAST_FACTOR_SLICES = 5
 I8_FAST_SLICES = 4
 I8_FAMILY = ("i8", "i8fast")
 # precision "tf32" names the 1e-4 tier on the tensor cores.  Up to this many (padded) training points it is the
-# split-TF32 tcgen05 kernel (fp32 accumulation: 4.7e-5 s^2 at N = 4096); beyond, fp32 accumulation of N cancelling terms
-# leaves the tier (1.7e-4 s^2 at N = 16384, measured), and the same tier is served by the 4-plane digit GEMM
-# (5e-6 s^2, and faster there)
+# split-TF32 tcgen05 variance kernel on an fp64 factor (fp32 accumulation: 4.7e-5 s^2 at N = 4096); beyond, fp32
+# accumulation of N cancelling terms leaves the tier (1.7e-4 s^2 at N = 16384, measured), and the tier is served by the
+# digit path of "i8fast" (5-plane factor, 4-plane variance: 5e-6 s^2, and 2.7x faster there)
 TF32_MAX_N = 8192
+
+
+def factor_plan(precision, n_train):
+    """(factor kind, digit planes) of a precision mode: "i8" factors through 8-plane digit GEMMs where N is large enough
+    to pay ("auto"), the 1e-4-tier modes through 5 planes -- "i8fast" always, "tf32" above TF32_MAX_N (where it is the
+    same path as "i8fast") --, everything else through DMMA."""
+    if precision == "i8":
+        return "auto", None
+    if precision == "i8fast" or (precision == "tf32" and pad_to(n_train) > TF32_MAX_N):
+        return "auto", I8_FAST_FACTOR_SLICES
+    return "dmma", None
 
 
 def uses_digits(precision, n_train):

@@ -113,8 +113,8 @@ class GPR(object):
         self.dtype = np.float64      # np.float32 reproduces the reference's float32 kernel matrix (utils.py:19)
         # O(N^3) / O(N^2 M) arithmetic: "fp64" = DMMA; "i8" = exact INT8 digit GEMMs on tcgen05 for the variance and,
         # from N = 8192, the factorisation (same fp64 tier, ~7x faster at N = 16384); "i8fast" = the same digit path with
-        # 5 / 4 planes (1e-4 tier); "tf32" = the 1e-4 tier with an fp64 factor: split-TF32 variance on tcgen05 up to
-        # engine.TF32_MAX_N training points, the 4-plane digit GEMM beyond (where fp32 accumulation leaves the tier)
+        # 5 / 4 planes (1e-4 tier); "tf32" = the 1e-4 tier: fp64 factor + split-TF32 variance on tcgen05 up to
+        # engine.TF32_MAX_N training points, the "i8fast" path beyond (where fp32 accumulation leaves the tier)
         self.precision = "fp64"
         self._cache = {}
 

@@ -95,7 +95,7 @@ def _factor_for(gp, hyper, train_x, train_var, reorder=False):
     cache = getattr(gp, "_cache", None)
     prec = getattr(gp, "precision", "fp64")
     # precision "i8": factor through the recursive INT8 digit factorisation when N is large enough to pay
-    key = ("factor", _digest(train_x, train_var), hyper.key(), prec if prec in engine.I8_FAMILY else "dmma", bool(reorder))
+    key = ("factor", _digest(train_x, train_var), hyper.key(), engine.factor_plan(prec, np.shape(train_x)[0]), bool(reorder))
     if cache is not None and cache.get("factor_key") == key:
         return cache["factor"]
     dev = engine.require_cuda()
@@ -107,8 +107,8 @@ def _factor_for(gp, hyper, train_x, train_var, reorder=False):
         box = (lo, hi)
         x = x.index_select(0, perm).contiguous()
         wn = None if wn is None else wn.index_select(0, perm).contiguous()
-    f = engine.GPFactor(hyper, x, diag_add=wn, diag_scalar=hyper.noise, factor="auto" if prec in engine.I8_FAMILY else "dmma",
-                        factor_slices=engine.I8_FAST_FACTOR_SLICES if prec == "i8fast" else None)
+    fkind, fslices = engine.factor_plan(prec, train_x.shape[0])
+    f = engine.GPFactor(hyper, x, diag_add=wn, diag_scalar=hyper.noise, factor=fkind, factor_slices=fslices)
     f.perm, f.box = perm, box
     if cache is not None:
         cache.clear()
