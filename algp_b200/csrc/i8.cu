@@ -166,7 +166,8 @@ struct I8Cfg {
   // hang with 3 and 5 stages).
 #ifndef I8_STAGES_OVERRIDE
   // as deep as 200 KB allow, at most 8: the 4-plane variance GEMM takes 27.8 / 18.5 / 17.9 / 16.1 ms with 2 / 4 / 6 / 8 stages
-  static constexpr int STAGES_RAW = (S >= 8) ? 4 : ((200 * 1024) / STAGE_BYTES > 8 ? 8 : (200 * 1024) / STAGE_BYTES);
+  static constexpr int SMEM_BUDGET = (S <= 4) ? 104 * 1024 : 200 * 1024;    // S <= 4: two CTAs per SM
+  static constexpr int STAGES_RAW = (S >= 8) ? 4 : (SMEM_BUDGET / STAGE_BYTES > 8 ? 8 : SMEM_BUDGET / STAGE_BYTES);
 #else
   static constexpr int STAGES_RAW = I8_STAGES_OVERRIDE;   // pipeline-depth experiments
 #endif
@@ -232,8 +233,11 @@ __device__ __forceinline__ void issue_sparse(int L, int W, uint32_t td, uint32_t
 
 // MODE 0: row sums of squares per 64-column tile (variance path, nothing else is written)
 // MODE 1: C = alpha A B^T + beta C (optionally stored transposed)
+// S <= 4: the group accumulators take 256 TMEM columns and a 4-stage ring 96 KB, so TWO CTAs fit an SM and one tile's
+// prologue / epilogue (TMEM zero-fill, plan decode, pipeline ramp, tcgen05.ld + Horner: about half of a 4-plane tile's
+// time) overlaps the other tile's MMAs.
 template <int S, int MODE>
-__global__ void __launch_bounds__(I8_THREADS, 1)
+__global__ void __launch_bounds__(I8_THREADS, (S <= 4) ? 2 : 1)
 gemm_i8_kernel(const I8Gemm p) {
   using C = I8Cfg<S>;
   extern __shared__ unsigned char i8_smem_raw[];
