@@ -244,7 +244,7 @@ class HotPath(object):
         ctx = None
         for _ in range(num_samples):
             if ctx is None:
-                ctx = engine.MIContext(state.hyper, state.X, pi)
+                ctx = engine.MIContext(state.hyper, state.X, pi, precision=state.precision)
             ent_a = state.H_base_dev + state.greedy_utilities(d)
             ut = ctx.greedy_utilities(ent_a, self.static_std, self.mobile_std).contiguous()
             state.argmax(ut, 0, out=pair)
@@ -295,7 +295,7 @@ class HotPath(object):
         if self._use_mi():
             ctx = getattr(state, "_mi_ctx", None)
             if ctx is None:
-                ctx = state._mi_ctx = engine.MIContext(state.hyper, state.X, pi, full_inverse=True)
+                ctx = state._mi_ctx = engine.MIContext(state.hyper, state.X, pi, full_inverse=True, precision=state.precision)
                 ctx.check()
             scores = ctx.path_utilities(scores, idx_d, state._skip, self.static_std, self.mobile_std).contiguous()
         pair = state.argmax(scores)

@@ -693,8 +693,11 @@ class MIContext(object):
     (reference agent.py:330-339): A2 = Sigma_AbarAbar (unsampled locations) and A3 = Sigma + D
     (D = per-location noise variance on the sampled locations, 0 elsewhere)."""
 
-    def __init__(self, hyper, X, pi, full_inverse=False):
+    def __init__(self, hyper, X, pi, full_inverse=False, precision="fp64"):
+        """precision="i8": the two n-scale factorizations run as INT8 digit GEMMs where n is large enough to pay
+        (GPFactor factor="auto"), as for the posterior state itself."""
         dev = X.device
+        fkind = "auto" if precision == "i8" else "dmma"
         self.n = X.shape[0]
         pi = np.asarray(pi, dtype=np.float64)
         sampled = pi > 0
@@ -706,7 +709,7 @@ class MIContext(object):
         self.inv2 = self.inv3 = None
         if self.n_abar:
             xa = X.index_select(0, to_dev(abar, dtype=torch.int64, device=dev)).contiguous()
-            self.f2 = GPFactor(hyper, xa, diag_add=None, diag_scalar=hyper.noise)        # cov_matrix[~S][:, ~S]
+            self.f2 = GPFactor(hyper, xa, diag_add=None, diag_scalar=hyper.noise, factor=fkind)        # cov_matrix[~S][:, ~S]
             self.ld2 = self.f2.logdet_quad()[0:1].clone()
             self.diag2 = self._inv_diag(self.f2)[:self.n_abar]
             if full_inverse:
@@ -716,7 +719,7 @@ class MIContext(object):
             self.ld2 = torch.zeros(1, dtype=torch.float64, device=dev)
             self.diag2 = torch.ones(1, dtype=torch.float64, device=dev)
         var_all = np.where(sampled, 1.0 / np.where(sampled, pi, 1.0), 0.0)               # agent.py:334-337
-        self.f3 = GPFactor(hyper, X, diag_add=to_dev(var_all, device=dev), diag_scalar=hyper.noise)
+        self.f3 = GPFactor(hyper, X, diag_add=to_dev(var_all, device=dev), diag_scalar=hyper.noise, factor=fkind)
         self.ld3 = self.f3.logdet_quad()[0:1].clone()
         self.diag3 = self._inv_diag(self.f3)[:self.n]
         if full_inverse:

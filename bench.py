@@ -482,7 +482,7 @@ def fit_predict_bench(torch, engine, n_train, grid_side, reps, peak_hbm):
 
 
 def episode_bench(torch, engine, side=200, n_pilot=1024, acquisitions=500, per_batch=4, n_paths=256, path_len=16,
-                  distributed=False, dist=None, rank=0, world=1, dev=None):
+                  distributed=False, dist=None, rank=0, world=1, dev=None, oracle_batches=0):
     """BASELINE configs[4]: active-sampling episode on a side x side field: `acquisitions` static picks in batches
     of `per_batch` (greedy, rank-1 appends), each batch followed by scoring `n_paths` candidate paths of `path_len`
     mobile readings and committing the winner.  Path enumeration (env.py) is the planner's job: paths here are
@@ -490,26 +490,9 @@ def episode_bench(torch, engine, side=200, n_pilot=1024, acquisitions=500, per_b
     posterior state, scores a contiguous block of the paths (algp_b200.dist.sharded_best, winners over the NVLink
     mailboxes) and applies the same commits; rank 0 then repeats the episode alone and the chosen indices must agree."""
     from algp_b200.episode import run_episode
-    from algp_b200.utils import generate_gaussian_data
-    grid, _ = generate_gaussian_data(side, side, seed=1)
-    grid = grid.astype(np.float64)
+    hyper, grid, static, mobile, path_fn = episode_problem(engine, side, n_pilot, n_paths, path_len)
     n = len(grid)
-    rng = np.random.default_rng(3)
-    static = np.zeros(n, bool)
-    static[rng.choice(n, n_pilot, replace=False)] = True
-    mobile = np.zeros(n, bool)
-    hyper = engine.Hyper(np.log([side / 16.0] * 2), 0.0, np.log(1e-2), "rbf")
     batches = acquisitions // per_batch
-
-    def path_fn(b, picks):
-        prng = np.random.default_rng(1000 + b)
-        starts = np.array(picks)[prng.integers(0, len(picks), n_paths)]
-        r, c = starts // side, starts % side
-        dr, dc = prng.integers(-1, 2, n_paths), prng.integers(-1, 2, n_paths)
-        steps = np.arange(1, path_len + 1)[None, :]
-        rr = np.clip(r[:, None] + dr[:, None] * steps, 0, side - 1)
-        cc = np.clip(c[:, None] + dc[:, None] * steps, 0, side - 1)
-        return (rr * side + cc).astype(np.int32)
 
     Xd = engine.to_dev(grid, device=dev)
     run_episode(hyper, Xd, static, mobile, STATIC_STD, MOBILE_STD, 2, per_batch, path_fn, distributed=distributed)   # warm-up
@@ -543,7 +526,51 @@ def episode_bench(torch, engine, side=200, n_pilot=1024, acquisitions=500, per_b
         dist.barrier()
     out["ms_per_acquisition"] = ms_a
     out["ms_per_batch"] = ms_b
+    if not distributed and oracle_batches > 0:
+        # chosen-index agreement with the fp64 oracle at this scale (BASELINE.md, configs[4] row): the first batches
+        # against oracle.LeanEpisode, the restructured episode that never forms an n x n matrix
+        import oracle as O
+        t0 = time.perf_counter()
+        th = O.Theta(hyper.log_ls.copy(), hyper.log_os, hyper.log_noise, "rbf")
+        ep = O.LeanEpisode(th, grid, static, mobile, STATIC_STD, MOBILE_STD)
+        same, dH = True, 0.0
+        for b in range(min(oracle_batches, batches)):
+            picks = ep.greedy(per_batch)
+            paths = path_fn(b, picks)
+            sc = ep.score_paths(paths)
+            best = int(np.argmax(sc))
+            same = same and picks == res["picks"][b] and best == res["best_paths"][b]
+            dH = max(dH, abs(float(sc[best]) - res["H"][b]) / abs(float(sc[best])))
+            ep.commit_path(paths[best], sc[best])
+        out["oracle_agreement"] = {"batches_checked": min(oracle_batches, batches), "same_picks_and_paths": bool(same),
+                                   "max_rel_entropy_diff": dH, "cpu_s": time.perf_counter() - t0}
     return out
+
+
+def episode_problem(engine, side=200, n_pilot=1024, n_paths=256, path_len=16):
+    """The synthetic episode of configs[4]: field grid, pilot flags, hyper-parameters and the per-batch candidate paths
+    (straight runs of `path_len` locations starting at the batch's picks).  Shared with tests/test_gpu_fullsize.py."""
+    from algp_b200.utils import generate_gaussian_data
+    grid, _ = generate_gaussian_data(side, side, seed=1)
+    grid = grid.astype(np.float64)
+    n = len(grid)
+    rng = np.random.default_rng(3)
+    static = np.zeros(n, bool)
+    static[rng.choice(n, n_pilot, replace=False)] = True
+    mobile = np.zeros(n, bool)
+    hyper = engine.Hyper(np.log([side / 16.0] * 2), 0.0, np.log(1e-2), "rbf")
+
+    def path_fn(b, picks):
+        prng = np.random.default_rng(1000 + b)
+        starts = np.array(picks)[prng.integers(0, len(picks), n_paths)]
+        r, c = starts // side, starts % side
+        dr, dc = prng.integers(-1, 2, n_paths), prng.integers(-1, 2, n_paths)
+        steps = np.arange(1, path_len + 1)[None, :]
+        rr = np.clip(r[:, None] + dr[:, None] * steps, 0, side - 1)
+        cc = np.clip(c[:, None] + dc[:, None] * steps, 0, side - 1)
+        return (rr * side + cc).astype(np.int32)
+
+    return hyper, grid, static, mobile, path_fn
 
 
 def patched_reference_style_agent():
@@ -1333,7 +1360,7 @@ def run_ours(args, rank, world, local_rank):
         except Exception as e:       # the headline line must still print
             extra["fit_predict_error"] = repr(e)
         try:
-            extra["episode"] = episode_bench(torch, engine)
+            extra["episode"] = episode_bench(torch, engine, oracle_batches=0 if args.no_cpu else 6)
         except Exception as e:
             extra["episode_error"] = repr(e)
         try:

@@ -38,7 +38,7 @@ __all__ = [
     "predictive_distribution", "predictive_distribution_chol",
     "get_sampled_dataset", "precisions_from_flags", "greedy_literal",
     "best_path_literal", "set_entropy_literal", "posterior_state",
-    "greedy_restructured", "score_sets_restructured", "mll_loss", "mll_loss_grad",
+    "greedy_restructured", "score_sets_restructured", "LeanEpisode", "mll_loss", "mll_loss_grad",
     "gaussian_mixture_field",
 ]
 
@@ -441,6 +441,106 @@ def greedy_restructured(cov_matrix, static_sampled, mobile_sampled, static_std, 
     if return_utilities:
         return picks, np.array(uts)
     return picks
+
+
+class LeanEpisode(object):
+    """The episode of Agent.run_ipp (agent.py:133-201: greedy picks, path scoring, commits) in the restructured form of
+    SURVEY.md 9.3 WITHOUT ever forming an n x n matrix, so that BASELINE configs[4] (a 200 x 200 field, n = 40 000) can
+    be checked on the host: only W = L^-1 Sigma_{B,:} (one row per sampled reading, n columns) and diag(P) are kept;
+    a commit at location j with precision increment delta appends the row  P_{j,:} / sqrt(P_jj + 1/delta)  to W.
+    Pinned against greedy_literal / best_path_literal on small fields in tests/test_oracle.py."""
+
+    def __init__(self, theta, X, static_sampled, mobile_sampled, static_std, mobile_std):
+        import scipy.linalg as sla
+        self.theta, self.X = theta, np.asarray(X, dtype=np.float64)
+        self.ss, self.ms = static_std, mobile_std
+        self.static = np.array(static_sampled, dtype=bool)
+        self.mobile = np.array(mobile_sampled, dtype=bool)
+        self.pi = precisions_from_flags(self.static, self.mobile, static_std, mobile_std)
+        self.prior = np.exp(theta.log_outputscale) + np.exp(theta.log_noise)          # diag of cov_matrix (agent.py:90)
+        base = np.nonzero(self.pi > 0)[0]
+        n = len(self.X)
+        if len(base):
+            A = self._sigma(base, base) + np.diag(1.0 / self.pi[base])
+            L = np.linalg.cholesky(A)
+            self.W = sla.solve_triangular(L, self._sigma(base, None), lower=True)
+            self.H = len(base) * CONST + np.sum(np.log(np.diag(L)))
+        else:
+            self.W = np.zeros((0, n))
+            self.H = 0.0
+        self.diagP = self.prior - np.sum(self.W * self.W, axis=0)
+
+    def _sigma(self, rows, cols):
+        """Sigma[rows, cols] = s^2 k + sigma_n^2 [row location == column location] (cov_matrix of agent.py:90)."""
+        rows = np.asarray(rows)
+        xc = self.X if cols is None else self.X[np.asarray(cols)]
+        K = kernel_matrix(self.theta, self.X[rows], xc, "fp64")
+        cidx = np.arange(len(self.X)) if cols is None else np.asarray(cols)
+        K[rows[:, None] == cidx[None, :]] += np.exp(self.theta.log_noise)
+        return K
+
+    def _P(self, rows, cols):
+        rows, cidx = np.asarray(rows), (np.arange(len(self.X)) if cols is None else np.asarray(cols))
+        return self._sigma(rows, cols) - self.W[:, rows].T @ self.W[:, cidx]
+
+    def commit(self, j, delta, make_static):
+        row = self._P([j], None)[0]
+        w = row / np.sqrt(row[j] + 1.0 / delta)
+        self.W = np.vstack([self.W, w[None, :]])
+        self.diagP = self.diagP - w * w
+        self.pi[j] += delta
+        if make_static:
+            self.static[j] = True
+        else:
+            self.mobile[j] = True
+
+    def greedy(self, num_samples):
+        """agent.py:313-354 (entropy criterion): picks, and H advanced by the chosen utilities."""
+        d = 1.0 / self.ss ** 2
+        picks = []
+        for _ in range(num_samples):
+            pi = self.pi
+            with np.errstate(divide="ignore"):
+                ut = np.where(pi == 0, CONST, 0.0) + 0.5 * (np.log1p(d * self.diagP) - np.log(pi + d)
+                                                             + np.where(pi > 0, np.log(np.where(pi > 0, pi, 1.0)), 0.0))
+            ut[self.static] = -np.inf
+            j = int(np.argmax(ut))
+            picks.append(j)
+            self.H += ut[j]
+            self.commit(j, d, True)
+        return picks
+
+    def score_paths(self, paths):
+        """agent.py:373-400 (entropy criterion): H(S + mobile readings of the path) for every path (rows of -1-padded
+        indices; already-mobile locations and repeats add nothing)."""
+        dm = 1.0 / self.ms ** 2
+        out = np.empty(len(paths))
+        for c, path in enumerate(paths):
+            seen, ii = set(), []
+            for j in path:
+                j = int(j)
+                if j < 0 or self.mobile[j] or j in seen:
+                    continue
+                seen.add(j)
+                ii.append(j)
+            if not ii:
+                out[c] = self.H
+                continue
+            ii = np.array(ii)
+            M = np.eye(len(ii)) + dm * self._P(ii, ii)
+            ld = 2.0 * np.sum(np.log(np.diag(np.linalg.cholesky(M))))
+            p0 = self.pi[ii]
+            corr = np.sum(np.log(p0 + dm)) - np.sum(np.log(p0[p0 > 0]))
+            out[c] = self.H + np.sum(p0 == 0) * CONST + 0.5 * (ld - corr)
+        return out
+
+    def commit_path(self, path, score):
+        dm = 1.0 / self.ms ** 2
+        for j in path:
+            j = int(j)
+            if j >= 0 and not self.mobile[j]:
+                self.commit(j, dm, False)
+        self.H = float(score)
 
 
 # ----------------------------------------------------------------------------

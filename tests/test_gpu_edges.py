@@ -212,3 +212,34 @@ def test_state_is_extended_not_rebuilt_between_planning_steps():
     mo = np.zeros(n, bool); mo[list(mobile1)] = True
     assert O.greedy_restructured(cov, st, mo, 0.1, 1.0, 2) == picks2
     assert O.best_path_literal(cov, st, mo, 0.1, 1.0, paths2, picks2) == best2
+
+
+def test_staging_buffers_are_safe_to_reuse():
+    """engine.to_dev copies through two reused pinned buffers per device; a buffer is only overwritten once the copy
+    that last read it has finished, so a burst of uploads of different sizes and dtypes lands intact."""
+    rng = np.random.default_rng(0)
+    hosts, devs = [], []
+    for i in range(12):
+        n = int(rng.integers(1, 400000))
+        if i % 3 == 0:
+            a = rng.integers(-5, 5, size=(n, 3)).astype(np.int32)
+            t = engine.to_dev(a, dtype=torch.int32)
+        elif i % 3 == 1:
+            a = rng.normal(size=n)
+            t = engine.to_dev(a)
+        else:
+            a = (rng.random(n) < 0.5).astype(np.uint8)
+            t = engine.to_dev(a, dtype=torch.uint8)
+        hosts.append(a)
+        devs.append(t)
+    big = rng.normal(size=3_000_000)                         # larger than the initial buffers: they grow
+    tb = engine.to_dev(big)
+    torch.cuda.synchronize()
+    for a, t in zip(hosts, devs):
+        np.testing.assert_array_equal(t.cpu().numpy(), a)
+    np.testing.assert_array_equal(tb.cpu().numpy(), big)
+    assert engine.to_dev(np.zeros((0, 4))).shape == (0, 4)
+    # float32 host data is converted, a device tensor passes through
+    f32 = rng.normal(size=100).astype(np.float32)
+    np.testing.assert_array_equal(engine.to_dev(f32).cpu().numpy(), f32.astype(np.float64))
+    assert engine.to_dev(tb) is not None and engine.to_dev(tb).data_ptr() == tb.data_ptr()

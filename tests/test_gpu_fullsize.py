@@ -195,3 +195,28 @@ def test_config_c_mean_and_variance_match_the_oracle_at_full_size():
             assert dm <= 1e-4 and dv <= 1e-4, (mode, report)
         torch.cuda.empty_cache()
     print("config C vs oracle (max |dmean|/max|mean|, max |dvar|/s^2, max |dvar|/var):", report)
+
+
+def test_config_d_episode_matches_the_lean_oracle_at_full_scale():
+    """configs[4] at its own scale: the 200 x 200 field (n = 40 000) with 1024 pilot samples, the first batches of the
+    bench's episode (4 greedy picks, 256 candidate paths of 16 readings, commit) on the GPU against oracle.LeanEpisode
+    -- the restructured fp64 episode that never forms an n x n matrix, pinned to the literal agent.py loops on small
+    fields in tests/test_oracle.py.  Chosen indices identical, entropies within the log-det tier (rel 1e-8)."""
+    from algp_b200.episode import run_episode
+    hyper, grid, static, mobile, path_fn = bench.episode_problem(engine)
+    batches, per_batch = 4, 4
+    res = run_episode(hyper, dev(grid), static, mobile, bench.STATIC_STD, bench.MOBILE_STD, batches, per_batch, path_fn,
+                      return_scores=True, distributed=False)
+    th = O.Theta(hyper.log_ls.copy(), hyper.log_os, hyper.log_noise, "rbf")
+    ep = O.LeanEpisode(th, grid, static, mobile, bench.STATIC_STD, bench.MOBILE_STD)
+    for b in range(batches):
+        picks = ep.greedy(per_batch)
+        assert res["picks"][b] == picks, b
+        paths = path_fn(b, picks)
+        scores = ep.score_paths(paths)
+        best = int(np.argmax(scores))
+        assert res["best_paths"][b] == best, b
+        assert res["scores"][b] == pytest.approx(float(scores[best]), rel=1e-8)
+        ep.commit_path(paths[best], scores[best])
+    np.testing.assert_allclose(res["state"].diagP.cpu().numpy(), ep.diagP, rtol=0, atol=1e-9)
+    np.testing.assert_allclose(res["state"].pi.cpu().numpy(), ep.pi, rtol=1e-12)

@@ -108,3 +108,29 @@ def test_field_generator_seeded():
     g2, y2 = O.gaussian_mixture_field(16, 12, seed=1)
     assert g1.shape == (192, 2) and (y1 == y2).all() and y1.max() > 0
     assert (g1[1] == [0, 1]).all()          # row-major (row, col) grid as utils.py:91-92
+
+
+@pytest.mark.parametrize("kind", ["rbf", "matern"])
+def test_lean_episode_equals_literal_loops(kind):
+    """oracle.LeanEpisode (the memory-lean restructured episode used to check BASELINE configs[4] at its own 200 x 200
+    scale) against the literal loops of agent.py:295-403 over three batches of greedy picks, path scoring and commits."""
+    X, th, cov, static, mobile, rng = small_problem(kind, n=70, seed=5)
+    ss, ms = 0.1, 1.0
+    ep = O.LeanEpisode(th, X, static, mobile, ss, ms)
+    st, mo = static.copy(), mobile.copy()
+    assert ep.H == pytest.approx(O.set_entropy_literal(cov, st, mo, ss, ms), rel=1e-12)
+    for b in range(3):
+        picks = ep.greedy(2)
+        assert picks == [int(p) for p in O.greedy_literal(cov, st, mo, ss, ms, 2)]
+        paths = np.stack([rng.choice(len(X), 6, replace=False) for _ in range(9)]).astype(np.int64)
+        paths[0, 4] = paths[0, 1]                           # a repeat inside a path
+        paths[2, 5] = -1                                    # a ragged path
+        scores = ep.score_paths(paths)
+        lists = [[int(v) for v in row if v >= 0] for row in paths]
+        best, ut = O.best_path_literal(cov, st, mo, ss, ms, lists, picks, return_utilities=True)
+        np.testing.assert_allclose(scores, ut, rtol=1e-11, atol=1e-10)
+        assert int(np.argmax(scores)) == best
+        ep.commit_path(paths[best], scores[best])
+        st[picks] = True
+        mo[lists[best]] = True
+        assert ep.H == pytest.approx(O.set_entropy_literal(cov, st, mo, ss, ms), rel=1e-11)
