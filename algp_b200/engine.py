@@ -506,13 +506,31 @@ class PosteriorState(object):
 
     # ---- resident posterior covariance ("If the build precomputes P (allowed)") ----
     COV_MAX_K = 128                # slots per candidate algp_score_sets_cov accepts
-    STREAM_BYTES_PER_S = 10.0e12   # measured L2->SM delivery of score_sets_k8_kernel (profiles/r01_prof_score_summary.csv)
+    # priors of the rent-or-buy rule, replaced by measurements as soon as there are any: every streaming call is timed with
+    # CUDA events (_harvest_stream_time) and every build calibrates the build rate (_measured_build_rate)
+    STREAM_BYTES_PER_S = 10.0e12   # L2->SM delivery of score_sets_k8_kernel (profiles/r02_prof_score_summary.csv)
     COV_FLOPS_PER_S = {"fp64": 30.0e12, "i8": 100.0e12}   # lower-triangle SYRK rates of algp_gemm_nt / algp_gemm_nt_i8
 
+    _measured_build_rate = {}      # kind -> flops/s of the last build_cov() in this process (replaces the prior below)
+
     def cov_build_seconds(self):
-        """Model of the build_cov() time: n_pad^2 x ncols flops (lower triangle of a SYRK) at the measured rates."""
+        """Expected build_cov() time: n_pad^2 x ncols flops (lower triangle of a SYRK) at the rate the last build in this
+        process measured (CUDA events), or at the prior COV_FLOPS_PER_S (round-1 measurements) before the first one."""
         kind = "i8" if (self.precision == "i8" and 1024 <= pad_to(self.ncols, 32) <= I8_MAX_K) else "fp64"
-        return float(self.n_pad) ** 2 * max(self.ncols, 1) / self.COV_FLOPS_PER_S[kind] + 1.0e-3
+        rate = PosteriorState._measured_build_rate.get(kind, self.COV_FLOPS_PER_S[kind])
+        return float(self.n_pad) ** 2 * max(self.ncols, 1) / rate + 1.0e-3
+
+    def _harvest_stream_time(self):
+        """Add the MEASURED duration of the streaming score calls that have completed since the last look (CUDA events
+        recorded around each call, read without synchronising) to the rent-or-buy account; calls still in flight stay
+        on the books at their modelled cost."""
+        pending = []
+        for e0, e1, modelled in getattr(self, "_stream_events", []):
+            if e1.query():
+                self._stream_s += e0.elapsed_time(e1) * 1e-3 - modelled
+            else:
+                pending.append((e0, e1, modelled))
+        self._stream_events = pending
 
     def build_cov(self):
         """P = Sigma + sigma_n^2 I - Wt Wt^T, lower triangle, [n_pad x n_pad] fp64 resident in HBM: the posterior
@@ -520,6 +538,8 @@ class PosteriorState(object):
         entries per set (algp_score_sets_cov) instead of streaming k rows of Wt.  One kernel-matrix build plus one
         SYRK (DMMA, or exact INT8 digit GEMM with precision "i8").  append / append_block keep it: the new columns are
         folded in by _sync_cov (P -= w w^T) before the next scoring call that reads it."""
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
         P, _ = kbuild(self.hyper, self.X, None, self.n_pad, self.n_pad, diag_scalar=self.hyper.noise)
         kpad = pad_to(self.ncols, 32)
         if self.ncols > 0:
@@ -533,14 +553,22 @@ class PosteriorState(object):
             else:
                 call("algp_gemm_nt", ptr(self.Wt), self.ldw, ptr(self.Wt), self.ldw, ptr(P), P.stride(0), self.n_pad,
                      self.n_pad, kpad, -1.0, 1.0, 1, stream())
+        e1.record()
         self.P = P
         self._P_ncols = self.ncols
+        if self.ncols > 0 and self.n_pad >= 4096:
+            # calibrate the rent-or-buy rule with this build (a build is rare and tens of ms: the wait is noise)
+            e1.synchronize()
+            kind = "i8" if (self.precision == "i8" and 1024 <= kpad <= I8_MAX_K) else "fp64"
+            secs = max(e0.elapsed_time(e1) * 1e-3 - 1.0e-3, 1.0e-4)
+            PosteriorState._measured_build_rate[kind] = float(self.n_pad) ** 2 * self.ncols / secs
         return P
 
     def drop_cov(self):
         self.P = None
         self._P_ncols = 0
         self._stream_s = 0.0
+        self._stream_events = []
 
     def _sync_cov(self):
         """Bring the resident P up to date with the columns appended since it was built / last synchronised: every
@@ -563,6 +591,7 @@ class PosteriorState(object):
         if self.cov_mode == "never" or k > self.COV_MAX_K or self.ncols == 0:
             return False
         if self.cov_mode == "auto":
+            self._harvest_stream_time()
             if self._stream_s < self.cov_build_seconds():
                 return False
             free, total = torch.cuda.mem_get_info(self.X.device)
@@ -592,7 +621,22 @@ class PosteriorState(object):
             call("algp_score_sets_cov", ptr(self.P), self.P.stride(0), ptr(self.pi), ptr(idx), ptr(delta),
                  float(delta_scalar), ptr(skip), k, B, float(hb), ptr(out), stream())
             return out
-        self._stream_s += 8.0 * B * k * max(self.ncols, 1) / self.STREAM_BYTES_PER_S
+        modelled = 8.0 * B * k * max(self.ncols, 1) / self.STREAM_BYTES_PER_S
+        self._stream_s += modelled
+        ev = None
+        if self.cov_mode == "auto" and k <= self.COV_MAX_K and self.ncols > 0:
+            ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True), modelled)
+            ev[0].record()
+        try:
+            return self._score_streaming(idx, delta, delta_scalar, skip, k, B, hb, out, ls_p)
+        finally:
+            if ev is not None:
+                ev[1].record()
+                if not hasattr(self, "_stream_events"):
+                    self._stream_events = []
+                self._stream_events.append(ev)
+
+    def _score_streaming(self, idx, delta, delta_scalar, skip, k, B, hb, out, ls_p):
         if k <= 8 and self._want_tiled(B, k):
             # small sets with a workspace: split tail / column chunks decided by the library (csrc/score.cu)
             nwork = _lib.lib.algp_score_sets_tiled_work_doubles(B)

@@ -221,6 +221,52 @@ def config_dict():
 # --------------------------------------------------------------------------------------
 # our arm
 # --------------------------------------------------------------------------------------
+def i8_surviving_work(torch, km, lm, S, MT, NT, kchunks):
+    """The MMA work that survives the occupancy masks of the INT8 digit variance GEMM (csrc/i8.cu plan_word /
+    issue_sparse, restated on the masks): for every (128-row tile of K(X*,X), 64-row tile of Linv, 32-byte k chunk) inside
+    the triangular k-range, the A planes [pmin, S-1-qmin] meet the B planes [qmin, min(S-p, qmax+1)).  Returns
+    (surviving chunks, in-range chunks, MMA instructions, accumulator columns issued)."""
+    mld = (kchunks + 7) // 8 * 8
+    a = km.view(-1)[: MT * mld].view(MT, mld)[:, :kchunks].to(torch.int32)
+    b = lm.view(-1)[: NT * mld].view(NT, mld)[:, :kchunks].to(torch.int32)
+
+    def lowest(v):
+        out = torch.full_like(v, 99)
+        for p in range(S - 1, -1, -1):
+            out = torch.where(((v >> p) & 1) > 0, torch.full_like(v, p), out)
+        return out
+
+    def highest(v):
+        out = torch.full_like(v, -1)
+        for p in range(S):
+            out = torch.where(((v >> p) & 1) > 0, torch.full_like(v, p), out)
+        return out
+    pmin, qmin, qmax = lowest(a), lowest(b), highest(b)
+    kend = (torch.arange(NT, device=b.device) * 64 + 64) // 32
+    inrange = torch.arange(kchunks, device=b.device)[None, :] < kend[:, None]
+    qmin = torch.where(inrange, qmin, torch.full_like(qmin, 99))
+    cntA = torch.stack([(pmin == p).sum(0) for p in range(S)], 0).double()
+    cntB = torch.zeros((S, S, kchunks), dtype=torch.float64, device=b.device)
+    for q0 in range(S):
+        for q1 in range(S):
+            cntB[q0, q1] = ((qmin == q0) & (qmax == q1)).sum(0)
+    H = torch.einsum("pk,qrk->pqr", cntA, cntB).cpu().numpy()
+    chunks = mmas = cols = 0.0
+    for p in range(S):
+        for q0 in range(S):
+            for q1 in range(q0, S):
+                c = H[p, q0, q1]
+                if c == 0 or p + q0 > S - 1:
+                    continue
+                chunks += c
+                for pa in range(p, S - q0):
+                    nplanes = min(S - pa, q1 + 1) - q0
+                    for part in ([nplanes] if nplanes <= 4 else [4, nplanes - 4]):
+                        mmas += c
+                        cols += c * part * 64
+    return chunks, float(MT) * float(inrange.sum().item()), mmas, cols
+
+
 def med_of(v):
     return float(np.median(v)) if len(v) else None
 
@@ -244,6 +290,7 @@ def fit_predict_bench(torch, engine, n_train, grid_side, reps, peak_hbm):
     M = xs.shape[0]
     Npad = max(128, engine.pad_to(n_train))
     Mpad = max(128, engine.pad_to(M))
+    N_, Mp_ = float(Npad), float(Mpad)
     dev = xd.device
     # buffers live across repetitions: the timed region is kernels only (inputs resident in HBM)
     A = torch.empty((Npad, Npad), dtype=torch.float64, device=dev)
@@ -379,6 +426,31 @@ def fit_predict_bench(torch, engine, n_train, grid_side, reps, peak_hbm):
             times["variance_i8_7planes"].append(t0.elapsed_time(t1))
         del rn7
     f8._linv_i8 = None
+    # the same product with the occupancy masks OFF (the dense digit-tile schedule: what a field whose length-scale is
+    # comparable to its extent costs), and the MMA work that survives the masks on this field
+    i8_dense_ms = i8_survive = None
+    if reorder:
+        try:
+            S8 = engine.I8_SLICES
+            dts = []
+            for rep in range(2):
+                t0, t1 = ev(), ev()
+                t0.record()
+                rnd = f8.whiten_norm_i8(Ks, nslices=S8, use_masks=False)
+                t1.record()
+                torch.cuda.synchronize()
+                dts.append(t0.elapsed_time(t1))
+                del rnd
+            i8_dense_ms = float(min(dts))
+            _, _, km8 = f8.split_i8(Ks, S8, 128, want_mask=True)
+            _, _, lm8 = f8._linv_digits(S8)
+            ch, inr, mmas, cols = i8_surviving_work(torch, km8, lm8, S8, Mpad // 128, Npad // 64, Npad // 32)
+            i8_survive = {"surviving_chunks": ch, "in_range_chunks": inr, "mma_instructions": mmas,
+                          "surviving_int8_ops": 2.0 * 128 * 32 * cols, "dense_int8_ops": S8 * (S8 + 1) / 2 * 2.0 * N_ * N_ * Mp_ / 2}
+            del km8, lm8
+            f8._linv_i8 = None
+        except Exception as e:
+            i8_survive = {"error": repr(e)}
     if reorder:
         inv = torch.empty_like(tperm)
         inv[tperm] = torch.arange(M, device=dev)
@@ -471,10 +543,18 @@ def fit_predict_bench(torch, engine, n_train, grid_side, reps, peak_hbm):
                                         "rate can exceed the dense GEMM peak",
                                "achieved": engine.I8_SLICES * (engine.I8_SLICES + 1) / 2 * N * N * Mp / med["variance_i8"] / 1e9,
                                "unit": "TOP/s(int8)", "effective_fp64_equiv_tflops": N * N * Mp / med["variance_i8"] / 1e9},
+               "variance_i8_surviving": None if not i8_survive or "error" in i8_survive else {
+                   "bound": "int8 tensor (tcgen05 kind::i8) on the MMA work that SURVIVES the occupancy masks (GEMM + split passes timed)",
+                   "achieved": i8_survive["surviving_int8_ops"] / med["variance_i8"] / 1e9, "unit": "TOP/s(int8)",
+                   "surviving_fraction_of_dense_schedule": i8_survive["surviving_int8_ops"] / i8_survive["dense_int8_ops"],
+                   "surviving_chunks": i8_survive["surviving_chunks"], "in_range_chunks": i8_survive["in_range_chunks"],
+                   "mma_instructions": i8_survive["mma_instructions"],
+                   "dense_digit_tiles_ms_masks_off": i8_dense_ms},
                "variance_tf32": {"bound": "tf32 tensor (tcgen05), 3 MMAs per product, incl. the hi/lo split passes",
                                  "achieved": 3 * N * N * Mp / med["variance_tf32"] / 1e9, "unit": "TFLOP/s(tf32)",
                                  "effective_fp64_equiv_tflops": N * N * Mp / med["variance_tf32"] / 1e9},
            }}
+    out["rooflines"] = {k: v for k, v in out["rooflines"].items() if v is not None}
     for r in out["rooflines"].values():
         if "peak" in r:
             r["frac"] = r["achieved"] / r["peak"]
