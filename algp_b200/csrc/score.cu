@@ -22,9 +22,11 @@
 #include <stdlib.h>
 
 #define ALGP_CONST 1.4189385332046727   // 0.5*log(2*pi*e), utils.py:10
-// workspace of algp_score_sets_tiled: [arrival counters: SCORE_SPLIT_MAX_B uint32][fragments]
+// workspace of algp_score_sets_tiled: [arrival counters: 2 x SCORE_SPLIT_MAX_B uint32][fragments].  One counter array per
+// PARTS value (2 and 4): a counter must be a multiple of PARTS when a call starts, which mixing the two on one array
+// would break.
 #define SCORE_SPLIT_MAX_B 16384
-#define SCORE_COUNTER_DOUBLES (SCORE_SPLIT_MAX_B / 2)
+#define SCORE_COUNTER_DOUBLES SCORE_SPLIT_MAX_B
 
 struct ScoreArgs {
   KernelParams kp;
@@ -425,7 +427,7 @@ extern "C" int algp_score_sets_large(const double* Wt, int64_t ldw, int64_t ncol
       if (parts > 1 && (a.ncols16 < 32 * parts || B > SCORE_SPLIT_MAX_B || work_doubles < SCORE_COUNTER_DOUBLES + B * parts * 64))
         parts = 1;
       if (parts > 1) {
-        a.counters = (unsigned int*)work;
+        a.counters = (unsigned int*)work + (parts == 4 ? SCORE_SPLIT_MAX_B : 0);
         a.gpart = work + SCORE_COUNTER_DOUBLES;
       }
       score_k8_launch<2, false, 256>(a, sms, 32, parts, st);

@@ -255,6 +255,24 @@ def test_score_sets_tiled_matches_oracle_and_streaming(kind, k, tile, monkeypatc
     assert _lib.lib.algp_set_score_tile_cols(100) == 1       # not a multiple of 64: rejected
 
 
+def test_score_sets_split_candidates_share_one_workspace(monkeypatch):
+    """Calls with 2 and with 4 warps per candidate alternate on the same state (same workspace): the arrival counters
+    of the two variants are separate, so each call still finds its counters at a multiple of its PARTS."""
+    X, th, hy, static, mobile, pi0, cov, ss, ms, rng = scoring_problem("rbf", n_side=24, n_base=300)
+    n = len(X)
+    idx = np.stack([rng.choice(n, 8, replace=False) for _ in range(900)]).astype(np.int32)
+    delta = np.full(idx.shape, 1 / ms ** 2)
+    state = engine.PosteriorState(hy, dev(X), np.nonzero(pi0 > 0)[0], pi0, cov_mode="never")
+    state.score_mode = "stream"
+    ref = state.score_sets(dev(idx, torch.int32), dev(delta)).cpu().numpy()
+    state.score_mode = "tiled"
+    for parts in (2, 4, 4, 2, 4, 2, 2):
+        monkeypatch.setenv("ALGP_SCORE_PARTS", str(parts))
+        for B in (900, 37):
+            got = state.score_sets(dev(idx[:B], torch.int32), dev(delta[:B])).cpu().numpy()
+            np.testing.assert_allclose(got, ref[:B], rtol=1e-12, atol=1e-10)
+
+
 def test_score_sets_tiled_empty_base():
     X, th, hy, static, mobile, pi0, cov, ss, ms, rng = scoring_problem("rbf")
     n = len(X)
