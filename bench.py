@@ -1513,6 +1513,9 @@ def run_ours(args, rank, world, local_rank):
         if res:
             roof["resources"] = res
             roof["binding"] = max(res, key=lambda k: res[k]["frac"])
+            b = res[roof["binding"]]
+            # the fraction of the BINDING measured roof (for DRAM: bytes and time of the same ncu capture)
+            roof["frac_of_binding_roof"] = b.get("frac_within_the_ncu_capture") or b["frac"]
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warmup,
             "ms_per_step": ms / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
