@@ -359,6 +359,12 @@ __global__ void __launch_bounds__(256, 1) potf2inv_rank_kernel(double* __restric
 // (~115 issued instructions per column per warp, a third of them DFMA), not by the barrier chain.  A DMMA-fragment
 // variant (8x8 tiles dealt to the warps, one DMMA per tile per 4-column step) was correct but 2x slower: per-tile
 // addressing and activity tests cost more issue slots than the eight DFMAs a DMMA replaces.
+// Round 2: a BLOCKED variant (16-column panels eliminated inside the warps by shuffles, rank-16 register updates, two
+// barriers per panel; scripts/micro/potf2_blocked.cuh) is correct and no faster, 43.5 us: shared memory delivers
+// 128 B per clock to the register files however few distinct addresses a load has, so both the pivot-row broadcasts
+// of the in-warp elimination and the operand loads of the rank-16 update (16 loads per 36 DFMAs per thread) sit on
+// the LSU; with one pivot warp and trailing consumer warps the per-column publish / release costs as much as the
+// barrier it replaced (47.6 us).  Measurements and the phase breakdown: profiles/r02_potf2_blocked.log.
 static int g_potf2_rank = 2;
 extern "C" int algp_set_potf2_rank(int r) {
   if (r != 1 && r != 2 && r != 4) return ALGP_ERR_INVALID;

@@ -461,6 +461,27 @@ def fit_predict_bench(torch, engine, n_train, grid_side, reps, peak_hbm):
     i7_rel = float(((v7 - v).abs() / v).max().item())
     tf32_rel = float(((v32 - v).abs() / v).max().item())
     i8_mu_err = float(((mu8 - mu).abs().max() / mu.abs().max()).item())
+    # cond_2(K) estimate ("record cond(K) estimates in the output") from the fp64 factor: largest eigenvalue of
+    # K = L L^T and of K^-1 = Linv^T Linv by 30 power iterations each (torch matrix-vector products: a bench statistic,
+    # not a product path)
+    cond_est = None
+    try:
+        g = torch.Generator(device=dev).manual_seed(0)
+        vv = torch.randn(Npad, dtype=torch.float64, device=dev, generator=g)
+        ww = vv.clone()
+        lam_max = lam_inv = 0.0
+        for _ in range(30):
+            vv = torch.mv(L_ref, torch.mv(L_ref.T, vv))
+            lam_max = float(vv.norm().item())
+            vv /= lam_max
+            ww = torch.mv(Linv_ref.T, torch.mv(Linv_ref, ww))
+            lam_inv = float(ww.norm().item())
+            ww /= lam_inv
+        cond_est = {"lambda_max": lam_max, "lambda_min": 1.0 / lam_inv, "cond_2": lam_max * lam_inv,
+                    "how": "30 power iterations on L L^T and on Linv^T Linv (padded identity rows included)"}
+        del vv, ww
+    except Exception as e:
+        cond_est = {"error": repr(e)}
     if reorder:
         i8_factor_err = None                        # a different (permuted) factor: compared through mean / variance
     else:
@@ -497,6 +518,27 @@ def fit_predict_bench(torch, engine, n_train, grid_side, reps, peak_hbm):
             e2e[mode + "_max_abs_var_diff_vs_fp64"] = float(np.abs(var_out - ref64[1]).max())
             e2e[mode + "_max_rel_var_diff_vs_fp64"] = float((np.abs(var_out - ref64[1]) / ref64[1]).max())
             e2e[mode + "_max_abs_mean_diff_over_max_abs_mean"] = float(np.abs(mu_h - ref64[0]).max() / np.abs(ref64[0]).max())
+    # the same call with the Matern-1.5 kernel at the same theta ("also a Matern-1.5 run with the same theta")
+    gpm = algp_b200.GPR(kernel_params={'type': 'matern'})
+    gpm.reset(x, y, var_h)
+    with torch.no_grad():
+        gpm.model.kernel_covar_module.base_kernel.log_lengthscale.copy_(torch.tensor(hy.log_ls).view(1, 1, -1))
+        gpm.model.kernel_covar_module.log_outputscale.fill_(hy.log_os)
+        gpm.likelihood.log_noise.fill_(hy.log_noise)
+    for mode in ("fp64", "i8"):
+        gpm.precision = mode
+        ts = []
+        for rep in range(min(reps, 2) + 1):
+            gpm._cache.clear()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            mu_m, var_m = algp_b200.predictive_distribution(gpm, x, y, xs, var_h, return_var=True)
+            ts.append((time.perf_counter() - t0) * 1e3)
+        e2e["matern_" + mode] = float(np.median(ts[1:]))
+        if mode == "fp64":
+            refm = var_m.copy()
+        else:
+            e2e["matern_i8_max_abs_var_diff_vs_fp64"] = float(np.abs(var_m - refm).max())
     e2e["h2d_bytes"] = int(x.nbytes + y.nbytes + var_h.nbytes + xs.nbytes)
     e2e["d2h_bytes"] = int(mu_h.nbytes + var_out.nbytes)
     med = {k: (float(np.median(v)) if len(v) else None) for k, v in times.items()}
@@ -526,7 +568,7 @@ def fit_predict_bench(torch, engine, n_train, grid_side, reps, peak_hbm):
            "tolerance_contract": "fp64 tier: |dmean| <= 1e-9 max|mean|, |dvar| <= 1e-9 s^2 (prior scale; SURVEY 7 'variance "
                                  "cancellation'), and with the default 8 digit planes also |dvar| <= 1e-9 var (relative); "
                                  "1e-4 tier: 1e-4 of the same scales",
-           "i8_digit_planes": engine.I8_SLICES, "ms_by_stage": med,
+           "i8_digit_planes": engine.I8_SLICES, "ms_by_stage": med, "cond_K_estimate": cond_est,
            "var_min": float(v.min().item()), "var_max": float(v.max().item()),
            "rooflines": {
                "kbuild_train": {"bound": "hbm", "achieved": 8 * N * N / med["kbuild_train"] / 1e6, "peak": peak_hbm, "unit": "GB/s"},
