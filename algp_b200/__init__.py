@@ -8,5 +8,6 @@ from . import _lib  # noqa: F401  (loads the library or raises)
 from .models import GPR, ExactGPModel  # noqa: F401
 from .utils import CONST, entropy_from_cov, predictive_distribution, to_numpy, to_torch  # noqa: F401
 from .agent import Agent, HotPath, patch  # noqa: F401
+from . import tracing  # noqa: F401  (ALGP_TRACE=1 enables per-call NVTX ranges + CUDA-event timings)
 
 __version__ = "0.1.0"

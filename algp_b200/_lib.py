@@ -72,6 +72,7 @@ SIGNATURES = {
     "algp_greedy_utilities": (C.c_int, [_p, _p, _p, _f64, _i64, _p, _p]),
     "algp_argmax": (C.c_int, [_p, _i64, _i64, _p, _p, _p]),
     "algp_argmax_work_bytes": (_i64, []),
+    "algp_check_indices": (C.c_int, [_p, _i64, _i64, _p, _p]),
     "algp_p2p_mailbox_bytes": (_i64, [_i32]),
     "algp_p2p_create": (C.c_int, [_i64, C.POINTER(C.c_void_p), _p]),
     "algp_p2p_open": (C.c_int, [_p, C.POINTER(C.c_void_p)]),
@@ -123,13 +124,17 @@ def check(name, code):
 # never go through call()); bench.py reads launch_count around its timed region for the "gpu_launches" it reports
 KERNELS_PER_CALL = {"algp_argmax": 2, "algp_argmax_exchange": 2, "algp_append": 3, "algp_append_block": 3}   # argmax: 1 up to 2^14 values
 launch_count = 0
+_trace = None          # an algp_b200.tracing.Tracer while tracing is enabled (NVTX range + CUDA events around every call)
 
 
 def call(name, *args):
     """Invoke a status-returning entry point and raise on failure."""
     global launch_count
     launch_count += KERNELS_PER_CALL.get(name, 1)
-    check(name, getattr(lib, name)(*args))
+    if _trace is None:
+        check(name, getattr(lib, name)(*args))
+    else:
+        _trace.around(name, lambda: check(name, getattr(lib, name)(*args)))
 
 
 def ptr(t):

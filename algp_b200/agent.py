@@ -273,7 +273,11 @@ class HotPath(object):
         # The mobile flag is boolean (agent.py:377): already-mobile locations and repeats add nothing.
         # A 2-D integer array [P, k] (-1 = empty slot) is taken as is -- the kernel skips already-mobile
         # and duplicate slots itself; lists of lists are de-duplicated and padded on the host.
-        if isinstance(paths_mobile_indices, np.ndarray) and paths_mobile_indices.ndim == 2:
+        # The slots of a caller's array are range-checked on the device (IndexError as NumPy would raise at
+        # agent.py:377; below -1 is out of range too: -1 is the empty slot, not "the last location"); list input
+        # has been through NumPy indexing in _pad_paths already.
+        caller_array = isinstance(paths_mobile_indices, np.ndarray) and paths_mobile_indices.ndim == 2
+        if caller_array:
             idx = paths_mobile_indices
         else:
             idx = _pad_paths(paths_mobile_indices, org_mobile)
@@ -287,10 +291,15 @@ class HotPath(object):
             # one process per GPU, replicated agent: every rank scores a contiguous block of the paths and the
             # per-rank winners are exchanged over NVLink (algp_b200.dist); all ranks return the same index
             from . import dist as adist
-            score, best = adist.sharded_best(state, idx, None, delta_scalar=dm, skip=state._skip)
+            score, best = adist.sharded_best(state, idx, None, delta_scalar=dm, skip=state._skip, check=caller_array)
             self._last_path_scores = None
             return int(best)
         idx_d = engine.to_dev(idx, dtype=torch.int32)
+        res = getattr(state, "_winner3", None)          # {score bits, winner, slots out of range}: one 24-byte read-back
+        if res is None:
+            res = state._winner3 = torch.zeros(3, dtype=torch.int64, device=idx_d.device)
+        if caller_array:
+            state.check_indices(idx_d, out=res[2:3])
         scores = state.score_sets(idx_d, None, delta_scalar=dm, skip=state._skip)
         if self._use_mi():
             ctx = getattr(state, "_mi_ctx", None)
@@ -298,9 +307,12 @@ class HotPath(object):
                 ctx = state._mi_ctx = engine.MIContext(state.hyper, state.X, pi, full_inverse=True, precision=state.precision)
                 ctx.check()
             scores = ctx.path_utilities(scores, idx_d, state._skip, self.static_std, self.mobile_std).contiguous()
-        pair = state.argmax(scores)
+        state.argmax(scores, out=res[:2])
         self._last_path_scores = scores
-        return int(pair[1].item())
+        vals = (res if caller_array else res[:2]).cpu()
+        if caller_array and int(vals[2]) != 0:
+            raise IndexError("best_path: %d slot(s) of the path array are outside [-1, %d)" % (int(vals[2]), state.n))
+        return int(vals[1])
 
 
 def patch(agent_cls):

@@ -576,6 +576,35 @@ extern "C" int algp_argmax(const double* x, int64_t n, int64_t idx_offset, void*
   return ALGP_OK;
 }
 
+// Candidate slots outside [-1, n): the reference indexes NumPy arrays with them (agent.py:377) and gets an IndexError;
+// the scoring kernels would read out of bounds.  One pass over the (device copy of the) slot array -- 2 MB for
+// configs[2], ~3 us -- counts them and turns them into empty slots, so that the scoring launched behind it is safe;
+// the count travels to the host together with the winner, so the check costs no extra synchronisation.
+__global__ void check_indices_kernel(int32_t* __restrict__ idx, int64_t count, int64_t n, unsigned long long* __restrict__ bad) {
+  unsigned mine = 0;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t v = idx[i];
+    if (v < -1 || v >= n) {
+      idx[i] = -1;
+      ++mine;
+    }
+  }
+  mine = __reduce_add_sync(0xffffffffu, mine);
+  if ((threadIdx.x & 31) == 0 && mine) atomicAdd(bad, (unsigned long long)mine);
+}
+
+extern "C" int algp_check_indices(int32_t* idx, int64_t count, int64_t n, int64_t* bad_count, void* stream) {
+  if (!bad_count || count < 0 || n < 0 || (count > 0 && !idx)) return ALGP_ERR_INVALID;
+  cudaStream_t st = (cudaStream_t)stream;
+  ALGP_CUDA(cudaMemsetAsync(bad_count, 0, sizeof(int64_t), st));
+  if (count == 0) return ALGP_OK;
+  int64_t blocks = (count + 4 * 256 - 1) / (4 * 256);
+  if (blocks > 4 * 148) blocks = 4 * 148;
+  check_indices_kernel<<<(unsigned)blocks, 256, 0, st>>>(idx, count, n, (unsigned long long*)bad_count);
+  ALGP_LAUNCH_CHECK();
+  return ALGP_OK;
+}
+
 extern "C" int algp_greedy_utilities(const double* diagP, const double* pi, const uint8_t* is_static, double d_static,
                                      int64_t n, double* ut, void* stream) {
   if (!diagP || !pi || !is_static || !ut || n < 0) return ALGP_ERR_INVALID;

@@ -167,19 +167,21 @@ def pack_pair(value, index, device="cpu"):
 
 
 def sharded_best(state, idx_all, delta_all=None, delta_scalar=0.0, skip=None, group=None, H_base=None, return_device=False,
-                 events=None):
+                 events=None, check=False):
     """Score this rank's block of the global candidate array idx_all [B,k] (host int32 array, or an int32 device
     tensor replicated on every rank) against the replicated PosteriorState and return the global (score, index) winner
     on every rank.  The per-rank winners travel through the NVLink mailboxes of PeerExchange (NCCL all-gather when peer
     mapping is unavailable, gloo on CPU tensors).  return_device=True (PeerExchange only) returns the device tensor
     {score bits, index, status} without synchronising.  events = (start, end) CUDA events recorded around the scoring
-    kernel (bench.py's per-kernel timing)."""
+    kernel (bench.py's per-kernel timing).  check=True (host idx_all only): this rank's block is range-checked on
+    the device before it is scored and IndexError is raised, after the exchange, on the ranks whose block held a slot
+    outside [-1, n) (agent.py:377 indexes NumPy arrays with the paths)."""
     from . import engine
     world = dist.get_world_size(group) if dist.is_initialized() else 1
     rank = dist.get_rank(group) if dist.is_initialized() else 0
     lo, hi = shard_range(len(idx_all), rank, world)
     dev = state.X.device
-    scores = None
+    scores = bad = None
     if hi > lo:
         if torch.is_tensor(idx_all):                  # candidates already on the device: this rank's block is a view
             idx = idx_all[lo:hi]
@@ -187,22 +189,30 @@ def sharded_best(state, idx_all, delta_all=None, delta_scalar=0.0, skip=None, gr
         else:
             idx = engine.to_dev(np.ascontiguousarray(idx_all[lo:hi]), dtype=torch.int32, device=dev)
             dl = None if delta_all is None else engine.to_dev(np.ascontiguousarray(delta_all[lo:hi]), device=dev)
+            if check:
+                bad = state.check_indices(idx)
         if events is not None:
             events[0].record()
         scores = state.score_sets(idx, dl, delta_scalar=delta_scalar, skip=skip, H_base=H_base)
         if events is not None:
             events[1].record()
+    def raise_if_bad(result):
+        if bad is not None and int(bad.item()) != 0:
+            raise IndexError("sharded_best: %d slot(s) of rows %d..%d of the candidate array are outside [-1, %d)"
+                             % (int(bad.item()), lo, hi - 1, state.n))
+        return result
+
     ex = peer_exchange(group) if (world > 1 and dev.type == "cuda") else None
     if ex is not None:
         out3 = ex.argmax(scores, idx_offset=lo)       # argmax + NVLink mailbox exchange in one kernel
-        return out3 if return_device else ex.result(out3)
+        return out3 if return_device else raise_if_bad(ex.result(out3))
     if scores is not None:
         pair = state.argmax(scores, idx_offset=lo)
     else:
         pair = pack_pair(-np.inf, np.iinfo(np.int64).max, dev)
     if return_device and world == 1:
         return pair                                   # {score bits, index} on the device, no synchronisation
-    return allgather_argmax(pair, group)
+    return raise_if_bad(allgather_argmax(pair, group))
 
 
 def row_block(total, rank, world):

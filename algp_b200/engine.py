@@ -667,6 +667,16 @@ class PosteriorState(object):
         call("algp_argmax", ptr(x), x.shape[0], int(idx_offset), ptr(out), ptr(self._argwork), stream())
         return out
 
+    def check_indices(self, idx, out=None):
+        """Range-check OUR device copy idx [B,k] (int32) of a caller's slot array before it is scored: returns the
+        device int64[1] count of slots outside [-1, n) and blanks them (-1), so the scoring kernels never read out of
+        bounds.  The reference indexes NumPy arrays with the path lists (agent.py:377) and raises IndexError there; the
+        caller of this method raises it once the count has come back with the winner."""
+        if out is None:
+            out = torch.empty(1, dtype=torch.int64, device=idx.device)
+        call("algp_check_indices", ptr(idx), idx.numel(), self.n, ptr(out), stream())
+        return out
+
     def greedy_utilities(self, d_static, out=None):
         if out is None:
             out = torch.empty(self.n, dtype=torch.float64, device=self.X.device)

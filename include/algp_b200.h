@@ -205,6 +205,12 @@ int algp_greedy_utilities(const double* diagP, const double* pi, const uint8_t* 
  * work: algp_argmax_work_bytes() bytes. */
 int algp_argmax(const double* x, int64_t n, int64_t idx_offset, void* out_pair, void* work, void* stream);
 int64_t algp_argmax_work_bytes(void);
+/* *bad_count (device int64) = number of candidate slots outside [-1, n) in idx[count] (-1 = empty slot); those
+ * slots are overwritten with -1.  The reference indexes NumPy arrays with the path lists (agent.py:377) and raises
+ * IndexError for such an entry; the scoring kernels do not range-check their slots, so the Python mirror runs this
+ * pass over its device copy of a caller's slot array before scoring it and reads the count back together with the
+ * winner (then raises IndexError). */
+int algp_check_indices(int32_t* idx, int64_t count, int64_t n, int64_t* bad_count, void* stream);
 /* ---- winner exchange between the GPUs of one box over NVLink peer memory (csrc/p2p.cu) ----
  * Replaces the NCCL all-gather of one 16-byte {score, global index} pair per rank that follows the sharded scoring
  * step: the last argmax kernel stores the rank's pair into a mailbox in every peer's memory, waits for

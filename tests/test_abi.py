@@ -51,3 +51,17 @@ def test_product_never_imports_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 src = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), f
+
+
+def test_tracing_toggles_without_a_gpu():
+    """algp_b200.tracing installs / removes the per-call hook of _lib.call; nothing touches CUDA until a call is made."""
+    from algp_b200 import _lib, tracing
+    assert _lib._trace is None
+    t = tracing.enable(nvtx=False)
+    assert _lib._trace is t and t.totals == {} and t.pending == []
+    assert tracing.disable() is t and _lib._trace is None
+    with tracing.trace() as t2:
+        assert _lib._trace is t2
+    assert _lib._trace is None
+    text = tracing.format_summary({"algp_potrf": {"calls": 3, "ms": 2.5}})
+    assert "algp_potrf" in text and "2.500" in text

@@ -555,3 +555,30 @@ def test_sharded_mean_var_single_rank_equals_posterior(precision, monkeypatch):
     mu_o, v_o = O.predictive_distribution_chol(O.OracleGP(th, "fp64"), x, y, xs, var, None, return_var=True)
     np.testing.assert_allclose(mu.cpu().numpy(), mu_o, rtol=1e-9, atol=1e-9)
     np.testing.assert_allclose(v.cpu().numpy(), v_o, rtol=0, atol=1e-9)
+
+
+def test_tracing_reports_device_time_per_entry_point_and_changes_nothing():
+    """algp_b200.tracing (the per-phase timers of run_ipp, agent.py:138-219, per kernel family): the traced call gives the
+    same numbers as the plain one, every C-ABI entry point it went through is listed with its call count and a
+    positive device time, and nothing is recorded once tracing is off."""
+    from algp_b200 import _lib, tracing
+    X, y, tr, ytr, rng = field_problem(24, 20, 300, seed=5)
+    te = rng.choice(len(X), 150, replace=False)
+    var = np.full(300, 0.01)
+    th, hy = hyper_pair([2.5, 3.5], 1.3, 0.02, "rbf")
+    gp = make_gpr("rbf", th.log_lengthscale, th.log_outputscale, th.log_noise, X[tr], ytr, var)
+    plain = algp_b200.predictive_distribution(gp, X[tr], ytr, X[te], var, return_var=True)
+    gp._cache.clear()
+    with tracing.trace() as t:
+        traced = algp_b200.predictive_distribution(gp, X[tr], ytr, X[te], var, return_var=True)
+        launches = _lib.launch_count
+    np.testing.assert_array_equal(plain[0], traced[0])
+    np.testing.assert_array_equal(plain[1], traced[1])
+    s = t.summary()
+    for name in ("algp_kbuild", "algp_potrf", "algp_trtri"):
+        assert s[name]["calls"] >= 1 and s[name]["ms"] > 0.0, (name, s)
+    assert list(s) == sorted(s, key=lambda k: -s[k]["ms"])          # slowest first
+    assert _lib._trace is None
+    gp._cache.clear()
+    algp_b200.predictive_distribution(gp, X[tr], ytr, X[te], var, return_var=True)
+    assert _lib.launch_count > launches and t.summary() == s          # untraced calls leave the tracer alone

@@ -243,3 +243,34 @@ def test_staging_buffers_are_safe_to_reuse():
     f32 = rng.normal(size=100).astype(np.float32)
     np.testing.assert_array_equal(engine.to_dev(f32).cpu().numpy(), f32.astype(np.float64))
     assert engine.to_dev(tb) is not None and engine.to_dev(tb).data_ptr() == tb.data_ptr()
+
+
+def test_out_of_range_path_indices_raise_index_error():
+    """agent.py:377 indexes a NumPy flag array with every path, so a location >= n raises IndexError in the reference.
+    Lists go through NumPy indexing on the host; a caller's [P, k] slot array is range-checked on the device (the
+    count comes back with the winner) -- and the agent stays usable afterwards."""
+    rng = np.random.default_rng(7)
+    X = rng.uniform(0, 8, (40, 2))
+    ag, th = _agent(X, {1, 2, 3}, {4, 5, 6})
+    with pytest.raises(IndexError):
+        ag.best_path([[10, 11], [12, 40]], [7])
+    good = np.array([[10, 11, -1], [12, 13, 14], [20, 21, 22]], dtype=np.int32)
+    want = ag.best_path(good, [7])
+    cov = O.OracleGP(th, "fp64").cov_mat(X, add_likelihood_var=True)
+    st = np.zeros(40, bool); st[[1, 2, 3]] = True
+    mo = np.zeros(40, bool); mo[[4, 5, 6]] = True
+    assert want == O.best_path_literal(cov, st, mo, 0.1, 1.0, [[10, 11], [12, 13, 14], [20, 21, 22]], [7])
+    for bad_value in (40, 2 ** 31 - 1, -2, -(2 ** 31)):
+        bad = good.copy()
+        bad[1, 2] = bad_value
+        with pytest.raises(IndexError):
+            ag.best_path(bad, [7])
+        assert ag.best_path(good, [7]) == want                  # no sticky CUDA error, same answer as before
+    # the C entry point itself: count + blanking
+    from algp_b200._lib import call, ptr, stream
+    idx = engine.to_dev(np.array([0, -1, 39, 40, -2, 7], dtype=np.int32), dtype=torch.int32)
+    cnt = torch.empty(1, dtype=torch.int64, device=idx.device)
+    call("algp_check_indices", ptr(idx), 6, 40, ptr(cnt), stream())
+    assert int(cnt.item()) == 2 and idx.cpu().tolist() == [0, -1, 39, -1, -1, 7]
+    call("algp_check_indices", ptr(idx), 0, 40, ptr(cnt), stream())
+    assert int(cnt.item()) == 0
