@@ -58,6 +58,7 @@ SIGNATURES = {
     "algp_score_sets_tiled": (C.c_int, [_p, _i64, _i64, _i64, _p, _i32, _p, _f64, _i32, _f64, _p, _p, _p, _f64, _p,
                                         _i32, _i64, _f64, _p, _p, _i64, _p]),
     "algp_score_sets_tiled_work_doubles": (_i64, [_i64]),
+    "algp_score_sets_tiled_launches": (C.c_int, [_i32, _i64, _i64, _i64]),
     "algp_set_score_tile_cols": (C.c_int, [_i32]),
     "algp_score_sets_cov": (C.c_int, [_p, _i64, _p, _p, _p, _f64, _p, _i32, _i64, _f64, _p, _p]),
     "algp_mi_terms_large": (C.c_int, [_p, _i64, _p, _p, _i64, _p, _i32, _i64, _p, _f64, _f64, _p, _p, _i64, _p]),
@@ -127,10 +128,11 @@ launch_count = 0
 _trace = None          # an algp_b200.tracing.Tracer while tracing is enabled (NVTX range + CUDA events around every call)
 
 
-def call(name, *args):
-    """Invoke a status-returning entry point and raise on failure."""
+def call(name, *args, launches=None):
+    """Invoke a status-returning entry point and raise on failure.  launches: kernels this call launches when it is not
+    the fixed number of KERNELS_PER_CALL (the chunked scoring call)."""
     global launch_count
-    launch_count += KERNELS_PER_CALL.get(name, 1)
+    launch_count += KERNELS_PER_CALL.get(name, 1) if launches is None else launches
     if _trace is None:
         check(name, getattr(lib, name)(*args))
     else:

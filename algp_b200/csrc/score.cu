@@ -484,16 +484,9 @@ extern "C" int64_t algp_score_sets_tiled_work_doubles(int64_t B) {
   return SCORE_COUNTER_DOUBLES + (B <= SCORE_SPLIT_MAX_B ? B * 4 * 64 : B * 64);
 }
 
-extern "C" int algp_score_sets_tiled(const double* Wt, int64_t ldw, int64_t ncols, int64_t n_rows, const double* X, int d,
-                                     const double* log_ls_host, double log_os, int kind, double noise, const double* pi0,
-                                     const int32_t* idx, const double* delta, double delta_scalar, const uint8_t* skip,
-                                     int k, int64_t B, double H_base, double* scores, double* work, int64_t work_doubles,
-                                     void* stream) {
-  if (k < 1 || k > 8 || B < 0 || n_rows < 1) return ALGP_ERR_INVALID;
-  if (B > 0 && (!work || work_doubles < algp_score_sets_tiled_work_doubles(B) || ((uintptr_t)work & 15))) return ALGP_ERR_INVALID;
-  // g_tile_cols > 0: that chunk; -1: plain single launch; 0 (auto): chunked launches where ONE call streams enough for
-  // the L2 hit rate to pay for the per-chunk prologues (>= ~12 GB: 1.50 vs 1.69 ms on configs[2] for an isolated call;
-  // back-to-back calls on the same rows find part of them in L2 anyway and the two are level), else the single launch
+// The column chunk algp_score_sets_tiled uses for this call: > 0 chunked launches, 0 one launch (with the workspace:
+// split candidates for small batches), -1 the plain single launch.
+static int tiled_chunk_cols(int k, int64_t B, int64_t ncols, int64_t n_rows, int* chunk_out) {
   int chunk = g_tile_cols;
   if (chunk == 0) {
     const double bytes = 8.0 * (double)B * k * (double)ncols;
@@ -506,6 +499,36 @@ extern "C" int algp_score_sets_tiled(const double* Wt, int64_t ldw, int64_t ncol
       chunk = (int)(c < 256 ? 256 : c);
     }
   }
+  *chunk_out = chunk;
+  return ALGP_OK;
+}
+
+// Kernel launches one algp_score_sets_tiled call of this shape makes (the chunked form launches the scoring kernel
+// once per column chunk); <= 0 on error.  For callers that count launches (bench.py's gpu_launches).
+extern "C" int algp_score_sets_tiled_launches(int k, int64_t B, int64_t ncols, int64_t n_rows) {
+  if (k < 1 || k > 8 || B <= 0 || n_rows < 1 || ncols < 0) return 0;
+  int chunk = 0;
+  if (tiled_chunk_cols(k, B, ncols, n_rows, &chunk)) return 0;
+  if (chunk <= 0) return 1;
+  const int64_t ncols16 = (ncols + 15) / 16 * 16;
+  int launches = 0;
+  for (int64_t c0 = 0; c0 < ncols16 || c0 == 0; c0 += chunk) ++launches;
+  return launches;
+}
+
+extern "C" int algp_score_sets_tiled(const double* Wt, int64_t ldw, int64_t ncols, int64_t n_rows, const double* X, int d,
+                                     const double* log_ls_host, double log_os, int kind, double noise, const double* pi0,
+                                     const int32_t* idx, const double* delta, double delta_scalar, const uint8_t* skip,
+                                     int k, int64_t B, double H_base, double* scores, double* work, int64_t work_doubles,
+                                     void* stream) {
+  if (k < 1 || k > 8 || B < 0 || n_rows < 1) return ALGP_ERR_INVALID;
+  if (B > 0 && (!work || work_doubles < algp_score_sets_tiled_work_doubles(B) || ((uintptr_t)work & 15))) return ALGP_ERR_INVALID;
+  // g_tile_cols > 0: that chunk; -1: plain single launch; 0 (auto): chunked launches where ONE call streams enough for
+  // the L2 hit rate to pay for the per-chunk prologues (>= ~12 GB: 1.50 vs 1.69 ms on configs[2] for an isolated call;
+  // back-to-back calls on the same rows find part of them in L2 anyway and the two are level), else the single launch
+  int chunk = 0;
+  const int rc = tiled_chunk_cols(k, B, ncols, n_rows, &chunk);
+  if (rc) return rc;
   if (chunk > 0)
     return algp_score_sets_large(Wt, ldw, ncols, X, d, log_ls_host, log_os, kind, noise, pi0, idx, delta, delta_scalar, skip,
                                  k, B, H_base, scores, B > 0 ? work : (double*)1, -(int64_t)chunk, stream);

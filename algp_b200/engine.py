@@ -643,9 +643,12 @@ class PosteriorState(object):
             if getattr(self, "_tilework", None) is None or self._tilework.numel() < nwork:
                 # zero-filled: the head of the buffer holds the arrival counters of the split-candidate kernel
                 self._tilework = torch.zeros(nwork, dtype=torch.float64, device=idx.device)
+            # one launch per L2-sized column chunk for calls that stream >= 12 GB (4 for configs[2]), else one
+            nlaunch = max(1, _lib.lib.algp_score_sets_tiled_launches(k, B, self.ncols, self.n_pad))
             call("algp_score_sets_tiled", ptr(self.Wt), self.ldw, self.ncols, self.n_pad, ptr(self.X), self.hyper.d, ls_p,
                  self.hyper.log_os, self.hyper.kind, self.hyper.noise, ptr(self.pi), ptr(idx), ptr(delta),
-                 float(delta_scalar), ptr(skip), k, B, float(hb), ptr(out), ptr(self._tilework), nwork, stream())
+                 float(delta_scalar), ptr(skip), k, B, float(hb), ptr(out), ptr(self._tilework), nwork, stream(),
+                 launches=nlaunch)
             return out
         if k > MAX_SET_SMEM:
             # long paths: the k x k matrix of a candidate lives in a global scratch instead of shared memory

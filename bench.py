@@ -1211,9 +1211,11 @@ def l2_probe(torch, mbytes=(32, 64)):
     return out
 
 
-def ncu_dram_traffic(kernel_substr, files=("r02_prof_score_summary.csv", "r01_prof_score_summary.csv")):
-    """dram__bytes_read.sum + dram__bytes_write.sum per launch of a kernel from the committed ncu summaries
-    (profiles/*.csv, written by scripts/ncu_summary.py from an `ncu --set full` capture): (bytes | None, file | None)."""
+def ncu_dram_traffic(kernel_substr, files=("r02_prof_score_summary.csv", "r01_prof_score_summary.csv"), reduce="mean"):
+    """dram__bytes_read.sum + dram__bytes_write.sum of a kernel from the committed ncu summaries (profiles/*.csv, written
+    by scripts/ncu_summary.py from an `ncu --set full` capture): (bytes | None, file | None, ms | None).  reduce="mean":
+    per launch; reduce="sum": over all captured launches (the chunk launches of ONE chunked scoring call), with
+    extra = {"launches", "dmma_pipe_pct" (time-weighted), "l2_hit_pct"}."""
     import csv
     units = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0, "Tbyte": 1e12}
     for name in files:
@@ -1232,12 +1234,22 @@ def ncu_dram_traffic(kernel_substr, files=("r02_prof_score_summary.csv", "r01_pr
                 for r in rows[2:] if r and kernel_substr in r[0]]
         if vals:
             ms = None
+            sel = [r for r in rows[2:] if r and kernel_substr in r[0]]
             if "gpu__time_duration.sum" in hdr:
                 it = hdr.index("gpu__time_duration.sum")
                 tu = {"ms": 1.0, "us": 1e-3, "ns": 1e-6, "s": 1e3}.get(unit[it], 1.0)
-                ms = float(np.mean([float(r[it]) * tu for r in rows[2:] if r and kernel_substr in r[0]]))
-            return float(np.mean(vals)), "profiles/" + name, ms
-    return None, None, None
+                tms = [float(r[it]) * tu for r in sel]
+                ms = float(np.sum(tms) if reduce == "sum" else np.mean(tms))
+            if reduce != "sum":
+                return float(np.mean(vals)), "profiles/" + name, ms
+            extra = {"launches": len(vals)}
+            for key, col in (("dmma_pipe_pct", "sm__pipe_tensor_subpipe_dmma_cycles_active.avg.pct_of_peak_sustained_active"),
+                             ("l2_hit_pct", "lts__t_sector_hit_rate.pct")):
+                if col in hdr and ms:
+                    ic = hdr.index(col)
+                    extra[key] = float(np.sum([float(r[ic]) * t for r, t in zip(sel, tms)]) / np.sum(tms))
+            return float(np.sum(vals)), "profiles/" + name, ms, extra
+    return (None, None, None) if reduce != "sum" else (None, None, None, None)
 
 
 def strong_scaling_bench(torch, dist, adist, engine, state, idx0_d, delta0_d, H_base, rank, world, dev, steps, warmup):
@@ -1526,25 +1538,45 @@ def run_ours(args, rank, world, local_rank):
     if rank == 0:
         algo_bytes = 8.0 * N_BASE * K_SET * N_CAND           # s*N*k per candidate
         achieved = algo_bytes / (kernel_ms / 1e3) / 1e9
-        traffic, traffic_src, ncu_ms = ncu_dram_traffic("score_sets_k8_kernel")
+        # the timed step scores its batch through algp_score_sets_tiled, which streams 17.2 GB and therefore launches the
+        # kernel once per L2-sized column chunk (4 x 1024 columns): the ncu capture of exactly those launches
+        # (profiles/r02_prof_score_tiled_summary.csv, summed) is the traffic of a step; the earlier capture of the plain
+        # single launch is kept beside it
+        launches_per_step = max(1, _lib.lib.algp_score_sets_tiled_launches(K_SET, N_CAND, state.ncols, state.n_pad))
+        traffic, traffic_src, ncu_ms, ncu_extra = ncu_dram_traffic("score_sets_k8_kernel", files=("r02_prof_score_tiled_summary.csv",),
+                                                                  reduce="sum")
+        single = ncu_dram_traffic("score_sets_k8_kernel")
+        if traffic is None or (ncu_extra or {}).get("launches") != launches_per_step:
+            traffic, traffic_src, ncu_ms = single            # no capture of the chunked form for this shape
+            ncu_extra = None
         gram_flops = 2.0 * N_BASE * K_SET * K_SET * N_CAND   # the full 8 x 8 Gram the DMMA tiles compute
         roof = {"bound": "hbm", "kernel": "score_sets_k8_kernel", "achieved": achieved, "peak": peak_hbm,
                 "unit": "GB/s", "frac": achieved / peak_hbm, "traffic": traffic, "traffic_source": traffic_src,
-                "peak_source": peak_src, "kernel_ms": kernel_ms, "algorithmic_bytes_per_launch": algo_bytes,
-                "note": "`achieved` is SURVEY 8d's no-reuse byte count over the kernel time: it exceeds the DRAM peak because part "
-                        "of the rows are served by the L2, so `frac` is not a fraction of a roof.  The resources this kernel "
-                        "actually loads are listed under `resources`; the binding one is the L2 -> SM delivery rate: all "
-                        "algorithmic bytes cross it exactly once."}
+                "peak_source": peak_src, "kernel_ms": kernel_ms, "kernel_launches_per_step": launches_per_step,
+                "algorithmic_bytes_per_launch": algo_bytes,
+                "note": "one step = ONE algp_score_sets_tiled call = %d launches of the kernel (one per 1024-column chunk); "
+                        "`achieved`, `traffic`, `kernel_ms` and `algorithmic_bytes_per_launch` are per step (the launches "
+                        "summed).  `achieved` is SURVEY 8d's no-reuse byte count over the kernel time: it exceeds the DRAM peak "
+                        "because the L2 serves most of the rows (59 %% sector hits in the capture), so `frac` is not a fraction of "
+                        "a roof.  The resources the kernel actually loads are under `resources`; none is saturated: all "
+                        "algorithmic bytes cross the L2 -> SM path exactly once, and the DMMA pipe is the busiest unit." % launches_per_step}
         res = {}
         if traffic is not None:
-            res["dram"] = {"bytes_per_launch_ncu": traffic, "achieved_gbs": traffic / (kernel_ms / 1e3) / 1e9, "peak_gbs": peak_hbm,
+            res["dram"] = {"bytes_per_step_ncu": traffic, "achieved_gbs": traffic / (kernel_ms / 1e3) / 1e9, "peak_gbs": peak_hbm,
                            "frac": traffic / (kernel_ms / 1e3) / 1e9 / peak_hbm,
                            "ncu_kernel_ms": ncu_ms,
                            "frac_within_the_ncu_capture": (traffic / (ncu_ms / 1e3) / 1e9 / peak_hbm) if ncu_ms else None,
-                           "note": "bytes from the committed ncu capture (one launch replayed from flushed caches) over the "
-                                   "kernel time of this run, where the same rows are re-scored back to back and part of them "
-                                   "is still in L2: an upper bound for the steady state; bytes over the capture's own time is "
+                           "note": "dram__bytes_read + write of the step's launches in the committed ncu capture (each replayed "
+                                   "from flushed caches) over the kernel time of this run; over the capture's own time: "
                                    "`frac_within_the_ncu_capture`"}
+            if ncu_extra:
+                res["dram"]["l2_sector_hit_pct_ncu"] = ncu_extra.get("l2_hit_pct")
+            if single[0] is not None and single[1] != traffic_src:
+                res["dram"]["plain_single_launch_capture"] = {
+                    "bytes": single[0], "ncu_kernel_ms": single[2], "source": single[1],
+                    "frac_within_the_ncu_capture": single[0] / (single[2] / 1e3) / 1e9 / peak_hbm if single[2] else None,
+                    "note": "algp_score_sets as ONE launch over all 4096 columns (what an isolated call ran before the chunked "
+                            "form): DRAM-bound there, 1.55 ms"}
         probe = extra.get("l2_to_sm_probe_tbs")
         if probe:
             pk = max(probe.values())
@@ -1552,12 +1584,13 @@ def run_ours(args, rank, world, local_rank):
         if fp64_peak:
             res["fp64_tensor_dmma"] = {"achieved_tflops": gram_flops / (kernel_ms / 1e3) / 1e12, "peak_tflops_cublas_dgemm": fp64_peak,
                                        "frac": gram_flops / (kernel_ms / 1e3) / 1e12 / fp64_peak}
+            if ncu_extra and ncu_extra.get("dmma_pipe_pct") is not None:
+                res["fp64_tensor_dmma"]["pipe_active_pct_ncu"] = ncu_extra["dmma_pipe_pct"]
         if res:
             roof["resources"] = res
             roof["binding"] = max(res, key=lambda k: res[k]["frac"])
-            b = res[roof["binding"]]
-            # the fraction of the BINDING measured roof (for DRAM: bytes and time of the same ncu capture)
-            roof["frac_of_binding_roof"] = b.get("frac_within_the_ncu_capture") or b["frac"]
+            # the fraction of the busiest measured resource, all three over the kernel time of THIS run
+            roof["frac_of_binding_roof"] = res[roof["binding"]]["frac"]
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warmup,
             "ms_per_step": ms / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,

@@ -185,6 +185,9 @@ int algp_score_sets_tiled(const double* Wt, int64_t ldw, int64_t ncols, int64_t 
                           const int32_t* idx, const double* delta, double delta_scalar, const uint8_t* skip, int k,
                           int64_t B, double H_base, double* scores, double* work, int64_t work_doubles, void* stream);
 int64_t algp_score_sets_tiled_work_doubles(int64_t B);
+/* Kernel launches one algp_score_sets_tiled call of this shape makes (one per column chunk in the chunked form);
+ * <= 0 for an invalid shape.  For callers that count launches. */
+int algp_score_sets_tiled_launches(int k, int64_t B, int64_t ncols, int64_t n_rows);
 int algp_set_score_tile_cols(int cols);
 /* The same scores from a RESIDENT posterior covariance of the base set, P = Sigma + sigma_n^2 I - Wt Wt^T
  * (lower triangle of an [n x ldp] matrix; build it with algp_kbuild + algp_gemm_nt / algp_gemm_nt_i8, lower_only):
