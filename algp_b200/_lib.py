@@ -70,6 +70,7 @@ SIGNATURES = {
     "algp_paths_fill_slots": (C.c_int, [_p, _p, _i64]),
     "algp_paths_free": (C.c_int, [_p]),
     "algp_cov_downdate": (C.c_int, [_p, _i64, _i64, _p, _i64, _i64, _i32, _p]),
+    "algp_cov_downdate_max_cols": (C.c_int, []),
     "algp_greedy_utilities": (C.c_int, [_p, _p, _p, _f64, _i64, _p, _p]),
     "algp_argmax": (C.c_int, [_p, _i64, _i64, _p, _p, _p]),
     "algp_argmax_work_bytes": (_i64, []),

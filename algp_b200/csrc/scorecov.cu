@@ -184,7 +184,7 @@ __global__ void __launch_bounds__(256) score_cov_generic_kernel(const CovArgs a)
 // 4 x 4 elements per thread, the two 64 x k slabs of Wt staged in shared memory.
 // ---------------------------------------------------------------------------
 #define CD_T 64
-#define CD_MAXK 16
+#define CD_MAXK 32
 __global__ void __launch_bounds__(256) cov_downdate_kernel(double* __restrict__ P, int64_t ldp, int64_t n, const double* __restrict__ Wt,
                                                            int64_t ldw, int col0, int k, int tiles) {
   __shared__ double wi[CD_T][CD_MAXK + 1], wj[CD_T][CD_MAXK + 1];
@@ -196,14 +196,29 @@ __global__ void __launch_bounds__(256) cov_downdate_kernel(double* __restrict__ 
   const int tj = (int)(b - (int64_t)ti * (ti + 1) / 2);
   (void)tiles;
   const int tid = threadIdx.x;
+  const int ty = tid >> 4, tx = tid & 15;
+  // The tile of P is requested FIRST (4 rows x 32 B per thread, 16 independent 16-byte loads): its DRAM latency then
+  // overlaps the slab loads, the barrier and the rank-k product instead of following them.
+  const int64_t gj = (int64_t)tj * CD_T + tx * 4;
+  const bool full = gj + 3 < n;
+  double2 lo[4], hi[4];
+#pragma unroll
+  for (int a = 0; a < 4; ++a) {
+    const int64_t gi = (int64_t)ti * CD_T + ty * 4 + a;
+    lo[a] = hi[a] = make_double2(0.0, 0.0);
+    if (gi < n && full) {
+      const double* row = P + gi * ldp + gj;
+      lo[a] = *reinterpret_cast<const double2*>(row);
+      hi[a] = *reinterpret_cast<const double2*>(row + 2);
+    }
+  }
   for (int e = tid; e < CD_T * k; e += 256) {
     const int r = e / k, c = e % k;
-    const int64_t gi = (int64_t)ti * CD_T + r, gj = (int64_t)tj * CD_T + r;
+    const int64_t gi = (int64_t)ti * CD_T + r, gjr = (int64_t)tj * CD_T + r;
     wi[r][c] = gi < n ? Wt[gi * ldw + col0 + c] : 0.0;
-    wj[r][c] = gj < n ? Wt[gj * ldw + col0 + c] : 0.0;
+    wj[r][c] = gjr < n ? Wt[gjr * ldw + col0 + c] : 0.0;
   }
   __syncthreads();
-  const int ty = tid >> 4, tx = tid & 15;
   double acc[4][4];
 #pragma unroll
   for (int a = 0; a < 4; ++a)
@@ -224,14 +239,12 @@ __global__ void __launch_bounds__(256) cov_downdate_kernel(double* __restrict__ 
 #pragma unroll
   for (int a = 0; a < 4; ++a) {
     const int64_t gi = (int64_t)ti * CD_T + ty * 4 + a;
-    const int64_t gj = (int64_t)tj * CD_T + tx * 4;
     if (gi >= n) continue;
     double* row = P + gi * ldp + gj;
-    if (gj + 3 < n) {
-      double2 lo = *reinterpret_cast<double2*>(row), hi = *reinterpret_cast<double2*>(row + 2);
-      lo.x -= acc[a][0]; lo.y -= acc[a][1]; hi.x -= acc[a][2]; hi.y -= acc[a][3];
-      *reinterpret_cast<double2*>(row) = lo;
-      *reinterpret_cast<double2*>(row + 2) = hi;
+    if (full) {
+      lo[a].x -= acc[a][0]; lo[a].y -= acc[a][1]; hi[a].x -= acc[a][2]; hi[a].y -= acc[a][3];
+      *reinterpret_cast<double2*>(row) = lo[a];
+      *reinterpret_cast<double2*>(row + 2) = hi[a];
     } else {
 #pragma unroll
       for (int c = 0; c < 4; ++c)
@@ -244,7 +257,9 @@ __global__ void __launch_bounds__(256) cov_downdate_kernel(double* __restrict__ 
 
 // P[i][j] -= sum_{c < k} Wt[i][col0 + c] Wt[j][col0 + c] on the lower triangle (j <= i) of the resident posterior
 // covariance P [n x ldp]: the k columns Wt gained through algp_append / algp_append_block since P was current.
-// k <= 16 per call; ldp even and P 16-byte aligned.
+// k <= algp_cov_downdate_max_cols() = 32 per call (one pass over the lower triangle each); ldp even and P 16-byte aligned.
+extern "C" int algp_cov_downdate_max_cols(void) { return CD_MAXK; }
+
 extern "C" int algp_cov_downdate(double* P, int64_t ldp, int64_t n, const double* Wt, int64_t ldw, int64_t col0, int k,
                                  void* stream) {
   if (!P || !Wt || n < 1 || ldp < n || (ldp & 1) || ((uintptr_t)P & 15) || col0 < 0 || k < 1 || k > CD_MAXK || col0 + k > ldw)

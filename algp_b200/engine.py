@@ -573,9 +573,9 @@ class PosteriorState(object):
     def _sync_cov(self):
         """Bring the resident P up to date with the columns appended since it was built / last synchronised: every
         commit is a rank-1 downdate of P stored as a column of Wt, so P -= w w^T over those columns (one pass over the
-        lower triangle per 16 columns) replaces the rebuild.  Lazy: runs before the next scoring call that reads P."""
+        lower triangle per 32 columns) replaces the rebuild.  Lazy: runs before the next scoring call that reads P."""
         while self.P is not None and self._P_ncols < self.ncols:
-            k = min(16, self.ncols - self._P_ncols)
+            k = min(_lib.lib.algp_cov_downdate_max_cols(), self.ncols - self._P_ncols)
             call("algp_cov_downdate", ptr(self.P), self.P.stride(0), self.n_pad, ptr(self.Wt), self.ldw, self._P_ncols, k,
                  stream())
             self._P_ncols += k

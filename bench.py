@@ -1030,6 +1030,7 @@ def resident_cov_bench(torch, engine, algp_b200, hyper, Xd, base, pi0, is_static
     precomputes P (allowed), the amortised SYRK cost is reported and included in a second end-to-end figure").
     A candidate then gathers 36 entries of P instead of streaming 8 rows of W^T.  Timed with 8 rotating candidate
     batches so the gathered sectors of one step (~75 MB) are not the L2 contents left by the previous one."""
+    from algp_b200 import _lib
     dev = Xd.device
     out = {}
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -1124,10 +1125,12 @@ def resident_cov_bench(torch, engine, algp_b200, hyper, Xd, base, pi0, is_static
         sc_s = st_c.score_sets(batches[1], delta_d)
         out["across_commits"] = {
             "what": "4 greedy picks + one 16-reading block append on a state with P resident; P is kept and brought up to date "
-                    "by algp_cov_downdate (2 passes over the lower triangle for the 20 new columns) instead of a rebuild",
+                    "by algp_cov_downdate (one pass over the lower triangle per <= %d new columns: %d for these 20) instead of a "
+                    "rebuild" % (_lib.lib.algp_cov_downdate_max_cols(), -(-20 // _lib.lib.algp_cov_downdate_max_cols())),
             "commit_ms": commit_ms, "downdate_ms": sync_ms, "rebuild_ms_for_comparison": bms, "score_from_P_ms": score_ms,
             "max_abs_score_diff_vs_streaming_after_commits": float((sc_p - sc_s).abs().max().item()),
-            "downdate_gbs": 2 * 2 * 8.0 * st_c.n_pad * (st_c.n_pad + 64) / 2 / (sync_ms / 1e3) / 1e9}
+            "downdate_gbs": -(-20 // _lib.lib.algp_cov_downdate_max_cols()) * 2 * 8.0 * st_c.n_pad * (st_c.n_pad + 64) / 2
+                            / (sync_ms / 1e3) / 1e9}
         del st_c, keepP
     except Exception as e:
         out["across_commits_error"] = repr(e)

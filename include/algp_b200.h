@@ -198,9 +198,10 @@ int algp_score_sets_cov(const double* P, int64_t ldp, const double* pi0, const i
                         double delta_scalar, const uint8_t* skip, int k, int64_t B, double H_base, double* scores,
                         void* stream);
 /* Keep a resident P current across commits: P[i][j] -= sum_{c<k} Wt[i][col0+c] Wt[j][col0+c] on the lower triangle,
- * for the k (<= 16) columns Wt gained through algp_append / algp_append_block since P was last current.  One pass over
- * the lower triangle of P (HBM bound) instead of a rebuild (kernel matrix + SYRK). */
+ * for the k (<= algp_cov_downdate_max_cols() = 32) columns Wt gained through algp_append / algp_append_block since P
+ * was last current.  One pass over the lower triangle of P (HBM bound) instead of a rebuild (kernel matrix + SYRK). */
 int algp_cov_downdate(double* P, int64_t ldp, int64_t n, const double* Wt, int64_t ldw, int64_t col0, int k, void* stream);
+int algp_cov_downdate_max_cols(void);
 /* greedy utilities for every location (k = 1 closed form, agent.py:341) */
 int algp_greedy_utilities(const double* diagP, const double* pi, const uint8_t* is_static, double d_static,
                           int64_t n, double* ut, void* stream);

@@ -343,13 +343,14 @@ def test_resident_cov_policy_and_commits():
     np.testing.assert_allclose(second, first, rtol=1e-11, atol=1e-10)
     P_before = state.P
     pi1 = pi0.copy()
-    # one rank-1 commit, then a block of 19 (two downdate passes: 16 + 3 columns), then another single one
+    # one rank-1 commit, then blocks of 19 and 16 (36 pending columns: two downdate passes, 32 + 4), then another single one
     j = torch.tensor([int(free[0])], dtype=torch.int64, device="cuda")
     state.append(j, 1 / ss ** 2)
     pi1[free[0]] += 1 / ss ** 2
-    blk = free[5:24]
-    state.append_block(blk, 1 / ms ** 2, mark_static=False)
-    pi1[blk] += 1 / ms ** 2
+    for blk in (free[5:24], free[40:56]):
+        state.append_block(blk, 1 / ms ** 2, mark_static=False)
+        pi1[blk] += 1 / ms ** 2
+    assert state.ncols - state._P_ncols == 36 > _lib.lib.algp_cov_downdate_max_cols()
     assert state.P is P_before and state._P_ncols < state.ncols      # kept, not yet synchronised
     after = state.score_sets(idx_d, None, delta_scalar=1 / ms ** 2).cpu().numpy()
     assert state.P is P_before and state._P_ncols == state.ncols
