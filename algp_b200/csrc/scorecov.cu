@@ -185,9 +185,12 @@ __global__ void __launch_bounds__(256) score_cov_generic_kernel(const CovArgs a)
 // ---------------------------------------------------------------------------
 #define CD_T 64
 #define CD_MAXK 32
+#define CD_PITCH (CD_MAXK + 4)
 __global__ void __launch_bounds__(256) cov_downdate_kernel(double* __restrict__ P, int64_t ldp, int64_t n, const double* __restrict__ Wt,
                                                            int64_t ldw, int col0, int k, int tiles) {
-  __shared__ double wi[CD_T][CD_MAXK + 1], wj[CD_T][CD_MAXK + 1];
+  // k-major slabs of the two row ranges; pitch = 4 (mod 16) doubles: the 8-byte fragment reads of a half-warp
+  // (4 rows x 4 k) hit 32 distinct banks
+  __shared__ double wi[CD_T][CD_PITCH], wj[CD_T][CD_PITCH];
   // blockIdx -> (ti, tj), tj <= ti
   const int64_t b = blockIdx.x;
   int ti = (int)((sqrt(8.0 * (double)b + 1.0) - 1.0) * 0.5);
@@ -195,60 +198,54 @@ __global__ void __launch_bounds__(256) cov_downdate_kernel(double* __restrict__ 
   while ((int64_t)ti * (ti + 1) / 2 > b) --ti;
   const int tj = (int)(b - (int64_t)ti * (ti + 1) / 2);
   (void)tiles;
-  const int tid = threadIdx.x;
-  const int ty = tid >> 4, tx = tid & 15;
-  // The tile of P is requested FIRST (4 rows x 32 B per thread, 16 independent 16-byte loads): its DRAM latency then
-  // overlaps the slab loads, the barrier and the rank-k product instead of following them.
-  const int64_t gj = (int64_t)tj * CD_T + tx * 4;
-  const bool full = gj + 3 < n;
-  double2 lo[4], hi[4];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, t = lane & 3;
+  const int wm = warp >> 1, wn = warp & 1;               // warp sub-tile: rows 16 wm .. +15, columns 32 wn .. +31
+  // The tile of P is requested FIRST, straight into the DMMA accumulator fragments (lane (g, t) holds columns 2t, 2t+1
+  // of row g of every 8x8 block: 8 independent 16-byte loads): its DRAM latency overlaps the slab loads and the
+  // barrier, and the rank-k product then runs as P - Wi Wj^T on the FP64 tensor cores with the accumulators starting
+  // at P (B fragments negated).  The first version did the product with DFMAs on 4x4 register patches: 8 shared
+  // operand loads per 16 DFMAs per thread and column, bound by shared-memory delivery (0.016 ms per column at
+  // n = 16 384); a fragment is shared by the 8 lanes of a row / column inside the tensor core instead.
+  double2 c[2][4];
+  int64_t grow[2];
 #pragma unroll
-  for (int a = 0; a < 4; ++a) {
-    const int64_t gi = (int64_t)ti * CD_T + ty * 4 + a;
-    lo[a] = hi[a] = make_double2(0.0, 0.0);
-    if (gi < n && full) {
-      const double* row = P + gi * ldp + gj;
-      lo[a] = *reinterpret_cast<const double2*>(row);
-      hi[a] = *reinterpret_cast<const double2*>(row + 2);
+  for (int i = 0; i < 2; ++i) {
+    grow[i] = (int64_t)ti * CD_T + wm * 16 + i * 8 + g;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int64_t gc = (int64_t)tj * CD_T + wn * 32 + j * 8 + 2 * t;
+      c[i][j] = make_double2(0.0, 0.0);
+      if (grow[i] < n && gc + 1 < n) c[i][j] = *reinterpret_cast<const double2*>(P + grow[i] * ldp + gc);
+      else if (grow[i] < n && gc < n) c[i][j].x = P[grow[i] * ldp + gc];
     }
   }
-  for (int e = tid; e < CD_T * k; e += 256) {
-    const int r = e / k, c = e % k;
+  const int k4 = (k + 3) & ~3;
+  for (int e = tid; e < CD_T * k4; e += 256) {
+    const int r = e / k4, q = e % k4;
     const int64_t gi = (int64_t)ti * CD_T + r, gjr = (int64_t)tj * CD_T + r;
-    wi[r][c] = gi < n ? Wt[gi * ldw + col0 + c] : 0.0;
-    wj[r][c] = gjr < n ? Wt[gjr * ldw + col0 + c] : 0.0;
+    wi[r][q] = (gi < n && q < k) ? Wt[gi * ldw + col0 + q] : 0.0;
+    wj[r][q] = (gjr < n && q < k) ? Wt[gjr * ldw + col0 + q] : 0.0;
   }
   __syncthreads();
-  double acc[4][4];
+  for (int q0 = 0; q0 < k4; q0 += 4) {
+    double af[2], bf[4];
 #pragma unroll
-  for (int a = 0; a < 4; ++a)
+    for (int i = 0; i < 2; ++i) af[i] = wi[wm * 16 + i * 8 + g][q0 + t];
 #pragma unroll
-    for (int c = 0; c < 4; ++c) acc[a][c] = 0.0;
-  for (int q = 0; q < k; ++q) {
-    double ra[4], rb[4];
+    for (int j = 0; j < 4; ++j) bf[j] = -wj[wn * 32 + j * 8 + g][q0 + t];
 #pragma unroll
-    for (int a = 0; a < 4; ++a) {
-      ra[a] = wi[ty * 4 + a][q];
-      rb[a] = wj[tx * 4 + a][q];
-    }
+    for (int i = 0; i < 2; ++i)
 #pragma unroll
-    for (int a = 0; a < 4; ++a)
-#pragma unroll
-      for (int c = 0; c < 4; ++c) acc[a][c] = fma(ra[a], rb[c], acc[a][c]);
+      for (int j = 0; j < 4; ++j) dmma884(c[i][j].x, c[i][j].y, af[i], bf[j]);
   }
 #pragma unroll
-  for (int a = 0; a < 4; ++a) {
-    const int64_t gi = (int64_t)ti * CD_T + ty * 4 + a;
-    if (gi >= n) continue;
-    double* row = P + gi * ldp + gj;
-    if (full) {
-      lo[a].x -= acc[a][0]; lo[a].y -= acc[a][1]; hi[a].x -= acc[a][2]; hi[a].y -= acc[a][3];
-      *reinterpret_cast<double2*>(row) = lo[a];
-      *reinterpret_cast<double2*>(row + 2) = hi[a];
-    } else {
+  for (int i = 0; i < 2; ++i) {
+    if (grow[i] >= n) continue;
 #pragma unroll
-      for (int c = 0; c < 4; ++c)
-        if (gj + c < n) row[c] -= acc[a][c];
+    for (int j = 0; j < 4; ++j) {
+      const int64_t gc = (int64_t)tj * CD_T + wn * 32 + j * 8 + 2 * t;
+      if (gc + 1 < n) *reinterpret_cast<double2*>(P + grow[i] * ldp + gc) = c[i][j];
+      else if (gc < n) P[grow[i] * ldp + gc] = c[i][j].x;
     }
   }
 }
