@@ -60,6 +60,7 @@ SIGNATURES = {
     "algp_score_sets_tiled_work_doubles": (_i64, [_i64]),
     "algp_score_sets_tiled_launches": (C.c_int, [_i32, _i64, _i64, _i64]),
     "algp_set_score_tile_cols": (C.c_int, [_i32]),
+    "algp_set_score_resident": (C.c_int, [_i32]),
     "algp_score_sets_cov": (C.c_int, [_p, _i64, _p, _p, _p, _f64, _p, _i32, _i64, _f64, _p, _p]),
     "algp_mi_terms_large": (C.c_int, [_p, _i64, _p, _p, _i64, _p, _i32, _i64, _p, _f64, _f64, _p, _p, _i64, _p]),
     "algp_mi_terms_large_work_doubles": (_i64, [_i32, _i64]),

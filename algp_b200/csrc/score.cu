@@ -20,6 +20,7 @@
 #include "argmax.cuh"
 #include <math.h>
 #include <stdlib.h>
+#include <stdio.h>
 
 #define ALGP_CONST 1.4189385332046727   // 0.5*log(2*pi*e), utils.py:10
 // workspace of algp_score_sets_tiled: [arrival counters: 2 x SCORE_SPLIT_MAX_B uint32][fragments].  One counter array per
@@ -79,6 +80,76 @@ __device__ __forceinline__ void sc_load(double (&v)[4 * UNROLL], const double* p
   }
 }
 
+// Slot g of candidate `cand` (4 lanes per slot): location, precision increment, and whether the slot adds anything
+// (empty, zero-precision, already-mobile and repeated slots do not: agent.py:377 sets a boolean flag).
+__device__ __forceinline__ bool score_k8_slot(const ScoreArgs& a, int64_t cand, int g, int& my_idx, double& my_delta) {
+  my_idx = (g < a.k) ? a.idx[cand * a.k + g] : -1;
+  my_delta = (g < a.k) ? (a.delta ? a.delta[cand * a.k + g] : a.delta_scalar) : 0.0;
+  bool active = (my_idx >= 0) && (my_delta > 0.0);
+  if (active && a.skip && a.skip[my_idx]) active = false;
+  // duplicates inside a set are idempotent (agent.py:377): keep the first
+#pragma unroll
+  for (int s = 0; s < 7; ++s) {
+    int o_idx = __shfl_sync(0xffffffffu, my_idx, 4 * s);
+    int o_act = __shfl_sync(0xffffffffu, (int)active, 4 * s);
+    if (s < g && o_act && o_idx == my_idx) active = false;
+  }
+  return active;
+}
+
+// Epilogue of the k <= 8 kernels: Sigma_CC from the coordinates, the 8 x 8 un-normalised elimination by shuffles and the
+// size / precision bookkeeping.  (G0, G1) = Gram entries (g, 2t), (g, 2t+1); only the lower triangle is read.
+__device__ __forceinline__ void score_k8_epilogue(const ScoreArgs& a, int64_t cand, int lane, int g, int t, int d, int my_idx,
+                                                  double my_delta, bool active, double G0, double G1) {
+  // Sigma_CC from coordinates: lane needs x of slot g (row) and slots 2t, 2t+1 (cols)
+  double r2a = 0.0, r2b = 0.0;
+  for (int j = 0; j < d; ++j) {
+    double xg = (my_idx >= 0) ? a.X[(int64_t)my_idx * d + j] * a.kp.inv_ls[j] : 0.0;
+    double xa = __shfl_sync(0xffffffffu, xg, 4 * (2 * t));
+    double xb = __shfl_sync(0xffffffffu, xg, 4 * (2 * t + 1));
+    r2a = fma(xg - xa, xg - xa, r2a);
+    r2b = fma(xg - xb, xg - xb, r2b);
+  }
+  const double sq = active ? sqrt(my_delta) : 0.0;
+  const double sqa = __shfl_sync(0xffffffffu, sq, 4 * (2 * t));
+  const double sqb = __shfl_sync(0xffffffffu, sq, 4 * (2 * t + 1));
+  double m0 = (kern_from_r2(r2a, a.kp.kind, a.kp.outputscale) + ((g == 2 * t) ? a.noise : 0.0) - G0) * sq * sqa;
+  double m1 = (kern_from_r2(r2b, a.kp.kind, a.kp.outputscale) + ((g == 2 * t + 1) ? a.noise : 0.0) - G1) * sq * sqb;
+  if (g == 2 * t) m0 += 1.0;
+  if (g == 2 * t + 1) m1 += 1.0;
+
+  // 8x8 un-normalised elimination; element (i,j) lives in lane 4i + (j>>1), register j&1
+  double logdet = 0.0;
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    const double src = (c & 1) ? m1 : m0;
+    const double piv = __shfl_sync(0xffffffffu, src, 4 * c + (c >> 1));
+    const double lic = __shfl_sync(0xffffffffu, src, 4 * g + (c >> 1));
+    const double lj0 = __shfl_sync(0xffffffffu, src, 4 * (2 * t) + (c >> 1));
+    const double lj1 = __shfl_sync(0xffffffffu, src, 4 * (2 * t + 1) + (c >> 1));
+    const double f = lic / piv;
+    if (g > c) {
+      if (2 * t > c) m0 = fma(-f, lj0, m0);
+      if (2 * t + 1 > c) m1 = fma(-f, lj1, m1);
+    }
+    logdet += log(piv);
+  }
+
+  // size / precision bookkeeping
+  double term = 0.0, nnew = 0.0;
+  if (t == 0 && active) {
+    const double p0 = a.pi0[my_idx];
+    term = log(p0 + my_delta) - (p0 > 0.0 ? log(p0) : 0.0);
+    nnew = (p0 > 0.0) ? 0.0 : 1.0;
+  }
+#pragma unroll
+  for (int o = 4; o < 32; o <<= 1) {
+    term += __shfl_xor_sync(0xffffffffu, term, o);
+    nnew += __shfl_xor_sync(0xffffffffu, nnew, o);
+  }
+  if (lane == 0) a.scores[cand] = a.H_base + nnew * ALGP_CONST + 0.5 * (logdet - term);
+}
+
 // PARTS > 1: a candidate is scored by PARTS independent warps, each over a slice of the columns.  A warp stores its
 // accumulator fragment to gpart[cand][part], fences, and bumps the candidate's arrival counter; the warp that arrives
 // last adds the other fragments and runs the epilogue ("last one out" -- no barrier, no extra launch; the counters are
@@ -104,18 +175,9 @@ __global__ void __launch_bounds__(THREADS, 3) score_sets_k8_kernel(const ScoreAr
       col0 = part * span;
       col1 = col0 + span;
     }
-    // slot g of this candidate (4 lanes per slot)
-    int my_idx = (g < a.k) ? a.idx[cand * a.k + g] : -1;
-    double my_delta = (g < a.k) ? (a.delta ? a.delta[cand * a.k + g] : a.delta_scalar) : 0.0;
-    bool active = (my_idx >= 0) && (my_delta > 0.0);
-    if (active && a.skip && a.skip[my_idx]) active = false;
-    // duplicates inside a set are idempotent (agent.py:377): keep the first
-#pragma unroll
-    for (int s = 0; s < 7; ++s) {
-      int o_idx = __shfl_sync(0xffffffffu, my_idx, 4 * s);
-      int o_act = __shfl_sync(0xffffffffu, (int)active, 4 * s);
-      if (s < g && o_act && o_idx == my_idx) active = false;
-    }
+    int my_idx;
+    double my_delta;
+    const bool active = score_k8_slot(a, cand, g, my_idx, my_delta);
     const double* row = a.Wt + (int64_t)(active ? my_idx : 0) * a.ldw + 4 * t;
 
     double c0[4], c1[4];
@@ -171,53 +233,7 @@ __global__ void __launch_bounds__(THREADS, 3) score_sets_k8_kernel(const ScoreAr
       continue;
     }
 
-    // Sigma_CC from coordinates: lane needs x of slot g (row) and slots 2t, 2t+1 (cols)
-    double r2a = 0.0, r2b = 0.0;
-    for (int j = 0; j < d; ++j) {
-      double xg = (my_idx >= 0) ? a.X[(int64_t)my_idx * d + j] * a.kp.inv_ls[j] : 0.0;
-      double xa = __shfl_sync(0xffffffffu, xg, 4 * (2 * t));
-      double xb = __shfl_sync(0xffffffffu, xg, 4 * (2 * t + 1));
-      r2a = fma(xg - xa, xg - xa, r2a);
-      r2b = fma(xg - xb, xg - xb, r2b);
-    }
-    const double sq = active ? sqrt(my_delta) : 0.0;
-    const double sqa = __shfl_sync(0xffffffffu, sq, 4 * (2 * t));
-    const double sqb = __shfl_sync(0xffffffffu, sq, 4 * (2 * t + 1));
-    double m0 = (kern_from_r2(r2a, a.kp.kind, a.kp.outputscale) + ((g == 2 * t) ? a.noise : 0.0) - G0) * sq * sqa;
-    double m1 = (kern_from_r2(r2b, a.kp.kind, a.kp.outputscale) + ((g == 2 * t + 1) ? a.noise : 0.0) - G1) * sq * sqb;
-    if (g == 2 * t) m0 += 1.0;
-    if (g == 2 * t + 1) m1 += 1.0;
-
-    // 8x8 un-normalised elimination; element (i,j) lives in lane 4i + (j>>1), register j&1
-    double logdet = 0.0;
-#pragma unroll
-    for (int c = 0; c < 8; ++c) {
-      const double src = (c & 1) ? m1 : m0;
-      const double piv = __shfl_sync(0xffffffffu, src, 4 * c + (c >> 1));
-      const double lic = __shfl_sync(0xffffffffu, src, 4 * g + (c >> 1));
-      const double lj0 = __shfl_sync(0xffffffffu, src, 4 * (2 * t) + (c >> 1));
-      const double lj1 = __shfl_sync(0xffffffffu, src, 4 * (2 * t + 1) + (c >> 1));
-      const double f = lic / piv;
-      if (g > c) {
-        if (2 * t > c) m0 = fma(-f, lj0, m0);
-        if (2 * t + 1 > c) m1 = fma(-f, lj1, m1);
-      }
-      logdet += log(piv);
-    }
-
-    // size / precision bookkeeping
-    double term = 0.0, nnew = 0.0;
-    if (t == 0 && active) {
-      const double p0 = a.pi0[my_idx];
-      term = log(p0 + my_delta) - (p0 > 0.0 ? log(p0) : 0.0);
-      nnew = (p0 > 0.0) ? 0.0 : 1.0;
-    }
-#pragma unroll
-    for (int o = 4; o < 32; o <<= 1) {
-      term += __shfl_xor_sync(0xffffffffu, term, o);
-      nnew += __shfl_xor_sync(0xffffffffu, nnew, o);
-    }
-    if (lane == 0) a.scores[cand] = a.H_base + nnew * ALGP_CONST + 0.5 * (logdet - term);
+    score_k8_epilogue(a, cand, lane, g, t, d, my_idx, my_delta, active, G0, G1);
   }
 }
 
@@ -230,6 +246,127 @@ static void score_k8_launch(const ScoreArgs& a, int sms, int blocks_per_sm, int 
   if (parts == 4) score_sets_k8_kernel<UNROLL, PREFETCH, THREADS, 4><<<grid, THREADS, 0, st>>>(a);
   else if (parts == 2) score_sets_k8_kernel<UNROLL, PREFETCH, THREADS, 2><<<grid, THREADS, 0, st>>>(a);
   else score_sets_k8_kernel<UNROLL, PREFETCH, THREADS, 1><<<grid, THREADS, 0, st>>>(a);
+}
+
+// ---------------------------------------------------------------------------
+// k <= 8, large batches: ONE persistent launch that sweeps the columns of Wt in L2-sized chunks with the candidates'
+// partial Grams resident in shared memory (the form algp_score_sets_tiled picks for batches that stream >= 3 GB).
+//
+// The chunked launches further down park every candidate's accumulator fragment in global memory between launches
+// (34 MB written and 34 MB read per chunk at 65 536 candidates: as much L2 traffic as a 512-column slice of Wt) and pay
+// a ramp and a tail per launch, so their best chunk is 1024 columns -- a 100 MB slice of which the 126 MB L2 keeps
+// 59 % (4.8 GB of DRAM reads per call for 0.4 GB of distinct rows).  Here each of the 24 warps of the one CTA per SM
+// OWNS up to SR_CAP candidates for the whole call: the lower triangle of a candidate's Gram (36 doubles), its eight
+// row indices after the slot rule and its id wait in the warp's own shared-memory region between chunks -- 65 536 x
+// 324 B = 21 MB over the 148 SMs -- so no fragment leaves the SM, no warp ever waits for another, and the chunk can be
+// as narrow as the L2 likes: 768 columns for the 16 384 rows of configs[2], 88 % sector hits, 1.1 GB of DRAM reads
+// (ncu: profiles/r02_prof_score_resident_summary.csv).  With the slice in L2 the loop is latency-bound, so a warp
+// keeps FOUR 128-byte lines per row in flight (96 KB per SM) where the DRAM-heavy single launch was best with two.
+// Ownership is decided during the first chunk by a global ticket counter: a warp on a fast SM takes more candidates
+// than one on a slow SM and keeps that share for the remaining chunks, which a static partition cannot do.  Shared
+// memory is kept to 187 KB: at 218 KB the L1 that stages the loads in flight shrinks and the kernel is 60 % slower.
+// Measured (profiles/r02_score_resident.log): 1.26-1.34 ms per 65 536 sets where the chunked launches take 1.45-1.55
+// and the single launch 1.51-1.67 on the same box.
+// ---------------------------------------------------------------------------
+static int g_tile_cols = 0;       // 0 = derive from the L2 size; algp_set_score_tile_cols overrides (tuning / tests)
+static int g_resident = 0;        // 0 = auto (resident when the chunk is derived, launches when it is forced), 1 always, -1 never
+static bool score_use_resident() { return g_resident > 0 || (g_resident == 0 && g_tile_cols == 0); }
+
+#define SR_WARPS 24
+#define SR_CAP 24
+#define SR_UNROLL 4
+#define SR_SLOT_BYTES (36 * sizeof(double) + 9 * sizeof(int))
+__global__ void __launch_bounds__(SR_WARPS * 32, 1) score_sets_k8_resident_kernel(const ScoreArgs a, int chunk, unsigned int* next) {
+  extern __shared__ __align__(16) double sr_gram[];        // [SR_WARPS][SR_CAP][36] Grams, then [.][.][8] rows, [.][.] ids
+  const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3, warp = threadIdx.x >> 5;
+  const int d = a.kp.d;
+  constexpr int STEP = 16 * SR_UNROLL;
+  double* mine = sr_gram + (size_t)warp * SR_CAP * 36 + g * (g + 1) / 2 + 2 * t;   // entry (g, 2t) of my first candidate
+  int* rows = reinterpret_cast<int*>(sr_gram + (size_t)SR_WARPS * SR_CAP * 36) + warp * SR_CAP * 8;   // row or -1
+  unsigned int* ids = reinterpret_cast<unsigned int*>(sr_gram + (size_t)SR_WARPS * SR_CAP * 36) + SR_WARPS * SR_CAP * 8 + warp * SR_CAP;
+  const bool keep0 = 2 * t <= g, keep1 = 2 * t + 1 <= g;   // lower triangle incl. the diagonal: all the epilogue reads
+  const int nchunks = a.ncols16 > chunk ? (a.ncols16 + chunk - 1) / chunk : 1;
+  int n_mine = 0;
+
+  for (int c = 0; c < nchunks; ++c) {
+    const int col0 = c * chunk;
+    const int cend = (col0 + chunk < a.ncols16) ? col0 + chunk : a.ncols16;
+    for (int i = 0; i < SR_CAP; ++i) {
+      unsigned int cu;
+      if (c == 0) {                                        // take a ticket
+        cu = 0;
+        if (lane == 0) cu = atomicAdd(next, 1u);
+        cu = __shfl_sync(0xffffffffu, cu, 0);
+        if ((int64_t)cu >= a.B) break;
+        if (lane == 0) ids[i] = cu;
+        n_mine = i + 1;
+      } else {
+        if (i >= n_mine) break;
+        cu = ids[i];
+      }
+      const int64_t cand = cu;
+      int my_idx = -1;
+      double my_delta = 0.0;
+      bool active;
+      int my_row;
+      double c0[4], c1[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) c0[q] = c1[q] = 0.0;
+      if (c == 0) {                                        // the slot rule once per candidate; later chunks read the row back
+        active = score_k8_slot(a, cand, g, my_idx, my_delta);
+        my_row = active ? my_idx : -1;
+        if (t == 0) rows[i * 8 + g] = my_row;
+      } else {
+        my_row = rows[i * 8 + g];
+        active = my_row >= 0;
+        if (keep0) c0[0] = mine[i * 36];
+        if (keep1) c1[0] = mine[i * 36 + 1];
+      }
+      const double* row = a.Wt + (int64_t)(active ? my_row : 0) * a.ldw + 4 * t;
+      for (int k0 = col0; k0 < cend; k0 += STEP) {
+        double v[4 * SR_UNROLL];
+        sc_load<SR_UNROLL>(v, row, active, k0, cend);
+#pragma unroll
+        for (int q = 0; q < 4 * SR_UNROLL; ++q) dmma884(c0[q & 3], c1[q & 3], v[q], v[q]);
+      }
+      const double G0 = (c0[0] + c0[1]) + (c0[2] + c0[3]);
+      const double G1 = (c1[0] + c1[1]) + (c1[2] + c1[3]);
+      if (c + 1 < nchunks) {
+        if (keep0) mine[i * 36] = G0;
+        if (keep1) mine[i * 36 + 1] = G1;
+        continue;
+      }
+      if (c > 0) active = score_k8_slot(a, cand, g, my_idx, my_delta);
+      score_k8_epilogue(a, cand, lane, g, t, d, my_idx, my_delta, active, G0, G1);
+    }
+  }
+}
+
+// Candidates one resident launch takes: 80 % of the shared-memory slots.  A warp stops taking tickets when its SR_CAP
+// slots are full, so every candidate is taken as long as the batch is below the slot count; the 20 % are the room the
+// fast SMs need to take more than their even share.
+static int64_t score_resident_batch(int sms) { return (int64_t)sms * SR_WARPS * SR_CAP * 4 / 5; }
+
+static int score_k8_resident(ScoreArgs a, int sms, int chunk, unsigned int* next, cudaStream_t st) {
+  const size_t smem = (size_t)SR_WARPS * SR_CAP * SR_SLOT_BYTES;
+  static AlgpPerDevice configured;
+  if (configured.raise(smem)) {
+    ALGP_CUDA(cudaFuncSetAttribute(score_sets_k8_resident_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  }
+  const int64_t batch = score_resident_batch(sms), B = a.B;
+  const int32_t* idx = a.idx;
+  const double* delta = a.delta;
+  double* scores = a.scores;
+  for (int64_t b0 = 0; b0 < B; b0 += batch) {
+    a.B = B - b0 < batch ? B - b0 : batch;
+    a.idx = idx + b0 * a.k;
+    a.delta = delta ? delta + b0 * a.k : nullptr;
+    a.scores = scores + b0;
+    ALGP_CUDA(cudaMemsetAsync(next, 0, sizeof(unsigned int), st));
+    score_sets_k8_resident_kernel<<<sms, SR_WARPS * 32, smem, st>>>(a, chunk, next);
+    ALGP_LAUNCH_CHECK();
+  }
+  return ALGP_OK;
 }
 
 // ---------------------------------------------------------------------------
@@ -400,9 +537,11 @@ extern "C" int algp_score_sets_large(const double* Wt, int64_t ldw, int64_t ncol
     // (profiles/r01_score_variants.log); MANY short CTAs beat a persistent resident grid (profiles/r02_score_tiling.log):
     // CTAs that start at different times keep the warps of an SM out of phase, so loads and DMMAs overlap.
     if (work && work_doubles < 0) {
-      // algp_score_sets_tiled, chunked: one launch per chunk of -work_doubles columns, accumulator fragments in work [B][64]
+      // algp_score_sets_tiled, swept in chunks of -work_doubles columns: the persistent launch (its ticket counter is the
+      // first word behind the arrival counters), or one launch per chunk with the accumulator fragments in work [B][64]
       const int chunk = (int)(-work_doubles);
       a.gpart = work + SCORE_COUNTER_DOUBLES;
+      if (score_use_resident()) return score_k8_resident(a, sms, chunk, (unsigned int*)a.gpart, st);
       for (int c0 = 0; c0 < a.ncols16 || c0 == 0; c0 += chunk) {
         a.col0 = c0;
         a.col1 = c0 + chunk;
@@ -470,11 +609,15 @@ extern "C" int algp_score_sets_large(const double* Wt, int64_t ldw, int64_t ncol
 // prologue than they gain in hit rate, and a 36-entry DFMA Gram (instead of the 64-entry DMMA tile) or a persistent
 // resident grid were both slower.
 // ---------------------------------------------------------------------------
-static int g_tile_cols = 0;       // 0 = derive from the L2 size; algp_set_score_tile_cols overrides (tuning / tests)
-
 extern "C" int algp_set_score_tile_cols(int cols) {
   if (cols < -1 || (cols > 0 && (cols & 63))) return ALGP_ERR_INVALID;
   g_tile_cols = cols;
+  return ALGP_OK;
+}
+
+extern "C" int algp_set_score_resident(int mode) {
+  if (mode < -1 || mode > 1) return ALGP_ERR_INVALID;
+  g_resident = mode;
   return ALGP_OK;
 }
 
@@ -490,12 +633,17 @@ static int tiled_chunk_cols(int k, int64_t B, int64_t ncols, int64_t n_rows, int
   int chunk = g_tile_cols;
   if (chunk == 0) {
     const double bytes = 8.0 * (double)B * k * (double)ncols;
-    if (bytes >= 12.0e9 && ncols >= 2048) {
+    // measured on configs[2] (profiles/r02_score_resident.log): the persistent sweep wins from ~12 000 sets of 8 on
+    // (3 GB of row reads: 0.287 vs 0.315 ms; 16 384 sets 0.373 vs 0.425; 65 536 sets 1.26-1.30 vs 1.48-1.61), the
+    // per-chunk launches only from ~12 GB
+    if (bytes >= (score_use_resident() ? 3.0e9 : 12.0e9) && ncols >= 2048) {
       int dev = 0, l2 = 64 << 20;
       ALGP_CUDA(cudaGetDevice(&dev));
       ALGP_CUDA(cudaDeviceGetAttribute(&l2, cudaDevAttrL2CacheSize, dev));
-      // the slice of a launch about the size of the L2: 1024 columns for the 16 384 rows of configs[2]
-      int64_t c = ((int64_t)l2 / (8 * n_rows) + 32) / 64 * 64;
+      // the slice of a chunk about the size of the L2 for the chunked launches (1024 columns for the 16 384 rows of
+      // configs[2]), three quarters of it for the resident form, whose warps are not all on the same chunk (768)
+      const int64_t budget = score_use_resident() ? (int64_t)l2 / 4 * 3 : (int64_t)l2;
+      int64_t c = (budget / (8 * n_rows) + 32) / 64 * 64;
       chunk = (int)(c < 256 ? 256 : c);
     }
   }
@@ -510,6 +658,13 @@ extern "C" int algp_score_sets_tiled_launches(int k, int64_t B, int64_t ncols, i
   int chunk = 0;
   if (tiled_chunk_cols(k, B, ncols, n_rows, &chunk)) return 0;
   if (chunk <= 0) return 1;
+  if (score_use_resident()) {
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int64_t batch = score_resident_batch(sms);
+    return (int)((B + batch - 1) / batch);
+  }
   const int64_t ncols16 = (ncols + 15) / 16 * 16;
   int launches = 0;
   for (int64_t c0 = 0; c0 < ncols16 || c0 == 0; c0 += chunk) ++launches;
@@ -523,9 +678,9 @@ extern "C" int algp_score_sets_tiled(const double* Wt, int64_t ldw, int64_t ncol
                                      void* stream) {
   if (k < 1 || k > 8 || B < 0 || n_rows < 1) return ALGP_ERR_INVALID;
   if (B > 0 && (!work || work_doubles < algp_score_sets_tiled_work_doubles(B) || ((uintptr_t)work & 15))) return ALGP_ERR_INVALID;
-  // g_tile_cols > 0: that chunk; -1: plain single launch; 0 (auto): chunked launches where ONE call streams enough for
-  // the L2 hit rate to pay for the per-chunk prologues (>= ~12 GB: 1.50 vs 1.69 ms on configs[2] for an isolated call;
-  // back-to-back calls on the same rows find part of them in L2 anyway and the two are level), else the single launch
+  // g_tile_cols > 0: that chunk; -1: plain single launch; 0 (auto): a sweep in L2-sized column chunks where ONE call
+  // streams enough for the L2 hit rate to pay for the per-chunk prologues (persistent form: >= ~3 GB), else the single
+  // launch (small batches: split candidates)
   int chunk = 0;
   const int rc = tiled_chunk_cols(k, B, ncols, n_rows, &chunk);
   if (rc) return rc;

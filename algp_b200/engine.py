@@ -508,7 +508,8 @@ class PosteriorState(object):
     COV_MAX_K = 128                # slots per candidate algp_score_sets_cov accepts
     # priors of the rent-or-buy rule, replaced by measurements as soon as there are any: every streaming call is timed with
     # CUDA events (_harvest_stream_time) and every build calibrates the build rate (_measured_build_rate)
-    STREAM_BYTES_PER_S = 10.0e12   # L2->SM delivery of score_sets_k8_kernel (profiles/r02_prof_score_summary.csv)
+    STREAM_BYTES_PER_S = 10.0e12   # L2->SM delivery of the single-launch scoring kernel (profiles/r02_prof_score_summary.csv); the
+                                   # persistent sweep of large batches reaches 13.9e12 (r02_prof_score_resident_summary.csv)
     COV_FLOPS_PER_S = {"fp64": 30.0e12, "i8": 100.0e12}   # lower-triangle SYRK rates of algp_gemm_nt / algp_gemm_nt_i8
 
     _measured_build_rate = {}      # kind -> flops/s of the last build_cov() in this process (replaces the prior below)
@@ -600,9 +601,10 @@ class PosteriorState(object):
         self.build_cov()
         return True
 
-    # k <= 8: "auto" = algp_score_sets_tiled decides (one launch with a split tail; one launch per L2-sized column chunk
-    # for isolated calls that stream >= ~12 GB), "stream" = the plain single launch of algp_score_sets, "tiled" = same
-    # entry as "auto" (tests force the chunk through algp_set_score_tile_cols)
+    # k <= 8: "auto" = algp_score_sets_tiled decides (split candidates for small batches; one persistent launch that
+    # sweeps L2-sized column chunks with the partial Grams in shared memory for calls that stream >= ~3 GB), "stream" =
+    # the plain single launch of algp_score_sets, "tiled" = same entry as "auto" (tests force the chunk and the form
+    # through algp_set_score_tile_cols / algp_set_score_resident)
     score_mode = "auto"
 
     def _want_tiled(self, B, k):
@@ -643,7 +645,7 @@ class PosteriorState(object):
             if getattr(self, "_tilework", None) is None or self._tilework.numel() < nwork:
                 # zero-filled: the head of the buffer holds the arrival counters of the split-candidate kernel
                 self._tilework = torch.zeros(nwork, dtype=torch.float64, device=idx.device)
-            # one launch per L2-sized column chunk for calls that stream >= 12 GB (4 for configs[2]), else one
+            # kernel launches this call makes: one (the persistent sweep takes ~68 000 candidates per launch)
             nlaunch = max(1, _lib.lib.algp_score_sets_tiled_launches(k, B, self.ncols, self.n_pad))
             call("algp_score_sets_tiled", ptr(self.Wt), self.ldw, self.ncols, self.n_pad, ptr(self.X), self.hyper.d, ls_p,
                  self.hyper.log_os, self.hyper.kind, self.hyper.noise, ptr(self.pi), ptr(idx), ptr(delta),

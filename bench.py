@@ -1541,28 +1541,31 @@ def run_ours(args, rank, world, local_rank):
     if rank == 0:
         algo_bytes = 8.0 * N_BASE * K_SET * N_CAND           # s*N*k per candidate
         achieved = algo_bytes / (kernel_ms / 1e3) / 1e9
-        # the timed step scores its batch through algp_score_sets_tiled, which streams 17.2 GB and therefore launches the
-        # kernel once per L2-sized column chunk (4 x 1024 columns): the ncu capture of exactly those launches
-        # (profiles/r02_prof_score_tiled_summary.csv, summed) is the traffic of a step; the earlier capture of the plain
-        # single launch is kept beside it
+        # the timed step scores its batch through algp_score_sets_tiled, which streams 17.2 GB and therefore runs the
+        # persistent sweep (one launch: 768-column chunks, partial Grams in shared memory): the ncu capture of exactly
+        # that launch (profiles/r02_prof_score_resident_summary.csv) is the traffic of a step; the captures of the
+        # earlier forms (one launch per 1024-column chunk; the plain single launch) are kept beside it
         launches_per_step = max(1, _lib.lib.algp_score_sets_tiled_launches(K_SET, N_CAND, state.ncols, state.n_pad))
-        traffic, traffic_src, ncu_ms, ncu_extra = ncu_dram_traffic("score_sets_k8_kernel", files=("r02_prof_score_tiled_summary.csv",),
-                                                                  reduce="sum")
+        traffic, traffic_src, ncu_ms, ncu_extra = ncu_dram_traffic("score_sets_k8_resident_kernel",
+                                                                  files=("r02_prof_score_resident_summary.csv",), reduce="sum")
+        chunked = ncu_dram_traffic("score_sets_k8_kernel", files=("r02_prof_score_tiled_summary.csv",), reduce="sum")
         single = ncu_dram_traffic("score_sets_k8_kernel")
+        kernel_name = "score_sets_k8_resident_kernel"
         if traffic is None or (ncu_extra or {}).get("launches") != launches_per_step:
-            traffic, traffic_src, ncu_ms = single            # no capture of the chunked form for this shape
+            traffic, traffic_src, ncu_ms = single            # no capture of the shipped form for this shape
             ncu_extra = None
+            kernel_name = "score_sets_k8_kernel"
         gram_flops = 2.0 * N_BASE * K_SET * K_SET * N_CAND   # the full 8 x 8 Gram the DMMA tiles compute
-        roof = {"bound": "hbm", "kernel": "score_sets_k8_kernel", "achieved": achieved, "peak": peak_hbm,
+        roof = {"bound": "hbm", "kernel": kernel_name, "achieved": achieved, "peak": peak_hbm,
                 "unit": "GB/s", "frac": achieved / peak_hbm, "traffic": traffic, "traffic_source": traffic_src,
                 "peak_source": peak_src, "kernel_ms": kernel_ms, "kernel_launches_per_step": launches_per_step,
                 "algorithmic_bytes_per_launch": algo_bytes,
-                "note": "one step = ONE algp_score_sets_tiled call = %d launches of the kernel (one per 1024-column chunk); "
-                        "`achieved`, `traffic`, `kernel_ms` and `algorithmic_bytes_per_launch` are per step (the launches "
-                        "summed).  `achieved` is SURVEY 8d's no-reuse byte count over the kernel time: it exceeds the DRAM peak "
-                        "because the L2 serves most of the rows (59 %% sector hits in the capture), so `frac` is not a fraction of "
-                        "a roof.  The resources the kernel actually loads are under `resources`; none is saturated: all "
-                        "algorithmic bytes cross the L2 -> SM path exactly once, and the DMMA pipe is the busiest unit." % launches_per_step}
+                "note": "one step = ONE algp_score_sets_tiled call = %d launch(es) of the persistent sweep (column chunks sized "
+                        "for the L2, the candidates' partial Grams resident in shared memory).  `achieved` is SURVEY 8d's "
+                        "no-reuse byte count over the kernel time: it exceeds the DRAM peak because the L2 serves most of the "
+                        "rows (sector hits in the capture: `resources.dram.l2_sector_hit_pct_ncu`), so `frac` is not a "
+                        "fraction of a roof.  The resources the kernel actually loads are under `resources`; none is saturated: "
+                        "all algorithmic bytes cross the L2 -> SM path exactly once, and the DMMA pipe is the busiest unit." % launches_per_step}
         res = {}
         if traffic is not None:
             res["dram"] = {"bytes_per_step_ncu": traffic, "achieved_gbs": traffic / (kernel_ms / 1e3) / 1e9, "peak_gbs": peak_hbm,
@@ -1574,6 +1577,12 @@ def run_ours(args, rank, world, local_rank):
                                    "`frac_within_the_ncu_capture`"}
             if ncu_extra:
                 res["dram"]["l2_sector_hit_pct_ncu"] = ncu_extra.get("l2_hit_pct")
+            if chunked[0] is not None and chunked[1] != traffic_src:
+                res["dram"]["per_chunk_launches_capture"] = {
+                    "bytes": chunked[0], "ncu_kernel_ms": chunked[2], "source": chunked[1],
+                    "l2_sector_hit_pct_ncu": (chunked[3] or {}).get("l2_hit_pct"),
+                    "note": "the form shipped before the persistent sweep: 4 launches of 1024-column chunks, accumulator "
+                            "fragments parked in global memory between them"}
             if single[0] is not None and single[1] != traffic_src:
                 res["dram"]["plain_single_launch_capture"] = {
                     "bytes": single[0], "ncu_kernel_ms": single[2], "source": single[1],

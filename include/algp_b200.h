@@ -172,23 +172,29 @@ int64_t algp_score_sets_large_work_doubles(int k, int64_t B);
  *  - small batches (up to ~1.5 x the resident warp slots, ~5000 sets): every candidate is scored by 2 or 4 independent warps,
  *    each over a slice of the columns; fragments and per-candidate arrival counters live in `work`, the warp that
  *    arrives last finishes the candidate (no barrier, no extra launch);
- *  - one call that streams >= ~12 GB of rows: one launch per L2-sized column chunk with the accumulator fragments
- *    parked in `work` between launches (random sets re-read every row of Wt many times; a chunk's slice of Wt, n_rows x
- *    chunk x 8 bytes, fits the L2 where whole rows do not: 1.50 vs 1.69 ms on configs[2]);
+ *  - one call that streams >= ~3 GB of rows: the columns of Wt are swept in L2-sized chunks (random sets re-read every
+ *    row of Wt many times; a chunk's slice of Wt, n_rows x chunk x 8 bytes, fits the L2 where whole rows do not) by
+ *    ONE persistent launch whose warps own their candidates for the whole call and keep the partial Grams in shared
+ *    memory between chunks (1.26-1.34 ms on configs[2] against 1.51-1.67 for the single launch); the older form --
+ *    one launch per chunk, accumulator fragments parked in `work` -- is kept behind the switches below (1.45-1.55 ms);
  *  - else the plain single launch.
  * work: algp_score_sets_tiled_work_doubles(B) doubles, 16-byte aligned, ZERO-FILLED when allocated and then left to
  * the library (its head holds arrival counters that are never reset); one workspace per stream.
- * algp_set_score_tile_cols(c): c > 0 forces chunked launches of c columns (multiple of 64), -1 the plain single
- * launch, 0 the default policy. */
+ * algp_set_score_tile_cols(c): c > 0 forces a sweep in chunks of c columns (multiple of 64), -1 the plain single
+ * launch, 0 the default policy.  algp_set_score_resident(m): how a chunked sweep runs -- 1 the persistent launch, -1
+ * one launch per chunk, 0 (default) persistent when the library derived the chunk, per-chunk launches when
+ * algp_set_score_tile_cols forced it.  Both are process-wide tuning / test switches. */
 int algp_score_sets_tiled(const double* Wt, int64_t ldw, int64_t ncols, int64_t n_rows, const double* X, int d,
                           const double* log_ls_host, double log_os, int kind, double noise, const double* pi0,
                           const int32_t* idx, const double* delta, double delta_scalar, const uint8_t* skip, int k,
                           int64_t B, double H_base, double* scores, double* work, int64_t work_doubles, void* stream);
 int64_t algp_score_sets_tiled_work_doubles(int64_t B);
-/* Kernel launches one algp_score_sets_tiled call of this shape makes (one per column chunk in the chunked form);
+/* Kernel launches one algp_score_sets_tiled call of this shape makes (one per column chunk in the per-chunk form, one
+ * per ~68 000 candidates in the persistent form);
  * <= 0 for an invalid shape.  For callers that count launches. */
 int algp_score_sets_tiled_launches(int k, int64_t B, int64_t ncols, int64_t n_rows);
 int algp_set_score_tile_cols(int cols);
+int algp_set_score_resident(int mode);
 /* The same scores from a RESIDENT posterior covariance of the base set, P = Sigma + sigma_n^2 I - Wt Wt^T
  * (lower triangle of an [n x ldp] matrix; build it with algp_kbuild + algp_gemm_nt / algp_gemm_nt_i8, lower_only):
  * a candidate reads its k(k+1)/2 entries P[c_i][c_j] instead of k rows of Wt.  The Schur complement of

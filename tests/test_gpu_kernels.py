@@ -200,11 +200,13 @@ def test_score_sets_matches_oracle(kind, k):
 
 
 @pytest.mark.parametrize("kind", ["rbf", "matern"])
-@pytest.mark.parametrize("k,tile", [(1, 64), (5, 64), (8, 64), (8, 128), (8, 0), (3, 192), (8, -2), (6, -4)])
+@pytest.mark.parametrize("k,tile", [(1, 64), (5, 64), (8, 64), (8, 128), (8, 0), (3, 192), (8, -2), (6, -4),
+                                    (8, "r64"), (5, "r128"), (1, "r192"), (7, "r1024")])
 def test_score_sets_tiled_matches_oracle_and_streaming(kind, k, tile, monkeypatch):
     """algp_score_sets_tiled -- one launch of the k <= 8 kernel per column chunk with the accumulator fragments parked in
     a work buffer, or (tile 0 / -2 / -4) one launch with 4 / 2 / 4 independent warps per candidate and a last-arriver
-    epilogue -- against the oracle and the plain single launch, several calls on the same workspace: several chunks per candidate, a column count that is not a multiple of the
+    epilogue, or ("r<chunk>") the persistent launch that sweeps the chunks with the partial Grams in shared memory --
+    against the oracle and the plain single launch, several calls on the same workspace: several chunks per candidate, a column count that is not a multiple of the
     64-column step (appended columns), empty / duplicate / zero-increment slots and skip flags."""
     from algp_b200 import _lib
     X, th, hy, static, mobile, pi0, cov, ss, ms, rng = scoring_problem(kind, n_side=24, n_base=300, d_extra=(2 if k == 5 else 0))
@@ -228,7 +230,10 @@ def test_score_sets_tiled_matches_oracle_and_streaming(kind, k, tile, monkeypatc
     ost = O.posterior_state(cov, pi1)
     skip = np.zeros(n, dtype=np.uint8)
     skip[rng.choice(n, n // 10, replace=False)] = 1
-    if tile < 0:                                   # -2 / -4: the default policy with 2 / 4 warps per candidate forced
+    if isinstance(tile, str):                      # "r<chunk>": the persistent form
+        assert _lib.lib.algp_set_score_resident(1) == 0
+        tile = int(tile[1:])
+    elif tile < 0:                                 # -2 / -4: the default policy with 2 / 4 warps per candidate forced
         monkeypatch.setenv("ALGP_SCORE_PARTS", str(-tile))
         tile = 0
     assert _lib.lib.algp_set_score_tile_cols(tile) == 0
@@ -252,7 +257,40 @@ def test_score_sets_tiled_matches_oracle_and_streaming(kind, k, tile, monkeypatc
         assert state.score_sets(dev(idx[:0], torch.int32), dev(delta[:0])).numel() == 0
     finally:
         _lib.lib.algp_set_score_tile_cols(0)
+        _lib.lib.algp_set_score_resident(0)
     assert _lib.lib.algp_set_score_tile_cols(100) == 1       # not a multiple of 64: rejected
+    assert _lib.lib.algp_set_score_resident(2) == 1
+
+
+def test_score_sets_resident_sweep_large_batch():
+    """The persistent sweep on more candidates than one launch owns (80 % of 148 x 24 x 24 shared-memory slots): the
+    batch is cut into several launches; every candidate is scored exactly once and equals the plain single launch.
+    Also a batch smaller than the number of resident warps, and the launch count the library reports."""
+    from algp_b200 import _lib
+    X, th, hy, static, mobile, pi0, cov, ss, ms, rng = scoring_problem("rbf", n_side=24, n_base=300)
+    n = len(X)
+    B = 150000
+    idx = rng.integers(0, n, size=(B, 8)).astype(np.int32)          # repeats inside a set are allowed (first one counts)
+    idx[rng.random((B, 8)) < 0.1] = -1
+    state = engine.PosteriorState(hy, dev(X), np.nonzero(pi0 > 0)[0], pi0, cov_mode="never")
+    idx_d = dev(idx, torch.int32)
+    state.score_mode = "stream"
+    ref = state.score_sets(idx_d, None, delta_scalar=1 / ms ** 2)
+    state.score_mode = "tiled"
+    try:
+        assert _lib.lib.algp_set_score_resident(1) == 0
+        assert _lib.lib.algp_set_score_tile_cols(128) == 0
+        nl = _lib.lib.algp_score_sets_tiled_launches(8, B, state.ncols, state.n_pad)
+        sms = torch.cuda.get_device_properties(0).multi_processor_count
+        assert nl == -(-B // (sms * 24 * 24 * 4 // 5)) and nl >= 2
+        for Bc in (B, 1000, 3):
+            out = torch.full((Bc,), float("nan"), dtype=torch.float64, device="cuda")
+            got = state.score_sets(idx_d[:Bc], None, delta_scalar=1 / ms ** 2, out=out)
+            assert not bool(torch.isnan(got).any())
+            assert float((got - ref[:Bc]).abs().max()) < 1e-10
+    finally:
+        _lib.lib.algp_set_score_tile_cols(0)
+        _lib.lib.algp_set_score_resident(0)
 
 
 def test_score_sets_split_candidates_share_one_workspace(monkeypatch):
