@@ -250,61 +250,96 @@ static void score_k8_launch(const ScoreArgs& a, int sms, int blocks_per_sm, int 
 
 // ---------------------------------------------------------------------------
 // k <= 8, large batches: ONE persistent launch that sweeps the columns of Wt in L2-sized chunks with the candidates'
-// partial Grams resident in shared memory (the form algp_score_sets_tiled picks for batches that stream >= 3 GB).
+// partial Grams resident in shared memory (the form algp_score_sets_tiled picks for batches that stream >= 2 GB).
 //
 // The chunked launches further down park every candidate's accumulator fragment in global memory between launches
 // (34 MB written and 34 MB read per chunk at 65 536 candidates: as much L2 traffic as a 512-column slice of Wt) and pay
 // a ramp and a tail per launch, so their best chunk is 1024 columns -- a 100 MB slice of which the 126 MB L2 keeps
-// 59 % (4.8 GB of DRAM reads per call for 0.4 GB of distinct rows).  Here each of the 24 warps of the one CTA per SM
-// OWNS up to SR_CAP candidates for the whole call: the lower triangle of a candidate's Gram (36 doubles), its eight
-// row indices after the slot rule and its id wait in the warp's own shared-memory region between chunks -- 65 536 x
-// 324 B = 21 MB over the 148 SMs -- so no fragment leaves the SM, no warp ever waits for another, and the chunk can be
-// as narrow as the L2 likes: 768 columns for the 16 384 rows of configs[2], 88 % sector hits, 1.1 GB of DRAM reads
-// (ncu: profiles/r02_prof_score_resident_summary.csv).  With the slice in L2 the loop is latency-bound, so a warp
-// keeps FOUR 128-byte lines per row in flight (96 KB per SM) where the DRAM-heavy single launch was best with two.
-// Ownership is decided during the first chunk by a global ticket counter: a warp on a fast SM takes more candidates
-// than one on a slow SM and keeps that share for the remaining chunks, which a static partition cannot do.  Shared
-// memory is kept to 187 KB: at 218 KB the L1 that stages the loads in flight shrinks and the kernel is 60 % slower.
-// Measured (profiles/r02_score_resident.log): 1.26-1.34 ms per 65 536 sets where the chunked launches take 1.45-1.55
-// and the single launch 1.51-1.67 on the same box.
+// 59 % (4.8 GB of DRAM reads per call for 0.4 GB of distinct rows).  Here an SM OWNS up to SR_CAP candidates for the
+// whole call: the lower triangle of a candidate's Gram (36 doubles), its eight row indices after the slot rule, its id
+// and a progress word wait in shared memory between chunks -- 65 536 x 328 B = 21 MB over the 148 SMs -- so no
+// fragment leaves the SM and the chunk can be as narrow as the L2 likes: 768 columns for the 16 384 rows of
+// configs[2], 74 % sector hits, 2.6 GB of DRAM reads (ncu: profiles/r02_prof_score_resident_summary.csv).  With the
+// slice in L2 the loop is latency-bound, so a warp keeps FOUR 128-byte lines per row in flight (96 KB per SM) where
+// the DRAM-heavy single launch was best with two.
+//
+// Work items are (candidate, chunk) pairs.  Chunk-0 items are created by taking a shared-memory slot and a ticket
+// from a global counter, so a fast SM (fewer SMs sharing its GPC's path to the L2) takes more candidates than a slow
+// one and keeps that share for the remaining chunks, which a static partition cannot do.  After one CTA barrier (the
+// slot list is final) the 24 warps take the remaining items of their SM chunk-major from a shared-memory counter:
+// the whole SM moves through the chunks together, and a batch of only a few candidates per warp (8192 sets: 2.3)
+// still splits evenly.  Item (slot, c) needs item (slot, c-1), which has a smaller index and is therefore already
+// taken by a warp that is running: the progress word of the slot is polled, nothing can deadlock.  Sums are in
+// chunk order whatever the schedule: results are deterministic.  Shared memory is kept to 189 KB: at 218 KB the L1
+// that stages the loads in flight shrinks and the kernel is 60 % slower.
+// Measured (profiles/r02_score_resident.log): 1.22-1.29 ms per 65 536 sets where the per-chunk launches take
+// 1.45-1.55 and the single launch 1.51-1.67 on the same box; 8192 sets 0.214 against 0.234.
 // ---------------------------------------------------------------------------
 static int g_tile_cols = 0;       // 0 = derive from the L2 size; algp_set_score_tile_cols overrides (tuning / tests)
 static int g_resident = 0;        // 0 = auto (resident when the chunk is derived, launches when it is forced), 1 always, -1 never
 static bool score_use_resident() { return g_resident > 0 || (g_resident == 0 && g_tile_cols == 0); }
 
 #define SR_WARPS 24
-#define SR_CAP 24
+#define SR_CAP (24 * 24)                                   // candidates per SM
 #define SR_UNROLL 4
-#define SR_SLOT_BYTES (36 * sizeof(double) + 9 * sizeof(int))
+#define SR_SLOT_BYTES (36 * sizeof(double) + 10 * sizeof(int))
+#define SR_NO_CAND 0xffffffffu
 __global__ void __launch_bounds__(SR_WARPS * 32, 1) score_sets_k8_resident_kernel(const ScoreArgs a, int chunk, unsigned int* next) {
-  extern __shared__ __align__(16) double sr_gram[];        // [SR_WARPS][SR_CAP][36] Grams, then [.][.][8] rows, [.][.] ids
-  const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3, warp = threadIdx.x >> 5;
+  // [SR_CAP][36] Grams, [SR_CAP][8] rows, [SR_CAP] ids, [SR_CAP] chunks done, {slots taken, items taken}
+  extern __shared__ __align__(16) double sr_gram[];
+  int* rows = reinterpret_cast<int*>(sr_gram + (size_t)SR_CAP * 36);
+  unsigned int* ids = reinterpret_cast<unsigned int*>(rows + SR_CAP * 8);
+  volatile int* done = reinterpret_cast<volatile int*>(ids + SR_CAP);
+  int* ctr = const_cast<int*>(done) + SR_CAP;
+  const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
   const int d = a.kp.d;
   constexpr int STEP = 16 * SR_UNROLL;
-  double* mine = sr_gram + (size_t)warp * SR_CAP * 36 + g * (g + 1) / 2 + 2 * t;   // entry (g, 2t) of my first candidate
-  int* rows = reinterpret_cast<int*>(sr_gram + (size_t)SR_WARPS * SR_CAP * 36) + warp * SR_CAP * 8;   // row or -1
-  unsigned int* ids = reinterpret_cast<unsigned int*>(sr_gram + (size_t)SR_WARPS * SR_CAP * 36) + SR_WARPS * SR_CAP * 8 + warp * SR_CAP;
+  const int tri = g * (g + 1) / 2 + 2 * t;                 // entry (g, 2t) of a slot's lower triangle
   const bool keep0 = 2 * t <= g, keep1 = 2 * t + 1 <= g;   // lower triangle incl. the diagonal: all the epilogue reads
   const int nchunks = a.ncols16 > chunk ? (a.ncols16 + chunk - 1) / chunk : 1;
-  int n_mine = 0;
+  if (threadIdx.x == 0) ctr[0] = ctr[1] = 0;
+  __syncthreads();
 
-  for (int c = 0; c < nchunks; ++c) {
-    const int col0 = c * chunk;
-    const int cend = (col0 + chunk < a.ncols16) ? col0 + chunk : a.ncols16;
-    for (int i = 0; i < SR_CAP; ++i) {
-      unsigned int cu;
-      if (c == 0) {                                        // take a ticket
-        cu = 0;
-        if (lane == 0) cu = atomicAdd(next, 1u);
+  // item (slot, c): chunk c of the candidate in `slot`.  c == 0 items are created by taking a slot and a ticket.
+  int count = 0, total = 0;
+  for (int phase = 0; phase < 2; ++phase) {
+    if (phase == 1) {
+      if (nchunks == 1) break;
+      __syncthreads();                                     // every chunk-0 item of this SM is done, the slot list is final
+      count = ctr[0] < SR_CAP ? ctr[0] : SR_CAP;
+      total = count * (nchunks - 1);
+    }
+    for (;;) {
+      int slot = 0, c = 0;
+      unsigned int cu = 0;
+      if (phase == 0) {
+        if (lane == 0) {
+          slot = atomicAdd(&ctr[0], 1);
+          cu = slot < SR_CAP ? atomicAdd(next, 1u) : SR_NO_CAND;
+        }
+        slot = __shfl_sync(0xffffffffu, slot, 0);
         cu = __shfl_sync(0xffffffffu, cu, 0);
-        if ((int64_t)cu >= a.B) break;
-        if (lane == 0) ids[i] = cu;
-        n_mine = i + 1;
+        if (slot >= SR_CAP) break;
+        if ((int64_t)cu >= a.B) {                          // tickets ran out: the slot stays empty
+          if (lane == 0) ids[slot] = SR_NO_CAND;
+          break;
+        }
+        if (lane == 0) ids[slot] = cu;
       } else {
-        if (i >= n_mine) break;
-        cu = ids[i];
+        int j = 0;
+        if (lane == 0) j = atomicAdd(&ctr[1], 1);
+        j = __shfl_sync(0xffffffffu, j, 0);
+        if (j >= total) break;
+        c = 1 + j / count;
+        slot = j - (c - 1) * count;
+        cu = ids[slot];
+        if (cu == SR_NO_CAND) continue;
+        while (done[slot] < c) {}                          // chunk c-1 of this slot is an earlier item: some warp is on it
+        __threadfence_block();
       }
       const int64_t cand = cu;
+      const int col0 = c * chunk;
+      const int cend = (col0 + chunk < a.ncols16) ? col0 + chunk : a.ncols16;
       int my_idx = -1;
       double my_delta = 0.0;
       bool active;
@@ -315,12 +350,12 @@ __global__ void __launch_bounds__(SR_WARPS * 32, 1) score_sets_k8_resident_kerne
       if (c == 0) {                                        // the slot rule once per candidate; later chunks read the row back
         active = score_k8_slot(a, cand, g, my_idx, my_delta);
         my_row = active ? my_idx : -1;
-        if (t == 0) rows[i * 8 + g] = my_row;
+        if (t == 0) rows[slot * 8 + g] = my_row;
       } else {
-        my_row = rows[i * 8 + g];
+        my_row = rows[slot * 8 + g];
         active = my_row >= 0;
-        if (keep0) c0[0] = mine[i * 36];
-        if (keep1) c1[0] = mine[i * 36 + 1];
+        if (keep0) c0[0] = sr_gram[slot * 36 + tri];
+        if (keep1) c1[0] = sr_gram[slot * 36 + tri + 1];
       }
       const double* row = a.Wt + (int64_t)(active ? my_row : 0) * a.ldw + 4 * t;
       for (int k0 = col0; k0 < cend; k0 += STEP) {
@@ -332,8 +367,11 @@ __global__ void __launch_bounds__(SR_WARPS * 32, 1) score_sets_k8_resident_kerne
       const double G0 = (c0[0] + c0[1]) + (c0[2] + c0[3]);
       const double G1 = (c1[0] + c1[1]) + (c1[2] + c1[3]);
       if (c + 1 < nchunks) {
-        if (keep0) mine[i * 36] = G0;
-        if (keep1) mine[i * 36 + 1] = G1;
+        if (keep0) sr_gram[slot * 36 + tri] = G0;
+        if (keep1) sr_gram[slot * 36 + tri + 1] = G1;
+        __threadfence_block();
+        __syncwarp();
+        if (lane == 0) done[slot] = c + 1;
         continue;
       }
       if (c > 0) active = score_k8_slot(a, cand, g, my_idx, my_delta);
@@ -342,13 +380,13 @@ __global__ void __launch_bounds__(SR_WARPS * 32, 1) score_sets_k8_resident_kerne
   }
 }
 
-// Candidates one resident launch takes: 80 % of the shared-memory slots.  A warp stops taking tickets when its SR_CAP
+// Candidates one resident launch takes: 80 % of the shared-memory slots.  An SM stops taking tickets when its SR_CAP
 // slots are full, so every candidate is taken as long as the batch is below the slot count; the 20 % are the room the
 // fast SMs need to take more than their even share.
-static int64_t score_resident_batch(int sms) { return (int64_t)sms * SR_WARPS * SR_CAP * 4 / 5; }
+static int64_t score_resident_batch(int sms) { return (int64_t)sms * SR_CAP * 4 / 5; }
 
 static int score_k8_resident(ScoreArgs a, int sms, int chunk, unsigned int* next, cudaStream_t st) {
-  const size_t smem = (size_t)SR_WARPS * SR_CAP * SR_SLOT_BYTES;
+  const size_t smem = (size_t)SR_CAP * SR_SLOT_BYTES + 2 * sizeof(int);
   static AlgpPerDevice configured;
   if (configured.raise(smem)) {
     ALGP_CUDA(cudaFuncSetAttribute(score_sets_k8_resident_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -633,10 +671,10 @@ static int tiled_chunk_cols(int k, int64_t B, int64_t ncols, int64_t n_rows, int
   int chunk = g_tile_cols;
   if (chunk == 0) {
     const double bytes = 8.0 * (double)B * k * (double)ncols;
-    // measured on configs[2] (profiles/r02_score_resident.log): the persistent sweep wins from ~12 000 sets of 8 on
-    // (3 GB of row reads: 0.287 vs 0.315 ms; 16 384 sets 0.373 vs 0.425; 65 536 sets 1.26-1.30 vs 1.48-1.61), the
-    // per-chunk launches only from ~12 GB
-    if (bytes >= (score_use_resident() ? 3.0e9 : 12.0e9) && ncols >= 2048) {
+    // measured on configs[2] (profiles/r02_score_resident.log): the persistent sweep wins from ~8000 sets of 8 on
+    // (2 GB of row reads: 8192 sets 0.214 vs 0.234 ms; 16 384 sets 0.357 vs 0.410; 65 536 sets 1.22-1.29 vs 1.48-1.61;
+    // 4096 sets are level with the split candidates), the per-chunk launches only from ~12 GB
+    if (bytes >= (score_use_resident() ? 2.0e9 : 12.0e9) && ncols >= 2048) {
       int dev = 0, l2 = 64 << 20;
       ALGP_CUDA(cudaGetDevice(&dev));
       ALGP_CUDA(cudaDeviceGetAttribute(&l2, cudaDevAttrL2CacheSize, dev));
@@ -679,7 +717,7 @@ extern "C" int algp_score_sets_tiled(const double* Wt, int64_t ldw, int64_t ncol
   if (k < 1 || k > 8 || B < 0 || n_rows < 1) return ALGP_ERR_INVALID;
   if (B > 0 && (!work || work_doubles < algp_score_sets_tiled_work_doubles(B) || ((uintptr_t)work & 15))) return ALGP_ERR_INVALID;
   // g_tile_cols > 0: that chunk; -1: plain single launch; 0 (auto): a sweep in L2-sized column chunks where ONE call
-  // streams enough for the L2 hit rate to pay for the per-chunk prologues (persistent form: >= ~3 GB), else the single
+  // streams enough for the L2 hit rate to pay for the per-chunk prologues (persistent form: >= ~2 GB), else the single
   // launch (small batches: split candidates)
   int chunk = 0;
   const int rc = tiled_chunk_cols(k, B, ncols, n_rows, &chunk);

@@ -602,7 +602,7 @@ class PosteriorState(object):
         return True
 
     # k <= 8: "auto" = algp_score_sets_tiled decides (split candidates for small batches; one persistent launch that
-    # sweeps L2-sized column chunks with the partial Grams in shared memory for calls that stream >= ~3 GB), "stream" =
+    # sweeps L2-sized column chunks with the partial Grams in shared memory for calls that stream >= ~2 GB), "stream" =
     # the plain single launch of algp_score_sets, "tiled" = same entry as "auto" (tests force the chunk and the form
     # through algp_set_score_tile_cols / algp_set_score_resident)
     score_mode = "auto"

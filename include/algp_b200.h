@@ -172,10 +172,10 @@ int64_t algp_score_sets_large_work_doubles(int k, int64_t B);
  *  - small batches (up to ~1.5 x the resident warp slots, ~5000 sets): every candidate is scored by 2 or 4 independent warps,
  *    each over a slice of the columns; fragments and per-candidate arrival counters live in `work`, the warp that
  *    arrives last finishes the candidate (no barrier, no extra launch);
- *  - one call that streams >= ~3 GB of rows: the columns of Wt are swept in L2-sized chunks (random sets re-read every
+ *  - one call that streams >= ~2 GB of rows: the columns of Wt are swept in L2-sized chunks (random sets re-read every
  *    row of Wt many times; a chunk's slice of Wt, n_rows x chunk x 8 bytes, fits the L2 where whole rows do not) by
- *    ONE persistent launch whose warps own their candidates for the whole call and keep the partial Grams in shared
- *    memory between chunks (1.26-1.34 ms on configs[2] against 1.51-1.67 for the single launch); the older form --
+ *    ONE persistent launch whose SMs own their candidates for the whole call and keep the partial Grams in shared
+ *    memory between chunks (1.22-1.29 ms on configs[2] against 1.51-1.67 for the single launch); the older form --
  *    one launch per chunk, accumulator fragments parked in `work` -- is kept behind the switches below (1.45-1.55 ms);
  *  - else the plain single launch.
  * work: algp_score_sets_tiled_work_doubles(B) doubles, 16-byte aligned, ZERO-FILLED when allocated and then left to
