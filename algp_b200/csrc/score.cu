@@ -259,7 +259,7 @@ static void score_k8_launch(const ScoreArgs& a, int sms, int blocks_per_sm, int 
 // whole call: the lower triangle of a candidate's Gram (36 doubles), its eight row indices after the slot rule, its id
 // and a progress word wait in shared memory between chunks -- 65 536 x 328 B = 21 MB over the 148 SMs -- so no
 // fragment leaves the SM and the chunk can be as narrow as the L2 likes: 768 columns for the 16 384 rows of
-// configs[2], 74 % sector hits, 2.6 GB of DRAM reads (ncu: profiles/r02_prof_score_resident_summary.csv).  With the
+// configs[2], 80 % sector hits, 1.9 GB of DRAM reads (ncu: profiles/r02_prof_score_resident_summary.csv).  With the
 // slice in L2 the loop is latency-bound, so a warp keeps FOUR 128-byte lines per row in flight (96 KB per SM) where
 // the DRAM-heavy single launch was best with two.
 //
