@@ -266,6 +266,13 @@ class HotPath(object):
         """agent.py:358-403: index of the path whose mobile samples maximise the joint entropy."""
         if len(paths_mobile_indices) == 1:
             return 0
+        caller_array = isinstance(paths_mobile_indices, np.ndarray) and paths_mobile_indices.ndim == 2
+        sharded = getattr(self, "shard_candidates", False) and not self._use_mi() and torch.distributed.is_available() \
+            and torch.distributed.is_initialized() and torch.distributed.get_world_size() > 1
+        idx_d = None
+        if caller_array and not sharded and paths_mobile_indices.shape[1] <= MAX_SET:
+            # the copy of the caller's array is queued first: its DMA runs while the host sorts out flags and state
+            idx_d = engine.to_dev(paths_mobile_indices, dtype=torch.int32)
         static_sampled, org_mobile = self._sample_flags()
         static_sampled[static_indices] = True
         state, pi = self._state_for(static_sampled, org_mobile, capacity=0)
@@ -276,7 +283,6 @@ class HotPath(object):
         # The slots of a caller's array are range-checked on the device (IndexError as NumPy would raise at
         # agent.py:377; below -1 is out of range too: -1 is the empty slot, not "the last location"); list input
         # has been through NumPy indexing in _pad_paths already.
-        caller_array = isinstance(paths_mobile_indices, np.ndarray) and paths_mobile_indices.ndim == 2
         if caller_array:
             idx = paths_mobile_indices
         else:
@@ -286,15 +292,15 @@ class HotPath(object):
         if getattr(state, "_skip_src", None) is None or not np.array_equal(state._skip_src, org_mobile):
             state._skip_src = org_mobile.copy()
             state._skip = engine.to_dev(org_mobile.astype(np.uint8), dtype=torch.uint8)
-        if getattr(self, "shard_candidates", False) and not self._use_mi() and torch.distributed.is_available() \
-                and torch.distributed.is_initialized() and torch.distributed.get_world_size() > 1:
+        if sharded:
             # one process per GPU, replicated agent: every rank scores a contiguous block of the paths and the
             # per-rank winners are exchanged over NVLink (algp_b200.dist); all ranks return the same index
             from . import dist as adist
             score, best = adist.sharded_best(state, idx, None, delta_scalar=dm, skip=state._skip, check=caller_array)
             self._last_path_scores = None
             return int(best)
-        idx_d = engine.to_dev(idx, dtype=torch.int32)
+        if idx_d is None:
+            idx_d = engine.to_dev(idx, dtype=torch.int32)
         res = getattr(state, "_winner3", None)          # {score bits, winner, slots out of range}: one 24-byte read-back
         if res is None:
             res = state._winner3 = torch.zeros(3, dtype=torch.int64, device=idx_d.device)
