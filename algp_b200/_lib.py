@@ -88,6 +88,7 @@ SIGNATURES = {
     "algp_append_block": (C.c_int, [_p, _i64, _i64, _p, _i64, _i32, _p, _f64, _i32, _f64, _p, _p, _p, _p, _i32, _p, _f64,
                                     _i32, _p, _p]),
     "algp_append_block_work_doubles": (_i64, []),
+    "algp_set_append_block_scalar": (C.c_int, [_i32]),
 }
 
 ERR_NOT_PD = 3

@@ -1078,10 +1078,123 @@ __global__ void __launch_bounds__(256) append_block_kernel(const AppendBlockArgs
   }
 }
 
+// Step 3 on DMMA fragments (the form algp_append_block launches when the rows of Wt are 32-byte aligned and the pitch
+// is a multiple of 16): the pass is the skinny product D[n x 16] = Wt[n x ncols] . Wt_C[16 x ncols]^T.  A warp owns 16
+// rows of Wt (two A fragments) for all columns and multiplies them with the two B fragments of the 16 chosen rows,
+// which every warp re-reads through L1: per 16 columns four 256-bit loads (a lane takes 32 bytes of its row, whose 4
+// doubles feed 4 DMMAs; A and B lanes take the same columns, so the k-order inside a line is permuted alike on both
+// sides) and 16 DMMAs.  No shared-memory staging and no block barrier in the column loop: the scalar version above
+// staged the chosen rows chunk by chunk between two barriers with 16 warps per SM and reached 1.07 TB/s on the
+// 40 000 x 2264 matrix of the configs[4] episode (0.68 ms per path commit; profiles/r02_episode_batch.log).
+// Columns [ncols, ncols rounded up to 16) of every row must be zero, as they are in a zero-filled Wt that only ever
+// gains columns (the scoring kernels read the same tail); a warp reads its own rows before it writes their new
+// columns, so the A side of the tail is zero whatever a chosen row's owner has written there meanwhile.
+#define ABD_ROWS 16
+#define ABD_WARPS 4
+__global__ void __launch_bounds__(ABD_WARPS * 32) append_block_dmma_kernel(const AppendBlockArgs a) {
+  __shared__ double Ts[AB_K * AB_K], dn[AB_K], xj[AB_K * ALGP_MAX_D];
+  __shared__ long long jloc[AB_K];
+  __shared__ double stage_all[ABD_WARPS][ABD_ROWS][AB_K + 1];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, t = lane & 3;
+  const int k = a.k, d = a.kp.d;
+  for (int e = tid; e < AB_K * AB_K; e += ABD_WARPS * 32) Ts[e] = a.pcc[e];
+  if (tid < AB_K) {
+    dn[tid] = tid < k ? a.denom[tid] : 1.0;
+    jloc[tid] = tid < k ? a.idx[tid] : -1;
+  }
+  for (int e = tid; e < AB_K * d; e += ABD_WARPS * 32) {
+    const int c = e / d, q = e % d;
+    xj[c * ALGP_MAX_D + q] = c < k ? a.X[a.idx[c] * d + q] * a.kp.inv_ls[q] : 0.0;
+  }
+  __syncthreads();
+  const int64_t loc0 = ((int64_t)blockIdx.x * ABD_WARPS + warp) * ABD_ROWS;
+  if (loc0 >= a.n) return;
+  double (*stage)[AB_K + 1] = stage_all[warp];
+
+  const int64_t ra0 = loc0 + g < a.n ? loc0 + g : a.n - 1;           // rows past the end repeat the last row (discarded)
+  const int64_t ra1 = loc0 + 8 + g < a.n ? loc0 + 8 + g : a.n - 1;
+  const bool b0_on = g < k, b1_on = g + 8 < k;
+  const double* pa0 = a.Wt + ra0 * a.ldw + 4 * t;
+  const double* pa1 = a.Wt + ra1 * a.ldw + 4 * t;
+  const double* pb0 = a.Wt + (b0_on ? a.idx[g] : 0) * a.ldw + 4 * t;
+  const double* pb1 = a.Wt + (b1_on ? a.idx[g + 8] : 0) * a.ldw + 4 * t;
+  const int ncols16 = (a.ncols + 15) / 16 * 16;
+  // acc[A half][B half][chain]: D[A half * 8 + g][B half * 8 + 2t + {0, 1}]
+  double c0[2][2][2], c1[2][2][2];
+#pragma unroll
+  for (int i = 0; i < 2; ++i)
+#pragma unroll
+    for (int j = 0; j < 2; ++j) c0[i][j][0] = c0[i][j][1] = c1[i][j][0] = c1[i][j][1] = 0.0;
+  for (int k0 = 0; k0 < ncols16; k0 += 16) {
+    double va0[4], va1[4], vb0[4], vb1[4];
+    ld256(pa0 + k0, va0[0], va0[1], va0[2], va0[3]);
+    ld256(pa1 + k0, va1[0], va1[1], va1[2], va1[3]);
+    vb0[0] = vb0[1] = vb0[2] = vb0[3] = 0.0;
+    vb1[0] = vb1[1] = vb1[2] = vb1[3] = 0.0;
+    if (b0_on) ld256_l1(pb0 + k0, vb0[0], vb0[1], vb0[2], vb0[3]);
+    if (b1_on) ld256_l1(pb1 + k0, vb1[0], vb1[1], vb1[2], vb1[3]);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      dmma884(c0[0][0][q & 1], c1[0][0][q & 1], va0[q], vb0[q]);
+      dmma884(c0[0][1][q & 1], c1[0][1][q & 1], va0[q], vb1[q]);
+      dmma884(c0[1][0][q & 1], c1[1][0][q & 1], va1[q], vb0[q]);
+      dmma884(c0[1][1][q & 1], c1[1][1][q & 1], va1[q], vb1[q]);
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 2; ++i)
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      stage[i * 8 + g][j * 8 + 2 * t] = c0[i][j][0] + c0[i][j][1];
+      stage[i * 8 + g][j * 8 + 2 * t + 1] = c1[i][j][0] + c1[i][j][1];
+    }
+  __syncwarp();
+  // P0[loc, j_c] = Sigma[loc, j_c] - dot
+  for (int e = lane; e < ABD_ROWS * AB_K; e += 32) {
+    const int l = e / AB_K, c = e % AB_K;
+    const int64_t loc = loc0 + l;
+    double p = 0.0;
+    if (loc < a.n && c < k) {
+      double r2 = 0.0;
+      for (int q = 0; q < d; ++q) {
+        const double df = a.X[loc * d + q] * a.kp.inv_ls[q] - xj[c * ALGP_MAX_D + q];
+        r2 = fma(df, df, r2);
+      }
+      p = kern_from_r2(r2, a.kp.kind, a.kp.outputscale) + ((loc == jloc[c]) ? a.noise : 0.0) - stage[l][c];
+    }
+    stage[l][c] = p;
+  }
+  __syncwarp();
+  // the k successive rank-1 columns of a row: lane l < 16 owns row loc0 + l
+  if (lane < ABD_ROWS && loc0 + lane < a.n) {
+    double* pr = stage[lane];
+    double ss = 0.0;
+    for (int c = 0; c < k; ++c) {
+      double v = pr[c];
+      for (int c1 = 0; c1 < c; ++c1) v = fma(-pr[c1], Ts[c * AB_K + c1], v);
+      v /= dn[c];
+      pr[c] = v;                                     // w_c[loc]
+      ss = fma(v, v, ss);
+    }
+    a.diagP[loc0 + lane] -= ss;
+  }
+  __syncwarp();
+  for (int e = lane; e < ABD_ROWS * AB_K; e += 32) {
+    const int l = e / AB_K, c = e % AB_K;
+    if (loc0 + l < a.n && c < k) a.Wt[(loc0 + l) * a.ldw + a.ncols + c] = stage[l][c];
+  }
+}
+
 extern "C" int64_t algp_append_block_work_doubles(void) { return AB_K * AB_K + AB_K; }
 
 // Commit k (1..16) DISTINCT locations idx[k] (device int64) with precision increments delta[k] (device, or NULL for
 // delta_scalar): the same k new columns of Wt, diagP, pi and flags as k successive algp_append calls in that order.
+static int g_append_block_scalar = 0;      // tuning / tests: 1 = the scalar shared-memory pass instead of the DMMA one
+extern "C" int algp_set_append_block_scalar(int on) {
+  g_append_block_scalar = on != 0;
+  return ALGP_OK;
+}
+
 extern "C" int algp_append_block(double* Wt, int64_t ldw, int64_t ncols, const double* X, int64_t n, int d,
                                  const double* log_ls_host, double log_os, int kind, double noise, double* diagP,
                                  double* pi, uint8_t* is_static, const void* idx_dev, int k, const double* delta_dev,
@@ -1102,6 +1215,12 @@ extern "C" int algp_append_block(double* Wt, int64_t ldw, int64_t ncols, const d
   ALGP_LAUNCH_CHECK();
   append_block_eliminate_kernel<<<1, 32, 0, st>>>(a);
   ALGP_LAUNCH_CHECK();
+  if (a.ldw % 16 == 0 && ((uintptr_t)Wt & 31) == 0 && !g_append_block_scalar) {
+    const int64_t warps = (n + ABD_ROWS - 1) / ABD_ROWS;
+    append_block_dmma_kernel<<<(unsigned)((warps + ABD_WARPS - 1) / ABD_WARPS), ABD_WARPS * 32, 0, st>>>(a);
+    ALGP_LAUNCH_CHECK();
+    return ALGP_OK;
+  }
   const size_t smem = (size_t)(AB_K * AB_CH + AB_K * AB_K + AB_K + AB_K * ALGP_MAX_D + 8 * AB_LB * AB_K) * 8 + AB_K * 8;
   static AlgpPerDevice configured;
   if (configured.raise(1)) {

@@ -249,12 +249,16 @@ int64_t algp_append_work_doubles(int64_t n);
 /* Commit k (1..16) DISTINCT locations idx[k] (device int64) at once, e.g. the mobile readings of the chosen path
  * (agent.py:179-192): the same k new columns of Wt, diagP, pi and flags as k successive algp_append calls in that
  * order, but Wt is read once instead of k times.  delta[k] on the device, or NULL for delta_scalar.
- * work: algp_append_block_work_doubles() doubles. */
+ * work: algp_append_block_work_doubles() doubles.  Columns [ncols, ncols rounded up to 16) of Wt must be zero (they
+ * are in a zero-filled Wt that only gains columns through these calls; the scoring kernels read the same tail).
+ * With 32-byte aligned rows (ldw % 16 == 0) the pass over Wt runs on DMMA fragments; algp_set_append_block_scalar(1)
+ * forces the scalar pass (tests / tuning, process-wide). */
 int algp_append_block(double* Wt, int64_t ldw, int64_t ncols, const double* X, int64_t n, int d,
                       const double* log_ls_host, double log_os, int kind, double noise, double* diagP, double* pi,
                       uint8_t* is_static, const void* idx_dev, int k, const double* delta_dev, double delta_scalar,
                       int mark_static, double* work, void* stream);
 int64_t algp_append_block_work_doubles(void);
+int algp_set_append_block_scalar(int on);
 
 /* ---- mutual-information criterion (agent.py:330-339, 388-397) ---------------------- */
 /* out[c] = sum_{r>=c} M[r][c]^2 = diag(A^-1) from the inverse factor; work: algp_colsumsq_work_doubles(n) */

@@ -680,9 +680,20 @@ def test_posterior_state_i8_build_matches_dmma():
     np.testing.assert_allclose(sc8, sc64, rtol=1e-10, atol=1e-9)
 
 
+@pytest.mark.parametrize("scalar,pre", [(0, 0), (0, 3), (1, 0), (1, 5)])
 @pytest.mark.parametrize("k", [1, 5, 16, 23])
-def test_append_block_equals_successive_appends(k):
-    """k locations committed at once: the same Wt columns, diag(P), precisions and scores as k rank-1 appends."""
+def test_append_block_equals_successive_appends(k, scalar, pre):
+    """k locations committed at once: the same Wt columns, diag(P), precisions and scores as k rank-1 appends -- through
+    the DMMA pass and the scalar one, on a column count that is a multiple of 16 and (after `pre` greedy picks) not."""
+    from algp_b200 import _lib
+    assert _lib.lib.algp_set_append_block_scalar(scalar) == 0
+    try:
+        _append_block_case(k, pre)
+    finally:
+        _lib.lib.algp_set_append_block_scalar(0)
+
+
+def _append_block_case(k, pre):
     X, y, tr, ytr, rng = field_problem(30, 34, 300, seed=8)
     th, hy = hyper_pair([3.0, 2.5], 1.3, 0.02, "matern")
     n = len(X)
@@ -693,11 +704,13 @@ def test_append_block_equals_successive_appends(k):
     seq = engine.PosteriorState(hy, dev(X), tr, pi0, is_static=pi0 > 0, capacity=40)
     blk = engine.PosteriorState(hy, dev(X), tr, pi0, is_static=pi0 > 0, capacity=40)
     jb = torch.empty(1, dtype=torch.int64, device=seq.X.device)
+    if pre:
+        assert seq.greedy(pre, 100.0) == blk.greedy(pre, 100.0)
     for j in chosen:
         jb.fill_(int(j))
         seq.append(jb, 1.0, mark_static=False)
     blk.append_block([int(j) for j in chosen], 1.0, mark_static=False)
-    assert blk.ncols == seq.ncols == seq.Npad + k
+    assert blk.ncols == seq.ncols == seq.Npad + pre + k
     np.testing.assert_allclose(blk.Wt.cpu().numpy(), seq.Wt.cpu().numpy(), rtol=0, atol=1e-12)
     np.testing.assert_allclose(blk.diagP.cpu().numpy(), seq.diagP.cpu().numpy(), rtol=0, atol=1e-12)
     np.testing.assert_array_equal(blk.pi.cpu().numpy(), seq.pi.cpu().numpy())
