@@ -740,8 +740,9 @@ class PosteriorState(object):
             if return_utilities:
                 uts.append(ut)
         picks = [int(v) for v in pairs[:, 1].cpu().tolist()]
-        if self.factor is not None:
-            self.factor.check()
+        if self.factor is not None and not getattr(self, "_factor_checked", False):
+            self.factor.check()                      # the factorisation's status word: one 4-byte read, once per state
+            self._factor_checked = True
         if return_utilities:
             return picks, torch.stack(uts).cpu().numpy()
         return picks
