@@ -59,6 +59,13 @@ __device__ __forceinline__ void ld256(const double* p, double& a, double& b, dou
 __device__ __forceinline__ void ld256_l1(const double* p, double& a, double& b, double& c, double& d) {
   asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(a), "=d"(b), "=d"(c), "=d"(d) : "l"(p));
 }
+// the same two loads without .nc, for a kernel that writes (other words of) the lines it reads: append_block_dmma_kernel
+__device__ __forceinline__ void ld256_rw(const double* p, double& a, double& b, double& c, double& d) {
+  asm volatile("ld.global.L1::no_allocate.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(a), "=d"(b), "=d"(c), "=d"(d) : "l"(p) : "memory");
+}
+__device__ __forceinline__ void ld256_rw_l1(const double* p, double& a, double& b, double& c, double& d) {
+  asm volatile("ld.global.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(a), "=d"(b), "=d"(c), "=d"(d) : "l"(p) : "memory");
+}
 
 // ---------------------------------------------------------------------------
 // k <= 8: one warp per candidate
@@ -1127,12 +1134,12 @@ __global__ void __launch_bounds__(ABD_WARPS * 32) append_block_dmma_kernel(const
     for (int j = 0; j < 2; ++j) c0[i][j][0] = c0[i][j][1] = c1[i][j][0] = c1[i][j][1] = 0.0;
   for (int k0 = 0; k0 < ncols16; k0 += 16) {
     double va0[4], va1[4], vb0[4], vb1[4];
-    ld256(pa0 + k0, va0[0], va0[1], va0[2], va0[3]);
-    ld256(pa1 + k0, va1[0], va1[1], va1[2], va1[3]);
+    ld256_rw(pa0 + k0, va0[0], va0[1], va0[2], va0[3]);
+    ld256_rw(pa1 + k0, va1[0], va1[1], va1[2], va1[3]);
     vb0[0] = vb0[1] = vb0[2] = vb0[3] = 0.0;
     vb1[0] = vb1[1] = vb1[2] = vb1[3] = 0.0;
-    if (b0_on) ld256_l1(pb0 + k0, vb0[0], vb0[1], vb0[2], vb0[3]);
-    if (b1_on) ld256_l1(pb1 + k0, vb1[0], vb1[1], vb1[2], vb1[3]);
+    if (b0_on) ld256_rw_l1(pb0 + k0, vb0[0], vb0[1], vb0[2], vb0[3]);
+    if (b1_on) ld256_rw_l1(pb1 + k0, vb1[0], vb1[1], vb1[2], vb1[3]);
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
       dmma884(c0[0][0][q & 1], c1[0][0][q & 1], va0[q], vb0[q]);
